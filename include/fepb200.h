@@ -1,0 +1,219 @@
+/*
+ * fepb200.h -- C-ABI of libfepb200.so, the sm_100a (B200) implementation of the
+ * GROMACS free-energy-perturbation (FEP) perturbed-pair non-bonded kernel.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference
+ * (GROMACS 2023.3 + FEP-GPU fork, paths relative to the reference root):
+ *
+ *   gmx_nb_free_energy_kernel()            src/gromacs/gmxlib/nonbonded/nb_free_energy.h:53-72
+ *   dispatchFreeEnergyKernel() + foreign-lambda loop
+ *                                          src/gromacs/nbnxm/freeenergydispatch.cpp:147-308
+ *   (fork GPU twins that this replaces)    src/gromacs/nbnxm/gpu_data_mgmt.h:74-108
+ *                                          src/gromacs/nbnxm/cuda/nbnxm_cuda.cu:755-851
+ *
+ * Plain C: POD structs, raw pointers and sizes only.  No exceptions cross this
+ * boundary; every entry point returns FEPB200_OK (0) or a negative error code and
+ * the message is available from fepb200_last_error().  There is NO CPU fallback:
+ * if no sm_100-class CUDA device is usable fepb200_create() fails.
+ *
+ * Threading: one host thread per context.  Each context owns one CUDA device,
+ * one stream and all device memory for its shard of the pair list.
+ *
+ * Index space: atom indices are the caller's local topology indices (the same
+ * indices t_nblist::iinr / jjnr use on the CPU path, nb_free_energy.cpp:476,546).
+ */
+#ifndef FEPB200_H
+#define FEPB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------- */
+#define FEPB200_OK 0
+#define FEPB200_ERR_INVALID_ARGUMENT (-1)
+#define FEPB200_ERR_CUDA (-2)
+#define FEPB200_ERR_NO_DEVICE (-3)
+#define FEPB200_ERR_UNSUPPORTED (-4)
+#define FEPB200_ERR_STATE (-5)
+
+/* ---- kernel flags: identical bit values to the reference ---------------
+ * src/gromacs/gmxlib/nonbonded/nonbonded.h:38-42 */
+#define FEPB200_DO_FORCE (1 << 1)
+#define FEPB200_DO_SHIFTFORCE (1 << 2)
+#define FEPB200_DO_FOREIGNLAMBDA (1 << 3)
+#define FEPB200_DO_POTENTIAL (1 << 4)
+#define FEPB200_DO_SR (1 << 5)
+/* extension bit (not in the reference): overwrite instead of accumulate into the
+ * host output arrays of fepb200_compute() */
+#define FEPB200_CLEAR_OUTPUTS (1 << 16)
+
+/* ---- enum values: identical integers to the reference enums ------------
+ * api/legacy/include/gromacs/mdtypes/md_enums.h:238-274,324-334,640-646 */
+#define FEPB200_EEL_CUT 0
+#define FEPB200_EEL_RF 1
+#define FEPB200_EEL_PME 3
+#define FEPB200_EEL_EWALD 4
+#define FEPB200_EEL_RFZERO 16
+#define FEPB200_VDW_CUT 0
+#define FEPB200_VDW_PME 5
+#define FEPB200_MOD_POTSHIFT 1
+#define FEPB200_MOD_NONE 2
+#define FEPB200_MOD_POTSWITCH 3
+#define FEPB200_MOD_FORCESWITCH 5
+#define FEPB200_SC_BEUTLER 0
+#define FEPB200_SC_GAPSYS 1
+
+#define FEPB200_NUM_SHIFT_VECTORS 45 /* pbcutil/ishift.h:41-54 */
+#define FEPB200_NUM_LAMBDA_COMPONENTS 7 /* md_enums.h:497-508 */
+#define FEPB200_LAMBDA_COUL 2
+#define FEPB200_LAMBDA_VDW 3
+
+/* Mirrors, field for field, what nb_free_energy.cpp:323-396 reads from
+ * interaction_const_t (mdtypes/interaction_const.h:111-184) and its
+ * SoftCoreParameters (:116-138).  `real` is float (mixed-precision build). */
+typedef struct fepb200_params
+{
+    int   eeltype;      /* CoulombInteractionType as int                       */
+    int   vdwtype;      /* VanDerWaalsType as int                              */
+    int   vdw_modifier; /* InteractionModifiers as int                         */
+    float epsfac;
+    float rcoulomb;
+    float rvdw;
+    float rvdw_switch;
+    float reactionFieldCoefficient; /* k_rf */
+    float reactionFieldShift;       /* c_rf */
+    float sh_ewald;
+    float sh_lj_ewald;
+    float ewaldcoeff_q;
+    float ewaldcoeff_lj;
+    float dispersion_shift_cpot;
+    float repulsion_shift_cpot;
+    /* SoftCoreParameters */
+    int   softcoreType; /* SoftcoreType as int */
+    float alphaVdw;
+    float alphaCoulomb;
+    int   lambdaPower;
+    float sigma6WithInvalidSigma;
+    float sigma6Minimum;
+    float gapsysScaleLinpointVdW;
+    float gapsysScaleLinpointCoul;
+    float gapsysSigma6VdW;
+} fepb200_params;
+
+typedef struct fepb200_ctx fepb200_ctx;
+
+/* Sizes of the result block a context produces, see fepb200_result_layout(). */
+typedef struct fepb200_layout
+{
+    int       natoms;      /* atoms in the caller's index space                 */
+    int       ntouched;    /* distinct atoms that appear in the FULL list       */
+    int       nri;         /* i-entries held by this context (its shard)        */
+    long long nrj;         /* pairs held by this context (its shard)            */
+    int       nri_total;   /* i-entries of the full list                        */
+    long long nrj_total;   /* pairs of the full list                            */
+    int       nenergrp;    /* energy-group pairs G                              */
+    int       nforeign;    /* L (foreign lambda points, without the current one) */
+    /* Device result block (fp32 words unless noted), identical on every rank so it
+     * can be handed to ncclAllReduce / ncclReduceScatter as is:
+     *   [0, 3*ntouched)          compact forces, atom k of fepb200_touched_atoms()
+     *   then 3*45                shift forces
+     * followed by an fp64 block (see offsets, in units of doubles from its start):
+     *   Vc[G] Vv[G] dvdl[2] foreign_E[L+1] foreign_dvdl[(L+1)][2]               */
+    long long f32_words;
+    long long f64_words;
+    long long off_fshift; /* in f32 words */
+    long long off_vc, off_vv, off_dvdl, off_foreign_e, off_foreign_dvdl; /* in f64 words */
+} fepb200_layout;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* Replaces Nbnxm::gpu_init(..., bFEP, n_lambda) (nbnxm_setup.cpp:463). */
+int fepb200_create(fepb200_ctx** ctx, int device_ordinal);
+int fepb200_destroy(fepb200_ctx* ctx);
+/* Message of the last failing call on this context ("" if none).  ctx may be
+ * NULL to read the message of a failed fepb200_create(). */
+const char* fepb200_last_error(const fepb200_ctx* ctx);
+/* Library/device description, e.g. "fepb200 0.1 sm_100a NVIDIA B200 148 SMs". */
+const char* fepb200_describe(const fepb200_ctx* ctx);
+
+/* ---- constants (init time) --------------------------------------------- */
+/* Replaces cuda_copy_fepparams() (nbnxm/gpu_data_mgmt.h:74-85) and the reads at
+ * nb_free_energy.cpp:323-396. */
+int fepb200_set_params(fepb200_ctx* ctx, const fepb200_params* params);
+/* nbfp = {6*C6, 12*C12} interleaved, real[2*ntype*ntype] (mdlib/forcerec.cpp:115-152);
+ * nbfp_grid likewise (only [2k] used; forcerec.cpp:154-190), may be NULL unless LJ-PME. */
+int fepb200_set_nbfp(fepb200_ctx* ctx, int ntype, const float* nbfp, const float* nbfp_grid);
+
+/* ---- search-step inputs ------------------------------------------------ */
+/* chargeA/B, typeA/B of nb_free_energy.h:61-64 (replaces setAtomPropertiesAB,
+ * atomdata.cpp:1055-1072).  Must precede fepb200_set_list(). */
+int fepb200_set_atoms(fepb200_ctx* ctx, int natoms, const float* chargeA, const float* chargeB,
+                      const int* typeA, const int* typeB);
+/* The FEP t_nblist (mdtypes/nblist.h:41-55), replaces gpu_init_feppairlist()
+ * (nbnxm_gpu_data_mgmt.cpp:761-871).  excl_fep may be NULL (= all included,
+ * nb_free_energy.cpp:545).  nenergrp_pairs = G, every gid must be < G.
+ * rank/nranks: the context keeps the rank-th of nranks contiguous i-entry ranges,
+ * balanced by pair count with the rule of balance_fep_lists() (pairlist.cpp:2786-2838);
+ * use rank=0,nranks=1 for a single GPU. */
+int fepb200_set_list(fepb200_ctx* ctx, int nri, const int* iinr, const int* gid, const int* shift,
+                     const int* jindex, const int* jjnr, const int* excl_fep, int nenergrp_pairs,
+                     int rank, int nranks);
+/* Round trip of the shard this context holds, bit-exact (tests).
+ * Call with NULL arrays to query sizes through fepb200_result_layout(). */
+int fepb200_get_list(const fepb200_ctx* ctx, int* first_entry, int* iinr, int* gid, int* shift,
+                     int* jindex, int* jjnr, int* excl_fep);
+/* Global indices of the touched atoms, int[ntouched], ascending. */
+int fepb200_touched_atoms(const fepb200_ctx* ctx, int* atoms);
+int fepb200_result_layout(const fepb200_ctx* ctx, fepb200_layout* layout);
+
+/* ---- per-step inputs --------------------------------------------------- */
+/* lambda[7] as passed to gmx_nb_free_energy_kernel (only [COUL],[VDW] are read,
+ * nb_free_energy.cpp:319-320).  n_foreign = L with all_lambda_coul/vdw[L] =
+ * fepvals->all_lambda[Coul|Vdw][0..L) (freeenergydispatch.cpp:247-253); L may be 0. */
+int fepb200_set_lambdas(fepb200_ctx* ctx, const float* lambda, int n_foreign,
+                        const float* all_lambda_coul, const float* all_lambda_vdw);
+
+/* ---- the hot call ------------------------------------------------------ */
+/* One force/energy evaluation of the perturbed pairs this context holds, i.e. what
+ * dispatchFreeEnergyKernel() does per step (freeenergydispatch.cpp:147-308):
+ *   - the pass at the current lambda honouring DO_FORCE / DO_SHIFTFORCE / DO_POTENTIAL;
+ *   - if DO_FOREIGNLAMBDA is set and L+1 > 0: the energy-only passes i = 0..L
+ *     (i = 0 repeats the current lambda) returning
+ *     foreign_energy[i] = sum_g Vc[g]+Vv[g] and foreign_dvdl[i][{coul,vdw}].
+ * Host buffers; x is rvec[natoms] (AoS xyz), shiftvec rvec[45].  Outputs are
+ * ACCUMULATED (+=) exactly like the reference kernel does into its thread buffers
+ * (nb_free_energy.cpp:1155-1178) unless FEPB200_CLEAR_OUTPUTS is set.  Any output
+ * pointer may be NULL when the corresponding flag is not set.
+ * Copies host->device (touched coordinates only) and device->host inside the call. */
+int fepb200_compute(fepb200_ctx* ctx, const float* x, const float* shiftvec, int flags, float* f,
+                    float* fshift, double* Vc, double* Vv, double* dvdl /*[2]: coul, vdw*/,
+                    double* foreign_energy /*[L+1]*/, double* foreign_dvdl /*[L+1][2]*/);
+
+/* ---- device-resident variants (replace gpu_launch_kernel / gpu_launch_cpyback /
+ * gpu_wait_finish_task, nbnxm_cuda.cu:642, nbnxm_gpu_data_mgmt.cpp:1117, gpu_common.h:405) */
+/* Stage coordinates: host rvec[natoms] -> device (touched atoms only). */
+int fepb200_upload_x(fepb200_ctx* ctx, const float* x, const float* shiftvec);
+/* Or gather them on the device from a device-resident rvec[natoms] array. */
+int fepb200_gather_x_device(fepb200_ctx* ctx, const float* d_x, const float* shiftvec);
+/* Launch all kernels of one step on `stream` (a cudaStream_t; NULL = the context's
+ * stream).  Results stay in the device result block.  Asynchronous. */
+int fepb200_launch(fepb200_ctx* ctx, int flags, void* stream);
+/* Block until the context's stream is idle. */
+int fepb200_wait(fepb200_ctx* ctx);
+/* Device pointers of the result block: f32 part and f64 part (see fepb200_layout). */
+int fepb200_result_device_ptrs(const fepb200_ctx* ctx, void** d_f32, void** d_f64);
+/* Copy the result block to the host and add it into the caller's arrays (same
+ * semantics as the tail of fepb200_compute).  Synchronous. */
+int fepb200_download(fepb200_ctx* ctx, int flags, float* f, float* fshift, double* Vc, double* Vv,
+                     double* dvdl, double* foreign_energy, double* foreign_dvdl);
+
+/* Number of kernel launches issued by this context since creation (bench evidence),
+ * and device time in ms of the last fepb200_launch() measured with CUDA events on
+ * the launching stream (valid after fepb200_wait()). */
+long long fepb200_launch_count(const fepb200_ctx* ctx);
+int       fepb200_last_launch_ms(fepb200_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEPB200_H */
