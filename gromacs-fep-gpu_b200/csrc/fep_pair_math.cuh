@@ -1,0 +1,403 @@
+/*
+ * fep_pair_math.cuh -- per-pair mathematics of the perturbed-pair kernel in fp32 for sm_100a.
+ *
+ * What is computed is specified by the reference CPU kernel
+ *   src/gromacs/gmxlib/nonbonded/nb_free_energy.cpp:539-1136 (pair parameters, soft-core radii,
+ *   Coulomb / Lennard-Jones per state, assembly over states A/B, excluded-pair reaction field,
+ *   Ewald and LJ-PME real-space corrections) and nb_softcore.h:45-279 (Gapsys);
+ * how it is computed is ours: pair-per-thread SIMT code, MUFU lg2/ex2/rcp/rsq for the sixth
+ * roots, erff + a Taylor branch for the Ewald correction instead of the reference's rational
+ * fits, everything lambda-independent hoisted out of the foreign-lambda loop.
+ */
+#ifndef FEPB200_FEP_PAIR_MATH_CUH
+#define FEPB200_FEP_PAIR_MATH_CUH
+
+#include "fep_types.h"
+
+#define FEP_MIN_RSQ 1.0e-12f  /* nb_free_energy.cpp:99  */
+#define FEP_MAX_RINV6 1.0e15f /* nb_free_energy.cpp:107 */
+
+__device__ __forceinline__ float fep_rcp(float x)
+{
+    return __fdividef(1.0f, x);
+}
+
+/* x^(-1/6) for x > 0 (normal range): two MUFU ops */
+__device__ __forceinline__ float fep_inv_sixth_root(float x)
+{
+    return exp2f(__log2f(x) * (-1.0f / 6.0f));
+}
+
+/* x^(1/6) */
+__device__ __forceinline__ float fep_sixth_root(float x)
+{
+    return exp2f(__log2f(x) * (1.0f / 6.0f));
+}
+
+/* Ewald real-space correction (reference :109-119, 1056-1101).
+ *   v_lr = beta * erf(z)/z = erf(beta r) / r
+ *   f_lr / r^2-scaled, i.e. the factor that multiplies the distance vector:
+ *          -beta^3 * ( 2 exp(-z^2)/(sqrt(pi) z^2) - erf(z)/z^3 )
+ * For z^2 < 1 the bracket is summed from its Taylor series, which has no cancellation:
+ *   2/sqrt(pi) * sum_{n>=1} (-1)^n z^(2n-2)/n! * 2n/(2n+1)                                   */
+template<bool FORCE>
+__device__ __forceinline__ void fep_ewald_correction(float r2, float r, float rinv, float beta, float beta2,
+                                                     float beta3, float* v_lr, float* f_lr)
+{
+    const float z  = beta * r;
+    const float ez = erff(z);
+    *v_lr          = ez * rinv;
+    if (FORCE)
+    {
+        const float z2 = beta2 * r2;
+        float       bracket;
+        if (z2 < 1.0f)
+        {
+            /* coefficients (-1)^n 2n/((2n+1) n!) for n = 12..1, Horner in z2 */
+            float p = 2.004168671e-09f;
+            p       = fmaf(p, z2, -2.396288628e-08f);
+            p       = fmaf(p, z2, 2.624506593e-07f);
+            p       = fmaf(p, z2, -2.610693400e-06f);
+            p       = fmaf(p, z2, 2.334267040e-05f);
+            p       = fmaf(p, z2, -1.851851852e-04f);
+            p       = fmaf(p, z2, 1.282051282e-03f);
+            p       = fmaf(p, z2, -7.575757576e-03f);
+            p       = fmaf(p, z2, 3.703703704e-02f);
+            p       = fmaf(p, z2, -1.428571429e-01f);
+            p       = fmaf(p, z2, 4.000000000e-01f);
+            p       = fmaf(p, z2, -6.666666667e-01f);
+            bracket = 1.1283791671f * p;
+        }
+        else
+        {
+            const float iz2 = fep_rcp(z2);
+            bracket         = 1.1283791671f * __expf(-z2) * iz2 - ez * iz2 * fep_rcp(z);
+        }
+        *f_lr = -beta3 * bracket;
+    }
+}
+
+/* LJ-PME grid correction (reference :121-163, 1103-1136).  term = r^-6 (1 - exp(-x)(1+x+x^2/2)),
+ * x = beta_lj^2 r^2; for x < 1 the series sum_{n>=3} (-1)^(n+1) (n-1)(n-2)/(2 n!) x^n is used
+ * (times beta_lj^6 / x^3 instead of r^-6), which is accurate where the closed form cancels. */
+template<bool FORCE>
+__device__ __forceinline__ void fep_ljpme_correction(float r2, float rinv, float csq, float c6div6, bool self,
+                                                     float* pot, float* force)
+{
+    const float rinv2 = rinv * rinv;
+    const float x     = csq * r2;
+    const float e     = __expf(-x);
+    float       term;
+    if (x < 1.0f)
+    {
+        /* r^-6 = beta_lj^6 / x^3, so term = beta_lj^6 * sum_{n>=3} a_n x^(n-3) with
+         * a_n = (-1)^(n+1) (n-1)(n-2)/(2 n!); below p = 6 * that sum (p(0) = 1), n = 14..3 */
+        float p = -5.368308940e-09f;
+        p       = fmaf(p, x, 6.359381359e-08f);
+        p       = fmaf(p, x, -6.889329806e-07f);
+        p       = fmaf(p, x, 6.764069264e-06f);
+        p       = fmaf(p, x, -5.952380952e-05f);
+        p       = fmaf(p, x, 4.629629630e-04f);
+        p       = fmaf(p, x, -3.125000000e-03f);
+        p       = fmaf(p, x, 1.785714286e-02f);
+        p       = fmaf(p, x, -8.333333333e-02f);
+        p       = fmaf(p, x, 3.000000000e-01f);
+        p       = fmaf(p, x, -7.500000000e-01f);
+        p       = fmaf(p, x, 1.000000000e+00f);
+        term    = c6div6 * p;
+    }
+    else
+    {
+        const float rinv6 = rinv2 * rinv2 * rinv2;
+        term              = rinv6 * (1.0f - e * (1.0f + x + 0.5f * x * x));
+    }
+    if (FORCE)
+    {
+        *force = (term - e * c6div6) * rinv2;
+    }
+    *pot = self ? 0.5f * c6div6 : term;
+}
+
+/* lambda-independent description of one pair */
+struct FepPair
+{
+    float r2;    /* clamped at FEP_MIN_RSQ */
+    float r, rinv;
+    float r6;    /* Beutler only */
+    float qq[2], c6[2], c12[2], sig6[2], c6g[2];
+    float a_c, a_v;      /* effective Beutler alphas or Gapsys scales for this pair */
+    float gbase[2];      /* Gapsys: (26/7 sigma6)^(1/6) per state */
+    bool  nonzero[2];
+    bool  included_within; /* included pair inside the cut-off sphere */
+};
+
+/* Included & within-cut-off part for one lambda point: adds to vc/vv totals, fscal and dvdl.
+ * Mirrors reference :747-1020. */
+template<int SC, bool EWALD, bool FORCE>
+__device__ __forceinline__ void fep_included_terms(const KernelArgs& ka, const LambdaPoint& lp, const FepPair& pr,
+                                                   float& vctot, float& vvtot, float& fscal, float& dvdl_c,
+                                                   float& dvdl_v)
+{
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+    {
+        if (!pr.nonzero[s])
+        {
+            continue;
+        }
+        const float dlfac = s == 0 ? -1.0f : 1.0f;
+        float       vc = 0.0f, vv = 0.0f, fc = 0.0f, fv = 0.0f;
+        float       rpinv_c = 1.0f, rinv_c = pr.rinv, rpinv_v = 1.0f, rinv_v = pr.rinv;
+        float       d_c = 0.0f, d_v = 0.0f;
+        if (SC == FEP_SC_BEUTLER)
+        {
+            d_c     = fmaf(pr.a_c * lp.sclfac_c[s], pr.sig6[s], pr.r6);
+            rpinv_c = fep_rcp(d_c);
+            rinv_c  = fep_inv_sixth_root(d_c);
+            if (lp.differ)
+            {
+                d_v     = fmaf(pr.a_v * lp.sclfac_v[s], pr.sig6[s], pr.r6);
+                rpinv_v = fep_rcp(d_v);
+                rinv_v  = fep_inv_sixth_root(d_v);
+            }
+            else
+            {
+                d_v     = d_c;
+                rpinv_v = rpinv_c;
+                rinv_v  = rinv_c;
+            }
+        }
+        /* ---- Coulomb (:804-874) ---- */
+        bool elec;
+        if (EWALD)
+        {
+            elec = pr.r < ka.rcoulomb;
+        }
+        else
+        {
+            /* rC < rc  <=>  rC^6 < rc^6 for the soft-cored radius */
+            elec = (SC == FEP_SC_BEUTLER) ? (d_c < ka.rcoulomb6) : (pr.r < ka.rcoulomb);
+        }
+        elec = elec && pr.qq[s] != 0.0f;
+        if (elec)
+        {
+            float r_c = pr.r;
+            if (EWALD)
+            {
+                vc = pr.qq[s] * (rinv_c - ka.sh_ewald);
+                fc = pr.qq[s] * rinv_c;
+            }
+            else
+            {
+                if (SC == FEP_SC_BEUTLER)
+                {
+                    r_c = fep_rcp(rinv_c);
+                }
+                const float krf_r2 = ka.krf * r_c * r_c;
+                vc                 = pr.qq[s] * (rinv_c + krf_r2 - ka.crf);
+                fc                 = pr.qq[s] * (rinv_c - 2.0f * krf_r2);
+            }
+            if (SC == FEP_SC_GAPSYS)
+            {
+                /* nb_softcore.h:73-195 */
+                const float lfac = lp.lfac_c[s];
+                if (lfac < 1.0f && pr.a_c > 0.0f && ka.epsfac != 0.0f)
+                {
+                    float      rq         = lp.g6_c[s] * (1.0f + fabsf(pr.qq[s] / ka.epsfac)) * pr.a_c;
+                    const bool within_cut = rq <= ka.rcoulomb;
+                    rq                    = fminf(rq, ka.rcoulomb);
+                    if (pr.r < rq)
+                    {
+                        const float rinvq = fep_rcp(rq);
+                        const float cst   = pr.qq[s] * rinvq;
+                        const float lin   = cst * pr.r * rinvq;
+                        const float quad  = lin * pr.r * rinvq;
+                        fc                = -2.0f * quad + 3.0f * lin;
+                        vc                = quad - 3.0f * (lin - cst);
+                        if (EWALD)
+                        {
+                            vc -= pr.qq[s] * ka.sh_ewald;
+                        }
+                        else
+                        {
+                            const float krf_r2 = ka.krf * pr.r * pr.r;
+                            fc -= pr.qq[s] * 2.0f * krf_r2;
+                            vc += pr.qq[s] * (krf_r2 - ka.crf);
+                        }
+                        if (within_cut)
+                        {
+                            dvdl_c += dlfac * 0.5f * lp.gdl_c[s] * (quad - 2.0f * lin + cst);
+                        }
+                    }
+                }
+            }
+        }
+        /* ---- Van der Waals (:880-971) ---- */
+        bool vdw;
+        if (SC == FEP_SC_BEUTLER)
+        {
+            vdw = ka.vdw_ewald ? (pr.r < ka.rvdw) : (d_v < ka.rvdw6);
+        }
+        else
+        {
+            vdw = pr.r < ka.rvdw;
+        }
+        vdw = vdw && (pr.c6[s] != 0.0f || pr.c12[s] != 0.0f);
+        if (vdw)
+        {
+            float rinv6;
+            if (SC == FEP_SC_BEUTLER)
+            {
+                rinv6 = rpinv_v;
+            }
+            else
+            {
+                const float ri2 = rinv_v * rinv_v;
+                rinv6           = ri2 * ri2 * ri2;
+            }
+            rinv6           = fminf(rinv6, FEP_MAX_RINV6);
+            const float v6  = pr.c6[s] * rinv6;
+            const float v12 = pr.c12[s] * rinv6 * rinv6;
+            vv = (v12 + pr.c12[s] * ka.rep_cpot) * (1.0f / 12.0f) - (v6 + pr.c6[s] * ka.disp_cpot) * (1.0f / 6.0f);
+            fv = v12 - v6;
+            if (SC == FEP_SC_GAPSYS)
+            {
+                /* nb_softcore.h:199-279 */
+                const float lfac = lp.lfac_v[s];
+                if (lfac < 1.0f && pr.a_v > 0.0f)
+                {
+                    const float rq = pr.gbase[s] * lp.g6_v[s] * pr.a_v;
+                    if (pr.r < rq)
+                    {
+                        const float c6s = pr.c6[s] * (1.0f / 6.0f), c12s = pr.c12[s] * (1.0f / 12.0f);
+                        const float ri  = fep_rcp(rq);
+                        const float ri3 = ri * ri * ri;
+                        const float ri6 = ri3 * ri3;
+                        const float ri7 = ri6 * ri;
+                        const float ri8 = ri7 * ri;
+                        const float t14 = c12s * ri7 * ri7 * pr.r2;
+                        const float t13 = c12s * ri7 * ri6 * pr.r;
+                        const float t12 = c12s * ri6 * ri6;
+                        const float t8  = ri8 * c6s * pr.r2;
+                        const float t7  = ri7 * c6s * pr.r;
+                        const float t6  = ri6 * c6s;
+                        const float quad = 156.0f * t14 - 42.0f * t8;
+                        const float lin  = 168.0f * t13 - 48.0f * t7;
+                        const float cst  = 91.0f * t12 - 28.0f * t6;
+                        fv               = -quad + lin;
+                        vv = 0.5f * quad - lin + cst + (c12s * ka.rep_cpot - c6s * ka.disp_cpot);
+                        dvdl_v += dlfac * 28.0f * lp.gdl_v[s]
+                                  * ((6.5f * t14 - t8) - (13.0f * t13 - 2.0f * t7) + (6.5f * t12 - t6));
+                    }
+                }
+            }
+            if (ka.vdw_ewald)
+            {
+                vv += pr.c6g[s] * ka.sh_lj_ewald * (1.0f / 6.0f);
+            }
+            if (ka.pot_switch)
+            {
+                const float r_v  = (SC == FEP_SC_BEUTLER) ? fep_rcp(rinv_v) : pr.r;
+                const float d    = fmaxf(r_v - ka.rvdw_switch, 0.0f);
+                const float d2   = d * d;
+                const float sw   = 1.0f + d2 * d * (ka.sw_v3 + d * (ka.sw_v4 + d * ka.sw_v5));
+                if (FORCE)
+                {
+                    const float dsw = d2 * (ka.sw_f2 + d * (ka.sw_f3 + d * ka.sw_f4));
+                    fv              = fv * sw - r_v * vv * dsw;
+                }
+                vv *= sw;
+            }
+        }
+        /* ---- assemble (:980-1020) ---- */
+        vctot = fmaf(lp.lfac_c[s], vc, vctot);
+        vvtot = fmaf(lp.lfac_v[s], vv, vvtot);
+        dvdl_c = fmaf(vc, dlfac, dvdl_c);
+        dvdl_v = fmaf(vv, dlfac, dvdl_v);
+        if (FORCE)
+        {
+            fc *= rpinv_c;
+            fv *= rpinv_v;
+            /* multiplied by r^(p-2) by the caller */
+            fscal += lp.lfac_c[s] * fc + lp.lfac_v[s] * fv;
+            if (SC == FEP_SC_BEUTLER)
+            {
+                /* the reference adds these only when forces are computed (:1005-1013 use the
+                 * force terms, which stay zero in energy-only passes) */
+                dvdl_c += lp.lfac_c[s] * pr.a_c * lp.scdl_c[s] * fc * pr.sig6[s];
+                dvdl_v += lp.lfac_v[s] * pr.a_v * lp.scdl_v[s] * fv * pr.sig6[s];
+            }
+        }
+    }
+}
+
+/* Loads one pair and derives its lambda-independent data.  Returns false when the pair
+ * contributes nothing (included and beyond the cut-off sphere, reference :667). */
+template<int SC>
+__device__ __forceinline__ bool fep_load_pair(const KernelArgs& ka, int slot, FepPair& pr, float& dx, float& dy,
+                                              float& dz, bool& excluded, bool& self, int& entry)
+{
+    const int pj  = __ldg(ka.pair_j + slot);
+    entry         = __ldg(ka.pair_e + slot);
+    excluded      = pj < 0;
+    const int  cj = pj & 0x7fffffff;
+    const int4 en = __ldg(ka.ent4 + entry);
+    const int  ci = en.x;
+    self          = (ci == cj);
+
+    const float4 xi = __ldg(ka.pos4 + ci);
+    const float4 sh = ka.dyn->shiftvec[en.y];
+    const float4 xj = __ldg(ka.pos4 + cj);
+    /* the reference shifts the i atom first (:478-480) */
+    dx = (sh.x + xi.x) - xj.x;
+    dy = (sh.y + xi.y) - xj.y;
+    dz = (sh.z + xi.z) - xj.z;
+    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const bool within = r2 < ka.rcut_max2;
+    if (!(within || excluded))
+    {
+        return false;
+    }
+    const float4 pi = __ldg(ka.par4 + ci);
+    const float4 pq = __ldg(ka.par4 + cj);
+    pr.qq[0]        = (ka.epsfac * pi.x) * pq.x;
+    pr.qq[1]        = (ka.epsfac * pi.y) * pq.y;
+    const int tA    = ka.ntype * __float_as_int(pi.z) + __float_as_int(pq.z);
+    const int tB    = ka.ntype * __float_as_int(pi.w) + __float_as_int(pq.w);
+    const float4 a  = __ldg(ka.typetab + tA);
+    const float4 b  = __ldg(ka.typetab + tB);
+    pr.c6[0] = a.x, pr.c12[0] = a.y, pr.sig6[0] = a.z, pr.c6g[0] = a.w;
+    pr.c6[1] = b.x, pr.c12[1] = b.y, pr.sig6[1] = b.z, pr.c6g[1] = b.w;
+    /* soft-core only if one end state has no repulsion (:597-628) */
+    const bool hard = (a.y > 0.0f && b.y > 0.0f);
+    if (SC == FEP_SC_BEUTLER)
+    {
+        pr.a_c = hard ? 0.0f : ka.alpha_c;
+        pr.a_v = hard ? 0.0f : ka.alpha_v;
+    }
+    else if (SC == FEP_SC_GAPSYS)
+    {
+        pr.a_c      = hard ? 0.0f : ka.gscale_c;
+        pr.a_v      = hard ? 0.0f : ka.gscale_v;
+        pr.gbase[0] = fep_sixth_root((26.0f / 7.0f) * a.z);
+        pr.gbase[1] = fep_sixth_root((26.0f / 7.0f) * b.z);
+    }
+    else
+    {
+        pr.a_c = pr.a_v = 0.0f;
+    }
+    r2      = fmaxf(r2, FEP_MIN_RSQ);
+    pr.r2   = r2;
+    pr.rinv = rsqrtf(r2);
+    pr.r    = r2 * pr.rinv;
+    if (SC == FEP_SC_BEUTLER)
+    {
+        pr.r6 = r2 * r2 * r2;
+    }
+    pr.nonzero[0]      = (pr.qq[0] != 0.0f || a.x != 0.0f || a.y != 0.0f);
+    pr.nonzero[1]      = (pr.qq[1] != 0.0f || b.x != 0.0f || b.y != 0.0f);
+    pr.included_within = within && !excluded;
+    return true;
+}
+
+#endif
