@@ -431,6 +431,15 @@ def random_problem(seed: int, params: Params, *, natoms=96, nri=40, max_j=70, nt
         jjnr.extend(js.tolist())
         excl.extend(ex.tolist())
         jindex.append(len(jjnr))
+    # Excluded pairs far outside the pair-search range do not occur in the reference (its
+    # ExclusionChecker aborts, pairlist.cpp:4456-4467) and its rational Ewald-correction fits
+    # are only valid for beta*r <~ 4 (simd_math.h:1560-1610): keep exclusions within 1.2 r_c.
+    ii = np.repeat(np.asarray(iinr), np.diff(jindex))
+    jj = np.asarray(jjnr)
+    ss = np.repeat(np.asarray(shift), np.diff(jindex))
+    dist = np.linalg.norm(x32[ii].astype(np.float64) + sv[ss] - x32[jj], axis=1)
+    excl = np.asarray(excl, np.int32)
+    excl[(excl == 0) & (dist > 1.2 * params.rcoulomb)] = 1
     lam = np.full(NUM_LAMBDA_COMPONENTS, lambda_vdw, np.float32)
     lam[LAMBDA_COUL] = lambda_coul
     lam[LAMBDA_VDW] = lambda_vdw
