@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the FEP perturbed-pair path on synthetic solvated systems.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C5] [--impl ours|reference]
+
+A "step" is one force step with free-energy output of the reference
+(dispatchFreeEnergyKernel, src/gromacs/nbnxm/freeenergydispatch.cpp:147-308): the pass at the current
+lambda (forces, shift forces, Vc/Vvdw per energy-group pair, dV/dlambda) followed by the L+1
+energy-only foreign-lambda passes.  Metric (BASELINE.json): perturbed pair-interactions/s, one
+pair-interaction = one (i,j) list entry evaluated at one lambda point, so a step is
+P * (1 + (L+1)) pair-interactions -- the reference's own count of kernel work.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, device time (CUDA events, max over
+ranks), L2 flushed between steps.  `e2e`: the same step through the public call with HOST buffers
+(fepb200_compute: pinned staging, H2D of the touched coordinates, kernels, D2H of the result block,
+scatter-add into the caller's force array), wall clock.  `roofline`: the dominant kernel
+(fep_foreign_kernel) against the FP32 pipe.  `cpu_baseline` / --impl reference: the reference's
+own CPU SIMD kernel (oracle/_ref, compiled from the reference's sources) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "gromacs-fep-gpu_b200", "python"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "FEP perturbed pair-interactions/s"
+UNIT = "pair-interactions/s"
+FLOP_PER_PAIR, FLOP_PER_ENTRY = 150, 12  # the reference's own count, nb_free_energy.cpp:1181-1186
+L2_FLUSH_BYTES = 512 << 20
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=float(d.get("hbm_gbs", 6650.0)), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def _workload(problem):
+    nb = problem.nblist
+    passes = 1 + (problem.n_foreign + 1)
+    return dict(pairs=nb.nrj, entries=nb.nri, passes=passes, units_per_step=nb.nrj * passes)
+
+
+def _config(problem, name, world, extra=None):
+    nb = problem.nblist
+    cfg = dict(workload=f"{name}: {problem.natoms}-atom synthetic water box, {len(problem.perturbed)} perturbed atoms, "
+                        f"{nb.nrj} perturbed pairs in {nb.nri} i-entries, {problem.n_foreign} foreign lambda",
+               natoms=problem.natoms, pairs=nb.nrj, entries=nb.nri, n_foreign=problem.n_foreign,
+               energy_group_pairs=problem.nenergrp_pairs,
+               passes_per_step=1 + problem.n_foreign + 1,
+               flags="FORCE|SHIFTFORCE|POTENTIAL|FOREIGNLAMBDA",
+               parallelism=f"i-entry shards x{world}", l2="flushed between timed steps (512 MiB write)")
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's CPU kernel on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(problem, flags, steps, warmup, budget_s=25.0):
+    """Times oracle/_ref (the reference's nb_free_energy.cpp compiled in place, mixed precision,
+    widest SIMD this host has, OpenMP over all host cores) or, if it did not travel, the C port."""
+    from oracle import oracle
+
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    nb = problem.nblist
+    kind = "reference" if oracle.have_ref("sp") else "port"
+
+    def run(prob):
+        if kind == "reference":
+            return oracle.run_ref(prob, flags, precision="sp", nthreads=cores, use_simd=True, repeats=1)
+        return oracle.run_port(prob, flags, nthreads=cores, repeats=1)
+
+    # bounded sample: all i-entries if one step fits the budget, else a leading range of entries
+    import copy
+
+    sample, frac = problem, 1.0
+    t0 = time.perf_counter()
+    r = run(sample)
+    first = sum(r["seconds"])
+    wall_first = time.perf_counter() - t0
+    if wall_first * (steps + warmup) > budget_s and nb.nri > 64:
+        frac = max(budget_s / (wall_first * (steps + warmup)), 0.02)
+        e1 = max(64, int(nb.nri * frac))
+        sample = copy.copy(problem)
+        sample.nblist = nb.slice_entries(0, e1)
+        frac = sample.nblist.nrj / nb.nrj
+    passes = 1 + problem.n_foreign + 1
+    for _ in range(warmup):
+        run(sample)
+    times = []
+    for _ in range(steps):
+        r = run(sample)
+        times.append(sum(r["seconds"]))
+    t = sum(times) / len(times)
+    value = sample.nblist.nrj * passes / t
+    simd = r.get("simd", "scalar C")
+    return dict(value=value, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{sample.nblist.nrj} of {nb.nrj} pairs ({frac:.0%} of the i-entries' pairs) x {passes} passes "
+                       f"per step, {steps} steps, {simd} mixed precision, OpenMP {cores} threads; first call {first:.3f}s",
+                ms_per_step=t * 1e3)
+
+
+def run_reference_arm(args, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fepb200 import params as P
+    from fepb200.synth import make_system
+
+    problem = make_system(name)
+    flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
+    cpu = cpu_reference(problem, flags, args.steps, args.warmup, budget_s=120.0)
+    line = dict(impl="reference", metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=cpu.pop("ms_per_step"), higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="f32", data="synthetic", config=_config(problem, name, 1, dict(
+                    parallelism=f"OpenMP x{cpu['cores']} host threads", l2="n/a (CPU)")),
+                cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, name):
+    import torch
+    import torch.distributed as dist
+
+    from fepb200 import params as P
+    from fepb200.distributed import ShardedFep
+    from fepb200.synth import make_system
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    problem = make_system(name)
+    wl = _workload(problem)
+    flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
+    sh = ShardedFep(problem, local, rank, world)
+    ctx = sh.ctx
+    lay = ctx.layout()
+    x_host = torch.from_numpy(np.ascontiguousarray(problem.x)).pin_memory()
+    x_np = x_host.numpy()
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")
+
+    # ---- value: inputs resident, device time --------------------------------------------
+    ctx.upload_x(x_np, problem.shiftvec)
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        sh.launch(flags)
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ctx.launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        sh.launch(flags)
+        stops[i].record()
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - n0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    dev_ms = max_over_ranks(dev_ms)
+    ms_per_step = dev_ms / args.steps
+    value = wl["units_per_step"] / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-kernel CUDA events, same launches -----------
+    ctx.set_profiling(True)
+    kms = []
+    for i in range(args.steps):
+        flush.zero_()
+        sh.launch(flags)
+        torch.cuda.synchronize()
+        kms.append(ctx.kernel_ms())
+    ctx.set_profiling(False)
+    k_pass, k_foreign, k_epi = (sum(k[j] for k in kms) / len(kms) for j in range(3))
+    my_pairs, my_entries = int(lay.nrj), int(lay.nri)
+    points = problem.n_foreign + 1
+    peaks = _peaks()
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    fp32_peak = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    alg_flop = (FLOP_PER_PAIR * my_pairs + FLOP_PER_ENTRY * my_entries) * points
+    achieved = alg_flop / (k_foreign * 1e-3) / 1e12 if k_foreign > 0 else 0.0
+    # algorithmic bytes of the step (list stream + touched-atom data + result), for the HBM view
+    alg_bytes = my_pairs * 8 + my_entries * 16 + int(lay.ntouched) * (16 + 16 + 12)
+    roofline = dict(bound="fp32", kernel="fep_foreign_kernel", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
+                    frac=achieved / fp32_peak, traffic=None,
+                    peak_source=f"{sms} SMs x 128 lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
+                    algorithmic_flop_per_launch=alg_flop,
+                    kernel_ms=dict(pass_kernel=k_pass, foreign_kernel=k_foreign, epilogue_kernel=k_epi),
+                    pair_points_per_s=my_pairs * points / (k_foreign * 1e-3) if k_foreign > 0 else 0.0,
+                    hbm=dict(algorithmic_bytes_per_step=alg_bytes,
+                             achieved_gbs=alg_bytes / ((k_pass + k_foreign + k_epi) * 1e-3) / 1e9,
+                             peak_gbs=peaks["hbm_gbs"]))
+
+    # ---- e2e: host buffers through the public call ------------------------------------------
+    out = ctx.new_outputs()
+    for _ in range(3):
+        sh.step(x_np, problem.shiftvec, flags | P.CLEAR_OUTPUTS, out)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        sh.step(x_np, problem.shiftvec, flags | P.CLEAR_OUTPUTS, out)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # the L2 flush is not part of the step: measure and subtract its device time
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_s = max(e2e_s - f0.elapsed_time(f1) * 1e-3, 1e-9)
+    e2e_value = wl["units_per_step"] / (e2e_s / args.steps)
+    h2d = 816 + 16 * int(lay.ntouched)  # DynHead (45 shift vectors + current-lambda block) + float4 per touched atom
+    d2h = int(lay.f32_words) * 4 + int(lay.f64_words) * 8
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference(problem, flags, 3, 1)
+            cpu.pop("ms_per_step", None)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+                    data="synthetic", config=_config(problem, name, world),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=e2e_s / args.steps * 1e3),
+                    gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, cpu_baseline=cpu,
+                    wall_ms_per_step_incl_flush=t_wall / args.steps * 1e3, device=ctx.describe())
+        print(json.dumps(line), flush=True)
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # re-launch ourselves one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference":
+        run_reference_arm(args, args.config)
+    else:
+        run_ours(args, args.config)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,639 @@
+/*
+ * fep_kernels.cu -- the sm_100a kernels of the perturbed-pair path.
+ *
+ *   fep_pass_kernel     one thread per pair of the flat pair space; the pass at the current lambda
+ *                       (forces + energies + dV/dlambda).  Replaces one call of
+ *                       gmx_nb_free_energy_kernel() (nb_free_energy.cpp:1367) over all OpenMP
+ *                       threads' lists (freeenergydispatch.cpp:189-231).
+ *   fep_foreign_kernel  grid = (pair tiles) x (chunks of lambda points); evaluates the energy-only
+ *                       passes of freeenergydispatch.cpp:236-306 for ALL lambda points with one
+ *                       load of each pair per chunk.
+ *   fep_epilogue_kernel atomic-free, deterministic gather of the pair force vectors into per-atom
+ *                       forces, of the per-segment i forces into shift forces, of the per-segment
+ *                       energies into energy-group pairs, and of the per-CTA partial sums into
+ *                       dV/dlambda and foreign energies.  Replaces ThreadedForceBuffer::reduce
+ *                       (threaded_force_buffer.cpp:320-402) and the sums at
+ *                       freeenergydispatch.cpp:298-305.
+ *
+ * No tensor cores: the work is pairwise FP32 FMA + MUFU (rcp/rsq/lg2/ex2).  No global atomics in
+ * any data path; the only atomic is the completion ticket of the epilogue.
+ */
+#include "fep_pair_math.cuh"
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+    }
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+    }
+    return v;
+}
+
+/* Lambda-independent correction factors of one pair (reference :1023-1136):
+ *   xc / fc multiply qq[s]  (excluded-pair reaction field, Ewald real-space correction)
+ *   xv / fv multiply c6grid[s] (LJ-PME grid correction)                                   */
+template<bool EWALD, bool FORCE>
+__device__ __forceinline__ void fep_corrections(const KernelArgs& ka, const FepPair& pr, bool excluded, bool self,
+                                                float& xc, float& fc, float& xv, float& fv)
+{
+    xc = fc = xv = fv = 0.0f;
+    if (!EWALD)
+    {
+        if (ka.rf_type && excluded)
+        {
+            float vv = fmaf(ka.krf, pr.r2, -ka.crf);
+            if (self)
+            {
+                vv *= 0.5f;
+            }
+            xc = vv;
+            fc = -2.0f * ka.krf;
+        }
+    }
+    else if (excluded || pr.r < ka.rcoulomb)
+    {
+        float v_lr, f_lr = 0.0f;
+        fep_ewald_correction<FORCE>(pr.r2, pr.r, pr.rinv, ka.beta, ka.beta2, ka.beta3, &v_lr, &f_lr);
+        if (self)
+        {
+            v_lr *= 0.5f;
+        }
+        xc = -v_lr;
+        fc = -f_lr;
+    }
+    if (ka.vdw_ewald && (excluded || pr.r < ka.rvdw))
+    {
+        float pot, force = 0.0f;
+        fep_ljpme_correction<FORCE>(pr.r2, pr.rinv, ka.lj_coeff_sq, ka.lj_coeff6_div6, self, &pot, &force);
+        xv = pot * (1.0f / 6.0f);
+        fv = force;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* pass at the current lambda                                                                  */
+/* ------------------------------------------------------------------------------------------- */
+template<int SC, bool EWALD, bool FORCE>
+__global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant__ KernelArgs ka)
+{
+    __shared__ LambdaPoint s_lp;
+    __shared__ float       s_red[FEP_CTA / 32][2];
+
+    const int tid  = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    if (tid < (int)(sizeof(LambdaPoint) / 4))
+    {
+        reinterpret_cast<int*>(&s_lp)[tid] = reinterpret_cast<const int*>(&ka.dyn->cur)[tid];
+    }
+    __syncthreads();
+
+    const int  slot  = blockIdx.x * FEP_CTA + tid;
+    const bool valid = slot < ka.n_pairs;
+
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f, vc = 0.0f, vv = 0.0f, dc = 0.0f, dv = 0.0f;
+    int   entry = -1;
+
+    if (valid)
+    {
+        FepPair pr;
+        float   dx, dy, dz;
+        bool    excluded, self;
+        if (fep_load_pair<SC>(ka, slot, pr, dx, dy, dz, excluded, self, entry))
+        {
+            float fscal = 0.0f;
+            if (pr.included_within)
+            {
+                fep_included_terms<SC, EWALD, FORCE>(ka, s_lp, pr, vc, vv, fscal, dc, dv);
+                if (FORCE)
+                {
+                    /* r^(p-2): r^4 for the Beutler soft-core radius power 6, r^-2 otherwise (:722-741) */
+                    fscal *= (SC == FEP_SC_BEUTLER) ? pr.r2 * pr.r2 : pr.rinv * pr.rinv;
+                }
+            }
+            float xc, fc, xv, fv;
+            fep_corrections<EWALD, FORCE>(ka, pr, excluded, self, xc, fc, xv, fv);
+            const float cA = pr.qq[0] * xc, cB = pr.qq[1] * xc;
+            const float gA = pr.c6g[0] * xv, gB = pr.c6g[1] * xv;
+            vc += s_lp.lfac_c[0] * cA + s_lp.lfac_c[1] * cB;
+            vv += s_lp.lfac_v[0] * gA + s_lp.lfac_v[1] * gB;
+            dc += cB - cA;
+            dv += gB - gA;
+            if (FORCE)
+            {
+                fscal += (s_lp.lfac_c[0] * pr.qq[0] + s_lp.lfac_c[1] * pr.qq[1]) * fc;
+                fscal += (s_lp.lfac_v[0] * pr.c6g[0] + s_lp.lfac_v[1] * pr.c6g[1]) * fv;
+                fx = fscal * dx;
+                fy = fscal * dy;
+                fz = fscal * dz;
+            }
+        }
+        if (FORCE)
+        {
+            /* pair force vector: the j atom receives -t, gathered by the epilogue */
+            ka.t4[slot] = make_float4(fx, fy, fz, 0.0f);
+        }
+    }
+
+    /* dV/dlambda of this CTA (the reference accumulates one scalar per call, :1170-1178) */
+    {
+        const float wc = warp_sum(dc), wv = warp_sum(dv);
+        if (lane == 0)
+        {
+            s_red[warp][0] = wc;
+            s_red[warp][1] = wv;
+        }
+    }
+
+    /* segmented sum over the lanes of one i-entry: i force and Vc/Vv of the segment */
+    const int      e_prev   = __shfl_up_sync(FULL_MASK, entry, 1);
+    const bool     boundary = (lane == 0) || (entry != e_prev);
+    const unsigned bmask    = __ballot_sync(FULL_MASK, boundary);
+    const unsigned hmask    = __ballot_sync(FULL_MASK, boundary && valid);
+    const unsigned above    = bmask & ~((2u << lane) - 1u);
+    const int      seg_last = (above ? (__ffs(above) - 1) : 32) - 1; /* last lane of my segment */
+    const int      after    = seg_last - lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const float ox = __shfl_down_sync(FULL_MASK, fx, o);
+        const float oy = __shfl_down_sync(FULL_MASK, fy, o);
+        const float oz = __shfl_down_sync(FULL_MASK, fz, o);
+        const float oc = __shfl_down_sync(FULL_MASK, vc, o);
+        const float ov = __shfl_down_sync(FULL_MASK, vv, o);
+        if (o <= after)
+        {
+            fx += ox;
+            fy += oy;
+            fz += oz;
+            vc += oc;
+            vv += ov;
+        }
+    }
+    if (boundary && valid)
+    {
+        const int gw = blockIdx.x * (FEP_CTA / 32) + warp;
+        const int h  = __ldg(ka.warp_hbase + gw) + __popc(hmask & ((1u << lane) - 1u));
+        if (FORCE)
+        {
+            ka.fi4[h] = make_float4(fx, fy, fz, 0.0f);
+        }
+        ka.ev2[h] = make_float2(vc, vv);
+    }
+
+    __syncthreads();
+    if (tid < 2)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < FEP_CTA / 32; w++)
+        {
+            s += (double)s_red[w][tid];
+        }
+        ka.cta_part[(size_t)tid * ka.n_cta + blockIdx.x] = s;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* energy-only passes at all lambda points                                                     */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Sums 8 per-lane values over the 32 lanes with 9 shuffles: after three halving exchanges lane l
+ * holds value index 4*(l&1) + 2*((l>>1)&1) + ((l>>2)&1), summed over all lanes. */
+__device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane)
+{
+    float a[4], b[2], c;
+    {
+        const bool up = lane & 1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            const float send = up ? v[i] : v[i + 4];
+            const float keep = up ? v[i + 4] : v[i];
+            a[i]             = keep + __shfl_xor_sync(FULL_MASK, send, 1);
+        }
+    }
+    {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            const float send = up ? a[i] : a[i + 2];
+            const float keep = up ? a[i + 2] : a[i];
+            b[i]             = keep + __shfl_xor_sync(FULL_MASK, send, 2);
+        }
+    }
+    {
+        const bool  up   = lane & 4;
+        const float send = up ? b[0] : b[1];
+        const float keep = up ? b[1] : b[0];
+        c                = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+    }
+    c += __shfl_xor_sync(FULL_MASK, c, 8);
+    c += __shfl_xor_sync(FULL_MASK, c, 16);
+    return c;
+}
+
+template<int SC, bool EWALD>
+__global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_constant__ KernelArgs ka)
+{
+    __shared__ LambdaPoint s_pts[FEP_LCHUNK];
+    __shared__ float       s_red[FEP_CTA / 32][3 * FEP_LCHUNK];
+
+    const int tid  = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int p0   = blockIdx.y * ka.chunk_points;
+    const int np   = min(ka.chunk_points, ka.n_points - p0);
+    if (tid < np * (int)(sizeof(LambdaPoint) / 4))
+    {
+        reinterpret_cast<int*>(s_pts)[tid] = reinterpret_cast<const int*>(ka.pts + p0)[tid];
+    }
+    __syncthreads();
+
+    float acc_e[FEP_LCHUNK], acc_c[FEP_LCHUNK], acc_v[FEP_LCHUNK];
+#pragma unroll
+    for (int p = 0; p < FEP_LCHUNK; p++)
+    {
+        acc_e[p] = acc_c[p] = acc_v[p] = 0.0f;
+    }
+
+    const int base = blockIdx.x * ka.tile_pairs;
+    const int end  = min(base + ka.tile_pairs, ka.n_pairs);
+    for (int slot = base + tid; slot < end; slot += FEP_CTA)
+    {
+        FepPair pr;
+        float   dx, dy, dz;
+        bool    excluded, self;
+        int     entry;
+        if (!fep_load_pair<SC>(ka, slot, pr, dx, dy, dz, excluded, self, entry))
+        {
+            continue;
+        }
+        float xc, fc, xv, fv;
+        fep_corrections<EWALD, false>(ka, pr, excluded, self, xc, fc, xv, fv);
+        const float cA = pr.qq[0] * xc, cB = pr.qq[1] * xc;
+        const float gA = pr.c6g[0] * xv, gB = pr.c6g[1] * xv;
+        const float dcorr_c = cB - cA, dcorr_v = gB - gA;
+#pragma unroll
+        for (int p = 0; p < FEP_LCHUNK; p++)
+        {
+            if (p < np)
+            {
+                const LambdaPoint& lp = s_pts[p];
+                float              vc = 0.0f, vv = 0.0f, fs = 0.0f, dc = dcorr_c, dv = dcorr_v;
+                if (pr.included_within)
+                {
+                    fep_included_terms<SC, EWALD, false>(ka, lp, pr, vc, vv, fs, dc, dv);
+                }
+                vc += lp.lfac_c[0] * cA + lp.lfac_c[1] * cB;
+                vv += lp.lfac_v[0] * gA + lp.lfac_v[1] * gB;
+                acc_e[p] += vc + vv;
+                acc_c[p] += dc;
+                acc_v[p] += dv;
+            }
+        }
+    }
+
+    const float re = warp_sum8(acc_e, lane), rc = warp_sum8(acc_c, lane), rv = warp_sum8(acc_v, lane);
+    if (lane < 8)
+    {
+        const int p         = 4 * (lane & 1) + 2 * ((lane >> 1) & 1) + ((lane >> 2) & 1);
+        s_red[warp][3 * p]     = re;
+        s_red[warp][3 * p + 1] = rc;
+        s_red[warp][3 * p + 2] = rv;
+    }
+    __syncthreads();
+    if (tid < 3 * np)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < FEP_CTA / 32; w++)
+        {
+            s += (double)s_red[w][tid];
+        }
+        const int p = tid / 3, k = tid - 3 * p;
+        ka.for_part[((size_t)(3 * (p0 + p) + k)) * ka.n_tiles + blockIdx.x] = s;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* epilogue                                                                                    */
+/* ------------------------------------------------------------------------------------------- */
+struct EpilogueLayout
+{
+    int atom_blocks;   /* blocks [0, atom_blocks): per-atom force gather                */
+    int job_begin;     /* first reduction job handled (skips shift jobs when not asked)  */
+    int job_blocks;    /* blocks for reduction jobs                                      */
+    int scalar_blocks; /* blocks for dvdl (2) + foreign (3*(L+1)) partial arrays         */
+};
+
+__device__ __forceinline__ double block_sum_d(double v, double* s_buf)
+{
+    v = warp_sum_d(v);
+    if ((threadIdx.x & 31) == 0)
+    {
+        s_buf[threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+    {
+        for (int w = 0; w < FEP_EPI_CTA / 32; w++)
+        {
+            s += s_buf[w];
+        }
+    }
+    __syncthreads();
+    return s; /* valid in thread 0 */
+}
+
+__global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_constant__ KernelArgs ka,
+                                                                  const EpilogueLayout lay, const StepFlags sf)
+{
+    __shared__ double s_buf[FEP_EPI_CTA / 32];
+    __shared__ bool   s_last;
+    const int         tid = threadIdx.x;
+    int               b   = blockIdx.x;
+
+    /* offsets into the fp64 result block: Vc[G] Vv[G] dvdl[2] foreign_E[L+1] foreign_dvdl[L+1][2] */
+    const int off_vv   = ka.n_gid;
+    const int off_dvdl = 2 * ka.n_gid;
+    const int off_fe   = off_dvdl + 2;
+    const int off_fd   = off_fe + ka.n_points;
+
+    if (b < lay.atom_blocks)
+    {
+        /* eight lanes per touched atom; contributions are visited in ascending index order by
+         * lane stride, then combined with a fixed xor tree: deterministic */
+        const int atom = b * (FEP_EPI_CTA / 8) + (tid >> 3);
+        const int sub  = tid & 7;
+        float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        if (atom < ka.n_touched)
+        {
+            const int k0 = __ldg(ka.atom_ptr + atom), k1 = __ldg(ka.atom_ptr + atom + 1);
+            for (int k = k0 + sub; k < k1; k += 8)
+            {
+                const int idx = __ldg(ka.atom_idx + k);
+                if (idx < ka.n_pairs)
+                {
+                    const float4 t = __ldcs(ka.t4 + idx);
+                    fx -= t.x;
+                    fy -= t.y;
+                    fz -= t.z;
+                }
+                else
+                {
+                    const float4 t = __ldg(ka.fi4 + (idx - ka.n_pairs));
+                    fx += t.x;
+                    fy += t.y;
+                    fz += t.z;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)
+        {
+            fx += __shfl_xor_sync(FULL_MASK, fx, o);
+            fy += __shfl_xor_sync(FULL_MASK, fy, o);
+            fz += __shfl_xor_sync(FULL_MASK, fz, o);
+        }
+        if (atom < ka.n_touched && sub < 3)
+        {
+            ka.res_f32[3 * (size_t)atom + sub] = sub == 0 ? fx : (sub == 1 ? fy : fz);
+        }
+    }
+    else if ((b -= lay.atom_blocks) < lay.job_blocks)
+    {
+        const int    j   = lay.job_begin + b;
+        const RedJob job = ka.red_jobs[j];
+        double       a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        if (job.kind == 0)
+        {
+            for (int k = job.begin + tid; k < job.end; k += FEP_EPI_CTA)
+            {
+                const float4 t = __ldg(ka.fi4 + __ldg(ka.red_idx + k));
+                a0 += t.x;
+                a1 += t.y;
+                a2 += t.z;
+            }
+        }
+        else
+        {
+            for (int k = job.begin + tid; k < job.end; k += FEP_EPI_CTA)
+            {
+                const float2 t = __ldg(ka.ev2 + __ldg(ka.red_idx + k));
+                a0 += t.x;
+                a1 += t.y;
+            }
+        }
+        a0 = block_sum_d(a0, s_buf);
+        a1 = block_sum_d(a1, s_buf);
+        a2 = block_sum_d(a2, s_buf);
+        if (tid == 0)
+        {
+            ka.job_part[4 * (size_t)j]     = a0;
+            ka.job_part[4 * (size_t)j + 1] = a1;
+            ka.job_part[4 * (size_t)j + 2] = a2;
+        }
+    }
+    else if ((b -= lay.job_blocks) < lay.scalar_blocks)
+    {
+        /* b = 0,1: dV/dlambda coul, vdw of the current-lambda pass; b = 2 + 3p + k: point p */
+        const double* src;
+        int           n;
+        if (b < 2)
+        {
+            src = ka.cta_part + (size_t)b * ka.n_cta;
+            n   = ka.n_cta;
+        }
+        else
+        {
+            src = ka.for_part + (size_t)(b - 2) * ka.n_tiles;
+            n   = ka.n_tiles;
+        }
+        double a = 0.0;
+        for (int k = tid; k < n; k += FEP_EPI_CTA)
+        {
+            a += src[k];
+        }
+        a = block_sum_d(a, s_buf);
+        if (tid == 0)
+        {
+            if (b < 2)
+            {
+                ka.res_f64[off_dvdl + b] = a;
+            }
+            else
+            {
+                const int p = (b - 2) / 3, k = (b - 2) - 3 * p;
+                if (k == 0)
+                {
+                    ka.res_f64[off_fe + p] = a;
+                }
+                else
+                {
+                    ka.res_f64[off_fd + 2 * p + (k - 1)] = a;
+                }
+            }
+        }
+    }
+
+    /* the block that finishes last adds up the job partials per output key, in job order */
+    __threadfence();
+    if (tid == 0)
+    {
+        const unsigned ticket = atomicAdd(ka.done_counter, 1u);
+        s_last                = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last)
+    {
+        return;
+    }
+    __threadfence();
+    if (sf.shift)
+    {
+        for (int o = tid; o < 3 * FEP_NUM_SHIFT; o += FEP_EPI_CTA)
+        {
+            const int s = o / 3, d = o - 3 * s;
+            double    a = 0.0;
+            for (int j = ka.key_job_ptr[s]; j < ka.key_job_ptr[s + 1]; j++)
+            {
+                a += __ldcg(ka.job_part + 4 * (size_t)j + d);
+            }
+            ka.res_f32[3 * (size_t)ka.n_touched + o] = (float)a;
+        }
+    }
+    if (sf.energy)
+    {
+        for (int g = tid; g < ka.n_gid; g += FEP_EPI_CTA)
+        {
+            double a = 0.0, c = 0.0;
+            for (int j = ka.key_job_ptr[FEP_NUM_SHIFT + g]; j < ka.key_job_ptr[FEP_NUM_SHIFT + g + 1]; j++)
+            {
+                a += __ldcg(ka.job_part + 4 * (size_t)j);
+                c += __ldcg(ka.job_part + 4 * (size_t)j + 1);
+            }
+            ka.res_f64[g]          = a;
+            ka.res_f64[off_vv + g] = c;
+        }
+    }
+    if (tid == 0)
+    {
+        *ka.done_counter = 0u;
+    }
+}
+
+/* coordinates of the touched atoms from a device-resident rvec[natoms] array */
+__global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restrict__ x, const int* __restrict__ touched,
+                                                          float4* __restrict__ pos4, int n)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < n)
+    {
+        const size_t a = (size_t)touched[k];
+        pos4[k]        = make_float4(x[3 * a], x[3 * a + 1], x[3 * a + 2], 0.0f);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* launchers                                                                                   */
+/* ------------------------------------------------------------------------------------------- */
+template<int SC, bool EWALD>
+static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStream_t stream, long long* counter,
+                                   cudaEvent_t* ev)
+{
+    if (ev)
+    {
+        cudaEventRecord(ev[0], stream);
+    }
+    if (ka.n_cta > 0)
+    {
+        if (sf.force)
+        {
+            fep_pass_kernel<SC, EWALD, true><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka);
+        }
+        else
+        {
+            fep_pass_kernel<SC, EWALD, false><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka);
+        }
+        (*counter)++;
+    }
+    if (ev)
+    {
+        cudaEventRecord(ev[1], stream);
+    }
+    if (ka.n_cta > 0 && sf.foreign && ka.n_points > 0)
+    {
+        const dim3 grid(ka.n_tiles, ka.n_chunks);
+        fep_foreign_kernel<SC, EWALD><<<grid, FEP_CTA, 0, stream>>>(ka);
+        (*counter)++;
+    }
+    if (ev)
+    {
+        cudaEventRecord(ev[2], stream);
+    }
+    return cudaGetLastError();
+}
+
+extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
+                               long long* counter, cudaEvent_t* ev)
+{
+    const KernelArgs& ka = *kap;
+    cudaError_t       err;
+    switch (softcore * 2 + (elec_ewald ? 1 : 0))
+    {
+        case FEP_SC_NONE * 2 + 0: err = launch_variants<FEP_SC_NONE, false>(ka, sf, stream, counter, ev); break;
+        case FEP_SC_NONE * 2 + 1: err = launch_variants<FEP_SC_NONE, true>(ka, sf, stream, counter, ev); break;
+        case FEP_SC_BEUTLER * 2 + 0: err = launch_variants<FEP_SC_BEUTLER, false>(ka, sf, stream, counter, ev); break;
+        case FEP_SC_BEUTLER * 2 + 1: err = launch_variants<FEP_SC_BEUTLER, true>(ka, sf, stream, counter, ev); break;
+        case FEP_SC_GAPSYS * 2 + 0: err = launch_variants<FEP_SC_GAPSYS, false>(ka, sf, stream, counter, ev); break;
+        case FEP_SC_GAPSYS * 2 + 1: err = launch_variants<FEP_SC_GAPSYS, true>(ka, sf, stream, counter, ev); break;
+        default: return (int)cudaErrorInvalidValue;
+    }
+    if (err != cudaSuccess)
+    {
+        return (int)err;
+    }
+    EpilogueLayout lay;
+    lay.atom_blocks   = sf.force ? (ka.n_touched + FEP_EPI_CTA / 8 - 1) / (FEP_EPI_CTA / 8) : 0;
+    /* jobs are ordered shift jobs first, then energy-group jobs */
+    const int j0      = sf.shift ? 0 : ka.n_shift_jobs;
+    const int j1      = sf.energy ? ka.n_red_jobs : ka.n_shift_jobs;
+    lay.job_begin     = j0;
+    lay.job_blocks    = j1 > j0 ? j1 - j0 : 0;
+    lay.scalar_blocks = 2 + ((sf.foreign && ka.n_points > 0) ? 3 * ka.n_points : 0);
+    const int blocks  = lay.atom_blocks + lay.job_blocks + lay.scalar_blocks;
+    fep_epilogue_kernel<<<blocks, FEP_EPI_CTA, 0, stream>>>(ka, lay, sf);
+    (*counter)++;
+    if (ev)
+    {
+        cudaEventRecord(ev[3], stream);
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched,
+                                   cudaStream_t stream, long long* counter)
+{
+    if (n_touched > 0)
+    {
+        fep_gather_x_kernel<<<(n_touched + 255) / 256, 256, 0, stream>>>(d_x, d_touched, pos4, n_touched);
+        (*counter)++;
+    }
+    return (int)cudaGetLastError();
+}

@@ -17,21 +17,42 @@
 #define FEP_MIN_RSQ 1.0e-12f  /* nb_free_energy.cpp:99  */
 #define FEP_MAX_RINV6 1.0e15f /* nb_free_energy.cpp:107 */
 
+/* bare MUFU operations (no denormal / range fix-up code): every argument here is a normal number */
 __device__ __forceinline__ float fep_rcp(float x)
 {
-    return __fdividef(1.0f, x);
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fep_rsqrt(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fep_lg2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fep_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 /* x^(-1/6) for x > 0 (normal range): two MUFU ops */
 __device__ __forceinline__ float fep_inv_sixth_root(float x)
 {
-    return exp2f(__log2f(x) * (-1.0f / 6.0f));
+    return fep_ex2(fep_lg2(x) * (-1.0f / 6.0f));
 }
 
 /* x^(1/6) */
 __device__ __forceinline__ float fep_sixth_root(float x)
 {
-    return exp2f(__log2f(x) * (1.0f / 6.0f));
+    return fep_ex2(fep_lg2(x) * (1.0f / 6.0f));
 }
 
 /* Ewald real-space correction (reference :109-119, 1056-1101).
@@ -71,7 +92,7 @@ __device__ __forceinline__ void fep_ewald_correction(float r2, float r, float ri
         else
         {
             const float iz2 = fep_rcp(z2);
-            bracket         = 1.1283791671f * __expf(-z2) * iz2 - ez * iz2 * fep_rcp(z);
+            bracket         = 1.1283791671f * fep_ex2(-1.4426950408889634f * z2) * iz2 - ez * iz2 * fep_rcp(z);
         }
         *f_lr = -beta3 * bracket;
     }
@@ -86,7 +107,7 @@ __device__ __forceinline__ void fep_ljpme_correction(float r2, float rinv, float
 {
     const float rinv2 = rinv * rinv;
     const float x     = csq * r2;
-    const float e     = __expf(-x);
+    const float e     = fep_ex2(-1.4426950408889634f * x);
     float       term;
     if (x < 1.0f)
     {
@@ -388,7 +409,7 @@ __device__ __forceinline__ bool fep_load_pair(const KernelArgs& ka, int slot, Fe
     }
     r2      = fmaxf(r2, FEP_MIN_RSQ);
     pr.r2   = r2;
-    pr.rinv = rsqrtf(r2);
+    pr.rinv = fep_rsqrt(r2);
     pr.r    = r2 * pr.rinv;
     if (SC == FEP_SC_BEUTLER)
     {

@@ -3,25 +3,26 @@
  * (fep_kernels.cu).  Vocabulary follows the reference: i-entries, j atoms, pairs, energy-group
  * pairs (gid), shift vectors, lambda states A/B.
  *
- * Device layout of one context (all arrays in HBM, "compact" = index into the ascending list of
+ * Device layout of one context (all arrays in HBM; "compact" = index into the ascending list of
  * atoms that occur anywhere in the FULL FEP list, so that every rank uses the same numbering):
  *
- *   dyn          DynBlock          per step: shift vectors + lambda-derived constants
+ *   dyn          DynHead           per step: shift vectors + constants of the current lambda
+ *   pts[L+1]     LambdaPoint       per set_lambdas: point 0 = current lambda, 1.. = foreign
  *   pos4[nT]     float4 {x,y,z,0}  per step: coordinates of the touched atoms (compact order)
  *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step
  *   typetab[T*T] float4 {c6,c12,sigma6,c6grid}               per nbfp upload
  *   pair_j[P]    int    compact j | excluded << 31           per search step
  *   pair_e[P]    int    local i-entry index of the pair      per search step
  *   ent4[E]      int4   {compact i, shift index, gid, 0}     per search step
- *   warp_hbase[P/32+1]  first "segment head" slot of each warp of the flat pair space
- *   t4[P]        float4 pair force vectors (written by the force kernel, read by the epilogue)
+ *   warp_hbase[ceil(P/32)]  index of the first "segment" of each warp of the flat pair space;
+ *                a segment is a maximal run of pairs of one i-entry inside one warp
+ *   t4[P]        float4 pair force vectors (written by the pass kernel, read by the epilogue)
  *   fi4[H]       float4 per-segment i forces;  ev2[H] float2 per-segment {Vc,Vv}
  *   atom_ptr[nT+1], atom_idx[P+H]   contributions per touched atom (idx < P: -t4, else +fi4)
- *   gid_ptr[G+1],  gid_idx[H]       segments per energy-group pair
- *   shf_ptr[46],   shf_idx[H]       segments per shift vector
- *   dvdl_part[nCta][2]   fp64 per-CTA partial dV/dlambda of the current-lambda pass
- *   for_part[3*(L+1)][nCta] fp64 per-CTA partial foreign energies / dV/dlambda
- *   res_f32[3*nT + 3*45], res_f64[2G + 2 + 3(L+1)]   the result block (include/fepb200.h)
+ *   red_*        chunked segment lists per shift vector and per energy-group pair
+ *   cta_part[nCta][2]        fp64 per-CTA partial dV/dlambda of the current-lambda pass
+ *   for_part[3*(L+1)][nTile] fp64 per-CTA partial foreign energies / dV/dlambda
+ *   result block: res_f32[3*nT + 3*45], res_f64[2G + 2 + 3(L+1)]   (include/fepb200.h)
  */
 #ifndef FEPB200_FEP_TYPES_H
 #define FEPB200_FEP_TYPES_H
@@ -29,33 +30,42 @@
 #include <cuda_runtime.h>
 
 #define FEP_NUM_SHIFT 45
-#define FEP_MAX_FOREIGN 255 /* L+1 <= 256 lambda points per step */
-#define FEP_CTA 256         /* threads (= pairs) per CTA of the pair kernels */
-#define FEP_LCHUNK 8        /* lambda points evaluated per thread in the foreign kernel */
+#define FEP_CENTRAL_SHIFT 22
+#define FEP_MAX_POINTS 256 /* L+1 <= 256 lambda points per step */
+#define FEP_CTA 256        /* threads per CTA of the pair kernels */
+#define FEP_LCHUNK 8       /* lambda points evaluated per thread per pair in the foreign kernel */
+#define FEP_RED_CHUNK 2048 /* segments per reduction job of the epilogue */
+#define FEP_EPI_CTA 256
 
 /* soft-core flavour actually evaluated (nb_free_energy.cpp:1324-1363) */
 enum { FEP_SC_NONE = 0, FEP_SC_BEUTLER = 1, FEP_SC_GAPSYS = 2 };
 
-/* Everything about one lambda point the kernels need (nb_free_energy.cpp:420-449). */
+/* Everything about one lambda point the kernels need (nb_free_energy.cpp:420-449). 96 bytes. */
 struct LambdaPoint
 {
     float lfac_c[2], lfac_v[2];     /* {1-lambda, lambda} */
     float sclfac_c[2], sclfac_v[2]; /* soft-core lambda factors */
-    float scdl_c[2], scdl_v[2];     /* d(soft-core lambda factor)/dlambda * p/6 */
+    float scdl_c[2], scdl_v[2];     /* dlfac * p/6 * (p==2 ? 1-lfac : 1) */
     float g6_c[2], g6_v[2];         /* Gapsys: (1-lfac)^(1/6) */
     float gdl_c[2], gdl_v[2];       /* Gapsys: lfac/(1-lfac) (0 when lfac == 1) */
     int   differ;                   /* scLambdasOrAlphasDiffer for this point (:1405-1419) */
     int   pad[3];
 };
 
-/* Per-step block, uploaded together with the coordinates. */
-struct DynBlock
+/* Per-step head block, uploaded in one copy together with the coordinates that follow it
+ * in device memory (step_in = [DynHead | pos4[nT]]). */
+struct DynHead
 {
     float4      shiftvec[FEP_NUM_SHIFT];
-    LambdaPoint cur;                           /* the current lambda */
-    int         n_points;                      /* L+1 */
-    int         pad[3];
-    LambdaPoint pts[FEP_MAX_FOREIGN + 1];      /* point 0 = current lambda, 1.. = foreign */
+    LambdaPoint cur; /* the current lambda (pass at the current lambda) */
+};
+
+/* One reduction job of the epilogue: segments idx[begin,end) all belong to output `key`. */
+struct RedJob
+{
+    int begin, end;
+    int key;  /* shift index (kind 0) or gid (kind 1) */
+    int kind; /* 0: fi4 -> shift force, 1: ev2 -> Vc/Vv */
 };
 
 /* Static constants + device pointers, passed by value as the kernel parameter. */
@@ -64,14 +74,17 @@ struct KernelArgs
     /* interaction constants (nb_free_energy.cpp:323-396) */
     float epsfac, rcoulomb, rvdw, rvdw_switch, krf, crf, sh_ewald, sh_lj_ewald;
     float beta, beta2, beta3, lj_coeff_sq, lj_coeff6_div6, disp_cpot, rep_cpot;
-    float rcut_max2, rcoulomb2, rvdw2, rcoulomb6, rvdw6;
+    float rcut_max2, rcoulomb6, rvdw6;
     float alpha_c, alpha_v, gscale_c, gscale_v;
     float sw_v3, sw_v4, sw_v5, sw_f2, sw_f3, sw_f4;
     int   vdw_ewald, pot_switch, rf_type, ntype;
     /* sizes */
-    int       n_pairs, n_entries, n_heads, n_touched, n_gid, n_cta;
+    int n_pairs, n_entries, n_segments, n_touched, n_gid, n_cta, n_tiles, tile_pairs;
+    int n_points, n_chunks, chunk_points;
+    int n_red_jobs, n_shift_jobs;
     /* inputs */
-    const DynBlock* dyn;
+    const DynHead*     dyn;
+    const LambdaPoint* pts;
     const float4*   pos4;
     const float4*   par4;
     const float4*   typetab;
@@ -83,21 +96,22 @@ struct KernelArgs
     float4* t4;
     float4* fi4;
     float2* ev2;
-    double* dvdl_part;
+    double* cta_part;
     double* for_part;
+    double* job_part; /* [n_red_jobs][4] */
+    unsigned int* done_counter;
     /* epilogue inputs */
-    const int* atom_ptr;
-    const int* atom_idx;
-    const int* gid_ptr;
-    const int* gid_idx;
-    const int* shf_ptr;
-    const int* shf_idx;
+    const int*    atom_ptr;
+    const int*    atom_idx;
+    const RedJob* red_jobs;
+    const int*    red_idx;
+    const int*    key_job_ptr; /* [45 + G + 1]: jobs of each key, shift keys first */
     /* outputs */
     float*  res_f32;
     double* res_f64;
 };
 
-/* step variants */
+/* what one step has to produce */
 struct StepFlags
 {
     int force, shift, energy, foreign;
@@ -106,10 +120,11 @@ struct StepFlags
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* implemented in fep_kernels.cu; all launches go to `stream`; returns a cudaError_t as int */
-int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlags sf, int n_points,
-                    cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t fork_ev, cudaEvent_t join_ev,
-                    long long* launch_counter);
+/* implemented in fep_kernels.cu; all launches go to `stream`; return a cudaError_t as int */
+/* `events`, when not NULL, are 4 events recorded before the pass kernel and after the pass,
+ * foreign and epilogue kernels (profiling mode only). */
+int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
+                    long long* launch_counter, cudaEvent_t* events);
 int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched, cudaStream_t stream,
                         long long* launch_counter);
 #ifdef __cplusplus

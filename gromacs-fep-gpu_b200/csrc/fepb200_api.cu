@@ -1,0 +1,1350 @@
+/*
+ * fepb200_api.cu -- host side of libfepb200.so: the C-ABI of include/fepb200.h.
+ *
+ * Owns the device-side layout (fep_types.h), turns the reference's inputs (t_nblist, per-atom
+ * A/B charges and types, nbfp, interaction_const_t scalars, lambda vectors) into it, and drives
+ * the kernels of fep_kernels.cu.  There is no CPU implementation of the pair mathematics in this
+ * file or anywhere else in the library: without a CUDA device fepb200_create() fails.
+ *
+ * Reference call sites this replaces (paths under src/gromacs/):
+ *   nbnxm/freeenergydispatch.cpp:147-308   dispatchFreeEnergyKernel() incl. foreign-lambda loop
+ *   nbnxm/nbnxm_gpu_data_mgmt.cpp:491-536  cuda_copy_fepparams()
+ *   nbnxm/nbnxm_gpu_data_mgmt.cpp:761-871  gpu_init_feppairlist()
+ *   nbnxm/atomdata.cpp:1055-1072           setAtomPropertiesAB
+ *   nbnxm/pairlist.cpp:2786-2838           balance_fep_lists() (here: split over ranks)
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fepb200.h"
+#include "fep_types.h"
+
+namespace
+{
+
+thread_local std::string g_create_error;
+
+template<typename T>
+struct DeviceArray
+{
+    T*     ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap)
+        {
+            return cudaSuccess;
+        }
+        if (ptr)
+        {
+            cudaFree(ptr);
+            ptr = nullptr;
+            cap = 0;
+        }
+        const size_t want = n + n / 8 + 64;
+        cudaError_t  e    = cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T));
+        if (e == cudaSuccess)
+        {
+            cap = want;
+        }
+        return e;
+    }
+    void release()
+    {
+        if (ptr)
+        {
+            cudaFree(ptr);
+        }
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+template<typename T>
+struct PinnedArray
+{
+    T*     ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap)
+        {
+            return cudaSuccess;
+        }
+        if (ptr)
+        {
+            cudaFreeHost(ptr);
+            ptr = nullptr;
+            cap = 0;
+        }
+        const size_t want = n + n / 8 + 64;
+        cudaError_t  e    = cudaMallocHost(reinterpret_cast<void**>(&ptr), want * sizeof(T));
+        if (e == cudaSuccess)
+        {
+            cap = want;
+        }
+        return e;
+    }
+    void release()
+    {
+        if (ptr)
+        {
+            cudaFreeHost(ptr);
+        }
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+float int_bits_as_float(int v)
+{
+    float f;
+    std::memcpy(&f, &v, sizeof(f));
+    return f;
+}
+
+bool eel_is_ewald(int e)
+{
+    /* md_enums.h: Pme 3, Ewald 4, P3mAD 5, PmeUser 13, PmeSwitch 14, PmeUserSwitch 15 */
+    return e == 3 || e == 4 || e == 5 || e == 13 || e == 14 || e == 15;
+}
+bool eel_is_rf(int e)
+{
+    /* RF 1, GRF(removed) 2, RF_NEC 11, RFZero 16 */
+    return e == 1 || e == 2 || e == 11 || e == 16;
+}
+
+} // namespace
+
+struct fepb200_ctx
+{
+    int          device = -1;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t  ev_prof[4] = { nullptr, nullptr, nullptr, nullptr };
+    bool         profiling = false, profiled = false;
+    std::string  error;
+    std::string  description;
+    long long    launches = 0;
+    bool         timed    = false;
+
+    /* constants */
+    bool           have_params = false;
+    fepb200_params params{};
+    int            softcore   = FEP_SC_NONE;
+    int            elec_ewald = 0;
+    KernelArgs     ka{};
+
+    /* nbfp */
+    int                 ntype = 0;
+    std::vector<float>  nbfp, nbfp_grid;
+    DeviceArray<float4> d_typetab;
+    bool                typetab_dirty = true;
+
+    /* atoms */
+    int                natoms = 0;
+    std::vector<float> qA, qB;
+    std::vector<int>   typeA, typeB;
+
+    /* lambdas */
+    bool                     have_lambda = false;
+    float                    lam_c = 0, lam_v = 0;
+    std::vector<float>       all_c, all_v;
+    LambdaPoint              cur{};
+    std::vector<LambdaPoint> pts;
+    DeviceArray<LambdaPoint> d_pts;
+    PinnedArray<LambdaPoint> h_pts;
+
+    /* list */
+    bool             have_list = false;
+    fepb200_layout   layout{};
+    int              first_entry = 0;
+    std::vector<int> touched;    /* compact -> atom */
+    std::vector<int> compact_of; /* atom -> compact or -1 */
+    int              n_segments = 0;
+
+    DeviceArray<int>    d_touched, d_pair_j, d_pair_e, d_warp_hbase, d_atom_ptr, d_atom_idx, d_red_idx, d_key_job_ptr;
+    DeviceArray<int4>   d_ent4;
+    DeviceArray<RedJob> d_red_jobs;
+    DeviceArray<float4> d_par4, d_t4, d_fi4;
+    DeviceArray<float2> d_ev2;
+    DeviceArray<double> d_cta_part, d_for_part, d_job_part;
+    DeviceArray<unsigned int> d_counter;
+    DeviceArray<unsigned char> d_step_in; /* [DynHead | pos4[nT]] */
+    DeviceArray<unsigned char> d_result;  /* [f64 block | f32 block] */
+    PinnedArray<unsigned char> h_step_in, h_result;
+    size_t res_f64_bytes = 0, res_f32_bytes = 0;
+};
+
+namespace
+{
+
+int fail(fepb200_ctx* ctx, int code, const char* fmt, ...)
+{
+    char    buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+    {
+        ctx->error = buf;
+    }
+    else
+    {
+        g_create_error = buf;
+    }
+    return code;
+}
+
+#define CU_CHECK(ctx, call)                                                                              \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+        {                                                                                                \
+            return fail(ctx, FEPB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                             \
+        }                                                                                                \
+    } while (0)
+
+/* nb_free_energy.cpp:420-449 and :1405-1419, evaluated in double and rounded once */
+LambdaPoint make_point(const fepb200_params& p, float lam_c_f, float lam_v_f)
+{
+    LambdaPoint  lp{};
+    const double lc = lam_c_f, lv = lam_v_f;
+    const double lfc[2] = { 1.0 - lc, lc }, lfv[2] = { 1.0 - lv, lv }, dl[2] = { -1.0, 1.0 };
+    for (int s = 0; s < 2; s++)
+    {
+        const double oc = 1.0 - lfc[s], ov = 1.0 - lfv[s];
+        const bool   p2 = p.lambdaPower == 2;
+        lp.lfac_c[s]    = (float)lfc[s];
+        lp.lfac_v[s]    = (float)lfv[s];
+        lp.sclfac_c[s]  = (float)(p2 ? oc * oc : oc);
+        lp.sclfac_v[s]  = (float)(p2 ? ov * ov : ov);
+        lp.scdl_c[s]    = (float)(dl[s] * p.lambdaPower / 6.0 * (p2 ? oc : 1.0));
+        lp.scdl_v[s]    = (float)(dl[s] * p.lambdaPower / 6.0 * (p2 ? ov : 1.0));
+        lp.g6_c[s]      = (float)std::pow(oc, 1.0 / 6.0);
+        lp.g6_v[s]      = (float)std::pow(ov, 1.0 / 6.0);
+        lp.gdl_c[s]     = lfc[s] < 1.0 ? (float)(lfc[s] / oc) : 0.0f;
+        lp.gdl_v[s]     = lfv[s] < 1.0 ? (float)(lfv[s] / ov) : 0.0f;
+    }
+    int differ = 1;
+    if (p.alphaCoulomb == 0.0f && p.alphaVdw == 0.0f)
+    {
+        differ = 0;
+    }
+    else if (lam_c_f == lam_v_f && p.alphaCoulomb == p.alphaVdw)
+    {
+        differ = 0;
+    }
+    lp.differ = differ;
+    return lp;
+}
+
+void refresh_points(fepb200_ctx* c)
+{
+    if (!c->have_params || !c->have_lambda)
+    {
+        return;
+    }
+    c->cur = make_point(c->params, c->lam_c, c->lam_v);
+    c->pts.clear();
+    c->pts.push_back(c->cur);
+    for (size_t i = 0; i < c->all_c.size(); i++)
+    {
+        c->pts.push_back(make_point(c->params, c->all_c[i], c->all_v[i]));
+    }
+}
+
+void fill_layout(fepb200_ctx* c)
+{
+    fepb200_layout& l  = c->layout;
+    const long long g  = l.nenergrp;
+    const long long np = l.nforeign + 1;
+    l.f32_words        = 3LL * l.ntouched + 3 * FEP_NUM_SHIFT;
+    l.off_fshift       = 3LL * l.ntouched;
+    l.off_vc           = 0;
+    l.off_vv           = g;
+    l.off_dvdl         = 2 * g;
+    l.off_foreign_e    = 2 * g + 2;
+    l.off_foreign_dvdl = 2 * g + 2 + np;
+    l.f64_words        = 2 * g + 2 + 3 * np;
+}
+
+/* (Re)allocates everything whose size depends on list, G and L, and refreshes the pointers
+ * and sizes in the kernel argument block. */
+int prepare_buffers(fepb200_ctx* c)
+{
+    fill_layout(c);
+    const fepb200_layout& l = c->layout;
+    KernelArgs&           k = c->ka;
+    const int             np = l.nforeign + 1;
+
+    k.n_points = np;
+    /* lambda chunks of at most FEP_LCHUNK points, evenly sized */
+    k.n_chunks     = (np + FEP_LCHUNK - 1) / FEP_LCHUNK;
+    k.chunk_points = (np + k.n_chunks - 1) / k.n_chunks;
+    k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
+    /* pair tiles of the foreign kernel: enough CTAs to fill the GPU several times over, but
+     * several pairs per thread on large lists to amortise the final reduction */
+    {
+        int       sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        const long long target_ctas = 8LL * sms;
+        long long       per_thread  = ((long long)k.n_pairs * k.n_chunks + target_ctas * FEP_CTA - 1)
+                               / (target_ctas * FEP_CTA);
+        per_thread   = std::max(1LL, std::min(per_thread, 8LL));
+        k.tile_pairs = (int)per_thread * FEP_CTA;
+        k.n_tiles    = (k.n_pairs + k.tile_pairs - 1) / k.tile_pairs;
+    }
+
+    CU_CHECK(c, c->d_pts.reserve(np));
+    CU_CHECK(c, c->h_pts.reserve(np));
+    CU_CHECK(c, c->d_cta_part.reserve(2 * (size_t)std::max(k.n_cta, 1)));
+    CU_CHECK(c, c->d_for_part.reserve(3 * (size_t)np * std::max(k.n_tiles, 1)));
+    c->res_f64_bytes = ((size_t)l.f64_words * sizeof(double) + 15) & ~(size_t)15;
+    c->res_f32_bytes = (size_t)l.f32_words * sizeof(float);
+    CU_CHECK(c, c->d_result.reserve(c->res_f64_bytes + c->res_f32_bytes));
+    CU_CHECK(c, c->h_result.reserve(c->res_f64_bytes + c->res_f32_bytes));
+    const size_t step_bytes = sizeof(DynHead) + sizeof(float4) * (size_t)l.ntouched;
+    CU_CHECK(c, c->d_step_in.reserve(step_bytes));
+    CU_CHECK(c, c->h_step_in.reserve(step_bytes));
+
+    k.dyn      = reinterpret_cast<const DynHead*>(c->d_step_in.ptr);
+    k.pos4     = reinterpret_cast<const float4*>(c->d_step_in.ptr + sizeof(DynHead));
+    k.pts      = c->d_pts.ptr;
+    k.cta_part = c->d_cta_part.ptr;
+    k.for_part = c->d_for_part.ptr;
+    k.res_f64  = reinterpret_cast<double*>(c->d_result.ptr);
+    k.res_f32  = reinterpret_cast<float*>(c->d_result.ptr + c->res_f64_bytes);
+    return FEPB200_OK;
+}
+
+int upload_points(fepb200_ctx* c)
+{
+    if (c->pts.empty())
+    {
+        return FEPB200_OK;
+    }
+    CU_CHECK(c, c->d_pts.reserve(c->pts.size()));
+    CU_CHECK(c, c->h_pts.reserve(c->pts.size()));
+    c->ka.pts = c->d_pts.ptr;
+    /* the previous copy out of the pinned buffer must have completed */
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(c->h_pts.ptr, c->pts.data(), c->pts.size() * sizeof(LambdaPoint));
+    CU_CHECK(c, cudaMemcpyAsync(c->d_pts.ptr, c->h_pts.ptr, c->pts.size() * sizeof(LambdaPoint),
+                                cudaMemcpyHostToDevice, c->stream));
+    return FEPB200_OK;
+}
+
+int upload_typetab(fepb200_ctx* c)
+{
+    if (!c->typetab_dirty || c->ntype == 0 || !c->have_params)
+    {
+        return FEPB200_OK;
+    }
+    const int           t = c->ntype;
+    std::vector<float4> tab((size_t)t * t);
+    const bool          gapsys = c->params.softcoreType == FEPB200_SC_GAPSYS;
+    for (int i = 0; i < t * t; i++)
+    {
+        const float c6 = c->nbfp[2 * i], c12 = c->nbfp[2 * i + 1];
+        float       sig6;
+        /* nb_free_energy.cpp:571-594; the division is done in fp32 like the mixed-precision build */
+        if (c6 > 0.0f && c12 > 0.0f)
+        {
+            sig6 = 0.5f * c12 / c6;
+            if (!gapsys && sig6 < c->params.sigma6Minimum)
+            {
+                sig6 = c->params.sigma6Minimum;
+            }
+        }
+        else
+        {
+            sig6 = gapsys ? c->params.gapsysSigma6VdW : c->params.sigma6WithInvalidSigma;
+        }
+        const float c6g = c->nbfp_grid.empty() ? 0.0f : c->nbfp_grid[2 * i];
+        tab[i]          = make_float4(c6, c12, sig6, c6g);
+    }
+    CU_CHECK(c, c->d_typetab.reserve(tab.size()));
+    CU_CHECK(c, cudaMemcpyAsync(c->d_typetab.ptr, tab.data(), tab.size() * sizeof(float4), cudaMemcpyHostToDevice,
+                                c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->ka.typetab    = c->d_typetab.ptr;
+    c->ka.ntype      = t;
+    c->typetab_dirty = false;
+    return FEPB200_OK;
+}
+
+template<typename T>
+int to_device(fepb200_ctx* c, DeviceArray<T>& d, const std::vector<T>& h)
+{
+    CU_CHECK(c, d.reserve(std::max<size_t>(h.size(), 1)));
+    if (!h.empty())
+    {
+        CU_CHECK(c, cudaMemcpyAsync(d.ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    }
+    return FEPB200_OK;
+}
+
+StepFlags step_flags(const fepb200_ctx* c, int flags)
+{
+    StepFlags sf;
+    sf.force   = (flags & FEPB200_DO_FORCE) != 0;
+    sf.shift   = sf.force && (flags & FEPB200_DO_SHIFTFORCE) != 0; /* nb_free_energy.cpp:1153-1164 */
+    sf.energy  = (flags & FEPB200_DO_POTENTIAL) != 0;
+    sf.foreign = (flags & FEPB200_DO_FOREIGNLAMBDA) != 0 && !c->pts.empty();
+    return sf;
+}
+
+int check_ready(fepb200_ctx* c)
+{
+    if (!c->have_params)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_params() has not been called");
+    }
+    if (c->ntype == 0)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_nbfp() has not been called");
+    }
+    if (!c->have_list)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_list() has not been called");
+    }
+    if (!c->have_lambda)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_lambdas() has not been called");
+    }
+    if (c->params.vdwtype == FEPB200_VDW_PME && c->nbfp_grid.empty())
+    {
+        return fail(c, FEPB200_ERR_STATE, "LJ-PME needs nbfp_grid in fepb200_set_nbfp()");
+    }
+    return upload_typetab(c);
+}
+
+} // namespace
+
+/* =========================================================================================== */
+extern "C" {
+
+int fepb200_create(fepb200_ctx** out, int device_ordinal)
+{
+    if (!out)
+    {
+        return fail(nullptr, FEPB200_ERR_INVALID_ARGUMENT, "ctx pointer is NULL");
+    }
+    *out      = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        return fail(nullptr, FEPB200_ERR_NO_DEVICE,
+                    "no CUDA device available; libfepb200 has no CPU implementation of this path");
+    }
+    if (device_ordinal < 0 || device_ordinal >= count)
+    {
+        return fail(nullptr, FEPB200_ERR_INVALID_ARGUMENT, "device ordinal %d out of range [0,%d)", device_ordinal,
+                    count);
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess)
+    {
+        return fail(nullptr, FEPB200_ERR_CUDA, "cudaGetDeviceProperties failed");
+    }
+    if (prop.major != 10)
+    {
+        return fail(nullptr, FEPB200_ERR_NO_DEVICE,
+                    "device %d (%s) is sm_%d%d; this library is built for sm_100a only", device_ordinal, prop.name,
+                    prop.major, prop.minor);
+    }
+    fepb200_ctx* c = new fepb200_ctx();
+    c->device      = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess
+        || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess
+        || c->d_counter.reserve(1) != cudaSuccess || cudaMemset(c->d_counter.ptr, 0, sizeof(unsigned int)) != cudaSuccess)
+    {
+        const int rc = fail(nullptr, FEPB200_ERR_CUDA, "CUDA initialisation failed: %s",
+                            cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return rc;
+    }
+    c->ka.done_counter = c->d_counter.ptr;
+    c->own_stream      = c->stream;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "fepb200 0.1 sm_100a %s %d SMs", prop.name, prop.multiProcessorCount);
+    c->description = buf;
+    *out           = c;
+    return FEPB200_OK;
+}
+
+int fepb200_destroy(fepb200_ctx* c)
+{
+    if (!c)
+    {
+        return FEPB200_OK;
+    }
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_typetab.release();
+    c->d_pts.release();
+    c->h_pts.release();
+    c->d_touched.release();
+    c->d_pair_j.release();
+    c->d_pair_e.release();
+    c->d_warp_hbase.release();
+    c->d_atom_ptr.release();
+    c->d_atom_idx.release();
+    c->d_red_idx.release();
+    c->d_key_job_ptr.release();
+    c->d_ent4.release();
+    c->d_red_jobs.release();
+    c->d_par4.release();
+    c->d_t4.release();
+    c->d_fi4.release();
+    c->d_ev2.release();
+    c->d_cta_part.release();
+    c->d_for_part.release();
+    c->d_job_part.release();
+    c->d_counter.release();
+    c->d_step_in.release();
+    c->d_result.release();
+    c->h_step_in.release();
+    c->h_result.release();
+    for (int i = 0; i < 4; i++)
+    {
+        if (c->ev_prof[i])
+        {
+            cudaEventDestroy(c->ev_prof[i]);
+        }
+    }
+    cudaEventDestroy(c->ev_start);
+    cudaEventDestroy(c->ev_stop);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return FEPB200_OK;
+}
+
+const char* fepb200_last_error(const fepb200_ctx* c)
+{
+    return c ? c->error.c_str() : g_create_error.c_str();
+}
+
+const char* fepb200_describe(const fepb200_ctx* c)
+{
+    return c ? c->description.c_str() : "fepb200 0.1 sm_100a (no context)";
+}
+
+int fepb200_set_stream(fepb200_ctx* c, void* stream)
+{
+    if (!c)
+    {
+        return FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaSetDevice(c->device);
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->stream = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
+    return FEPB200_OK;
+}
+
+int fepb200_set_params(fepb200_ctx* c, const fepb200_params* p)
+{
+    if (!c || !p)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "NULL argument");
+    }
+    /* nb_free_energy.cpp:1384-1386: only plain cut-off, reaction-field and Ewald-type electrostatics */
+    const bool ewald = eel_is_ewald(p->eeltype);
+    if (!(ewald || p->eeltype == FEPB200_EEL_CUT || eel_is_rf(p->eeltype)))
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "eeltype %d is not supported by the perturbed-pair kernel",
+                    p->eeltype);
+    }
+    if (p->lambdaPower != 1 && p->lambdaPower != 2)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "sc-power must be 1 or 2 (got %d)", p->lambdaPower);
+    }
+    if (p->softcoreType != FEPB200_SC_BEUTLER && p->softcoreType != FEPB200_SC_GAPSYS)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "unknown softcoreType %d", p->softcoreType);
+    }
+    cudaSetDevice(c->device);
+    c->params     = *p;
+    c->elec_ewald = ewald;
+    /* nb_free_energy.cpp:1324-1363 */
+    if (p->softcoreType == FEPB200_SC_BEUTLER)
+    {
+        c->softcore = (p->alphaCoulomb == 0.0f && p->alphaVdw == 0.0f) ? FEP_SC_NONE : FEP_SC_BEUTLER;
+    }
+    else
+    {
+        c->softcore = (p->gapsysScaleLinpointCoul == 0.0f && p->gapsysScaleLinpointVdW == 0.0f) ? FEP_SC_NONE
+                                                                                                  : FEP_SC_GAPSYS;
+    }
+    KernelArgs& k = c->ka;
+    k.epsfac      = p->epsfac;
+    k.rcoulomb    = p->rcoulomb;
+    k.rvdw        = p->rvdw;
+    k.rvdw_switch = p->rvdw_switch;
+    k.krf         = p->reactionFieldCoefficient;
+    k.crf         = p->reactionFieldShift;
+    k.sh_ewald    = p->sh_ewald;
+    k.sh_lj_ewald = p->sh_lj_ewald;
+    k.beta        = p->ewaldcoeff_q;
+    k.beta2       = p->ewaldcoeff_q * p->ewaldcoeff_q;
+    k.beta3       = k.beta2 * p->ewaldcoeff_q;
+    k.lj_coeff_sq = p->ewaldcoeff_lj * p->ewaldcoeff_lj;
+    k.lj_coeff6_div6 = k.lj_coeff_sq * k.lj_coeff_sq * k.lj_coeff_sq / 6.0f;
+    k.disp_cpot      = p->dispersion_shift_cpot;
+    k.rep_cpot       = p->repulsion_shift_cpot;
+    const float rmax = std::max(p->rcoulomb, p->rvdw);
+    k.rcut_max2      = rmax * rmax;
+    {
+        const double rc = p->rcoulomb, rv = p->rvdw;
+        k.rcoulomb6 = (float)(rc * rc * rc * rc * rc * rc);
+        k.rvdw6     = (float)(rv * rv * rv * rv * rv * rv);
+    }
+    k.alpha_c  = p->alphaCoulomb;
+    k.alpha_v  = p->alphaVdw;
+    k.gscale_c = p->gapsysScaleLinpointCoul;
+    k.gscale_v = p->gapsysScaleLinpointVdW;
+    k.vdw_ewald  = p->vdwtype == FEPB200_VDW_PME;
+    k.pot_switch = p->vdw_modifier == FEPB200_MOD_POTSWITCH;
+    k.rf_type    = !ewald;
+    if (k.pot_switch)
+    {
+        /* nb_free_energy.cpp:361-370 */
+        const double d = (double)p->rvdw - (double)p->rvdw_switch;
+        k.sw_v3        = (float)(-10.0 / (d * d * d));
+        k.sw_v4        = (float)(15.0 / (d * d * d * d));
+        k.sw_v5        = (float)(-6.0 / (d * d * d * d * d));
+        k.sw_f2        = (float)(-30.0 / (d * d * d));
+        k.sw_f3        = (float)(60.0 / (d * d * d * d));
+        k.sw_f4        = (float)(-30.0 / (d * d * d * d * d));
+    }
+    else
+    {
+        k.sw_v3 = k.sw_v4 = k.sw_v5 = k.sw_f2 = k.sw_f3 = k.sw_f4 = 0.0f;
+    }
+    c->have_params   = true;
+    c->typetab_dirty = true;
+    refresh_points(c);
+    if (c->have_list && !c->pts.empty())
+    {
+        return upload_points(c);
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_set_nbfp(fepb200_ctx* c, int ntype, const float* nbfp, const float* nbfp_grid)
+{
+    if (!c || ntype <= 0 || !nbfp)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_nbfp: bad arguments");
+    }
+    cudaSetDevice(c->device);
+    if (c->have_list && ntype != c->ntype)
+    {
+        c->have_list = false; /* types of the uploaded atoms refer to the old table */
+    }
+    c->ntype = ntype;
+    c->nbfp.assign(nbfp, nbfp + 2 * (size_t)ntype * ntype);
+    if (nbfp_grid)
+    {
+        c->nbfp_grid.assign(nbfp_grid, nbfp_grid + 2 * (size_t)ntype * ntype);
+    }
+    else
+    {
+        c->nbfp_grid.clear();
+    }
+    c->typetab_dirty = true;
+    return FEPB200_OK;
+}
+
+int fepb200_set_atoms(fepb200_ctx* c, int natoms, const float* qA, const float* qB, const int* typeA,
+                      const int* typeB)
+{
+    if (!c || natoms < 0 || (natoms > 0 && (!qA || !qB || !typeA || !typeB)))
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_atoms: bad arguments");
+    }
+    if (c->ntype == 0)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_nbfp() must precede fepb200_set_atoms()");
+    }
+    for (int a = 0; a < natoms; a++)
+    {
+        if (typeA[a] < 0 || typeA[a] >= c->ntype || typeB[a] < 0 || typeB[a] >= c->ntype)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "atom %d has a type outside [0,%d)", a, c->ntype);
+        }
+    }
+    c->natoms = natoms;
+    c->qA.assign(qA, qA + natoms);
+    c->qB.assign(qB, qB + natoms);
+    c->typeA.assign(typeA, typeA + natoms);
+    c->typeB.assign(typeB, typeB + natoms);
+    c->have_list = false;
+    return FEPB200_OK;
+}
+
+int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, const int* shift, const int* jindex,
+                     const int* jjnr, const int* excl_fep, int ngrp, int rank, int nranks)
+{
+    if (!c || nri < 0 || ngrp < 1 || nranks < 1 || rank < 0 || rank >= nranks)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: bad arguments");
+    }
+    if (nri > 0 && (!iinr || !gid || !shift || !jindex))
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: NULL list array");
+    }
+    if (c->natoms == 0 && nri > 0)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_atoms() must precede fepb200_set_list()");
+    }
+    cudaSetDevice(c->device);
+    const long long nrj_total = nri > 0 ? jindex[nri] : 0;
+    if (nri > 0 && (jindex[0] != 0 || nrj_total < 0 || (nrj_total > 0 && !jjnr)))
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: jindex must start at 0");
+    }
+    if (nrj_total >= (1LL << 31) - 64)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than 2^31 pairs in one list");
+    }
+    for (int n = 0; n < nri; n++)
+    {
+        if (jindex[n + 1] < jindex[n] || iinr[n] < 0 || iinr[n] >= c->natoms || gid[n] < 0 || gid[n] >= ngrp
+            || shift[n] < 0 || shift[n] >= FEP_NUM_SHIFT)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: i-entry %d is malformed", n);
+        }
+    }
+    for (long long k = 0; k < nrj_total; k++)
+    {
+        if (jjnr[k] < 0 || jjnr[k] >= c->natoms)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: jjnr[%lld] out of range", k);
+        }
+    }
+
+    /* touched atoms of the FULL list (same numbering on every rank; mirrors the reduction mask
+     * of setReductionMaskFromFepPairlist, freeenergydispatch.cpp:74-89) */
+    c->compact_of.assign(c->natoms, -1);
+    for (int n = 0; n < nri; n++)
+    {
+        c->compact_of[iinr[n]] = 0;
+    }
+    for (long long k = 0; k < nrj_total; k++)
+    {
+        c->compact_of[jjnr[k]] = 0;
+    }
+    c->touched.clear();
+    for (int a = 0; a < c->natoms; a++)
+    {
+        if (c->compact_of[a] == 0)
+        {
+            c->compact_of[a] = (int)c->touched.size();
+            c->touched.push_back(a);
+        }
+    }
+    const int nT = (int)c->touched.size();
+
+    /* this rank's contiguous range of i-entries, balanced by pair count */
+    int e0 = 0, e1 = nri;
+    if (nranks > 1)
+    {
+        std::vector<int> first(nranks + 1, nri);
+        first[0]               = 0;
+        const long long target = (nrj_total + nranks - 1) / nranks;
+        int             dest   = 0;
+        long long       have   = 0;
+        for (int n = 0; n < nri; n++)
+        {
+            const long long nrj = jindex[n + 1] - jindex[n];
+            if (dest + 1 < nranks && have > 0 && have + nrj - target > target - have)
+            {
+                dest++;
+                first[dest] = n;
+                have        = 0;
+            }
+            have += nrj;
+        }
+        e0 = first[rank];
+        e1 = first[rank + 1];
+    }
+    const int E  = e1 - e0;
+    const int j0 = E > 0 ? jindex[e0] : 0;
+    const int P  = E > 0 ? jindex[e1] - j0 : 0;
+
+    std::vector<int>  pair_j(P), pair_e(P);
+    std::vector<int4> ent4(E);
+    for (int n = 0; n < E; n++)
+    {
+        const int g = e0 + n;
+        ent4[n]     = make_int4(c->compact_of[iinr[g]], shift[g], gid[g], 0);
+        for (int k = jindex[g]; k < jindex[g + 1]; k++)
+        {
+            const bool excluded = excl_fep && excl_fep[k] == 0;
+            pair_j[k - j0]      = c->compact_of[jjnr[k]] | (excluded ? (int)0x80000000u : 0);
+            pair_e[k - j0]      = n;
+        }
+    }
+
+    /* segments: maximal runs of one i-entry inside one 32-pair warp */
+    const int        n_warps = (P + 31) / 32;
+    std::vector<int> warp_hbase(std::max(n_warps, 1), 0), seg_entry;
+    seg_entry.reserve((size_t)E + n_warps);
+    for (int w = 0; w < n_warps; w++)
+    {
+        warp_hbase[w]  = (int)seg_entry.size();
+        const int last = std::min(P, 32 * w + 32);
+        for (int s = 32 * w; s < last; s++)
+        {
+            if (s == 32 * w || pair_e[s] != pair_e[s - 1])
+            {
+                seg_entry.push_back(pair_e[s]);
+            }
+        }
+    }
+    const int H = (int)seg_entry.size();
+
+    /* per-atom contribution lists: pair slots (as j) then segments (as i), ascending */
+    std::vector<int> atom_ptr(nT + 1, 0), atom_idx((size_t)P + H);
+    for (int s = 0; s < P; s++)
+    {
+        atom_ptr[(pair_j[s] & 0x7fffffff) + 1]++;
+    }
+    for (int h = 0; h < H; h++)
+    {
+        atom_ptr[ent4[seg_entry[h]].x + 1]++;
+    }
+    for (int a = 0; a < nT; a++)
+    {
+        atom_ptr[a + 1] += atom_ptr[a];
+    }
+    {
+        std::vector<int> fill(atom_ptr.begin(), atom_ptr.end() - 1);
+        for (int s = 0; s < P; s++)
+        {
+            atom_idx[fill[pair_j[s] & 0x7fffffff]++] = s;
+        }
+        for (int h = 0; h < H; h++)
+        {
+            atom_idx[fill[ent4[seg_entry[h]].x]++] = P + h;
+        }
+    }
+
+    /* reduction jobs: segments per shift vector, then per energy-group pair, in chunks */
+    std::vector<RedJob> jobs;
+    std::vector<int>    red_idx, key_job_ptr(FEP_NUM_SHIFT + ngrp + 1, 0);
+    red_idx.reserve(2 * (size_t)H);
+    for (int kind = 0; kind < 2; kind++)
+    {
+        const int        nkeys = kind == 0 ? FEP_NUM_SHIFT : ngrp;
+        std::vector<int> cnt(nkeys + 1, 0);
+        for (int h = 0; h < H; h++)
+        {
+            const int4 e = ent4[seg_entry[h]];
+            cnt[(kind == 0 ? e.y : e.z) + 1]++;
+        }
+        for (int k = 0; k < nkeys; k++)
+        {
+            cnt[k + 1] += cnt[k];
+        }
+        const size_t     base = red_idx.size();
+        std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+        red_idx.resize(base + H);
+        for (int h = 0; h < H; h++)
+        {
+            const int4 e                                       = ent4[seg_entry[h]];
+            red_idx[base + fill[kind == 0 ? e.y : e.z]++] = h;
+        }
+        for (int k = 0; k < nkeys; k++)
+        {
+            key_job_ptr[(kind == 0 ? 0 : FEP_NUM_SHIFT) + k] = (int)jobs.size();
+            for (int b = cnt[k]; b < cnt[k + 1]; b += FEP_RED_CHUNK)
+            {
+                RedJob j;
+                j.begin = (int)base + b;
+                j.end   = (int)base + std::min(cnt[k + 1], b + FEP_RED_CHUNK);
+                j.key   = k;
+                j.kind  = kind;
+                jobs.push_back(j);
+            }
+        }
+        if (kind == 0)
+        {
+            c->ka.n_shift_jobs = (int)jobs.size();
+        }
+    }
+    key_job_ptr[FEP_NUM_SHIFT + ngrp] = (int)jobs.size();
+
+    /* per-atom parameters in compact order */
+    std::vector<float4> par4(nT);
+    for (int k = 0; k < nT; k++)
+    {
+        const int a = c->touched[k];
+        par4[k]     = make_float4(c->qA[a], c->qB[a], int_bits_as_float(c->typeA[a]), int_bits_as_float(c->typeB[a]));
+    }
+
+    int rc;
+    if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair_j, pair_j))
+        || (rc = to_device(c, c->d_pair_e, pair_e)) || (rc = to_device(c, c->d_ent4, ent4))
+        || (rc = to_device(c, c->d_warp_hbase, warp_hbase)) || (rc = to_device(c, c->d_atom_ptr, atom_ptr))
+        || (rc = to_device(c, c->d_atom_idx, atom_idx)) || (rc = to_device(c, c->d_red_jobs, jobs))
+        || (rc = to_device(c, c->d_red_idx, red_idx)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
+        || (rc = to_device(c, c->d_par4, par4)))
+    {
+        return rc;
+    }
+    CU_CHECK(c, c->d_t4.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_fi4.reserve(std::max(H, 1)));
+    CU_CHECK(c, c->d_ev2.reserve(std::max(H, 1)));
+    CU_CHECK(c, c->d_job_part.reserve(4 * std::max<size_t>(jobs.size(), 1)));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream)); /* host vectors go out of scope */
+
+    KernelArgs& k = c->ka;
+    k.n_pairs     = P;
+    k.n_entries   = E;
+    k.n_segments  = H;
+    k.n_touched   = nT;
+    k.n_gid       = ngrp;
+    k.n_cta       = (P + FEP_CTA - 1) / FEP_CTA;
+    k.n_red_jobs  = (int)jobs.size();
+    k.par4        = c->d_par4.ptr;
+    k.pair_j      = c->d_pair_j.ptr;
+    k.pair_e      = c->d_pair_e.ptr;
+    k.ent4        = c->d_ent4.ptr;
+    k.warp_hbase  = c->d_warp_hbase.ptr;
+    k.t4          = c->d_t4.ptr;
+    k.fi4         = c->d_fi4.ptr;
+    k.ev2         = c->d_ev2.ptr;
+    k.job_part    = c->d_job_part.ptr;
+    k.atom_ptr    = c->d_atom_ptr.ptr;
+    k.atom_idx    = c->d_atom_idx.ptr;
+    k.red_jobs    = c->d_red_jobs.ptr;
+    k.red_idx     = c->d_red_idx.ptr;
+    k.key_job_ptr = c->d_key_job_ptr.ptr;
+
+    fepb200_layout& l = c->layout;
+    l.natoms          = c->natoms;
+    l.ntouched        = nT;
+    l.nri             = E;
+    l.nrj             = P;
+    l.nri_total       = nri;
+    l.nrj_total       = nrj_total;
+    l.nenergrp        = ngrp;
+    l.nforeign        = (int)c->all_c.size();
+    c->first_entry    = e0;
+    c->n_segments     = H;
+    c->have_list      = true;
+    if ((rc = prepare_buffers(c)) != FEPB200_OK)
+    {
+        c->have_list = false;
+        return rc;
+    }
+    if (!c->pts.empty())
+    {
+        return upload_points(c);
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_get_list(const fepb200_ctx* cc, int* first_entry, int* iinr, int* gid, int* shift, int* jindex,
+                     int* jjnr, int* excl_fep)
+{
+    fepb200_ctx* c = const_cast<fepb200_ctx*>(cc);
+    if (!c || !c->have_list)
+    {
+        return fail(c, FEPB200_ERR_STATE, "no list has been set");
+    }
+    cudaSetDevice(c->device);
+    if (first_entry)
+    {
+        *first_entry = c->first_entry;
+    }
+    const int E = c->layout.nri;
+    const int P = (int)c->layout.nrj;
+    /* read the list back FROM THE DEVICE and undo the compaction */
+    if (iinr || gid || shift)
+    {
+        std::vector<int4> ent4(E);
+        if (E > 0)
+        {
+            CU_CHECK(c, cudaMemcpy(ent4.data(), c->d_ent4.ptr, E * sizeof(int4), cudaMemcpyDeviceToHost));
+        }
+        for (int n = 0; n < E; n++)
+        {
+            if (iinr)
+            {
+                iinr[n] = c->touched[ent4[n].x];
+            }
+            if (shift)
+            {
+                shift[n] = ent4[n].y;
+            }
+            if (gid)
+            {
+                gid[n] = ent4[n].z;
+            }
+        }
+    }
+    if (jindex || jjnr || excl_fep)
+    {
+        std::vector<int> pair_j(P), pair_e(P);
+        if (P > 0)
+        {
+            CU_CHECK(c, cudaMemcpy(pair_j.data(), c->d_pair_j.ptr, P * sizeof(int), cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(pair_e.data(), c->d_pair_e.ptr, P * sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        if (jindex)
+        {
+            std::fill(jindex, jindex + E + 1, 0);
+            for (int s = 0; s < P; s++)
+            {
+                jindex[pair_e[s] + 1]++;
+            }
+            for (int n = 0; n < E; n++)
+            {
+                jindex[n + 1] += jindex[n];
+            }
+        }
+        for (int s = 0; s < P; s++)
+        {
+            if (jjnr)
+            {
+                jjnr[s] = c->touched[pair_j[s] & 0x7fffffff];
+            }
+            if (excl_fep)
+            {
+                excl_fep[s] = pair_j[s] < 0 ? 0 : 1;
+            }
+        }
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_touched_atoms(const fepb200_ctx* c, int* atoms)
+{
+    if (!c || !c->have_list || !atoms)
+    {
+        return fail(const_cast<fepb200_ctx*>(c), FEPB200_ERR_STATE, "no list has been set");
+    }
+    std::copy(c->touched.begin(), c->touched.end(), atoms);
+    return FEPB200_OK;
+}
+
+int fepb200_result_layout(const fepb200_ctx* c, fepb200_layout* layout)
+{
+    if (!c || !layout || !c->have_list)
+    {
+        return fail(const_cast<fepb200_ctx*>(c), FEPB200_ERR_STATE, "no list has been set");
+    }
+    *layout = c->layout;
+    return FEPB200_OK;
+}
+
+int fepb200_set_lambdas(fepb200_ctx* c, const float* lambda, int n_foreign, const float* all_c, const float* all_v)
+{
+    if (!c || !lambda || n_foreign < 0 || (n_foreign > 0 && (!all_c || !all_v)))
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_lambdas: bad arguments");
+    }
+    if (n_foreign + 1 > FEP_MAX_POINTS)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "at most %d foreign lambda points", FEP_MAX_POINTS - 1);
+    }
+    cudaSetDevice(c->device);
+    c->lam_c = lambda[FEPB200_LAMBDA_COUL];
+    c->lam_v = lambda[FEPB200_LAMBDA_VDW];
+    c->all_c.assign(all_c, all_c + n_foreign);
+    c->all_v.assign(all_v, all_v + n_foreign);
+    c->have_lambda = true;
+    refresh_points(c);
+    if (c->have_list)
+    {
+        if (c->layout.nforeign != n_foreign)
+        {
+            c->layout.nforeign = n_foreign;
+            const int rc       = prepare_buffers(c);
+            if (rc != FEPB200_OK)
+            {
+                return rc;
+            }
+        }
+        if (!c->pts.empty())
+        {
+            return upload_points(c);
+        }
+    }
+    return FEPB200_OK;
+}
+
+/* ---- step ------------------------------------------------------------------------------- */
+static int stage_head(fepb200_ctx* c, const float* shiftvec)
+{
+    DynHead* head = reinterpret_cast<DynHead*>(c->h_step_in.ptr);
+    for (int s = 0; s < FEP_NUM_SHIFT; s++)
+    {
+        head->shiftvec[s] = make_float4(shiftvec[3 * s], shiftvec[3 * s + 1], shiftvec[3 * s + 2], 0.0f);
+    }
+    head->cur = c->cur;
+    return FEPB200_OK;
+}
+
+int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
+{
+    if (!c || !x || !shiftvec)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_upload_x: NULL argument");
+    }
+    int rc = check_ready(c);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    cudaSetDevice(c->device);
+    /* the previous H2D copy out of the pinned buffer must be done before it is overwritten */
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    stage_head(c, shiftvec);
+    float4*   pos = reinterpret_cast<float4*>(c->h_step_in.ptr + sizeof(DynHead));
+    const int nT  = c->layout.ntouched;
+    const int* t  = c->touched.data();
+    for (int k = 0; k < nT; k++)
+    {
+        const float* xa = x + 3 * (size_t)t[k];
+        pos[k]          = make_float4(xa[0], xa[1], xa[2], 0.0f);
+    }
+    CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr, c->h_step_in.ptr, sizeof(DynHead) + sizeof(float4) * (size_t)nT,
+                                cudaMemcpyHostToDevice, c->stream));
+    return FEPB200_OK;
+}
+
+int fepb200_gather_x_device(fepb200_ctx* c, const float* d_x, const float* shiftvec)
+{
+    if (!c || !d_x || !shiftvec)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_gather_x_device: NULL argument");
+    }
+    int rc = check_ready(c);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    cudaSetDevice(c->device);
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    stage_head(c, shiftvec);
+    CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr, c->h_step_in.ptr, sizeof(DynHead), cudaMemcpyHostToDevice,
+                                c->stream));
+    const int err = fep_launch_gather_x(d_x, c->d_touched.ptr,
+                                        reinterpret_cast<float4*>(c->d_step_in.ptr + sizeof(DynHead)),
+                                        c->layout.ntouched, c->stream, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "gather kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
+{
+    if (!c)
+    {
+        return FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    int rc = check_ready(c);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    cudaSetDevice(c->device);
+    cudaStream_t    stream = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
+    const StepFlags sf     = step_flags(c, flags);
+    CU_CHECK(c, cudaEventRecord(c->ev_start, stream));
+    const int err = fep_launch_step(&c->ka, c->softcore, c->elec_ewald, sf, stream, &c->launches,
+                                    c->profiling ? c->ev_prof : nullptr);
+    c->profiled   = c->profiling;
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    CU_CHECK(c, cudaEventRecord(c->ev_stop, stream));
+    c->timed = true;
+    return FEPB200_OK;
+}
+
+int fepb200_wait(fepb200_ctx* c)
+{
+    if (!c)
+    {
+        return FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaSetDevice(c->device);
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    return FEPB200_OK;
+}
+
+int fepb200_result_device_ptrs(const fepb200_ctx* c, void** d_f32, void** d_f64)
+{
+    if (!c || !c->have_list)
+    {
+        return fail(const_cast<fepb200_ctx*>(c), FEPB200_ERR_STATE, "no list has been set");
+    }
+    if (d_f32)
+    {
+        *d_f32 = c->ka.res_f32;
+    }
+    if (d_f64)
+    {
+        *d_f64 = c->ka.res_f64;
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double* Vc, double* Vv, double* dvdl,
+                     double* foreign_energy, double* foreign_dvdl)
+{
+    if (!c)
+    {
+        return FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    int rc = check_ready(c);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    cudaSetDevice(c->device);
+    const StepFlags       sf    = step_flags(c, flags);
+    const fepb200_layout& l     = c->layout;
+    const bool            clear = (flags & FEPB200_CLEAR_OUTPUTS) != 0;
+    if ((sf.force && !f) || (sf.shift && !fshift) || (sf.energy && (!Vc || !Vv)) || !dvdl
+        || (sf.foreign && (!foreign_energy || !foreign_dvdl)))
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_download: an output requested by flags is NULL");
+    }
+    const size_t bytes = c->res_f64_bytes + (sf.force ? c->res_f32_bytes : 0);
+    CU_CHECK(c, cudaMemcpyAsync(c->h_result.ptr, c->d_result.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    const double* r64 = reinterpret_cast<const double*>(c->h_result.ptr);
+    const float*  r32 = reinterpret_cast<const float*>(c->h_result.ptr + c->res_f64_bytes);
+    if (sf.force)
+    {
+        if (clear)
+        {
+            std::memset(f, 0, sizeof(float) * 3 * (size_t)l.natoms);
+        }
+        const int* t = c->touched.data();
+        for (int k = 0; k < l.ntouched; k++)
+        {
+            float* fa = f + 3 * (size_t)t[k];
+            fa[0] += r32[3 * k];
+            fa[1] += r32[3 * k + 1];
+            fa[2] += r32[3 * k + 2];
+        }
+        if (sf.shift)
+        {
+            for (int i = 0; i < 3 * FEP_NUM_SHIFT; i++)
+            {
+                fshift[i] = (clear ? 0.0f : fshift[i]) + r32[l.off_fshift + i];
+            }
+        }
+    }
+    if (sf.energy)
+    {
+        for (int g = 0; g < l.nenergrp; g++)
+        {
+            Vc[g] = (clear ? 0.0 : Vc[g]) + r64[l.off_vc + g];
+            Vv[g] = (clear ? 0.0 : Vv[g]) + r64[l.off_vv + g];
+        }
+    }
+    dvdl[0] = (clear ? 0.0 : dvdl[0]) + r64[l.off_dvdl];
+    dvdl[1] = (clear ? 0.0 : dvdl[1]) + r64[l.off_dvdl + 1];
+    if (sf.foreign)
+    {
+        /* the reference stores (not accumulates) these per lambda point, freeenergydispatch.cpp:298-305,
+         * but several localities add up in ForeignLambdaTerms::accumulate: keep += semantics */
+        for (int i = 0; i <= l.nforeign; i++)
+        {
+            foreign_energy[i] = (clear ? 0.0 : foreign_energy[i]) + r64[l.off_foreign_e + i];
+            foreign_dvdl[2 * i] = (clear ? 0.0 : foreign_dvdl[2 * i]) + r64[l.off_foreign_dvdl + 2 * i];
+            foreign_dvdl[2 * i + 1] =
+                    (clear ? 0.0 : foreign_dvdl[2 * i + 1]) + r64[l.off_foreign_dvdl + 2 * i + 1];
+        }
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_compute(fepb200_ctx* c, const float* x, const float* shiftvec, int flags, float* f, float* fshift,
+                    double* Vc, double* Vv, double* dvdl, double* foreign_energy, double* foreign_dvdl)
+{
+    int rc = fepb200_upload_x(c, x, shiftvec);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    rc = fepb200_launch(c, flags, nullptr);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    return fepb200_download(c, flags, f, fshift, Vc, Vv, dvdl, foreign_energy, foreign_dvdl);
+}
+
+int fepb200_set_profiling(fepb200_ctx* c, int on)
+{
+    if (!c)
+    {
+        return FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaSetDevice(c->device);
+    if (on && !c->ev_prof[0])
+    {
+        for (int i = 0; i < 4; i++)
+        {
+            CU_CHECK(c, cudaEventCreate(&c->ev_prof[i]));
+        }
+    }
+    c->profiling = on != 0;
+    return FEPB200_OK;
+}
+
+int fepb200_kernel_ms(fepb200_ctx* c, float* ms)
+{
+    if (!c || !ms || !c->profiled)
+    {
+        return fail(c, FEPB200_ERR_STATE, "the last launch was not profiled (fepb200_set_profiling)");
+    }
+    cudaSetDevice(c->device);
+    CU_CHECK(c, cudaEventSynchronize(c->ev_prof[3]));
+    for (int i = 0; i < 3; i++)
+    {
+        CU_CHECK(c, cudaEventElapsedTime(&ms[i], c->ev_prof[i], c->ev_prof[i + 1]));
+    }
+    return FEPB200_OK;
+}
+
+long long fepb200_launch_count(const fepb200_ctx* c)
+{
+    return c ? c->launches : 0;
+}
+
+int fepb200_last_launch_ms(fepb200_ctx* c, float* ms)
+{
+    if (!c || !ms || !c->timed)
+    {
+        return fail(c, FEPB200_ERR_STATE, "no launch has been timed");
+    }
+    cudaSetDevice(c->device);
+    CU_CHECK(c, cudaEventSynchronize(c->ev_stop));
+    CU_CHECK(c, cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
+    return FEPB200_OK;
+}
+
+} /* extern "C" */

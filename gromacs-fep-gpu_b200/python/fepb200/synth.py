@@ -376,7 +376,7 @@ def scaled_spec(name: str, box: float, n_blobs: int, blob_size: int | None = Non
 
 def random_problem(seed: int, params: Params, *, natoms=96, nri=40, max_j=70, ntype=5, n_groups=2,
                    box=1.6, n_foreign=0, lambda_coul=0.35, lambda_vdw=0.6, frac_excluded=0.15,
-                   frac_self=0.05, frac_overlap=0.03, frac_cutoff=0.03, dtype=np.float32) -> Problem:
+                   frac_self=0.05, frac_overlap=0.03, frac_cutoff=0.03, min_overlap=1e-7, dtype=np.float32) -> Problem:
     """A small unphysical problem that hits every branch: random types (some with zero c6/c12 in
     one or both states), random charges (some zero), all 45 shift vectors, several energy-group
     pairs, excluded pairs inside and beyond the cut-off, self pairs, overlapping atoms and pairs
@@ -417,7 +417,7 @@ def random_problem(seed: int, params: Params, *, natoms=96, nri=40, max_j=70, nt
             elif u < frac_self + frac_overlap:
                 # move atom j on top of the shifted i atom
                 d = rng.normal(size=3)
-                d *= rng.uniform(1e-7, 2e-3) / np.linalg.norm(d)
+                d *= rng.uniform(min_overlap, max(2e-3, 2 * min_overlap)) / np.linalg.norm(d)
                 if js[k] != i:
                     x32[js[k]] = (x32[i].astype(np.float64) + sv[s] + d).astype(np.float32)
             elif u < frac_self + frac_overlap + frac_cutoff:

@@ -136,6 +136,12 @@ const char* fepb200_last_error(const fepb200_ctx* ctx);
 /* Library/device description, e.g. "fepb200 0.1 sm_100a NVIDIA B200 148 SMs". */
 const char* fepb200_describe(const fepb200_ctx* ctx);
 
+/* Makes every later operation of the context (copies, kernels, timing events) use the
+ * caller's cudaStream_t instead of the context's own stream, the way the reference hands its
+ * per-locality DeviceStream to the nbnxm GPU module (nbnxm_gpu_data_mgmt.cpp:404-423).
+ * NULL restores the context's own stream.  The context's previous stream is drained first. */
+int fepb200_set_stream(fepb200_ctx* ctx, void* stream);
+
 /* ---- constants (init time) --------------------------------------------- */
 /* Replaces cuda_copy_fepparams() (nbnxm/gpu_data_mgmt.h:74-85) and the reads at
  * nb_free_energy.cpp:323-396. */
@@ -212,6 +218,12 @@ int fepb200_download(fepb200_ctx* ctx, int flags, float* f, float* fshift, doubl
  * the launching stream (valid after fepb200_wait()). */
 long long fepb200_launch_count(const fepb200_ctx* ctx);
 int       fepb200_last_launch_ms(fepb200_ctx* ctx, float* ms);
+/* Profiling mode (replaces the reference's GpuRegionTimer fep_k, gpu_types_common.h:275-276):
+ * when on, fepb200_launch() also records CUDA events between its kernels and
+ * fepb200_kernel_ms() returns ms[3] = device time of {current-lambda pass kernel,
+ * foreign-lambda kernel, epilogue kernel} of the last launch. */
+int fepb200_set_profiling(fepb200_ctx* ctx, int on);
+int fepb200_kernel_ms(fepb200_ctx* ctx, float* ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,346 @@
+"""Parity of the sm_100a path with the CPU oracle, through the C-ABI (libfepb200.so).
+
+Tolerances are the ones BASELINE.json's north_star states, checked against a DOUBLE-precision
+oracle (the reference kernel itself, oracle/_ref/libfepref_dp.so, when it travelled to this box;
+else oracle/fep_oracle.c which is pinned to it by tests/test_oracle.py):
+
+  FORCE_RTOL  = 1e-5   per-atom forces, relative RMS over the touched atoms
+  ENERGY_RTOL = 1e-4   dV/dlambda, Vc/Vvdw and every foreign-lambda energy, relative to the
+                       magnitude of the quantity (with the floor described in `_scalar_close`)
+  lists and pair counts: bit-exact
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fepb200 import params as P
+from fepb200.synth import SPECS, make_system, random_problem, scaled_spec
+from kat_cases import KAT_FLAGS, NUM_CASES, kat_problem
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-5
+ENERGY_RTOL = 1e-4
+ALL = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "nb_free_energy_kat.json")) as fh:
+    GOLDEN = {c["index"]: c for c in json.load(fh)["cases"]}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from fepb200.lib import FepContext
+
+    c = FepContext(0)
+    yield c
+    c.close()
+
+
+def _oracle():
+    from oracle import oracle
+
+    return oracle
+
+
+def _force_rms(f, ref):
+    ref = np.asarray(ref, float)
+    den = np.sqrt(np.mean(ref**2))
+    return np.sqrt(np.mean((np.asarray(f, float) - ref) ** 2)) / max(den, 1e-30)
+
+
+def _scalar_close(a, b, rtol, what, floor=0.0):
+    """|a-b| <= rtol * max(|b|, floor) elementwise; `floor` is the magnitude of the terms the
+    quantity is a (cancelling) sum of, when the caller knows it."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = np.maximum(np.abs(b), floor)
+    bad = np.abs(a - b) > rtol * scale
+    assert not np.any(bad), f"{what}: got {a[bad]} want {b[bad]} (rel {np.abs(a - b)[bad] / scale[bad]})"
+
+
+def _check(out, ref, flags, force_rtol=FORCE_RTOL, energy_rtol=ENERGY_RTOL, label=""):
+    if flags & P.DO_FORCE:
+        rms = _force_rms(out["f"], ref["f"])
+        assert rms <= force_rtol, f"{label} force rel-RMS {rms:.3e}"
+        if flags & P.DO_SHIFTFORCE:
+            sc = np.max(np.abs(ref["f"])) if ref["f"].size else 1.0
+            assert np.max(np.abs(out["fshift"] - ref["fshift"])) <= 50 * force_rtol * max(sc, 1e-30), f"{label} fshift"
+    if flags & P.DO_POTENTIAL:
+        # energy-group pairs: relative to the largest group-pair energy of the same kind
+        for key in ("Vc", "Vv"):
+            floor = np.max(np.abs(ref[key])) * 1e-2 if ref[key].size else 0.0
+            _scalar_close(out[key], ref[key], energy_rtol, f"{label} {key}", floor)
+    floor = 1e-2 * np.max(np.abs(ref["dvdl"]))
+    _scalar_close(out["dvdl"], ref["dvdl"], energy_rtol, f"{label} dvdl", floor)
+    if flags & P.DO_FOREIGNLAMBDA:
+        floor = 1e-2 * np.max(np.abs(ref["foreign_energy"]))
+        _scalar_close(out["foreign_energy"], ref["foreign_energy"], energy_rtol, f"{label} foreign E", floor)
+        floor = 1e-2 * np.max(np.abs(ref["foreign_dvdl"]))
+        _scalar_close(out["foreign_dvdl"], ref["foreign_dvdl"], energy_rtol, f"{label} foreign dvdl", floor)
+
+
+def _run(ctx, prob, flags=ALL):
+    ctx.set_problem(prob)
+    return ctx.compute(prob.x, prob.shiftvec, flags)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own 72 known-answer cases, in float32 through the GPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("index", range(NUM_CASES))
+def test_reference_golden_vectors(ctx, index):
+    prob = kat_problem(index, np.float32)
+    out = _run(ctx, prob, KAT_FLAGS)
+    g = GOLDEN[index]
+    # same layout as the oracle result
+    ref = dict(f=np.array(g["forces"]), Vc=np.array([g["ECoul"]]), Vv=np.array([g["EVdw"]]),
+               dvdl=np.array([g["dVdlCoul"], g["dVdlVdw"]]))
+    fs = np.zeros((45, 3))
+    fs[0] = g["shift_force_central"]
+    ref["fshift"] = fs
+    # the reference runs these in float at relative 1e-6 of the magnitude; four atoms, no sums
+    assert _force_rms(out["f"], ref["f"]) < 5e-6
+    scale = max(abs(g["ECoul"]), abs(g["EVdw"]), 1e-3)
+    assert abs(out["Vc"][0] - g["ECoul"]) < 5e-6 * scale
+    assert abs(out["Vv"][0] - g["EVdw"]) < 5e-6 * scale
+    dscale = max(abs(g["dVdlCoul"]), abs(g["dVdlVdw"]), scale)
+    assert abs(out["dvdl"][0] - g["dVdlCoul"]) < 5e-6 * dscale
+    assert abs(out["dvdl"][1] - g["dVdlVdw"]) < 5e-6 * dscale
+    assert np.max(np.abs(out["fshift"] - fs)) < 5e-6 * np.max(np.abs(ref["f"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# random problems over the whole template space
+# ------------------------------------------------------------------------------------------------
+def _param_grid():
+    grid = []
+    for sc in ("beutler", "gapsys"):
+        for coul, vdw, mod in (("pme", "cut", "potshift"), ("rf", "cut", "potshift"), ("cut", "cut", "potswitch"),
+                               ("pme", "pme", "potshift"), ("pme", "cut", "forceswitch"), ("rf", "cut", "none")):
+            for power in (1, 2):
+                for sccoul in (False, True):
+                    grid.append((sc, coul, vdw, mod, power, sccoul))
+    return grid
+
+
+@pytest.mark.parametrize("sc,coul,vdw,mod,power,sccoul", _param_grid())
+def test_random_problems_match_oracle(ctx, sc, coul, vdw, mod, power, sccoul):
+    prm = P.make_params(coulombtype=coul, vdwtype=vdw, vdw_modifier=mod, rvdw_switch=0.8 if "switch" in mod else 0.0,
+                        softcore=sc, sc_alpha=0.5, sc_power=power, sc_coul=sccoul)
+    seed = 31 * len(sc) + 7 * len(coul) + 3 * len(mod) + power + 2 * sccoul
+    # no overlapping atoms here: with r ~ 1e-6 two or three pairs carry forces of 1e20 and nothing
+    # else would be tested (overlaps have their own test below)
+    prob = random_problem(2000 + seed, prm, natoms=400, nri=120, n_foreign=6, frac_overlap=0.0)
+    out = _run(ctx, prob)
+    ref = _oracle().run_best(prob, ALL)
+    _check(out, ref, ALL, label=f"{sc}/{coul}/{vdw}/{mod}/p{power}/sccoul={sccoul}")
+
+
+@pytest.mark.parametrize("sc", ["beutler", "gapsys"])
+@pytest.mark.parametrize("coul", ["pme", "rf"])
+def test_overlapping_atoms_and_clamps(ctx, sc, coul):
+    prm = P.make_params(coulombtype=coul, softcore=sc, sc_alpha=0.5)
+    prob = random_problem(9, prm, natoms=300, nri=60, n_foreign=3, frac_overlap=0.05, min_overlap=2e-4)
+    out = _run(ctx, prob)
+    ref = _oracle().run_best(prob, ALL)
+    assert np.all(np.isfinite(out["f"])) and np.all(np.isfinite(out["foreign_energy"]))
+    # a handful of pairs at r ~ 1e-4 dominate every sum: float32 rounding of r itself is what is left
+    _check(out, ref, ALL, force_rtol=1e-4, energy_rtol=1e-3, label=f"overlap {sc}/{coul}")
+
+
+@pytest.mark.parametrize("flags", [P.DO_FORCE, P.DO_FORCE | P.DO_SHIFTFORCE, P.DO_POTENTIAL,
+                                   P.DO_FORCE | P.DO_POTENTIAL, P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA,
+                                   P.DO_SHIFTFORCE | P.DO_POTENTIAL])
+@pytest.mark.parametrize("sc", ["beutler", "gapsys"])
+def test_flag_subsets(ctx, flags, sc):
+    prm = P.make_params(coulombtype="pme", softcore=sc, sc_alpha=0.5, sc_coul=True)
+    prob = random_problem(77, prm, natoms=300, nri=80, n_foreign=4, frac_overlap=0.0, lambda_coul=0.5, lambda_vdw=0.5)
+    out = _run(ctx, prob, flags)
+    ref = _oracle().run_best(prob, flags)
+    _check(out, ref, flags, label=f"flags={flags:#x}")
+    if not flags & P.DO_FORCE:
+        assert not np.any(out["f"]) and not np.any(out["fshift"])
+    if not flags & P.DO_POTENTIAL:
+        assert not np.any(out["Vc"]) and not np.any(out["Vv"])
+
+
+def test_lambda_end_points_and_equal_lambdas(ctx):
+    for lam in (0.0, 1.0, 0.25):
+        for sc in ("beutler", "gapsys"):
+            prm = P.make_params(coulombtype="pme", softcore=sc, sc_alpha=0.5)
+            prob = random_problem(5, prm, natoms=300, nri=80, lambda_coul=lam, lambda_vdw=lam, n_foreign=3,
+                                  frac_overlap=0.0)
+            _check(_run(ctx, prob), _oracle().run_best(prob, ALL), ALL, label=f"{sc} lambda={lam}")
+
+
+# ------------------------------------------------------------------------------------------------
+# solvated systems of the five BASELINE.json shapes
+# ------------------------------------------------------------------------------------------------
+SMALL = {
+    "C1": scaled_spec("C1", 3.0, 1, 5),
+    "C2": scaled_spec("C2", 3.6, 1, 30),
+    "C3": scaled_spec("C3", 4.0, 2, 25, n_foreign=8),
+    "C4": scaled_spec("C4", 4.2, 2, 25, n_foreign=12),
+    "C5": scaled_spec("C5", 4.5, 3, 20, n_foreign=6),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_scaled_configs_match_oracle(ctx, name):
+    prob = make_system(SMALL[name])
+    out = _run(ctx, prob)
+    ref = _oracle().run_best(prob, ALL, nthreads=4)
+    _check(out, ref, ALL, label=name)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_full_size_configs_match_oracle(ctx, name):
+    prob = make_system(SPECS[name])
+    out = _run(ctx, prob)
+    ref = _oracle().run_best(prob, ALL, nthreads=max(1, min(8, os.cpu_count() or 1)))
+    _check(out, ref, ALL, label=name)
+
+
+# ------------------------------------------------------------------------------------------------
+# lists: bit-exact round trip, shards, empty and ragged inputs
+# ------------------------------------------------------------------------------------------------
+def _assert_lists_equal(a, b):
+    for k in ("iinr", "gid", "shift", "jindex", "jjnr", "excl_fep"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_list_round_trip_is_bit_exact(ctx):
+    prob = make_system(SMALL["C4"])
+    ctx.set_problem(prob)
+    first, back = ctx.get_list()
+    assert first == 0
+    _assert_lists_equal(back, prob.nblist)
+    lay = ctx.layout()
+    assert (lay.nri, lay.nrj, lay.nri_total, lay.nrj_total) == (prob.nblist.nri, prob.nblist.nrj) * 2
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_shards_partition_the_list_bit_exactly_and_sum_to_the_whole(nranks):
+    from fepb200.lib import FepContext
+    from fepb200.shard import balanced_ranges
+
+    prob = make_system(SMALL["C4"])
+    whole = None
+    with FepContext(0) as c0:
+        c0.set_problem(prob)
+        whole = c0.compute(prob.x, prob.shiftvec, ALL)
+    ranges = balanced_ranges(prob.nblist.jindex, nranks)
+    total = None
+    nri = nrj = 0
+    for r in range(nranks):
+        with FepContext(0) as c:
+            c.set_problem(prob, rank=r, nranks=nranks)
+            first, part = c.get_list()
+            assert (first, first + part.nri) == ranges[r]
+            _assert_lists_equal(part, prob.nblist.slice_entries(*ranges[r]))
+            nri += part.nri
+            nrj += part.nrj
+            out = c.compute(prob.x, prob.shiftvec, ALL)
+        if total is None:
+            total = out
+        else:
+            for k in total:
+                total[k] = total[k] + out[k]
+    assert (nri, nrj) == (prob.nblist.nri, prob.nblist.nrj)
+    assert _force_rms(total["f"], whole["f"]) < 2e-6
+    for k in ("Vc", "Vv", "dvdl", "foreign_energy", "foreign_dvdl"):
+        assert np.allclose(total[k], whole[k], rtol=1e-6, atol=1e-6 * np.max(np.abs(whole[k])))
+
+
+def test_empty_and_ragged_lists(ctx):
+    from fepb200.problem import FepList
+
+    prm = P.make_params(coulombtype="pme", softcore="beutler")
+    prob = random_problem(3, prm, natoms=64, nri=10, n_foreign=2, frac_overlap=0.0)
+    # empty list
+    prob.nblist = FepList([], [], [], [0], [], [])
+    out = _run(ctx, prob)
+    for k, v in out.items():
+        assert not np.any(v), k
+    # entries without pairs, one-pair entries and a 64-pair entry next to each other
+    rng = np.random.default_rng(1)
+    sizes = [0, 1, 0, 64, 3, 0, 33, 1, 0]
+    jj = rng.integers(0, 64, size=sum(sizes))
+    jindex = np.concatenate([[0], np.cumsum(sizes)])
+    prob.nblist = FepList(rng.integers(0, 64, size=len(sizes)), rng.integers(0, 4, size=len(sizes)),
+                          np.full(len(sizes), 22), jindex, jj, np.ones(len(jj)))
+    out = _run(ctx, prob)
+    ref = _oracle().run_best(prob, ALL)
+    _check(out, ref, ALL, label="ragged")
+    _, back = ctx.get_list()
+    _assert_lists_equal(back, prob.nblist)
+
+
+def test_outputs_accumulate_like_the_reference_and_clear_flag(ctx):
+    prm = P.make_params(coulombtype="rf", softcore="beutler", sc_coul=True)
+    prob = random_problem(11, prm, natoms=200, nri=50, n_foreign=2, frac_overlap=0.0)
+    ctx.set_problem(prob)
+    one = ctx.compute(prob.x, prob.shiftvec, ALL)
+    two = ctx.compute(prob.x, prob.shiftvec, ALL, out={k: v.copy() for k, v in one.items()})
+    for k in one:
+        assert np.allclose(two[k], 2 * one[k], rtol=1e-6, atol=1e-30), k
+    again = ctx.compute(prob.x, prob.shiftvec, ALL | P.CLEAR_OUTPUTS, out=two)
+    for k in one:
+        assert np.array_equal(again[k], one[k]), k  # also: the path is deterministic, bit for bit
+
+
+def test_device_resident_entry_points_agree_with_compute(ctx):
+    import torch
+
+    prob = make_system(SMALL["C2"])
+    ctx.set_problem(prob)
+    want = ctx.compute(prob.x, prob.shiftvec, ALL)
+    d_x = torch.from_numpy(np.ascontiguousarray(prob.x)).cuda()
+    torch.cuda.synchronize()
+    ctx.gather_x_device(d_x.data_ptr(), prob.shiftvec)
+    ctx.launch(ALL)
+    ctx.wait()
+    got = ctx.download(ALL)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    assert ctx.last_launch_ms() > 0
+    # the result block can be wrapped without a copy (what the NCCL reduction uses)
+    from fepb200.distributed import result_tensors
+
+    f32, f64 = result_tensors(ctx)
+    lay = ctx.layout()
+    touched = ctx.touched_atoms()
+    assert np.array_equal(f32[: 3 * lay.ntouched].cpu().numpy().reshape(-1, 3), want["f"][touched])
+    assert np.array_equal(f64[lay.off_dvdl : lay.off_dvdl + 2].cpu().numpy(), want["dvdl"])
+
+
+def test_lambda_update_without_new_list(ctx):
+    prm = P.make_params(coulombtype="pme", softcore="beutler")
+    prob = random_problem(21, prm, natoms=200, nri=50, n_foreign=3, frac_overlap=0.0)
+    ctx.set_problem(prob)
+    ctx.compute(prob.x, prob.shiftvec, ALL)
+    prob.set_lambda(0.8, 0.1)
+    prob.all_lambda_coul = np.array([0.0, 0.3, 0.6, 0.9, 1.0], np.float32)
+    prob.all_lambda_vdw = np.array([0.0, 0.1, 0.2, 0.3, 1.0], np.float32)
+    ctx.set_lambdas(prob.lambda_, prob.all_lambda_coul, prob.all_lambda_vdw)
+    out = ctx.compute(prob.x, prob.shiftvec, ALL)
+    _check(out, _oracle().run_best(prob, ALL), ALL, label="new lambdas")
+
+
+def test_error_reporting(ctx):
+    from fepb200.lib import FepContext, FepError
+
+    with FepContext(0) as c:
+        with pytest.raises(FepError) as ei:
+            c.compute(np.zeros((4, 3), np.float32), np.zeros((45, 3), np.float32), ALL,
+                      out=dict(f=np.zeros((4, 3), np.float32), fshift=np.zeros((45, 3), np.float32), Vc=np.zeros(1),
+                               Vv=np.zeros(1), dvdl=np.zeros(2), foreign_energy=np.zeros(1),
+                               foreign_dvdl=np.zeros((1, 2))))
+        assert ei.value.code == -5
+        prm = P.make_params(coulombtype="pme")
+        prm.eeltype = 7  # not a type the perturbed-pair kernel supports
+        with pytest.raises(FepError) as ei:
+            c.set_params(prm)
+        assert ei.value.code == -4
