@@ -118,11 +118,6 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
             if (pr.included_within)
             {
                 fep_included_terms<SC, EWALD, FORCE>(ka, s_lp, pr, vc, vv, fscal, dc, dv);
-                if (FORCE)
-                {
-                    /* r^(p-2): r^4 for the Beutler soft-core radius power 6, r^-2 otherwise (:722-741) */
-                    fscal *= (SC == FEP_SC_BEUTLER) ? pr.r2 * pr.r2 : pr.rinv * pr.rinv;
-                }
             }
             float xc, fc, xv, fv;
             fep_corrections<EWALD, FORCE>(ka, pr, excluded, self, xc, fc, xv, fv);

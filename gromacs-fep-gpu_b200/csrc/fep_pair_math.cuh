@@ -145,6 +145,7 @@ struct FepPair
     float r2;    /* clamped at FEP_MIN_RSQ */
     float r, rinv;
     float r6;    /* Beutler only */
+    float rpm2;  /* r^(p-2): r^4 with the Beutler radius power 6, r^-2 otherwise (:722-741) */
     float qq[2], c6[2], c12[2], sig6[2], c6g[2];
     float a_c, a_v;      /* effective Beutler alphas or Gapsys scales for this pair */
     float gbase[2];      /* Gapsys: (26/7 sigma6)^(1/6) per state */
@@ -337,16 +338,17 @@ __device__ __forceinline__ void fep_included_terms(const KernelArgs& ka, const L
         dvdl_v = fmaf(vv, dlfac, dvdl_v);
         if (FORCE)
         {
-            fc *= rpinv_c;
-            fv *= rpinv_v;
-            /* multiplied by r^(p-2) by the caller */
-            fscal += lp.lfac_c[s] * fc + lp.lfac_v[s] * fv;
-            if (SC == FEP_SC_BEUTLER)
+            /* The reference scales by rC^-6 (:980-981) and later by r^(p-2) (:998-1002).  The two
+             * factors are combined first: for hard-core pairs at r -> 0 the product F * rC^-6
+             * leaves the fp32 range although the force itself does not. */
+            fscal += lp.lfac_c[s] * (fc * (rpinv_c * pr.rpm2)) + lp.lfac_v[s] * (fv * (rpinv_v * pr.rpm2));
+            if (SC == FEP_SC_BEUTLER && pr.a_v + pr.a_c != 0.0f)
             {
                 /* the reference adds these only when forces are computed (:1005-1013 use the
-                 * force terms, which stay zero in energy-only passes) */
-                dvdl_c += lp.lfac_c[s] * pr.a_c * lp.scdl_c[s] * fc * pr.sig6[s];
-                dvdl_v += lp.lfac_v[s] * pr.a_v * lp.scdl_v[s] * fv * pr.sig6[s];
+                 * force terms, which stay zero in energy-only passes); they vanish for pairs that
+                 * are not soft-cored (alpha_eff == 0) */
+                dvdl_c += lp.lfac_c[s] * pr.a_c * lp.scdl_c[s] * (fc * rpinv_c) * pr.sig6[s];
+                dvdl_v += lp.lfac_v[s] * pr.a_v * lp.scdl_v[s] * (fv * rpinv_v) * pr.sig6[s];
             }
         }
     }
@@ -413,7 +415,12 @@ __device__ __forceinline__ bool fep_load_pair(const KernelArgs& ka, int slot, Fe
     pr.r    = r2 * pr.rinv;
     if (SC == FEP_SC_BEUTLER)
     {
-        pr.r6 = r2 * r2 * r2;
+        pr.rpm2 = r2 * r2;
+        pr.r6   = pr.rpm2 * r2;
+    }
+    else
+    {
+        pr.rpm2 = pr.rinv * pr.rinv;
     }
     pr.nonzero[0]      = (pr.qq[0] != 0.0f || a.x != 0.0f || a.y != 0.0f);
     pr.nonzero[1]      = (pr.qq[1] != 0.0f || b.x != 0.0f || b.y != 0.0f);

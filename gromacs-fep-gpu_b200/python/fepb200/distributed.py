@@ -40,21 +40,22 @@ class ShardedFep:
         self.rank, self.world, self.group = rank, world, group
         torch.cuda.set_device(device)
         self.ctx = FepContext(device)
-        # all work of the context goes to torch's current stream so that kernels, collectives and
+        # all work of the context goes to one torch stream so that kernels, NCCL collectives and
         # copies are ordered without host synchronisation
-        self.stream = torch.cuda.current_stream(device)
+        self.stream = torch.cuda.Stream(device)
         self.ctx.set_stream(self.stream.cuda_stream)
         self.ctx.set_problem(problem, rank=rank, nranks=world)
         self.f32, self.f64 = result_tensors(self.ctx)
 
     def launch(self, flags: int) -> None:
-        """Kernels of this rank's shard, then the two all-reduces, all asynchronous."""
+        """Kernels of this rank's shard, then the two all-reduces, all asynchronous on self.stream."""
         import torch.distributed as dist
 
         self.ctx.launch(flags)
         if self.world > 1:
-            dist.all_reduce(self.f64, group=self.group)
-            dist.all_reduce(self.f32, group=self.group)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.f64, group=self.group)
+                dist.all_reduce(self.f32, group=self.group)
 
     def step(self, x, shiftvec, flags: int, out: dict | None = None) -> dict:
         """Host buffers in, reduced host buffers out (every rank receives the full result)."""

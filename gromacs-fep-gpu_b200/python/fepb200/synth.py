@@ -425,6 +425,7 @@ def random_problem(seed: int, params: Params, *, natoms=96, nri=40, max_j=70, nt
                 d *= params.rcoulomb / np.linalg.norm(d)
                 if js[k] != i:
                     x32[js[k]] = (x32[i].astype(np.float64) + sv[s] + d).astype(np.float32)
+        ex[js == i] = 0  # an included i == j pair (r = 0 without exclusion) is not a physical input
         iinr.append(i)
         gid.append(int(rng.integers(0, n_groups * n_groups)))
         shift.append(s)
