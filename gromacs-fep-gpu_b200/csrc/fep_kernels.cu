@@ -42,47 +42,6 @@ __device__ __forceinline__ double warp_sum_d(double v)
     return v;
 }
 
-/* Lambda-independent correction factors of one pair (reference :1023-1136):
- *   xc / fc multiply qq[s]  (excluded-pair reaction field, Ewald real-space correction)
- *   xv / fv multiply c6grid[s] (LJ-PME grid correction)                                   */
-template<bool EWALD, bool FORCE>
-__device__ __forceinline__ void fep_corrections(const KernelArgs& ka, const FepPair& pr, bool excluded, bool self,
-                                                float& xc, float& fc, float& xv, float& fv)
-{
-    xc = fc = xv = fv = 0.0f;
-    if (!EWALD)
-    {
-        if (ka.rf_type && excluded)
-        {
-            float vv = fmaf(ka.krf, pr.r2, -ka.crf);
-            if (self)
-            {
-                vv *= 0.5f;
-            }
-            xc = vv;
-            fc = -2.0f * ka.krf;
-        }
-    }
-    else if (excluded || pr.r < ka.rcoulomb)
-    {
-        float v_lr, f_lr = 0.0f;
-        fep_ewald_correction<FORCE>(pr.r2, pr.r, pr.rinv, ka.beta, ka.beta2, ka.beta3, &v_lr, &f_lr);
-        if (self)
-        {
-            v_lr *= 0.5f;
-        }
-        xc = -v_lr;
-        fc = -f_lr;
-    }
-    if (ka.vdw_ewald && (excluded || pr.r < ka.rvdw))
-    {
-        float pot, force = 0.0f;
-        fep_ljpme_correction<FORCE>(pr.r2, pr.rinv, ka.lj_coeff_sq, ka.lj_coeff6_div6, self, &pot, &force);
-        xv = pot * (1.0f / 6.0f);
-        fv = force;
-    }
-}
-
 /* ------------------------------------------------------------------------------------------- */
 /* pass at the current lambda                                                                  */
 /* ------------------------------------------------------------------------------------------- */
@@ -370,49 +329,12 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
     const int off_fe   = off_dvdl + 2;
     const int off_fd   = off_fe + ka.n_points;
 
-    if (b < lay.atom_blocks)
+    /* role order: reduction jobs and scalar sums first (few, long), per-atom gathers after, so the
+     * long blocks overlap with the bulk instead of forming a tail */
+    bool is_job = false;
+    if (b < lay.job_blocks)
     {
-        /* eight lanes per touched atom; contributions are visited in ascending index order by
-         * lane stride, then combined with a fixed xor tree: deterministic */
-        const int atom = b * (FEP_EPI_CTA / 8) + (tid >> 3);
-        const int sub  = tid & 7;
-        float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
-        if (atom < ka.n_touched)
-        {
-            const int k0 = __ldg(ka.atom_ptr + atom), k1 = __ldg(ka.atom_ptr + atom + 1);
-            for (int k = k0 + sub; k < k1; k += 8)
-            {
-                const int idx = __ldg(ka.atom_idx + k);
-                if (idx < ka.n_pairs)
-                {
-                    const float4 t = __ldcs(ka.t4 + idx);
-                    fx -= t.x;
-                    fy -= t.y;
-                    fz -= t.z;
-                }
-                else
-                {
-                    const float4 t = __ldg(ka.fi4 + (idx - ka.n_pairs));
-                    fx += t.x;
-                    fy += t.y;
-                    fz += t.z;
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1)
-        {
-            fx += __shfl_xor_sync(FULL_MASK, fx, o);
-            fy += __shfl_xor_sync(FULL_MASK, fy, o);
-            fz += __shfl_xor_sync(FULL_MASK, fz, o);
-        }
-        if (atom < ka.n_touched && sub < 3)
-        {
-            ka.res_f32[3 * (size_t)atom + sub] = sub == 0 ? fx : (sub == 1 ? fy : fz);
-        }
-    }
-    else if ((b -= lay.atom_blocks) < lay.job_blocks)
-    {
+        is_job           = true;
         const int    j   = lay.job_begin + b;
         const RedJob job = ka.red_jobs[j];
         double       a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -486,20 +408,80 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             }
         }
     }
+    else
+    {
+        /* eight lanes per touched atom; contributions are visited in ascending index order by
+         * lane stride, then combined with a fixed xor tree: deterministic */
+        b -= lay.scalar_blocks;
+        const int atom = b * (FEP_EPI_CTA / 8) + (tid >> 3);
+        const int sub  = tid & 7;
+        float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        if (atom < ka.n_touched)
+        {
+            const int k0 = __ldg(ka.atom_ptr + atom), k1 = __ldg(ka.atom_ptr + atom + 1);
+            for (int k = k0 + sub; k < k1; k += 8)
+            {
+                const int idx = __ldg(ka.atom_idx + k);
+                if (idx < ka.n_pairs)
+                {
+                    const float4 t = __ldcs(ka.t4 + idx);
+                    fx -= t.x;
+                    fy -= t.y;
+                    fz -= t.z;
+                }
+                else
+                {
+                    const float4 t = __ldg(ka.fi4 + (idx - ka.n_pairs));
+                    fx += t.x;
+                    fy += t.y;
+                    fz += t.z;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)
+        {
+            fx += __shfl_xor_sync(FULL_MASK, fx, o);
+            fy += __shfl_xor_sync(FULL_MASK, fy, o);
+            fz += __shfl_xor_sync(FULL_MASK, fz, o);
+        }
+        if (atom < ka.n_touched && sub < 3)
+        {
+            ka.res_f32[3 * (size_t)atom + sub] = sub == 0 ? fx : (sub == 1 ? fy : fz);
+        }
+    }
 
-    /* the block that finishes last adds up the job partials per output key, in job order */
-    __threadfence();
-    if (tid == 0)
+    /* the job block that finishes last adds up the job partials per output key, in job order;
+     * only job blocks take a ticket (bar.sync + one fence by the ticket thread orders the block's
+     * partial before the ticket) */
+    if (lay.job_blocks == 0)
     {
-        const unsigned ticket = atomicAdd(ka.done_counter, 1u);
-        s_last                = (ticket == gridDim.x - 1);
+        /* nothing to add up (empty shard): the first block writes the zeros */
+        if (blockIdx.x != 0)
+        {
+            return;
+        }
     }
-    __syncthreads();
-    if (!s_last)
+    else
     {
-        return;
+        if (!is_job)
+        {
+            return;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            __threadfence();
+            const unsigned ticket = atomicAdd(ka.done_counter, 1u);
+            s_last                = (ticket == (unsigned)lay.job_blocks - 1u);
+        }
+        __syncthreads();
+        if (!s_last)
+        {
+            return;
+        }
+        __threadfence();
     }
-    __threadfence();
     if (sf.shift)
     {
         for (int o = tid; o < 3 * FEP_NUM_SHIFT; o += FEP_EPI_CTA)
@@ -527,7 +509,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             ka.res_f64[off_vv + g] = c;
         }
     }
-    if (tid == 0)
+    if (tid == 0 && lay.job_blocks != 0)
     {
         *ka.done_counter = 0u;
     }
@@ -550,7 +532,7 @@ __global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restri
 /* ------------------------------------------------------------------------------------------- */
 template<int SC, bool EWALD>
 static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStream_t stream, long long* counter,
-                                   cudaEvent_t* ev)
+                                   cudaEvent_t* ev, const LambdaPoint* host_pts, int foreign_mode)
 {
     if (ev)
     {
@@ -574,9 +556,21 @@ static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStrea
     }
     if (ka.n_cta > 0 && sf.foreign && ka.n_points > 0)
     {
-        const dim3 grid(ka.n_tiles, ka.n_chunks);
-        fep_foreign_kernel<SC, EWALD><<<grid, FEP_CTA, 0, stream>>>(ka);
-        (*counter)++;
+        if (SC == FEP_SC_BEUTLER && foreign_mode >= 0)
+        {
+            /* specialised kernels of fep_foreign_beutler.cu, one launch per chunk of lambda points */
+            const int rc = fep_launch_foreign_beutler(&ka, EWALD ? 1 : 0, foreign_mode, host_pts, stream, counter);
+            if (rc != 0)
+            {
+                return rc > 0 ? (cudaError_t)rc : cudaErrorInvalidValue;
+            }
+        }
+        else
+        {
+            const dim3 grid(ka.n_tiles, ka.n_chunks);
+            fep_foreign_kernel<SC, EWALD><<<grid, FEP_CTA, 0, stream>>>(ka);
+            (*counter)++;
+        }
     }
     if (ev)
     {
@@ -586,18 +580,18 @@ static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStrea
 }
 
 extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
-                               long long* counter, cudaEvent_t* ev)
+                               long long* counter, cudaEvent_t* ev, const LambdaPoint* host_pts, int foreign_mode)
 {
     const KernelArgs& ka = *kap;
     cudaError_t       err;
     switch (softcore * 2 + (elec_ewald ? 1 : 0))
     {
-        case FEP_SC_NONE * 2 + 0: err = launch_variants<FEP_SC_NONE, false>(ka, sf, stream, counter, ev); break;
-        case FEP_SC_NONE * 2 + 1: err = launch_variants<FEP_SC_NONE, true>(ka, sf, stream, counter, ev); break;
-        case FEP_SC_BEUTLER * 2 + 0: err = launch_variants<FEP_SC_BEUTLER, false>(ka, sf, stream, counter, ev); break;
-        case FEP_SC_BEUTLER * 2 + 1: err = launch_variants<FEP_SC_BEUTLER, true>(ka, sf, stream, counter, ev); break;
-        case FEP_SC_GAPSYS * 2 + 0: err = launch_variants<FEP_SC_GAPSYS, false>(ka, sf, stream, counter, ev); break;
-        case FEP_SC_GAPSYS * 2 + 1: err = launch_variants<FEP_SC_GAPSYS, true>(ka, sf, stream, counter, ev); break;
+        case FEP_SC_NONE * 2 + 0: err = launch_variants<FEP_SC_NONE, false>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
+        case FEP_SC_NONE * 2 + 1: err = launch_variants<FEP_SC_NONE, true>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
+        case FEP_SC_BEUTLER * 2 + 0: err = launch_variants<FEP_SC_BEUTLER, false>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
+        case FEP_SC_BEUTLER * 2 + 1: err = launch_variants<FEP_SC_BEUTLER, true>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
+        case FEP_SC_GAPSYS * 2 + 0: err = launch_variants<FEP_SC_GAPSYS, false>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
+        case FEP_SC_GAPSYS * 2 + 1: err = launch_variants<FEP_SC_GAPSYS, true>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
         default: return (int)cudaErrorInvalidValue;
     }
     if (err != cudaSuccess)

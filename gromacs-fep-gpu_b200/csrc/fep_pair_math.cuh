@@ -428,4 +428,45 @@ __device__ __forceinline__ bool fep_load_pair(const KernelArgs& ka, int slot, Fe
     return true;
 }
 
+/* Lambda-independent correction factors of one pair (reference :1023-1136):
+ *   xc / fc multiply qq[s]  (excluded-pair reaction field, Ewald real-space correction)
+ *   xv / fv multiply c6grid[s] (LJ-PME grid correction)                                   */
+template<bool EWALD, bool FORCE>
+__device__ __forceinline__ void fep_corrections(const KernelArgs& ka, const FepPair& pr, bool excluded, bool self,
+                                                float& xc, float& fc, float& xv, float& fv)
+{
+    xc = fc = xv = fv = 0.0f;
+    if (!EWALD)
+    {
+        if (ka.rf_type && excluded)
+        {
+            float vv = fmaf(ka.krf, pr.r2, -ka.crf);
+            if (self)
+            {
+                vv *= 0.5f;
+            }
+            xc = vv;
+            fc = -2.0f * ka.krf;
+        }
+    }
+    else if (excluded || pr.r < ka.rcoulomb)
+    {
+        float v_lr, f_lr = 0.0f;
+        fep_ewald_correction<FORCE>(pr.r2, pr.r, pr.rinv, ka.beta, ka.beta2, ka.beta3, &v_lr, &f_lr);
+        if (self)
+        {
+            v_lr *= 0.5f;
+        }
+        xc = -v_lr;
+        fc = -f_lr;
+    }
+    if (ka.vdw_ewald && (excluded || pr.r < ka.rvdw))
+    {
+        float pot, force = 0.0f;
+        fep_ljpme_correction<FORCE>(pr.r2, pr.rinv, ka.lj_coeff_sq, ka.lj_coeff6_div6, self, &pot, &force);
+        xv = pot * (1.0f / 6.0f);
+        fv = force;
+    }
+}
+
 #endif

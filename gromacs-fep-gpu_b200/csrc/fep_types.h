@@ -124,7 +124,13 @@ extern "C" {
 /* `events`, when not NULL, are 4 events recorded before the pass kernel and after the pass,
  * foreign and epilogue kernels (profiling mode only). */
 int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
-                    long long* launch_counter, cudaEvent_t* events);
+                    long long* launch_counter, cudaEvent_t* events, const LambdaPoint* host_pts, int foreign_mode);
+/* fep_foreign_beutler.cu: specialised foreign-lambda kernels (Beutler soft-core, no potential
+ * switch).  foreign_mode 0: alphaCoul == 0; 1: one soft-core radius; 2: separate radii. */
+#define FEP_FB_CTA 128
+int fep_foreign_beutler_chunk_size(int n_points, int n_chunks_wanted);
+int fep_launch_foreign_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_pts,
+                               cudaStream_t stream, long long* launch_counter);
 int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched, cudaStream_t stream,
                         long long* launch_counter);
 #ifdef __cplusplus

@@ -138,6 +138,7 @@ struct fepb200_ctx
     fepb200_params params{};
     int            softcore   = FEP_SC_NONE;
     int            elec_ewald = 0;
+    int            foreign_mode = -1; /* >= 0: specialised Beutler foreign kernels */
     KernelArgs     ka{};
 
     /* nbfp */
@@ -287,15 +288,49 @@ int prepare_buffers(fepb200_ctx* c)
     const int             np = l.nforeign + 1;
 
     k.n_points = np;
-    /* lambda chunks of at most FEP_LCHUNK points, evenly sized */
-    k.n_chunks     = (np + FEP_LCHUNK - 1) / FEP_LCHUNK;
-    k.chunk_points = (np + k.n_chunks - 1) / k.n_chunks;
-    k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
-    /* pair tiles of the foreign kernel: enough CTAs to fill the GPU several times over, but
-     * several pairs per thread on large lists to amortise the final reduction */
+    int sms    = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    c->foreign_mode = -1;
+    if (c->softcore == FEP_SC_BEUTLER && !k.pot_switch)
     {
-        int       sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        /* nb_free_energy.cpp:1405-1419 decides per call whether the Coulomb and LJ soft-core radii
+         * differ; here per set of lambda points */
+        if (c->params.alphaCoulomb == 0.0f)
+        {
+            c->foreign_mode = 0;
+        }
+        else
+        {
+            bool same = c->params.alphaCoulomb == c->params.alphaVdw && c->lam_c == c->lam_v;
+            for (size_t i = 0; i < c->all_c.size(); i++)
+            {
+                same = same && c->all_c[i] == c->all_v[i];
+            }
+            c->foreign_mode = same ? 1 : 2;
+        }
+        /* one launch per chunk; split the points only when the pair CTAs alone cannot fill the GPU */
+        const long long pair_ctas = (k.n_pairs + FEP_FB_CTA - 1) / FEP_FB_CTA;
+        int             want      = 1;
+        if (pair_ctas > 0 && pair_ctas < 2LL * sms)
+        {
+            want = (int)std::min<long long>(np, (2LL * sms + pair_ctas - 1) / pair_ctas);
+        }
+        k.chunk_points = fep_foreign_beutler_chunk_size(np, want);
+        k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
+        const long long target_ctas = 8LL * sms;
+        long long       per_thread  = ((long long)k.n_pairs + target_ctas * FEP_FB_CTA - 1) / (target_ctas * FEP_FB_CTA);
+        per_thread   = std::max(1LL, std::min(per_thread, 8LL));
+        k.tile_pairs = (int)per_thread * FEP_FB_CTA;
+        k.n_tiles    = (k.n_pairs + k.tile_pairs - 1) / k.tile_pairs;
+    }
+    else
+    {
+        /* generic kernel: lambda chunks of at most FEP_LCHUNK points, evenly sized */
+        k.n_chunks     = (np + FEP_LCHUNK - 1) / FEP_LCHUNK;
+        k.chunk_points = (np + k.n_chunks - 1) / k.n_chunks;
+        k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
+        /* pair tiles: enough CTAs to fill the GPU several times over, but several pairs per thread
+         * on large lists to amortise the final reduction */
         const long long target_ctas = 8LL * sms;
         long long       per_thread  = ((long long)k.n_pairs * k.n_chunks + target_ctas * FEP_CTA - 1)
                                / (target_ctas * FEP_CTA);
@@ -634,9 +669,17 @@ int fepb200_set_params(fepb200_ctx* c, const fepb200_params* p)
     c->have_params   = true;
     c->typetab_dirty = true;
     refresh_points(c);
-    if (c->have_list && !c->pts.empty())
+    if (c->have_list)
     {
-        return upload_points(c);
+        const int rc = prepare_buffers(c);
+        if (rc != FEPB200_OK)
+        {
+            return rc;
+        }
+        if (!c->pts.empty())
+        {
+            return upload_points(c);
+        }
     }
     return FEPB200_OK;
 }
@@ -1070,14 +1113,12 @@ int fepb200_set_lambdas(fepb200_ctx* c, const float* lambda, int n_foreign, cons
     refresh_points(c);
     if (c->have_list)
     {
-        if (c->layout.nforeign != n_foreign)
+        /* sizes depend on L, the choice of foreign kernel on the lambda values */
+        c->layout.nforeign = n_foreign;
+        const int rc       = prepare_buffers(c);
+        if (rc != FEPB200_OK)
         {
-            c->layout.nforeign = n_foreign;
-            const int rc       = prepare_buffers(c);
-            if (rc != FEPB200_OK)
-            {
-                return rc;
-            }
+            return rc;
         }
         if (!c->pts.empty())
         {
@@ -1169,7 +1210,7 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     const StepFlags sf     = step_flags(c, flags);
     CU_CHECK(c, cudaEventRecord(c->ev_start, stream));
     const int err = fep_launch_step(&c->ka, c->softcore, c->elec_ewald, sf, stream, &c->launches,
-                                    c->profiling ? c->ev_prof : nullptr);
+                                    c->profiling ? c->ev_prof : nullptr, c->pts.data(), c->foreign_mode);
     c->profiled   = c->profiling;
     if (err != 0)
     {
