@@ -8,10 +8,11 @@
  *   fep_foreign_kernel  grid = (pair tiles) x (chunks of lambda points); evaluates the energy-only
  *                       passes of freeenergydispatch.cpp:236-306 for ALL lambda points with one
  *                       load of each pair per chunk.
- *   fep_epilogue_kernel atomic-free, deterministic gather of the pair force vectors into per-atom
- *                       forces, of the per-segment i forces into shift forces, of the per-segment
- *                       energies into energy-group pairs, and of the per-CTA partial sums into
- *                       dV/dlambda and foreign energies.  Replaces ThreadedForceBuffer::reduce
+ *   fep_epilogue_kernel atomic-free, deterministic: sums each atom's contiguous range of the
+ *                       atom-sorted contribution buffer into per-atom forces, the shift-sorted
+ *                       segment forces into shift forces, the group-sorted segment energies into
+ *                       energy-group pairs, and the per-CTA partial sums into dV/dlambda and
+ *                       foreign energies.  Replaces ThreadedForceBuffer::reduce
  *                       (threaded_force_buffer.cpp:320-402) and the sums at
  *                       freeenergydispatch.cpp:298-305.
  *
@@ -46,7 +47,7 @@ __device__ __forceinline__ double warp_sum_d(double v)
 /* pass at the current lambda                                                                  */
 /* ------------------------------------------------------------------------------------------- */
 template<int SC, bool EWALD, bool FORCE>
-__global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant__ KernelArgs ka)
+__global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant__ KernelArgs ka, const int want_shift)
 {
     __shared__ LambdaPoint s_lp;
     __shared__ float       s_red[FEP_CTA / 32][2];
@@ -97,8 +98,9 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         }
         if (FORCE)
         {
-            /* pair force vector: the j atom receives -t, gathered by the epilogue */
-            ka.t4[slot] = make_float4(fx, fy, fz, 0.0f);
+            /* the j atom receives -t: scattered to this pair's own slot in the atom-sorted buffer
+             * (unique destination, no atomics; skipped pairs write their zero) */
+            ka.fsorted[__ldg(ka.pair_dst + slot)] = make_float4(-fx, -fy, -fz, 0.0f);
         }
     }
 
@@ -141,11 +143,17 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
     {
         const int gw = blockIdx.x * (FEP_CTA / 32) + warp;
         const int h  = __ldg(ka.warp_hbase + gw) + __popc(hmask & ((1u << lane) - 1u));
+        const int4 sd = __ldg(ka.seg_dst + h);
         if (FORCE)
         {
-            ka.fi4[h] = make_float4(fx, fy, fz, 0.0f);
+            const float4 fi = make_float4(fx, fy, fz, 0.0f);
+            ka.fsorted[sd.x] = fi;
+            if (want_shift)
+            {
+                ka.fshift_sorted[sd.y] = fi;
+            }
         }
-        ka.ev2[h] = make_float2(vc, vv);
+        ka.ev2[sd.z] = make_float2(vc, vv);
     }
 
     __syncthreads();
@@ -338,23 +346,39 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         const int    j   = lay.job_begin + b;
         const RedJob job = ka.red_jobs[j];
         double       a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        /* a job is a contiguous range of at most FEP_RED_CHUNK = PER * CTA elements */
+        constexpr int PER = FEP_RED_CHUNK / FEP_EPI_CTA;
         if (job.kind == 0)
         {
-            for (int k = job.begin + tid; k < job.end; k += FEP_EPI_CTA)
+            float4 t[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++)
             {
-                const float4 t = __ldg(ka.fi4 + __ldg(ka.red_idx + k));
-                a0 += t.x;
-                a1 += t.y;
-                a2 += t.z;
+                const int k = job.begin + tid + u * FEP_EPI_CTA;
+                t[u]        = k < job.end ? __ldcs(ka.fshift_sorted + k) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++)
+            {
+                a0 += t[u].x;
+                a1 += t[u].y;
+                a2 += t[u].z;
             }
         }
         else
         {
-            for (int k = job.begin + tid; k < job.end; k += FEP_EPI_CTA)
+            float2 t[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++)
             {
-                const float2 t = __ldg(ka.ev2 + __ldg(ka.red_idx + k));
-                a0 += t.x;
-                a1 += t.y;
+                const int k = job.begin + tid + u * FEP_EPI_CTA;
+                t[u]        = k < job.end ? __ldcs(ka.ev2 + k) : make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++)
+            {
+                a0 += t[u].x;
+                a1 += t[u].y;
             }
         }
         a0 = block_sum_d(a0, s_buf);
@@ -419,22 +443,22 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         if (atom < ka.n_touched)
         {
             const int k0 = __ldg(ka.atom_ptr + atom), k1 = __ldg(ka.atom_ptr + atom + 1);
-            for (int k = k0 + sub; k < k1; k += 8)
+            /* the atom's contributions are contiguous in fsorted: eight lanes stream them, four
+             * independent 16-byte loads per lane and trip (most atoms need a single trip) */
+            for (int k = k0 + sub; k < k1; k += 32)
             {
-                const int idx = __ldg(ka.atom_idx + k);
-                if (idx < ka.n_pairs)
+                float4 t[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
                 {
-                    const float4 t = __ldcs(ka.t4 + idx);
-                    fx -= t.x;
-                    fy -= t.y;
-                    fz -= t.z;
+                    t[u] = (k + 8 * u < k1) ? __ldcs(ka.fsorted + k + 8 * u) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
-                else
+#pragma unroll
+                for (int u = 0; u < 4; u++)
                 {
-                    const float4 t = __ldg(ka.fi4 + (idx - ka.n_pairs));
-                    fx += t.x;
-                    fy += t.y;
-                    fz += t.z;
+                    fx += t[u].x;
+                    fy += t[u].y;
+                    fz += t[u].z;
                 }
             }
         }
@@ -542,11 +566,11 @@ static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStrea
     {
         if (sf.force)
         {
-            fep_pass_kernel<SC, EWALD, true><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka);
+            fep_pass_kernel<SC, EWALD, true><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, sf.shift);
         }
         else
         {
-            fep_pass_kernel<SC, EWALD, false><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka);
+            fep_pass_kernel<SC, EWALD, false><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, 0);
         }
         (*counter)++;
     }

@@ -16,10 +16,13 @@
  *   ent4[E]      int4   {compact i, shift index, gid, 0}     per search step
  *   warp_hbase[ceil(P/32)]  index of the first "segment" of each warp of the flat pair space;
  *                a segment is a maximal run of pairs of one i-entry inside one warp
- *   t4[P]        float4 pair force vectors (written by the pass kernel, read by the epilogue)
- *   fi4[H]       float4 per-segment i forces;  ev2[H] float2 per-segment {Vc,Vv}
- *   atom_ptr[nT+1], atom_idx[P+H]   contributions per touched atom (idx < P: -t4, else +fi4)
- *   red_*        chunked segment lists per shift vector and per energy-group pair
+ *   pair_dst[P]  int    where the pair's force on its j atom goes in fsorted     per search step
+ *   seg_dst[H]   int4   {slot in fsorted, slot in fshift_sorted, slot in ev2, 0} per search step
+ *   fsorted[P+H] float4 force contributions SORTED BY RECEIVING ATOM: atom k owns the contiguous
+ *                range [atom_ptr[k], atom_ptr[k+1]); the pass kernel scatters -t (pairs, as j) and
+ *                +f_i (segments, as i) to precomputed unique slots, the epilogue streams ranges
+ *   fshift_sorted[H] float4 segment i-forces sorted by shift index;  ev2[H] float2 segment
+ *                {Vc,Vv} sorted by energy-group pair; red_jobs = chunks of those ranges
  *   cta_part[nCta][2]        fp64 per-CTA partial dV/dlambda of the current-lambda pass
  *   for_part[3*(L+1)][nTile] fp64 per-CTA partial foreign energies / dV/dlambda
  *   result block: res_f32[3*nT + 3*45], res_f64[2G + 2 + 3(L+1)]   (include/fepb200.h)
@@ -60,12 +63,13 @@ struct DynHead
     LambdaPoint cur; /* the current lambda (pass at the current lambda) */
 };
 
-/* One reduction job of the epilogue: segments idx[begin,end) all belong to output `key`. */
+/* One reduction job of the epilogue: elements [begin,end) of fshift_sorted (kind 0) or ev2
+ * (kind 1) all belong to output `key`. */
 struct RedJob
 {
     int begin, end;
     int key;  /* shift index (kind 0) or gid (kind 1) */
-    int kind; /* 0: fi4 -> shift force, 1: ev2 -> Vc/Vv */
+    int kind; /* 0: fshift_sorted -> shift force, 1: ev2 -> Vc/Vv */
 };
 
 /* Static constants + device pointers, passed by value as the kernel parameter. */
@@ -92,9 +96,11 @@ struct KernelArgs
     const int*      pair_e;
     const int4*     ent4;
     const int*      warp_hbase;
+    const int*      pair_dst;
+    const int4*     seg_dst;
     /* intermediates */
-    float4* t4;
-    float4* fi4;
+    float4* fsorted;
+    float4* fshift_sorted;
     float2* ev2;
     double* cta_part;
     double* for_part;
@@ -102,9 +108,7 @@ struct KernelArgs
     unsigned int* done_counter;
     /* epilogue inputs */
     const int*    atom_ptr;
-    const int*    atom_idx;
     const RedJob* red_jobs;
-    const int*    red_idx;
     const int*    key_job_ptr; /* [45 + G + 1]: jobs of each key, shift keys first */
     /* outputs */
     float*  res_f32;

@@ -13,6 +13,8 @@
  *   nbnxm/atomdata.cpp:1055-1072           setAtomPropertiesAB
  *   nbnxm/pairlist.cpp:2786-2838           balance_fep_lists() (here: split over ranks)
  */
+#include <omp.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -101,6 +103,13 @@ struct PinnedArray
     }
 };
 
+/* threads for the host-side gather / scatter of the touched atoms (about 16k atoms per thread) */
+int host_threads(int n)
+{
+    const int want = std::max(1, n / 16384);
+    return std::min(std::min(want, 8), std::max(1, omp_get_max_threads()));
+}
+
 float int_bits_as_float(int v)
 {
     float f;
@@ -169,10 +178,10 @@ struct fepb200_ctx
     std::vector<int> compact_of; /* atom -> compact or -1 */
     int              n_segments = 0;
 
-    DeviceArray<int>    d_touched, d_pair_j, d_pair_e, d_warp_hbase, d_atom_ptr, d_atom_idx, d_red_idx, d_key_job_ptr;
-    DeviceArray<int4>   d_ent4;
+    DeviceArray<int>    d_touched, d_pair_j, d_pair_e, d_warp_hbase, d_atom_ptr, d_pair_dst, d_key_job_ptr;
+    DeviceArray<int4>   d_ent4, d_seg_dst;
     DeviceArray<RedJob> d_red_jobs;
-    DeviceArray<float4> d_par4, d_t4, d_fi4;
+    DeviceArray<float4> d_par4, d_fsorted, d_fshift_sorted;
     DeviceArray<float2> d_ev2;
     DeviceArray<double> d_cta_part, d_for_part, d_job_part;
     DeviceArray<unsigned int> d_counter;
@@ -317,9 +326,12 @@ int prepare_buffers(fepb200_ctx* c)
         }
         k.chunk_points = fep_foreign_beutler_chunk_size(np, want);
         k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
-        const long long target_ctas = 8LL * sms;
+        /* one wave: as many pair tiles as CTAs can be resident (launch bounds of the kernels:
+         * 4 CTAs of 128 threads per SM, 2 when there are more than 56 accumulators) */
+        const int       nacc        = (c->foreign_mode == 0 ? 2 : 4) * k.chunk_points + 4;
+        const long long target_ctas = (long long)sms * (nacc > 56 ? 2 : 4);
         long long       per_thread  = ((long long)k.n_pairs + target_ctas * FEP_FB_CTA - 1) / (target_ctas * FEP_FB_CTA);
-        per_thread   = std::max(1LL, std::min(per_thread, 8LL));
+        per_thread   = std::max(1LL, std::min(per_thread, 32LL));
         k.tile_pairs = (int)per_thread * FEP_FB_CTA;
         k.n_tiles    = (k.n_pairs + k.tile_pairs - 1) / k.tile_pairs;
     }
@@ -534,14 +546,14 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_pair_e.release();
     c->d_warp_hbase.release();
     c->d_atom_ptr.release();
-    c->d_atom_idx.release();
-    c->d_red_idx.release();
+    c->d_pair_dst.release();
+    c->d_seg_dst.release();
     c->d_key_job_ptr.release();
     c->d_ent4.release();
     c->d_red_jobs.release();
     c->d_par4.release();
-    c->d_t4.release();
-    c->d_fi4.release();
+    c->d_fsorted.release();
+    c->d_fshift_sorted.release();
     c->d_ev2.release();
     c->d_cta_part.release();
     c->d_for_part.release();
@@ -858,8 +870,10 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     }
     const int H = (int)seg_entry.size();
 
-    /* per-atom contribution lists: pair slots (as j) then segments (as i), ascending */
-    std::vector<int> atom_ptr(nT + 1, 0), atom_idx((size_t)P + H);
+    /* Atom-sorted contribution buffer: atom k owns [atom_ptr[k], atom_ptr[k+1]); within a range
+     * the pair contributions (as j) come first in slot order, then the segments (as i). */
+    std::vector<int>  atom_ptr(nT + 1, 0), pair_dst(P);
+    std::vector<int4> seg_dst(H);
     for (int s = 0; s < P; s++)
     {
         atom_ptr[(pair_j[s] & 0x7fffffff) + 1]++;
@@ -876,18 +890,18 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         std::vector<int> fill(atom_ptr.begin(), atom_ptr.end() - 1);
         for (int s = 0; s < P; s++)
         {
-            atom_idx[fill[pair_j[s] & 0x7fffffff]++] = s;
+            pair_dst[s] = fill[pair_j[s] & 0x7fffffff]++;
         }
         for (int h = 0; h < H; h++)
         {
-            atom_idx[fill[ent4[seg_entry[h]].x]++] = P + h;
+            seg_dst[h] = make_int4(fill[ent4[seg_entry[h]].x]++, 0, 0, 0);
         }
     }
 
-    /* reduction jobs: segments per shift vector, then per energy-group pair, in chunks */
+    /* segments sorted by shift vector (-> fshift_sorted) and by energy-group pair (-> ev2); the
+     * reduction jobs are chunks of those ranges */
     std::vector<RedJob> jobs;
-    std::vector<int>    red_idx, key_job_ptr(FEP_NUM_SHIFT + ngrp + 1, 0);
-    red_idx.reserve(2 * (size_t)H);
+    std::vector<int>    key_job_ptr(FEP_NUM_SHIFT + ngrp + 1, 0);
     for (int kind = 0; kind < 2; kind++)
     {
         const int        nkeys = kind == 0 ? FEP_NUM_SHIFT : ngrp;
@@ -901,13 +915,19 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         {
             cnt[k + 1] += cnt[k];
         }
-        const size_t     base = red_idx.size();
         std::vector<int> fill(cnt.begin(), cnt.end() - 1);
-        red_idx.resize(base + H);
         for (int h = 0; h < H; h++)
         {
-            const int4 e                                       = ent4[seg_entry[h]];
-            red_idx[base + fill[kind == 0 ? e.y : e.z]++] = h;
+            const int4 e   = ent4[seg_entry[h]];
+            const int  pos = fill[kind == 0 ? e.y : e.z]++;
+            if (kind == 0)
+            {
+                seg_dst[h].y = pos;
+            }
+            else
+            {
+                seg_dst[h].z = pos;
+            }
         }
         for (int k = 0; k < nkeys; k++)
         {
@@ -915,8 +935,8 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
             for (int b = cnt[k]; b < cnt[k + 1]; b += FEP_RED_CHUNK)
             {
                 RedJob j;
-                j.begin = (int)base + b;
-                j.end   = (int)base + std::min(cnt[k + 1], b + FEP_RED_CHUNK);
+                j.begin = b;
+                j.end   = std::min(cnt[k + 1], b + FEP_RED_CHUNK);
                 j.key   = k;
                 j.kind  = kind;
                 jobs.push_back(j);
@@ -941,14 +961,14 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair_j, pair_j))
         || (rc = to_device(c, c->d_pair_e, pair_e)) || (rc = to_device(c, c->d_ent4, ent4))
         || (rc = to_device(c, c->d_warp_hbase, warp_hbase)) || (rc = to_device(c, c->d_atom_ptr, atom_ptr))
-        || (rc = to_device(c, c->d_atom_idx, atom_idx)) || (rc = to_device(c, c->d_red_jobs, jobs))
-        || (rc = to_device(c, c->d_red_idx, red_idx)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
+        || (rc = to_device(c, c->d_pair_dst, pair_dst)) || (rc = to_device(c, c->d_red_jobs, jobs))
+        || (rc = to_device(c, c->d_seg_dst, seg_dst)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
         || (rc = to_device(c, c->d_par4, par4)))
     {
         return rc;
     }
-    CU_CHECK(c, c->d_t4.reserve(std::max(P, 1)));
-    CU_CHECK(c, c->d_fi4.reserve(std::max(H, 1)));
+    CU_CHECK(c, c->d_fsorted.reserve(std::max(P + H, 1)));
+    CU_CHECK(c, c->d_fshift_sorted.reserve(std::max(H, 1)));
     CU_CHECK(c, c->d_ev2.reserve(std::max(H, 1)));
     CU_CHECK(c, c->d_job_part.reserve(4 * std::max<size_t>(jobs.size(), 1)));
     CU_CHECK(c, cudaStreamSynchronize(c->stream)); /* host vectors go out of scope */
@@ -966,14 +986,14 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     k.pair_e      = c->d_pair_e.ptr;
     k.ent4        = c->d_ent4.ptr;
     k.warp_hbase  = c->d_warp_hbase.ptr;
-    k.t4          = c->d_t4.ptr;
-    k.fi4         = c->d_fi4.ptr;
+    k.fsorted       = c->d_fsorted.ptr;
+    k.fshift_sorted = c->d_fshift_sorted.ptr;
+    k.pair_dst      = c->d_pair_dst.ptr;
+    k.seg_dst       = c->d_seg_dst.ptr;
     k.ev2         = c->d_ev2.ptr;
     k.job_part    = c->d_job_part.ptr;
     k.atom_ptr    = c->d_atom_ptr.ptr;
-    k.atom_idx    = c->d_atom_idx.ptr;
     k.red_jobs    = c->d_red_jobs.ptr;
-    k.red_idx     = c->d_red_idx.ptr;
     k.key_job_ptr = c->d_key_job_ptr.ptr;
 
     fepb200_layout& l = c->layout;
@@ -1158,6 +1178,7 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
     float4*   pos = reinterpret_cast<float4*>(c->h_step_in.ptr + sizeof(DynHead));
     const int nT  = c->layout.ntouched;
     const int* t  = c->touched.data();
+#pragma omp parallel for schedule(static) num_threads(host_threads(nT)) if (nT > 16384)
     for (int k = 0; k < nT; k++)
     {
         const float* xa = x + 3 * (size_t)t[k];
@@ -1277,17 +1298,26 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
     const float*  r32 = reinterpret_cast<const float*>(c->h_result.ptr + c->res_f64_bytes);
     if (sf.force)
     {
-        if (clear)
-        {
-            std::memset(f, 0, sizeof(float) * 3 * (size_t)l.natoms);
-        }
-        const int* t = c->touched.data();
-        for (int k = 0; k < l.ntouched; k++)
+        /* scatter of the compact forces into the caller's rvec array; only atoms that occur in
+         * the list are written (with FEPB200_CLEAR_OUTPUTS: overwritten, all others untouched) */
+        const int* t  = c->touched.data();
+        const int  nT = l.ntouched;
+#pragma omp parallel for schedule(static) num_threads(host_threads(nT)) if (nT > 16384)
+        for (int k = 0; k < nT; k++)
         {
             float* fa = f + 3 * (size_t)t[k];
-            fa[0] += r32[3 * k];
-            fa[1] += r32[3 * k + 1];
-            fa[2] += r32[3 * k + 2];
+            if (clear)
+            {
+                fa[0] = r32[3 * k];
+                fa[1] = r32[3 * k + 1];
+                fa[2] = r32[3 * k + 2];
+            }
+            else
+            {
+                fa[0] += r32[3 * k];
+                fa[1] += r32[3 * k + 1];
+                fa[2] += r32[3 * k + 2];
+            }
         }
         if (sf.shift)
         {

@@ -45,7 +45,8 @@ extern "C" {
 #define FEPB200_DO_POTENTIAL (1 << 4)
 #define FEPB200_DO_SR (1 << 5)
 /* extension bit (not in the reference): overwrite instead of accumulate into the
- * host output arrays of fepb200_compute() */
+ * host output arrays of fepb200_compute() / fepb200_download().  For the force array only
+ * the entries of atoms that occur in the pair list are written; all others are left alone. */
 #define FEPB200_CLEAR_OUTPUTS (1 << 16)
 
 /* ---- enum values: identical integers to the reference enums ------------
