@@ -27,3 +27,51 @@ def balanced_ranges(jindex, nranks: int) -> list[tuple[int, int]]:
             have = 0
         have += nrj
     return [(first[r], first[r + 1]) for r in range(nranks)]
+
+
+def touched_atoms(nblist) -> np.ndarray:
+    """Ascending atom indices that occur anywhere in the FULL list -- the compact numbering every
+    rank uses for the force part of the result block (same rule as fepb200_set_list(), which
+    mirrors setReductionMaskFromFepPairlist, src/gromacs/nbnxm/freeenergydispatch.cpp:74-89)."""
+    return np.unique(np.concatenate([np.asarray(nblist.iinr, np.int64), np.asarray(nblist.jjnr, np.int64)])).astype(np.int32)
+
+
+class ResultLayout:
+    """Host-side mirror of `struct fepb200_layout`: where forces, shift forces, energy-group
+    energies, dV/dlambda and foreign-lambda terms sit in the fp32 / fp64 result blocks."""
+
+    def __init__(self, ntouched: int, nenergrp: int, nforeign: int):
+        self.ntouched, self.nenergrp, self.nforeign = ntouched, nenergrp, nforeign
+        self.f32_words = 3 * ntouched + 3 * 45
+        self.off_fshift = 3 * ntouched
+        self.off_vc, self.off_vv = 0, nenergrp
+        self.off_dvdl = 2 * nenergrp
+        self.off_foreign_e = 2 * nenergrp + 2
+        self.off_foreign_dvdl = 2 * nenergrp + 2 + (nforeign + 1)
+        self.f64_words = 2 * nenergrp + 2 + 3 * (nforeign + 1)
+
+    def pack(self, out: dict, touched: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        """Result dict (full-size arrays) -> (fp32 block, fp64 block)."""
+        f32 = np.zeros(self.f32_words, np.float32)
+        f64 = np.zeros(self.f64_words, np.float64)
+        f32[: self.off_fshift] = np.asarray(out["f"], np.float32)[touched].ravel()
+        f32[self.off_fshift :] = np.asarray(out["fshift"], np.float32).ravel()
+        f64[self.off_vc : self.off_vc + self.nenergrp] = out["Vc"]
+        f64[self.off_vv : self.off_vv + self.nenergrp] = out["Vv"]
+        f64[self.off_dvdl : self.off_dvdl + 2] = out["dvdl"]
+        f64[self.off_foreign_e : self.off_foreign_e + self.nforeign + 1] = out["foreign_energy"]
+        f64[self.off_foreign_dvdl :] = np.asarray(out["foreign_dvdl"]).ravel()
+        return f32, f64
+
+    def unpack(self, f32: np.ndarray, f64: np.ndarray, touched: np.ndarray, natoms: int) -> dict:
+        f = np.zeros((natoms, 3), np.float32)
+        f[touched] = f32[: self.off_fshift].reshape(-1, 3)
+        return dict(
+            f=f,
+            fshift=f32[self.off_fshift :].reshape(45, 3).copy(),
+            Vc=f64[self.off_vc : self.off_vc + self.nenergrp].copy(),
+            Vv=f64[self.off_vv : self.off_vv + self.nenergrp].copy(),
+            dvdl=f64[self.off_dvdl : self.off_dvdl + 2].copy(),
+            foreign_energy=f64[self.off_foreign_e : self.off_foreign_e + self.nforeign + 1].copy(),
+            foreign_dvdl=f64[self.off_foreign_dvdl :].reshape(-1, 2).copy(),
+        )

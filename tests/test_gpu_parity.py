@@ -233,6 +233,20 @@ def _assert_lists_equal(a, b):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
 
 
+def test_layout_matches_host_mirror(ctx):
+    from fepb200.shard import ResultLayout, touched_atoms
+
+    prob = make_system(SMALL["C4"])
+    ctx.set_problem(prob)
+    lay = ctx.layout()
+    touched = touched_atoms(prob.nblist)
+    assert np.array_equal(ctx.touched_atoms(), touched)
+    mirror = ResultLayout(len(touched), prob.nenergrp_pairs, prob.n_foreign)
+    for k in ("f32_words", "f64_words", "off_fshift", "off_vc", "off_vv", "off_dvdl", "off_foreign_e",
+              "off_foreign_dvdl"):
+        assert getattr(lay, k) == getattr(mirror, k), k
+
+
 def test_list_round_trip_is_bit_exact(ctx):
     prob = make_system(SMALL["C4"])
     ctx.set_problem(prob)

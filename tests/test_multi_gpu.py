@@ -1,0 +1,68 @@
+"""The N>1 path on real GPUs: one process per GPU, NCCL all-reduce of the result block.  Skipped
+when the box has a single GPU (the host-side logic is covered on CPU by test_sharding_cpu.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, root, result_file):
+    for p in (os.path.join(root, "gromacs-fep-gpu_b200", "python"), root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    from fepb200 import params as P
+    from fepb200.distributed import ShardedFep
+    from fepb200.synth import make_system, scaled_spec
+    from oracle import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
+    prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=5))
+    sh = ShardedFep(prob, rank, rank, world)
+    lay = sh.ctx.layout()
+    out = sh.step(prob.x, prob.shiftvec, flags)
+    out2 = sh.step(prob.x, prob.shiftvec, flags | P.CLEAR_OUTPUTS, out={k: v.copy() for k, v in out.items()})
+    want = oracle.run_best(prob, flags)
+    rms = np.sqrt(np.mean((out["f"] - want["f"]) ** 2) / np.mean(want["f"] ** 2))
+    ok = rms < 1e-5 and int(lay.nri_total) == prob.nblist.nri and 0 < int(lay.nri) < prob.nblist.nri
+    for k in ("Vc", "Vv", "dvdl", "foreign_energy", "foreign_dvdl"):
+        scale = np.maximum(np.abs(want[k]), 1e-2 * np.max(np.abs(want[k])))
+        ok = ok and bool(np.all(np.abs(out[k] - want[k]) <= 1e-4 * scale))
+    ok = ok and all(np.array_equal(out[k], out2[k]) for k in out)  # deterministic, incl. the collective
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        with open(result_file, "w") as fh:
+            fh.write("ok" if int(flag.item()) == 1 else f"mismatch rms={rms:.3e}")
+    sh.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_nccl_match_oracle(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    result = str(tmp_path / "result.txt")
+    mp.spawn(_worker, args=(2, _free_port(), root, result), nprocs=2, join=True)
+    assert open(result).read() == "ok"
