@@ -1,0 +1,674 @@
+/*
+ * fep_beutler.cu -- the Beutler soft-core path as ONE kernel per step: the pass at the current
+ * lambda (forces, shift forces, Vc/Vv, dV/dlambda) and the energy-only foreign-lambda passes share
+ * one load of every pair, one evaluation of everything that does not depend on lambda, and one
+ * launch.  This is the path taken by all BASELINE.json configurations that use the Beutler
+ * soft-core without a potential switch; Gapsys, no-soft-core and pot-switch go through the generic
+ * kernels of fep_kernels.cu.
+ *
+ * What is computed (reference, src/gromacs):
+ *   FORCE part    gmxlib/nonbonded/nb_free_energy.cpp:466-1179 with computeForces == true
+ *   foreign part  nbnxm/freeenergydispatch.cpp:236-306 calling the energy-only flavour once per
+ *                 lambda point
+ * How (ours):
+ *   - flat pair space, a warp owns 32 consecutive pair slots per trip, several trips per thread;
+ *     one 16-byte pair record (fep_types.h) -> atom data -> type table is the whole load chain;
+ *   - per state the interaction is expressed with coefficients that are ZERO when the state, the
+ *     charge product, the LJ parameters or the lambda-independent part of a cut-off test rule the
+ *     term out: straight-line FMA/MUFU code instead of the reference's masks and branches; a
+ *     state nobody in the warp needs is skipped for 32 pairs at once;
+ *   - foreign lambda: sums over pairs are kept per state because every lambda dependence outside
+ *     the soft-core radius is a weight applied after the sum:
+ *         E(p)         = sum_s lfacC[s][p] (C_s + Cp_s[p]) + lfacV[s][p] (G_s + V_s[p])
+ *         dVdl_coul(p) = (C_B + Cp_B[p]) - (C_A + Cp_A[p]),  dVdl_vdw(p) = (G_B + V_B[p]) - (G_A + V_A[p])
+ *     C_s: RF / Ewald / exclusion terms linear in qq[s] (:1023-1101) plus the whole Coulomb energy
+ *     of state s when alphaCoul == 0; G_s: LJ-PME grid term (:1103-1136); V_s[p], Cp_s[p]: LJ and
+ *     Coulomb energy with the soft-core radius of point p (:804-971).  State-A sums and per-pair
+ *     B-minus-A DIFFERENCES are accumulated, so pairs with identical end states cancel exactly,
+ *     as they do in the reference where the difference is formed per pair (:1005-1020).
+ *     (energy-only passes have no soft-core term in dV/dlambda: it is built from force terms,
+ *     which are zero when computeForces == false, :754-755,1005-1013.)
+ *   - the lambda factors arrive as a __grid_constant__ kernel parameter: constant-bank operands
+ *     of the FMAs, no loads in the loop over lambda points;
+ *   - forces leave through the atom-sorted scatter of fep_types.h (no atomics).
+ *
+ * MODE 0: alphaCoul == 0 (GROMACS default sc-coul = no): rC == r, per point and state
+ *         d = alphaVdwEff sigma6 sclfacV + r^6 ; 1/d by MUFU.RCP ; LJ from 1/d : 8 instructions.
+ * MODE 1: alphaCoul == alphaVdw and lambdaCoul == lambdaVdw at every point: one radius; the
+ *         Coulomb part needs d^(-1/6) = ex2(-lg2(d)/6).
+ * MODE 2: separate Coulomb and LJ radii.
+ */
+#include "fep_pair_math.cuh"
+
+#define FULL_MASK 0xffffffffu
+
+struct BeutlerStep
+{
+    /* current lambda (nb_free_energy.cpp:420-449) */
+    float cur_lfc[2], cur_lfv[2], cur_sclc[2], cur_sclv[2], cur_scdlc[2], cur_scdlv[2];
+    /* chunk of foreign lambda points */
+    float sclv[2][FEP_FB_MAXC]; /* soft-core lambda factor, vdw, per state */
+    float sclc[2][FEP_FB_MAXC]; /* same for coulomb                         */
+    float lfc[2][FEP_FB_MAXC];  /* {1-lambda_c, lambda_c}                   */
+    float lfv[2][FEP_FB_MAXC];
+    int   p0, np;               /* first point of the chunk, valid points   */
+    int   want_shift;           /* also store segment forces sorted by shift vector */
+    int   tile_pairs, n_tiles;  /* pair tile of one CTA for this launch     */
+};
+
+/* sums N8*8 per-lane values over the warp; afterwards lane l < 8 holds, for group g, the value
+ * with index 8*g + 4*(l&1) + 2*((l>>1)&1) + ((l>>2)&1) */
+template<int N8>
+__device__ __forceinline__ void warp_sum_groups(float (&v)[N8 * 8], float (&out)[N8], int lane)
+{
+#pragma unroll
+    for (int g = 0; g < N8; g++)
+    {
+        float a[4], b[2], c;
+        {
+            const bool up = lane & 1;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                const float send = up ? v[8 * g + i] : v[8 * g + i + 4];
+                const float keep = up ? v[8 * g + i + 4] : v[8 * g + i];
+                a[i]             = keep + __shfl_xor_sync(FULL_MASK, send, 1);
+            }
+        }
+        {
+            const bool up = lane & 2;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+            {
+                const float send = up ? a[i] : a[i + 2];
+                const float keep = up ? a[i + 2] : a[i];
+                b[i]             = keep + __shfl_xor_sync(FULL_MASK, send, 2);
+            }
+        }
+        {
+            const bool  up   = lane & 4;
+            const float send = up ? b[0] : b[1];
+            const float keep = up ? b[1] : b[0];
+            c                = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+        }
+        c += __shfl_xor_sync(FULL_MASK, c, 8);
+        c += __shfl_xor_sync(FULL_MASK, c, 16);
+        out[g] = c;
+    }
+}
+
+/* lambda-independent data of one state of one pair; every coefficient is zero when the term it
+ * multiplies does not apply */
+struct StateConsts
+{
+    float c6_6, c12_12, shiftc, kv, kc, qe, qsh, qkrf;
+};
+
+/* One foreign lambda point of one state: LJ energy vv (and Coulomb energy vc when the Coulomb
+ * radius is soft-cored).  8 instructions in MODE 0. */
+template<bool EWALD, int MODE>
+__device__ __forceinline__ void fb_point(const StateConsts& st, float r6, float sclv, float sclc, float thr_v,
+                                         float rcoulomb6, float& vv, float& vc)
+{
+    const float dv  = fmaf(st.kv, sclv, r6);
+    const float ri6 = fminf(fep_rcp(dv), FEP_MAX_RINV6);
+    vv              = fmaf(ri6, fmaf(st.c12_12, ri6, -st.c6_6), st.shiftc);
+    vv              = dv < thr_v ? vv : 0.0f;
+    if (MODE != 0)
+    {
+        const float dc  = (MODE == 1) ? dv : fmaf(st.kc, sclc, r6);
+        const float lg  = fep_lg2(dc);
+        const float ric = fep_ex2(lg * (-1.0f / 6.0f));
+        if (EWALD)
+        {
+            vc = fmaf(st.qe, ric, st.qsh);
+        }
+        else
+        {
+            const float rc2 = fep_ex2(lg * (1.0f / 3.0f));
+            vc              = fmaf(st.qe, ric, fmaf(st.qkrf, rc2, st.qsh));
+            vc              = dc < rcoulomb6 ? vc : 0.0f;
+        }
+    }
+}
+
+/* One state at the current lambda WITH forces (:747-1020).  Adds to the scalar force (already
+ * multiplied by r^(p-2)), the lambda-weighted energies and dV/dlambda incl. the soft-core term. */
+template<bool EWALD, int MODE>
+__device__ __forceinline__ void fb_force_state(const StateConsts& st, const BeutlerStep& bs, int s, float r2, float r6,
+                                               float r4, float rinv, float thr_v, float rcoulomb6, float krf,
+                                               float crf, float sh_ewald, float& fscal, float& vctot, float& vvtot,
+                                               float& dc, float& dv)
+{
+    const float sign = s == 0 ? -1.0f : 1.0f;
+    /* Lennard-Jones with the soft-core radius rV^6 = alpha sigma6 sclfac + r^6 */
+    const float d_v  = fmaf(st.kv, bs.cur_sclv[s], r6);
+    const float rp_v = fep_rcp(d_v);
+    const float ri6  = fminf(rp_v, FEP_MAX_RINV6);
+    const float t12  = st.c12_12 * ri6;
+    float       vv   = fmaf(ri6, t12 - st.c6_6, st.shiftc);
+    float       fv   = ri6 * fmaf(12.0f, t12, -6.0f * st.c6_6); /* V12 - V6 */
+    const bool  on_v = d_v < thr_v;
+    vv               = on_v ? vv : 0.0f;
+    fv               = on_v ? fv : 0.0f;
+    /* F rV^-6 r^4, the two factors combined first (stays in fp32 range for hard cores at r -> 0) */
+    fscal = fmaf(bs.cur_lfv[s] * fv, rp_v * r4, fscal);
+    vvtot = fmaf(bs.cur_lfv[s], vv, vvtot);
+    dv    = fmaf(sign, vv, dv);
+    dv    = fmaf((bs.cur_lfv[s] * bs.cur_scdlv[s] * st.kv) * fv, rp_v, dv); /* (:1010-1012), kv = alphaEff sigma6 */
+
+    float vc, fc, w_c;
+    if (MODE == 0)
+    {
+        /* rC == r */
+        if (EWALD)
+        {
+            vc = st.qe * (rinv - sh_ewald);
+            fc = st.qe * rinv;
+        }
+        else
+        {
+            const float k2 = krf * r2;
+            vc             = st.qe * (rinv + k2 - crf);
+            fc             = st.qe * (rinv - 2.0f * k2);
+        }
+        w_c = rinv * rinv; /* r^-6 r^4 */
+    }
+    else
+    {
+        const float d_c  = (MODE == 1) ? d_v : fmaf(st.kc, bs.cur_sclc[s], r6);
+        const float rp_c = (MODE == 1) ? rp_v : fep_rcp(d_c);
+        const float lg   = fep_lg2(d_c);
+        const float ric  = fep_ex2(lg * (-1.0f / 6.0f));
+        if (EWALD)
+        {
+            vc = fmaf(st.qe, ric, st.qsh);
+            fc = st.qe * ric;
+        }
+        else
+        {
+            const float rc2 = fep_ex2(lg * (1.0f / 3.0f));
+            const float k2  = st.qkrf * rc2;
+            vc              = fmaf(st.qe, ric, k2 + st.qsh);
+            fc              = fmaf(st.qe, ric, -2.0f * k2);
+            const bool on_c = d_c < rcoulomb6;
+            vc              = on_c ? vc : 0.0f;
+            fc              = on_c ? fc : 0.0f;
+        }
+        w_c = rp_c * r4;
+        dc  = fmaf((bs.cur_lfc[s] * bs.cur_scdlc[s] * st.kc) * fc, rp_c, dc); /* (:1007-1009) */
+    }
+    fscal = fmaf(bs.cur_lfc[s] * fc, w_c, fscal);
+    vctot = fmaf(bs.cur_lfc[s], vc, vctot);
+    dc    = fmaf(sign, vc, dc);
+}
+
+template<int MODE, int C, bool FORCE>
+struct AccLayout
+{
+    static constexpr int NPER = (MODE == 0) ? 2 : 4; /* per-point: V_A DV (Cp_A DCp)                */
+    static constexpr int NFOR = C > 0 ? NPER * C + 4 : 0; /* + C_A DC G_A DG                         */
+    static constexpr int NACC = NFOR + (FORCE ? 2 : 0);  /* + dV/dlambda coul, vdw at current lambda */
+    static constexpr int N8   = (NACC + 7) / 8;
+    static constexpr int iCA = NPER * C, iDC = iCA + 1, iGA = iCA + 2, iDG = iCA + 3;
+    static constexpr int iCUR = NFOR;
+    /* register budget: 4 CTAs of 128 threads per SM up to ~56 accumulators, else 2 */
+    static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : 4;
+};
+
+template<bool EWALD, int MODE, int C, bool FORCE>
+__global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
+        fep_beutler_kernel(const __grid_constant__ KernelArgs ka, const __grid_constant__ BeutlerStep bs)
+{
+    using L            = AccLayout<MODE, C, FORCE>;
+    constexpr int N8   = L::N8 > 0 ? L::N8 : 1;
+    constexpr int NW   = FEP_FB_CTA / 32;
+    __shared__ float  s_red[NW][N8 * 8];
+    __shared__ double s_sum[N8 * 8];
+
+    const int tid  = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    /* Layout: [0,C) V_A, [C,2C) DV, MODE>0: [2C,3C) Cp_A, [3C,4C) DCp, then C_A DC G_A DG,
+     * then (FORCE) dV/dlambda_coul, dV/dlambda_vdw of the current-lambda pass. */
+    float acc[N8 * 8];
+#pragma unroll
+    for (int i = 0; i < N8 * 8; i++)
+    {
+        acc[i] = 0.0f;
+    }
+
+    const float thr_v = ka.vdw_ewald ? __int_as_float(0x7f800000) : ka.rvdw6; /* LJ-PME tests r, below */
+    const int   base  = blockIdx.x * bs.tile_pairs;
+    const int   end   = min(base + bs.tile_pairs, ka.n_pairs);
+
+    /* the pair record of the NEXT trip is fetched while the current one is evaluated, which takes
+     * the streamed (DRAM) load out of the dependent chain record -> atom data -> type table */
+    int4 rec_next = make_int4(0, 0, -1, 0);
+    if (base + warp * 32 + lane < end)
+    {
+        rec_next = __ldg(ka.pair4 + base + warp * 32 + lane);
+    }
+    for (int w0 = base + warp * 32; w0 < end; w0 += FEP_FB_CTA)
+    {
+        const int  slot   = w0 + lane;
+        const bool active = slot < end;
+        const int4 rec    = rec_next;
+        rec_next          = make_int4(0, 0, -1, 0);
+        if (slot + FEP_FB_CTA < end)
+        {
+            rec_next = __ldg(ka.pair4 + slot + FEP_FB_CTA);
+        }
+        const bool   excluded = rec.x < 0;
+        const int    cj       = rec.x & 0x7fffffff;
+        const int    ci       = rec.y & (FEP_MAX_TOUCHED - 1);
+        const float4 xi       = __ldg(ka.pos4 + ci);
+        const float4 sh       = ka.dyn->shiftvec[(rec.y >> 24) & 63];
+        const float4 xj       = __ldg(ka.pos4 + cj);
+        /* the reference shifts the i atom first (:478-480) */
+        const float dx = (sh.x + xi.x) - xj.x, dy = (sh.y + xi.y) - xj.y, dz = (sh.z + xi.z) - xj.z;
+        float       r2      = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool  within  = r2 < ka.rcut_max2;
+        const bool  contrib = active && (within || excluded); /* :667 */
+
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f, vctot = 0.0f, vvtot = 0.0f;
+
+        if (__any_sync(FULL_MASK, contrib))
+        {
+            const float4 pi = __ldg(ka.par4 + ci);
+            const float4 pq = __ldg(ka.par4 + cj);
+            const float4 ta = __ldg(ka.typetab + (ka.ntype * __float_as_int(pi.z) + __float_as_int(pq.z)));
+            const float4 tb = __ldg(ka.typetab + (ka.ntype * __float_as_int(pi.w) + __float_as_int(pq.w)));
+            const float  m  = contrib ? 1.0f : 0.0f;
+            const float  qq[2]  = { (ka.epsfac * pi.x) * pq.x * m, (ka.epsfac * pi.y) * pq.y * m };
+            const float  c6[2]  = { ta.x, tb.x }, c12[2] = { ta.y, tb.y }, sig6[2] = { ta.z, tb.z };
+            const float  c6g[2] = { ta.w * m, tb.w * m };
+            const bool   hard   = (ta.y > 0.0f && tb.y > 0.0f); /* :597-628 */
+            const float  a_v    = hard ? 0.0f : ka.alpha_v;
+            const float  a_c    = hard ? 0.0f : ka.alpha_c;
+            const bool   self   = (ci == cj);
+
+            FepPair pr;
+            r2      = fmaxf(r2, FEP_MIN_RSQ);
+            pr.r2   = r2;
+            pr.rinv = fep_rsqrt(r2);
+            pr.r    = r2 * pr.rinv;
+            const float r4   = r2 * r2;
+            const float r6   = r4 * r2;
+            const bool  incl = contrib && within && !excluded;
+
+            float fscal = 0.0f, dcur_c = 0.0f, dcur_v = 0.0f;
+
+            /* lambda-independent correction terms, linear in qq[s] / c6grid[s] */
+            {
+                float xc, fcorr, xv, fvcorr;
+                fep_corrections<EWALD, FORCE>(ka, pr, excluded, self, xc, fcorr, xv, fvcorr);
+                const float cA = qq[0] * xc, cB = qq[1] * xc, gA = c6g[0] * xv, gB = c6g[1] * xv;
+                if (C > 0)
+                {
+                    acc[L::iCA] += cA;
+                    acc[L::iDC] += cB - cA;
+                    acc[L::iGA] += gA;
+                    acc[L::iDG] += gB - gA;
+                }
+                if (FORCE)
+                {
+                    vctot  = bs.cur_lfc[0] * cA + bs.cur_lfc[1] * cB;
+                    vvtot  = bs.cur_lfv[0] * gA + bs.cur_lfv[1] * gB;
+                    dcur_c = cB - cA;
+                    dcur_v = gB - gA;
+                    fscal  = (bs.cur_lfc[0] * qq[0] + bs.cur_lfc[1] * qq[1]) * fcorr
+                            + (bs.cur_lfv[0] * c6g[0] + bs.cur_lfv[1] * c6g[1]) * fvcorr;
+                }
+            }
+
+            StateConsts st[2];
+            bool        elec_on[2], vdw_on[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+            {
+                const bool nz = incl && (qq[s] != 0.0f || c6[s] != 0.0f || c12[s] != 0.0f); /* :747-752 */
+                /* lambda-independent parts of the interaction tests (:805-812, :880-890) */
+                elec_on[s] = nz && qq[s] != 0.0f;
+                vdw_on[s]  = nz && (c6[s] != 0.0f || c12[s] != 0.0f);
+                if (EWALD || MODE == 0)
+                {
+                    elec_on[s] = elec_on[s] && pr.r < ka.rcoulomb;
+                }
+                if (ka.vdw_ewald)
+                {
+                    vdw_on[s] = vdw_on[s] && pr.r < ka.rvdw;
+                }
+                st[s].qe     = elec_on[s] ? qq[s] : 0.0f;
+                st[s].c6_6   = vdw_on[s] ? c6[s] * (1.0f / 6.0f) : 0.0f;
+                st[s].c12_12 = vdw_on[s] ? c12[s] * (1.0f / 12.0f) : 0.0f;
+                st[s].shiftc = st[s].c12_12 * ka.rep_cpot - st[s].c6_6 * ka.disp_cpot;
+                if (ka.vdw_ewald)
+                {
+                    st[s].shiftc = fmaf(vdw_on[s] ? c6g[s] : 0.0f, ka.sh_lj_ewald * (1.0f / 6.0f), st[s].shiftc);
+                }
+                st[s].kv   = a_v * sig6[s];
+                st[s].kc   = a_c * sig6[s];
+                st[s].qsh  = EWALD ? -st[s].qe * ka.sh_ewald : -st[s].qe * ka.crf;
+                st[s].qkrf = st[s].qe * ka.krf;
+            }
+            if (C > 0 && MODE == 0)
+            {
+                /* Coulomb radius not soft-cored: rC == r, the whole term is lambda-independent */
+                const float k2  = EWALD ? -ka.sh_ewald : fmaf(ka.krf, r2, -ka.crf);
+                const float vcA = st[0].qe * (pr.rinv + k2), vcB = st[1].qe * (pr.rinv + k2);
+                acc[L::iCA] += vcA;
+                acc[L::iDC] += vcB - vcA;
+            }
+            /* a state nobody in the warp needs is skipped; the choice is made once per 32 pairs */
+            const bool needA = __any_sync(FULL_MASK, vdw_on[0] || elec_on[0]);
+            const bool needB = __any_sync(FULL_MASK, vdw_on[1] || elec_on[1]);
+
+            if (FORCE)
+            {
+                if (needA)
+                {
+                    fb_force_state<EWALD, MODE>(st[0], bs, 0, r2, r6, r4, pr.rinv, thr_v, ka.rcoulomb6, ka.krf, ka.crf,
+                                                ka.sh_ewald, fscal, vctot, vvtot, dcur_c, dcur_v);
+                }
+                if (needB)
+                {
+                    fb_force_state<EWALD, MODE>(st[1], bs, 1, r2, r6, r4, pr.rinv, thr_v, ka.rcoulomb6, ka.krf, ka.crf,
+                                                ka.sh_ewald, fscal, vctot, vvtot, dcur_c, dcur_v);
+                }
+                fx = fscal * dx;
+                fy = fscal * dy;
+                fz = fscal * dz;
+                acc[L::iCUR]     += dcur_c;
+                acc[L::iCUR + 1] += dcur_v;
+            }
+
+            if (C > 0)
+            {
+                const bool pA = __any_sync(FULL_MASK, vdw_on[0] || (MODE != 0 && elec_on[0]));
+                const bool pB = __any_sync(FULL_MASK, vdw_on[1] || (MODE != 0 && elec_on[1]));
+                if (pA && pB)
+                {
+#pragma unroll
+                    for (int p = 0; p < C; p++)
+                    {
+                        float vvA, vvB, vcA = 0.0f, vcB = 0.0f;
+                        fb_point<EWALD, MODE>(st[0], r6, bs.sclv[0][p], bs.sclc[0][p], thr_v, ka.rcoulomb6, vvA, vcA);
+                        fb_point<EWALD, MODE>(st[1], r6, bs.sclv[1][p], bs.sclc[1][p], thr_v, ka.rcoulomb6, vvB, vcB);
+                        acc[p]     += vvA;
+                        acc[C + p] += vvB - vvA;
+                        if (MODE != 0)
+                        {
+                            acc[2 * C + p] += vcA;
+                            acc[3 * C + p] += vcB - vcA;
+                        }
+                    }
+                }
+                else if (pA)
+                {
+#pragma unroll
+                    for (int p = 0; p < C; p++)
+                    {
+                        float vvA, vcA = 0.0f;
+                        fb_point<EWALD, MODE>(st[0], r6, bs.sclv[0][p], bs.sclc[0][p], thr_v, ka.rcoulomb6, vvA, vcA);
+                        acc[p]     += vvA;
+                        acc[C + p] -= vvA;
+                        if (MODE != 0)
+                        {
+                            acc[2 * C + p] += vcA;
+                            acc[3 * C + p] -= vcA;
+                        }
+                    }
+                }
+                else if (pB)
+                {
+#pragma unroll
+                    for (int p = 0; p < C; p++)
+                    {
+                        float vvB, vcB = 0.0f;
+                        fb_point<EWALD, MODE>(st[1], r6, bs.sclv[1][p], bs.sclc[1][p], thr_v, ka.rcoulomb6, vvB, vcB);
+                        acc[C + p] += vvB;
+                        if (MODE != 0)
+                        {
+                            acc[3 * C + p] += vcB;
+                        }
+                    }
+                }
+            }
+        }
+
+        if (FORCE)
+        {
+            if (active)
+            {
+                /* the j atom receives -f: scattered to this pair's own slot in the atom-sorted
+                 * buffer (unique destination, no atomics; skipped pairs write their zero) */
+                ka.fsorted[__ldg(ka.pair_dst + slot)] = make_float4(-fx, -fy, -fz, 0.0f);
+            }
+            /* segmented sum over the lanes of one i-entry: i force and Vc/Vv of the segment */
+            const int      entry    = rec.z;
+            const int      e_prev   = __shfl_up_sync(FULL_MASK, entry, 1);
+            const bool     boundary = (lane == 0) || (entry != e_prev);
+            const unsigned bmask    = __ballot_sync(FULL_MASK, boundary);
+            const unsigned hmask    = __ballot_sync(FULL_MASK, boundary && active);
+            const unsigned above    = bmask & ~((2u << lane) - 1u);
+            const int      after    = (above ? (__ffs(above) - 1) : 32) - 1 - lane;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const float ox = __shfl_down_sync(FULL_MASK, fx, o);
+                const float oy = __shfl_down_sync(FULL_MASK, fy, o);
+                const float oz = __shfl_down_sync(FULL_MASK, fz, o);
+                const float oc = __shfl_down_sync(FULL_MASK, vctot, o);
+                const float ov = __shfl_down_sync(FULL_MASK, vvtot, o);
+                if (o <= after)
+                {
+                    fx += ox;
+                    fy += oy;
+                    fz += oz;
+                    vctot += oc;
+                    vvtot += ov;
+                }
+            }
+            if (boundary && active)
+            {
+                const int  h  = __ldg(ka.warp_hbase + (w0 >> 5)) + __popc(hmask & ((1u << lane) - 1u));
+                const int4 sd = __ldg(ka.seg_dst + h);
+                const float4 fi = make_float4(fx, fy, fz, 0.0f);
+                ka.fsorted[sd.x] = fi;
+                if (bs.want_shift)
+                {
+                    ka.fshift_sorted[sd.y] = fi;
+                }
+                ka.ev2[sd.z] = make_float2(vctot, vvtot);
+            }
+        }
+    }
+
+    if (L::NACC == 0)
+    {
+        return;
+    }
+    float red[N8];
+    warp_sum_groups<N8>(acc, red, lane);
+    if (lane < 8)
+    {
+        const int k = 4 * (lane & 1) + 2 * ((lane >> 1) & 1) + ((lane >> 2) & 1);
+#pragma unroll
+        for (int g = 0; g < N8; g++)
+        {
+            s_red[warp][8 * g + k] = red[g];
+        }
+    }
+    __syncthreads();
+    if (tid < L::NACC)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++)
+        {
+            s += (double)s_red[w][tid];
+        }
+        s_sum[tid] = s;
+    }
+    __syncthreads();
+    if (FORCE && tid < 2)
+    {
+        ka.cta_part[(size_t)tid * bs.n_tiles + blockIdx.x] = s_sum[L::iCUR + tid];
+    }
+    if (C > 0 && tid < bs.np)
+    {
+        const int    p  = tid;
+        const double CA = s_sum[L::iCA] + (MODE != 0 ? s_sum[2 * C + p] : 0.0);
+        const double DC = s_sum[L::iDC] + (MODE != 0 ? s_sum[3 * C + p] : 0.0);
+        const double GA = s_sum[L::iGA] + s_sum[p];
+        const double DG = s_sum[L::iDG] + s_sum[C + p];
+        /* E = lfacC[A] C_A + lfacC[B] C_B + lfacV[A] G_A + lfacV[B] G_B with X_B = X_A + DX */
+        const double e = (double)bs.lfc[0][p] * CA + (double)bs.lfc[1][p] * (CA + DC) + (double)bs.lfv[0][p] * GA
+                         + (double)bs.lfv[1][p] * (GA + DG);
+        const size_t o = (size_t)(3 * (bs.p0 + p)) * bs.n_tiles + blockIdx.x;
+        ka.for_part[o]                  = e;
+        ka.for_part[o + bs.n_tiles]     = DC;
+        ka.for_part[o + 2 * bs.n_tiles] = DG;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+template<bool EWALD, int MODE, int C, bool FORCE>
+static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream)
+{
+    fep_beutler_kernel<EWALD, MODE, C, FORCE><<<bs.n_tiles, FEP_FB_CTA, 0, stream>>>(ka, bs);
+}
+
+template<bool EWALD, int MODE, bool FORCE>
+static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cudaStream_t stream)
+{
+    switch (c)
+    {
+#define FEP_FB_CASE(N) \
+    case N: launch_one<EWALD, MODE, N, FORCE>(ka, bs, stream); return true;
+        FEP_FB_CASE(1)
+        FEP_FB_CASE(2)
+        FEP_FB_CASE(3)
+        FEP_FB_CASE(4)
+        FEP_FB_CASE(6)
+        FEP_FB_CASE(7)
+        FEP_FB_CASE(8)
+        FEP_FB_CASE(11)
+        FEP_FB_CASE(14)
+        FEP_FB_CASE(16)
+        FEP_FB_CASE(21)
+        FEP_FB_CASE(24)
+#undef FEP_FB_CASE
+        case 0:
+            if (FORCE)
+            {
+                launch_one<EWALD, MODE, 0, true>(ka, bs, stream);
+                return true;
+            }
+            return false;
+        default: return false;
+    }
+}
+
+template<bool EWALD, bool FORCE>
+static bool launch_mode(const KernelArgs& ka, const BeutlerStep& bs, int mode, int c, cudaStream_t stream)
+{
+    return mode == 0   ? launch_size<EWALD, 0, FORCE>(ka, bs, c, stream)
+           : mode == 1 ? launch_size<EWALD, 1, FORCE>(ka, bs, c, stream)
+                       : launch_size<EWALD, 2, FORCE>(ka, bs, c, stream);
+}
+
+static const int c_sizes[] = { 1, 2, 3, 4, 6, 7, 8, 11, 14, 16, 21, 24 };
+
+extern "C" int fep_beutler_chunk_size(int n_points, int n_chunks_wanted)
+{
+    if (n_chunks_wanted < 1)
+    {
+        n_chunks_wanted = 1;
+    }
+    const int need = (n_points + n_chunks_wanted - 1) / n_chunks_wanted;
+    for (int c : c_sizes)
+    {
+        if (c >= need)
+        {
+            return c;
+        }
+    }
+    return FEP_FB_MAXC;
+}
+
+/* accumulators of the largest kernel a step launches, for the tile sizing on the host */
+extern "C" int fep_beutler_ctas_per_sm(int mode, int c, int force)
+{
+    const int nper = mode == 0 ? 2 : 4;
+    const int nacc = (c > 0 ? nper * c + 4 : 0) + (force ? 2 : 0);
+    return (nacc + (force ? 10 : 0) > 56) ? 2 : 4;
+}
+
+/* One step of the Beutler path: `do_force` -> the pass at the current lambda is computed (fused
+ * with the first chunk of foreign points when `do_foreign`); `pts` are the HOST copies of the
+ * lambda points, pts[0] = current.  Returns cudaSuccess (0) or an error code. */
+extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mode, const LambdaPoint* cur,
+                                  const LambdaPoint* pts, int do_force, int do_foreign, int want_shift,
+                                  cudaStream_t stream, long long* counter)
+{
+    const KernelArgs& ka = *kap;
+    const int         c  = do_foreign ? ka.chunk_points : 0;
+    const int         np = do_foreign ? ka.n_points : 0;
+    BeutlerStep       bs;
+    for (int s = 0; s < 2; s++)
+    {
+        bs.cur_lfc[s]   = cur->lfac_c[s];
+        bs.cur_lfv[s]   = cur->lfac_v[s];
+        bs.cur_sclc[s]  = cur->sclfac_c[s];
+        bs.cur_sclv[s]  = cur->sclfac_v[s];
+        bs.cur_scdlc[s] = cur->scdl_c[s];
+        bs.cur_scdlv[s] = cur->scdl_v[s];
+    }
+    bs.want_shift = want_shift;
+    bs.tile_pairs = do_foreign ? ka.tile_pairs : ka.pass_tile_pairs;
+    bs.n_tiles    = do_foreign ? ka.n_tiles : ka.pass_n_tiles;
+    bool first    = true;
+    for (int p0 = 0; p0 < np || first; p0 += (c > 0 ? c : 1))
+    {
+        bs.p0 = p0;
+        bs.np = c > 0 ? ((np - p0 < c) ? np - p0 : c) : 0;
+        for (int p = 0; p < FEP_FB_MAXC; p++)
+        {
+            /* padding points repeat the last valid one; their results are not written */
+            const int q = c > 0 ? p0 + (p < bs.np ? p : bs.np - 1) : 0;
+            for (int s = 0; s < 2; s++)
+            {
+                bs.sclv[s][p] = c > 0 ? pts[q].sclfac_v[s] : 0.0f;
+                bs.sclc[s][p] = c > 0 ? pts[q].sclfac_c[s] : 0.0f;
+                bs.lfc[s][p]  = c > 0 ? pts[q].lfac_c[s] : 0.0f;
+                bs.lfv[s][p]  = c > 0 ? pts[q].lfac_v[s] : 0.0f;
+            }
+        }
+        const bool force = first && do_force;
+        bool       ok;
+        if (force)
+        {
+            ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, stream)
+                            : launch_mode<false, true>(ka, bs, mode, c, stream);
+        }
+        else
+        {
+            ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, stream)
+                            : launch_mode<false, false>(ka, bs, mode, c, stream);
+        }
+        if (!ok)
+        {
+            return (int)cudaErrorInvalidValue;
+        }
+        (*counter)++;
+        first = false;
+        if (c == 0)
+        {
+            break;
+        }
+    }
+    return (int)cudaGetLastError();
+}

@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         int           n;
         if (b < 2)
         {
-            src = ka.cta_part + (size_t)b * ka.n_cta;
-            n   = ka.n_cta;
+            src = ka.cta_part + (size_t)b * ka.n_parts;
+            n   = ka.n_parts;
         }
         else
         {
@@ -555,38 +555,58 @@ __global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restri
 /* launchers                                                                                   */
 /* ------------------------------------------------------------------------------------------- */
 template<int SC, bool EWALD>
-static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStream_t stream, long long* counter,
-                                   cudaEvent_t* ev, const LambdaPoint* host_pts, int foreign_mode)
+static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t stream, long long* counter,
+                                   cudaEvent_t* ev, const LambdaPoint* host_cur, const LambdaPoint* host_pts,
+                                   int beutler_mode)
 {
+    const bool foreign = sf.foreign && ka.n_points > 0;
+    const bool beutler = SC == FEP_SC_BEUTLER && beutler_mode >= 0;
+    /* fep_beutler.cu.  Small lists are latency-bound: one launch computes the pass at the current
+     * lambda and the first chunk of foreign points from one load of each pair.  On large lists the
+     * fused kernel's register count costs more occupancy than the shared load saves, so the pass
+     * and the foreign chunks are separate launches of the same code. */
+    const bool one_launch = beutler && sf.force && foreign && ka.fuse_pass_and_foreign;
+    int        rc         = 0;
     if (ev)
     {
         cudaEventRecord(ev[0], stream);
     }
-    if (ka.n_cta > 0)
+    ka.n_parts = 0;
+    if (ka.n_pairs > 0 && !one_launch)
     {
-        if (sf.force)
+        if (beutler && sf.force)
         {
-            fep_pass_kernel<SC, EWALD, true><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, sf.shift);
+            rc = fep_launch_beutler(&ka, EWALD ? 1 : 0, beutler_mode, host_cur, host_pts, 1, 0, sf.shift, stream, counter);
+            ka.n_parts = ka.pass_n_tiles;
         }
         else
         {
-            fep_pass_kernel<SC, EWALD, false><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, 0);
+            /* generic pass kernel, one thread per pair */
+            if (sf.force)
+            {
+                fep_pass_kernel<SC, EWALD, true><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, sf.shift);
+            }
+            else
+            {
+                fep_pass_kernel<SC, EWALD, false><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, 0);
+            }
+            ka.n_parts = ka.n_cta;
+            (*counter)++;
         }
-        (*counter)++;
     }
     if (ev)
     {
         cudaEventRecord(ev[1], stream);
     }
-    if (ka.n_cta > 0 && sf.foreign && ka.n_points > 0)
+    if (rc == 0 && ka.n_pairs > 0 && foreign)
     {
-        if (SC == FEP_SC_BEUTLER && foreign_mode >= 0)
+        if (beutler)
         {
-            /* specialised kernels of fep_foreign_beutler.cu, one launch per chunk of lambda points */
-            const int rc = fep_launch_foreign_beutler(&ka, EWALD ? 1 : 0, foreign_mode, host_pts, stream, counter);
-            if (rc != 0)
+            rc = fep_launch_beutler(&ka, EWALD ? 1 : 0, beutler_mode, host_cur, host_pts, one_launch ? 1 : 0, 1,
+                                    one_launch ? sf.shift : 0, stream, counter);
+            if (one_launch)
             {
-                return rc > 0 ? (cudaError_t)rc : cudaErrorInvalidValue;
+                ka.n_parts = ka.n_tiles;
             }
         }
         else
@@ -596,6 +616,10 @@ static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStrea
             (*counter)++;
         }
     }
+    if (rc != 0)
+    {
+        return (cudaError_t)rc;
+    }
     if (ev)
     {
         cudaEventRecord(ev[2], stream);
@@ -604,18 +628,24 @@ static cudaError_t launch_variants(const KernelArgs& ka, StepFlags sf, cudaStrea
 }
 
 extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
-                               long long* counter, cudaEvent_t* ev, const LambdaPoint* host_pts, int foreign_mode)
+                               long long* counter, cudaEvent_t* ev, const LambdaPoint* host_cur,
+                               const LambdaPoint* host_pts, int beutler_mode)
 {
-    const KernelArgs& ka = *kap;
-    cudaError_t       err;
+    KernelArgs  ka = *kap; /* local copy: n_parts depends on which pass kernel ran */
+    cudaError_t err;
     switch (softcore * 2 + (elec_ewald ? 1 : 0))
     {
-        case FEP_SC_NONE * 2 + 0: err = launch_variants<FEP_SC_NONE, false>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
-        case FEP_SC_NONE * 2 + 1: err = launch_variants<FEP_SC_NONE, true>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
-        case FEP_SC_BEUTLER * 2 + 0: err = launch_variants<FEP_SC_BEUTLER, false>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
-        case FEP_SC_BEUTLER * 2 + 1: err = launch_variants<FEP_SC_BEUTLER, true>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
-        case FEP_SC_GAPSYS * 2 + 0: err = launch_variants<FEP_SC_GAPSYS, false>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
-        case FEP_SC_GAPSYS * 2 + 1: err = launch_variants<FEP_SC_GAPSYS, true>(ka, sf, stream, counter, ev, host_pts, foreign_mode); break;
+#define FEP_CASE(SCV, EW) \
+    case SCV * 2 + (EW ? 1 : 0): \
+        err = launch_variants<SCV, EW>(ka, sf, stream, counter, ev, host_cur, host_pts, beutler_mode); \
+        break;
+        FEP_CASE(FEP_SC_NONE, false)
+        FEP_CASE(FEP_SC_NONE, true)
+        FEP_CASE(FEP_SC_BEUTLER, false)
+        FEP_CASE(FEP_SC_BEUTLER, true)
+        FEP_CASE(FEP_SC_GAPSYS, false)
+        FEP_CASE(FEP_SC_GAPSYS, true)
+#undef FEP_CASE
         default: return (int)cudaErrorInvalidValue;
     }
     if (err != cudaSuccess)

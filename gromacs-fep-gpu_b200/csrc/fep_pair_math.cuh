@@ -360,16 +360,15 @@ template<int SC>
 __device__ __forceinline__ bool fep_load_pair(const KernelArgs& ka, int slot, FepPair& pr, float& dx, float& dy,
                                               float& dz, bool& excluded, bool& self, int& entry)
 {
-    const int pj  = __ldg(ka.pair_j + slot);
-    entry         = __ldg(ka.pair_e + slot);
-    excluded      = pj < 0;
-    const int  cj = pj & 0x7fffffff;
-    const int4 en = __ldg(ka.ent4 + entry);
-    const int  ci = en.x;
-    self          = (ci == cj);
+    const int4 rec = __ldg(ka.pair4 + slot);
+    entry          = rec.z;
+    excluded       = rec.x < 0;
+    const int cj   = rec.x & 0x7fffffff;
+    const int ci   = rec.y & (FEP_MAX_TOUCHED - 1);
+    self           = (ci == cj);
 
     const float4 xi = __ldg(ka.pos4 + ci);
-    const float4 sh = ka.dyn->shiftvec[en.y];
+    const float4 sh = ka.dyn->shiftvec[rec.y >> 24];
     const float4 xj = __ldg(ka.pos4 + cj);
     /* the reference shifts the i atom first (:478-480) */
     dx = (sh.x + xi.x) - xj.x;

@@ -11,9 +11,10 @@
  *   pos4[nT]     float4 {x,y,z,0}  per step: coordinates of the touched atoms (compact order)
  *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step
  *   typetab[T*T] float4 {c6,c12,sigma6,c6grid}               per nbfp upload
- *   pair_j[P]    int    compact j | excluded << 31           per search step
- *   pair_e[P]    int    local i-entry index of the pair      per search step
- *   ent4[E]      int4   {compact i, shift index, gid, 0}     per search step
+ *   pair4[P]     int4   {compact j | excluded << 31, compact i | shift << 24, local i-entry
+ *                       index, 0}: everything a pair needs in ONE coalesced 16-byte load, so the
+ *                       dependent chain is record -> atom data -> type table  per search step
+ *   ent4[E]      int4   {compact i, shift index, gid, 0}  (list read-back only) per search step
  *   warp_hbase[ceil(P/32)]  index of the first "segment" of each warp of the flat pair space;
  *                a segment is a maximal run of pairs of one i-entry inside one warp
  *   pair_dst[P]  int    where the pair's force on its j atom goes in fsorted     per search step
@@ -33,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #define FEP_NUM_SHIFT 45
+#define FEP_MAX_TOUCHED (1 << 24) /* compact atom index and shift index share one word of pair4 */
 #define FEP_CENTRAL_SHIFT 22
 #define FEP_MAX_POINTS 256 /* L+1 <= 256 lambda points per step */
 #define FEP_CTA 256        /* threads per CTA of the pair kernels */
@@ -85,6 +87,9 @@ struct KernelArgs
     /* sizes */
     int n_pairs, n_entries, n_segments, n_touched, n_gid, n_cta, n_tiles, tile_pairs;
     int n_points, n_chunks, chunk_points;
+    int pass_tile_pairs, pass_n_tiles; /* tiles of the force-only Beutler kernel */
+    int n_parts;                       /* per-CTA dV/dlambda partials written by the pass of this step */
+    int fuse_pass_and_foreign;         /* Beutler path: pass + first foreign chunk in one launch */
     int n_red_jobs, n_shift_jobs;
     /* inputs */
     const DynHead*     dyn;
@@ -92,9 +97,7 @@ struct KernelArgs
     const float4*   pos4;
     const float4*   par4;
     const float4*   typetab;
-    const int*      pair_j;
-    const int*      pair_e;
-    const int4*     ent4;
+    const int4*     pair4;
     const int*      warp_hbase;
     const int*      pair_dst;
     const int4*     seg_dst;
@@ -126,15 +129,19 @@ extern "C" {
 #endif
 /* implemented in fep_kernels.cu; all launches go to `stream`; return a cudaError_t as int */
 /* `events`, when not NULL, are 4 events recorded before the pass kernel and after the pass,
- * foreign and epilogue kernels (profiling mode only). */
+ * foreign and epilogue kernels (profiling mode only).  host_cur / host_pts: host copies of the
+ * lambda points; beutler_mode >= 0 selects the fused Beutler kernels of fep_beutler.cu
+ * (0: alphaCoul == 0; 1: one soft-core radius; 2: separate radii). */
 int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
-                    long long* launch_counter, cudaEvent_t* events, const LambdaPoint* host_pts, int foreign_mode);
-/* fep_foreign_beutler.cu: specialised foreign-lambda kernels (Beutler soft-core, no potential
- * switch).  foreign_mode 0: alphaCoul == 0; 1: one soft-core radius; 2: separate radii. */
+                    long long* launch_counter, cudaEvent_t* events, const LambdaPoint* host_cur,
+                    const LambdaPoint* host_pts, int beutler_mode);
 #define FEP_FB_CTA 128
-int fep_foreign_beutler_chunk_size(int n_points, int n_chunks_wanted);
-int fep_launch_foreign_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_pts,
-                               cudaStream_t stream, long long* launch_counter);
+#define FEP_FB_MAXC 24
+int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
+int fep_beutler_ctas_per_sm(int mode, int chunk_points, int force);
+int fep_launch_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_cur,
+                       const LambdaPoint* host_pts, int do_force, int do_foreign, int want_shift, cudaStream_t stream,
+                       long long* launch_counter);
 int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched, cudaStream_t stream,
                         long long* launch_counter);
 #ifdef __cplusplus

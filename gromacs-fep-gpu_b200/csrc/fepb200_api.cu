@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -147,7 +148,7 @@ struct fepb200_ctx
     fepb200_params params{};
     int            softcore   = FEP_SC_NONE;
     int            elec_ewald = 0;
-    int            foreign_mode = -1; /* >= 0: specialised Beutler foreign kernels */
+    int            foreign_mode = -1; /* >= 0: fused Beutler kernels of fep_beutler.cu */
     KernelArgs     ka{};
 
     /* nbfp */
@@ -178,8 +179,8 @@ struct fepb200_ctx
     std::vector<int> compact_of; /* atom -> compact or -1 */
     int              n_segments = 0;
 
-    DeviceArray<int>    d_touched, d_pair_j, d_pair_e, d_warp_hbase, d_atom_ptr, d_pair_dst, d_key_job_ptr;
-    DeviceArray<int4>   d_ent4, d_seg_dst;
+    DeviceArray<int>    d_touched, d_warp_hbase, d_atom_ptr, d_pair_dst, d_key_job_ptr;
+    DeviceArray<int4>   d_ent4, d_seg_dst, d_pair4;
     DeviceArray<RedJob> d_red_jobs;
     DeviceArray<float4> d_par4, d_fsorted, d_fshift_sorted;
     DeviceArray<float2> d_ev2;
@@ -324,16 +325,24 @@ int prepare_buffers(fepb200_ctx* c)
         {
             want = (int)std::min<long long>(np, (2LL * sms + pair_ctas - 1) / pair_ctas);
         }
-        k.chunk_points = fep_foreign_beutler_chunk_size(np, want);
+        k.chunk_points = fep_beutler_chunk_size(np, want);
         k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
-        /* one wave: as many pair tiles as CTAs can be resident (launch bounds of the kernels:
-         * 4 CTAs of 128 threads per SM, 2 when there are more than 56 accumulators) */
-        const int       nacc        = (c->foreign_mode == 0 ? 2 : 4) * k.chunk_points + 4;
-        const long long target_ctas = (long long)sms * (nacc > 56 ? 2 : 4);
-        long long       per_thread  = ((long long)k.n_pairs + target_ctas * FEP_FB_CTA - 1) / (target_ctas * FEP_FB_CTA);
-        per_thread   = std::max(1LL, std::min(per_thread, 32LL));
-        k.tile_pairs = (int)per_thread * FEP_FB_CTA;
-        k.n_tiles    = (k.n_pairs + k.tile_pairs - 1) / k.tile_pairs;
+        /* one wave: as many pair tiles as CTAs can be resident */
+        auto tiles = [&](long long ctas_per_sm, int& tile_pairs, int& n_tiles) {
+            const long long target     = (long long)sms * ctas_per_sm;
+            long long       per_thread = ((long long)k.n_pairs + target * FEP_FB_CTA - 1) / (target * FEP_FB_CTA);
+            per_thread                 = std::max(1LL, std::min(per_thread, 32LL));
+            tile_pairs                 = (int)per_thread * FEP_FB_CTA;
+            n_tiles                    = (k.n_pairs + tile_pairs - 1) / tile_pairs;
+        };
+        /* fuse pass + foreign when the list is too small to fill the GPU anyway */
+        k.fuse_pass_and_foreign = pair_ctas < 8LL * sms;
+        if (const char* env = std::getenv("FEPB200_FUSE"))
+        {
+            k.fuse_pass_and_foreign = std::atoi(env) != 0;
+        }
+        tiles(fep_beutler_ctas_per_sm(c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign), k.tile_pairs, k.n_tiles);
+        tiles(8, k.pass_tile_pairs, k.pass_n_tiles);
     }
     else
     {
@@ -353,7 +362,7 @@ int prepare_buffers(fepb200_ctx* c)
 
     CU_CHECK(c, c->d_pts.reserve(np));
     CU_CHECK(c, c->h_pts.reserve(np));
-    CU_CHECK(c, c->d_cta_part.reserve(2 * (size_t)std::max(k.n_cta, 1)));
+    CU_CHECK(c, c->d_cta_part.reserve(2 * (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1))));
     CU_CHECK(c, c->d_for_part.reserve(3 * (size_t)np * std::max(k.n_tiles, 1)));
     c->res_f64_bytes = ((size_t)l.f64_words * sizeof(double) + 15) & ~(size_t)15;
     c->res_f32_bytes = (size_t)l.f32_words * sizeof(float);
@@ -542,8 +551,7 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_pts.release();
     c->h_pts.release();
     c->d_touched.release();
-    c->d_pair_j.release();
-    c->d_pair_e.release();
+    c->d_pair4.release();
     c->d_warp_hbase.release();
     c->d_atom_ptr.release();
     c->d_pair_dst.release();
@@ -838,8 +846,12 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     const int j0 = E > 0 ? jindex[e0] : 0;
     const int P  = E > 0 ? jindex[e1] - j0 : 0;
 
+    if (nT >= FEP_MAX_TOUCHED)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d distinct atoms in one FEP list", FEP_MAX_TOUCHED);
+    }
     std::vector<int>  pair_j(P), pair_e(P);
-    std::vector<int4> ent4(E);
+    std::vector<int4> ent4(E), pair4(P);
     for (int n = 0; n < E; n++)
     {
         const int g = e0 + n;
@@ -849,6 +861,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
             const bool excluded = excl_fep && excl_fep[k] == 0;
             pair_j[k - j0]      = c->compact_of[jjnr[k]] | (excluded ? (int)0x80000000u : 0);
             pair_e[k - j0]      = n;
+            pair4[k - j0]       = make_int4(pair_j[k - j0], ent4[n].x | (shift[g] << 24), n, 0);
         }
     }
 
@@ -958,8 +971,8 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     }
 
     int rc;
-    if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair_j, pair_j))
-        || (rc = to_device(c, c->d_pair_e, pair_e)) || (rc = to_device(c, c->d_ent4, ent4))
+    if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair4, pair4))
+        || (rc = to_device(c, c->d_ent4, ent4))
         || (rc = to_device(c, c->d_warp_hbase, warp_hbase)) || (rc = to_device(c, c->d_atom_ptr, atom_ptr))
         || (rc = to_device(c, c->d_pair_dst, pair_dst)) || (rc = to_device(c, c->d_red_jobs, jobs))
         || (rc = to_device(c, c->d_seg_dst, seg_dst)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
@@ -982,9 +995,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     k.n_cta       = (P + FEP_CTA - 1) / FEP_CTA;
     k.n_red_jobs  = (int)jobs.size();
     k.par4        = c->d_par4.ptr;
-    k.pair_j      = c->d_pair_j.ptr;
-    k.pair_e      = c->d_pair_e.ptr;
-    k.ent4        = c->d_ent4.ptr;
+    k.pair4       = c->d_pair4.ptr;
     k.warp_hbase  = c->d_warp_hbase.ptr;
     k.fsorted       = c->d_fsorted.ptr;
     k.fshift_sorted = c->d_fshift_sorted.ptr;
@@ -1061,11 +1072,16 @@ int fepb200_get_list(const fepb200_ctx* cc, int* first_entry, int* iinr, int* gi
     }
     if (jindex || jjnr || excl_fep)
     {
-        std::vector<int> pair_j(P), pair_e(P);
+        std::vector<int>  pair_j(P), pair_e(P);
+        std::vector<int4> pair4(P);
         if (P > 0)
         {
-            CU_CHECK(c, cudaMemcpy(pair_j.data(), c->d_pair_j.ptr, P * sizeof(int), cudaMemcpyDeviceToHost));
-            CU_CHECK(c, cudaMemcpy(pair_e.data(), c->d_pair_e.ptr, P * sizeof(int), cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(pair4.data(), c->d_pair4.ptr, P * sizeof(int4), cudaMemcpyDeviceToHost));
+        }
+        for (int s = 0; s < P; s++)
+        {
+            pair_j[s] = pair4[s].x;
+            pair_e[s] = pair4[s].z;
         }
         if (jindex)
         {
@@ -1231,7 +1247,7 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     const StepFlags sf     = step_flags(c, flags);
     CU_CHECK(c, cudaEventRecord(c->ev_start, stream));
     const int err = fep_launch_step(&c->ka, c->softcore, c->elec_ewald, sf, stream, &c->launches,
-                                    c->profiling ? c->ev_prof : nullptr, c->pts.data(), c->foreign_mode);
+                                    c->profiling ? c->ev_prof : nullptr, &c->cur, c->pts.data(), c->foreign_mode);
     c->profiled   = c->profiling;
     if (err != 0)
     {
