@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restri
 template<int SC, bool EWALD>
 static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t stream, long long* counter,
                                    cudaEvent_t* ev, const LambdaPoint* host_cur, const LambdaPoint* host_pts,
-                                   int beutler_mode)
+                                   int beutler_mode, cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev)
 {
     const bool foreign = sf.foreign && ka.n_points > 0;
     const bool beutler = SC == FEP_SC_BEUTLER && beutler_mode >= 0;
@@ -572,6 +572,10 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
         cudaEventRecord(ev[0], stream);
     }
     ka.n_parts = 0;
+    if (!ev && side != nullptr && beutler && sf.force && foreign && !one_launch)
+    {
+        cudaEventRecord(fork_ev, stream);
+    }
     if (ka.n_pairs > 0 && !one_launch)
     {
         if (beutler && sf.force)
@@ -602,8 +606,24 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
     {
         if (beutler)
         {
+            /* the pass kernel (already queued on `stream`) and the foreign kernels are independent
+             * and both latency-bound: on a second stream they share the SMs instead of queueing.
+             * Not in profiling mode, where each kernel is timed alone. */
+            const bool   overlap = !one_launch && !ev && side != nullptr && ka.n_parts > 0;
+            cudaStream_t fstream = stream;
+            if (overlap)
+            {
+                /* fork_ev was recorded on `stream` before the pass kernel was queued */
+                cudaStreamWaitEvent(side, fork_ev, 0);
+                fstream = side;
+            }
             rc = fep_launch_beutler(&ka, EWALD ? 1 : 0, beutler_mode, host_cur, host_pts, one_launch ? 1 : 0, 1,
-                                    one_launch ? sf.shift : 0, stream, counter);
+                                    one_launch ? sf.shift : 0, fstream, counter);
+            if (overlap)
+            {
+                cudaEventRecord(join_ev, side);
+                cudaStreamWaitEvent(stream, join_ev, 0);
+            }
             if (one_launch)
             {
                 ka.n_parts = ka.n_tiles;
@@ -629,7 +649,8 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
 
 extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
                                long long* counter, cudaEvent_t* ev, const LambdaPoint* host_cur,
-                               const LambdaPoint* host_pts, int beutler_mode)
+                               const LambdaPoint* host_pts, int beutler_mode, cudaStream_t side, cudaEvent_t fork_ev,
+                               cudaEvent_t join_ev)
 {
     KernelArgs  ka = *kap; /* local copy: n_parts depends on which pass kernel ran */
     cudaError_t err;
@@ -637,7 +658,8 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     {
 #define FEP_CASE(SCV, EW) \
     case SCV * 2 + (EW ? 1 : 0): \
-        err = launch_variants<SCV, EW>(ka, sf, stream, counter, ev, host_cur, host_pts, beutler_mode); \
+        err = launch_variants<SCV, EW>(ka, sf, stream, counter, ev, host_cur, host_pts, beutler_mode, side, fork_ev, \
+                                        join_ev); \
         break;
         FEP_CASE(FEP_SC_NONE, false)
         FEP_CASE(FEP_SC_NONE, true)

@@ -131,10 +131,12 @@ extern "C" {
 /* `events`, when not NULL, are 4 events recorded before the pass kernel and after the pass,
  * foreign and epilogue kernels (profiling mode only).  host_cur / host_pts: host copies of the
  * lambda points; beutler_mode >= 0 selects the fused Beutler kernels of fep_beutler.cu
- * (0: alphaCoul == 0; 1: one soft-core radius; 2: separate radii). */
+ * (0: alphaCoul == 0; 1: one soft-core radius; 2: separate radii).  side_stream / fork_ev / join_ev
+ * (may be NULL): the independent pass and foreign kernels of a large list run concurrently. */
 int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlags sf, cudaStream_t stream,
                     long long* launch_counter, cudaEvent_t* events, const LambdaPoint* host_cur,
-                    const LambdaPoint* host_pts, int beutler_mode);
+                    const LambdaPoint* host_pts, int beutler_mode, cudaStream_t side_stream, cudaEvent_t fork_ev,
+                    cudaEvent_t join_ev);
 #define FEP_FB_CTA 128
 #define FEP_FB_MAXC 24
 int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);

@@ -134,7 +134,8 @@ bool eel_is_rf(int e)
 struct fepb200_ctx
 {
     int          device = -1;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t  fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t  ev_prof[4] = { nullptr, nullptr, nullptr, nullptr };
     bool         profiling = false, profiled = false;
@@ -522,6 +523,9 @@ int fepb200_create(fepb200_ctx** out, int device_ordinal)
     c->device      = device_ordinal;
     if (cudaSetDevice(device_ordinal) != cudaSuccess
         || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess
         || cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess
         || c->d_counter.reserve(1) != cudaSuccess || cudaMemset(c->d_counter.ptr, 0, sizeof(unsigned int)) != cudaSuccess)
     {
@@ -581,6 +585,9 @@ int fepb200_destroy(fepb200_ctx* c)
     cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_stop);
     cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->side_stream);
+    cudaEventDestroy(c->fork_ev);
+    cudaEventDestroy(c->join_ev);
     delete c;
     return FEPB200_OK;
 }
@@ -1247,7 +1254,8 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     const StepFlags sf     = step_flags(c, flags);
     CU_CHECK(c, cudaEventRecord(c->ev_start, stream));
     const int err = fep_launch_step(&c->ka, c->softcore, c->elec_ewald, sf, stream, &c->launches,
-                                    c->profiling ? c->ev_prof : nullptr, &c->cur, c->pts.data(), c->foreign_mode);
+                                    c->profiling ? c->ev_prof : nullptr, &c->cur, c->pts.data(), c->foreign_mode,
+                                    c->side_stream, c->fork_ev, c->join_ev);
     c->profiled   = c->profiling;
     if (err != 0)
     {
