@@ -97,4 +97,5 @@ def test_cpp_dispatch_matches_oracle(tmp_path, name, groups):
     assert not np.any(np.delete(dvdl_nonlin, [P.LAMBDA_COUL, P.LAMBDA_VDW]))
     # the plain force step gives the same forces and dV/dlambda
     assert np.array_equal(f2, f)
-    assert np.array_equal(dvdl2, dvdl_nonlin)
+    # (different launch configuration of the pass, hence a different summation order of the partials)
+    assert np.allclose(dvdl2, dvdl_nonlin, rtol=2e-6, atol=0)
