@@ -217,12 +217,33 @@ def test_scaled_configs_match_oracle(ctx, name):
     _check(out, ref, ALL, label=name)
 
 
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5"])
 def test_full_size_configs_match_oracle(ctx, name):
+    """All five BASELINE.json configurations at full size (C5: 991 k atoms, 915 k pairs, 21 lambda
+    points) against the double-precision oracle, at the north_star tolerances."""
     prob = make_system(SPECS[name])
     out = _run(ctx, prob)
-    ref = _oracle().run_best(prob, ALL, nthreads=max(1, min(8, os.cpu_count() or 1)))
+    ref = _oracle().run_best(prob, ALL, nthreads=max(1, min(16, os.cpu_count() or 1)))
     _check(out, ref, ALL, label=name)
+    # the pair count the library reports is the list's, bit for bit
+    lay = ctx.layout()
+    assert (lay.nri, lay.nrj) == (prob.nblist.nri, prob.nblist.nrj)
+
+
+def test_full_size_c5_properties(ctx):
+    """Size-independent properties at the largest configuration: Newton's third law (the FEP
+    forces sum to zero because every pair force is applied with both signs), E(lambda) at foreign
+    point 0 equals the energy of the current-lambda pass, and two runs are bit-identical."""
+    prob = make_system(SPECS["C5"])
+    out = _run(ctx, prob)
+    fsum = np.abs(out["f"].astype(np.float64).sum(axis=0))
+    fabs = np.abs(out["f"]).astype(np.float64).sum(axis=0)
+    assert np.all(fsum <= 1e-5 * fabs)
+    e0 = out["Vc"].sum() + out["Vv"].sum()
+    assert abs(out["foreign_energy"][0] - e0) <= 1e-5 * max(abs(e0), np.max(np.abs(out["foreign_energy"])))
+    again = ctx.compute(prob.x, prob.shiftvec, ALL)
+    for k in out:
+        assert np.array_equal(out[k], again[k]), k
 
 
 # ------------------------------------------------------------------------------------------------
