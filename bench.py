@@ -116,6 +116,8 @@ def _config(problem, name, world, extra=None):
                passes_per_step=1 + problem.n_foreign + 1,
                flags="FORCE|SHIFTFORCE|POTENTIAL|FOREIGNLAMBDA",
                parallelism=f"i-entry shards x{world}", l2="flushed between timed steps (512 MiB write)")
+    if extra is None and world > 1:
+        extra = {}
     if extra:
         cfg.update(extra)
     return cfg
@@ -340,7 +342,7 @@ def run_ours(args, name):
             cpu.pop("ms_per_step", None)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
-                    data="synthetic", config=_config(problem, name, world),
+                    data="synthetic", config=_config(problem, name, world, dict(reduction=sh.reduction)),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_s / args.steps * 1e3),
                     gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, cpu_baseline=cpu,

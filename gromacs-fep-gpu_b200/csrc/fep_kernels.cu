@@ -19,6 +19,8 @@
  * No tensor cores: the work is pairwise FP32 FMA + MUFU (rcp/rsq/lg2/ex2).  No global atomics in
  * any data path; the only atomic is the completion ticket of the epilogue.
  */
+#include <algorithm>
+
 #include "fep_pair_math.cuh"
 
 #define FULL_MASK 0xffffffffu
@@ -689,6 +691,65 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     {
         cudaEventRecord(ev[3], stream);
     }
+    return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* multi-GPU: one-shot reduction over peer memory                                              */
+/* ------------------------------------------------------------------------------------------- */
+/* Every rank has published its result block [f64 | f32] in a buffer all ranks have mapped
+ * (NVLink peer access).  Each rank reads every block once and keeps the full sum: a one-shot
+ * all-reduce, latency-optimal for the ~1 MB blocks of this path; the order of the additions is the
+ * rank order on every rank, so all ranks obtain bit-identical results. */
+__global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_constant__ PeerPtrs peers, int nranks,
+                                                             double* __restrict__ out_f64, int n64, size_t f64_bytes,
+                                                             float* __restrict__ out_f32, long long n32)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long n4 = n32 >> 2;
+    if (i < n4)
+    {
+        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int r = 0; r < nranks; r++)
+        {
+            const float4* src = reinterpret_cast<const float4*>(static_cast<const char*>(peers.p[r]) + f64_bytes);
+            const float4  v   = __ldcv(src + i); /* written by another GPU: never from a stale cache line */
+            a.x += v.x;
+            a.y += v.y;
+            a.z += v.z;
+            a.w += v.w;
+        }
+        reinterpret_cast<float4*>(out_f32)[i] = a;
+    }
+    else if (i < n4 + (n32 & 3))
+    {
+        const long long j = 4 * n4 + (i - n4);
+        float           a = 0.0f;
+        for (int r = 0; r < nranks; r++)
+        {
+            const float* src = reinterpret_cast<const float*>(static_cast<const char*>(peers.p[r]) + f64_bytes);
+            a += __ldcv(src + j);
+        }
+        out_f32[j] = a;
+    }
+    if (i < n64)
+    {
+        double a = 0.0;
+        for (int r = 0; r < nranks; r++)
+        {
+            a += __ldcv(static_cast<const double*>(peers.p[r]) + i);
+        }
+        out_f64[i] = a;
+    }
+}
+
+extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, int nranks, double* out_f64, int n64, size_t f64_bytes,
+                                      float* out_f32, long long n32, cudaStream_t stream, long long* counter)
+{
+    const long long items  = (n32 >> 2) + (n32 & 3);
+    const long long blocks = (std::max<long long>(items, n64) + 255) / 256;
+    fep_peer_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*peers, nranks, out_f64, n64, f64_bytes, out_f32, n32);
+    (*counter)++;
     return (int)cudaGetLastError();
 }
 

@@ -144,6 +144,16 @@ int fep_beutler_ctas_per_sm(int mode, int chunk_points, int force);
 int fep_launch_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_cur,
                        const LambdaPoint* host_pts, int do_force, int do_foreign, int want_shift, cudaStream_t stream,
                        long long* launch_counter);
+/* Sum over ranks of result blocks that live in peer-mapped memory (NVLink): out = sum_r peer[r],
+ * in rank order (deterministic).  n16 = number of 16-byte words that hold fp32 data, n64 = number
+ * of doubles; each peer block is [n64 doubles padded to 16 B | fp32 words]. */
+#define FEP_MAX_PEERS 16
+struct PeerPtrs
+{
+    const void* p[FEP_MAX_PEERS];
+};
+int fep_launch_peer_reduce(const PeerPtrs* peers, int nranks, double* out_f64, int n64, size_t f64_bytes,
+                           float* out_f32, long long n32, cudaStream_t stream, long long* launch_counter);
 int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched, cudaStream_t stream,
                         long long* launch_counter);
 #ifdef __cplusplus

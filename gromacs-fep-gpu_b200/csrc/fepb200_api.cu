@@ -1294,6 +1294,46 @@ int fepb200_result_device_ptrs(const fepb200_ctx* c, void** d_f32, void** d_f64)
     return FEPB200_OK;
 }
 
+size_t fepb200_result_block_bytes(const fepb200_ctx* c)
+{
+    return (c && c->have_list) ? c->res_f64_bytes + c->res_f32_bytes : 0;
+}
+
+int fepb200_publish_result(fepb200_ctx* c, void* d_block)
+{
+    if (!c || !c->have_list || !d_block)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_publish_result: bad arguments");
+    }
+    cudaSetDevice(c->device);
+    /* the device result block is contiguous [f64 | f32] */
+    CU_CHECK(c, cudaMemcpyAsync(d_block, c->d_result.ptr, c->res_f64_bytes + c->res_f32_bytes, cudaMemcpyDeviceToDevice,
+                                c->stream));
+    return FEPB200_OK;
+}
+
+int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks)
+{
+    if (!c || !c->have_list || !d_peer_blocks || nranks < 1 || nranks > FEP_MAX_PEERS)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_reduce_peers: bad arguments (at most %d ranks)",
+                    FEP_MAX_PEERS);
+    }
+    cudaSetDevice(c->device);
+    PeerPtrs pp{};
+    for (int r = 0; r < nranks; r++)
+    {
+        pp.p[r] = d_peer_blocks[r];
+    }
+    const int err = fep_launch_peer_reduce(&pp, nranks, c->ka.res_f64, (int)c->layout.f64_words, c->res_f64_bytes,
+                                           c->ka.res_f32, c->layout.f32_words, c->stream, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "peer reduce launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    return FEPB200_OK;
+}
+
 int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double* Vc, double* Vv, double* dvdl,
                      double* foreign_energy, double* foreign_dvdl)
 {

@@ -2,14 +2,18 @@
 i-entry over the ranks (shard.py), coordinates and parameters replicated, and two collectives per
 step over NCCL/NVLink:
 
-  * forces + shift forces: all-reduce of the fp32 result block [3*nTouched + 135] -- every rank
-    numbers the touched atoms identically, so the block is handed to NCCL as is;
-  * Vc/Vvdw per energy-group pair, dV/dlambda, foreign energies: all-reduce of the small fp64 block.
+  * forces + shift forces: sum of the fp32 result block [3*nTouched + 135] -- every rank
+    numbers the touched atoms identically, so the blocks add up element by element;
+  * Vc/Vvdw per energy-group pair, dV/dlambda, foreign energies: sum of the small fp64 block.
+Both sums are done by ONE kernel of libfepb200 over NVLink peer memory (ShardedFep.reduction ==
+"p2p"), or by two ncclAllReduce calls ("nccl").
 
 torch.distributed is plumbing only (process group, NCCL communicator, stream); the tensors it
 reduces are zero-copy views of the library's device result block.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -34,25 +38,65 @@ def result_tensors(ctx: FepContext) -> tuple[torch.Tensor, torch.Tensor]:
 
 
 class ShardedFep:
-    """The per-rank object: holds this rank's shard and reduces results over the group."""
+    """The per-rank object: holds this rank's shard and reduces results over the group.
 
-    def __init__(self, problem, device: int, rank: int, world: int, group=None):
+    reduction = "p2p" (default when available): every rank publishes its result block in
+    symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations every rank of the
+    node has mapped over NVLink), passes a device-side barrier, and libfepb200's own kernel reads
+    all blocks through the peer pointers and sums them in rank order (fepb200_reduce_peers).
+    reduction = "nccl": two ncclAllReduce calls on zero-copy views of the result block.
+    """
+
+    def __init__(self, problem, device: int, rank: int, world: int, group=None, reduction: str | None = None):
         self.rank, self.world, self.group = rank, world, group
         torch.cuda.set_device(device)
         self.ctx = FepContext(device)
-        # all work of the context goes to one torch stream so that kernels, NCCL collectives and
-        # copies are ordered without host synchronisation
+        # all work of the context goes to one torch stream so that kernels, collectives and copies
+        # are ordered without host synchronisation
         self.stream = torch.cuda.Stream(device)
         self.ctx.set_stream(self.stream.cuda_stream)
         self.ctx.set_problem(problem, rank=rank, nranks=world)
         self.f32, self.f64 = result_tensors(self.ctx)
+        self.reduction = "none"
+        self._step = 0
+        if world > 1:
+            want = reduction or os.environ.get("FEPB200_REDUCTION", "p2p")
+            self.reduction = "nccl"
+            if want == "p2p":
+                try:
+                    self._setup_p2p(device)
+                    self.reduction = "p2p"
+                except Exception as exc:  # no symmetric memory on this system: NCCL does the same job
+                    self._p2p_error = repr(exc)
+
+    def _setup_p2p(self, device: int) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = self.group if self.group is not None else dist.group.WORLD
+        self.block_bytes = (self.ctx.result_block_bytes() + 255) // 256 * 256
+        with torch.cuda.stream(self.stream):
+            self._sym = symm_mem.empty(2 * self.block_bytes, dtype=torch.uint8, device=torch.device("cuda", device))
+            self._hdl = symm_mem.rendezvous(self._sym, group)
+        base = [int(p) for p in self._hdl.buffer_ptrs]
+        # two alternating slots: a rank that runs ahead writes the other slot, and cannot come back
+        # to this one before everybody has passed the next step's barrier
+        self._slots = [[b + k * self.block_bytes for b in base] for k in (0, 1)]
+        self.stream.synchronize()
 
     def launch(self, flags: int) -> None:
-        """Kernels of this rank's shard, then the two all-reduces, all asynchronous on self.stream."""
-        import torch.distributed as dist
-
+        """Kernels of this rank's shard, then the reduction over ranks, all asynchronous on self.stream."""
         self.ctx.launch(flags)
-        if self.world > 1:
+        if self.reduction == "p2p":
+            k = self._step & 1
+            self._step += 1
+            with torch.cuda.stream(self.stream):
+                self.ctx.publish_result(self._slots[k][self.rank])
+                self._hdl.barrier(channel=k)
+                self.ctx.reduce_peers(self._slots[k])
+        elif self.reduction == "nccl":
+            import torch.distributed as dist
+
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(self.f64, group=self.group)
                 dist.all_reduce(self.f32, group=self.group)

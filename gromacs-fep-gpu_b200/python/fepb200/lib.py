@@ -70,6 +70,9 @@ SYMBOLS = {
     "fepb200_launch": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "fepb200_wait": (ctypes.c_int, [_VP]),
     "fepb200_result_device_ptrs": (ctypes.c_int, [_VP, ctypes.POINTER(_VP), ctypes.POINTER(_VP)]),
+    "fepb200_result_block_bytes": (ctypes.c_size_t, [_VP]),
+    "fepb200_publish_result": (ctypes.c_int, [_VP, _VP]),
+    "fepb200_reduce_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP)]),
     "fepb200_download": (ctypes.c_int, [_VP, ctypes.c_int, _FP, _FP, _DP, _DP, _DP, _DP, _DP]),
     "fepb200_launch_count": (ctypes.c_longlong, [_VP]),
     "fepb200_last_launch_ms": (ctypes.c_int, [_VP, _FP]),
@@ -307,3 +310,14 @@ class FepContext:
         ms = (ctypes.c_float * 3)()
         self._check(self._lib.fepb200_kernel_ms(self._h, ms))
         return float(ms[0]), float(ms[1]), float(ms[2])
+
+    # ---- peer-memory reduction ------------------------------------------------------------
+    def result_block_bytes(self) -> int:
+        return int(self._lib.fepb200_result_block_bytes(self._h))
+
+    def publish_result(self, d_block: int) -> None:
+        self._check(self._lib.fepb200_publish_result(self._h, _VP(d_block)))
+
+    def reduce_peers(self, peer_blocks: list[int]) -> None:
+        arr = (_VP * len(peer_blocks))(*[_VP(p) for p in peer_blocks])
+        self._check(self._lib.fepb200_reduce_peers(self._h, len(peer_blocks), arr))

@@ -209,6 +209,19 @@ int fepb200_launch(fepb200_ctx* ctx, int flags, void* stream);
 int fepb200_wait(fepb200_ctx* ctx);
 /* Device pointers of the result block: f32 part and f64 part (see fepb200_layout). */
 int fepb200_result_device_ptrs(const fepb200_ctx* ctx, void** d_f32, void** d_f64);
+/* ---- multi-GPU reduction over peer memory (NVLink), the alternative to handing the device
+ * pointers to ncclAllReduce.  Every rank (1) publishes its result block into a buffer that all
+ * ranks of the node have mapped (e.g. CUDA VMM / symmetric memory; fepb200_result_block_bytes()
+ * bytes, 16-byte aligned), (2) passes a barrier the caller provides on the context's stream, then
+ * (3) calls fepb200_reduce_peers() with the device pointers of ALL ranks' buffers in rank order:
+ * one kernel reads every block over NVLink and leaves the full sum in this context's own result
+ * block (ready for fepb200_download()).  Sums are taken in rank order: every rank gets
+ * bit-identical results.  Use two alternating buffers so that a fast rank cannot overwrite a
+ * block a slow rank is still reading. */
+size_t fepb200_result_block_bytes(const fepb200_ctx* ctx);
+int    fepb200_publish_result(fepb200_ctx* ctx, void* d_block);
+int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks);
+
 /* Copy the result block to the host and add it into the caller's arrays (same
  * semantics as the tail of fepb200_compute).  Synchronous. */
 int fepb200_download(fepb200_ctx* ctx, int flags, float* f, float* fshift, double* Vc, double* Vv,

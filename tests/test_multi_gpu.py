@@ -18,7 +18,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, root, result_file):
+def _worker(rank, world, port, root, result_file, reduction):
     for p in (os.path.join(root, "gromacs-fep-gpu_b200", "python"), root):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -36,7 +36,8 @@ def _worker(rank, world, port, root, result_file):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
     prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=5))
-    sh = ShardedFep(prob, rank, rank, world)
+    sh = ShardedFep(prob, rank, rank, world, reduction=reduction)
+    used = sh.reduction
     lay = sh.ctx.layout()
     out = sh.step(prob.x, prob.shiftvec, flags)
     out2 = sh.step(prob.x, prob.shiftvec, flags | P.CLEAR_OUTPUTS, out={k: v.copy() for k, v in out.items()})
@@ -51,12 +52,13 @@ def _worker(rank, world, port, root, result_file):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         with open(result_file, "w") as fh:
-            fh.write("ok" if int(flag.item()) == 1 else f"mismatch rms={rms:.3e}")
+            fh.write(f"ok {used}" if int(flag.item()) == 1 else f"mismatch rms={rms:.3e} {used}")
     sh.close()
     dist.destroy_process_group()
 
 
-def test_two_ranks_nccl_match_oracle(tmp_path):
+@pytest.mark.parametrize("reduction", ["p2p", "nccl"])
+def test_two_ranks_match_oracle(tmp_path, reduction):
     import torch
     import torch.multiprocessing as mp
 
@@ -64,5 +66,9 @@ def test_two_ranks_nccl_match_oracle(tmp_path):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     result = str(tmp_path / "result.txt")
-    mp.spawn(_worker, args=(2, _free_port(), root, result), nprocs=2, join=True)
-    assert open(result).read() == "ok"
+    mp.spawn(_worker, args=(2, _free_port(), root, result, reduction), nprocs=2, join=True)
+    got = open(result).read()
+    assert got.startswith("ok"), got
+    if reduction == "nccl":
+        assert got == "ok nccl"
+    print(got)
