@@ -17,7 +17,8 @@ ALL = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
 
 def rel(a, b):
     a, b = np.asarray(a, float), np.asarray(b, float)
-    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-2 * np.max(np.abs(b)))))
+    scale = np.maximum(np.abs(b), 1e-2 * np.max(np.abs(b)))
+    return float(np.max(np.abs(a - b) / np.where(scale > 0, scale, 1.0)))
 
 
 print(f"{'cfg':4s} {'atoms':>8s} {'pairs':>8s} {'L':>3s} {'force rel-RMS':>14s} {'Vc':>9s} {'Vv':>9s} {'dvdl':>9s} "
