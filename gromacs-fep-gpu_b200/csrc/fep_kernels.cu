@@ -701,23 +701,72 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
  * (NVLink peer access).  Each rank reads every block once and keeps the full sum: a one-shot
  * all-reduce, latency-optimal for the ~1 MB blocks of this path; the order of the additions is the
  * rank order on every rank, so all ranks obtain bit-identical results. */
-__global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_constant__ PeerPtrs peers, int nranks,
-                                                             double* __restrict__ out_f64, int n64, size_t f64_bytes,
-                                                             float* __restrict__ out_f32, long long n32)
+template<int NR>
+__global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_constant__ PeerPtrs peers,
+                                                             const __grid_constant__ PeerPtrs flags, int rank,
+                                                             unsigned int seq, int nranks, double* __restrict__ out_f64,
+                                                             int n64, size_t f64_bytes, float* __restrict__ out_f32,
+                                                             long long n32)
 {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (flags.p[0] != nullptr)
+    {
+        /* Cross-GPU barrier inside the reduction kernel.  This rank's block was completed by the
+         * previous kernel on this stream; announce step `seq` in every peer's flag array (slot
+         * `rank`), then wait until every peer's announcement has arrived in ours.  One kernel per
+         * GPU takes part, so the spin cannot starve a producer on the same device. */
+        if (blockIdx.x == 0 && threadIdx.x < nranks)
+        {
+            __threadfence_system();
+            unsigned int* dst = static_cast<unsigned int*>(const_cast<void*>(flags.p[threadIdx.x])) + rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
+        }
+        if (threadIdx.x < nranks)
+        {
+            const unsigned int* src = static_cast<const unsigned int*>(flags.p[rank]) + threadIdx.x;
+            unsigned int        v;
+            do
+            {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            } while ((int)(v - seq) < 0);
+        }
+        __syncthreads();
+    }
+    /* NR > 0: compile-time rank count, all NR remote loads are in flight before the first add
+     * (a peer load is ~1.5 us; serialising them would cost NR times that) */
+    const int       nr = NR > 0 ? NR : nranks;
+    const long long i  = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long n4 = n32 >> 2;
     if (i < n4)
     {
         float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        for (int r = 0; r < nranks; r++)
+        if (NR > 0)
         {
-            const float4* src = reinterpret_cast<const float4*>(static_cast<const char*>(peers.p[r]) + f64_bytes);
-            const float4  v   = __ldcv(src + i); /* written by another GPU: never from a stale cache line */
-            a.x += v.x;
-            a.y += v.y;
-            a.z += v.z;
-            a.w += v.w;
+            float4 v[NR > 0 ? NR : 1];
+#pragma unroll
+            for (int r = 0; r < NR; r++)
+            {
+                /* written by another GPU: never from a stale cache line */
+                v[r] = __ldcv(reinterpret_cast<const float4*>(static_cast<const char*>(peers.p[r]) + f64_bytes) + i);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; r++)
+            {
+                a.x += v[r].x;
+                a.y += v[r].y;
+                a.z += v[r].z;
+                a.w += v[r].w;
+            }
+        }
+        else
+        {
+            for (int r = 0; r < nr; r++)
+            {
+                const float4 v = __ldcv(reinterpret_cast<const float4*>(static_cast<const char*>(peers.p[r]) + f64_bytes) + i);
+                a.x += v.x;
+                a.y += v.y;
+                a.z += v.z;
+                a.w += v.w;
+            }
         }
         reinterpret_cast<float4*>(out_f32)[i] = a;
     }
@@ -725,17 +774,16 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
     {
         const long long j = 4 * n4 + (i - n4);
         float           a = 0.0f;
-        for (int r = 0; r < nranks; r++)
+        for (int r = 0; r < nr; r++)
         {
-            const float* src = reinterpret_cast<const float*>(static_cast<const char*>(peers.p[r]) + f64_bytes);
-            a += __ldcv(src + j);
+            a += __ldcv(reinterpret_cast<const float*>(static_cast<const char*>(peers.p[r]) + f64_bytes) + j);
         }
         out_f32[j] = a;
     }
     if (i < n64)
     {
         double a = 0.0;
-        for (int r = 0; r < nranks; r++)
+        for (int r = 0; r < nr; r++)
         {
             a += __ldcv(static_cast<const double*>(peers.p[r]) + i);
         }
@@ -743,12 +791,21 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
     }
 }
 
-extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, int nranks, double* out_f64, int n64, size_t f64_bytes,
-                                      float* out_f32, long long n32, cudaStream_t stream, long long* counter)
+extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flagsp, int rank, unsigned int seq,
+                                      int nranks, double* out_f64, int n64, size_t f64_bytes, float* out_f32,
+                                      long long n32, cudaStream_t stream, long long* counter)
 {
+    PeerPtrs noflags{};
+    const PeerPtrs* flags = flagsp ? flagsp : &noflags;
     const long long items  = (n32 >> 2) + (n32 & 3);
-    const long long blocks = (std::max<long long>(items, n64) + 255) / 256;
-    fep_peer_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*peers, nranks, out_f64, n64, f64_bytes, out_f32, n32);
+    const unsigned  blocks = (unsigned)((std::max<long long>(items, n64) + 255) / 256);
+    switch (nranks)
+    {
+        case 2: fep_peer_reduce_kernel<2><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        case 4: fep_peer_reduce_kernel<4><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        case 8: fep_peer_reduce_kernel<8><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        default: fep_peer_reduce_kernel<0><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+    }
     (*counter)++;
     return (int)cudaGetLastError();
 }

@@ -152,8 +152,12 @@ struct PeerPtrs
 {
     const void* p[FEP_MAX_PEERS];
 };
-int fep_launch_peer_reduce(const PeerPtrs* peers, int nranks, double* out_f64, int n64, size_t f64_bytes,
-                           float* out_f32, long long n32, cudaStream_t stream, long long* launch_counter);
+/* flags (may be NULL): per rank a peer-mapped array of FEP_MAX_PEERS uint32 sequence numbers; the
+ * kernel then first announces `seq` in every peer's array and waits until all peers announced it
+ * (the cross-GPU barrier is part of the reduction kernel). */
+int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flags, int rank, unsigned int seq, int nranks,
+                           double* out_f64, int n64, size_t f64_bytes, float* out_f32, long long n32,
+                           cudaStream_t stream, long long* launch_counter);
 int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched, cudaStream_t stream,
                         long long* launch_counter);
 #ifdef __cplusplus

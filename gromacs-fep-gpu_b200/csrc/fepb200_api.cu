@@ -191,6 +191,7 @@ struct fepb200_ctx
     DeviceArray<unsigned char> d_result;  /* [f64 block | f32 block] */
     PinnedArray<unsigned char> h_step_in, h_result;
     size_t res_f64_bytes = 0, res_f32_bytes = 0;
+    unsigned char* res_target = nullptr; /* where the epilogue writes; nullptr = own result block */
 };
 
 namespace
@@ -337,7 +338,7 @@ int prepare_buffers(fepb200_ctx* c)
             n_tiles                    = (k.n_pairs + tile_pairs - 1) / tile_pairs;
         };
         /* fuse pass + foreign when the list is too small to fill the GPU anyway */
-        k.fuse_pass_and_foreign = pair_ctas < 8LL * sms;
+        k.fuse_pass_and_foreign = pair_ctas < 16LL * sms;
         if (const char* env = std::getenv("FEPB200_FUSE"))
         {
             k.fuse_pass_and_foreign = std::atoi(env) != 0;
@@ -380,6 +381,7 @@ int prepare_buffers(fepb200_ctx* c)
     k.for_part = c->d_for_part.ptr;
     k.res_f64  = reinterpret_cast<double*>(c->d_result.ptr);
     k.res_f32  = reinterpret_cast<float*>(c->d_result.ptr + c->res_f64_bytes);
+    c->res_target = nullptr;
     return FEPB200_OK;
 }
 
@@ -1253,7 +1255,13 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     cudaStream_t    stream = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
     const StepFlags sf     = step_flags(c, flags);
     CU_CHECK(c, cudaEventRecord(c->ev_start, stream));
-    const int err = fep_launch_step(&c->ka, c->softcore, c->elec_ewald, sf, stream, &c->launches,
+    KernelArgs ka_step = c->ka;
+    if (c->res_target)
+    {
+        ka_step.res_f64 = reinterpret_cast<double*>(c->res_target);
+        ka_step.res_f32 = reinterpret_cast<float*>(c->res_target + c->res_f64_bytes);
+    }
+    const int err = fep_launch_step(&ka_step, c->softcore, c->elec_ewald, sf, stream, &c->launches,
                                     c->profiling ? c->ev_prof : nullptr, &c->cur, c->pts.data(), c->foreign_mode,
                                     c->side_stream, c->fork_ev, c->join_ev);
     c->profiled   = c->profiling;
@@ -1299,6 +1307,20 @@ size_t fepb200_result_block_bytes(const fepb200_ctx* c)
     return (c && c->have_list) ? c->res_f64_bytes + c->res_f32_bytes : 0;
 }
 
+int fepb200_set_partial_result_block(fepb200_ctx* c, void* d_block)
+{
+    if (!c || !c->have_list)
+    {
+        return fail(c, FEPB200_ERR_STATE, "no list has been set");
+    }
+    if ((reinterpret_cast<size_t>(d_block) & 15) != 0)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "result block must be 16-byte aligned");
+    }
+    c->res_target = static_cast<unsigned char*>(d_block);
+    return FEPB200_OK;
+}
+
 int fepb200_publish_result(fepb200_ctx* c, void* d_block)
 {
     if (!c || !c->have_list || !d_block)
@@ -1312,21 +1334,24 @@ int fepb200_publish_result(fepb200_ctx* c, void* d_block)
     return FEPB200_OK;
 }
 
-int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks)
+int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags, int rank,
+                         unsigned int seq)
 {
-    if (!c || !c->have_list || !d_peer_blocks || nranks < 1 || nranks > FEP_MAX_PEERS)
+    if (!c || !c->have_list || !d_peer_blocks || nranks < 1 || nranks > FEP_MAX_PEERS || rank < 0 || rank >= nranks)
     {
         return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_reduce_peers: bad arguments (at most %d ranks)",
                     FEP_MAX_PEERS);
     }
     cudaSetDevice(c->device);
-    PeerPtrs pp{};
+    PeerPtrs pp{}, ff{};
     for (int r = 0; r < nranks; r++)
     {
         pp.p[r] = d_peer_blocks[r];
+        ff.p[r] = d_peer_flags ? d_peer_flags[r] : nullptr;
     }
-    const int err = fep_launch_peer_reduce(&pp, nranks, c->ka.res_f64, (int)c->layout.f64_words, c->res_f64_bytes,
-                                           c->ka.res_f32, c->layout.f32_words, c->stream, &c->launches);
+    const int err = fep_launch_peer_reduce(&pp, d_peer_flags ? &ff : nullptr, rank, seq, nranks, c->ka.res_f64,
+                                           (int)c->layout.f64_words, c->res_f64_bytes, c->ka.res_f32,
+                                           c->layout.f32_words, c->stream, &c->launches);
     if (err != 0)
     {
         return fail(c, FEPB200_ERR_CUDA, "peer reduce launch failed: %s", cudaGetErrorString((cudaError_t)err));

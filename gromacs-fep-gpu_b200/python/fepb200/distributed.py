@@ -76,25 +76,31 @@ class ShardedFep:
         group = self.group if self.group is not None else dist.group.WORLD
         self.block_bytes = (self.ctx.result_block_bytes() + 255) // 256 * 256
         with torch.cuda.stream(self.stream):
-            self._sym = symm_mem.empty(2 * self.block_bytes, dtype=torch.uint8, device=torch.device("cuda", device))
+            # [slot 0 | slot 1 | flag array (16 x uint32 sequence numbers)]
+            self._sym = symm_mem.empty(2 * self.block_bytes + 256, dtype=torch.uint8, device=torch.device("cuda", device))
+            self._sym.zero_()
             self._hdl = symm_mem.rendezvous(self._sym, group)
+            self._hdl.barrier(channel=0)  # everybody's flags are zero before anybody announces a step
         base = [int(p) for p in self._hdl.buffer_ptrs]
         # two alternating slots: a rank that runs ahead writes the other slot, and cannot come back
-        # to this one before everybody has passed the next step's barrier
+        # to this one before everybody has announced the next step
         self._slots = [[b + k * self.block_bytes for b in base] for k in (0, 1)]
+        self._flags = [b + 2 * self.block_bytes for b in base]
         self.stream.synchronize()
 
     def launch(self, flags: int) -> None:
         """Kernels of this rank's shard, then the reduction over ranks, all asynchronous on self.stream."""
-        self.ctx.launch(flags)
         if self.reduction == "p2p":
             k = self._step & 1
             self._step += 1
-            with torch.cuda.stream(self.stream):
-                self.ctx.publish_result(self._slots[k][self.rank])
-                self._hdl.barrier(channel=k)
-                self.ctx.reduce_peers(self._slots[k])
-        elif self.reduction == "nccl":
+            # the epilogue writes this rank's partial result straight into its symmetric slot
+            self.ctx.set_partial_result_block(self._slots[k][self.rank])
+            self.ctx.launch(flags)
+            # one kernel: announce the step to all peers, wait for theirs, sum all blocks over NVLink
+            self.ctx.reduce_peers(self._slots[k], self._flags, self.rank, self._step)
+            return
+        self.ctx.launch(flags)
+        if self.reduction == "nccl":
             import torch.distributed as dist
 
             with torch.cuda.stream(self.stream):

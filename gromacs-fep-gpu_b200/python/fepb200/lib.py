@@ -72,7 +72,9 @@ SYMBOLS = {
     "fepb200_result_device_ptrs": (ctypes.c_int, [_VP, ctypes.POINTER(_VP), ctypes.POINTER(_VP)]),
     "fepb200_result_block_bytes": (ctypes.c_size_t, [_VP]),
     "fepb200_publish_result": (ctypes.c_int, [_VP, _VP]),
-    "fepb200_reduce_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP)]),
+    "fepb200_set_partial_result_block": (ctypes.c_int, [_VP, _VP]),
+    "fepb200_reduce_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int,
+                                            ctypes.c_uint]),
     "fepb200_download": (ctypes.c_int, [_VP, ctypes.c_int, _FP, _FP, _DP, _DP, _DP, _DP, _DP]),
     "fepb200_launch_count": (ctypes.c_longlong, [_VP]),
     "fepb200_last_launch_ms": (ctypes.c_int, [_VP, _FP]),
@@ -318,6 +320,11 @@ class FepContext:
     def publish_result(self, d_block: int) -> None:
         self._check(self._lib.fepb200_publish_result(self._h, _VP(d_block)))
 
-    def reduce_peers(self, peer_blocks: list[int]) -> None:
+    def set_partial_result_block(self, d_block: int | None) -> None:
+        self._check(self._lib.fepb200_set_partial_result_block(self._h, _VP(d_block) if d_block else None))
+
+    def reduce_peers(self, peer_blocks: list[int], peer_flags: list[int] | None = None, rank: int = 0,
+                     seq: int = 0) -> None:
         arr = (_VP * len(peer_blocks))(*[_VP(p) for p in peer_blocks])
-        self._check(self._lib.fepb200_reduce_peers(self._h, len(peer_blocks), arr))
+        flg = (_VP * len(peer_flags))(*[_VP(p) for p in peer_flags]) if peer_flags else None
+        self._check(self._lib.fepb200_reduce_peers(self._h, len(peer_blocks), arr, flg, int(rank), int(seq) & 0xFFFFFFFF))

@@ -212,15 +212,23 @@ int fepb200_result_device_ptrs(const fepb200_ctx* ctx, void** d_f32, void** d_f6
 /* ---- multi-GPU reduction over peer memory (NVLink), the alternative to handing the device
  * pointers to ncclAllReduce.  Every rank (1) publishes its result block into a buffer that all
  * ranks of the node have mapped (e.g. CUDA VMM / symmetric memory; fepb200_result_block_bytes()
- * bytes, 16-byte aligned), (2) passes a barrier the caller provides on the context's stream, then
- * (3) calls fepb200_reduce_peers() with the device pointers of ALL ranks' buffers in rank order:
- * one kernel reads every block over NVLink and leaves the full sum in this context's own result
- * block (ready for fepb200_download()).  Sums are taken in rank order: every rank gets
- * bit-identical results.  Use two alternating buffers so that a fast rank cannot overwrite a
+ * bytes, 16-byte aligned), then (2) calls fepb200_reduce_peers() with the device pointers of ALL
+ * ranks' buffers in rank order: one kernel reads every block over NVLink and leaves the full sum
+ * in this context's own result block (ready for fepb200_download()).  Sums are taken in rank
+ * order: every rank gets bit-identical results.
+ * The cross-GPU barrier between (1) and (2) is part of the same kernel when d_peer_flags is given:
+ * per rank a peer-mapped, zero-initialised array of 16 uint32; `seq` must be the same on all
+ * ranks and increase by one per step.  With d_peer_flags == NULL the caller provides the barrier
+ * on the context's stream.  Use two alternating buffers so that a fast rank cannot overwrite a
  * block a slow rank is still reading. */
 size_t fepb200_result_block_bytes(const fepb200_ctx* ctx);
 int    fepb200_publish_result(fepb200_ctx* ctx, void* d_block);
-int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks);
+/* Instead of publishing with a copy: make the following fepb200_launch() calls write this rank's
+ * (partial) result block directly at d_block (NULL = back to the context's own block).
+ * fepb200_reduce_peers() always writes the sum into the context's own block. */
+int    fepb200_set_partial_result_block(fepb200_ctx* ctx, void* d_block);
+int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags,
+                            int rank, unsigned int seq);
 
 /* Copy the result block to the host and add it into the caller's arrays (same
  * semantics as the tail of fepb200_compute).  Synchronous. */
