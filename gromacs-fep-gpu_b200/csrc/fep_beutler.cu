@@ -213,7 +213,7 @@ struct AccLayout
     static constexpr int iCA = NPER * C, iDC = iCA + 1, iGA = iCA + 2, iDG = iCA + 3;
     static constexpr int iCUR = NFOR;
     /* register budget: 4 CTAs of 128 threads per SM up to ~56 accumulators, else 2 */
-    static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : 4;
+    static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : (NACC > 30 ? 3 : 4);
 };
 
 template<bool EWALD, int MODE, int C, bool FORCE>
@@ -243,29 +243,57 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     const int   base  = blockIdx.x * bs.tile_pairs;
     const int   end   = min(base + bs.tile_pairs, ka.n_pairs);
 
-    /* the pair record of the NEXT trip is fetched while the current one is evaluated, which takes
-     * the streamed (DRAM) load out of the dependent chain record -> atom data -> type table */
-    int4 rec_next = make_int4(0, 0, -1, 0);
-    if (base + warp * 32 + lane < end)
-    {
-        rec_next = __ldg(ka.pair4 + base + warp * 32 + lane);
-    }
+    /* Software pipeline over the trips: while trip k is evaluated, the pair record of trip k+2 and
+     * the atom data of trip k+1 (whose record arrived during trip k-1) are in flight, so the
+     * dependent chain record -> atom data is paid once per thread, not once per trip. */
+    const int4 dummy  = make_int4(0, 0, -1, 0);
+    const int  slot0  = base + warp * 32 + lane;
+    int4       rec_n1 = slot0 < end ? __ldg(ka.pair4 + slot0) : dummy;
+    int4       rec_n2 = slot0 + FEP_FB_CTA < end ? __ldg(ka.pair4 + slot0 + FEP_FB_CTA) : dummy;
+    float4     xi_n   = __ldg(ka.pos4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
+    float4     xj_n   = __ldg(ka.pos4 + (rec_n1.x & 0x7fffffff));
+    float4     pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
+    float4     pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
     for (int w0 = base + warp * 32; w0 < end; w0 += FEP_FB_CTA)
     {
-        const int  slot   = w0 + lane;
-        const bool active = slot < end;
-        const int4 rec    = rec_next;
-        rec_next          = make_int4(0, 0, -1, 0);
-        if (slot + FEP_FB_CTA < end)
+        const int    slot   = w0 + lane;
+        const bool   active = slot < end;
+        const int4   rec    = rec_n1;
+        const float4 xi = xi_n, xj = xj_n, pi = pi_n, pq = pq_n;
+        rec_n1 = rec_n2;
+        rec_n2 = slot + 2 * FEP_FB_CTA < end ? __ldg(ka.pair4 + slot + 2 * FEP_FB_CTA) : dummy;
+        xi_n   = __ldg(ka.pos4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
+        xj_n   = __ldg(ka.pos4 + (rec_n1.x & 0x7fffffff));
+        pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
+        pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
+
+        /* segment structure of this trip and, for head lanes, where the segment sums go: known
+         * from the records alone, so these loads also overlap the evaluation */
+        int4     sd    = make_int4(0, 0, 0, 0);
+        unsigned hmask = 0;
+        int      after = 0;
+        bool     head  = false;
+        if (FORCE)
         {
-            rec_next = __ldg(ka.pair4 + slot + FEP_FB_CTA);
+            const int      entry    = rec.z;
+            const int      e_prev   = __shfl_up_sync(FULL_MASK, entry, 1);
+            const bool     boundary = (lane == 0) || (entry != e_prev);
+            const unsigned bmask    = __ballot_sync(FULL_MASK, boundary);
+            hmask                   = __ballot_sync(FULL_MASK, boundary && active);
+            const unsigned above    = bmask & ~((2u << lane) - 1u);
+            after                   = (above ? (__ffs(above) - 1) : 32) - 1 - lane;
+            head                    = boundary && active;
+            if (head)
+            {
+                const int h = __ldg(ka.warp_hbase + (w0 >> 5)) + __popc(hmask & ((1u << lane) - 1u));
+                sd          = __ldg(ka.seg_dst + h);
+            }
         }
+
         const bool   excluded = rec.x < 0;
         const int    cj       = rec.x & 0x7fffffff;
         const int    ci       = rec.y & (FEP_MAX_TOUCHED - 1);
-        const float4 xi       = __ldg(ka.pos4 + ci);
         const float4 sh       = ka.dyn->shiftvec[(rec.y >> 24) & 63];
-        const float4 xj       = __ldg(ka.pos4 + cj);
         /* the reference shifts the i atom first (:478-480) */
         const float dx = (sh.x + xi.x) - xj.x, dy = (sh.y + xi.y) - xj.y, dz = (sh.z + xi.z) - xj.z;
         float       r2      = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -276,8 +304,6 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 
         if (__any_sync(FULL_MASK, contrib))
         {
-            const float4 pi = __ldg(ka.par4 + ci);
-            const float4 pq = __ldg(ka.par4 + cj);
             const float4 ta = __ldg(ka.typetab + (ka.ntype * __float_as_int(pi.z) + __float_as_int(pq.z)));
             const float4 tb = __ldg(ka.typetab + (ka.ntype * __float_as_int(pi.w) + __float_as_int(pq.w)));
             const float  m  = contrib ? 1.0f : 0.0f;
@@ -444,16 +470,9 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
             {
                 /* the j atom receives -f: scattered to this pair's own slot in the atom-sorted
                  * buffer (unique destination, no atomics; skipped pairs write their zero) */
-                ka.fsorted[__ldg(ka.pair_dst + slot)] = make_float4(-fx, -fy, -fz, 0.0f);
+                ka.fsorted[rec.w] = make_float4(-fx, -fy, -fz, 0.0f);
             }
             /* segmented sum over the lanes of one i-entry: i force and Vc/Vv of the segment */
-            const int      entry    = rec.z;
-            const int      e_prev   = __shfl_up_sync(FULL_MASK, entry, 1);
-            const bool     boundary = (lane == 0) || (entry != e_prev);
-            const unsigned bmask    = __ballot_sync(FULL_MASK, boundary);
-            const unsigned hmask    = __ballot_sync(FULL_MASK, boundary && active);
-            const unsigned above    = bmask & ~((2u << lane) - 1u);
-            const int      after    = (above ? (__ffs(above) - 1) : 32) - 1 - lane;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
             {
@@ -471,11 +490,9 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
                     vvtot += ov;
                 }
             }
-            if (boundary && active)
+            if (head)
             {
-                const int  h  = __ldg(ka.warp_hbase + (w0 >> 5)) + __popc(hmask & ((1u << lane) - 1u));
-                const int4 sd = __ldg(ka.seg_dst + h);
-                const float4 fi = make_float4(fx, fy, fz, 0.0f);
+                const float4 fi  = make_float4(fx, fy, fz, 0.0f);
                 ka.fsorted[sd.x] = fi;
                 if (bs.want_shift)
                 {
@@ -604,7 +621,7 @@ extern "C" int fep_beutler_ctas_per_sm(int mode, int c, int force)
 {
     const int nper = mode == 0 ? 2 : 4;
     const int nacc = (c > 0 ? nper * c + 4 : 0) + (force ? 2 : 0);
-    return (nacc + (force ? 10 : 0) > 56) ? 2 : 4;
+    return (nacc + (force ? 10 : 0) > 56) ? 2 : (nacc > 30 ? 3 : 4);
 }
 
 /* One step of the Beutler path: `do_force` -> the pass at the current lambda is computed (fused

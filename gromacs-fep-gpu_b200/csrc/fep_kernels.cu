@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         {
             /* the j atom receives -t: scattered to this pair's own slot in the atom-sorted buffer
              * (unique destination, no atomics; skipped pairs write their zero) */
-            ka.fsorted[__ldg(ka.pair_dst + slot)] = make_float4(-fx, -fy, -fz, 0.0f);
+            ka.fsorted[__ldg(ka.pair4 + slot).w] = make_float4(-fx, -fy, -fz, 0.0f);
         }
     }
 

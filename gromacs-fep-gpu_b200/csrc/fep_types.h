@@ -12,7 +12,7 @@
  *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step
  *   typetab[T*T] float4 {c6,c12,sigma6,c6grid}               per nbfp upload
  *   pair4[P]     int4   {compact j | excluded << 31, compact i | shift << 24, local i-entry
- *                       index, 0}: everything a pair needs in ONE coalesced 16-byte load, so the
+ *                       index, pair_dst}: everything a pair needs in ONE coalesced 16-byte load, so the
  *                       dependent chain is record -> atom data -> type table  per search step
  *   ent4[E]      int4   {compact i, shift index, gid, 0}  (list read-back only) per search step
  *   warp_hbase[ceil(P/32)]  index of the first "segment" of each warp of the flat pair space;

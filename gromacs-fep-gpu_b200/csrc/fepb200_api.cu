@@ -913,6 +913,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         for (int s = 0; s < P; s++)
         {
             pair_dst[s] = fill[pair_j[s] & 0x7fffffff]++;
+            pair4[s].w  = pair_dst[s]; /* the record carries the pair's scatter slot */
         }
         for (int h = 0; h < H; h++)
         {
