@@ -230,6 +230,14 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
+    /* the 45 shift vectors are read once per pair with a data-dependent index: keep them on chip */
+    __shared__ float4 s_shift[FEP_NUM_SHIFT];
+    if (tid < FEP_NUM_SHIFT)
+    {
+        s_shift[tid] = ka.dyn->shiftvec[tid];
+    }
+    __syncthreads();
+
     /* Layout: [0,C) V_A, [C,2C) DV, MODE>0: [2C,3C) Cp_A, [3C,4C) DCp, then C_A DC G_A DG,
      * then (FORCE) dV/dlambda_coul, dV/dlambda_vdw of the current-lambda pass. */
     float acc[N8 * 8];
@@ -254,6 +262,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     float4     xj_n   = __ldg(ka.pos4 + (rec_n1.x & 0x7fffffff));
     float4     pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
     float4     pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
+    int        hb_n   = (FORCE && base + warp * 32 < end) ? __ldg(ka.warp_hbase + ((base + warp * 32) >> 5)) : 0;
     for (int w0 = base + warp * 32; w0 < end; w0 += FEP_FB_CTA)
     {
         const int    slot   = w0 + lane;
@@ -266,6 +275,11 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         xj_n   = __ldg(ka.pos4 + (rec_n1.x & 0x7fffffff));
         pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
         pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
+        const int hbase = hb_n; /* first segment id of this warp trip, fetched during the previous trip */
+        if (FORCE && w0 + FEP_FB_CTA < end)
+        {
+            hb_n = __ldg(ka.warp_hbase + ((w0 + FEP_FB_CTA) >> 5));
+        }
 
         /* segment structure of this trip and, for head lanes, where the segment sums go: known
          * from the records alone, so these loads also overlap the evaluation */
@@ -285,7 +299,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
             head                    = boundary && active;
             if (head)
             {
-                const int h = __ldg(ka.warp_hbase + (w0 >> 5)) + __popc(hmask & ((1u << lane) - 1u));
+                const int h = hbase + __popc(hmask & ((1u << lane) - 1u));
                 sd          = __ldg(ka.seg_dst + h);
             }
         }
@@ -293,7 +307,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         const bool   excluded = rec.x < 0;
         const int    cj       = rec.x & 0x7fffffff;
         const int    ci       = rec.y & (FEP_MAX_TOUCHED - 1);
-        const float4 sh       = ka.dyn->shiftvec[(rec.y >> 24) & 63];
+        const float4 sh       = s_shift[min((rec.y >> 24) & 63, FEP_NUM_SHIFT - 1)];
         /* the reference shifts the i atom first (:478-480) */
         const float dx = (sh.x + xi.x) - xj.x, dy = (sh.y + xi.y) - xj.y, dz = (sh.z + xi.z) - xj.z;
         float       r2      = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -552,19 +566,25 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* occ != nullptr: only report how many CTAs of this instantiation fit on one SM */
 template<bool EWALD, int MODE, int C, bool FORCE>
-static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream)
+static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream, int* occ)
 {
+    if (occ)
+    {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE>, FEP_FB_CTA, 0);
+        return;
+    }
     fep_beutler_kernel<EWALD, MODE, C, FORCE><<<bs.n_tiles, FEP_FB_CTA, 0, stream>>>(ka, bs);
 }
 
 template<bool EWALD, int MODE, bool FORCE>
-static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cudaStream_t stream)
+static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cudaStream_t stream, int* occ)
 {
     switch (c)
     {
 #define FEP_FB_CASE(N) \
-    case N: launch_one<EWALD, MODE, N, FORCE>(ka, bs, stream); return true;
+    case N: launch_one<EWALD, MODE, N, FORCE>(ka, bs, stream, occ); return true;
         FEP_FB_CASE(1)
         FEP_FB_CASE(2)
         FEP_FB_CASE(3)
@@ -581,7 +601,7 @@ static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cuda
         case 0:
             if (FORCE)
             {
-                launch_one<EWALD, MODE, 0, true>(ka, bs, stream);
+                launch_one<EWALD, MODE, 0, true>(ka, bs, stream, occ);
                 return true;
             }
             return false;
@@ -590,11 +610,11 @@ static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cuda
 }
 
 template<bool EWALD, bool FORCE>
-static bool launch_mode(const KernelArgs& ka, const BeutlerStep& bs, int mode, int c, cudaStream_t stream)
+static bool launch_mode(const KernelArgs& ka, const BeutlerStep& bs, int mode, int c, cudaStream_t stream, int* occ)
 {
-    return mode == 0   ? launch_size<EWALD, 0, FORCE>(ka, bs, c, stream)
-           : mode == 1 ? launch_size<EWALD, 1, FORCE>(ka, bs, c, stream)
-                       : launch_size<EWALD, 2, FORCE>(ka, bs, c, stream);
+    return mode == 0   ? launch_size<EWALD, 0, FORCE>(ka, bs, c, stream, occ)
+           : mode == 1 ? launch_size<EWALD, 1, FORCE>(ka, bs, c, stream, occ)
+                       : launch_size<EWALD, 2, FORCE>(ka, bs, c, stream, occ);
 }
 
 static const int c_sizes[] = { 1, 2, 3, 4, 6, 7, 8, 11, 14, 16, 21, 24 };
@@ -616,12 +636,24 @@ extern "C" int fep_beutler_chunk_size(int n_points, int n_chunks_wanted)
     return FEP_FB_MAXC;
 }
 
-/* accumulators of the largest kernel a step launches, for the tile sizing on the host */
-extern "C" int fep_beutler_ctas_per_sm(int mode, int c, int force)
+/* resident CTAs per SM of the kernel instantiation a launch would use (for one-wave tile sizing) */
+extern "C" int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int c, int force)
 {
-    const int nper = mode == 0 ? 2 : 4;
-    const int nacc = (c > 0 ? nper * c + 4 : 0) + (force ? 2 : 0);
-    return (nacc + (force ? 10 : 0) > 56) ? 2 : (nacc > 30 ? 3 : 4);
+    KernelArgs  ka{};
+    BeutlerStep bs{};
+    int         occ = 0;
+    bool        ok;
+    if (force)
+    {
+        ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, nullptr, &occ)
+                        : launch_mode<false, true>(ka, bs, mode, c, nullptr, &occ);
+    }
+    else
+    {
+        ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, nullptr, &occ)
+                        : launch_mode<false, false>(ka, bs, mode, c, nullptr, &occ);
+    }
+    return (ok && occ > 0) ? occ : 1;
 }
 
 /* One step of the Beutler path: `do_force` -> the pass at the current lambda is computed (fused
@@ -668,13 +700,13 @@ extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mod
         bool       ok;
         if (force)
         {
-            ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, stream)
-                            : launch_mode<false, true>(ka, bs, mode, c, stream);
+            ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, stream, nullptr)
+                            : launch_mode<false, true>(ka, bs, mode, c, stream, nullptr);
         }
         else
         {
-            ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, stream)
-                            : launch_mode<false, false>(ka, bs, mode, c, stream);
+            ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, stream, nullptr)
+                            : launch_mode<false, false>(ka, bs, mode, c, stream, nullptr);
         }
         if (!ok)
         {

@@ -140,7 +140,7 @@ int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlag
 #define FEP_FB_CTA 128
 #define FEP_FB_MAXC 24
 int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
-int fep_beutler_ctas_per_sm(int mode, int chunk_points, int force);
+int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force);
 int fep_launch_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_cur,
                        const LambdaPoint* host_pts, int do_force, int do_foreign, int want_shift, cudaStream_t stream,
                        long long* launch_counter);

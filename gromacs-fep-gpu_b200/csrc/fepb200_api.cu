@@ -343,8 +343,10 @@ int prepare_buffers(fepb200_ctx* c)
         {
             k.fuse_pass_and_foreign = std::atoi(env) != 0;
         }
-        tiles(fep_beutler_ctas_per_sm(c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign), k.tile_pairs, k.n_tiles);
-        tiles(8, k.pass_tile_pairs, k.pass_n_tiles);
+        /* occupancy of the very kernels the step will launch (cudaOccupancyMaxActiveBlocksPerMultiprocessor) */
+        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign),
+              k.tile_pairs, k.n_tiles);
+        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1), k.pass_tile_pairs, k.pass_n_tiles);
     }
     else
     {
