@@ -104,6 +104,8 @@ struct PinnedArray
     }
 };
 
+constexpr int c_copy_chunks = 1; /* pipeline depth of the host<->device copies of large steps */
+
 /* threads for the host-side gather / scatter of the touched atoms (about 16k atoms per thread) */
 int host_threads(int n)
 {
@@ -138,6 +140,7 @@ struct fepb200_ctx
     cudaEvent_t  fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t  ev_prof[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t  ev_copy[8] = {};
     bool         profiling = false, profiled = false;
     std::string  error;
     std::string  description;
@@ -491,6 +494,18 @@ int check_ready(fepb200_ctx* c)
 
 } // namespace
 
+static bool create_copy_events(fepb200_ctx* c)
+{
+    for (int i = 0; i < c_copy_chunks; i++)
+    {
+        if (cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming) != cudaSuccess)
+        {
+            return false;
+        }
+    }
+    return true;
+}
+
 /* =========================================================================================== */
 extern "C" {
 
@@ -531,6 +546,7 @@ int fepb200_create(fepb200_ctx** out, int device_ordinal)
         || cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess
         || cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess
         || cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess
+        || !create_copy_events(c)
         || c->d_counter.reserve(1) != cudaSuccess || cudaMemset(c->d_counter.ptr, 0, sizeof(unsigned int)) != cudaSuccess)
     {
         const int rc = fail(nullptr, FEPB200_ERR_CUDA, "CUDA initialisation failed: %s",
@@ -584,6 +600,13 @@ int fepb200_destroy(fepb200_ctx* c)
         if (c->ev_prof[i])
         {
             cudaEventDestroy(c->ev_prof[i]);
+        }
+    }
+    for (cudaEvent_t e : c->ev_copy)
+    {
+        if (e)
+        {
+            cudaEventDestroy(e);
         }
     }
     cudaEventDestroy(c->ev_start);
@@ -1203,17 +1226,27 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
     /* the previous H2D copy out of the pinned buffer must be done before it is overwritten */
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     stage_head(c, shiftvec);
-    float4*   pos = reinterpret_cast<float4*>(c->h_step_in.ptr + sizeof(DynHead));
-    const int nT  = c->layout.ntouched;
-    const int* t  = c->touched.data();
-#pragma omp parallel for schedule(static) num_threads(host_threads(nT)) if (nT > 16384)
-    for (int k = 0; k < nT; k++)
+    float4*    pos = reinterpret_cast<float4*>(c->h_step_in.ptr + sizeof(DynHead));
+    const int  nT  = c->layout.ntouched;
+    const int* t   = c->touched.data();
+    /* Pipelined: the touched coordinates are gathered into pinned memory chunk by chunk and each
+     * chunk's H2D copy is queued at once, so the DMA of chunk k runs while the host gathers k+1. */
+    const int nchunks = nT > 32768 ? c_copy_chunks : 1;
+    size_t    done    = 0; /* bytes of [DynHead | pos4] already queued */
+    for (int ch = 0; ch < nchunks; ch++)
     {
-        const float* xa = x + 3 * (size_t)t[k];
-        pos[k]          = make_float4(xa[0], xa[1], xa[2], 0.0f);
+        const int k0 = (int)((long long)nT * ch / nchunks), k1 = (int)((long long)nT * (ch + 1) / nchunks);
+#pragma omp parallel for schedule(static) num_threads(host_threads(k1 - k0)) if (k1 - k0 > 16384)
+        for (int k = k0; k < k1; k++)
+        {
+            const float* xa = x + 3 * (size_t)t[k];
+            pos[k]          = make_float4(xa[0], xa[1], xa[2], 0.0f);
+        }
+        const size_t upto = sizeof(DynHead) + sizeof(float4) * (size_t)k1;
+        CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr + done, c->h_step_in.ptr + done, upto - done, cudaMemcpyHostToDevice,
+                                    c->stream));
+        done = upto;
     }
-    CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr, c->h_step_in.ptr, sizeof(DynHead) + sizeof(float4) * (size_t)nT,
-                                cudaMemcpyHostToDevice, c->stream));
     return FEPB200_OK;
 }
 
@@ -1383,32 +1416,54 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
     {
         return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_download: an output requested by flags is NULL");
     }
-    const size_t bytes = c->res_f64_bytes + (sf.force ? c->res_f32_bytes : 0);
-    CU_CHECK(c, cudaMemcpyAsync(c->h_result.ptr, c->d_result.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    /* Pipelined: the fp64 block and the compact forces come back in chunks, each followed by an
+     * event; the host scatter-adds chunk k while the DMA of chunk k+1 runs. */
+    const int    nT      = l.ntouched;
+    const int    nchunks = (sf.force && nT > 32768) ? c_copy_chunks : 1;
+    const size_t f32_off = c->res_f64_bytes;
+    {
+        size_t done = 0;
+        for (int ch = 0; ch < nchunks; ch++)
+        {
+            size_t upto = f32_off;
+            if (sf.force)
+            {
+                const int k1 = (int)((long long)nT * (ch + 1) / nchunks);
+                upto         = (ch == nchunks - 1) ? f32_off + c->res_f32_bytes : f32_off + sizeof(float) * 3 * (size_t)k1;
+            }
+            CU_CHECK(c, cudaMemcpyAsync(c->h_result.ptr + done, c->d_result.ptr + done, upto - done,
+                                        cudaMemcpyDeviceToHost, c->stream));
+            CU_CHECK(c, cudaEventRecord(c->ev_copy[ch], c->stream));
+            done = upto;
+        }
+    }
     const double* r64 = reinterpret_cast<const double*>(c->h_result.ptr);
     const float*  r32 = reinterpret_cast<const float*>(c->h_result.ptr + c->res_f64_bytes);
     if (sf.force)
     {
         /* scatter of the compact forces into the caller's rvec array; only atoms that occur in
          * the list are written (with FEPB200_CLEAR_OUTPUTS: overwritten, all others untouched) */
-        const int* t  = c->touched.data();
-        const int  nT = l.ntouched;
-#pragma omp parallel for schedule(static) num_threads(host_threads(nT)) if (nT > 16384)
-        for (int k = 0; k < nT; k++)
+        const int* t = c->touched.data();
+        for (int ch = 0; ch < nchunks; ch++)
         {
-            float* fa = f + 3 * (size_t)t[k];
-            if (clear)
+            const int k0 = (int)((long long)nT * ch / nchunks), k1 = (int)((long long)nT * (ch + 1) / nchunks);
+            CU_CHECK(c, cudaEventSynchronize(c->ev_copy[ch]));
+#pragma omp parallel for schedule(static) num_threads(host_threads(k1 - k0)) if (k1 - k0 > 16384)
+            for (int k = k0; k < k1; k++)
             {
-                fa[0] = r32[3 * k];
-                fa[1] = r32[3 * k + 1];
-                fa[2] = r32[3 * k + 2];
-            }
-            else
-            {
-                fa[0] += r32[3 * k];
-                fa[1] += r32[3 * k + 1];
-                fa[2] += r32[3 * k + 2];
+                float* fa = f + 3 * (size_t)t[k];
+                if (clear)
+                {
+                    fa[0] = r32[3 * k];
+                    fa[1] = r32[3 * k + 1];
+                    fa[2] = r32[3 * k + 2];
+                }
+                else
+                {
+                    fa[0] += r32[3 * k];
+                    fa[1] += r32[3 * k + 1];
+                    fa[2] += r32[3 * k + 2];
+                }
             }
         }
         if (sf.shift)
@@ -1419,6 +1474,7 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
             }
         }
     }
+    CU_CHECK(c, cudaEventSynchronize(c->ev_copy[nchunks - 1]));
     if (sf.energy)
     {
         for (int g = 0; g < l.nenergrp; g++)
