@@ -54,6 +54,7 @@ struct BeutlerStep
     int   p0, np;               /* first point of the chunk, valid points   */
     int   want_shift;           /* also store segment forces sorted by shift vector */
     int   tile_pairs, n_tiles;  /* pair tile of one CTA for this launch     */
+    int   always_check;         /* a lambda outside [0,1]: no fast path     */
 };
 
 /* sums N8*8 per-lane values over the warp; afterwards lane l < 8 holds, for group g, the value
@@ -105,15 +106,24 @@ struct StateConsts
 };
 
 /* One foreign lambda point of one state: LJ energy vv (and Coulomb energy vc when the Coulomb
- * radius is soft-cored).  8 instructions in MODE 0. */
-template<bool EWALD, int MODE>
+ * radius is soft-cored).  CHECK = false is the fast path for warps in which no lane needs the
+ * lambda-dependent cut-off tests or the r^-6 clamp (see the caller): 5 instructions in MODE 0
+ * (FFMA, MUFU.RCP, FFMA, FFMA + the caller's FADD); CHECK = true adds clamp, compare and select. */
+template<bool EWALD, int MODE, bool CHECK>
 __device__ __forceinline__ void fb_point(const StateConsts& st, float r6, float sclv, float sclc, float thr_v,
                                          float rcoulomb6, float& vv, float& vc)
 {
     const float dv  = fmaf(st.kv, sclv, r6);
-    const float ri6 = fminf(fep_rcp(dv), FEP_MAX_RINV6);
-    vv              = fmaf(ri6, fmaf(st.c12_12, ri6, -st.c6_6), st.shiftc);
-    vv              = dv < thr_v ? vv : 0.0f;
+    float       ri6 = fep_rcp(dv);
+    if (CHECK)
+    {
+        ri6 = fminf(ri6, FEP_MAX_RINV6);
+    }
+    vv = fmaf(ri6, fmaf(st.c12_12, ri6, -st.c6_6), st.shiftc);
+    if (CHECK)
+    {
+        vv = dv < thr_v ? vv : 0.0f;
+    }
     if (MODE != 0)
     {
         const float dc  = (MODE == 1) ? dv : fmaf(st.kc, sclc, r6);
@@ -127,7 +137,43 @@ __device__ __forceinline__ void fb_point(const StateConsts& st, float r6, float 
         {
             const float rc2 = fep_ex2(lg * (1.0f / 3.0f));
             vc              = fmaf(st.qe, ric, fmaf(st.qkrf, rc2, st.qsh));
-            vc              = dc < rcoulomb6 ? vc : 0.0f;
+            if (CHECK)
+            {
+                vc = dc < rcoulomb6 ? vc : 0.0f;
+            }
+        }
+    }
+}
+
+/* the loop over the C lambda points of a chunk for the states the warp needs */
+template<bool EWALD, int MODE, int C, bool CHECK, bool DO_A, bool DO_B>
+__device__ __forceinline__ void fb_points(const StateConsts (&st)[2], const BeutlerStep& bs, float r6, float thr_v,
+                                          float rcoulomb6, float* acc)
+{
+#pragma unroll
+    for (int p = 0; p < C; p++)
+    {
+        float vvA = 0.0f, vvB = 0.0f, vcA = 0.0f, vcB = 0.0f;
+        if (DO_A)
+        {
+            fb_point<EWALD, MODE, CHECK>(st[0], r6, bs.sclv[0][p], bs.sclc[0][p], thr_v, rcoulomb6, vvA, vcA);
+        }
+        if (DO_B)
+        {
+            fb_point<EWALD, MODE, CHECK>(st[1], r6, bs.sclv[1][p], bs.sclc[1][p], thr_v, rcoulomb6, vvB, vcB);
+        }
+        if (DO_A)
+        {
+            acc[p] += vvA;
+        }
+        acc[C + p] += DO_A ? (DO_B ? vvB - vvA : -vvA) : vvB;
+        if (MODE != 0)
+        {
+            if (DO_A)
+            {
+                acc[2 * C + p] += vcA;
+            }
+            acc[3 * C + p] += DO_A ? (DO_B ? vcB - vcA : -vcA) : vcB;
         }
     }
 }
@@ -426,53 +472,71 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 
             if (C > 0)
             {
-                const bool pA = __any_sync(FULL_MASK, vdw_on[0] || (MODE != 0 && elec_on[0]));
-                const bool pB = __any_sync(FULL_MASK, vdw_on[1] || (MODE != 0 && elec_on[1]));
-                if (pA && pB)
-                {
+                /* Per lane and state the lambda-dependent tests fall in one of three classes, because
+                 * the soft-core radius satisfies r^6 <= rV^6 <= r^6 + alphaEff sigma6 for every lambda:
+                 * always outside (r^6 >= rc^6: coefficients zeroed here), always inside, or borderline.
+                 * Only warps with a borderline lane, or a lane so close that r^-6 needs its clamp,
+                 * take the loop with the per-point tests. */
+                bool slow = (r6 < 1.0e-15f && incl) || bs.always_check != 0;
 #pragma unroll
-                    for (int p = 0; p < C; p++)
+                for (int s = 0; s < 2; s++)
+                {
+                    if (vdw_on[s])
                     {
-                        float vvA, vvB, vcA = 0.0f, vcB = 0.0f;
-                        fb_point<EWALD, MODE>(st[0], r6, bs.sclv[0][p], bs.sclc[0][p], thr_v, ka.rcoulomb6, vvA, vcA);
-                        fb_point<EWALD, MODE>(st[1], r6, bs.sclv[1][p], bs.sclc[1][p], thr_v, ka.rcoulomb6, vvB, vcB);
-                        acc[p]     += vvA;
-                        acc[C + p] += vvB - vvA;
-                        if (MODE != 0)
+                        if (r6 >= thr_v)
                         {
-                            acc[2 * C + p] += vcA;
-                            acc[3 * C + p] += vcB - vcA;
+                            st[s].c6_6 = st[s].c12_12 = st[s].shiftc = 0.0f;
+                            vdw_on[s]                                = false;
+                        }
+                        else
+                        {
+                            slow = slow || (r6 + st[s].kv >= thr_v);
+                        }
+                    }
+                    if (MODE != 0 && !EWALD && elec_on[s])
+                    {
+                        if (r6 >= ka.rcoulomb6)
+                        {
+                            st[s].qe = st[s].qsh = st[s].qkrf = 0.0f;
+                            elec_on[s]                        = false;
+                        }
+                        else
+                        {
+                            slow = slow || (r6 + st[s].kc >= ka.rcoulomb6);
                         }
                     }
                 }
-                else if (pA)
+                const bool pA   = __any_sync(FULL_MASK, vdw_on[0] || (MODE != 0 && elec_on[0]));
+                const bool pB   = __any_sync(FULL_MASK, vdw_on[1] || (MODE != 0 && elec_on[1]));
+                const bool chk  = __any_sync(FULL_MASK, slow);
+                if (!chk)
                 {
-#pragma unroll
-                    for (int p = 0; p < C; p++)
+                    if (pA && pB)
                     {
-                        float vvA, vcA = 0.0f;
-                        fb_point<EWALD, MODE>(st[0], r6, bs.sclv[0][p], bs.sclc[0][p], thr_v, ka.rcoulomb6, vvA, vcA);
-                        acc[p]     += vvA;
-                        acc[C + p] -= vvA;
-                        if (MODE != 0)
-                        {
-                            acc[2 * C + p] += vcA;
-                            acc[3 * C + p] -= vcA;
-                        }
+                        fb_points<EWALD, MODE, C, false, true, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
+                    }
+                    else if (pA)
+                    {
+                        fb_points<EWALD, MODE, C, false, true, false>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
+                    }
+                    else if (pB)
+                    {
+                        fb_points<EWALD, MODE, C, false, false, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
                     }
                 }
-                else if (pB)
+                else
                 {
-#pragma unroll
-                    for (int p = 0; p < C; p++)
+                    if (pA && pB)
                     {
-                        float vvB, vcB = 0.0f;
-                        fb_point<EWALD, MODE>(st[1], r6, bs.sclv[1][p], bs.sclc[1][p], thr_v, ka.rcoulomb6, vvB, vcB);
-                        acc[C + p] += vvB;
-                        if (MODE != 0)
-                        {
-                            acc[3 * C + p] += vcB;
-                        }
+                        fb_points<EWALD, MODE, C, true, true, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
+                    }
+                    else if (pA)
+                    {
+                        fb_points<EWALD, MODE, C, true, true, false>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
+                    }
+                    else if (pB)
+                    {
+                        fb_points<EWALD, MODE, C, true, false, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
                     }
                 }
             }
@@ -676,7 +740,20 @@ extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mod
         bs.cur_scdlc[s] = cur->scdl_c[s];
         bs.cur_scdlv[s] = cur->scdl_v[s];
     }
-    bs.want_shift = want_shift;
+    bs.want_shift   = want_shift;
+    /* the fast path of the point loop assumes 0 <= soft-core lambda factor <= 1 */
+    bs.always_check = 0;
+    for (int q = 0; q < np; q++)
+    {
+        for (int s = 0; s < 2; s++)
+        {
+            if (!(pts[q].sclfac_v[s] >= 0.0f && pts[q].sclfac_v[s] <= 1.0f && pts[q].sclfac_c[s] >= 0.0f
+                  && pts[q].sclfac_c[s] <= 1.0f))
+            {
+                bs.always_check = 1;
+            }
+        }
+    }
     bs.tile_pairs = do_foreign ? ka.tile_pairs : ka.pass_tile_pairs;
     bs.n_tiles    = do_foreign ? ka.n_tiles : ka.pass_n_tiles;
     bool first    = true;
