@@ -295,7 +295,10 @@ def run_ours(args, name):
         and problem.params.vdw_modifier != 3 else "fep_foreign_kernel"
     roofline = dict(bound="fp32", kernel=dominant + (" (current-lambda pass fused in)" if fused else " (foreign-lambda passes)"),
                     achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
-                    frac=achieved / fp32_peak, traffic=None,
+                    frac=achieved / fp32_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
+                    # ncu --set full capture committed as profiles/r01_ncu_full_final_raw.csv (C5, 1 GPU)
+                    traffic=17102080 if (name == "C5" and world == 1) else None,
                     note="achieved = ALGORITHMIC flop (150/pair + 12/i-entry per lambda pass, the reference's count) / kernel time; "
                          "the kernel hoists everything lambda-independent out of the pass loop, so the executed "
                          "FP32 instruction count per pass is far below 150 and frac can exceed 1; "
