@@ -17,7 +17,7 @@
  *   ent4[E]      int4   {compact i, shift index, gid, 0}  (list read-back only) per search step
  *   warp_hbase[ceil(P/32)]  index of the first "segment" of each warp of the flat pair space;
  *                a segment is a maximal run of pairs of one i-entry inside one warp
- *   pair_dst[P]  int    where the pair's force on its j atom goes in fsorted     per search step
+ *                (pair4[].w is where the pair's force on its j atom goes in fsorted)
  *   seg_dst[H]   int4   {slot in fsorted, slot in fshift_sorted, slot in ev2, 0} per search step
  *   fsorted[P+H] float4 force contributions SORTED BY RECEIVING ATOM: atom k owns the contiguous
  *                range [atom_ptr[k], atom_ptr[k+1]); the pass kernel scatters -t (pairs, as j) and
@@ -99,7 +99,6 @@ struct KernelArgs
     const float4*   typetab;
     const int4*     pair4;
     const int*      warp_hbase;
-    const int*      pair_dst;
     const int4*     seg_dst;
     /* intermediates */
     float4* fsorted;

@@ -16,6 +16,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -183,7 +184,7 @@ struct fepb200_ctx
     std::vector<int> compact_of; /* atom -> compact or -1 */
     int              n_segments = 0;
 
-    DeviceArray<int>    d_touched, d_warp_hbase, d_atom_ptr, d_pair_dst, d_key_job_ptr;
+    DeviceArray<int>    d_touched, d_warp_hbase, d_atom_ptr, d_key_job_ptr;
     DeviceArray<int4>   d_ent4, d_seg_dst, d_pair4;
     DeviceArray<RedJob> d_red_jobs;
     DeviceArray<float4> d_par4, d_fsorted, d_fshift_sorted;
@@ -578,7 +579,6 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_pair4.release();
     c->d_warp_hbase.release();
     c->d_atom_ptr.release();
-    c->d_pair_dst.release();
     c->d_seg_dst.release();
     c->d_key_job_ptr.release();
     c->d_ent4.release();
@@ -806,6 +806,17 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         return fail(c, FEPB200_ERR_STATE, "fepb200_set_atoms() must precede fepb200_set_list()");
     }
     cudaSetDevice(c->device);
+    const bool  timing = std::getenv("FEPB200_TIMING") != nullptr;
+    const auto  t_begin = std::chrono::steady_clock::now();
+    auto        lap     = [&, last = t_begin](const char* what) mutable {
+        if (timing)
+        {
+            const auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[fepb200_set_list] %-28s %8.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(now - last).count());
+            last = now;
+        }
+    };
     const long long nrj_total = nri > 0 ? jindex[nri] : 0;
     if (nri > 0 && (jindex[0] != 0 || nrj_total < 0 || (nrj_total > 0 && !jjnr)))
     {
@@ -823,14 +834,23 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
             return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: i-entry %d is malformed", n);
         }
     }
-    for (long long k = 0; k < nrj_total; k++)
     {
-        if (jjnr[k] < 0 || jjnr[k] >= c->natoms)
+        long long bad = -1;
+#pragma omp parallel for schedule(static) reduction(max : bad) num_threads(std::min(8, std::max(1, omp_get_max_threads()))) if (nrj_total > 65536)
+        for (long long k = 0; k < nrj_total; k++)
         {
-            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: jjnr[%lld] out of range", k);
+            if (jjnr[k] < 0 || jjnr[k] >= c->natoms)
+            {
+                bad = std::max(bad, k);
+            }
+        }
+        if (bad >= 0)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: jjnr[%lld] out of range", bad);
         }
     }
 
+    lap("validate");
     /* touched atoms of the FULL list (same numbering on every rank; mirrors the reduction mask
      * of setReductionMaskFromFepPairlist, freeenergydispatch.cpp:74-89) */
     c->compact_of.assign(c->natoms, -1);
@@ -853,6 +873,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     }
     const int nT = (int)c->touched.size();
 
+    lap("touched atoms");
     /* this rank's contiguous range of i-entries, balanced by pair count */
     int e0 = 0, e1 = nri;
     if (nranks > 1)
@@ -886,6 +907,8 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     }
     std::vector<int>  pair_j(P), pair_e(P);
     std::vector<int4> ent4(E), pair4(P);
+    const int         nthr = std::min(8, std::max(1, omp_get_max_threads()));
+#pragma omp parallel for schedule(static) num_threads(nthr) if (P > 65536)
     for (int n = 0; n < E; n++)
     {
         const int g = e0 + n;
@@ -899,6 +922,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         }
     }
 
+    lap("pair records");
     /* segments: maximal runs of one i-entry inside one 32-pair warp */
     const int        n_warps = (P + 31) / 32;
     std::vector<int> warp_hbase(std::max(n_warps, 1), 0), seg_entry;
@@ -917,6 +941,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     }
     const int H = (int)seg_entry.size();
 
+    lap("segments");
     /* Atom-sorted contribution buffer: atom k owns [atom_ptr[k], atom_ptr[k+1]); within a range
      * the pair contributions (as j) come first in slot order, then the segments (as i). */
     std::vector<int>  atom_ptr(nT + 1, 0), pair_dst(P);
@@ -946,6 +971,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         }
     }
 
+    lap("atom-sorted slots");
     /* segments sorted by shift vector (-> fshift_sorted) and by energy-group pair (-> ev2); the
      * reduction jobs are chunks of those ranges */
     std::vector<RedJob> jobs;
@@ -997,6 +1023,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     }
     key_job_ptr[FEP_NUM_SHIFT + ngrp] = (int)jobs.size();
 
+    lap("reduction jobs");
     /* per-atom parameters in compact order */
     std::vector<float4> par4(nT);
     for (int k = 0; k < nT; k++)
@@ -1005,11 +1032,12 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         par4[k]     = make_float4(c->qA[a], c->qB[a], int_bits_as_float(c->typeA[a]), int_bits_as_float(c->typeB[a]));
     }
 
+    lap("atom parameters");
     int rc;
     if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair4, pair4))
         || (rc = to_device(c, c->d_ent4, ent4))
         || (rc = to_device(c, c->d_warp_hbase, warp_hbase)) || (rc = to_device(c, c->d_atom_ptr, atom_ptr))
-        || (rc = to_device(c, c->d_pair_dst, pair_dst)) || (rc = to_device(c, c->d_red_jobs, jobs))
+        || (rc = to_device(c, c->d_red_jobs, jobs))
         || (rc = to_device(c, c->d_seg_dst, seg_dst)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
         || (rc = to_device(c, c->d_par4, par4)))
     {
@@ -1020,6 +1048,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     CU_CHECK(c, c->d_ev2.reserve(std::max(H, 1)));
     CU_CHECK(c, c->d_job_part.reserve(4 * std::max<size_t>(jobs.size(), 1)));
     CU_CHECK(c, cudaStreamSynchronize(c->stream)); /* host vectors go out of scope */
+    lap("H2D copies");
 
     KernelArgs& k = c->ka;
     k.n_pairs     = P;
@@ -1034,7 +1063,6 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     k.warp_hbase  = c->d_warp_hbase.ptr;
     k.fsorted       = c->d_fsorted.ptr;
     k.fshift_sorted = c->d_fshift_sorted.ptr;
-    k.pair_dst      = c->d_pair_dst.ptr;
     k.seg_dst       = c->d_seg_dst.ptr;
     k.ev2         = c->d_ev2.ptr;
     k.job_part    = c->d_job_part.ptr;
