@@ -182,6 +182,11 @@ struct fepb200_ctx
     int              first_entry = 0;
     std::vector<int> touched;    /* compact -> atom */
     std::vector<int> compact_of; /* atom -> compact or -1 */
+    /* work arrays of fepb200_set_list(), kept between calls so that a search step does not pay for
+     * page faults of fresh allocations */
+    std::vector<int>    w_pair_j, w_pair_e, w_warp_hbase, w_seg_entry, w_atom_ptr, w_fill;
+    std::vector<int4>   w_ent4, w_pair4, w_seg_dst;
+    std::vector<float4> w_par4;
     int              n_segments = 0;
 
     DeviceArray<int>    d_touched, d_warp_hbase, d_atom_ptr, d_key_job_ptr;
@@ -905,8 +910,14 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     {
         return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d distinct atoms in one FEP list", FEP_MAX_TOUCHED);
     }
-    std::vector<int>  pair_j(P), pair_e(P);
-    std::vector<int4> ent4(E), pair4(P);
+    std::vector<int>&  pair_j = c->w_pair_j;
+    std::vector<int>&  pair_e = c->w_pair_e;
+    std::vector<int4>& ent4   = c->w_ent4;
+    std::vector<int4>& pair4  = c->w_pair4;
+    pair_j.resize(P);
+    pair_e.resize(P);
+    ent4.resize(E);
+    pair4.resize(P);
     const int         nthr = std::min(8, std::max(1, omp_get_max_threads()));
 #pragma omp parallel for schedule(static) num_threads(nthr) if (P > 65536)
     for (int n = 0; n < E; n++)
@@ -925,7 +936,10 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     lap("pair records");
     /* segments: maximal runs of one i-entry inside one 32-pair warp */
     const int        n_warps = (P + 31) / 32;
-    std::vector<int> warp_hbase(std::max(n_warps, 1), 0), seg_entry;
+    std::vector<int>& warp_hbase = c->w_warp_hbase;
+    std::vector<int>& seg_entry  = c->w_seg_entry;
+    warp_hbase.assign(std::max(n_warps, 1), 0);
+    seg_entry.clear();
     seg_entry.reserve((size_t)E + n_warps);
     for (int w = 0; w < n_warps; w++)
     {
@@ -944,8 +958,10 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     lap("segments");
     /* Atom-sorted contribution buffer: atom k owns [atom_ptr[k], atom_ptr[k+1]); within a range
      * the pair contributions (as j) come first in slot order, then the segments (as i). */
-    std::vector<int>  atom_ptr(nT + 1, 0), pair_dst(P);
-    std::vector<int4> seg_dst(H);
+    std::vector<int>&  atom_ptr = c->w_atom_ptr;
+    std::vector<int4>& seg_dst  = c->w_seg_dst;
+    atom_ptr.assign(nT + 1, 0);
+    seg_dst.resize(H);
     for (int s = 0; s < P; s++)
     {
         atom_ptr[(pair_j[s] & 0x7fffffff) + 1]++;
@@ -959,11 +975,11 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
         atom_ptr[a + 1] += atom_ptr[a];
     }
     {
-        std::vector<int> fill(atom_ptr.begin(), atom_ptr.end() - 1);
+        std::vector<int>& fill = c->w_fill;
+        fill.assign(atom_ptr.begin(), atom_ptr.end() - 1);
         for (int s = 0; s < P; s++)
         {
-            pair_dst[s] = fill[pair_j[s] & 0x7fffffff]++;
-            pair4[s].w  = pair_dst[s]; /* the record carries the pair's scatter slot */
+            pair4[s].w = fill[pair_j[s] & 0x7fffffff]++; /* the record carries the pair's scatter slot */
         }
         for (int h = 0; h < H; h++)
         {
@@ -1025,7 +1041,8 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
 
     lap("reduction jobs");
     /* per-atom parameters in compact order */
-    std::vector<float4> par4(nT);
+    std::vector<float4>& par4 = c->w_par4;
+    par4.resize(nT);
     for (int k = 0; k < nT; k++)
     {
         const int a = c->touched[k];
