@@ -101,6 +101,16 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def _make_problem(name, args):
+    from fepb200.synth import SPECS, make_system
+
+    if args.n_foreign is None:
+        return make_system(name)
+    import dataclasses
+
+    return make_system(dataclasses.replace(SPECS[name], n_foreign=args.n_foreign))
+
+
 def _workload(problem):
     nb = problem.nblist
     passes = 1 + (problem.n_foreign + 1)
@@ -181,7 +191,7 @@ def run_reference_arm(args, name):
     from fepb200 import params as P
     from fepb200.synth import make_system
 
-    problem = make_system(name)
+    problem = _make_problem(name, args)
     flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
     cpu = cpu_reference(problem, flags, args.steps, args.warmup, budget_s=120.0)
     line = dict(impl="reference", metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
@@ -224,7 +234,7 @@ def run_ours(args, name):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    problem = make_system(name)
+    problem = _make_problem(name, args)
     wl = _workload(problem)
     flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
     sh = ShardedFep(problem, local, rank, world)
@@ -364,6 +374,7 @@ def main():
     ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-foreign", type=int, default=None, help="override the number of foreign lambda points")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "ours" and world != args.gpus:
