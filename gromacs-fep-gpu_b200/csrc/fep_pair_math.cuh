@@ -223,11 +223,14 @@ __device__ __forceinline__ void fep_included_terms(const KernelArgs& ka, const L
             {
                 /* nb_softcore.h:73-195 */
                 const float lfac = lp.lfac_c[s];
-                if (lfac < 1.0f && pr.a_c > 0.0f && ka.epsfac != 0.0f)
+                if (lfac < 1.0f && pr.a_c > 0.0f && ka.gapsys_facel != 0.0f)
                 {
-                    float      rq         = lp.g6_c[s] * (1.0f + fabsf(pr.qq[s] / ka.epsfac)) * pr.a_c;
-                    const bool within_cut = rq <= ka.rcoulomb;
-                    rq                    = fminf(rq, ka.rcoulomb);
+                    /* facel and the cut-off of the linearisation point are separate constants: for
+                     * 1-4 pairs they are not the (fudged) epsfac / cut-off of the interaction itself
+                     * (listed_forces/pairs.cpp:318-338) */
+                    float      rq         = lp.g6_c[s] * (1.0f + fabsf(pr.qq[s] / ka.gapsys_facel)) * pr.a_c;
+                    const bool within_cut = rq <= ka.gapsys_rcoul;
+                    rq                    = fminf(rq, ka.gapsys_rcoul);
                     if (pr.r < rq)
                     {
                         const float rinvq = fep_rcp(rq);

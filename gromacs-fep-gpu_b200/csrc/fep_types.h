@@ -82,6 +82,7 @@ struct KernelArgs
     float beta, beta2, beta3, lj_coeff_sq, lj_coeff6_div6, disp_cpot, rep_cpot;
     float rcut_max2, rcoulomb6, rvdw6;
     float alpha_c, alpha_v, gscale_c, gscale_v;
+    float gapsys_facel, gapsys_rcoul; /* epsfac and r_coulomb as seen by the Gapsys Coulomb linearisation */
     float sw_v3, sw_v4, sw_v5, sw_f2, sw_f3, sw_f4;
     int   vdw_ewald, pot_switch, rf_type, ntype;
     /* sizes */

@@ -707,6 +707,8 @@ int fepb200_set_params(fepb200_ctx* c, const fepb200_params* p)
     k.alpha_v  = p->alphaVdw;
     k.gscale_c = p->gapsysScaleLinpointCoul;
     k.gscale_v = p->gapsysScaleLinpointVdW;
+    k.gapsys_facel = p->epsfac;
+    k.gapsys_rcoul = p->rcoulomb;
     k.vdw_ewald  = p->vdwtype == FEPB200_VDW_PME;
     k.pot_switch = p->vdw_modifier == FEPB200_MOD_POTSWITCH;
     k.rf_type    = !ewald;
@@ -1608,6 +1610,308 @@ int fepb200_last_launch_ms(fepb200_ctx* c, float* ms)
     cudaSetDevice(c->device);
     CU_CHECK(c, cudaEventSynchronize(c->ev_stop));
     CU_CHECK(c, cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
+    return FEPB200_OK;
+}
+
+
+/* =========================================================================================== */
+/* Perturbed 1-4 pair interactions.
+ *
+ * Replaces the perturbed branch of do_pairs(F_LJ14, ...) (listed_forces/pairs.cpp:516-835 with
+ * free_energy_evaluate_single, :170-515) and the fork's pairs_fep_gpu
+ * (listed_forces/listed_forces_gpu_internal.cu:1365-1500).  The soft-core mathematics is the one of
+ * the non-bonded perturbed pairs without cut-offs, shifts and long-range corrections, so the
+ * pairs are run through the same kernels: every 1-4 pair becomes an i-entry with one j atom of a
+ * private pair list whose "atoms" are per-pair copies (i copy: charges of ai and the 1-4 type as
+ * its A/B type; j copy: charges of aj), evaluated with plain Coulomb (epsfac * fudgeQQ, k_rf = c_rf
+ * = 0), plain LJ and effectively infinite cut-offs.  The minimum-image shift of pbc_dx_aiuc
+ * (pbcutil/pbc.cpp:825-851, rectangular boxes) is applied to the i copy's coordinates on the host
+ * each step, and the shift forces follow from the per-pair forces (pairs.cpp:822-829). */
+/* =========================================================================================== */
+struct fepb200_pairs14
+{
+    fepb200_ctx*       ctx = nullptr;
+    std::string        error;
+    fepb200_params     ic{};
+    float              fudge       = 1.0f;
+    bool               have_params = false, have_pairs = false;
+    int                natoms = 0, npairs = 0, ngrp = 1;
+    std::vector<int>   ai, aj, shift_idx;
+    std::vector<float> xp, fp, zero_shift;
+    std::vector<double> vc, vv;
+    float              last_lambda[FEPB200_NUM_LAMBDA_COMPONENTS];
+    bool               have_lambda = false;
+};
+
+static int fail14(fepb200_pairs14* h, int code, const char* msg)
+{
+    if (h)
+    {
+        h->error = msg;
+    }
+    else
+    {
+        g_create_error = msg;
+    }
+    return code;
+}
+
+static int inner14(fepb200_pairs14* h, int rc)
+{
+    if (rc != FEPB200_OK)
+    {
+        h->error = fepb200_last_error(h->ctx);
+    }
+    return rc;
+}
+
+int fepb200_pairs14_create(fepb200_pairs14** out, int device_ordinal)
+{
+    if (!out)
+    {
+        return fail14(nullptr, FEPB200_ERR_INVALID_ARGUMENT, "handle pointer is NULL");
+    }
+    *out                = nullptr;
+    fepb200_pairs14* h  = new fepb200_pairs14();
+    const int        rc = fepb200_create(&h->ctx, device_ordinal);
+    if (rc != FEPB200_OK)
+    {
+        delete h;
+        return rc; /* message already in the create-error slot */
+    }
+    h->zero_shift.assign(3 * FEP_NUM_SHIFT, 0.0f);
+    *out = h;
+    return FEPB200_OK;
+}
+
+int fepb200_pairs14_destroy(fepb200_pairs14* h)
+{
+    if (h)
+    {
+        fepb200_destroy(h->ctx);
+        delete h;
+    }
+    return FEPB200_OK;
+}
+
+const char* fepb200_pairs14_last_error(const fepb200_pairs14* h)
+{
+    return h ? h->error.c_str() : g_create_error.c_str();
+}
+
+int fepb200_pairs14_set_params(fepb200_pairs14* h, const fepb200_params* ic, float fudgeQQ)
+{
+    if (!h || !ic)
+    {
+        return fail14(h, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_pairs14_set_params: NULL argument");
+    }
+    fepb200_params p            = *ic;
+    p.eeltype                   = FEPB200_EEL_CUT; /* plain Coulomb: reaction-field form with k_rf = c_rf = 0 */
+    p.vdwtype                   = FEPB200_VDW_CUT;
+    p.vdw_modifier              = FEPB200_MOD_NONE;
+    p.epsfac                    = ic->epsfac * fudgeQQ; /* pairs.cpp:624 */
+    p.rcoulomb                  = 1.0e15f;              /* no cut-off for 1-4 pairs */
+    p.rvdw                      = 1.0e15f;
+    p.rvdw_switch               = 0.0f;
+    p.reactionFieldCoefficient  = 0.0f;
+    p.reactionFieldShift        = 0.0f;
+    p.sh_ewald                  = 0.0f;
+    p.sh_lj_ewald               = 0.0f;
+    p.dispersion_shift_cpot     = 0.0f;
+    p.repulsion_shift_cpot      = 0.0f;
+    const int rc                = inner14(h, fepb200_set_params(h->ctx, &p));
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    /* the Gapsys linearisation point uses the un-fudged epsfac and the real Coulomb cut-off */
+    h->ctx->ka.gapsys_facel = ic->epsfac;
+    h->ctx->ka.gapsys_rcoul = ic->rcoulomb;
+    h->ic                   = *ic;
+    h->fudge                = fudgeQQ;
+    h->have_params          = true;
+    return FEPB200_OK;
+}
+
+int fepb200_pairs14_set_pairs(fepb200_pairs14* h, int natoms, const float* chargeA, const float* chargeB, int npairs,
+                              const int* iatoms, int ntypes, const float* c6A, const float* c12A, const float* c6B,
+                              const float* c12B, const int* gid, int nenergrp_pairs)
+{
+    if (!h || natoms < 0 || npairs < 0 || ntypes < 1 || nenergrp_pairs < 1
+        || (npairs > 0 && (!chargeA || !chargeB || !iatoms || !c6A || !c12A || !c6B || !c12B)))
+    {
+        return fail14(h, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_pairs14_set_pairs: bad arguments");
+    }
+    if (!h->have_params)
+    {
+        return fail14(h, FEPB200_ERR_STATE, "fepb200_pairs14_set_params() has not been called");
+    }
+    if (ntypes > 2048)
+    {
+        return fail14(h, FEPB200_ERR_UNSUPPORTED, "more than 2048 perturbed 1-4 interaction types");
+    }
+    /* 1-4 type t -> inner atom types 2t (state A) and 2t+1 (state B) of the i copy; j copies have
+     * type 0, so the pair parameters sit in column 0 of the inner table */
+    const int          nt = 2 * ntypes;
+    std::vector<float> nbfp(2 * (size_t)nt * nt, 0.0f);
+    for (int t = 0; t < ntypes; t++)
+    {
+        nbfp[2 * ((size_t)nt * (2 * t) + 0)]         = 6.0f * c6A[t]; /* pairs.cpp:655-656 */
+        nbfp[2 * ((size_t)nt * (2 * t) + 0) + 1]     = 12.0f * c12A[t];
+        nbfp[2 * ((size_t)nt * (2 * t + 1) + 0)]     = 6.0f * c6B[t]; /* pairs.cpp:686-687 */
+        nbfp[2 * ((size_t)nt * (2 * t + 1) + 0) + 1] = 12.0f * c12B[t];
+    }
+    int rc = inner14(h, fepb200_set_nbfp(h->ctx, nt, nbfp.data(), nullptr));
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    std::vector<float> qa(2 * (size_t)npairs), qb(2 * (size_t)npairs);
+    std::vector<int>   ta(2 * (size_t)npairs), tb(2 * (size_t)npairs), iinr(npairs), shift(npairs, FEP_CENTRAL_SHIFT),
+            jindex(npairs + 1), jjnr(npairs), gids(npairs, 0);
+    h->ai.resize(npairs);
+    h->aj.resize(npairs);
+    for (int p = 0; p < npairs; p++)
+    {
+        const int t = iatoms[3 * p], i = iatoms[3 * p + 1], j = iatoms[3 * p + 2];
+        if (t < 0 || t >= ntypes || i < 0 || i >= natoms || j < 0 || j >= natoms || (gid && (gid[p] < 0 || gid[p] >= nenergrp_pairs)))
+        {
+            return fail14(h, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_pairs14_set_pairs: malformed pair");
+        }
+        h->ai[p]      = i;
+        h->aj[p]      = j;
+        qa[2 * p]     = chargeA[i];
+        qb[2 * p]     = chargeB[i];
+        ta[2 * p]     = 2 * t;
+        tb[2 * p]     = 2 * t + 1;
+        qa[2 * p + 1] = chargeA[j];
+        qb[2 * p + 1] = chargeB[j];
+        ta[2 * p + 1] = 0;
+        tb[2 * p + 1] = 0;
+        iinr[p]       = 2 * p;
+        jjnr[p]       = 2 * p + 1;
+        jindex[p]     = p;
+        gids[p]       = gid ? gid[p] : 0;
+    }
+    jindex[npairs] = npairs;
+    if ((rc = inner14(h, fepb200_set_atoms(h->ctx, 2 * npairs, qa.data(), qb.data(), ta.data(), tb.data()))) != FEPB200_OK
+        || (rc = inner14(h, fepb200_set_list(h->ctx, npairs, iinr.data(), gids.data(), shift.data(), jindex.data(),
+                                             jjnr.data(), nullptr, nenergrp_pairs, 0, 1)))
+                   != FEPB200_OK)
+    {
+        return rc;
+    }
+    h->natoms = natoms;
+    h->npairs = npairs;
+    h->ngrp   = nenergrp_pairs;
+    h->xp.assign(6 * (size_t)npairs, 0.0f);
+    h->fp.assign(6 * (size_t)npairs, 0.0f);
+    h->shift_idx.assign(npairs, FEP_CENTRAL_SHIFT);
+    h->vc.assign(nenergrp_pairs, 0.0);
+    h->vv.assign(nenergrp_pairs, 0.0);
+    h->have_pairs = true;
+    return FEPB200_OK;
+}
+
+int fepb200_pairs14_compute(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, const float* lambda,
+                            int flags, float* f, float* fshift, double* Vc14, double* Vv14, double* dvdl)
+{
+    if (!h || !x || !lambda || !dvdl || (pbc_type != 0 && !box_diag) || pbc_type < 0 || pbc_type > 2)
+    {
+        return fail14(h, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_pairs14_compute: bad arguments");
+    }
+    if (!h->have_pairs)
+    {
+        return fail14(h, FEPB200_ERR_STATE, "fepb200_pairs14_set_pairs() has not been called");
+    }
+    const bool do_f = (flags & FEPB200_DO_FORCE) != 0, do_vir = do_f && (flags & FEPB200_DO_SHIFTFORCE) != 0,
+               do_e = (flags & FEPB200_DO_POTENTIAL) != 0;
+    if ((do_f && !f) || (do_vir && !fshift) || (do_e && (!Vc14 || !Vv14)))
+    {
+        return fail14(h, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_pairs14_compute: an output requested by flags is NULL");
+    }
+    int rc;
+    if (!h->have_lambda || std::memcmp(h->last_lambda, lambda, sizeof(h->last_lambda)) != 0)
+    {
+        if ((rc = inner14(h, fepb200_set_lambdas(h->ctx, lambda, 0, nullptr, nullptr))) != FEPB200_OK)
+        {
+            return rc;
+        }
+        std::memcpy(h->last_lambda, lambda, sizeof(h->last_lambda));
+        h->have_lambda = true;
+    }
+    if (h->npairs == 0)
+    {
+        return FEPB200_OK;
+    }
+    /* per-pair copies of the coordinates; the minimum-image shift goes onto the i copy */
+    for (int p = 0; p < h->npairs; p++)
+    {
+        const float* xi = x + 3 * (size_t)h->ai[p];
+        const float* xj = x + 3 * (size_t)h->aj[p];
+        int          is[3] = { 0, 0, 0 };
+        for (int d = 0; d < 3; d++)
+        {
+            float sh = 0.0f;
+            if (pbc_type == 1 || (pbc_type == 2 && d < 2))
+            {
+                const float dx = xi[d] - xj[d], hbox = 0.5f * box_diag[d];
+                if (dx > hbox)
+                {
+                    sh = -box_diag[d];
+                    is[d]--;
+                }
+                else if (dx <= -hbox)
+                {
+                    sh = box_diag[d];
+                    is[d]++;
+                }
+            }
+            h->xp[6 * (size_t)p + d]     = xi[d] + sh;
+            h->xp[6 * (size_t)p + 3 + d] = xj[d];
+        }
+        h->shift_idx[p] = 5 * (3 * (is[2] + 1) + (is[1] + 1)) + (is[0] + 2);
+    }
+    const int inner_flags = (flags & (FEPB200_DO_FORCE | FEPB200_DO_POTENTIAL)) | FEPB200_CLEAR_OUTPUTS;
+    double    dv[2]       = { 0.0, 0.0 };
+    rc = inner14(h, fepb200_compute(h->ctx, h->xp.data(), h->zero_shift.data(), inner_flags, h->fp.data(), nullptr,
+                                    h->vc.data(), h->vv.data(), dv, nullptr, nullptr));
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    if (do_f)
+    {
+        for (int p = 0; p < h->npairs; p++)
+        {
+            const float* fi = h->fp.data() + 6 * (size_t)p;
+            float*       fa = f + 3 * (size_t)h->ai[p];
+            float*       fb = f + 3 * (size_t)h->aj[p];
+            for (int d = 0; d < 3; d++)
+            {
+                fa[d] += fi[d];
+                fb[d] += fi[3 + d];
+            }
+            if (do_vir && h->shift_idx[p] != FEP_CENTRAL_SHIFT)
+            {
+                for (int d = 0; d < 3; d++)
+                {
+                    fshift[3 * h->shift_idx[p] + d] += fi[d];
+                    fshift[3 * FEP_CENTRAL_SHIFT + d] -= fi[d];
+                }
+            }
+        }
+    }
+    if (do_e)
+    {
+        for (int g = 0; g < h->ngrp; g++)
+        {
+            Vc14[g] += h->vc[g];
+            Vv14[g] += h->vv[g];
+        }
+    }
+    dvdl[0] += dv[0];
+    dvdl[1] += dv[1];
     return FEPB200_OK;
 }
 

@@ -80,6 +80,13 @@ SYMBOLS = {
     "fepb200_last_launch_ms": (ctypes.c_int, [_VP, _FP]),
     "fepb200_set_profiling": (ctypes.c_int, [_VP, ctypes.c_int]),
     "fepb200_kernel_ms": (ctypes.c_int, [_VP, _FP]),
+    "fepb200_pairs14_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int]),
+    "fepb200_pairs14_destroy": (ctypes.c_int, [_VP]),
+    "fepb200_pairs14_last_error": (ctypes.c_char_p, [_VP]),
+    "fepb200_pairs14_set_params": (ctypes.c_int, [_VP, ctypes.POINTER(CParams), ctypes.c_float]),
+    "fepb200_pairs14_set_pairs": (ctypes.c_int, [_VP, ctypes.c_int, _FP, _FP, ctypes.c_int, _IP, ctypes.c_int, _FP, _FP,
+                                                 _FP, _FP, _IP, ctypes.c_int]),
+    "fepb200_pairs14_compute": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, ctypes.c_int, _FP, _FP, _DP, _DP, _DP]),
 }  # fmt: skip
 
 _lib = None

@@ -247,6 +247,32 @@ int       fepb200_last_launch_ms(fepb200_ctx* ctx, float* ms);
 int fepb200_set_profiling(fepb200_ctx* ctx, int on);
 int fepb200_kernel_ms(fepb200_ctx* ctx, float* ms);
 
+/* ---- perturbed 1-4 pair interactions (the step next to the path) -----------
+ * Replaces the perturbed (bFreeEnergy) branch of do_pairs(F_LJ14, ...)
+ * (src/gromacs/listed_forces/pairs.cpp:516-835, free_energy_evaluate_single :170-515) and the
+ * fork's pairs_fep_gpu (listed_forces/listed_forces_gpu_internal.cu:1365-1500): plain Coulomb
+ * (scaled by fudgeQQ) and plain LJ with the Beutler or Gapsys soft-core, no cut-off.
+ * Only PERTURBED pairs belong here; the others stay with the reference's tabulated evaluation.
+ * The pairs run through the same sm_100a kernels as the non-bonded perturbed pairs. */
+typedef struct fepb200_pairs14 fepb200_pairs14;
+int         fepb200_pairs14_create(fepb200_pairs14** h, int device_ordinal);
+int         fepb200_pairs14_destroy(fepb200_pairs14* h);
+const char* fepb200_pairs14_last_error(const fepb200_pairs14* h);
+/* ic: epsfac, rcoulomb (only the Gapsys linearisation point looks at it) and the
+ * SoftCoreParameters fields are used; fudgeQQ = fr->fudgeQQ (pairs.cpp:624). */
+int fepb200_pairs14_set_params(fepb200_pairs14* h, const fepb200_params* ic, float fudgeQQ);
+/* iatoms: int[3*npairs] = {1-4 type, ai, aj} (the t_iatom layout of the reference);
+ * c6A/c12A/c6B/c12B: t_iparams::lj14 per 1-4 type; gid: energy-group pair per pair (may be NULL). */
+int fepb200_pairs14_set_pairs(fepb200_pairs14* h, int natoms, const float* chargeA, const float* chargeB, int npairs,
+                              const int* iatoms, int ntypes, const float* c6A, const float* c12A, const float* c6B,
+                              const float* c12B, const int* gid, int nenergrp_pairs);
+/* x rvec[natoms]; box_diag float[3] (rectangular box); pbc_type 0 = none (molecules whole),
+ * 1 = xyz, 2 = xy (pbc_dx_aiuc, pbcutil/pbc.cpp:825-851); flags: FEPB200_DO_FORCE,
+ * _SHIFTFORCE, _POTENTIAL.  Outputs are accumulated: f rvec[natoms], fshift rvec[45],
+ * Vc14/Vv14[G] (Coulomb-14 / LJ-14 energy terms), dvdl[2] (coul, vdw). */
+int fepb200_pairs14_compute(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, const float* lambda,
+                            int flags, float* f, float* fshift, double* Vc14, double* Vv14, double* dvdl);
+
 #ifdef __cplusplus
 }
 #endif

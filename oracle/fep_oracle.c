@@ -752,3 +752,206 @@ int fep_oracle_dispatch(const fep_oracle_params* p, int use_simd, int nthreads, 
     free(tdv);
     return 0;
 }
+
+/* ============================================================================================
+ * Perturbed 1-4 pair interactions: restatement of
+ *   listed_forces/pairs.cpp:170-515  free_energy_evaluate_single<softcoreType>
+ *   listed_forces/pairs.cpp:516-835  do_pairs_general, perturbed (bFreeEnergy) branch, F_LJ14
+ *   pbcutil/pbc.cpp:825-851          pbc_dx_aiuc, rectangular boxes
+ * The reference evaluates plain Coulomb and r^-6 / r^-12 through cubic-spline tables
+ * (fr->pairsTable, made by make_tables(..., GMX_MAKETABLES_14ONLY)); here they are evaluated
+ * analytically.  The reference's own test of this function accepts 1e-7 (double) / 1e-5 (float)
+ * because of the tables; tests/test_oracle_pairs14.py pins this restatement to the golden vectors
+ * of that test (listed_forces/tests/refdata/14Interaction_ListedForcesPairsTest_Ifunc_{0,1,2}.xml).
+ * ========================================================================================== */
+int fep_oracle_pairs14(const fep_oracle_params* p, double fudgeQQ, int npairs, const int* iatoms, const double* c6A,
+                       const double* c12A, const double* c6B, const double* c12B, const double* x, const double* qA,
+                       const double* qB, const double* box_diag, int pbc_type /* 0 none, 1 xyz, 2 xy */,
+                       const int* gid, double lam_c, double lam_v, double* f, double* fshift, double* Vc, double* Vv,
+                       double* dvdl /*[2]*/)
+{
+    int ksc;
+    if (p->softcoreType == SC_BEUTLER)
+    {
+        ksc = (p->alphaCoulomb == 0 && p->alphaVdw == 0) ? KSC_NONE : KSC_BEUTLER; /* :721-762 */
+    }
+    else
+    {
+        ksc = (p->gapsysScaleCoul == 0 && p->gapsysScaleVdW == 0) ? KSC_NONE : KSC_GAPSYS;
+    }
+    /* :575-601 */
+    const double LFC[2] = { 1.0 - lam_c, lam_c }, LFV[2] = { 1.0 - lam_v, lam_v }, DLF[2] = { -1.0, 1.0 };
+    double       lfac_coul[2], lfac_vdw[2], dlfac_coul[2], dlfac_vdw[2];
+    for (int i = 0; i < 2; i++)
+    {
+        const int p2  = p->lambdaPower == 2;
+        lfac_coul[i]  = p2 ? (1 - LFC[i]) * (1 - LFC[i]) : (1 - LFC[i]);
+        dlfac_coul[i] = DLF[i] * p->lambdaPower / 6.0 * (p2 ? (1 - LFC[i]) : 1);
+        lfac_vdw[i]   = p2 ? (1 - LFV[i]) * (1 - LFV[i]) : (1 - LFV[i]);
+        dlfac_vdw[i]  = DLF[i] * p->lambdaPower / 6.0 * (p2 ? (1 - LFV[i]) : 1);
+    }
+    for (int n = 0; n < npairs; n++)
+    {
+        const int itype = iatoms[3 * n], ai = iatoms[3 * n + 1], aj = iatoms[3 * n + 2];
+        double    dx[3];
+        int       ishift[3] = { 0, 0, 0 };
+        for (int d = 0; d < 3; d++)
+        {
+            dx[d] = x[3 * ai + d] - x[3 * aj + d];
+            if (pbc_type == 1 || (pbc_type == 2 && d < 2))
+            {
+                const double hbox = 0.5 * box_diag[d];
+                if (dx[d] > hbox)
+                {
+                    dx[d] -= box_diag[d];
+                    ishift[d]--;
+                }
+                else if (dx[d] <= -hbox)
+                {
+                    dx[d] += box_diag[d];
+                    ishift[d]++;
+                }
+            }
+        }
+        const int    is = 5 * (3 * (ishift[2] + 1) + (ishift[1] + 1)) + (ishift[0] + 2);
+        const double r2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+        const double qq[2]  = { qA[ai] * qA[aj] * p->epsfac * fudgeQQ, qB[ai] * qB[aj] * p->epsfac * fudgeQQ };
+        const double c6[2]  = { 6.0 * c6A[itype], 6.0 * c6B[itype] };
+        const double c12[2] = { 12.0 * c12A[itype], 12.0 * c12B[itype] };
+        const double rpm2 = r2 * r2, rp = rpm2 * r2, r = sqrt(r2);
+        double       sigma6[2], gsig6[2];
+        for (int i = 0; i < 2; i++)
+        {
+            if (c6[i] > 0 && c12[i] > 0)
+            {
+                sigma6[i] = 0.5 * c12[i] / c6[i];
+                gsig6[i]  = sigma6[i];
+                if (sigma6[i] < p->sigma6Minimum)
+                {
+                    sigma6[i] = p->sigma6Minimum;
+                }
+            }
+            else
+            {
+                sigma6[i] = p->sigma6WithInvalidSigma;
+                gsig6[i]  = p->gapsysSigma6VdW;
+            }
+        }
+        const int    hard = (c12[0] > 0 && c12[1] > 0);
+        const double a_c = hard ? 0 : p->alphaCoulomb, a_v = hard ? 0 : p->alphaVdw;
+        const double g_c = hard ? 0 : p->gapsysScaleCoul, g_v = hard ? 0 : p->gapsysScaleVdW;
+        double       fe[2] = { 0, 0 }, fv[2] = { 0, 0 }, ve[2] = { 0, 0 }, vv[2] = { 0, 0 }, de[2] = { 0, 0 },
+               dv[2] = { 0, 0 };
+        for (int i = 0; i < 2; i++)
+        {
+            if (!(qq[i] != 0 || c6[i] != 0 || c12[i] != 0))
+            {
+                continue;
+            }
+            double rpinv, r_coul, r_vdw, rQ = 0, rLJ = 0, scaleDvdl = 1;
+            if (ksc == KSC_BEUTLER)
+            {
+                rpinv  = 1.0 / (a_c * lfac_coul[i] * sigma6[i] + rp);
+                r_coul = pow(rpinv, -1.0 / 6.0);
+            }
+            else
+            {
+                rpinv  = 1.0 / rp;
+                r_coul = r;
+            }
+            if (ksc == KSC_GAPSYS)
+            {
+                if (p->epsfac != 0 && LFC[i] < 1)
+                {
+                    rQ = pow(1.0 - LFC[i], 1.0 / 6.0) * (1.0 + fabs(qq[i] / p->epsfac)) * g_c;
+                }
+                if (rQ > p->rcoulomb)
+                {
+                    rQ        = p->rcoulomb;
+                    scaleDvdl = 0;
+                }
+            }
+            if (ksc == KSC_GAPSYS && r < rQ)
+            {
+                const double ri = 1.0 / rQ, cst = qq[i] * ri, lin = cst * r * ri, quad = lin * r * ri;
+                fe[i] = (-2 * quad + 3 * lin) * rpinv;
+                ve[i] = quad - 3 * (lin - cst);
+                de[i] += scaleDvdl * DLF[i] * 0.5 * (LFC[i] / (1 - LFC[i])) * (quad - 2 * lin + cst);
+            }
+            else
+            {
+                ve[i] = qq[i] / r_coul;
+                fe[i] = qq[i] / r_coul * rpinv;
+            }
+            if (ksc == KSC_BEUTLER)
+            {
+                rpinv = 1.0 / (a_v * lfac_vdw[i] * sigma6[i] + rp);
+                r_vdw = pow(rpinv, -1.0 / 6.0);
+            }
+            else
+            {
+                rpinv = 1.0 / rp;
+                r_vdw = r;
+            }
+            if (ksc == KSC_GAPSYS && LFV[i] < 1)
+            {
+                rLJ = pow(26.0 / 7.0 * gsig6[i] * (1.0 - LFV[i]), 1.0 / 6.0) * g_v;
+            }
+            if (ksc == KSC_GAPSYS && r < rLJ)
+            {
+                const double c6s = c6[i] / 6.0, c12s = c12[i] / 12.0, ri = 1.0 / rLJ;
+                double       ri6 = ri * ri * ri;
+                ri6 *= ri6;
+                const double ri7 = ri6 * ri, ri8 = ri7 * ri;
+                const double t14 = c12s * ri7 * ri7 * r2, t13 = c12s * ri7 * ri6 * r, t12 = c12s * ri6 * ri6;
+                const double t8 = ri8 * c6s * r2, t7 = ri7 * c6s * r, t6 = ri6 * c6s;
+                const double quad = 156 * t14 - 42 * t8, lin = 168 * t13 - 48 * t7, cst = 91 * t12 - 28 * t6;
+                fv[i] = (-quad + lin) * rpinv;
+                vv[i] = 0.5 * quad - lin + cst;
+                dv[i] += DLF[i] * 28 * (LFV[i] / (1.0 - LFV[i])) * ((6.5 * t14 - t8) - (13 * t13 - 2 * t7) + (6.5 * t12 - t6));
+            }
+            else
+            {
+                const double ri6 = 1.0 / (r_vdw * r_vdw * r_vdw * r_vdw * r_vdw * r_vdw);
+                const double v6 = c6[i] * ri6, v12 = c12[i] * ri6 * ri6;
+                vv[i] = v12 / 12.0 - v6 / 6.0;
+                fv[i] = (v12 - v6) * rpinv;
+            }
+        }
+        double velec = 0, vvdw = 0, fscal = 0, dc = 0, dvv = 0;
+        for (int i = 0; i < 2; i++)
+        {
+            velec += LFC[i] * ve[i];
+            vvdw += LFV[i] * vv[i];
+            fscal += (LFC[i] * fe[i] + LFV[i] * fv[i]) * rpm2;
+            if (ksc == KSC_GAPSYS)
+            {
+                dc += de[i];
+                dvv += dv[i];
+            }
+            dc += ve[i] * DLF[i];
+            dvv += vv[i] * DLF[i];
+            if (ksc == KSC_BEUTLER)
+            {
+                dc += LFC[i] * a_c * dlfac_coul[i] * fe[i] * sigma6[i];
+                dvv += LFV[i] * a_v * dlfac_vdw[i] * fv[i] * sigma6[i];
+            }
+        }
+        dvdl[0] += dc;
+        dvdl[1] += dvv;
+        Vc[gid[n]] += velec;
+        Vv[gid[n]] += vvdw;
+        for (int d = 0; d < 3; d++)
+        {
+            const double t = fscal * dx[d];
+            f[3 * ai + d] += t;
+            f[3 * aj + d] -= t;
+            if (fshift && is != 22)
+            {
+                fshift[3 * is + d] += t;
+                fshift[3 * 22 + d] -= t;
+            }
+        }
+    }
+    return 0;
+}

@@ -227,3 +227,29 @@ def run_best(problem, flags, **kw):
         return run_ref(problem, flags, precision="dp", **kw)
     kw.pop("use_simd", None)
     return run_port(problem, flags, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# perturbed 1-4 pairs (oracle/fep_oracle.c: fep_oracle_pairs14)
+# ---------------------------------------------------------------------------------------------
+def run_pairs14(problem, compute_virial=True):
+    """Double-precision restatement of do_pairs(F_LJ14) for perturbed pairs; returns f [N,3],
+    fshift [45,3], Vc [G] (Coulomb-14), Vv [G] (LJ-14), dvdl [2]."""
+    lib = _load_port()
+    fn = lib.fep_oracle_pairs14
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.POINTER(CParamsD), ctypes.c_double, ctypes.c_int, _IP, _DP, _DP, _DP, _DP, _DP, _DP, _DP, _DP,
+                   ctypes.c_int, _IP, ctypes.c_double, ctypes.c_double, _DP, _DP, _DP, _DP, _DP]
+    p = problem
+    out = dict(f=np.zeros((p.natoms, 3)), fshift=np.zeros((45, 3)), Vc=np.zeros(p.nenergrp_pairs),
+               Vv=np.zeros(p.nenergrp_pairs), dvdl=np.zeros(2))
+    cp = _params_d(p.params)
+    ia, gid = _i(p.iatoms), _i(p.gid)
+    arrs = [_d(a) for a in (p.c6A, p.c12A, p.c6B, p.c12B, p.x, p.qA, p.qB, p.box_diag)]
+    lam = _d(p.lambda_)
+    rc = fn(ctypes.byref(cp), float(p.fudgeQQ), p.npairs, _ptr_i(ia), *[_ptr_d(a) for a in arrs], int(p.pbc_type),
+            _ptr_i(gid), float(lam[2]), float(lam[3]), _ptr_d(out["f"]),
+            _ptr_d(out["fshift"]) if compute_virial else None, _ptr_d(out["Vc"]), _ptr_d(out["Vv"]), _ptr_d(out["dvdl"]))
+    if rc != 0:
+        raise RuntimeError(f"pairs14 oracle failed with code {rc}")
+    return out
