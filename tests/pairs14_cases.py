@@ -41,20 +41,30 @@ def kat_pairs14(case: dict, dtype=np.float64) -> Pairs14Problem:
         box_diag=[1.0, 1.0, 1.0], pbc_type=PBC[case["pbc"]], lambda_=lam, real_dtype=dtype)
 
 
-def random_pairs14(seed: int, softcore: str, *, natoms=200, npairs=300, ntypes=12, n_groups=2, lam_c=0.35, lam_v=0.6,
+def random_pairs14(seed: int, softcore: str, *, natoms=600, npairs=300, ntypes=12, n_groups=2, lam_c=0.35, lam_v=0.6,
                    sc_power=1, sc_coul=True, pbc_type=PBC_XYZ, dtype=np.float32) -> Pairs14Problem:
     rng = np.random.default_rng(seed)
     box = np.array([2.0, 2.3, 1.9])
     x = rng.uniform(0, 1, size=(natoms, 3)) * box
     ai = rng.integers(0, natoms, size=npairs)
     aj = (ai + rng.integers(1, natoms, size=npairs)) % natoms
-    # 1-4 partners sit 0.25 .. 0.4 nm apart (a few much closer, to exercise the soft core), across the box too
+    # 1-4 partners sit 0.25 .. 0.4 nm apart (a few at 0.12 .. 0.2 nm, inside the soft core), across the
+    # box too.  Every atom is the j atom of at most one pair, so that placing it does not move an
+    # earlier pair's partner to an arbitrary (possibly overlapping) distance.
+    aj = rng.permutation(natoms)[:npairs] if npairs <= natoms else aj
+    ai = np.where(ai == aj, (ai + 1) % natoms, ai)
     d = rng.normal(size=(npairs, 3))
     d *= (rng.uniform(0.25, 0.4, size=npairs) / np.linalg.norm(d, axis=1))[:, None]
     close = rng.random(npairs) < 0.1
-    d[close] *= 0.2
+    d[close] *= 0.5
+    x0 = x.copy()
     for k in range(npairs):
-        x[aj[k]] = np.mod(x[ai[k]] + d[k], box) if pbc_type != PBC_NONE else x[ai[k]] + d[k]
+        x[aj[k]] = np.mod(x0[ai[k]] + d[k], box) if pbc_type != PBC_NONE else x0[ai[k]] + d[k]
+    moved = np.zeros(natoms, bool)
+    moved[aj] = True
+    keep = ~moved[ai]  # pairs whose i atom kept its original position have exactly the intended distance
+    ai, aj = ai[keep], aj[keep]
+    npairs = int(keep.sum())
     sig, eps = rng.uniform(0.25, 0.36, size=ntypes), rng.uniform(0.2, 1.0, size=ntypes)
     c6a, c12a = 4 * eps * sig**6, 4 * eps * sig**12
     c6b, c12b = c6a.copy(), c12a.copy()
