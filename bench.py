@@ -126,8 +126,6 @@ def _config(problem, name, world, extra=None):
                passes_per_step=1 + problem.n_foreign + 1,
                flags="FORCE|SHIFTFORCE|POTENTIAL|FOREIGNLAMBDA",
                parallelism=f"i-entry shards x{world}", l2="flushed between timed steps (512 MiB write)")
-    if extra is None and world > 1:
-        extra = {}
     if extra:
         cfg.update(extra)
     return cfg

@@ -58,6 +58,7 @@ class ShardedFep:
         self.ctx.set_problem(problem, rank=rank, nranks=world)
         self.f32, self.f64 = result_tensors(self.ctx)
         self.reduction = "none"
+        self._p2p_error = None  # why symmetric memory was not used, if it was asked for
         self._step = 0
         if world > 1:
             want = reduction or os.environ.get("FEPB200_REDUCTION", "p2p")

@@ -374,6 +374,37 @@ def test_device_resident_entry_points_agree_with_compute(ctx):
     assert np.array_equal(f64[lay.off_dvdl : lay.off_dvdl + 2].cpu().numpy(), want["dvdl"])
 
 
+def test_peer_reduce_entry_points_with_one_rank(ctx):
+    """fepb200_publish_result / _set_partial_result_block / _reduce_peers on a single GPU: with one
+    rank the 'sum over ranks' of the published block must give back the same result (the N > 1
+    behaviour is covered by tests/test_multi_gpu.py)."""
+    import torch
+
+    prob = make_system(SMALL["C2"])
+    ctx.set_problem(prob)
+    want = ctx.compute(prob.x, prob.shiftvec, ALL)
+    nbytes = ctx.result_block_bytes()
+    assert nbytes == 8 * ((ctx.layout().f64_words + 1) // 2 * 2) + 4 * ctx.layout().f32_words
+    slot = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+    # (a) publish with a copy, then reduce
+    ctx.upload_x(prob.x, prob.shiftvec)
+    ctx.launch(ALL)
+    ctx.publish_result(slot.data_ptr())
+    ctx.reduce_peers([slot.data_ptr()])
+    got = ctx.download(ALL)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    # (b) the epilogue writes straight into the slot
+    slot.zero_()
+    ctx.set_partial_result_block(slot.data_ptr())
+    ctx.launch(ALL)
+    ctx.reduce_peers([slot.data_ptr()])
+    ctx.set_partial_result_block(None)
+    got = ctx.download(ALL)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+
+
 def test_lambda_update_without_new_list(ctx):
     prm = P.make_params(coulombtype="pme", softcore="beutler")
     prob = random_problem(21, prm, natoms=200, nri=50, n_foreign=3, frac_overlap=0.0)
