@@ -28,6 +28,21 @@
 #include "../../include/fepb200.h"
 #include "fep_types.h"
 
+/* fep_list_build.cu */
+extern "C" size_t fep_list_build_temp_bytes(int natoms, long long n_sort_max);
+extern "C" int    fep_list_build_touched(const int* d_iinr, int nri_total, const int* d_jjnr, long long nrj_total, int natoms,
+                                         int* d_mark, int* d_cscan, int* d_touched, void* d_tmp, size_t tmp_bytes,
+                                         cudaStream_t stream, long long* counter);
+extern "C" int    fep_list_build_pairs(const int* d_iinr, const int* d_gid, const int* d_shift, const int* d_jindex,
+                                       const int* d_jjnr, const int* d_excl, const int* d_cscan, int e0, int E, int j0, int P,
+                                       int4* d_ent4, int4* d_pair4, int* d_keys, int* d_head, int* d_hscan, void* d_tmp,
+                                       size_t tmp_bytes, cudaStream_t stream, long long* counter);
+extern "C" int    fep_list_build_slots(const int4* d_ent4, int4* d_pair4, const int* d_head, const int* d_hscan, int P, int H,
+                                       int nT, int ngrp, int* d_keys, int* d_keys_out, int* d_vals, int* d_vals_out,
+                                       int* d_seg_shift, int* d_seg_gid, int* d_warp_hbase, int4* d_seg_dst, int* d_atom_ptr,
+                                       int* d_key_ptr, void* d_tmp, size_t tmp_bytes, cudaStream_t stream,
+                                       long long* counter);
+
 namespace
 {
 
@@ -196,6 +211,10 @@ struct fepb200_ctx
     DeviceArray<float2> d_ev2;
     DeviceArray<double> d_cta_part, d_for_part, d_job_part;
     DeviceArray<unsigned int> d_counter;
+    /* raw list + scratch of the device-side list build (fep_list_build.cu) */
+    DeviceArray<int> d_raw_iinr, d_raw_gid, d_raw_shift, d_raw_jindex, d_raw_jjnr, d_raw_excl, d_mark, d_cscan, d_keys,
+            d_keys_out, d_vals, d_vals_out, d_head, d_hscan, d_seg_shift, d_seg_gid, d_key_ptr;
+    DeviceArray<unsigned char> d_cub_tmp;
     DeviceArray<unsigned char> d_step_in; /* [DynHead | pos4[nT]] */
     DeviceArray<unsigned char> d_result;  /* [f64 block | f32 block] */
     PinnedArray<unsigned char> h_step_in, h_result;
@@ -500,6 +519,164 @@ int check_ready(fepb200_ctx* c)
 
 } // namespace
 
+/* Reduction jobs of the epilogue from the prefix arrays of the shift-sorted and gid-sorted
+ * segment orders: chunks of at most FEP_RED_CHUNK elements per key, shift keys first. */
+static void build_jobs(const int* shift_ptr /*[46]*/, const int* gid_ptr /*[G+1]*/, int ngrp, std::vector<RedJob>* jobs,
+                       std::vector<int>* key_job_ptr, int* n_shift_jobs)
+{
+    jobs->clear();
+    key_job_ptr->assign(FEP_NUM_SHIFT + ngrp + 1, 0);
+    for (int kind = 0; kind < 2; kind++)
+    {
+        const int  nkeys = kind == 0 ? FEP_NUM_SHIFT : ngrp;
+        const int* ptr   = kind == 0 ? shift_ptr : gid_ptr;
+        for (int k = 0; k < nkeys; k++)
+        {
+            (*key_job_ptr)[(kind == 0 ? 0 : FEP_NUM_SHIFT) + k] = (int)jobs->size();
+            for (int b = ptr[k]; b < ptr[k + 1]; b += FEP_RED_CHUNK)
+            {
+                RedJob j;
+                j.begin = b;
+                j.end   = std::min(ptr[k + 1], b + FEP_RED_CHUNK);
+                j.key   = k;
+                j.kind  = kind;
+                jobs->push_back(j);
+            }
+        }
+        if (kind == 0)
+        {
+            *n_shift_jobs = (int)jobs->size();
+        }
+    }
+    (*key_job_ptr)[FEP_NUM_SHIFT + ngrp] = (int)jobs->size();
+}
+
+/* The device-side builder of the list layout (fep_list_build.cu): raw list to the GPU, then
+ * kernels, scans and stable sorts; only two scalars (nT, H), the touched-atom list and 47 + G
+ * counters come back to the host. */
+static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int* gid, const int* shift,
+                             const int* jindex, const int* jjnr, const int* excl_fep, long long nrj_total, int ngrp, int e0,
+                             int E, int j0, int P, int* nT_out, int* H_out, std::vector<RedJob>* jobs,
+                             std::vector<int>* key_job_ptr)
+{
+    cudaStream_t st = c->stream;
+    /* raw list */
+    CU_CHECK(c, c->d_raw_iinr.reserve(std::max(nri, 1)));
+    CU_CHECK(c, c->d_raw_gid.reserve(std::max(nri, 1)));
+    CU_CHECK(c, c->d_raw_shift.reserve(std::max(nri, 1)));
+    CU_CHECK(c, c->d_raw_jindex.reserve((size_t)nri + 1));
+    CU_CHECK(c, c->d_raw_jjnr.reserve(std::max<long long>(nrj_total, 1)));
+    if (nri > 0)
+    {
+        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_iinr.ptr, iinr, sizeof(int) * nri, cudaMemcpyHostToDevice, st));
+        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_gid.ptr, gid, sizeof(int) * nri, cudaMemcpyHostToDevice, st));
+        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_shift.ptr, shift, sizeof(int) * nri, cudaMemcpyHostToDevice, st));
+        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_jindex.ptr, jindex, sizeof(int) * ((size_t)nri + 1), cudaMemcpyHostToDevice, st));
+    }
+    else
+    {
+        CU_CHECK(c, cudaMemsetAsync(c->d_raw_jindex.ptr, 0, sizeof(int), st));
+    }
+    if (nrj_total > 0)
+    {
+        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_jjnr.ptr, jjnr, sizeof(int) * nrj_total, cudaMemcpyHostToDevice, st));
+    }
+    const int* d_excl = nullptr;
+    if (excl_fep && nrj_total > 0)
+    {
+        CU_CHECK(c, c->d_raw_excl.reserve(nrj_total));
+        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_excl.ptr, excl_fep, sizeof(int) * nrj_total, cudaMemcpyHostToDevice, st));
+        d_excl = c->d_raw_excl.ptr;
+    }
+    /* scratch */
+    const int       n_warps = (P + 31) / 32;
+    const long long h_max   = (long long)E + n_warps; /* a segment starts at an entry start or a warp start */
+    const long long n_max   = P + h_max;
+    if (n_max >= (1LL << 31) - 64)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "list too large");
+    }
+    const size_t tmp_bytes = fep_list_build_temp_bytes(c->natoms, n_max);
+    CU_CHECK(c, c->d_cub_tmp.reserve(tmp_bytes));
+    CU_CHECK(c, c->d_mark.reserve((size_t)c->natoms + 1));
+    CU_CHECK(c, c->d_cscan.reserve((size_t)c->natoms + 1));
+    CU_CHECK(c, c->d_touched.reserve(std::max(c->natoms, 1)));
+    int err = fep_list_build_touched(c->d_raw_iinr.ptr, nri, c->d_raw_jjnr.ptr, nrj_total, c->natoms, c->d_mark.ptr,
+                                     c->d_cscan.ptr, c->d_touched.ptr, c->d_cub_tmp.ptr, tmp_bytes, st, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "list build (touched) failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    /* pair records and segment heads do not need nT on the host: queue them before the first sync */
+    CU_CHECK(c, c->d_ent4.reserve(std::max(E, 1)));
+    CU_CHECK(c, c->d_pair4.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_keys.reserve(std::max<long long>(n_max, 1)));
+    CU_CHECK(c, c->d_head.reserve((size_t)P + 1));
+    CU_CHECK(c, c->d_hscan.reserve((size_t)P + 1));
+    err = fep_list_build_pairs(c->d_raw_iinr.ptr, c->d_raw_gid.ptr, c->d_raw_shift.ptr, c->d_raw_jindex.ptr,
+                               c->d_raw_jjnr.ptr, d_excl, c->d_cscan.ptr, e0, E, j0, P, c->d_ent4.ptr, c->d_pair4.ptr,
+                               c->d_keys.ptr, c->d_head.ptr, c->d_hscan.ptr, c->d_cub_tmp.ptr, tmp_bytes, st, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "list build (pairs) failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    int nT = 0, H = 0;
+    CU_CHECK(c, cudaMemcpyAsync(&nT, c->d_cscan.ptr + c->natoms, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaMemcpyAsync(&H, c->d_hscan.ptr + P, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaStreamSynchronize(st));
+    if (nT >= FEP_MAX_TOUCHED)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d distinct atoms in one FEP list", FEP_MAX_TOUCHED);
+    }
+    const int n = P + H;
+    CU_CHECK(c, c->d_keys_out.reserve(std::max(n, 1)));
+    CU_CHECK(c, c->d_vals.reserve(std::max(n, 1)));
+    CU_CHECK(c, c->d_vals_out.reserve(std::max(n, 1)));
+    CU_CHECK(c, c->d_seg_shift.reserve(std::max(H, 1)));
+    CU_CHECK(c, c->d_seg_gid.reserve(std::max(H, 1)));
+    CU_CHECK(c, c->d_warp_hbase.reserve(std::max(n_warps, 1)));
+    CU_CHECK(c, c->d_seg_dst.reserve(std::max(H, 1)));
+    CU_CHECK(c, c->d_atom_ptr.reserve((size_t)nT + 1));
+    CU_CHECK(c, c->d_key_ptr.reserve(FEP_NUM_SHIFT + 1 + ngrp + 1));
+    err = fep_list_build_slots(c->d_ent4.ptr, c->d_pair4.ptr, c->d_head.ptr, c->d_hscan.ptr, P, H, nT, ngrp, c->d_keys.ptr,
+                               c->d_keys_out.ptr, c->d_vals.ptr, c->d_vals_out.ptr, c->d_seg_shift.ptr, c->d_seg_gid.ptr,
+                               c->d_warp_hbase.ptr, c->d_seg_dst.ptr, c->d_atom_ptr.ptr, c->d_key_ptr.ptr, c->d_cub_tmp.ptr,
+                               tmp_bytes, st, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "list build (slots) failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    /* back to the host: the touched atoms (for the coordinate gather / force scatter of every
+     * step) and the per-key counts (for the reduction jobs) */
+    std::vector<int> key_ptr(FEP_NUM_SHIFT + 1 + ngrp + 1, 0);
+    c->touched.resize(nT);
+    if (nT > 0)
+    {
+        CU_CHECK(c, cudaMemcpyAsync(c->touched.data(), c->d_touched.ptr, sizeof(int) * nT, cudaMemcpyDeviceToHost, st));
+    }
+    CU_CHECK(c, cudaMemcpyAsync(key_ptr.data(), c->d_key_ptr.ptr, sizeof(int) * key_ptr.size(), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaStreamSynchronize(st));
+    build_jobs(key_ptr.data(), key_ptr.data() + FEP_NUM_SHIFT + 1, ngrp, jobs, key_job_ptr, &c->ka.n_shift_jobs);
+    /* per-atom parameters in compact order (the per-atom arrays of set_atoms live on the host) */
+    std::vector<float4>& par4 = c->w_par4;
+    par4.resize(nT);
+#pragma omp parallel for schedule(static) num_threads(host_threads(nT)) if (nT > 16384)
+    for (int k = 0; k < nT; k++)
+    {
+        const int a = c->touched[k];
+        par4[k]     = make_float4(c->qA[a], c->qB[a], int_bits_as_float(c->typeA[a]), int_bits_as_float(c->typeB[a]));
+    }
+    int rc;
+    if ((rc = to_device(c, c->d_red_jobs, *jobs)) || (rc = to_device(c, c->d_key_job_ptr, *key_job_ptr))
+        || (rc = to_device(c, c->d_par4, par4)))
+    {
+        return rc;
+    }
+    *nT_out = nT;
+    *H_out  = H;
+    return FEPB200_OK;
+}
+
 static bool create_copy_events(fepb200_ctx* c)
 {
     for (int i = 0; i < c_copy_chunks; i++)
@@ -596,6 +773,24 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_for_part.release();
     c->d_job_part.release();
     c->d_counter.release();
+    c->d_raw_iinr.release();
+    c->d_raw_gid.release();
+    c->d_raw_shift.release();
+    c->d_raw_jindex.release();
+    c->d_raw_jjnr.release();
+    c->d_raw_excl.release();
+    c->d_mark.release();
+    c->d_cscan.release();
+    c->d_keys.release();
+    c->d_keys_out.release();
+    c->d_vals.release();
+    c->d_vals_out.release();
+    c->d_head.release();
+    c->d_hscan.release();
+    c->d_seg_shift.release();
+    c->d_seg_gid.release();
+    c->d_key_ptr.release();
+    c->d_cub_tmp.release();
     c->d_step_in.release();
     c->d_result.release();
     c->h_step_in.release();
@@ -858,29 +1053,6 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     }
 
     lap("validate");
-    /* touched atoms of the FULL list (same numbering on every rank; mirrors the reduction mask
-     * of setReductionMaskFromFepPairlist, freeenergydispatch.cpp:74-89) */
-    c->compact_of.assign(c->natoms, -1);
-    for (int n = 0; n < nri; n++)
-    {
-        c->compact_of[iinr[n]] = 0;
-    }
-    for (long long k = 0; k < nrj_total; k++)
-    {
-        c->compact_of[jjnr[k]] = 0;
-    }
-    c->touched.clear();
-    for (int a = 0; a < c->natoms; a++)
-    {
-        if (c->compact_of[a] == 0)
-        {
-            c->compact_of[a] = (int)c->touched.size();
-            c->touched.push_back(a);
-        }
-    }
-    const int nT = (int)c->touched.size();
-
-    lap("touched atoms");
     /* this rank's contiguous range of i-entries, balanced by pair count */
     int e0 = 0, e1 = nri;
     if (nranks > 1)
@@ -908,166 +1080,210 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     const int j0 = E > 0 ? jindex[e0] : 0;
     const int P  = E > 0 ? jindex[e1] - j0 : 0;
 
-    if (nT >= FEP_MAX_TOUCHED)
-    {
-        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d distinct atoms in one FEP list", FEP_MAX_TOUCHED);
-    }
-    std::vector<int>&  pair_j = c->w_pair_j;
-    std::vector<int>&  pair_e = c->w_pair_e;
-    std::vector<int4>& ent4   = c->w_ent4;
-    std::vector<int4>& pair4  = c->w_pair4;
-    pair_j.resize(P);
-    pair_e.resize(P);
-    ent4.resize(E);
-    pair4.resize(P);
-    const int         nthr = std::min(8, std::max(1, omp_get_max_threads()));
-#pragma omp parallel for schedule(static) num_threads(nthr) if (P > 65536)
-    for (int n = 0; n < E; n++)
-    {
-        const int g = e0 + n;
-        ent4[n]     = make_int4(c->compact_of[iinr[g]], shift[g], gid[g], 0);
-        for (int k = jindex[g]; k < jindex[g + 1]; k++)
-        {
-            const bool excluded = excl_fep && excl_fep[k] == 0;
-            pair_j[k - j0]      = c->compact_of[jjnr[k]] | (excluded ? (int)0x80000000u : 0);
-            pair_e[k - j0]      = n;
-            pair4[k - j0]       = make_int4(pair_j[k - j0], ent4[n].x | (shift[g] << 24), n, 0);
-        }
-    }
 
-    lap("pair records");
-    /* segments: maximal runs of one i-entry inside one 32-pair warp */
-    const int        n_warps = (P + 31) / 32;
-    std::vector<int>& warp_hbase = c->w_warp_hbase;
-    std::vector<int>& seg_entry  = c->w_seg_entry;
-    warp_hbase.assign(std::max(n_warps, 1), 0);
-    seg_entry.clear();
-    seg_entry.reserve((size_t)E + n_warps);
-    for (int w = 0; w < n_warps; w++)
+    /* Two builders of the device layout with identical results: kernels + scans + stable sorts
+     * on the GPU (default), or loops on the host (FEPB200_SETLIST=host). */
+    bool device_build = true;
+    if (const char* env = std::getenv("FEPB200_SETLIST"))
     {
-        warp_hbase[w]  = (int)seg_entry.size();
-        const int last = std::min(P, 32 * w + 32);
-        for (int s = 32 * w; s < last; s++)
+        device_build = std::string(env) != "host";
+    }
+    int                 nT = 0, H = 0, rc = 0;
+    std::vector<RedJob> jobs;
+    std::vector<int>    key_job_ptr;
+    if (device_build)
+    {
+        rc = build_list_device(c, nri, iinr, gid, shift, jindex, jjnr, excl_fep, nrj_total, ngrp, e0, E, j0, P, &nT, &H,
+                               &jobs, &key_job_ptr);
+        if (rc != FEPB200_OK)
         {
-            if (s == 32 * w || pair_e[s] != pair_e[s - 1])
+            return rc;
+        }
+        lap("device build");
+    }
+    else
+    {
+        /* touched atoms of the FULL list (same numbering on every rank; mirrors the reduction mask
+         * of setReductionMaskFromFepPairlist, freeenergydispatch.cpp:74-89) */
+        c->compact_of.assign(c->natoms, -1);
+        for (int n = 0; n < nri; n++)
+        {
+            c->compact_of[iinr[n]] = 0;
+        }
+        for (long long k = 0; k < nrj_total; k++)
+        {
+            c->compact_of[jjnr[k]] = 0;
+        }
+        c->touched.clear();
+        for (int a = 0; a < c->natoms; a++)
+        {
+            if (c->compact_of[a] == 0)
             {
-                seg_entry.push_back(pair_e[s]);
+                c->compact_of[a] = (int)c->touched.size();
+                c->touched.push_back(a);
             }
         }
-    }
-    const int H = (int)seg_entry.size();
+        nT = (int)c->touched.size();
 
-    lap("segments");
-    /* Atom-sorted contribution buffer: atom k owns [atom_ptr[k], atom_ptr[k+1]); within a range
-     * the pair contributions (as j) come first in slot order, then the segments (as i). */
-    std::vector<int>&  atom_ptr = c->w_atom_ptr;
-    std::vector<int4>& seg_dst  = c->w_seg_dst;
-    atom_ptr.assign(nT + 1, 0);
-    seg_dst.resize(H);
-    for (int s = 0; s < P; s++)
-    {
-        atom_ptr[(pair_j[s] & 0x7fffffff) + 1]++;
-    }
-    for (int h = 0; h < H; h++)
-    {
-        atom_ptr[ent4[seg_entry[h]].x + 1]++;
-    }
-    for (int a = 0; a < nT; a++)
-    {
-        atom_ptr[a + 1] += atom_ptr[a];
-    }
-    {
-        std::vector<int>& fill = c->w_fill;
-        fill.assign(atom_ptr.begin(), atom_ptr.end() - 1);
+        if (nT >= FEP_MAX_TOUCHED)
+        {
+            return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d distinct atoms in one FEP list", FEP_MAX_TOUCHED);
+        }
+        std::vector<int>&  pair_j = c->w_pair_j;
+        std::vector<int>&  pair_e = c->w_pair_e;
+        std::vector<int4>& ent4   = c->w_ent4;
+        std::vector<int4>& pair4  = c->w_pair4;
+        pair_j.resize(P);
+        pair_e.resize(P);
+        ent4.resize(E);
+        pair4.resize(P);
+        const int         nthr = std::min(8, std::max(1, omp_get_max_threads()));
+    #pragma omp parallel for schedule(static) num_threads(nthr) if (P > 65536)
+        for (int n = 0; n < E; n++)
+        {
+            const int g = e0 + n;
+            ent4[n]     = make_int4(c->compact_of[iinr[g]], shift[g], gid[g], 0);
+            for (int k = jindex[g]; k < jindex[g + 1]; k++)
+            {
+                const bool excluded = excl_fep && excl_fep[k] == 0;
+                pair_j[k - j0]      = c->compact_of[jjnr[k]] | (excluded ? (int)0x80000000u : 0);
+                pair_e[k - j0]      = n;
+                pair4[k - j0]       = make_int4(pair_j[k - j0], ent4[n].x | (shift[g] << 24), n, 0);
+            }
+        }
+
+        lap("pair records");
+        /* segments: maximal runs of one i-entry inside one 32-pair warp */
+        const int        n_warps = (P + 31) / 32;
+        std::vector<int>& warp_hbase = c->w_warp_hbase;
+        std::vector<int>& seg_entry  = c->w_seg_entry;
+        warp_hbase.assign(std::max(n_warps, 1), 0);
+        seg_entry.clear();
+        seg_entry.reserve((size_t)E + n_warps);
+        for (int w = 0; w < n_warps; w++)
+        {
+            warp_hbase[w]  = (int)seg_entry.size();
+            const int last = std::min(P, 32 * w + 32);
+            for (int s = 32 * w; s < last; s++)
+            {
+                if (s == 32 * w || pair_e[s] != pair_e[s - 1])
+                {
+                    seg_entry.push_back(pair_e[s]);
+                }
+            }
+        }
+        H = (int)seg_entry.size();
+
+        lap("segments");
+        /* Atom-sorted contribution buffer: atom k owns [atom_ptr[k], atom_ptr[k+1]); within a range
+         * the pair contributions (as j) come first in slot order, then the segments (as i). */
+        std::vector<int>&  atom_ptr = c->w_atom_ptr;
+        std::vector<int4>& seg_dst  = c->w_seg_dst;
+        atom_ptr.assign(nT + 1, 0);
+        seg_dst.resize(H);
         for (int s = 0; s < P; s++)
         {
-            pair4[s].w = fill[pair_j[s] & 0x7fffffff]++; /* the record carries the pair's scatter slot */
+            atom_ptr[(pair_j[s] & 0x7fffffff) + 1]++;
         }
         for (int h = 0; h < H; h++)
         {
-            seg_dst[h] = make_int4(fill[ent4[seg_entry[h]].x]++, 0, 0, 0);
+            atom_ptr[ent4[seg_entry[h]].x + 1]++;
         }
-    }
+        for (int a = 0; a < nT; a++)
+        {
+            atom_ptr[a + 1] += atom_ptr[a];
+        }
+        {
+            std::vector<int>& fill = c->w_fill;
+            fill.assign(atom_ptr.begin(), atom_ptr.end() - 1);
+            for (int s = 0; s < P; s++)
+            {
+                pair4[s].w = fill[pair_j[s] & 0x7fffffff]++; /* the record carries the pair's scatter slot */
+            }
+            for (int h = 0; h < H; h++)
+            {
+                seg_dst[h] = make_int4(fill[ent4[seg_entry[h]].x]++, 0, 0, 0);
+            }
+        }
 
-    lap("atom-sorted slots");
-    /* segments sorted by shift vector (-> fshift_sorted) and by energy-group pair (-> ev2); the
-     * reduction jobs are chunks of those ranges */
-    std::vector<RedJob> jobs;
-    std::vector<int>    key_job_ptr(FEP_NUM_SHIFT + ngrp + 1, 0);
-    for (int kind = 0; kind < 2; kind++)
-    {
-        const int        nkeys = kind == 0 ? FEP_NUM_SHIFT : ngrp;
-        std::vector<int> cnt(nkeys + 1, 0);
-        for (int h = 0; h < H; h++)
+        lap("atom-sorted slots");
+        /* segments sorted by shift vector (-> fshift_sorted) and by energy-group pair (-> ev2); the
+         * reduction jobs are chunks of those ranges */
+        key_job_ptr.assign(FEP_NUM_SHIFT + ngrp + 1, 0);
+        for (int kind = 0; kind < 2; kind++)
         {
-            const int4 e = ent4[seg_entry[h]];
-            cnt[(kind == 0 ? e.y : e.z) + 1]++;
-        }
-        for (int k = 0; k < nkeys; k++)
-        {
-            cnt[k + 1] += cnt[k];
-        }
-        std::vector<int> fill(cnt.begin(), cnt.end() - 1);
-        for (int h = 0; h < H; h++)
-        {
-            const int4 e   = ent4[seg_entry[h]];
-            const int  pos = fill[kind == 0 ? e.y : e.z]++;
+            const int        nkeys = kind == 0 ? FEP_NUM_SHIFT : ngrp;
+            std::vector<int> cnt(nkeys + 1, 0);
+            for (int h = 0; h < H; h++)
+            {
+                const int4 e = ent4[seg_entry[h]];
+                cnt[(kind == 0 ? e.y : e.z) + 1]++;
+            }
+            for (int k = 0; k < nkeys; k++)
+            {
+                cnt[k + 1] += cnt[k];
+            }
+            std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+            for (int h = 0; h < H; h++)
+            {
+                const int4 e   = ent4[seg_entry[h]];
+                const int  pos = fill[kind == 0 ? e.y : e.z]++;
+                if (kind == 0)
+                {
+                    seg_dst[h].y = pos;
+                }
+                else
+                {
+                    seg_dst[h].z = pos;
+                }
+            }
+            for (int k = 0; k < nkeys; k++)
+            {
+                key_job_ptr[(kind == 0 ? 0 : FEP_NUM_SHIFT) + k] = (int)jobs.size();
+                for (int b = cnt[k]; b < cnt[k + 1]; b += FEP_RED_CHUNK)
+                {
+                    RedJob j;
+                    j.begin = b;
+                    j.end   = std::min(cnt[k + 1], b + FEP_RED_CHUNK);
+                    j.key   = k;
+                    j.kind  = kind;
+                    jobs.push_back(j);
+                }
+            }
             if (kind == 0)
             {
-                seg_dst[h].y = pos;
-            }
-            else
-            {
-                seg_dst[h].z = pos;
+                c->ka.n_shift_jobs = (int)jobs.size();
             }
         }
-        for (int k = 0; k < nkeys; k++)
-        {
-            key_job_ptr[(kind == 0 ? 0 : FEP_NUM_SHIFT) + k] = (int)jobs.size();
-            for (int b = cnt[k]; b < cnt[k + 1]; b += FEP_RED_CHUNK)
-            {
-                RedJob j;
-                j.begin = b;
-                j.end   = std::min(cnt[k + 1], b + FEP_RED_CHUNK);
-                j.key   = k;
-                j.kind  = kind;
-                jobs.push_back(j);
-            }
-        }
-        if (kind == 0)
-        {
-            c->ka.n_shift_jobs = (int)jobs.size();
-        }
-    }
-    key_job_ptr[FEP_NUM_SHIFT + ngrp] = (int)jobs.size();
+        key_job_ptr[FEP_NUM_SHIFT + ngrp] = (int)jobs.size();
 
-    lap("reduction jobs");
-    /* per-atom parameters in compact order */
-    std::vector<float4>& par4 = c->w_par4;
-    par4.resize(nT);
-    for (int k = 0; k < nT; k++)
-    {
-        const int a = c->touched[k];
-        par4[k]     = make_float4(c->qA[a], c->qB[a], int_bits_as_float(c->typeA[a]), int_bits_as_float(c->typeB[a]));
-    }
+        lap("reduction jobs");
+        /* per-atom parameters in compact order */
+        std::vector<float4>& par4 = c->w_par4;
+        par4.resize(nT);
+        for (int k = 0; k < nT; k++)
+        {
+            const int a = c->touched[k];
+            par4[k]     = make_float4(c->qA[a], c->qB[a], int_bits_as_float(c->typeA[a]), int_bits_as_float(c->typeB[a]));
+        }
 
-    lap("atom parameters");
-    int rc;
-    if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair4, pair4))
-        || (rc = to_device(c, c->d_ent4, ent4))
-        || (rc = to_device(c, c->d_warp_hbase, warp_hbase)) || (rc = to_device(c, c->d_atom_ptr, atom_ptr))
-        || (rc = to_device(c, c->d_red_jobs, jobs))
-        || (rc = to_device(c, c->d_seg_dst, seg_dst)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
-        || (rc = to_device(c, c->d_par4, par4)))
-    {
-        return rc;
+        lap("atom parameters");
+        if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair4, pair4))
+            || (rc = to_device(c, c->d_ent4, ent4))
+            || (rc = to_device(c, c->d_warp_hbase, warp_hbase)) || (rc = to_device(c, c->d_atom_ptr, atom_ptr))
+            || (rc = to_device(c, c->d_red_jobs, jobs))
+            || (rc = to_device(c, c->d_seg_dst, seg_dst)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
+            || (rc = to_device(c, c->d_par4, par4)))
+        {
+            return rc;
+        }
     }
     CU_CHECK(c, c->d_fsorted.reserve(std::max(P + H, 1)));
     CU_CHECK(c, c->d_fshift_sorted.reserve(std::max(H, 1)));
     CU_CHECK(c, c->d_ev2.reserve(std::max(H, 1)));
     CU_CHECK(c, c->d_job_part.reserve(4 * std::max<size_t>(jobs.size(), 1)));
     CU_CHECK(c, cudaStreamSynchronize(c->stream)); /* host vectors go out of scope */
-    lap("H2D copies");
+    lap("buffers");
 
     KernelArgs& k = c->ka;
     k.n_pairs     = P;

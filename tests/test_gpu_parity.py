@@ -311,6 +311,35 @@ def test_shards_partition_the_list_bit_exactly_and_sum_to_the_whole(nranks):
         assert np.allclose(total[k], whole[k], rtol=1e-6, atol=1e-6 * np.max(np.abs(whole[k])))
 
 
+@pytest.mark.parametrize("name", ["C4", "C3", "C1"])
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_device_and_host_list_builders_agree_bit_for_bit(name, nranks, monkeypatch):
+    """fepb200_set_list() builds the device layout with kernels, scans and stable sorts on the GPU
+    (default) or with loops on the host (FEPB200_SETLIST=host).  Both follow the same ordering
+    rules, so every result -- including the order of the floating-point additions -- is identical."""
+    from fepb200.lib import FepContext
+
+    prob = make_system(SMALL[name])
+    results = {}
+    for mode in ("device", "host"):
+        monkeypatch.setenv("FEPB200_SETLIST", mode)
+        outs = []
+        for r in range(nranks):
+            with FepContext(0) as c:
+                c.set_problem(prob, rank=r, nranks=nranks)
+                first, back = c.get_list()
+                lay = c.layout()
+                outs.append((first, back, (lay.ntouched, lay.nri, lay.nrj), c.touched_atoms().copy(),
+                             c.compute(prob.x, prob.shiftvec, ALL)))
+        results[mode] = outs
+    for (fa, la, sa, ta, oa), (fb, lb, sb, tb, ob) in zip(results["device"], results["host"]):
+        assert fa == fb and sa == sb
+        _assert_lists_equal(la, lb)
+        assert np.array_equal(ta, tb)
+        for k in oa:
+            assert np.array_equal(oa[k], ob[k]), k
+
+
 def test_empty_and_ragged_lists(ctx):
     from fepb200.problem import FepList
 
