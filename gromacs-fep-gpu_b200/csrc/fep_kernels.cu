@@ -436,24 +436,25 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
     }
     else
     {
-        /* eight lanes per touched atom; contributions are visited in ascending index order by
+        /* FEP_EPI_LANES lanes per touched atom; contributions are visited in ascending index order by
          * lane stride, then combined with a fixed xor tree: deterministic */
         b -= lay.scalar_blocks;
-        const int atom = b * (FEP_EPI_CTA / 8) + (tid >> 3);
-        const int sub  = tid & 7;
+        const int atom = b * (FEP_EPI_CTA / FEP_EPI_LANES) + (tid / FEP_EPI_LANES);
+        const int sub  = tid % FEP_EPI_LANES;
         float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
         if (atom < ka.n_touched)
         {
             const int k0 = __ldg(ka.atom_ptr + atom), k1 = __ldg(ka.atom_ptr + atom + 1);
-            /* the atom's contributions are contiguous in fsorted: eight lanes stream them, four
+            /* the atom's contributions are contiguous in fsorted: the lanes stream them, four
              * independent 16-byte loads per lane and trip (most atoms need a single trip) */
-            for (int k = k0 + sub; k < k1; k += 32)
+            for (int k = k0 + sub; k < k1; k += 4 * FEP_EPI_LANES)
             {
                 float4 t[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                 {
-                    t[u] = (k + 8 * u < k1) ? __ldcs(ka.fsorted + k + 8 * u) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    t[u] = (k + FEP_EPI_LANES * u < k1) ? __ldcs(ka.fsorted + k + FEP_EPI_LANES * u)
+                                                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             }
         }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1)
+        for (int o = FEP_EPI_LANES / 2; o > 0; o >>= 1)
         {
             fx += __shfl_xor_sync(FULL_MASK, fx, o);
             fy += __shfl_xor_sync(FULL_MASK, fy, o);
@@ -677,7 +678,7 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
         return (int)err;
     }
     EpilogueLayout lay;
-    lay.atom_blocks   = sf.force ? (ka.n_touched + FEP_EPI_CTA / 8 - 1) / (FEP_EPI_CTA / 8) : 0;
+    lay.atom_blocks   = sf.force ? (ka.n_touched + FEP_EPI_CTA / FEP_EPI_LANES - 1) / (FEP_EPI_CTA / FEP_EPI_LANES) : 0;
     /* jobs are ordered shift jobs first, then energy-group jobs */
     const int j0      = sf.shift ? 0 : ka.n_shift_jobs;
     const int j1      = sf.energy ? ka.n_red_jobs : ka.n_shift_jobs;

@@ -41,6 +41,7 @@
 #define FEP_LCHUNK 8       /* lambda points evaluated per thread per pair in the foreign kernel */
 #define FEP_RED_CHUNK 2048 /* segments per reduction job of the epilogue */
 #define FEP_EPI_CTA 256
+#define FEP_EPI_LANES 8 /* lanes per touched atom in the epilogue (32 contributions per trip; 4 lanes measured slower) */
 
 /* soft-core flavour actually evaluated (nb_free_energy.cpp:1324-1363) */
 enum { FEP_SC_NONE = 0, FEP_SC_BEUTLER = 1, FEP_SC_GAPSYS = 2 };
