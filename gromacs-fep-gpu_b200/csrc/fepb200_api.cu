@@ -162,6 +162,7 @@ struct fepb200_ctx
     std::string  description;
     long long    launches = 0;
     bool         timed    = false;
+    bool         staging_in_flight = false; /* an H2D copy out of h_step_in may still be running */
 
     /* constants */
     bool           have_params = false;
@@ -837,7 +838,8 @@ int fepb200_set_stream(fepb200_ctx* c, void* stream)
     }
     cudaSetDevice(c->device);
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
-    c->stream = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
+    c->staging_in_flight = false;
+    c->stream            = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
     return FEPB200_OK;
 }
 
@@ -976,18 +978,42 @@ int fepb200_set_atoms(fepb200_ctx* c, int natoms, const float* qA, const float* 
     {
         return fail(c, FEPB200_ERR_STATE, "fepb200_set_nbfp() must precede fepb200_set_atoms()");
     }
-    for (int a = 0; a < natoms; a++)
     {
-        if (typeA[a] < 0 || typeA[a] >= c->ntype || typeB[a] < 0 || typeB[a] >= c->ntype)
+        int       bad  = -1;
+        const int nthr = std::min(8, std::max(1, omp_get_max_threads()));
+#pragma omp parallel for schedule(static) reduction(max : bad) num_threads(nthr) if (natoms > 65536)
+        for (int a = 0; a < natoms; a++)
         {
-            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "atom %d has a type outside [0,%d)", a, c->ntype);
+            if (typeA[a] < 0 || typeA[a] >= c->ntype || typeB[a] < 0 || typeB[a] >= c->ntype)
+            {
+                bad = std::max(bad, a);
+            }
+        }
+        if (bad >= 0)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "atom %d has a type outside [0,%d)", bad, c->ntype);
+        }
+        c->natoms = natoms;
+        c->qA.resize(natoms);
+        c->qB.resize(natoms);
+        c->typeA.resize(natoms);
+        c->typeB.resize(natoms);
+        /* four arrays of natoms words: copied by four threads */
+        if (natoms > 0)
+        {
+#pragma omp parallel sections num_threads(std::min(4, nthr)) if (natoms > 65536)
+        {
+#pragma omp section
+            std::memcpy(c->qA.data(), qA, sizeof(float) * (size_t)natoms);
+#pragma omp section
+            std::memcpy(c->qB.data(), qB, sizeof(float) * (size_t)natoms);
+#pragma omp section
+            std::memcpy(c->typeA.data(), typeA, sizeof(int) * (size_t)natoms);
+#pragma omp section
+            std::memcpy(c->typeB.data(), typeB, sizeof(int) * (size_t)natoms);
+        }
         }
     }
-    c->natoms = natoms;
-    c->qA.assign(qA, qA + natoms);
-    c->qB.assign(qB, qB + natoms);
-    c->typeA.assign(typeA, typeA + natoms);
-    c->typeB.assign(typeB, typeB + natoms);
     c->have_list = false;
     return FEPB200_OK;
 }
@@ -1486,8 +1512,12 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
         return rc;
     }
     cudaSetDevice(c->device);
-    /* the previous H2D copy out of the pinned buffer must be done before it is overwritten */
-    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    /* the previous H2D copy out of the pinned buffer must be done before it is overwritten (it is,
+     * whenever a download or wait followed it: then no synchronisation is needed here) */
+    if (c->staging_in_flight)
+    {
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    }
     stage_head(c, shiftvec);
     float4*    pos = reinterpret_cast<float4*>(c->h_step_in.ptr + sizeof(DynHead));
     const int  nT  = c->layout.ntouched;
@@ -1510,6 +1540,7 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
                                     c->stream));
         done = upto;
     }
+    c->staging_in_flight = true;
     return FEPB200_OK;
 }
 
@@ -1525,10 +1556,14 @@ int fepb200_gather_x_device(fepb200_ctx* c, const float* d_x, const float* shift
         return rc;
     }
     cudaSetDevice(c->device);
-    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->staging_in_flight)
+    {
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    }
     stage_head(c, shiftvec);
     CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr, c->h_step_in.ptr, sizeof(DynHead), cudaMemcpyHostToDevice,
                                 c->stream));
+    c->staging_in_flight = true;
     const int err = fep_launch_gather_x(d_x, c->d_touched.ptr,
                                         reinterpret_cast<float4*>(c->d_step_in.ptr + sizeof(DynHead)),
                                         c->layout.ntouched, c->stream, &c->launches);
@@ -1581,6 +1616,7 @@ int fepb200_wait(fepb200_ctx* c)
     }
     cudaSetDevice(c->device);
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->staging_in_flight = false;
     return FEPB200_OK;
 }
 
@@ -1738,6 +1774,7 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
         }
     }
     CU_CHECK(c, cudaEventSynchronize(c->ev_copy[nchunks - 1]));
+    c->staging_in_flight = false; /* everything queued before the last D2H copy has completed */
     if (sf.energy)
     {
         for (int g = 0; g < l.nenergrp; g++)
