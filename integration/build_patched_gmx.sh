@@ -1,0 +1,32 @@
+#!/bin/bash
+# Builds the reference's gmx with the fepb200 hook (see README.md).  Needs /root/reference.
+set -euo pipefail
+ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+SRC=/tmp/gmxsrc
+BUILD=/tmp/gmxbuild
+OUT="$ROOT/integration/_gmx"
+if [ ! -f "$SRC/.patched" ]; then
+  rm -rf "$SRC"; mkdir -p "$SRC"; cp -r /root/reference/. "$SRC/"
+  (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/freeenergydispatch_fepb200.patch" && touch .patched)
+fi
+mkdir -p "$BUILD"
+cmake -G Ninja -S "$SRC" -B "$BUILD" -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ \
+  -DCMAKE_POLICY_VERSION_MINIMUM=3.5 -DGMX_GPU=OFF -DGMX_MPI=OFF -DGMX_THREAD_MPI=ON -DGMX_OPENMP=ON \
+  -DGMX_FFT_LIBRARY=fftpack -DGMX_DOUBLE=OFF -DGMX_HWLOC=OFF -DGMX_EXTERNAL_BLAS=OFF -DGMX_EXTERNAL_LAPACK=OFF \
+  -DGMXAPI=OFF -DBUILD_TESTING=OFF -DCMAKE_BUILD_TYPE=Release -DGMX_SIMD=AVX2_256 \
+  "-DCMAKE_CXX_FLAGS=-I$ROOT/include -I$ROOT/integration/gromacs_shim" > "$BUILD/cmake.log" 2>&1
+ninja -C "$BUILD" gmx > "$BUILD/ninja.log" 2>&1
+mkdir -p "$OUT/bin" "$OUT/lib"
+cp "$BUILD/bin/gmx" "$OUT/bin/"
+cp -P "$BUILD"/lib/libgromacs.so* "$OUT/lib/"
+cp -P "$BUILD"/lib/libmuparser.so* "$OUT/lib/" 2>/dev/null || true
+strip "$OUT/lib/"*.so.*.* 2>/dev/null || true
+# run inputs of the reference's free-energy test systems
+TPR="$ROOT/tests/golden/mdrun_tpr"; mkdir -p "$TPR"
+export GMXLIB="$SRC/share/top" LD_LIBRARY_PATH="$OUT/lib"
+for sys in coulandvdwsequential_coul coulandvdwsequential_vdw coulandvdwtogether transformAtoB vdwalone; do
+  d="$SRC/src/testutils/simulationdatabase/freeenergy/$sys"
+  (cd /tmp && "$OUT/bin/gmx" -quiet grompp -f "$d/grompp.mdp" -c "$d/conf.gro" -p "$d/topol.top" -o "$TPR/$sys.tpr" \
+     -po /tmp/mdout_$sys.mdp -maxwarn 10 > /tmp/grompp_$sys.log 2>&1) || { echo "grompp failed for $sys"; tail -5 /tmp/grompp_$sys.log; }
+done
+ls -la "$OUT/bin" "$OUT/lib" "$TPR"

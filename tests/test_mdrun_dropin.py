@@ -1,0 +1,91 @@
+"""The drop-in claim, end to end: the reference's own `gmx mdrun` (built from /root/reference with the
+12-line hook of integration/gromacs_shim/freeenergydispatch_fepb200.patch) runs the reference's own
+free-energy test systems twice -- perturbed pairs on the reference's CPU kernel, and through
+libfepb200.so on the B200 (GMX_FEPB200=1) -- and the per-step dH/dlambda, foreign-lambda energy
+differences and potential energies must agree at the tolerance the reference's own mdrun test uses
+(src/programs/mdrun/tests/freeenergy.cpp:115-117: relative 1e-4 in mixed precision).
+
+Needs integration/_gmx (integration/build_patched_gmx.sh, built where /root/reference exists; the
+binaries travel to the GPU box with the repo snapshot)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GMX = os.path.join(ROOT, "integration", "_gmx", "bin", "gmx")
+GMXLIBDIR = os.path.join(ROOT, "integration", "_gmx", "lib")
+TPR = os.path.join(ROOT, "tests", "golden", "mdrun_tpr")
+LIB = os.path.join(ROOT, "gromacs-fep-gpu_b200", "lib", "libfepb200.so")
+SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwtogether", "transformAtoB", "vdwalone"]
+
+
+def _xvg(path):
+    rows = []
+    for line in open(path):
+        if line.startswith(("#", "@")) or not line.strip():
+            continue
+        rows.append([float(v) for v in line.split()])
+    return np.array(rows)
+
+
+WANT = ("Potential", "LJ-(SR)", "Coulomb-(SR)", "dVremain/dl", "dVcoul/dl", "dVvdw/dl", "dVbonded/dl", "dVrestraint/dl")
+
+
+def _energy_terms(workdir, env):
+    """Names of the energy terms in run.edr (gmx energy prints the table before it asks)."""
+    r = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr", "-o", "none.xvg"], cwd=workdir, env=env, input="\n",
+                       capture_output=True, text=True, timeout=120)
+    names = []
+    for line in (r.stdout + r.stderr).splitlines():
+        parts = line.split()
+        if len(parts) >= 2 and parts[0].isdigit() and all(p.isdigit() for p in parts[0::2]):
+            names += parts[1::2]
+    return names
+
+
+def _run(tpr, workdir, use_gpu):
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = GMXLIBDIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    env["GMX_FEPB200_LIB"] = LIB
+    env.pop("GMX_FEPB200", None)
+    if use_gpu:
+        env["GMX_FEPB200"] = "1"
+    os.makedirs(workdir, exist_ok=True)
+    r = subprocess.run([GMX, "-quiet", "mdrun", "-s", tpr, "-deffnm", "run", "-nb", "cpu", "-pme", "cpu", "-bonded", "cpu",
+                        "-update", "cpu", "-fep", "cpu", "-ntmpi", "1", "-ntomp", "2", "-notunepme"],
+                       cwd=workdir, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    terms = [t for t in WANT if t in _energy_terms(workdir, env)]
+    assert "Potential" in terms
+    e = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr", "-s", tpr, "-o", "terms.xvg", "-odh", "dh.xvg", "-xvg",
+                        "none"], cwd=workdir, env=env, input="\n".join(terms) + "\n\n", capture_output=True, text=True,
+                       timeout=120)
+    assert e.returncode == 0, e.stderr[-2000:]
+    return r.stderr, terms, _xvg(os.path.join(workdir, "terms.xvg")), _xvg(os.path.join(workdir, "dh.xvg"))
+
+
+@pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
+@pytest.mark.parametrize("system", SYSTEMS)
+def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, tmp_path):
+    tpr = os.path.join(TPR, system + ".tpr")
+    if not os.path.exists(tpr):
+        pytest.skip("no run input for " + system)
+    err_cpu, terms_cpu, e_cpu, dh_cpu = _run(tpr, str(tmp_path / "cpu"), False)
+    err_gpu, terms_gpu, e_gpu, dh_gpu = _run(tpr, str(tmp_path / "gpu"), True)
+    assert "computed by fepb200" in err_gpu and "computed by fepb200" not in err_cpu
+    assert terms_cpu == terms_gpu and e_cpu.shape == e_gpu.shape and e_cpu.shape[0] >= 20
+    # per-step energies and dV/dlambda components (every step), relative to the size of the quantity
+    for col, name in enumerate(terms_cpu, start=1):
+        a, b = e_gpu[:, col], e_cpu[:, col]
+        scale = max(np.max(np.abs(b)), 1.0)
+        assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, name, np.max(np.abs(a - b)), scale)
+    # dH/dlambda and the energy differences to the foreign lambda states (every nstdhdl steps)
+    assert dh_cpu.shape == dh_gpu.shape and dh_cpu.shape[0] >= 2 and dh_cpu.shape[1] >= 2
+    for col in range(1, dh_cpu.shape[1]):
+        a, b = dh_gpu[:, col], dh_cpu[:, col]
+        scale = max(np.max(np.abs(b)), 1.0)
+        assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, "dh column", col, np.max(np.abs(a - b)), scale)
