@@ -61,10 +61,10 @@ def _run(tpr, workdir, use_gpu):
     assert r.returncode == 0, r.stderr[-2000:]
     terms = [t for t in WANT if t in _energy_terms(workdir, env)]
     assert "Potential" in terms
-    e = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr", "-s", tpr, "-o", "terms.xvg", "-odh", "dh.xvg", "-xvg",
-                        "none"], cwd=workdir, env=env, input="\n".join(terms) + "\n\n", capture_output=True, text=True,
-                       timeout=120)
-    assert e.returncode == 0, e.stderr[-2000:]
+    for extra in (["-o", "terms.xvg"], ["-s", tpr, "-odh", "dh.xvg"]):  # -odh suppresses the -o output
+        e = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr", "-xvg", "none"] + extra, cwd=workdir, env=env,
+                           input="\n".join(terms) + "\n\n", capture_output=True, text=True, timeout=120)
+        assert e.returncode == 0, e.stderr[-2000:]
     return r.stderr, terms, _xvg(os.path.join(workdir, "terms.xvg")), _xvg(os.path.join(workdir, "dh.xvg"))
 
 
@@ -85,7 +85,11 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
         assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, name, np.max(np.abs(a - b)), scale)
     # dH/dlambda and the energy differences to the foreign lambda states (every nstdhdl steps)
     assert dh_cpu.shape == dh_gpu.shape and dh_cpu.shape[0] >= 2 and dh_cpu.shape[1] >= 2
+    # (a foreign state equal to the current one gives exactly 0 on the CPU path, where both energies
+    # come from the same code; here they come from two kernels and differ by fp32 rounding of
+    # energies of size |Epot|: the floor of the scale is 1e-3 |Epot|, i.e. 1e-7 of the energies)
+    epot = np.max(np.abs(e_cpu[:, 1]))
     for col in range(1, dh_cpu.shape[1]):
         a, b = dh_gpu[:, col], dh_cpu[:, col]
-        scale = max(np.max(np.abs(b)), 1.0)
+        scale = max(np.max(np.abs(b)), 1.0, 1e-3 * epot)
         assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, "dh column", col, np.max(np.abs(a - b)), scale)
