@@ -85,11 +85,12 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
         assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, name, np.max(np.abs(a - b)), scale)
     # dH/dlambda and the energy differences to the foreign lambda states (every nstdhdl steps)
     assert dh_cpu.shape == dh_gpu.shape and dh_cpu.shape[0] >= 2 and dh_cpu.shape[1] >= 2
-    # (a foreign state equal to the current one gives exactly 0 on the CPU path, where both energies
-    # come from the same code; here they come from two kernels and differ by fp32 rounding of
-    # energies of size |Epot|: the floor of the scale is 1e-3 |Epot|, i.e. 1e-7 of the energies)
-    epot = np.max(np.abs(e_cpu[:, 1]))
+    # A foreign state equal to the current one gives exactly 0 on the CPU path, where both energies
+    # come from the same code; here they come from two kernels and differ by fp32 rounding of the
+    # perturbed energies (observed: 1.3e-4 kJ/mol). The bar is the reference test's own energy
+    # tolerance, relativeToleranceAsFloatingPoint(50.0, 1e-4) (src/programs/mdrun/tests/freeenergy.cpp:115):
+    # relative 1e-4 of the value, with an absolute floor of 50 * 1e-4 kJ/mol.
     for col in range(1, dh_cpu.shape[1]):
         a, b = dh_gpu[:, col], dh_cpu[:, col]
-        scale = max(np.max(np.abs(b)), 1.0, 1e-3 * epot)
+        scale = max(np.max(np.abs(b)), 50.0)
         assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, "dh column", col, np.max(np.abs(a - b)), scale)
