@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    fep_pdl_launch_dependents(); /* the next kernel of the step may fill SM space we leave free */
 
     /* the 45 shift vectors are read once per pair with a data-dependent index: keep them on chip */
     __shared__ float4 s_shift[FEP_NUM_SHIFT];
@@ -583,6 +584,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 
     if (L::NACC == 0)
     {
+        fep_pdl_wait();
         return;
     }
     float red[N8];
@@ -627,28 +629,30 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         ka.for_part[o + bs.n_tiles]     = DC;
         ka.for_part[o + 2 * bs.n_tiles] = DG;
     }
+    /* nothing here depends on the preceding kernel; completing after it keeps the chain ordered */
+    fep_pdl_wait();
 }
 
 /* ------------------------------------------------------------------------------------------- */
 /* occ != nullptr: only report how many CTAs of this instantiation fit on one SM */
 template<bool EWALD, int MODE, int C, bool FORCE>
-static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream, int* occ)
+static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream, int* occ, bool chained)
 {
     if (occ)
     {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE>, FEP_FB_CTA, 0);
         return;
     }
-    fep_beutler_kernel<EWALD, MODE, C, FORCE><<<bs.n_tiles, FEP_FB_CTA, 0, stream>>>(ka, bs);
+    fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
 }
 
 template<bool EWALD, int MODE, bool FORCE>
-static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cudaStream_t stream, int* occ)
+static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cudaStream_t stream, int* occ, bool chained)
 {
     switch (c)
     {
 #define FEP_FB_CASE(N) \
-    case N: launch_one<EWALD, MODE, N, FORCE>(ka, bs, stream, occ); return true;
+    case N: launch_one<EWALD, MODE, N, FORCE>(ka, bs, stream, occ, chained); return true;
         FEP_FB_CASE(1)
         FEP_FB_CASE(2)
         FEP_FB_CASE(3)
@@ -665,7 +669,7 @@ static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cuda
         case 0:
             if (FORCE)
             {
-                launch_one<EWALD, MODE, 0, true>(ka, bs, stream, occ);
+                launch_one<EWALD, MODE, 0, true>(ka, bs, stream, occ, chained);
                 return true;
             }
             return false;
@@ -674,11 +678,12 @@ static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cuda
 }
 
 template<bool EWALD, bool FORCE>
-static bool launch_mode(const KernelArgs& ka, const BeutlerStep& bs, int mode, int c, cudaStream_t stream, int* occ)
+static bool launch_mode(const KernelArgs& ka, const BeutlerStep& bs, int mode, int c, cudaStream_t stream, int* occ,
+                        bool chained = false)
 {
-    return mode == 0   ? launch_size<EWALD, 0, FORCE>(ka, bs, c, stream, occ)
-           : mode == 1 ? launch_size<EWALD, 1, FORCE>(ka, bs, c, stream, occ)
-                       : launch_size<EWALD, 2, FORCE>(ka, bs, c, stream, occ);
+    return mode == 0   ? launch_size<EWALD, 0, FORCE>(ka, bs, c, stream, occ, chained)
+           : mode == 1 ? launch_size<EWALD, 1, FORCE>(ka, bs, c, stream, occ, chained)
+                       : launch_size<EWALD, 2, FORCE>(ka, bs, c, stream, occ, chained);
 }
 
 static const int c_sizes[] = { 1, 2, 3, 4, 6, 7, 8, 11, 14, 16, 21, 24 };
@@ -725,7 +730,7 @@ extern "C" int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int c, int forc
  * lambda points, pts[0] = current.  Returns cudaSuccess (0) or an error code. */
 extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mode, const LambdaPoint* cur,
                                   const LambdaPoint* pts, int do_force, int do_foreign, int want_shift,
-                                  cudaStream_t stream, long long* counter)
+                                  cudaStream_t stream, long long* counter, int chained)
 {
     const KernelArgs& ka = *kap;
     const int         c  = do_foreign ? ka.chunk_points : 0;
@@ -777,20 +782,21 @@ extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mod
         bool       ok;
         if (force)
         {
-            ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, stream, nullptr)
-                            : launch_mode<false, true>(ka, bs, mode, c, stream, nullptr);
+            ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, stream, nullptr, chained != 0)
+                            : launch_mode<false, true>(ka, bs, mode, c, stream, nullptr, chained != 0);
         }
         else
         {
-            ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, stream, nullptr)
-                            : launch_mode<false, false>(ka, bs, mode, c, stream, nullptr);
+            ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, stream, nullptr, chained != 0)
+                            : launch_mode<false, false>(ka, bs, mode, c, stream, nullptr, chained != 0);
         }
         if (!ok)
         {
             return (int)cudaErrorInvalidValue;
         }
         (*counter)++;
-        first = false;
+        first   = false;
+        chained = chained != 0 ? chained : (ka.pdl_chain ? 1 : 0); /* later chunks follow a kernel of this step */
         if (c == 0)
         {
             break;

@@ -20,6 +20,8 @@
  * any data path; the only atomic is the completion ticket of the epilogue.
  */
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "fep_pair_math.cuh"
 
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    fep_pdl_launch_dependents();
     if (tid < (int)(sizeof(LambdaPoint) / 4))
     {
         reinterpret_cast<int*>(&s_lp)[tid] = reinterpret_cast<const int*>(&ka.dyn->cur)[tid];
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         }
         ka.cta_part[(size_t)tid * ka.n_cta + blockIdx.x] = s;
     }
+    fep_pdl_wait(); /* first kernel of a step: no-op */
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
     const int warp = tid >> 5;
     const int p0   = blockIdx.y * ka.chunk_points;
     const int np   = min(ka.chunk_points, ka.n_points - p0);
+    fep_pdl_launch_dependents();
     if (tid < np * (int)(sizeof(LambdaPoint) / 4))
     {
         reinterpret_cast<int*>(s_pts)[tid] = reinterpret_cast<const int*>(ka.pts + p0)[tid];
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
         const int p = tid / 3, k = tid - 3 * p;
         ka.for_part[((size_t)(3 * (p0 + p) + k)) * ka.n_tiles + blockIdx.x] = s;
     }
+    fep_pdl_wait(); /* independent of the pass kernel before it; see fep_types.h */
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -339,6 +345,10 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
     const int off_fe   = off_dvdl + 2;
     const int off_fd   = off_fe + ka.n_points;
 
+    /* Chained behind the pair kernels (fep_types.h): what does not depend on their results -- the
+     * static descriptors of this block's work -- is fetched before fep_pdl_wait(). */
+    fep_pdl_launch_dependents();
+
     /* role order: reduction jobs and scalar sums first (few, long), per-atom gathers after, so the
      * long blocks overlap with the bulk instead of forming a tail */
     bool is_job = false;
@@ -347,6 +357,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         is_job           = true;
         const int    j   = lay.job_begin + b;
         const RedJob job = ka.red_jobs[j];
+        fep_pdl_wait();
         double       a0 = 0.0, a1 = 0.0, a2 = 0.0;
         /* a job is a contiguous range of at most FEP_RED_CHUNK = PER * CTA elements */
         constexpr int PER = FEP_RED_CHUNK / FEP_EPI_CTA;
@@ -398,6 +409,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         /* b = 0,1: dV/dlambda coul, vdw of the current-lambda pass; b = 2 + 3p + k: point p */
         const double* src;
         int           n;
+        fep_pdl_wait();
         if (b < 2)
         {
             src = ka.cta_part + (size_t)b * ka.n_parts;
@@ -442,9 +454,15 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         const int atom = b * (FEP_EPI_CTA / FEP_EPI_LANES) + (tid / FEP_EPI_LANES);
         const int sub  = tid % FEP_EPI_LANES;
         float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        int       k0 = 0, k1 = 0;
         if (atom < ka.n_touched)
         {
-            const int k0 = __ldg(ka.atom_ptr + atom), k1 = __ldg(ka.atom_ptr + atom + 1);
+            k0 = __ldg(ka.atom_ptr + atom);
+            k1 = __ldg(ka.atom_ptr + atom + 1);
+        }
+        fep_pdl_wait();
+        if (atom < ka.n_touched)
+        {
             /* the atom's contributions are contiguous in fsorted: the lanes stream them, four
              * independent 16-byte loads per lane and trip (most atoms need a single trip) */
             for (int k = k0 + sub; k < k1; k += 4 * FEP_EPI_LANES)
@@ -557,10 +575,29 @@ __global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restri
 /* ------------------------------------------------------------------------------------------- */
 /* launchers                                                                                   */
 /* ------------------------------------------------------------------------------------------- */
+/* FEPB200_OVERLAP = pdl (default) | streams | none */
+static int fep_overlap_mode()
+{
+    static const int mode = [] {
+        const char* e = std::getenv("FEPB200_OVERLAP");
+        if (e && std::strcmp(e, "streams") == 0)
+        {
+            return 1;
+        }
+        if (e && std::strcmp(e, "none") == 0)
+        {
+            return 0;
+        }
+        return 2;
+    }();
+    return mode;
+}
+
 template<int SC, bool EWALD>
 static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t stream, long long* counter,
                                    cudaEvent_t* ev, const LambdaPoint* host_cur, const LambdaPoint* host_pts,
-                                   int beutler_mode, cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev)
+                                   int beutler_mode, cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev,
+                                   bool* chain_out)
 {
     const bool foreign = sf.foreign && ka.n_points > 0;
     const bool beutler = SC == FEP_SC_BEUTLER && beutler_mode >= 0;
@@ -570,12 +607,21 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
      * and the foreign chunks are separate launches of the same code. */
     const bool one_launch = beutler && sf.force && foreign && ka.fuse_pass_and_foreign;
     int        rc         = 0;
+    /* How the independent pass and foreign kernels of a large list share the GPU, and how the
+     * epilogue follows them: "pdl" (default) chains all kernels of the step on one stream with
+     * programmatic dependent launches (fep_types.h); "streams" forks the foreign kernels to a side
+     * stream; "none" queues them plainly.  Profiling mode times every kernel alone. */
+    const int  mode   = ev ? 0 : fep_overlap_mode();
+    const bool pdl    = mode == 2;
+    bool       queued = false; /* a kernel of this step is on `stream` */
+    ka.pdl_chain      = pdl ? 1 : 0;
     if (ev)
     {
         cudaEventRecord(ev[0], stream);
     }
     ka.n_parts = 0;
-    if (!ev && side != nullptr && beutler && sf.force && foreign && !one_launch)
+    const bool use_side = mode == 1 && side != nullptr && beutler && sf.force && foreign && !one_launch;
+    if (use_side)
     {
         cudaEventRecord(fork_ev, stream);
     }
@@ -583,7 +629,7 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
     {
         if (beutler && sf.force)
         {
-            rc = fep_launch_beutler(&ka, EWALD ? 1 : 0, beutler_mode, host_cur, host_pts, 1, 0, sf.shift, stream, counter);
+            rc = fep_launch_beutler(&ka, EWALD ? 1 : 0, beutler_mode, host_cur, host_pts, 1, 0, sf.shift, stream, counter, 0);
             ka.n_parts = ka.pass_n_tiles;
         }
         else
@@ -591,15 +637,16 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
             /* generic pass kernel, one thread per pair */
             if (sf.force)
             {
-                fep_pass_kernel<SC, EWALD, true><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, sf.shift);
+                fep_launch_kernel(fep_pass_kernel<SC, EWALD, true>, dim3(ka.n_cta), dim3(FEP_CTA), stream, false, ka, sf.shift);
             }
             else
             {
-                fep_pass_kernel<SC, EWALD, false><<<ka.n_cta, FEP_CTA, 0, stream>>>(ka, 0);
+                fep_launch_kernel(fep_pass_kernel<SC, EWALD, false>, dim3(ka.n_cta), dim3(FEP_CTA), stream, false, ka, 0);
             }
             ka.n_parts = ka.n_cta;
             (*counter)++;
         }
+        queued = true;
     }
     if (ev)
     {
@@ -609,10 +656,7 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
     {
         if (beutler)
         {
-            /* the pass kernel (already queued on `stream`) and the foreign kernels are independent
-             * and both latency-bound: on a second stream they share the SMs instead of queueing.
-             * Not in profiling mode, where each kernel is timed alone. */
-            const bool   overlap = !one_launch && !ev && side != nullptr && ka.n_parts > 0;
+            const bool   overlap = use_side && ka.n_parts > 0;
             cudaStream_t fstream = stream;
             if (overlap)
             {
@@ -621,7 +665,7 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
                 fstream = side;
             }
             rc = fep_launch_beutler(&ka, EWALD ? 1 : 0, beutler_mode, host_cur, host_pts, one_launch ? 1 : 0, 1,
-                                    one_launch ? sf.shift : 0, fstream, counter);
+                                    one_launch ? sf.shift : 0, fstream, counter, (pdl && queued) ? 1 : 0);
             if (overlap)
             {
                 cudaEventRecord(join_ev, side);
@@ -635,9 +679,10 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
         else
         {
             const dim3 grid(ka.n_tiles, ka.n_chunks);
-            fep_foreign_kernel<SC, EWALD><<<grid, FEP_CTA, 0, stream>>>(ka);
+            fep_launch_kernel(fep_foreign_kernel<SC, EWALD>, grid, dim3(FEP_CTA), stream, pdl && queued, ka);
             (*counter)++;
         }
+        queued = true;
     }
     if (rc != 0)
     {
@@ -647,6 +692,7 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
     {
         cudaEventRecord(ev[2], stream);
     }
+    *chain_out = pdl && queued;
     return cudaGetLastError();
 }
 
@@ -657,12 +703,13 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
 {
     KernelArgs  ka = *kap; /* local copy: n_parts depends on which pass kernel ran */
     cudaError_t err;
+    bool        chain = false;
     switch (softcore * 2 + (elec_ewald ? 1 : 0))
     {
 #define FEP_CASE(SCV, EW) \
     case SCV * 2 + (EW ? 1 : 0): \
         err = launch_variants<SCV, EW>(ka, sf, stream, counter, ev, host_cur, host_pts, beutler_mode, side, fork_ev, \
-                                        join_ev); \
+                                        join_ev, &chain); \
         break;
         FEP_CASE(FEP_SC_NONE, false)
         FEP_CASE(FEP_SC_NONE, true)
@@ -686,7 +733,7 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     lay.job_blocks    = j1 > j0 ? j1 - j0 : 0;
     lay.scalar_blocks = 2 + ((sf.foreign && ka.n_points > 0) ? 3 * ka.n_points : 0);
     const int blocks  = lay.atom_blocks + lay.job_blocks + lay.scalar_blocks;
-    fep_epilogue_kernel<<<blocks, FEP_EPI_CTA, 0, stream>>>(ka, lay, sf);
+    fep_launch_kernel(fep_epilogue_kernel, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
     (*counter)++;
     if (ev)
     {
@@ -709,6 +756,7 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
                                                              int n64, size_t f64_bytes, float* __restrict__ out_f32,
                                                              long long n32)
 {
+    fep_pdl_wait(); /* chained behind the epilogue that completes this rank's block */
     if (flags.p[0] != nullptr)
     {
         /* Cross-GPU barrier inside the reduction kernel.  This rank's block was completed by the
@@ -794,7 +842,7 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
 
 extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flagsp, int rank, unsigned int seq,
                                       int nranks, double* out_f64, int n64, size_t f64_bytes, float* out_f32,
-                                      long long n32, cudaStream_t stream, long long* counter)
+                                      long long n32, cudaStream_t stream, long long* counter, int chained)
 {
     PeerPtrs noflags{};
     const PeerPtrs* flags = flagsp ? flagsp : &noflags;
@@ -802,10 +850,10 @@ extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* fla
     const unsigned  blocks = (unsigned)((std::max<long long>(items, n64) + 255) / 256);
     switch (nranks)
     {
-        case 2: fep_peer_reduce_kernel<2><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
-        case 4: fep_peer_reduce_kernel<4><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
-        case 8: fep_peer_reduce_kernel<8><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
-        default: fep_peer_reduce_kernel<0><<<blocks, 256, 0, stream>>>(*peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        case 2: fep_launch_kernel(fep_peer_reduce_kernel<2>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        case 4: fep_launch_kernel(fep_peer_reduce_kernel<4>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        case 8: fep_launch_kernel(fep_peer_reduce_kernel<8>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        default: fep_launch_kernel(fep_peer_reduce_kernel<0>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
     }
     (*counter)++;
     return (int)cudaGetLastError();

@@ -55,46 +55,65 @@ __device__ __forceinline__ float fep_sixth_root(float x)
     return fep_ex2(fep_lg2(x) * (1.0f / 6.0f));
 }
 
-/* Ewald real-space correction (reference :109-119, 1056-1101).
- *   v_lr = beta * erf(z)/z = erf(beta r) / r
- *   f_lr / r^2-scaled, i.e. the factor that multiplies the distance vector:
- *          -beta^3 * ( 2 exp(-z^2)/(sqrt(pi) z^2) - erf(z)/z^3 )
- * For z^2 < 1 the bracket is summed from its Taylor series, which has no cancellation:
- *   2/sqrt(pi) * sum_{n>=1} (-1)^n z^(2n-2)/n! * 2n/(2n+1)                                   */
+/* Ewald real-space correction (reference :109-119, 1056-1101).  With w = z^2 = beta^2 r^2:
+ *   v_lr = beta * V(w),    V(w) = erf(z)/z
+ *   f_lr = -beta^3 * B(w), B(w) = 2 exp(-w)/(sqrt(pi) w) - erf(z)/z^3 = 2 dV/dw
+ * (f_lr is the factor that multiplies the distance vector).  Both are smooth functions of w, so for
+ * w <= 16 (beta r <= 4: every pair inside a cut-off chosen with ewald-rtol >= 2e-8, and the
+ * excluded neighbours beside it) they are evaluated branch-free as rational functions P(w)/Q(w),
+ * like the reference does (simd_math.h pmeForceCorrection / pmePotentialCorrection); the
+ * coefficients are our own weighted least-squares/Lawson fits (tools/fit_ewald_rational.py):
+ * V [6/4] 6.9e-8, B [6/5] 6.3e-8 maximum relative error in exact arithmetic, 4e-7 (8.6e-8 rms)
+ * evaluated with fp32 FMAs.  Beyond w = 16 (only possible for excluded pairs far outside the
+ * cut-off) the closed forms are used. */
 template<bool FORCE>
 __device__ __forceinline__ void fep_ewald_correction(float r2, float r, float rinv, float beta, float beta2,
                                                      float beta3, float* v_lr, float* f_lr)
 {
-    const float z  = beta * r;
-    const float ez = erff(z);
-    *v_lr          = ez * rinv;
-    if (FORCE)
+    const float w = beta2 * r2;
+    if (w <= 16.0f)
     {
-        const float z2 = beta2 * r2;
-        float       bracket;
-        if (z2 < 1.0f)
+        float pv = 1.914866538e-08f;
+        pv       = fmaf(pv, w, -1.938895923e-06f);
+        pv       = fmaf(pv, w, 1.461872746e-04f);
+        pv       = fmaf(pv, w, 3.943561305e-03f);
+        pv       = fmaf(pv, w, 5.137383335e-02f);
+        pv       = fmaf(pv, w, 2.060183881e-01f);
+        pv       = fmaf(pv, w, 1.128379099e+00f);
+        float qv = 1.009842853e-03f;
+        qv       = fmaf(qv, w, 1.486172240e-02f);
+        qv       = fmaf(qv, w, 1.175093691e-01f);
+        qv       = fmaf(qv, w, 5.159104191e-01f);
+        qv       = fmaf(qv, w, 1.0f);
+        *v_lr    = beta * pv * fep_rcp(qv);
+        if (FORCE)
         {
-            /* coefficients (-1)^n 2n/((2n+1) n!) for n = 12..1, Horner in z2 */
-            float p = 2.004168671e-09f;
-            p       = fmaf(p, z2, -2.396288628e-08f);
-            p       = fmaf(p, z2, 2.624506593e-07f);
-            p       = fmaf(p, z2, -2.610693400e-06f);
-            p       = fmaf(p, z2, 2.334267040e-05f);
-            p       = fmaf(p, z2, -1.851851852e-04f);
-            p       = fmaf(p, z2, 1.282051282e-03f);
-            p       = fmaf(p, z2, -7.575757576e-03f);
-            p       = fmaf(p, z2, 3.703703704e-02f);
-            p       = fmaf(p, z2, -1.428571429e-01f);
-            p       = fmaf(p, z2, 4.000000000e-01f);
-            p       = fmaf(p, z2, -6.666666667e-01f);
-            bracket = 1.1283791671f * p;
+            float pb = -1.081098709e-08f;
+            pb       = fmaf(pb, w, 1.028332784e-06f);
+            pb       = fmaf(pb, w, -5.036981975e-05f);
+            pb       = fmaf(pb, w, 2.020152613e-04f);
+            pb       = fmaf(pb, w, -1.807793702e-02f);
+            pb       = fmaf(pb, w, 3.588346990e-02f);
+            pb       = fmaf(pb, w, -7.522528250e-01f);
+            float qb = 1.302164612e-04f;
+            qb       = fmaf(qb, w, 2.096415634e-03f);
+            qb       = fmaf(qb, w, 2.163110569e-02f);
+            qb       = fmaf(qb, w, 1.411150645e-01f);
+            qb       = fmaf(qb, w, 5.523007151e-01f);
+            qb       = fmaf(qb, w, 1.0f);
+            *f_lr    = -beta3 * pb * fep_rcp(qb);
         }
-        else
+    }
+    else
+    {
+        const float z  = beta * r;
+        const float ez = erff(z);
+        *v_lr          = ez * rinv;
+        if (FORCE)
         {
-            const float iz2 = fep_rcp(z2);
-            bracket         = 1.1283791671f * fep_ex2(-1.4426950408889634f * z2) * iz2 - ez * iz2 * fep_rcp(z);
+            const float iw = fep_rcp(w);
+            *f_lr = -beta3 * (1.1283791671f * fep_ex2(-1.4426950408889634f * w) * iw - ez * iw * fep_rcp(z));
         }
-        *f_lr = -beta3 * bracket;
     }
 }
 

@@ -93,6 +93,7 @@ struct KernelArgs
     int n_parts;                       /* per-CTA dV/dlambda partials written by the pass of this step */
     int fuse_pass_and_foreign;         /* Beutler path: pass + first foreign chunk in one launch */
     int n_red_jobs, n_shift_jobs;
+    int pdl_chain;                     /* set per step by the launcher: kernels after the first are chained (PDL) */
     /* inputs */
     const DynHead*     dyn;
     const LambdaPoint* pts;
@@ -142,9 +143,11 @@ int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlag
 #define FEP_FB_MAXC 24
 int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
 int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force);
+/* chained != 0: a kernel of this step is already queued on `stream` and the launches may start
+ * before it has completed (programmatic dependent launch, see fep_launch_kernel below) */
 int fep_launch_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_cur,
                        const LambdaPoint* host_pts, int do_force, int do_foreign, int want_shift, cudaStream_t stream,
-                       long long* launch_counter);
+                       long long* launch_counter, int chained);
 /* Sum over ranks of result blocks that live in peer-mapped memory (NVLink): out = sum_r peer[r],
  * in rank order (deterministic).  n16 = number of 16-byte words that hold fp32 data, n64 = number
  * of doubles; each peer block is [n64 doubles padded to 16 B | fp32 words]. */
@@ -158,10 +161,47 @@ struct PeerPtrs
  * (the cross-GPU barrier is part of the reduction kernel). */
 int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flags, int rank, unsigned int seq, int nranks,
                            double* out_f64, int n64, size_t f64_bytes, float* out_f32, long long n32,
-                           cudaStream_t stream, long long* launch_counter);
+                           cudaStream_t stream, long long* launch_counter, int chained);
 int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched, cudaStream_t stream,
                         long long* launch_counter);
 #ifdef __cplusplus
+}
+#endif
+
+#ifdef __CUDACC__
+/* Programmatic dependent launch (sm_90+).  The kernels of one step are queued back to back on one
+ * stream.  Every kernel lets its successor start as soon as all of its own CTAs are running
+ * (fep_pdl_launch_dependents at the top), so independent kernels (pass and foreign passes) share
+ * the SMs and a dependent kernel (epilogue) has its launch latency and its prologue hidden behind
+ * its predecessor's tail.  A kernel that needs its predecessors' results calls fep_pdl_wait()
+ * first: it returns when the preceding kernel has completed and its writes are visible.  A kernel
+ * that does NOT depend on its predecessor still calls fep_pdl_wait() as its last action, so that
+ * "my predecessor in the stream has completed" implies "everything before it has completed".
+ * Both instructions are no-ops in a kernel launched without the attribute. */
+__device__ __forceinline__ void fep_pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void fep_pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template<typename... KArgs, typename... Args>
+static inline cudaError_t fep_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream,
+                                            bool chained, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = grid;
+    cfg.blockDim           = block;
+    cfg.dynamicSmemBytes   = 0;
+    cfg.stream             = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = chained ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif
 

@@ -153,6 +153,7 @@ struct fepb200_ctx
 {
     int          device = -1;
     cudaStream_t stream = nullptr, own_stream = nullptr, side_stream = nullptr;
+    bool         chain_open = false; /* the last thing queued on `stream` is this step's epilogue (see fepb200_launch) */
     cudaEvent_t  fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t  ev_prof[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -1489,6 +1490,16 @@ int fepb200_set_lambdas(fepb200_ctx* c, const float* lambda, int n_foreign, cons
 }
 
 /* ---- step ------------------------------------------------------------------------------- */
+/* something other than the reduction kernel follows the epilogue on the stream: end the step here */
+static void close_chain(fepb200_ctx* c)
+{
+    if (c->chain_open)
+    {
+        c->chain_open = false;
+        cudaEventRecord(c->ev_stop, c->stream);
+    }
+}
+
 static int stage_head(fepb200_ctx* c, const float* shiftvec)
 {
     DynHead* head = reinterpret_cast<DynHead*>(c->h_step_in.ptr);
@@ -1586,6 +1597,7 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
         return rc;
     }
     cudaSetDevice(c->device);
+    close_chain(c);
     cudaStream_t    stream = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
     const StepFlags sf     = step_flags(c, flags);
     CU_CHECK(c, cudaEventRecord(c->ev_start, stream));
@@ -1603,7 +1615,13 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     {
         return fail(c, FEPB200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
     }
-    CU_CHECK(c, cudaEventRecord(c->ev_stop, stream));
+    /* multi-GPU with a published partial block: the reduction kernel follows on the same stream and
+     * is chained behind the epilogue (nothing may be queued between them); it records ev_stop */
+    c->chain_open = c->res_target != nullptr && stream == c->stream && !c->profiling;
+    if (!c->chain_open)
+    {
+        CU_CHECK(c, cudaEventRecord(c->ev_stop, stream));
+    }
     c->timed = true;
     return FEPB200_OK;
 }
@@ -1615,6 +1633,7 @@ int fepb200_wait(fepb200_ctx* c)
         return FEPB200_ERR_INVALID_ARGUMENT;
     }
     cudaSetDevice(c->device);
+    close_chain(c);
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     c->staging_in_flight = false;
     return FEPB200_OK;
@@ -1663,6 +1682,7 @@ int fepb200_publish_result(fepb200_ctx* c, void* d_block)
         return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_publish_result: bad arguments");
     }
     cudaSetDevice(c->device);
+    close_chain(c);
     /* the device result block is contiguous [f64 | f32] */
     CU_CHECK(c, cudaMemcpyAsync(d_block, c->d_result.ptr, c->res_f64_bytes + c->res_f32_bytes, cudaMemcpyDeviceToDevice,
                                 c->stream));
@@ -1686,7 +1706,12 @@ int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks,
     }
     const int err = fep_launch_peer_reduce(&pp, d_peer_flags ? &ff : nullptr, rank, seq, nranks, c->ka.res_f64,
                                            (int)c->layout.f64_words, c->res_f64_bytes, c->ka.res_f32,
-                                           c->layout.f32_words, c->stream, &c->launches);
+                                           c->layout.f32_words, c->stream, &c->launches, c->chain_open ? 1 : 0);
+    if (c->chain_open)
+    {
+        c->chain_open = false;
+        cudaEventRecord(c->ev_stop, c->stream);
+    }
     if (err != 0)
     {
         return fail(c, FEPB200_ERR_CUDA, "peer reduce launch failed: %s", cudaGetErrorString((cudaError_t)err));
@@ -1707,6 +1732,7 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
         return rc;
     }
     cudaSetDevice(c->device);
+    close_chain(c);
     const StepFlags       sf    = step_flags(c, flags);
     const fepb200_layout& l     = c->layout;
     const bool            clear = (flags & FEPB200_CLEAR_OUTPUTS) != 0;
@@ -1861,6 +1887,7 @@ int fepb200_last_launch_ms(fepb200_ctx* c, float* ms)
         return fail(c, FEPB200_ERR_STATE, "no launch has been timed");
     }
     cudaSetDevice(c->device);
+    close_chain(c);
     CU_CHECK(c, cudaEventSynchronize(c->ev_stop));
     CU_CHECK(c, cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
     return FEPB200_OK;
