@@ -294,19 +294,6 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         acc[i] = 0.0f;
     }
 
-    /* The per-atom arrays (32 bytes per touched atom) are gathered with data-dependent indices whose
-     * load latency from HBM a one-trip prefetch does not cover: the grid pulls both arrays into L2
-     * once, one 128-byte line per thread, while the first pair records are on their way. */
-    {
-        const int lines = (ka.n_touched * (int)sizeof(float4) + 127) >> 7;
-        for (int l = blockIdx.x * FEP_FB_CTA + tid; l < 2 * lines; l += gridDim.x * FEP_FB_CTA)
-        {
-            const char* a = l < lines ? reinterpret_cast<const char*>(ka.pos4) + ((size_t)l << 7)
-                                      : reinterpret_cast<const char*>(ka.par4) + ((size_t)(l - lines) << 7);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-        }
-    }
-
     const float thr_v = ka.vdw_ewald ? __int_as_float(0x7f800000) : ka.rvdw6; /* LJ-PME tests r, below */
     const int   base  = blockIdx.x * bs.tile_pairs;
     const int   end   = min(base + bs.tile_pairs, ka.n_pairs);
