@@ -191,7 +191,10 @@ int fepb200_set_lambdas(fepb200_ctx* ctx, const float* lambda, int n_foreign,
  * ACCUMULATED (+=) exactly like the reference kernel does into its thread buffers
  * (nb_free_energy.cpp:1155-1178) unless FEPB200_CLEAR_OUTPUTS is set.  Any output
  * pointer may be NULL when the corresponding flag is not set.
- * Copies host->device (touched coordinates only) and device->host inside the call. */
+ * Copies host->device (touched coordinates only) inside the call; the results travel back as
+ * they are produced: the last kernel writes them into the library's pinned host buffer over PCIe
+ * (no separate device->host copy), from where they are added into the caller's arrays.  The device
+ * result block (fepb200_result_device_ptrs) is only filled by fepb200_launch(). */
 int fepb200_compute(fepb200_ctx* ctx, const float* x, const float* shiftvec, int flags, float* f,
                     float* fshift, double* Vc, double* Vv, double* dvdl /*[2]: coul, vdw*/,
                     double* foreign_energy /*[L+1]*/, double* foreign_dvdl /*[L+1][2]*/);
