@@ -298,7 +298,7 @@ def run_ours(args, name):
     alg_flop = (FLOP_PER_PAIR * my_pairs + FLOP_PER_ENTRY * my_entries) * passes_in_launch
     achieved = alg_flop / (k_foreign * 1e-3) / 1e12 if k_foreign > 0 else 0.0
     # algorithmic bytes of the step (pair records + touched-atom data + result), for the HBM view
-    alg_bytes = my_pairs * 16 + int(lay.ntouched) * (16 + 16 + 12)
+    alg_bytes = my_pairs * 16 + int(lay.ntouched) * (12 + 16 + 12)
     dominant = "fep_beutler_kernel" if problem.params.softcoreType == 0 and problem.params.alphaVdw != 0 \
         and problem.params.vdw_modifier != 3 else "fep_foreign_kernel"
     roofline = dict(bound="fp32", kernel=dominant + (" (current-lambda pass fused in)" if fused else " (foreign-lambda passes)"),
@@ -342,7 +342,7 @@ def run_ours(args, name):
     torch.cuda.synchronize()
     e2e_s = max(e2e_s - f0.elapsed_time(f1) * 1e-3, 1e-9)
     e2e_value = wl["units_per_step"] / (e2e_s / args.steps)
-    h2d = 816 + 16 * int(lay.ntouched)  # DynHead (45 shift vectors + current-lambda block) + float4 per touched atom
+    h2d = 816 + 12 * int(lay.ntouched)  # DynHead (45 shift vectors + current-lambda block) + packed xyz per touched atom
     d2h = int(lay.f32_words) * 4 + int(lay.f64_words) * 8
 
     clocks = sampler.stop() if rank == 0 else None

@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     const int  slot0  = base + warp * 32 + lane;
     int4       rec_n1 = slot0 < end ? __ldg(ka.pair4 + slot0) : dummy;
     int4       rec_n2 = slot0 + FEP_FB_CTA < end ? __ldg(ka.pair4 + slot0 + FEP_FB_CTA) : dummy;
-    float4     xi_n   = __ldg(ka.pos4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
-    float4     xj_n   = __ldg(ka.pos4 + (rec_n1.x & 0x7fffffff));
+    float3     xi_n   = fep_load_pos(ka.pos3, rec_n1.y & (FEP_MAX_TOUCHED - 1));
+    float3     xj_n   = fep_load_pos(ka.pos3, rec_n1.x & 0x7fffffff);
     float4     pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
     float4     pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
     int        hb_n   = (FORCE && base + warp * 32 < end) ? __ldg(ka.warp_hbase + ((base + warp * 32) >> 5)) : 0;
@@ -315,11 +315,12 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         const int    slot   = w0 + lane;
         const bool   active = slot < end;
         const int4   rec    = rec_n1;
-        const float4 xi = xi_n, xj = xj_n, pi = pi_n, pq = pq_n;
+        const float3 xi = xi_n, xj = xj_n;
+        const float4 pi = pi_n, pq = pq_n;
         rec_n1 = rec_n2;
         rec_n2 = slot + 2 * FEP_FB_CTA < end ? __ldg(ka.pair4 + slot + 2 * FEP_FB_CTA) : dummy;
-        xi_n   = __ldg(ka.pos4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
-        xj_n   = __ldg(ka.pos4 + (rec_n1.x & 0x7fffffff));
+        xi_n   = fep_load_pos(ka.pos3, rec_n1.y & (FEP_MAX_TOUCHED - 1));
+        xj_n   = fep_load_pos(ka.pos3, rec_n1.x & 0x7fffffff);
         pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
         pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
         const int hbase = hb_n; /* first segment id of this warp trip, fetched during the previous trip */

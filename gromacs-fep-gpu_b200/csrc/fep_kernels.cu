@@ -562,13 +562,15 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
 
 /* coordinates of the touched atoms from a device-resident rvec[natoms] array */
 __global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restrict__ x, const int* __restrict__ touched,
-                                                          float4* __restrict__ pos4, int n)
+                                                          float* __restrict__ pos3, int n)
 {
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k < n)
     {
         const size_t a = (size_t)touched[k];
-        pos4[k]        = make_float4(x[3 * a], x[3 * a + 1], x[3 * a + 2], 0.0f);
+        pos3[3 * (size_t)k]     = x[3 * a];
+        pos3[3 * (size_t)k + 1] = x[3 * a + 1];
+        pos3[3 * (size_t)k + 2] = x[3 * a + 2];
     }
 }
 
@@ -859,12 +861,12 @@ extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* fla
     return (int)cudaGetLastError();
 }
 
-extern "C" int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched,
+extern "C" int fep_launch_gather_x(const float* d_x, const int* d_touched, float* pos3, int n_touched,
                                    cudaStream_t stream, long long* counter)
 {
     if (n_touched > 0)
     {
-        fep_gather_x_kernel<<<(n_touched + 255) / 256, 256, 0, stream>>>(d_x, d_touched, pos4, n_touched);
+        fep_gather_x_kernel<<<(n_touched + 255) / 256, 256, 0, stream>>>(d_x, d_touched, pos3, n_touched);
         (*counter)++;
     }
     return (int)cudaGetLastError();

@@ -43,6 +43,13 @@ __device__ __forceinline__ float fep_ex2(float x)
     return y;
 }
 
+/* coordinates of compact atom k (packed xyz) */
+__device__ __forceinline__ float3 fep_load_pos(const float* __restrict__ pos3, int k)
+{
+    const float* p = pos3 + 3 * (size_t)k;
+    return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+
 /* x^(-1/6) for x > 0 (normal range): two MUFU ops */
 __device__ __forceinline__ float fep_inv_sixth_root(float x)
 {
@@ -389,9 +396,9 @@ __device__ __forceinline__ bool fep_load_pair(const KernelArgs& ka, int slot, Fe
     const int ci   = rec.y & (FEP_MAX_TOUCHED - 1);
     self           = (ci == cj);
 
-    const float4 xi = __ldg(ka.pos4 + ci);
+    const float3 xi = fep_load_pos(ka.pos3, ci);
     const float4 sh = ka.dyn->shiftvec[rec.y >> 24];
-    const float4 xj = __ldg(ka.pos4 + cj);
+    const float3 xj = fep_load_pos(ka.pos3, cj);
     /* the reference shifts the i atom first (:478-480) */
     dx = (sh.x + xi.x) - xj.x;
     dy = (sh.y + xi.y) - xj.y;

@@ -8,7 +8,8 @@
  *
  *   dyn          DynHead           per step: shift vectors + constants of the current lambda
  *   pts[L+1]     LambdaPoint       per set_lambdas: point 0 = current lambda, 1.. = foreign
- *   pos4[nT]     float4 {x,y,z,0}  per step: coordinates of the touched atoms (compact order)
+ *   pos3[nT]     float[3] {x,y,z}  per step: coordinates of the touched atoms (compact order),
+ *                                  packed: 12 bytes per atom cross PCIe, not 16
  *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step
  *   typetab[T*T] float4 {c6,c12,sigma6,c6grid}               per nbfp upload
  *   pair4[P]     int4   {compact j | excluded << 31, compact i | shift << 24, local i-entry
@@ -59,7 +60,7 @@ struct LambdaPoint
 };
 
 /* Per-step head block, uploaded in one copy together with the coordinates that follow it
- * in device memory (step_in = [DynHead | pos4[nT]]). */
+ * in device memory (step_in = [DynHead | pos3[nT]]). */
 struct DynHead
 {
     float4      shiftvec[FEP_NUM_SHIFT];
@@ -97,7 +98,7 @@ struct KernelArgs
     /* inputs */
     const DynHead*     dyn;
     const LambdaPoint* pts;
-    const float4*   pos4;
+    const float*    pos3;
     const float4*   par4;
     const float4*   typetab;
     const int4*     pair4;
@@ -162,7 +163,7 @@ struct PeerPtrs
 int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flags, int rank, unsigned int seq, int nranks,
                            double* out_f64, int n64, size_t f64_bytes, float* out_f32, long long n32,
                            cudaStream_t stream, long long* launch_counter, int chained);
-int fep_launch_gather_x(const float* d_x, const int* d_touched, float4* pos4, int n_touched, cudaStream_t stream,
+int fep_launch_gather_x(const float* d_x, const int* d_touched, float* pos3, int n_touched, cudaStream_t stream,
                         long long* launch_counter);
 #ifdef __cplusplus
 }

@@ -232,7 +232,7 @@ struct fepb200_ctx
     DeviceArray<int> d_raw_iinr, d_raw_gid, d_raw_shift, d_raw_jindex, d_raw_jjnr, d_raw_excl, d_mark, d_cscan, d_keys,
             d_keys_out, d_vals, d_vals_out, d_head, d_hscan, d_seg_shift, d_seg_gid, d_key_ptr;
     DeviceArray<unsigned char> d_cub_tmp;
-    DeviceArray<unsigned char> d_step_in; /* [DynHead | pos4[nT]] */
+    DeviceArray<unsigned char> d_step_in; /* [DynHead | pos3[nT]] */
     DeviceArray<unsigned char> d_result;  /* [f64 block | f32 block] */
     PinnedArray<unsigned char> h_step_in, h_result;
     size_t res_f64_bytes = 0, res_f32_bytes = 0;
@@ -423,12 +423,12 @@ int prepare_buffers(fepb200_ctx* c)
                 (cudaHostGetDevicePointer(&dp, c->h_result.ptr, 0) == cudaSuccess) ? static_cast<unsigned char*>(dp) : nullptr;
         cudaGetLastError();
     }
-    const size_t step_bytes = sizeof(DynHead) + sizeof(float4) * (size_t)l.ntouched;
+    const size_t step_bytes = sizeof(DynHead) + 3 * sizeof(float) * (size_t)l.ntouched;
     CU_CHECK(c, c->d_step_in.reserve(step_bytes));
     CU_CHECK(c, c->h_step_in.reserve(step_bytes));
 
     k.dyn      = reinterpret_cast<const DynHead*>(c->d_step_in.ptr);
-    k.pos4     = reinterpret_cast<const float4*>(c->d_step_in.ptr + sizeof(DynHead));
+    k.pos3     = reinterpret_cast<const float*>(c->d_step_in.ptr + sizeof(DynHead));
     k.pts      = c->d_pts.ptr;
     k.cta_part = c->d_cta_part.ptr;
     k.for_part = c->d_for_part.ptr;
@@ -1585,13 +1585,13 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
         CU_CHECK(c, cudaStreamSynchronize(c->stream));
     }
     stage_head(c, shiftvec);
-    float4*    pos = reinterpret_cast<float4*>(c->h_step_in.ptr + sizeof(DynHead));
+    float*     pos = reinterpret_cast<float*>(c->h_step_in.ptr + sizeof(DynHead));
     const int  nT  = c->layout.ntouched;
     const int* t   = c->touched.data();
     /* Pipelined: the touched coordinates are gathered into pinned memory chunk by chunk and each
      * chunk's H2D copy is queued at once, so the DMA of chunk k runs while the host gathers k+1. */
     const int nchunks = nT > 32768 ? c_copy_chunks : 1;
-    size_t    done    = 0; /* bytes of [DynHead | pos4] already queued */
+    size_t    done    = 0; /* bytes of [DynHead | pos3] already queued */
     for (int ch = 0; ch < nchunks; ch++)
     {
         const int k0 = (int)((long long)nT * ch / nchunks), k1 = (int)((long long)nT * (ch + 1) / nchunks);
@@ -1599,10 +1599,12 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
         for (int k = k0; k < k1; k++)
         {
             const float* xa = x + 3 * (size_t)t[k];
-            pos[k]          = make_float4(xa[0], xa[1], xa[2], 0.0f);
+            pos[3 * (size_t)k]     = xa[0];
+            pos[3 * (size_t)k + 1] = xa[1];
+            pos[3 * (size_t)k + 2] = xa[2];
         }
         lap_us(c, 0);
-        const size_t upto = sizeof(DynHead) + sizeof(float4) * (size_t)k1;
+        const size_t upto = sizeof(DynHead) + 3 * sizeof(float) * (size_t)k1;
         if (c->lap_on)
         {
             cudaEventRecord(c->lap_ev[0], c->stream);
@@ -1641,7 +1643,7 @@ int fepb200_gather_x_device(fepb200_ctx* c, const float* d_x, const float* shift
                                 c->stream));
     c->staging_in_flight = true;
     const int err = fep_launch_gather_x(d_x, c->d_touched.ptr,
-                                        reinterpret_cast<float4*>(c->d_step_in.ptr + sizeof(DynHead)),
+                                        reinterpret_cast<float*>(c->d_step_in.ptr + sizeof(DynHead)),
                                         c->layout.ntouched, c->stream, &c->launches);
     if (err != 0)
     {
