@@ -125,7 +125,7 @@ def _config(problem, name, world, extra=None):
                energy_group_pairs=problem.nenergrp_pairs,
                passes_per_step=1 + problem.n_foreign + 1,
                flags="FORCE|SHIFTFORCE|POTENTIAL|FOREIGNLAMBDA",
-               parallelism=f"i-entry shards x{world}", l2="flushed between timed steps (512 MiB write)")
+               parallelism=f"pair-list shards x{world}", l2="flushed between timed steps (512 MiB write)")
     if extra:
         cfg.update(extra)
     return cfg
@@ -285,7 +285,12 @@ def run_ours(args, name):
         kms.append(ctx.kernel_ms())
     ctx.set_profiling(False)
     k_pass, k_foreign, k_epi = (sum(k[j] for k in kms) / len(kms) for j in range(3))
-    my_pairs, my_entries = int(lay.nrj), int(lay.nri)
+    my_pairs, my_entries, my_atoms = int(lay.nrj), int(lay.nri), int(lay.ntouched)
+    if sh.reduction == "fused":
+        # every rank holds the full layout, evaluates its share of the pairs and owns a range of atoms
+        p0, p1, a0, a1 = ctx.peer_ranges()
+        my_entries = int(round(my_entries * (p1 - p0) / max(my_pairs, 1)))
+        my_pairs, my_atoms = p1 - p0, a1 - a0
     points = problem.n_foreign + 1
     peaks = _peaks()
     sms = torch.cuda.get_device_properties(local).multi_processor_count
@@ -343,7 +348,7 @@ def run_ours(args, name):
     e2e_s = max(e2e_s - f0.elapsed_time(f1) * 1e-3, 1e-9)
     e2e_value = wl["units_per_step"] / (e2e_s / args.steps)
     h2d = 816 + 12 * int(lay.ntouched)  # DynHead (45 shift vectors + current-lambda block) + packed xyz per touched atom
-    d2h = int(lay.f32_words) * 4 + int(lay.f64_words) * 8
+    d2h = (3 * my_atoms + 135) * 4 + int(lay.f64_words) * 8
 
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
@@ -353,7 +358,10 @@ def run_ours(args, name):
             cpu.pop("ms_per_step", None)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
-                    data="synthetic", config=_config(problem, name, world, dict(reduction=sh.reduction)),
+                    data="synthetic", config=_config(problem, name, world, dict(
+                        reduction=sh.reduction if world > 1 else "none",
+                        outputs="forces reduce-scattered by atom range, scalars on every rank" if sh.reduction == "fused"
+                        else "full result on every rank")),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_s / args.steps * 1e3),
                     gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, cpu_baseline=cpu,

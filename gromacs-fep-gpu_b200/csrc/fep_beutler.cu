@@ -262,7 +262,7 @@ struct AccLayout
     static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : (NACC > 30 ? 3 : 4);
 };
 
-template<bool EWALD, int MODE, int C, bool FORCE>
+template<bool EWALD, int MODE, int C, bool FORCE, bool PEER>
 __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         fep_beutler_kernel(const __grid_constant__ KernelArgs ka, const __grid_constant__ BeutlerStep bs)
 {
@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     }
 
     const float thr_v = ka.vdw_ewald ? __int_as_float(0x7f800000) : ka.rvdw6; /* LJ-PME tests r, below */
-    const int   base  = blockIdx.x * bs.tile_pairs;
-    const int   end   = min(base + bs.tile_pairs, ka.n_pairs);
+    const int   base  = ka.pair_begin + blockIdx.x * bs.tile_pairs; /* a multiple of 32 */
+    const int   end   = min(base + bs.tile_pairs, ka.pair_end);
 
     /* Software pipeline over the trips: while trip k is evaluated, the pair record of trip k+2 and
      * the atom data of trip k+1 (whose record arrived during trip k-1) are in flight, so the
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
             {
                 /* the j atom receives -f: scattered to this pair's own slot in the atom-sorted
                  * buffer (unique destination, no atomics; skipped pairs write their zero) */
-                ka.fsorted[rec.w] = make_float4(-fx, -fy, -fz, 0.0f);
+                fep_put_force<PEER>(ka, rec.w, make_float4(-fx, -fy, -fz, 0.0f));
             }
             /* segmented sum over the lanes of one i-entry: i force and Vc/Vv of the segment */
 #pragma unroll
@@ -572,20 +572,15 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
             }
             if (head)
             {
-                const float4 fi  = make_float4(fx, fy, fz, 0.0f);
-                ka.fsorted[sd.x] = fi;
-                if (bs.want_shift)
-                {
-                    ka.fshift_sorted[sd.y] = fi;
-                }
-                ka.ev2[sd.z] = make_float2(vctot, vvtot);
+                fep_put_segment<PEER>(ka, sd, make_float4(fx, fy, fz, 0.0f), true, bs.want_shift != 0, true,
+                                make_float2(vctot, vvtot));
             }
         }
     }
 
     if (L::NACC == 0)
     {
-        fep_pdl_wait();
+        fep_pair_kernel_done<PEER>();
         return;
     }
     float red[N8];
@@ -613,7 +608,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     __syncthreads();
     if (FORCE && tid < 2)
     {
-        ka.cta_part[(size_t)tid * bs.n_tiles + blockIdx.x] = s_sum[L::iCUR + tid];
+        fep_put_cta_part<PEER>(ka, fep_part_index(ka, tid, bs.n_tiles, blockIdx.x), s_sum[L::iCUR + tid]);
     }
     if (C > 0 && tid < bs.np)
     {
@@ -625,13 +620,13 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         /* E = lfacC[A] C_A + lfacC[B] C_B + lfacV[A] G_A + lfacV[B] G_B with X_B = X_A + DX */
         const double e = (double)bs.lfc[0][p] * CA + (double)bs.lfc[1][p] * (CA + DC) + (double)bs.lfv[0][p] * GA
                          + (double)bs.lfv[1][p] * (GA + DG);
-        const size_t o = (size_t)(3 * (bs.p0 + p)) * bs.n_tiles + blockIdx.x;
-        ka.for_part[o]                  = e;
-        ka.for_part[o + bs.n_tiles]     = DC;
-        ka.for_part[o + 2 * bs.n_tiles] = DG;
+        const int row = 3 * (bs.p0 + p);
+        fep_put_for_part<PEER>(ka, fep_part_index(ka, row, bs.n_tiles, blockIdx.x), e);
+        fep_put_for_part<PEER>(ka, fep_part_index(ka, row + 1, bs.n_tiles, blockIdx.x), DC);
+        fep_put_for_part<PEER>(ka, fep_part_index(ka, row + 2, bs.n_tiles, blockIdx.x), DG);
     }
     /* nothing here depends on the preceding kernel; completing after it keeps the chain ordered */
-    fep_pdl_wait();
+    fep_pair_kernel_done<PEER>();
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -639,12 +634,29 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 template<bool EWALD, int MODE, int C, bool FORCE>
 static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream, int* occ, bool chained)
 {
+    /* the peer-exchange variant (stores through the peers' pointers, system-scope fence at the end)
+     * is a separate instantiation: the single-GPU code carries none of it */
+    const bool peer = ka.px.nranks > 1;
     if (occ)
     {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE>, FEP_FB_CTA, 0);
+        if (peer)
+        {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, FEP_FB_CTA, 0);
+        }
+        else
+        {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE, false>, FEP_FB_CTA, 0);
+        }
         return;
     }
-    fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
+    if (peer)
+    {
+        fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
+    }
+    else
+    {
+        fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE, false>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
+    }
 }
 
 template<bool EWALD, int MODE, bool FORCE>
@@ -707,9 +719,10 @@ extern "C" int fep_beutler_chunk_size(int n_points, int n_chunks_wanted)
 }
 
 /* resident CTAs per SM of the kernel instantiation a launch would use (for one-wave tile sizing) */
-extern "C" int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int c, int force)
+extern "C" int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int c, int force, int peer)
 {
     KernelArgs  ka{};
+    ka.px.nranks = peer ? 2 : 1;
     BeutlerStep bs{};
     int         occ = 0;
     bool        ok;

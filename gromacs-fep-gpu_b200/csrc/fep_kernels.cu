@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
     }
     __syncthreads();
 
-    const int  slot  = blockIdx.x * FEP_CTA + tid;
-    const bool valid = slot < ka.n_pairs;
+    const int  slot  = ka.pair_begin + blockIdx.x * FEP_CTA + tid; /* pair_begin is a multiple of 32 */
+    const bool valid = slot < ka.pair_end;
 
     float fx = 0.0f, fy = 0.0f, fz = 0.0f, vc = 0.0f, vv = 0.0f, dc = 0.0f, dv = 0.0f;
     int   entry = -1;
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         {
             /* the j atom receives -t: scattered to this pair's own slot in the atom-sorted buffer
              * (unique destination, no atomics; skipped pairs write their zero) */
-            ka.fsorted[__ldg(ka.pair4 + slot).w] = make_float4(-fx, -fy, -fz, 0.0f);
+            const int    w = __ldg(ka.pair4 + slot).w;
+            const float4 t = make_float4(-fx, -fy, -fz, 0.0f);
+            FEP_PX(ka, fep_put_force<true>(ka, w, t), fep_put_force<false>(ka, w, t));
         }
     }
 
@@ -146,19 +148,13 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
     }
     if (boundary && valid)
     {
-        const int gw = blockIdx.x * (FEP_CTA / 32) + warp;
+        const int gw = (ka.pair_begin >> 5) + blockIdx.x * (FEP_CTA / 32) + warp;
         const int h  = __ldg(ka.warp_hbase + gw) + __popc(hmask & ((1u << lane) - 1u));
         const int4 sd = __ldg(ka.seg_dst + h);
-        if (FORCE)
-        {
-            const float4 fi = make_float4(fx, fy, fz, 0.0f);
-            ka.fsorted[sd.x] = fi;
-            if (want_shift)
-            {
-                ka.fshift_sorted[sd.y] = fi;
-            }
-        }
-        ka.ev2[sd.z] = make_float2(vc, vv);
+        const float4 fi = make_float4(fx, fy, fz, 0.0f);
+        const float2 e2 = make_float2(vc, vv);
+        FEP_PX(ka, fep_put_segment<true>(ka, sd, fi, FORCE, FORCE && want_shift != 0, true, e2),
+               fep_put_segment<false>(ka, sd, fi, FORCE, FORCE && want_shift != 0, true, e2));
     }
 
     __syncthreads();
@@ -170,9 +166,10 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         {
             s += (double)s_red[w][tid];
         }
-        ka.cta_part[(size_t)tid * ka.n_cta + blockIdx.x] = s;
+        const size_t o = fep_part_index(ka, tid, ka.n_cta, blockIdx.x);
+        FEP_PX(ka, fep_put_cta_part<true>(ka, o, s), fep_put_cta_part<false>(ka, o, s));
     }
-    fep_pdl_wait(); /* first kernel of a step: no-op */
+    FEP_PX(ka, fep_pair_kernel_done<true>(), fep_pair_kernel_done<false>()); /* first kernel of a step: the wait is a no-op */
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -240,8 +237,8 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
         acc_e[p] = acc_c[p] = acc_v[p] = 0.0f;
     }
 
-    const int base = blockIdx.x * ka.tile_pairs;
-    const int end  = min(base + ka.tile_pairs, ka.n_pairs);
+    const int base = ka.pair_begin + blockIdx.x * ka.tile_pairs;
+    const int end  = min(base + ka.tile_pairs, ka.pair_end);
     for (int slot = base + tid; slot < end; slot += FEP_CTA)
     {
         FepPair pr;
@@ -295,9 +292,10 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
             s += (double)s_red[w][tid];
         }
         const int p = tid / 3, k = tid - 3 * p;
-        ka.for_part[((size_t)(3 * (p0 + p) + k)) * ka.n_tiles + blockIdx.x] = s;
+        const size_t o = fep_part_index(ka, 3 * (p0 + p) + k, ka.n_tiles, blockIdx.x);
+        FEP_PX(ka, fep_put_for_part<true>(ka, o, s), fep_put_for_part<false>(ka, o, s));
     }
-    fep_pdl_wait(); /* independent of the pass kernel before it; see fep_types.h */
+    FEP_PX(ka, fep_pair_kernel_done<true>(), fep_pair_kernel_done<false>()); /* independent of the pass kernel before it */
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -331,9 +329,58 @@ __device__ __forceinline__ double block_sum_d(double v, double* s_buf)
     return s; /* valid in thread 0 */
 }
 
+/* Cross-GPU barrier of the peer exchange (fep_types.h), taken by every CTA of the epilogue right
+ * after fep_pdl_wait(), i.e. when this rank's pair kernels have completed (their threads fenced
+ * their peer stores at system scope before exiting).  Block 0 announces step `seq` in slot `rank`
+ * of every peer's flag array; every block waits until all peers' announcements have arrived in the
+ * local array.  Exactly one kernel per GPU spins and its producers have already finished, so the
+ * spin cannot starve anybody; a peer that never arrives (a rank that did not launch) trips the
+ * time-out and the kernel traps instead of hanging the GPU. */
+__device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
+{
+    const int nr = ka.px.nranks;
+    if (threadIdx.x < nr)
+    {
+        if (blockIdx.x == 0)
+        {
+            __threadfence_system();
+            unsigned int* dst = ka.px.flags[threadIdx.x] + ka.px.rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(ka.px.seq) : "memory");
+        }
+        const unsigned int* src = ka.px.flags[ka.px.rank] + threadIdx.x;
+        unsigned int        v;
+        unsigned long long  t0 = 0;
+        for (unsigned int spins = 0;; spins++)
+        {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if ((int)(v - ka.px.seq) >= 0)
+            {
+                break;
+            }
+            if ((spins & 1023u) == 1023u)
+            {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0)
+                {
+                    t0 = now;
+                }
+                else if (now - t0 > 4000000000ull) /* 4 s */
+                {
+                    __trap();
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template<bool PEER>
 __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_constant__ KernelArgs ka,
                                                                   const EpilogueLayout lay, const StepFlags sf)
 {
+/* data other GPUs wrote into this rank's exchange slot is read at L2 (the point of coherence) */
+#define FEP_EPI_LOAD(ptr) (PEER ? __ldcg(ptr) : __ldcs(ptr))
     __shared__ double s_buf[FEP_EPI_CTA / 32];
     __shared__ bool   s_last;
     const int         tid = threadIdx.x;
@@ -358,6 +405,10 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         const int    j   = lay.job_begin + b;
         const RedJob job = ka.red_jobs[j];
         fep_pdl_wait();
+        if (PEER)
+        {
+            fep_peer_barrier(ka);
+        }
         double       a0 = 0.0, a1 = 0.0, a2 = 0.0;
         /* a job is a contiguous range of at most FEP_RED_CHUNK = PER * CTA elements */
         constexpr int PER = FEP_RED_CHUNK / FEP_EPI_CTA;
@@ -368,7 +419,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             for (int u = 0; u < PER; u++)
             {
                 const int k = job.begin + tid + u * FEP_EPI_CTA;
-                t[u]        = k < job.end ? __ldcs(ka.fshift_sorted + k) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                t[u]        = k < job.end ? FEP_EPI_LOAD(ka.fshift_sorted + k) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
 #pragma unroll
             for (int u = 0; u < PER; u++)
@@ -385,7 +436,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             for (int u = 0; u < PER; u++)
             {
                 const int k = job.begin + tid + u * FEP_EPI_CTA;
-                t[u]        = k < job.end ? __ldcs(ka.ev2 + k) : make_float2(0.0f, 0.0f);
+                t[u]        = k < job.end ? FEP_EPI_LOAD(ka.ev2 + k) : make_float2(0.0f, 0.0f);
             }
 #pragma unroll
             for (int u = 0; u < PER; u++)
@@ -410,20 +461,25 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         const double* src;
         int           n;
         fep_pdl_wait();
+        if (PEER)
+        {
+            fep_peer_barrier(ka);
+        }
+        /* rows of part_mult x (local CTAs) partials, in rank order (fep_part_index) */
         if (b < 2)
         {
-            src = ka.cta_part + (size_t)b * ka.n_parts;
-            n   = ka.n_parts;
+            n   = ka.n_parts * ka.part_mult;
+            src = ka.cta_part + (size_t)b * n;
         }
         else
         {
-            src = ka.for_part + (size_t)(b - 2) * ka.n_tiles;
-            n   = ka.n_tiles;
+            n   = ka.n_tiles * ka.part_mult;
+            src = ka.for_part + (size_t)(b - 2) * n;
         }
         double a = 0.0;
         for (int k = tid; k < n; k += FEP_EPI_CTA)
         {
-            a += src[k];
+            a += PEER ? __ldcg(src + k) : src[k];
         }
         a = block_sum_d(a, s_buf);
         if (tid == 0)
@@ -451,17 +507,23 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         /* FEP_EPI_LANES lanes per touched atom; contributions are visited in ascending index order by
          * lane stride, then combined with a fixed xor tree: deterministic */
         b -= lay.scalar_blocks;
-        const int atom = b * (FEP_EPI_CTA / FEP_EPI_LANES) + (tid / FEP_EPI_LANES);
-        const int sub  = tid % FEP_EPI_LANES;
+        /* PEER: this rank sums the atoms it owns (the forces are reduce-scattered by atom range) */
+        const int atom     = (PEER ? ka.px.atom_begin : 0) + b * (FEP_EPI_CTA / FEP_EPI_LANES) + (tid / FEP_EPI_LANES);
+        const int atom_end = PEER ? ka.px.atom_end : ka.n_touched;
+        const int sub      = tid % FEP_EPI_LANES;
         float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
         int       k0 = 0, k1 = 0;
-        if (atom < ka.n_touched)
+        if (atom < atom_end)
         {
             k0 = __ldg(ka.atom_ptr + atom);
             k1 = __ldg(ka.atom_ptr + atom + 1);
         }
         fep_pdl_wait();
-        if (atom < ka.n_touched)
+        if (PEER)
+        {
+            fep_peer_barrier(ka);
+        }
+        if (atom < atom_end)
         {
             /* the atom's contributions are contiguous in fsorted: the lanes stream them, four
              * independent 16-byte loads per lane and trip (most atoms need a single trip) */
@@ -471,7 +533,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                 {
-                    t[u] = (k + FEP_EPI_LANES * u < k1) ? __ldcs(ka.fsorted + k + FEP_EPI_LANES * u)
+                    t[u] = (k + FEP_EPI_LANES * u < k1) ? FEP_EPI_LOAD(ka.fsorted + k + FEP_EPI_LANES * u)
                                                         : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
 #pragma unroll
@@ -490,7 +552,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             fy += __shfl_xor_sync(FULL_MASK, fy, o);
             fz += __shfl_xor_sync(FULL_MASK, fz, o);
         }
-        if (atom < ka.n_touched && sub < 3)
+        if (atom < atom_end && sub < 3)
         {
             ka.res_f32[3 * (size_t)atom + sub] = sub == 0 ? fx : (sub == 1 ? fy : fz);
         }
@@ -558,6 +620,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
     {
         *ka.done_counter = 0u;
     }
+#undef FEP_EPI_LOAD
 }
 
 /* coordinates of the touched atoms from a device-resident rvec[natoms] array */
@@ -726,8 +789,10 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     {
         return (int)err;
     }
+    const bool     peer    = ka.px.nranks > 1;
+    const int      n_atoms = peer ? ka.px.atom_end - ka.px.atom_begin : ka.n_touched;
     EpilogueLayout lay;
-    lay.atom_blocks   = sf.force ? (ka.n_touched + FEP_EPI_CTA / FEP_EPI_LANES - 1) / (FEP_EPI_CTA / FEP_EPI_LANES) : 0;
+    lay.atom_blocks   = sf.force ? (n_atoms + FEP_EPI_CTA / FEP_EPI_LANES - 1) / (FEP_EPI_CTA / FEP_EPI_LANES) : 0;
     /* jobs are ordered shift jobs first, then energy-group jobs */
     const int j0      = sf.shift ? 0 : ka.n_shift_jobs;
     const int j1      = sf.energy ? ka.n_red_jobs : ka.n_shift_jobs;
@@ -735,7 +800,14 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     lay.job_blocks    = j1 > j0 ? j1 - j0 : 0;
     lay.scalar_blocks = 2 + ((sf.foreign && ka.n_points > 0) ? 3 * ka.n_points : 0);
     const int blocks  = lay.atom_blocks + lay.job_blocks + lay.scalar_blocks;
-    fep_launch_kernel(fep_epilogue_kernel, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+    if (peer)
+    {
+        fep_launch_kernel(fep_epilogue_kernel<true>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+    }
+    else
+    {
+        fep_launch_kernel(fep_epilogue_kernel<false>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+    }
     (*counter)++;
     if (ev)
     {

@@ -294,3 +294,53 @@ extern "C" int fep_list_build_slots(const int4* d_ent4, int4* d_pair4, const int
     }
     return (int)cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* peer exchange (fep_types.h): the rank that owns the receiving atom, in the top bits of every
+ * scatter slot.  slot_bound[r] = first slot of rank r's atom range; nranks == 1 clears the bits. */
+struct OwnerBounds
+{
+    int n;
+    int b[FEP_XMAX + 1];
+};
+
+__global__ void __launch_bounds__(256) k_tag_owners(int4* __restrict__ pair4, int P, int4* __restrict__ seg_dst, int H,
+                                                    const OwnerBounds ob)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    auto tag = [&](int w) {
+        w &= FEP_X_SLOT_MASK;
+        int owner = 0;
+        for (int r = 1; r < ob.n; r++)
+        {
+            owner += (w >= ob.b[r]) ? 1 : 0;
+        }
+        return w | (owner << FEP_X_OWNER_SHIFT);
+    };
+    if (i < P)
+    {
+        pair4[i].w = tag(pair4[i].w);
+    }
+    if (i < H)
+    {
+        seg_dst[i].x = tag(seg_dst[i].x);
+    }
+}
+
+extern "C" int fep_launch_tag_owners(int4* d_pair4, int P, int4* d_seg_dst, int H, const int* slot_bound, int nranks,
+                                     cudaStream_t stream, long long* counter)
+{
+    OwnerBounds ob{};
+    ob.n = nranks;
+    for (int r = 0; r <= nranks && r <= FEP_XMAX; r++)
+    {
+        ob.b[r] = slot_bound[r];
+    }
+    const int n = P > H ? P : H;
+    if (n > 0)
+    {
+        k_tag_owners<<<(n + 255) / 256, 256, 0, stream>>>(d_pair4, P, d_seg_dst, H, ob);
+        (*counter)++;
+    }
+    return (int)cudaGetLastError();
+}

@@ -37,6 +37,8 @@ extern "C" int    fep_list_build_pairs(const int* d_iinr, const int* d_gid, cons
                                        const int* d_jjnr, const int* d_excl, const int* d_cscan, int e0, int E, int j0, int P,
                                        int4* d_ent4, int4* d_pair4, int* d_keys, int* d_head, int* d_hscan, void* d_tmp,
                                        size_t tmp_bytes, cudaStream_t stream, long long* counter);
+extern "C" int    fep_launch_tag_owners(int4* d_pair4, int P, int4* d_seg_dst, int H, const int* slot_bound, int nranks,
+                                        cudaStream_t stream, long long* counter);
 extern "C" int    fep_list_build_slots(const int4* d_ent4, int4* d_pair4, const int* d_head, const int* d_hscan, int P, int H,
                                        int nT, int ngrp, int* d_keys, int* d_keys_out, int* d_vals, int* d_vals_out,
                                        int* d_seg_shift, int* d_seg_gid, int* d_warp_hbase, int4* d_seg_dst, int* d_atom_ptr,
@@ -237,6 +239,18 @@ struct fepb200_ctx
     PinnedArray<unsigned char> h_step_in, h_result;
     size_t res_f64_bytes = 0, res_f32_bytes = 0;
     unsigned char* res_target = nullptr; /* where the epilogue writes; nullptr = own result block */
+
+    /* peer exchange (fepb200_set_peer_exchange): the list is evaluated by x_nranks GPUs, this one
+     * takes a range of pairs and owns a range of atoms */
+    bool           px_on = false;
+    int            x_nranks = 1, x_rank = 0;
+    int            x_range_pairs = 0;   /* pairs per rank, rounded up (same on every rank) */
+    int            x_pair_begin = 0, x_pair_end = 0, x_atom_begin = 0, x_atom_end = 0;
+    int            x_slot_bound[FEP_XMAX + 1] = {}; /* first scatter slot owned by each rank */
+    unsigned int   x_seq = 0;
+    unsigned char* x_base[FEP_XMAX] = {};
+    size_t         x_bytes = 0; /* size of each rank's exchange buffer */
+    size_t         x_off_fsorted = 0, x_off_fshift = 0, x_off_ev2 = 0, x_off_cta = 0, x_off_for = 0, x_slot_bytes = 0;
 };
 
 namespace
@@ -347,6 +361,14 @@ int prepare_buffers(fepb200_ctx* c)
     k.n_points = np;
     int sms    = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    /* the pairs this context evaluates: all of its list, or its share of it (peer exchange); every
+     * launch size below follows from `range`, which is the same on all ranks of an exchange */
+    const int range = c->px_on ? c->x_range_pairs : k.n_pairs;
+    k.pair_begin    = c->px_on ? c->x_pair_begin : 0;
+    k.pair_end      = c->px_on ? c->x_pair_end : k.n_pairs;
+    k.part_mult     = c->px_on ? c->x_nranks : 1;
+    k.part_rank     = c->px_on ? c->x_rank : 0;
+    k.n_cta         = (range + FEP_CTA - 1) / FEP_CTA;
     c->foreign_mode = -1;
     if (c->softcore == FEP_SC_BEUTLER && !k.pot_switch)
     {
@@ -366,7 +388,7 @@ int prepare_buffers(fepb200_ctx* c)
             c->foreign_mode = same ? 1 : 2;
         }
         /* one launch per chunk; split the points only when the pair CTAs alone cannot fill the GPU */
-        const long long pair_ctas = (k.n_pairs + FEP_FB_CTA - 1) / FEP_FB_CTA;
+        const long long pair_ctas = (range + FEP_FB_CTA - 1) / FEP_FB_CTA;
         int             want      = 1;
         if (pair_ctas > 0 && pair_ctas < 2LL * sms)
         {
@@ -377,10 +399,10 @@ int prepare_buffers(fepb200_ctx* c)
         /* one wave: as many pair tiles as CTAs can be resident */
         auto tiles = [&](long long ctas_per_sm, int& tile_pairs, int& n_tiles) {
             const long long target     = (long long)sms * ctas_per_sm;
-            long long       per_thread = ((long long)k.n_pairs + target * FEP_FB_CTA - 1) / (target * FEP_FB_CTA);
+            long long       per_thread = ((long long)range + target * FEP_FB_CTA - 1) / (target * FEP_FB_CTA);
             per_thread                 = std::max(1LL, std::min(per_thread, 32LL));
             tile_pairs                 = (int)per_thread * FEP_FB_CTA;
-            n_tiles                    = (k.n_pairs + tile_pairs - 1) / tile_pairs;
+            n_tiles                    = (range + tile_pairs - 1) / tile_pairs;
         };
         /* fuse pass + foreign when the list is too small to fill the GPU anyway */
         k.fuse_pass_and_foreign = pair_ctas < 16LL * sms;
@@ -389,9 +411,9 @@ int prepare_buffers(fepb200_ctx* c)
             k.fuse_pass_and_foreign = std::atoi(env) != 0;
         }
         /* occupancy of the very kernels the step will launch (cudaOccupancyMaxActiveBlocksPerMultiprocessor) */
-        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign),
+        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign, c->px_on),
               k.tile_pairs, k.n_tiles);
-        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1), k.pass_tile_pairs, k.pass_n_tiles);
+        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1, c->px_on), k.pass_tile_pairs, k.pass_n_tiles);
     }
     else
     {
@@ -402,11 +424,32 @@ int prepare_buffers(fepb200_ctx* c)
         /* pair tiles: enough CTAs to fill the GPU several times over, but several pairs per thread
          * on large lists to amortise the final reduction */
         const long long target_ctas = 8LL * sms;
-        long long       per_thread  = ((long long)k.n_pairs * k.n_chunks + target_ctas * FEP_CTA - 1)
+        long long       per_thread  = ((long long)range * k.n_chunks + target_ctas * FEP_CTA - 1)
                                / (target_ctas * FEP_CTA);
         per_thread   = std::max(1LL, std::min(per_thread, 8LL));
         k.tile_pairs = (int)per_thread * FEP_CTA;
-        k.n_tiles    = (k.n_pairs + k.tile_pairs - 1) / k.tile_pairs;
+        k.n_tiles    = (range + k.tile_pairs - 1) / k.tile_pairs;
+    }
+    if (c->px_on)
+    {
+        /* carve one exchange slot: [fsorted | fshift_sorted | ev2 | cta_part | for_part], every part
+         * 256-byte aligned; identical on all ranks because every input of the sizes is */
+        auto         up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t P       = (size_t)k.n_pairs, H = (size_t)k.n_segments, nr = (size_t)c->x_nranks;
+        const size_t n_parts = nr * (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1));
+        c->x_off_fsorted     = 0;
+        c->x_off_fshift      = c->x_off_fsorted + up((P + H) * sizeof(float4));
+        c->x_off_ev2         = c->x_off_fshift + up(H * sizeof(float4));
+        c->x_off_cta         = c->x_off_ev2 + up(H * sizeof(float2));
+        c->x_off_for         = c->x_off_cta + up(2 * n_parts * sizeof(double));
+        c->x_slot_bytes      = c->x_off_for + up(3 * (size_t)np * nr * (size_t)std::max(k.n_tiles, 1) * sizeof(double));
+        if (2 * c->x_slot_bytes + 256 > c->x_bytes)
+        {
+            return fail(c, FEPB200_ERR_STATE,
+                        "peer exchange buffers are too small for this list / number of lambda points (%zu bytes needed, "
+                        "%zu given): call fepb200_set_peer_exchange() again",
+                        2 * c->x_slot_bytes + 256, c->x_bytes);
+        }
     }
 
     CU_CHECK(c, c->d_pts.reserve(np));
@@ -1354,6 +1397,8 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     lap("buffers");
 
     KernelArgs& k = c->ka;
+    c->px_on      = false; /* a new list has a new slot layout: the peer exchange must be set up again */
+    k.px          = PeerExchange{};
     k.n_pairs     = P;
     k.n_entries   = E;
     k.n_segments  = H;
@@ -1684,6 +1729,36 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
         c->result_on_host = true;
     }
     c->zc_next = false;
+    if (c->px_on)
+    {
+        /* the exchange slot of this step on every rank; all ranks launch in lockstep, so they agree
+         * on the sequence number.  Two alternating slots: a rank that runs ahead writes the other one
+         * and cannot come back to this one before every rank has announced the next step. */
+        const unsigned int seq  = ++c->x_seq;
+        const size_t       so   = (size_t)(seq & 1u) * c->x_slot_bytes;
+        PeerExchange&      px   = ka_step.px;
+        px.nranks               = c->x_nranks;
+        px.rank                 = c->x_rank;
+        px.atom_begin           = c->x_atom_begin;
+        px.atom_end             = c->x_atom_end;
+        px.seq                  = seq;
+        for (int r = 0; r < c->x_nranks; r++)
+        {
+            unsigned char* b    = c->x_base[r] + so;
+            px.fsorted[r]       = reinterpret_cast<float4*>(b + c->x_off_fsorted);
+            px.fshift_sorted[r] = reinterpret_cast<float4*>(b + c->x_off_fshift);
+            px.ev2[r]           = reinterpret_cast<float2*>(b + c->x_off_ev2);
+            px.cta_part[r]      = reinterpret_cast<double*>(b + c->x_off_cta);
+            px.for_part[r]      = reinterpret_cast<double*>(b + c->x_off_for);
+            px.flags[r]         = reinterpret_cast<unsigned int*>(c->x_base[r] + 2 * c->x_slot_bytes);
+        }
+        /* what the epilogue of this rank reads */
+        ka_step.fsorted       = px.fsorted[c->x_rank];
+        ka_step.fshift_sorted = px.fshift_sorted[c->x_rank];
+        ka_step.ev2           = px.ev2[c->x_rank];
+        ka_step.cta_part      = px.cta_part[c->x_rank];
+        ka_step.for_part      = px.for_part[c->x_rank];
+    }
     const int err = fep_launch_step(&ka_step, c->softcore, c->elec_ewald, sf, stream, &c->launches,
                                     c->profiling ? c->ev_prof : nullptr, &c->cur, c->pts.data(), c->foreign_mode,
                                     c->side_stream, c->fork_ev, c->join_ev);
@@ -1796,6 +1871,166 @@ int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks,
     return FEPB200_OK;
 }
 
+/* back to the plain single-GPU path: owner bits cleared, launch geometry of the whole list */
+static int peer_exchange_off(fepb200_ctx* c)
+{
+    c->px_on    = false;
+    c->x_nranks = 1;
+    c->x_rank   = 0;
+    const int bound[FEP_XMAX + 1] = {};
+    const int err = fep_launch_tag_owners(c->d_pair4.ptr, c->ka.n_pairs, c->d_seg_dst.ptr, c->ka.n_segments, bound, 1,
+                                          c->stream, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "owner tagging failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    const int rc = prepare_buffers(c);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    if (!c->pts.empty())
+    {
+        return upload_points(c);
+    }
+    return FEPB200_OK;
+}
+
+size_t fepb200_exchange_bytes(const fepb200_ctx* c, int nranks)
+{
+    if (!c || !c->have_list || nranks < 1 || nranks > FEP_XMAX)
+    {
+        return 0;
+    }
+    /* upper bound that does not depend on the launch geometry: at most one CTA per 128 pairs of a
+     * rank's range, room for 32 lambda points (or the current number if larger) */
+    auto            up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t    P       = (size_t)c->ka.n_pairs, H = (size_t)c->ka.n_segments;
+    const long long n_warps = ((long long)P + 31) / 32;
+    const long long wpr     = (n_warps + nranks - 1) / nranks;
+    const size_t    ctas    = (size_t)nranks * (size_t)((wpr * 32 + 127) / 128 + 1);
+    const size_t    np      = (size_t)std::max(c->layout.nforeign + 1, 32);
+    const size_t    slot    = up((P + H) * sizeof(float4)) + up(H * sizeof(float4)) + up(H * sizeof(float2))
+                        + up(2 * ctas * sizeof(double)) + up(3 * np * ctas * sizeof(double));
+    return 2 * slot + 256;
+}
+
+int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const* d_peer_bufs, size_t bytes)
+{
+    if (!c || !c->have_list)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_peer_exchange: no list has been set");
+    }
+    if (nranks < 1 || nranks > FEP_XMAX || rank < 0 || rank >= nranks || (nranks > 1 && !d_peer_bufs))
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_peer_exchange: bad arguments (at most %d ranks)", FEP_XMAX);
+    }
+    if (c->layout.nri != c->layout.nri_total)
+    {
+        return fail(c, FEPB200_ERR_STATE,
+                    "fepb200_set_peer_exchange: every rank must hold the full list (fepb200_set_list with rank 0 of 1)");
+    }
+    cudaSetDevice(c->device);
+    close_chain(c);
+    KernelArgs& k = c->ka;
+    const int   P = k.n_pairs, H = k.n_segments, nT = k.n_touched;
+    if ((long long)P + H >= (1LL << FEP_X_OWNER_SHIFT))
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "fepb200_set_peer_exchange: more than 2^%d force contributions", FEP_X_OWNER_SHIFT);
+    }
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (nranks == 1)
+    {
+        return peer_exchange_off(c);
+    }
+    for (int r = 0; r < nranks; r++)
+    {
+        if (!d_peer_bufs[r] || (reinterpret_cast<size_t>(d_peer_bufs[r]) & 255) != 0)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_peer_exchange: buffer %d is NULL or not 256-byte aligned", r);
+        }
+    }
+    int bound[FEP_XMAX + 1] = {};
+    c->px_on                = true;
+    c->x_nranks             = nranks;
+    c->x_rank               = rank;
+    {
+        for (int r = 0; r < nranks; r++)
+        {
+            c->x_base[r] = static_cast<unsigned char*>(d_peer_bufs[r]);
+        }
+        c->x_bytes = bytes;
+        /* pairs: equal shares of the 32-pair warps of the flat pair space (an i-entry may straddle
+         * two ranks: its segments are separate contributions anyway) */
+        const long long n_warps = ((long long)P + 31) / 32;
+        const long long wpr     = (n_warps + nranks - 1) / nranks;
+        c->x_range_pairs        = (int)(wpr * 32);
+        c->x_pair_begin         = (int)std::min<long long>((long long)rank * wpr * 32, P);
+        c->x_pair_end           = (int)std::min<long long>((long long)(rank + 1) * wpr * 32, P);
+        /* atoms: contiguous ranges with equal shares of the force contributions */
+        std::vector<int> atom_ptr((size_t)nT + 1, 0);
+        if (nT > 0)
+        {
+            CU_CHECK(c, cudaMemcpy(atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost));
+        }
+        const long long total = (long long)P + H;
+        int             a_of[FEP_XMAX + 1];
+        a_of[0]      = 0;
+        a_of[nranks] = nT;
+        for (int r = 1; r < nranks; r++)
+        {
+            const int target = (int)(total * r / nranks);
+            a_of[r] = (int)(std::lower_bound(atom_ptr.begin(), atom_ptr.begin() + nT, target) - atom_ptr.begin());
+            a_of[r] = std::max(a_of[r], a_of[r - 1]);
+        }
+        for (int r = 0; r <= nranks; r++)
+        {
+            bound[r]           = atom_ptr[a_of[r]];
+            c->x_slot_bound[r] = bound[r];
+        }
+        c->x_atom_begin = a_of[rank];
+        c->x_atom_end   = a_of[rank + 1];
+    }
+    /* the owner rank goes into the top bits of every scatter slot (all zero when the exchange is off) */
+    const int err = fep_launch_tag_owners(c->d_pair4.ptr, P, c->d_seg_dst.ptr, H, bound, nranks, c->stream, &c->launches);
+    if (err != 0)
+    {
+        c->px_on = false;
+        return fail(c, FEPB200_ERR_CUDA, "owner tagging failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    c->x_seq = 0;
+    int rc   = prepare_buffers(c);
+    if (rc != FEPB200_OK)
+    {
+        const std::string why = c->error;
+        peer_exchange_off(c);
+        c->error = why;
+        return rc;
+    }
+    /* forces of atoms other ranks own are never written here: keep them zero */
+    CU_CHECK(c, cudaMemsetAsync(c->d_result.ptr, 0, c->res_f64_bytes + c->res_f32_bytes, c->stream));
+    std::memset(c->h_result.ptr, 0, c->res_f64_bytes + c->res_f32_bytes);
+    if (!c->pts.empty() && (rc = upload_points(c)) != FEPB200_OK)
+    {
+        return rc;
+    }
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    return FEPB200_OK;
+}
+
+int fepb200_peer_ranges(const fepb200_ctx* c, int* pair_begin, int* pair_end, int* atom_begin, int* atom_end)
+{
+    if (!c || !c->have_list)
+    {
+        return fail(const_cast<fepb200_ctx*>(c), FEPB200_ERR_STATE, "no list has been set");
+    }
+    if (pair_begin) *pair_begin = c->px_on ? c->x_pair_begin : 0;
+    if (pair_end) *pair_end = c->px_on ? c->x_pair_end : c->ka.n_pairs;
+    if (atom_begin) *atom_begin = c->px_on ? c->x_atom_begin : 0;
+    if (atom_end) *atom_end = c->px_on ? c->x_atom_end : c->ka.n_touched;
+    return FEPB200_OK;
+}
+
 int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double* Vc, double* Vv, double* dvdl,
                      double* foreign_energy, double* foreign_dvdl)
 {
@@ -1821,8 +2056,20 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
     /* Pipelined: the fp64 block and the compact forces come back in chunks, each followed by an
      * event; the host scatter-adds chunk k while the DMA of chunk k+1 runs. */
     const int    nT      = l.ntouched;
-    const int    nchunks = (sf.force && nT > 32768) ? c_copy_chunks : 1;
+    /* peer exchange: this rank holds the forces of the atoms it owns (and all scalars) */
+    const int    ka0     = c->px_on ? c->x_atom_begin : 0;
+    const int    ka1     = c->px_on ? c->x_atom_end : nT;
+    const int    nA      = ka1 - ka0;
+    const int    nchunks = (sf.force && nA > 32768) ? c_copy_chunks : 1;
     const size_t f32_off = c->res_f64_bytes;
+    if (c->px_on && !c->result_on_host)
+    {
+        /* fp64 block and shift forces, then the owned force range in chunks */
+        CU_CHECK(c, cudaMemcpyAsync(c->h_result.ptr, c->d_result.ptr, f32_off, cudaMemcpyDeviceToHost, c->stream));
+        const size_t so = f32_off + sizeof(float) * (size_t)l.off_fshift;
+        CU_CHECK(c, cudaMemcpyAsync(c->h_result.ptr + so, c->d_result.ptr + so, sizeof(float) * 3 * FEP_NUM_SHIFT,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    }
     {
         size_t done = 0;
         for (int ch = 0; ch < nchunks; ch++)
@@ -1830,10 +2077,15 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
             size_t upto = f32_off;
             if (sf.force)
             {
-                const int k1 = (int)((long long)nT * (ch + 1) / nchunks);
-                upto         = (ch == nchunks - 1) ? f32_off + c->res_f32_bytes : f32_off + sizeof(float) * 3 * (size_t)k1;
+                const int k1 = ka0 + (int)((long long)nA * (ch + 1) / nchunks);
+                upto         = (ch == nchunks - 1 && !c->px_on) ? f32_off + c->res_f32_bytes
+                                                                : f32_off + sizeof(float) * 3 * (size_t)k1;
             }
-            if (!c->result_on_host)
+            if (c->px_on && ch == 0)
+            {
+                done = f32_off + sizeof(float) * 3 * (size_t)ka0;
+            }
+            if (!c->result_on_host && upto > done)
             {
                 CU_CHECK(c, cudaMemcpyAsync(c->h_result.ptr + done, c->d_result.ptr + done, upto - done,
                                             cudaMemcpyDeviceToHost, c->stream));
@@ -1856,7 +2108,7 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
         const int* t = c->touched.data();
         for (int ch = 0; ch < nchunks; ch++)
         {
-            const int k0 = (int)((long long)nT * ch / nchunks), k1 = (int)((long long)nT * (ch + 1) / nchunks);
+            const int k0 = ka0 + (int)((long long)nA * ch / nchunks), k1 = ka0 + (int)((long long)nA * (ch + 1) / nchunks);
             CU_CHECK(c, cudaEventSynchronize(c->ev_copy[ch]));
             lap_us(c, 4);
 #pragma omp parallel for schedule(static) num_threads(host_threads(k1 - k0)) if (k1 - k0 > c_host_grain)

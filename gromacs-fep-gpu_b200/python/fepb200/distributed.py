@@ -1,12 +1,17 @@
-"""Multi-GPU driver of the perturbed-pair path: one process per GPU, the FEP pair list split by
-i-entry over the ranks (shard.py), coordinates and parameters replicated, and two collectives per
-step over NCCL/NVLink:
+"""Multi-GPU driver of the perturbed-pair path: one process per GPU, the FEP pair list split over
+the ranks, coordinates and parameters replicated.  Three ways to combine the ranks' results
+(SURVEY.md section 8e), selected by ShardedFep.reduction:
 
-  * forces + shift forces: sum of the fp32 result block [3*nTouched + 135] -- every rank
-    numbers the touched atoms identically, so the blocks add up element by element;
-  * Vc/Vvdw per energy-group pair, dV/dlambda, foreign energies: sum of the small fp64 block.
-Both sums are done by ONE kernel of libfepb200 over NVLink peer memory (ShardedFep.reduction ==
-"p2p"), or by two ncclAllReduce calls ("nccl").
+  "fused" (default): no separate collective.  Every rank holds the layout of the full list and
+      evaluates its share of the pairs; the pair kernels store each force contribution over NVLink
+      straight into the atom-sorted buffer of the rank that owns the receiving atom, the small
+      scalar inputs go to every rank, and after a cross-GPU barrier inside the epilogue kernel each
+      rank sums the atoms it owns (forces: reduce-scatter) and all scalars (all-reduce).
+      fepb200_set_peer_exchange().
+  "p2p":  the list is split by i-entry (shard.py), every rank computes a full result block for its
+      shard and ONE kernel of libfepb200 sums all blocks over NVLink peer memory
+      (fepb200_reduce_peers; all ranks get everything).
+  "nccl": same split, two ncclAllReduce calls on zero-copy views of the result block.
 
 torch.distributed is plumbing only (process group, NCCL communicator, stream); the tensors it
 reduces are zero-copy views of the library's device result block.
@@ -40,7 +45,10 @@ def result_tensors(ctx: FepContext) -> tuple[torch.Tensor, torch.Tensor]:
 class ShardedFep:
     """The per-rank object: holds this rank's shard and reduces results over the group.
 
-    reduction = "p2p" (default when available): every rank publishes its result block in
+    reduction = "fused" (default when available): see the module docstring; step() returns the
+    forces of the atoms this rank owns (zeros elsewhere: the sum over ranks is the full force array)
+    and the full scalars on every rank.
+    reduction = "p2p": every rank publishes its result block in
     symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations every rank of the
     node has mapped over NVLink), passes a device-side barrier, and libfepb200's own kernel reads
     all blocks through the peer pointers and sums them in rank order (fepb200_reduce_peers).
@@ -55,13 +63,22 @@ class ShardedFep:
         # are ordered without host synchronisation
         self.stream = torch.cuda.Stream(device)
         self.ctx.set_stream(self.stream.cuda_stream)
-        self.ctx.set_problem(problem, rank=rank, nranks=world)
-        self.f32, self.f64 = result_tensors(self.ctx)
         self.reduction = "none"
         self._p2p_error = None  # why symmetric memory was not used, if it was asked for
         self._step = 0
-        if world > 1:
-            want = reduction or os.environ.get("FEPB200_REDUCTION", "p2p")
+        want = (reduction or os.environ.get("FEPB200_REDUCTION", "fused")) if world > 1 else "none"
+        if want == "fused":
+            try:
+                self.ctx.set_problem(problem)  # the full list on every rank
+                self._setup_fused(device)
+                self.reduction = "fused"
+            except Exception as exc:  # no symmetric memory on this system
+                self._p2p_error = repr(exc)
+                want = "p2p"
+        if self.reduction != "fused":
+            self.ctx.set_problem(problem, rank=rank, nranks=world)
+        self.f32, self.f64 = result_tensors(self.ctx)
+        if world > 1 and self.reduction != "fused":
             self.reduction = "nccl"
             if want == "p2p":
                 try:
@@ -69,6 +86,22 @@ class ShardedFep:
                     self.reduction = "p2p"
                 except Exception as exc:  # no symmetric memory on this system: NCCL does the same job
                     self._p2p_error = repr(exc)
+
+    def _setup_fused(self, device: int) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = self.group if self.group is not None else dist.group.WORLD
+        nbytes = (self.ctx.exchange_bytes(self.world) + 4095) // 4096 * 4096
+        with torch.cuda.stream(self.stream):
+            # two exchange slots + the barrier's sequence flags, zero before anybody announces a step
+            self._sym = symm_mem.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", device))
+            self._sym.zero_()
+            self._hdl = symm_mem.rendezvous(self._sym, group)
+            self._hdl.barrier(channel=0)
+        self.stream.synchronize()
+        self.ctx.set_peer_exchange(self.world, self.rank, [int(p) for p in self._hdl.buffer_ptrs], nbytes)
+        self.exchange_bytes = nbytes
 
     def _setup_p2p(self, device: int) -> None:
         import torch.distributed as dist
@@ -91,6 +124,9 @@ class ShardedFep:
 
     def launch(self, flags: int) -> None:
         """Kernels of this rank's shard, then the reduction over ranks, all asynchronous on self.stream."""
+        if self.reduction == "fused":
+            self.ctx.launch(flags)  # the exchange is part of the pair kernels and the epilogue
+            return
         if self.reduction == "p2p":
             k = self._step & 1
             self._step += 1
@@ -109,7 +145,8 @@ class ShardedFep:
                 dist.all_reduce(self.f32, group=self.group)
 
     def step(self, x, shiftvec, flags: int, out: dict | None = None) -> dict:
-        """Host buffers in, reduced host buffers out (every rank receives the full result)."""
+        """Host buffers in, reduced host buffers out ("fused": the forces of the atoms this rank owns and
+        all scalars; "p2p" / "nccl": every rank receives the full result)."""
         self.ctx.upload_x(x, shiftvec)
         self.launch(flags)
         return self.ctx.download(flags, out)

@@ -17,7 +17,7 @@ import numpy as np
 from .params import CParams, NUM_LAMBDA_COMPONENTS, NUM_SHIFT_VECTORS
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libfepb200.so"))
+LIB_PATH = os.environ.get("FEPB200_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libfepb200.so"))
 
 _FP = ctypes.POINTER(ctypes.c_float)
 _DP = ctypes.POINTER(ctypes.c_double)
@@ -75,6 +75,9 @@ SYMBOLS = {
     "fepb200_set_partial_result_block": (ctypes.c_int, [_VP, _VP]),
     "fepb200_reduce_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int,
                                             ctypes.c_uint]),
+    "fepb200_exchange_bytes": (ctypes.c_size_t, [_VP, ctypes.c_int]),
+    "fepb200_set_peer_exchange": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_VP), ctypes.c_size_t]),
+    "fepb200_peer_ranges": (ctypes.c_int, [_VP, _IP, _IP, _IP, _IP]),
     "fepb200_download": (ctypes.c_int, [_VP, ctypes.c_int, _FP, _FP, _DP, _DP, _DP, _DP, _DP]),
     "fepb200_launch_count": (ctypes.c_longlong, [_VP]),
     "fepb200_last_launch_ms": (ctypes.c_int, [_VP, _FP]),
@@ -111,6 +114,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         )
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in SYMBOLS.items():
+        if os.environ.get("FEPB200_LIB") and not hasattr(lib, name):
+            continue  # A/B timing against an older build of the library (tools/): newer entry points are absent
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
@@ -335,3 +340,17 @@ class FepContext:
         arr = (_VP * len(peer_blocks))(*[_VP(p) for p in peer_blocks])
         flg = (_VP * len(peer_flags))(*[_VP(p) for p in peer_flags]) if peer_flags else None
         self._check(self._lib.fepb200_reduce_peers(self._h, len(peer_blocks), arr, flg, int(rank), int(seq) & 0xFFFFFFFF))
+
+    # ---- fused peer exchange (pair kernels scatter over NVLink, every rank sums its atoms) ----
+    def exchange_bytes(self, nranks: int) -> int:
+        return int(self._lib.fepb200_exchange_bytes(self._h, int(nranks)))
+
+    def set_peer_exchange(self, nranks: int, rank: int, peer_bufs: list[int] | None, nbytes: int = 0) -> None:
+        arr = (_VP * len(peer_bufs))(*[_VP(p) for p in peer_bufs]) if peer_bufs else None
+        self._check(self._lib.fepb200_set_peer_exchange(self._h, int(nranks), int(rank), arr, int(nbytes)))
+
+    def peer_ranges(self) -> tuple[int, int, int, int]:
+        """(pair_begin, pair_end, atom_begin, atom_end) of this context."""
+        v = [ctypes.c_int(0) for _ in range(4)]
+        self._check(self._lib.fepb200_peer_ranges(self._h, *[ctypes.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)

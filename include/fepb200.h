@@ -233,6 +233,37 @@ int    fepb200_set_partial_result_block(fepb200_ctx* ctx, void* d_block);
 int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags,
                             int rank, unsigned int seq);
 
+/* ---- multi-GPU, fused: the pair kernels scatter over NVLink, every rank sums its own atoms -----
+ * The force reduce-scatter and the scalar all-reduce of SURVEY 8e without a separate collective
+ * (replaces what the reference does with per-thread buffers + ThreadedForceBuffer::reduce,
+ * threaded_force_buffer.cpp:320-402, across GPUs instead of across OpenMP threads):
+ *   1. every rank calls fepb200_set_list() with the FULL list (rank 0 of 1), so that all ranks
+ *      hold the same atom-sorted slot layout;
+ *   2. every rank allocates fepb200_exchange_bytes() bytes of zero-initialised memory that all
+ *      ranks of the node have mapped (CUDA VMM / symmetric memory), and calls
+ *      fepb200_set_peer_exchange() with the device pointers of ALL ranks' buffers in rank order;
+ *   3. from then on fepb200_launch() / fepb200_compute() of rank r evaluates the r-th share of the
+ *      32-pair warps of the flat pair space; its pair kernels store each force contribution
+ *      directly into the atom-sorted buffer of the rank that owns the receiving atom (contiguous
+ *      atom ranges with equal numbers of contributions), and the segment shift forces / energies
+ *      and per-CTA dV/dlambda and foreign-energy partials into every rank's buffer.  The epilogue
+ *      first passes a cross-GPU barrier (sequence flags in the exchange buffers), then sums what
+ *      arrived: forces of the atoms this rank owns (entries of all other atoms in the result block
+ *      stay zero), and ALL scalars (shift forces, Vc/Vv, dV/dlambda, foreign energies) on every
+ *      rank.  Forces and the job-reduced scalars are bit-identical to the single-GPU result
+ *      (same slots, same summation order).
+ * All ranks must call fepb200_launch()/fepb200_compute() the same number of times (lockstep); a
+ * rank that waits more than 4 s for a peer traps.  fepb200_download()/fepb200_compute() add the
+ * owned atoms' forces and the full scalars into the caller's arrays: sum the force arrays over
+ * ranks (or keep them distributed), take the scalars from one rank.
+ * nranks == 1 (d_peer_bufs may be NULL) switches the exchange off.  fepb200_set_list() switches it
+ * off as well: call fepb200_set_peer_exchange() again after every search step. */
+size_t fepb200_exchange_bytes(const fepb200_ctx* ctx, int nranks);
+int    fepb200_set_peer_exchange(fepb200_ctx* ctx, int nranks, int rank, void* const* d_peer_bufs, size_t bytes);
+/* The pairs [pair_begin, pair_end) of the flat pair space this context evaluates and the compact
+ * atoms [atom_begin, atom_end) (indices into fepb200_touched_atoms()) it owns; any pointer may be NULL. */
+int    fepb200_peer_ranges(const fepb200_ctx* ctx, int* pair_begin, int* pair_end, int* atom_begin, int* atom_end);
+
 /* Copy the result block to the host and add it into the caller's arrays (same
  * semantics as the tail of fepb200_compute).  Synchronous. */
 int fepb200_download(fepb200_ctx* ctx, int flags, float* f, float* fshift, double* Vc, double* Vv,

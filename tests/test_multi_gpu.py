@@ -1,5 +1,8 @@
-"""The N>1 path on real GPUs: one process per GPU, NCCL all-reduce of the result block.  Skipped
-when the box has a single GPU (the host-side logic is covered on CPU by test_sharding_cpu.py)."""
+"""The N>1 path on real GPUs: one process per GPU; "fused" = the pair kernels scatter over NVLink
+and every rank sums the atoms it owns (fepb200_set_peer_exchange), "p2p" = one reduction kernel over
+peer memory, "nccl" = ncclAllReduce of the result block.  Skipped when the box has a single GPU (the
+fused exchange then runs with several contexts on one device, test_gpu_peer_exchange.py; the
+host-side logic is covered on CPU by test_sharding_cpu.py)."""
 import os
 import socket
 import sys
@@ -42,8 +45,20 @@ def _worker(rank, world, port, root, result_file, reduction):
     out = sh.step(prob.x, prob.shiftvec, flags)
     out2 = sh.step(prob.x, prob.shiftvec, flags | P.CLEAR_OUTPUTS, out={k: v.copy() for k, v in out.items()})
     want = oracle.run_best(prob, flags)
-    rms = np.sqrt(np.mean((out["f"] - want["f"]) ** 2) / np.mean(want["f"] ** 2))
-    ok = rms < 1e-5 and int(lay.nri_total) == prob.nblist.nri and 0 < int(lay.nri) < prob.nblist.nri
+    f_full = out["f"]
+    if used == "fused":
+        # every rank returns the forces of the atoms it owns: the sum over ranks is the force array
+        p0, p1, a0, a1 = sh.ctx.peer_ranges()
+        owned = np.zeros(prob.natoms, bool)
+        owned[sh.ctx.touched_atoms()[a0:a1]] = True
+        split_ok = 0 < p1 - p0 < prob.nblist.nrj and 0 < a1 - a0 and not np.any(out["f"][~owned])
+        t = torch.from_numpy(out["f"].copy()).cuda()
+        dist.all_reduce(t)
+        f_full = t.cpu().numpy()
+    else:
+        split_ok = 0 < int(lay.nri) < prob.nblist.nri
+    rms = np.sqrt(np.mean((f_full - want["f"]) ** 2) / np.mean(want["f"] ** 2))
+    ok = rms < 1e-5 and int(lay.nri_total) == prob.nblist.nri and split_ok
     for k in ("Vc", "Vv", "dvdl", "foreign_energy", "foreign_dvdl"):
         scale = np.maximum(np.abs(want[k]), 1e-2 * np.max(np.abs(want[k])))
         ok = ok and bool(np.all(np.abs(out[k] - want[k]) <= 1e-4 * scale))
@@ -57,7 +72,7 @@ def _worker(rank, world, port, root, result_file, reduction):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("reduction", ["p2p", "nccl"])
+@pytest.mark.parametrize("reduction", ["fused", "p2p", "nccl"])
 def test_two_ranks_match_oracle(tmp_path, reduction):
     import torch
     import torch.multiprocessing as mp
@@ -71,4 +86,6 @@ def test_two_ranks_match_oracle(tmp_path, reduction):
     assert got.startswith("ok"), got
     if reduction == "nccl":
         assert got == "ok nccl"
+    if reduction == "fused":
+        assert got == "ok fused"  # symmetric memory is available on an NVLink box: no silent downgrade
     print(got)
