@@ -393,6 +393,15 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, args.config)
     else:
+        if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+            # torchrun defaults every rank to ONE OpenMP thread; the library's host-side gather /
+            # scatter of the touched atoms (fepb200_compute) is threaded: give each rank its share
+            # of the host cores (must happen before libgomp is loaded)
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                cores = os.cpu_count() or 1
+            os.environ["OMP_NUM_THREADS"] = str(max(1, min(16, cores // world)))
         run_ours(args, args.config)
 
 

@@ -262,7 +262,7 @@ struct AccLayout
     static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : (NACC > 30 ? 3 : 4);
 };
 
-template<bool EWALD, int MODE, int C, bool FORCE, bool PEER>
+template<bool EWALD, int MODE, int C, bool FORCE>
 __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         fep_beutler_kernel(const __grid_constant__ KernelArgs ka, const __grid_constant__ BeutlerStep bs)
 {
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
             {
                 /* the j atom receives -f: scattered to this pair's own slot in the atom-sorted
                  * buffer (unique destination, no atomics; skipped pairs write their zero) */
-                fep_put_force<PEER>(ka, rec.w, make_float4(-fx, -fy, -fz, 0.0f));
+                ka.fsorted[rec.w] = make_float4(-fx, -fy, -fz, 0.0f);
             }
             /* segmented sum over the lanes of one i-entry: i force and Vc/Vv of the segment */
 #pragma unroll
@@ -572,15 +572,20 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
             }
             if (head)
             {
-                fep_put_segment<PEER>(ka, sd, make_float4(fx, fy, fz, 0.0f), true, bs.want_shift != 0, true,
-                                make_float2(vctot, vvtot));
+                const float4 fi  = make_float4(fx, fy, fz, 0.0f);
+                ka.fsorted[sd.x] = fi;
+                if (bs.want_shift)
+                {
+                    ka.fshift_sorted[sd.y] = fi;
+                }
+                ka.ev2[sd.z] = make_float2(vctot, vvtot);
             }
         }
     }
 
     if (L::NACC == 0)
     {
-        fep_pair_kernel_done<PEER>();
+        fep_pdl_wait();
         return;
     }
     float red[N8];
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     __syncthreads();
     if (FORCE && tid < 2)
     {
-        fep_put_cta_part<PEER>(ka, fep_part_index(ka, tid, bs.n_tiles, blockIdx.x), s_sum[L::iCUR + tid]);
+        ka.cta_part[(size_t)tid * bs.n_tiles + blockIdx.x] = s_sum[L::iCUR + tid];
     }
     if (C > 0 && tid < bs.np)
     {
@@ -620,13 +625,13 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         /* E = lfacC[A] C_A + lfacC[B] C_B + lfacV[A] G_A + lfacV[B] G_B with X_B = X_A + DX */
         const double e = (double)bs.lfc[0][p] * CA + (double)bs.lfc[1][p] * (CA + DC) + (double)bs.lfv[0][p] * GA
                          + (double)bs.lfv[1][p] * (GA + DG);
-        const int row = 3 * (bs.p0 + p);
-        fep_put_for_part<PEER>(ka, fep_part_index(ka, row, bs.n_tiles, blockIdx.x), e);
-        fep_put_for_part<PEER>(ka, fep_part_index(ka, row + 1, bs.n_tiles, blockIdx.x), DC);
-        fep_put_for_part<PEER>(ka, fep_part_index(ka, row + 2, bs.n_tiles, blockIdx.x), DG);
+        const size_t o = (size_t)(3 * (bs.p0 + p)) * bs.n_tiles + blockIdx.x;
+        ka.for_part[o]                  = e;
+        ka.for_part[o + bs.n_tiles]     = DC;
+        ka.for_part[o + 2 * bs.n_tiles] = DG;
     }
     /* nothing here depends on the preceding kernel; completing after it keeps the chain ordered */
-    fep_pair_kernel_done<PEER>();
+    fep_pdl_wait();
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -634,29 +639,12 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 template<bool EWALD, int MODE, int C, bool FORCE>
 static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream, int* occ, bool chained)
 {
-    /* the peer-exchange variant (stores through the peers' pointers, system-scope fence at the end)
-     * is a separate instantiation: the single-GPU code carries none of it */
-    const bool peer = ka.px.nranks > 1;
     if (occ)
     {
-        if (peer)
-        {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, FEP_FB_CTA, 0);
-        }
-        else
-        {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE, false>, FEP_FB_CTA, 0);
-        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE>, FEP_FB_CTA, 0);
         return;
     }
-    if (peer)
-    {
-        fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
-    }
-    else
-    {
-        fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE, false>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
-    }
+    fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
 }
 
 template<bool EWALD, int MODE, bool FORCE>
@@ -719,10 +707,9 @@ extern "C" int fep_beutler_chunk_size(int n_points, int n_chunks_wanted)
 }
 
 /* resident CTAs per SM of the kernel instantiation a launch would use (for one-wave tile sizing) */
-extern "C" int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int c, int force, int peer)
+extern "C" int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int c, int force)
 {
     KernelArgs  ka{};
-    ka.px.nranks = peer ? 2 : 1;
     BeutlerStep bs{};
     int         occ = 0;
     bool        ok;

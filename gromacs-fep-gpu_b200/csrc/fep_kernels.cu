@@ -105,9 +105,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         {
             /* the j atom receives -t: scattered to this pair's own slot in the atom-sorted buffer
              * (unique destination, no atomics; skipped pairs write their zero) */
-            const int    w = __ldg(ka.pair4 + slot).w;
-            const float4 t = make_float4(-fx, -fy, -fz, 0.0f);
-            FEP_PX(ka, fep_put_force<true>(ka, w, t), fep_put_force<false>(ka, w, t));
+            ka.fsorted[__ldg(ka.pair4 + slot).w] = make_float4(-fx, -fy, -fz, 0.0f);
         }
     }
 
@@ -151,10 +149,16 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         const int gw = (ka.pair_begin >> 5) + blockIdx.x * (FEP_CTA / 32) + warp;
         const int h  = __ldg(ka.warp_hbase + gw) + __popc(hmask & ((1u << lane) - 1u));
         const int4 sd = __ldg(ka.seg_dst + h);
-        const float4 fi = make_float4(fx, fy, fz, 0.0f);
-        const float2 e2 = make_float2(vc, vv);
-        FEP_PX(ka, fep_put_segment<true>(ka, sd, fi, FORCE, FORCE && want_shift != 0, true, e2),
-               fep_put_segment<false>(ka, sd, fi, FORCE, FORCE && want_shift != 0, true, e2));
+        if (FORCE)
+        {
+            const float4 fi = make_float4(fx, fy, fz, 0.0f);
+            ka.fsorted[sd.x] = fi;
+            if (want_shift)
+            {
+                ka.fshift_sorted[sd.y] = fi;
+            }
+        }
+        ka.ev2[sd.z] = make_float2(vc, vv);
     }
 
     __syncthreads();
@@ -166,10 +170,9 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         {
             s += (double)s_red[w][tid];
         }
-        const size_t o = fep_part_index(ka, tid, ka.n_cta, blockIdx.x);
-        FEP_PX(ka, fep_put_cta_part<true>(ka, o, s), fep_put_cta_part<false>(ka, o, s));
+        ka.cta_part[(size_t)tid * ka.n_cta + blockIdx.x] = s;
     }
-    FEP_PX(ka, fep_pair_kernel_done<true>(), fep_pair_kernel_done<false>()); /* first kernel of a step: the wait is a no-op */
+    fep_pdl_wait(); /* first kernel of a step: no-op */
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -292,10 +295,9 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
             s += (double)s_red[w][tid];
         }
         const int p = tid / 3, k = tid - 3 * p;
-        const size_t o = fep_part_index(ka, 3 * (p0 + p) + k, ka.n_tiles, blockIdx.x);
-        FEP_PX(ka, fep_put_for_part<true>(ka, o, s), fep_put_for_part<false>(ka, o, s));
+        ka.for_part[((size_t)(3 * (p0 + p) + k)) * ka.n_tiles + blockIdx.x] = s;
     }
-    FEP_PX(ka, fep_pair_kernel_done<true>(), fep_pair_kernel_done<false>()); /* independent of the pass kernel before it */
+    fep_pdl_wait(); /* independent of the pass kernel before it; see fep_types.h */
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -303,7 +305,8 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
 /* ------------------------------------------------------------------------------------------- */
 struct EpilogueLayout
 {
-    int atom_blocks;   /* blocks [0, atom_blocks): per-atom force gather                */
+    int atom_blocks;   /* blocks of the per-atom force sums, FEP_EPI_LANES lanes per atom    */
+    int heavy_blocks;  /* blocks of the heavy atoms' force sums, one warp per atom       */
     int job_begin;     /* first reduction job handled (skips shift jobs when not asked)  */
     int job_blocks;    /* blocks for reduction jobs                                      */
     int scalar_blocks; /* blocks for dvdl (2) + foreign (3*(L+1)) partial arrays         */
@@ -330,12 +333,20 @@ __device__ __forceinline__ double block_sum_d(double v, double* s_buf)
 }
 
 /* Cross-GPU barrier of the peer exchange (fep_types.h), taken by every CTA of the epilogue right
- * after fep_pdl_wait(), i.e. when this rank's pair kernels have completed (their threads fenced
- * their peer stores at system scope before exiting).  Block 0 announces step `seq` in slot `rank`
- * of every peer's flag array; every block waits until all peers' announcements have arrived in the
- * local array.  Exactly one kernel per GPU spins and its producers have already finished, so the
- * spin cannot starve anybody; a peer that never arrives (a rank that did not launch) trips the
+ * after fep_pdl_wait(), i.e. when this rank's pair kernels have completed and their results are in
+ * this rank's exchange slot.  Block 0 publishes them (system-scope fence, then a release store of
+ * the step number `seq` into slot `rank` of every peer's flag array); every block waits until all
+ * peers' announcements have arrived in the local array (acquire loads), after which the peers'
+ * slots may be read.  Exactly one kernel per GPU spins and its producers have already finished, so
+ * the spin cannot starve anybody; a peer that never arrives (a rank that did not launch) trips the
  * time-out and the kernel traps instead of hanging the GPU. */
+__device__ __forceinline__ unsigned long long fep_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
 {
     const int nr = ka.px.nranks;
@@ -359,8 +370,7 @@ __device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
             }
             if ((spins & 1023u) == 1023u)
             {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                const unsigned long long now = fep_globaltimer();
                 if (t0 == 0)
                 {
                     t0 = now;
@@ -375,16 +385,46 @@ __device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
     __syncthreads();
 }
 
-template<bool PEER>
+/* PEER: the exchange of fep_types.h.  STRONG: peer data is read with system-scope strong loads
+ * (ld.volatile) instead of plain loads ordered by the barrier's acquire (FEPB200_PEER_LOAD=strong;
+ * measured slower by far, kept for diagnosis). */
+template<bool PEER, bool STRONG>
 __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_constant__ KernelArgs ka,
                                                                   const EpilogueLayout lay, const StepFlags sf)
 {
-/* data other GPUs wrote into this rank's exchange slot is read at L2 (the point of coherence) */
-#define FEP_EPI_LOAD(ptr) (PEER ? __ldcg(ptr) : __ldcs(ptr))
+/* PEER: element k of a sorted array lives in the exchange slot of the rank that produced it (byte
+ * tables px.*_src).  The loads follow the barrier's acquire (fep_peer_barrier: ld.acquire.sys by
+ * the polling threads, then bar.sync), which orders them after the producers' release. */
+#define FEP_EPI_LOAD(arr, k, src) \
+    (PEER ? (STRONG ? __ldcv(ka.px.arr[src] + (k)) : __ldcs(ka.px.arr[src] + (k))) : __ldcs(ka.arr + (k)))
     __shared__ double s_buf[FEP_EPI_CTA / 32];
     __shared__ bool   s_last;
     const int         tid = threadIdx.x;
     int               b   = blockIdx.x;
+    /* optional trace (fepb200_epilogue_trace): per block the global timer at entry, after the wait
+     * for this rank's pair kernels, after the cross-GPU barrier, and when the block's sums are done */
+    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+    if (PEER && ka.trace)
+    {
+        tr0 = fep_globaltimer();
+    }
+#define FEP_EPI_SYNC_POINT()                  \
+    do                                        \
+    {                                         \
+        fep_pdl_wait();                       \
+        if (PEER)                             \
+        {                                     \
+            if (ka.trace)                     \
+            {                                 \
+                tr1 = fep_globaltimer();      \
+            }                                 \
+            fep_peer_barrier(ka);             \
+            if (ka.trace)                     \
+            {                                 \
+                tr2 = fep_globaltimer();      \
+            }                                 \
+        }                                     \
+    } while (0)
 
     /* offsets into the fp64 result block: Vc[G] Vv[G] dvdl[2] foreign_E[L+1] foreign_dvdl[L+1][2] */
     const int off_vv   = ka.n_gid;
@@ -404,14 +444,17 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         is_job           = true;
         const int    j   = lay.job_begin + b;
         const RedJob job = ka.red_jobs[j];
-        fep_pdl_wait();
-        if (PEER)
-        {
-            fep_peer_barrier(ka);
-        }
-        double       a0 = 0.0, a1 = 0.0, a2 = 0.0;
         /* a job is a contiguous range of at most FEP_RED_CHUNK = PER * CTA elements */
         constexpr int PER = FEP_RED_CHUNK / FEP_EPI_CTA;
+        int           sr[PER]; /* producer rank of this thread's elements: static, fetched before the wait */
+#pragma unroll
+        for (int u = 0; u < PER; u++)
+        {
+            const int k = job.begin + tid + u * FEP_EPI_CTA;
+            sr[u]       = (PEER && k < job.end) ? (job.kind == 0 ? ka.px.fshift_src[k] : ka.px.ev2_src[k]) : 0;
+        }
+        FEP_EPI_SYNC_POINT();
+        double       a0 = 0.0, a1 = 0.0, a2 = 0.0;
         if (job.kind == 0)
         {
             float4 t[PER];
@@ -419,7 +462,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             for (int u = 0; u < PER; u++)
             {
                 const int k = job.begin + tid + u * FEP_EPI_CTA;
-                t[u]        = k < job.end ? FEP_EPI_LOAD(ka.fshift_sorted + k) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                t[u]        = k < job.end ? FEP_EPI_LOAD(fshift_sorted, k, sr[u]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
 #pragma unroll
             for (int u = 0; u < PER; u++)
@@ -436,7 +479,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             for (int u = 0; u < PER; u++)
             {
                 const int k = job.begin + tid + u * FEP_EPI_CTA;
-                t[u]        = k < job.end ? FEP_EPI_LOAD(ka.ev2 + k) : make_float2(0.0f, 0.0f);
+                t[u]        = k < job.end ? FEP_EPI_LOAD(ev2, k, sr[u]) : make_float2(0.0f, 0.0f);
             }
 #pragma unroll
             for (int u = 0; u < PER; u++)
@@ -460,26 +503,52 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         /* b = 0,1: dV/dlambda coul, vdw of the current-lambda pass; b = 2 + 3p + k: point p */
         const double* src;
         int           n;
-        fep_pdl_wait();
-        if (PEER)
-        {
-            fep_peer_barrier(ka);
-        }
-        /* rows of part_mult x (local CTAs) partials, in rank order (fep_part_index) */
+        FEP_EPI_SYNC_POINT();
         if (b < 2)
         {
-            n   = ka.n_parts * ka.part_mult;
-            src = ka.cta_part + (size_t)b * n;
+            src = ka.cta_part + (size_t)b * ka.n_parts;
+            n   = ka.n_parts;
         }
         else
         {
-            n   = ka.n_tiles * ka.part_mult;
-            src = ka.for_part + (size_t)(b - 2) * n;
+            src = ka.for_part + (size_t)(b - 2) * ka.n_tiles;
+            n   = ka.n_tiles;
         }
         double a = 0.0;
-        for (int k = tid; k < n; k += FEP_EPI_CTA)
+        if (PEER)
         {
-            a += PEER ? __ldcg(src + k) : src[k];
+            /* row b of every rank's partial array, ranks in order (all ranks launch the same grids) */
+            const size_t row = b < 2 ? (size_t)b * ka.n_parts : (size_t)(b - 2) * ka.n_tiles;
+            /* four independent (possibly remote) loads in flight per thread, summed in index order */
+            const int total = n * ka.px.nranks;
+            for (int k = tid; k < total; k += 4 * FEP_EPI_CTA)
+            {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int kk = k + u * FEP_EPI_CTA;
+                    v[u]         = 0.0;
+                    if (kk < total)
+                    {
+                        const int     r = kk / n;
+                        const double* q = (b < 2 ? ka.px.cta_part[r] : ka.px.for_part[r]) + row + (kk - r * n);
+                        v[u]            = STRONG ? __ldcv(q) : __ldcs(q);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    a += v[u];
+                }
+            }
+        }
+        else
+        {
+            for (int k = tid; k < n; k += FEP_EPI_CTA)
+            {
+                a += src[k];
+            }
         }
         a = block_sum_d(a, s_buf);
         if (tid == 0)
@@ -502,39 +571,127 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             }
         }
     }
+    else if ((b -= lay.scalar_blocks) < lay.heavy_blocks)
+    {
+        /* atoms with long ranges (the perturbed atoms themselves: hundreds of contributions): one
+         * warp per atom, FEP_HEAVY_LOADS independent loads per lane and trip, so that even over
+         * NVLink the range costs one or two memory round trips instead of one per 32 contributions */
+        const int lane = tid & 31;
+        const int hi   = (PEER ? ka.px.heavy_begin : 0) + b * (FEP_EPI_CTA / 32) + (tid >> 5);
+        const int hend = PEER ? ka.px.heavy_end : ka.n_heavy;
+        int       atom = 0, k0 = 0, k1 = 0;
+        int       sr[FEP_HEAVY_LOADS];
+#pragma unroll
+        for (int u = 0; u < FEP_HEAVY_LOADS; u++)
+        {
+            sr[u] = 0;
+        }
+        if (hi < hend)
+        {
+            atom = __ldg(ka.heavy_atoms + hi);
+            k0   = __ldg(ka.atom_ptr + atom);
+            k1   = __ldg(ka.atom_ptr + atom + 1);
+            if (PEER)
+            {
+#pragma unroll
+                for (int u = 0; u < FEP_HEAVY_LOADS; u++)
+                {
+                    const int k = k0 + lane + 32 * u;
+                    sr[u]       = k < k1 ? ka.px.slot_src[k] : 0;
+                }
+            }
+        }
+        FEP_EPI_SYNC_POINT();
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        for (int k = k0 + lane; k < k1; k += 32 * FEP_HEAVY_LOADS)
+        {
+            float4 t[FEP_HEAVY_LOADS];
+            if (PEER && k != k0 + lane)
+            {
+#pragma unroll
+                for (int u = 0; u < FEP_HEAVY_LOADS; u++)
+                {
+                    sr[u] = (k + 32 * u < k1) ? ka.px.slot_src[k + 32 * u] : 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FEP_HEAVY_LOADS; u++)
+            {
+                t[u] = (k + 32 * u < k1) ? FEP_EPI_LOAD(fsorted, k + 32 * u, sr[u]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < FEP_HEAVY_LOADS; u++)
+            {
+                fx += t[u].x;
+                fy += t[u].y;
+                fz += t[u].z;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            fx += __shfl_xor_sync(FULL_MASK, fx, o);
+            fy += __shfl_xor_sync(FULL_MASK, fy, o);
+            fz += __shfl_xor_sync(FULL_MASK, fz, o);
+        }
+        if (hi < hend && lane < 3)
+        {
+            ka.res_f32[3 * (size_t)atom + lane] = lane == 0 ? fx : (lane == 1 ? fy : fz);
+        }
+    }
     else
     {
         /* FEP_EPI_LANES lanes per touched atom; contributions are visited in ascending index order by
          * lane stride, then combined with a fixed xor tree: deterministic */
-        b -= lay.scalar_blocks;
-        /* PEER: this rank sums the atoms it owns (the forces are reduce-scattered by atom range) */
-        const int atom     = (PEER ? ka.px.atom_begin : 0) + b * (FEP_EPI_CTA / FEP_EPI_LANES) + (tid / FEP_EPI_LANES);
+        b -= lay.heavy_blocks;
+        /* PEER: this rank sums the atoms it owns (the forces are reduce-scattered by atom range);
+         * a remote round trip costs the same for 4 lanes as for 8, and half the threads means half
+         * the waves of blocks */
+        constexpr int LANES = PEER ? FEP_EPI_LANES_PEER : FEP_EPI_LANES;
+        const int atom     = (PEER ? ka.px.atom_begin : 0) + b * (FEP_EPI_CTA / LANES) + (tid / LANES);
         const int atom_end = PEER ? ka.px.atom_end : ka.n_touched;
-        const int sub      = tid % FEP_EPI_LANES;
+        const int sub      = tid % LANES;
         float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
         int       k0 = 0, k1 = 0;
+        int       sr[4] = { 0, 0, 0, 0 }; /* producer ranks of the first trip's elements (static) */
+        bool      mine  = false;
         if (atom < atom_end)
         {
-            k0 = __ldg(ka.atom_ptr + atom);
-            k1 = __ldg(ka.atom_ptr + atom + 1);
+            k0   = __ldg(ka.atom_ptr + atom);
+            k1   = __ldg(ka.atom_ptr + atom + 1);
+            mine = k1 - k0 <= FEP_HEAVY_MIN; /* the others belong to the heavy role above */
+            k1   = mine ? k1 : k0;
+            if (PEER)
+            {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int k = k0 + sub + LANES * u;
+                    sr[u]       = k < k1 ? ka.px.slot_src[k] : 0;
+                }
+            }
         }
-        fep_pdl_wait();
-        if (PEER)
-        {
-            fep_peer_barrier(ka);
-        }
+        FEP_EPI_SYNC_POINT();
         if (atom < atom_end)
         {
             /* the atom's contributions are contiguous in fsorted: the lanes stream them, four
              * independent 16-byte loads per lane and trip (most atoms need a single trip) */
-            for (int k = k0 + sub; k < k1; k += 4 * FEP_EPI_LANES)
+            for (int k = k0 + sub; k < k1; k += 4 * LANES)
             {
                 float4 t[4];
+                if (PEER && k != k0 + sub)
+                {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                    {
+                        sr[u] = (k + LANES * u < k1) ? ka.px.slot_src[k + LANES * u] : 0;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                 {
-                    t[u] = (k + FEP_EPI_LANES * u < k1) ? FEP_EPI_LOAD(ka.fsorted + k + FEP_EPI_LANES * u)
-                                                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    t[u] = (k + LANES * u < k1) ? FEP_EPI_LOAD(fsorted, k + LANES * u, sr[u])
+                                                : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
@@ -546,18 +703,31 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             }
         }
 #pragma unroll
-        for (int o = FEP_EPI_LANES / 2; o > 0; o >>= 1)
+        for (int o = LANES / 2; o > 0; o >>= 1)
         {
             fx += __shfl_xor_sync(FULL_MASK, fx, o);
             fy += __shfl_xor_sync(FULL_MASK, fy, o);
             fz += __shfl_xor_sync(FULL_MASK, fz, o);
         }
-        if (atom < atom_end && sub < 3)
+        if (mine && sub < 3)
         {
             ka.res_f32[3 * (size_t)atom + sub] = sub == 0 ? fx : (sub == 1 ? fy : fz);
         }
     }
 
+    if (PEER && ka.trace && tid == 0 && blockIdx.x < FEP_TRACE_BLOCKS)
+    {
+        /* role of the block in the low two bits of the first stamp: 0 job, 1 scalar, 2 heavy atoms, 3 atoms */
+        const int role = (int)blockIdx.x < lay.job_blocks                                        ? 0
+                         : (int)blockIdx.x < lay.job_blocks + lay.scalar_blocks                  ? 1
+                         : (int)blockIdx.x < lay.job_blocks + lay.scalar_blocks + lay.heavy_blocks ? 2
+                                                                                                  : 3;
+        unsigned long long* t = ka.trace + 4 * (size_t)blockIdx.x;
+        t[0] = (tr0 & ~3ull) | (unsigned long long)role;
+        t[1] = tr1;
+        t[2] = tr2;
+        t[3] = fep_globaltimer();
+    }
     /* the job block that finishes last adds up the job partials per output key, in job order;
      * only job blocks take a ticket (bar.sync + one fence by the ticket thread orders the block's
      * partial before the ticket) */
@@ -621,6 +791,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         *ka.done_counter = 0u;
     }
 #undef FEP_EPI_LOAD
+#undef FEP_EPI_SYNC_POINT
 }
 
 /* coordinates of the touched atoms from a device-resident rvec[natoms] array */
@@ -792,21 +963,35 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     const bool     peer    = ka.px.nranks > 1;
     const int      n_atoms = peer ? ka.px.atom_end - ka.px.atom_begin : ka.n_touched;
     EpilogueLayout lay;
-    lay.atom_blocks   = sf.force ? (n_atoms + FEP_EPI_CTA / FEP_EPI_LANES - 1) / (FEP_EPI_CTA / FEP_EPI_LANES) : 0;
+    const int      n_heavy = peer ? ka.px.heavy_end - ka.px.heavy_begin : ka.n_heavy;
+    const int      per_blk = FEP_EPI_CTA / (peer ? FEP_EPI_LANES_PEER : FEP_EPI_LANES);
+    lay.atom_blocks   = sf.force ? (n_atoms + per_blk - 1) / per_blk : 0;
+    lay.heavy_blocks  = sf.force ? (n_heavy + FEP_EPI_CTA / 32 - 1) / (FEP_EPI_CTA / 32) : 0;
     /* jobs are ordered shift jobs first, then energy-group jobs */
     const int j0      = sf.shift ? 0 : ka.n_shift_jobs;
     const int j1      = sf.energy ? ka.n_red_jobs : ka.n_shift_jobs;
     lay.job_begin     = j0;
     lay.job_blocks    = j1 > j0 ? j1 - j0 : 0;
     lay.scalar_blocks = 2 + ((sf.foreign && ka.n_points > 0) ? 3 * ka.n_points : 0);
-    const int blocks  = lay.atom_blocks + lay.job_blocks + lay.scalar_blocks;
+    const int blocks  = lay.atom_blocks + lay.heavy_blocks + lay.job_blocks + lay.scalar_blocks;
     if (peer)
     {
-        fep_launch_kernel(fep_epilogue_kernel<true>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+        static const bool strong = [] {
+            const char* e = std::getenv("FEPB200_PEER_LOAD");
+            return e && std::strcmp(e, "strong") == 0;
+        }();
+        if (strong)
+        {
+            fep_launch_kernel(fep_epilogue_kernel<true, true>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+        }
+        else
+        {
+            fep_launch_kernel(fep_epilogue_kernel<true, false>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+        }
     }
     else
     {
-        fep_launch_kernel(fep_epilogue_kernel<false>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+        fep_launch_kernel(fep_epilogue_kernel<false, false>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
     }
     (*counter)++;
     if (ev)

@@ -296,50 +296,46 @@ extern "C" int fep_list_build_slots(const int4* d_ent4, int4* d_pair4, const int
 }
 
 /* ------------------------------------------------------------------------------------------- */
-/* peer exchange (fep_types.h): the rank that owns the receiving atom, in the top bits of every
- * scatter slot.  slot_bound[r] = first slot of rank r's atom range; nranks == 1 clears the bits. */
-struct OwnerBounds
-{
-    int n;
-    int b[FEP_XMAX + 1];
-};
-
-__global__ void __launch_bounds__(256) k_tag_owners(int4* __restrict__ pair4, int P, int4* __restrict__ seg_dst, int H,
-                                                    const OwnerBounds ob)
+/* peer exchange (fep_types.h): which rank PRODUCES every element of the atom-sorted contribution
+ * buffer, of the shift-sorted segment forces and of the group-sorted segment energies, when rank r
+ * evaluates the 32-pair warps [r * wpr, (r + 1) * wpr) of the flat pair space.  One byte per
+ * element; the epilogue of the exchange reads each element from its producer's memory. */
+__global__ void __launch_bounds__(256) k_source_tables(const int4* __restrict__ pair4, int P, const int4* __restrict__ seg_dst,
+                                                       int H, const int* __restrict__ warp_hbase, int n_warps, int wpr,
+                                                       unsigned char* __restrict__ slot_src,
+                                                       unsigned char* __restrict__ fshift_src,
+                                                       unsigned char* __restrict__ ev2_src)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    auto tag = [&](int w) {
-        w &= FEP_X_SLOT_MASK;
-        int owner = 0;
-        for (int r = 1; r < ob.n; r++)
-        {
-            owner += (w >= ob.b[r]) ? 1 : 0;
-        }
-        return w | (owner << FEP_X_OWNER_SHIFT);
-    };
     if (i < P)
     {
-        pair4[i].w = tag(pair4[i].w);
+        slot_src[pair4[i].w] = (unsigned char)((i >> 5) / wpr);
     }
-    if (i < H)
+    if (i < n_warps)
     {
-        seg_dst[i].x = tag(seg_dst[i].x);
+        /* the segments of warp i (at most 32) */
+        const int           h0 = warp_hbase[i];
+        const int           h1 = (i + 1 < n_warps) ? warp_hbase[i + 1] : H;
+        const unsigned char r  = (unsigned char)(i / wpr);
+        for (int h = h0; h < h1; h++)
+        {
+            const int4 sd    = seg_dst[h];
+            slot_src[sd.x]   = r;
+            fshift_src[sd.y] = r;
+            ev2_src[sd.z]    = r;
+        }
     }
 }
 
-extern "C" int fep_launch_tag_owners(int4* d_pair4, int P, int4* d_seg_dst, int H, const int* slot_bound, int nranks,
-                                     cudaStream_t stream, long long* counter)
+extern "C" int fep_launch_source_tables(const int4* d_pair4, int P, const int4* d_seg_dst, int H, const int* d_warp_hbase,
+                                        int wpr, unsigned char* d_slot_src, unsigned char* d_fshift_src,
+                                        unsigned char* d_ev2_src, cudaStream_t stream, long long* counter)
 {
-    OwnerBounds ob{};
-    ob.n = nranks;
-    for (int r = 0; r <= nranks && r <= FEP_XMAX; r++)
+    const int n_warps = (P + 31) / 32;
+    if (P > 0 && wpr > 0)
     {
-        ob.b[r] = slot_bound[r];
-    }
-    const int n = P > H ? P : H;
-    if (n > 0)
-    {
-        k_tag_owners<<<(n + 255) / 256, 256, 0, stream>>>(d_pair4, P, d_seg_dst, H, ob);
+        k_source_tables<<<(P + 255) / 256, 256, 0, stream>>>(d_pair4, P, d_seg_dst, H, d_warp_hbase, n_warps, wpr, d_slot_src,
+                                                            d_fshift_src, d_ev2_src);
         (*counter)++;
     }
     return (int)cudaGetLastError();

@@ -43,6 +43,10 @@
 #define FEP_RED_CHUNK 2048 /* segments per reduction job of the epilogue */
 #define FEP_EPI_CTA 256
 #define FEP_EPI_LANES 8 /* lanes per touched atom in the epilogue (32 contributions per trip; 4 lanes measured slower) */
+#define FEP_EPI_LANES_PEER 8 /* the same when the contributions are read over NVLink; equal to FEP_EPI_LANES so that the
+                                summation order, and with it every force bit, is the one of the single-GPU path */
+#define FEP_HEAVY_MIN 32 /* atoms with more force contributions than this are summed by a whole warp */
+#define FEP_HEAVY_LOADS 8 /* independent 16-byte loads per lane and trip of that warp (256 contributions per trip) */
 
 /* soft-core flavour actually evaluated (nb_free_energy.cpp:1324-1363) */
 enum { FEP_SC_NONE = 0, FEP_SC_BEUTLER = 1, FEP_SC_GAPSYS = 2 };
@@ -77,28 +81,35 @@ struct RedJob
 };
 
 /* Multi-GPU "owner computes" exchange (fepb200_set_peer_exchange): every rank holds the layout of
- * the FULL list, evaluates a contiguous range of 32-pair warps of the flat pair space, and its pair
- * kernels store every force contribution straight into the atom-sorted buffer of the rank that
- * owns the receiving atom (a contiguous atom range per rank) -- over NVLink peer memory, from
- * inside the pair kernel, one posted 16-byte store per contribution.  Segment shift forces /
- * energies and the per-CTA fp64 partials are small and go to every rank.  After a cross-GPU
- * barrier at the top of the epilogue each rank sums ITS atoms (forces: reduce-scatter) and all
- * scalars (all-reduce), reading local memory only.  nranks <= 1: off. */
+ * the FULL list and evaluates a contiguous range of 32-pair warps of the flat pair space with the
+ * unchanged single-GPU pair kernels; they store force contributions, segment values and per-CTA
+ * partials at their usual places in the rank's OWN exchange slot, which every rank of the node has
+ * mapped (NVLink peer memory).  Nothing is sent: after a cross-GPU barrier at the top of the
+ * epilogue each rank PULLS what it needs -- the contributions of the atoms it owns (a contiguous
+ * atom range per rank: the forces are reduce-scattered) and all scalar inputs (all-reduced: every
+ * rank sums them in the same order) -- from whichever rank produced each element.  The producer of
+ * every element is static (it follows from the pair ranges) and kept in byte tables, and because
+ * the sorted orders are stable in the pair index, consecutive elements mostly share a producer,
+ * so the remote reads are coalesced.  nranks <= 1: off. */
 #define FEP_XMAX 8
-#define FEP_X_OWNER_SHIFT 28 /* owner rank in the top bits of a scatter slot (slots < 2^28) */
-#define FEP_X_SLOT_MASK ((1 << FEP_X_OWNER_SHIFT) - 1)
+#define FEP_TRACE_BLOCKS 4096
 struct PeerExchange
 {
     int          nranks, rank;
-    int          atom_begin, atom_end; /* compact atoms whose forces this rank sums */
-    unsigned int seq;                  /* step number announced in the barrier (set per launch) */
+    int          atom_begin, atom_end;   /* compact atoms whose forces this rank sums */
+    int          heavy_begin, heavy_end; /* the part of heavy_atoms[] inside that range */
+    unsigned int seq;                    /* step number announced in the barrier (set per launch) */
     int          pad;
+    /* producer rank of every element of fsorted / fshift_sorted / ev2 (local, static per list) */
+    const unsigned char* slot_src;
+    const unsigned char* fshift_src;
+    const unsigned char* ev2_src;
     /* the exchange slot of this step on every rank (index = rank) */
-    float4*       fsorted[FEP_XMAX];
-    float4*       fshift_sorted[FEP_XMAX];
-    float2*       ev2[FEP_XMAX];
-    double*       cta_part[FEP_XMAX];
-    double*       for_part[FEP_XMAX];
+    const float4* fsorted[FEP_XMAX];
+    const float4* fshift_sorted[FEP_XMAX];
+    const float2* ev2[FEP_XMAX];
+    const double* cta_part[FEP_XMAX];
+    const double* for_part[FEP_XMAX];
     unsigned int* flags[FEP_XMAX]; /* per rank FEP_XMAX sequence numbers, slot r written by rank r */
 };
 
@@ -116,7 +127,6 @@ struct KernelArgs
     /* sizes */
     int n_pairs, n_entries, n_segments, n_touched, n_gid, n_cta, n_tiles, tile_pairs;
     int pair_begin, pair_end; /* the pairs this context evaluates ([0, n_pairs) unless the list is split over peers) */
-    int part_mult, part_rank; /* per-CTA partial arrays: part_mult ranks x local CTAs per row, this rank's CTAs at part_rank */
     int n_points, n_chunks, chunk_points;
     int pass_tile_pairs, pass_n_tiles; /* tiles of the force-only Beutler kernel */
     int n_parts;                       /* per-CTA dV/dlambda partials written by the pass of this step */
@@ -142,12 +152,15 @@ struct KernelArgs
     unsigned int* done_counter;
     /* epilogue inputs */
     const int*    atom_ptr;
+    const int*    heavy_atoms; /* [n_heavy] atoms with more than FEP_HEAVY_MIN contributions, ascending */
+    int           n_heavy;
     const RedJob* red_jobs;
     const int*    key_job_ptr; /* [45 + G + 1]: jobs of each key, shift keys first */
     /* outputs */
     float*  res_f32;
     double* res_f64;
     PeerExchange px;
+    unsigned long long* trace; /* NULL, or FEP_TRACE_BLOCKS x 4 global-timer stamps of the epilogue's blocks */
 };
 
 /* what one step has to produce */
@@ -172,7 +185,7 @@ int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlag
 #define FEP_FB_CTA 128
 #define FEP_FB_MAXC 24
 int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
-int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force, int peer);
+int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force);
 /* chained != 0: a kernel of this step is already queued on `stream` and the launches may start
  * before it has completed (programmatic dependent launch, see fep_launch_kernel below) */
 int fep_launch_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_cur,
@@ -216,125 +229,6 @@ __device__ __forceinline__ void fep_pdl_wait()
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-
-/* ---- where the pair kernels put their results (local buffers, or the peers' exchange slots) ----
- * PEER is a compile-time choice in the Beutler kernels (fep_beutler.cu: the single-GPU code is
- * exactly what it was without the exchange) and a uniform run-time branch in the generic ones. */
-/* slot w of the atom-sorted contribution buffer; in peer mode w carries the owner rank */
-template<bool PEER>
-__device__ __forceinline__ void fep_put_force(const KernelArgs& ka, int w, float4 v)
-{
-    if (PEER)
-    {
-        ka.px.fsorted[(unsigned)w >> FEP_X_OWNER_SHIFT][w & FEP_X_SLOT_MASK] = v;
-    }
-    else
-    {
-        ka.fsorted[w] = v;
-    }
-}
-/* i force of a segment (to its atom's owner), and the copies sorted by shift vector / the {Vc,Vv}
- * sorted by energy-group pair (to every rank: each rank reduces all scalars) */
-template<bool PEER>
-__device__ __forceinline__ void fep_put_segment(const KernelArgs& ka, int4 sd, float4 fi, bool force, bool shift,
-                                                bool energy, float2 e)
-{
-    if (PEER)
-    {
-        if (force)
-        {
-            ka.px.fsorted[(unsigned)sd.x >> FEP_X_OWNER_SHIFT][sd.x & FEP_X_SLOT_MASK] = fi;
-        }
-#pragma unroll 1
-        for (int r = 0; r < ka.px.nranks; r++)
-        {
-            if (shift)
-            {
-                ka.px.fshift_sorted[r][sd.y] = fi;
-            }
-            if (energy)
-            {
-                ka.px.ev2[r][sd.z] = e;
-            }
-        }
-    }
-    else
-    {
-        if (force)
-        {
-            ka.fsorted[sd.x] = fi;
-        }
-        if (shift)
-        {
-            ka.fshift_sorted[sd.y] = fi;
-        }
-        if (energy)
-        {
-            ka.ev2[sd.z] = e;
-        }
-    }
-}
-/* element (row, blk) of a per-CTA partial array with n_local CTAs per rank */
-__device__ __forceinline__ size_t fep_part_index(const KernelArgs& ka, int row, int n_local, int blk)
-{
-    return (size_t)row * ((size_t)n_local * ka.part_mult) + (size_t)ka.part_rank * n_local + blk;
-}
-template<bool PEER>
-__device__ __forceinline__ void fep_put_cta_part(const KernelArgs& ka, size_t idx, double v)
-{
-    if (PEER)
-    {
-#pragma unroll 1
-        for (int r = 0; r < ka.px.nranks; r++)
-        {
-            ka.px.cta_part[r][idx] = v;
-        }
-    }
-    else
-    {
-        ka.cta_part[idx] = v;
-    }
-}
-template<bool PEER>
-__device__ __forceinline__ void fep_put_for_part(const KernelArgs& ka, size_t idx, double v)
-{
-    if (PEER)
-    {
-#pragma unroll 1
-        for (int r = 0; r < ka.px.nranks; r++)
-        {
-            ka.px.for_part[r][idx] = v;
-        }
-    }
-    else
-    {
-        ka.for_part[idx] = v;
-    }
-}
-/* last action of a pair kernel's thread before it lets the step go on: stores to peer memory must
- * have arrived before the epilogue announces this rank in the cross-GPU barrier */
-template<bool PEER>
-__device__ __forceinline__ void fep_pair_kernel_done()
-{
-    if (PEER)
-    {
-        __threadfence_system();
-    }
-    fep_pdl_wait();
-}
-/* run-time dispatch for kernels that are not specialised on PEER */
-#define FEP_PX(ka, call_true, call_false) \
-    do                                      \
-    {                                       \
-        if ((ka).px.nranks > 1)             \
-        {                                   \
-            call_true;                      \
-        }                                   \
-        else                                \
-        {                                   \
-            call_false;                     \
-        }                                   \
-    } while (0)
 
 template<typename... KArgs, typename... Args>
 static inline cudaError_t fep_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream,

@@ -37,8 +37,9 @@ extern "C" int    fep_list_build_pairs(const int* d_iinr, const int* d_gid, cons
                                        const int* d_jjnr, const int* d_excl, const int* d_cscan, int e0, int E, int j0, int P,
                                        int4* d_ent4, int4* d_pair4, int* d_keys, int* d_head, int* d_hscan, void* d_tmp,
                                        size_t tmp_bytes, cudaStream_t stream, long long* counter);
-extern "C" int    fep_launch_tag_owners(int4* d_pair4, int P, int4* d_seg_dst, int H, const int* slot_bound, int nranks,
-                                        cudaStream_t stream, long long* counter);
+extern "C" int    fep_launch_source_tables(const int4* d_pair4, int P, const int4* d_seg_dst, int H, const int* d_warp_hbase,
+                                           int wpr, unsigned char* d_slot_src, unsigned char* d_fshift_src,
+                                           unsigned char* d_ev2_src, cudaStream_t stream, long long* counter);
 extern "C" int    fep_list_build_slots(const int4* d_ent4, int4* d_pair4, const int* d_head, const int* d_hscan, int P, int H,
                                        int nT, int ngrp, int* d_keys, int* d_keys_out, int* d_vals, int* d_vals_out,
                                        int* d_seg_shift, int* d_seg_gid, int* d_warp_hbase, int4* d_seg_dst, int* d_atom_ptr,
@@ -245,8 +246,12 @@ struct fepb200_ctx
     bool           px_on = false;
     int            x_nranks = 1, x_rank = 0;
     int            x_range_pairs = 0;   /* pairs per rank, rounded up (same on every rank) */
-    int            x_pair_begin = 0, x_pair_end = 0, x_atom_begin = 0, x_atom_end = 0;
-    int            x_slot_bound[FEP_XMAX + 1] = {}; /* first scatter slot owned by each rank */
+    int            x_pair_begin = 0, x_pair_end = 0, x_atom_begin = 0, x_atom_end = 0, x_heavy_begin = 0, x_heavy_end = 0;
+    DeviceArray<unsigned char> d_slot_src, d_fshift_src, d_ev2_src; /* producer rank of every sorted element */
+    DeviceArray<int>    d_heavy;      /* atoms with more than FEP_HEAVY_MIN force contributions, ascending */
+    std::vector<int>    heavy_atoms;  /* host copy */
+    DeviceArray<unsigned long long> d_trace;                        /* fepb200_epilogue_trace() */
+    int                             trace_blocks = 0;               /* epilogue blocks of the last traced launch */
     unsigned int   x_seq = 0;
     unsigned char* x_base[FEP_XMAX] = {};
     size_t         x_bytes = 0; /* size of each rank's exchange buffer */
@@ -366,8 +371,6 @@ int prepare_buffers(fepb200_ctx* c)
     const int range = c->px_on ? c->x_range_pairs : k.n_pairs;
     k.pair_begin    = c->px_on ? c->x_pair_begin : 0;
     k.pair_end      = c->px_on ? c->x_pair_end : k.n_pairs;
-    k.part_mult     = c->px_on ? c->x_nranks : 1;
-    k.part_rank     = c->px_on ? c->x_rank : 0;
     k.n_cta         = (range + FEP_CTA - 1) / FEP_CTA;
     c->foreign_mode = -1;
     if (c->softcore == FEP_SC_BEUTLER && !k.pot_switch)
@@ -411,9 +414,9 @@ int prepare_buffers(fepb200_ctx* c)
             k.fuse_pass_and_foreign = std::atoi(env) != 0;
         }
         /* occupancy of the very kernels the step will launch (cudaOccupancyMaxActiveBlocksPerMultiprocessor) */
-        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign, c->px_on),
+        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign),
               k.tile_pairs, k.n_tiles);
-        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1, c->px_on), k.pass_tile_pairs, k.pass_n_tiles);
+        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1), k.pass_tile_pairs, k.pass_n_tiles);
     }
     else
     {
@@ -435,14 +438,14 @@ int prepare_buffers(fepb200_ctx* c)
         /* carve one exchange slot: [fsorted | fshift_sorted | ev2 | cta_part | for_part], every part
          * 256-byte aligned; identical on all ranks because every input of the sizes is */
         auto         up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t P       = (size_t)k.n_pairs, H = (size_t)k.n_segments, nr = (size_t)c->x_nranks;
-        const size_t n_parts = nr * (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1));
+        const size_t P       = (size_t)k.n_pairs, H = (size_t)k.n_segments;
+        const size_t n_parts = (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1));
         c->x_off_fsorted     = 0;
         c->x_off_fshift      = c->x_off_fsorted + up((P + H) * sizeof(float4));
         c->x_off_ev2         = c->x_off_fshift + up(H * sizeof(float4));
         c->x_off_cta         = c->x_off_ev2 + up(H * sizeof(float2));
         c->x_off_for         = c->x_off_cta + up(2 * n_parts * sizeof(double));
-        c->x_slot_bytes      = c->x_off_for + up(3 * (size_t)np * nr * (size_t)std::max(k.n_tiles, 1) * sizeof(double));
+        c->x_slot_bytes      = c->x_off_for + up(3 * (size_t)np * (size_t)std::max(k.n_tiles, 1) * sizeof(double));
         if (2 * c->x_slot_bytes + 256 > c->x_bytes)
         {
             return fail(c, FEPB200_ERR_STATE,
@@ -721,6 +724,9 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
         CU_CHECK(c, cudaMemcpyAsync(c->touched.data(), c->d_touched.ptr, sizeof(int) * nT, cudaMemcpyDeviceToHost, st));
     }
     CU_CHECK(c, cudaMemcpyAsync(key_ptr.data(), c->d_key_ptr.ptr, sizeof(int) * key_ptr.size(), cudaMemcpyDeviceToHost, st));
+    /* range of every touched atom in the atom-sorted buffer: the host picks the heavy atoms from it */
+    c->w_atom_ptr.resize((size_t)nT + 1);
+    CU_CHECK(c, cudaMemcpyAsync(c->w_atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost, st));
     CU_CHECK(c, cudaStreamSynchronize(st));
     build_jobs(key_ptr.data(), key_ptr.data() + FEP_NUM_SHIFT + 1, ngrp, jobs, key_job_ptr, &c->ka.n_shift_jobs);
     /* per-atom parameters in compact order (the per-atom arrays of set_atoms live on the host) */
@@ -852,6 +858,11 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_ent4.release();
     c->d_red_jobs.release();
     c->d_par4.release();
+    c->d_trace.release();
+    c->d_heavy.release();
+    c->d_slot_src.release();
+    c->d_fshift_src.release();
+    c->d_ev2_src.release();
     c->d_fsorted.release();
     c->d_fshift_sorted.release();
     c->d_ev2.release();
@@ -1389,6 +1400,20 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
             return rc;
         }
     }
+    /* atoms with long contribution ranges get a whole warp in the epilogue (both builders leave
+     * atom_ptr in w_atom_ptr) */
+    c->heavy_atoms.clear();
+    for (int a = 0; a < nT; a++)
+    {
+        if (c->w_atom_ptr[a + 1] - c->w_atom_ptr[a] > FEP_HEAVY_MIN)
+        {
+            c->heavy_atoms.push_back(a);
+        }
+    }
+    if ((rc = to_device(c, c->d_heavy, c->heavy_atoms)) != FEPB200_OK)
+    {
+        return rc;
+    }
     CU_CHECK(c, c->d_fsorted.reserve(std::max(P + H, 1)));
     CU_CHECK(c, c->d_fshift_sorted.reserve(std::max(H, 1)));
     CU_CHECK(c, c->d_ev2.reserve(std::max(H, 1)));
@@ -1415,6 +1440,8 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     k.ev2         = c->d_ev2.ptr;
     k.job_part    = c->d_job_part.ptr;
     k.atom_ptr    = c->d_atom_ptr.ptr;
+    k.heavy_atoms = c->d_heavy.ptr;
+    k.n_heavy     = (int)c->heavy_atoms.size();
     k.red_jobs    = c->d_red_jobs.ptr;
     k.key_job_ptr = c->d_key_job_ptr.ptr;
 
@@ -1741,7 +1768,12 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
         px.rank                 = c->x_rank;
         px.atom_begin           = c->x_atom_begin;
         px.atom_end             = c->x_atom_end;
+        px.heavy_begin          = c->x_heavy_begin;
+        px.heavy_end            = c->x_heavy_end;
         px.seq                  = seq;
+        px.slot_src             = c->d_slot_src.ptr;
+        px.fshift_src           = c->d_fshift_src.ptr;
+        px.ev2_src              = c->d_ev2_src.ptr;
         for (int r = 0; r < c->x_nranks; r++)
         {
             unsigned char* b    = c->x_base[r] + so;
@@ -1752,12 +1784,12 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
             px.for_part[r]      = reinterpret_cast<double*>(b + c->x_off_for);
             px.flags[r]         = reinterpret_cast<unsigned int*>(c->x_base[r] + 2 * c->x_slot_bytes);
         }
-        /* what the epilogue of this rank reads */
-        ka_step.fsorted       = px.fsorted[c->x_rank];
-        ka_step.fshift_sorted = px.fshift_sorted[c->x_rank];
-        ka_step.ev2           = px.ev2[c->x_rank];
-        ka_step.cta_part      = px.cta_part[c->x_rank];
-        ka_step.for_part      = px.for_part[c->x_rank];
+        /* the pair kernels of this rank write its own slot */
+        ka_step.fsorted       = const_cast<float4*>(px.fsorted[c->x_rank]);
+        ka_step.fshift_sorted = const_cast<float4*>(px.fshift_sorted[c->x_rank]);
+        ka_step.ev2           = const_cast<float2*>(px.ev2[c->x_rank]);
+        ka_step.cta_part      = const_cast<double*>(px.cta_part[c->x_rank]);
+        ka_step.for_part      = const_cast<double*>(px.for_part[c->x_rank]);
     }
     const int err = fep_launch_step(&ka_step, c->softcore, c->elec_ewald, sf, stream, &c->launches,
                                     c->profiling ? c->ev_prof : nullptr, &c->cur, c->pts.data(), c->foreign_mode,
@@ -1871,19 +1903,12 @@ int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks,
     return FEPB200_OK;
 }
 
-/* back to the plain single-GPU path: owner bits cleared, launch geometry of the whole list */
+/* back to the plain single-GPU path: launch geometry of the whole list, results in the context's own buffers */
 static int peer_exchange_off(fepb200_ctx* c)
 {
     c->px_on    = false;
     c->x_nranks = 1;
     c->x_rank   = 0;
-    const int bound[FEP_XMAX + 1] = {};
-    const int err = fep_launch_tag_owners(c->d_pair4.ptr, c->ka.n_pairs, c->d_seg_dst.ptr, c->ka.n_segments, bound, 1,
-                                          c->stream, &c->launches);
-    if (err != 0)
-    {
-        return fail(c, FEPB200_ERR_CUDA, "owner tagging failed: %s", cudaGetErrorString((cudaError_t)err));
-    }
     const int rc = prepare_buffers(c);
     if (rc != FEPB200_OK)
     {
@@ -1908,7 +1933,7 @@ size_t fepb200_exchange_bytes(const fepb200_ctx* c, int nranks)
     const size_t    P       = (size_t)c->ka.n_pairs, H = (size_t)c->ka.n_segments;
     const long long n_warps = ((long long)P + 31) / 32;
     const long long wpr     = (n_warps + nranks - 1) / nranks;
-    const size_t    ctas    = (size_t)nranks * (size_t)((wpr * 32 + 127) / 128 + 1);
+    const size_t    ctas    = (size_t)((wpr * 32 + 127) / 128 + 1);
     const size_t    np      = (size_t)std::max(c->layout.nforeign + 1, 32);
     const size_t    slot    = up((P + H) * sizeof(float4)) + up(H * sizeof(float4)) + up(H * sizeof(float2))
                         + up(2 * ctas * sizeof(double)) + up(3 * np * ctas * sizeof(double));
@@ -1934,10 +1959,6 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
     close_chain(c);
     KernelArgs& k = c->ka;
     const int   P = k.n_pairs, H = k.n_segments, nT = k.n_touched;
-    if ((long long)P + H >= (1LL << FEP_X_OWNER_SHIFT))
-    {
-        return fail(c, FEPB200_ERR_UNSUPPORTED, "fepb200_set_peer_exchange: more than 2^%d force contributions", FEP_X_OWNER_SHIFT);
-    }
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     if (nranks == 1)
     {
@@ -1950,7 +1971,6 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
             return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_peer_exchange: buffer %d is NULL or not 256-byte aligned", r);
         }
     }
-    int bound[FEP_XMAX + 1] = {};
     c->px_on                = true;
     c->x_nranks             = nranks;
     c->x_rank               = rank;
@@ -1968,35 +1988,42 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
         c->x_pair_begin         = (int)std::min<long long>((long long)rank * wpr * 32, P);
         c->x_pair_end           = (int)std::min<long long>((long long)(rank + 1) * wpr * 32, P);
         /* atoms: contiguous ranges with equal shares of the force contributions */
-        std::vector<int> atom_ptr((size_t)nT + 1, 0);
-        if (nT > 0)
-        {
-            CU_CHECK(c, cudaMemcpy(atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost));
-        }
-        const long long total = (long long)P + H;
+        const std::vector<int>& atom_ptr = c->w_atom_ptr; /* kept by fepb200_set_list() */
+        /* cost of an atom = its contributions + a fixed share for the lanes that serve it (a range
+         * of many light atoms needs more blocks than a range of few heavy ones with the same volume) */
+        const long long per_atom = 8;
+        const long long total    = (long long)P + H + per_atom * nT;
         int             a_of[FEP_XMAX + 1];
         a_of[0]      = 0;
         a_of[nranks] = nT;
-        for (int r = 1; r < nranks; r++)
         {
-            const int target = (int)(total * r / nranks);
-            a_of[r] = (int)(std::lower_bound(atom_ptr.begin(), atom_ptr.begin() + nT, target) - atom_ptr.begin());
-            a_of[r] = std::max(a_of[r], a_of[r - 1]);
+            int a = 0;
+            for (int r = 1; r < nranks; r++)
+            {
+                const long long target = total * r / nranks;
+                while (a < nT && atom_ptr[a] + per_atom * a < target)
+                {
+                    a++;
+                }
+                a_of[r] = a;
+            }
         }
-        for (int r = 0; r <= nranks; r++)
+        c->x_atom_begin  = a_of[rank];
+        c->x_atom_end    = a_of[rank + 1];
+        c->x_heavy_begin = (int)(std::lower_bound(c->heavy_atoms.begin(), c->heavy_atoms.end(), a_of[rank]) - c->heavy_atoms.begin());
+        c->x_heavy_end   = (int)(std::lower_bound(c->heavy_atoms.begin(), c->heavy_atoms.end(), a_of[rank + 1]) - c->heavy_atoms.begin());
+        /* producer rank of every element of the sorted arrays */
+        CU_CHECK(c, c->d_slot_src.reserve(std::max<size_t>((size_t)P + H, 1)));
+        CU_CHECK(c, c->d_fshift_src.reserve(std::max(H, 1)));
+        CU_CHECK(c, c->d_ev2_src.reserve(std::max(H, 1)));
+        const int err = fep_launch_source_tables(c->d_pair4.ptr, P, c->d_seg_dst.ptr, H, c->d_warp_hbase.ptr, (int)wpr,
+                                                 c->d_slot_src.ptr, c->d_fshift_src.ptr, c->d_ev2_src.ptr, c->stream,
+                                                 &c->launches);
+        if (err != 0)
         {
-            bound[r]           = atom_ptr[a_of[r]];
-            c->x_slot_bound[r] = bound[r];
+            c->px_on = false;
+            return fail(c, FEPB200_ERR_CUDA, "source tables failed: %s", cudaGetErrorString((cudaError_t)err));
         }
-        c->x_atom_begin = a_of[rank];
-        c->x_atom_end   = a_of[rank + 1];
-    }
-    /* the owner rank goes into the top bits of every scatter slot (all zero when the exchange is off) */
-    const int err = fep_launch_tag_owners(c->d_pair4.ptr, P, c->d_seg_dst.ptr, H, bound, nranks, c->stream, &c->launches);
-    if (err != 0)
-    {
-        c->px_on = false;
-        return fail(c, FEPB200_ERR_CUDA, "owner tagging failed: %s", cudaGetErrorString((cudaError_t)err));
     }
     c->x_seq = 0;
     int rc   = prepare_buffers(c);
@@ -2016,6 +2043,33 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
     }
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     return FEPB200_OK;
+}
+
+int fepb200_epilogue_trace(fepb200_ctx* c, int enable, unsigned long long* stamps, int max_blocks)
+{
+    if (!c || !c->have_list)
+    {
+        return fail(c, FEPB200_ERR_STATE, "no list has been set");
+    }
+    cudaSetDevice(c->device);
+    int n = 0;
+    if (stamps && max_blocks > 0 && c->ka.trace)
+    {
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+        n = std::min(max_blocks, FEP_TRACE_BLOCKS);
+        CU_CHECK(c, cudaMemcpy(stamps, c->d_trace.ptr, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    if (enable && !c->ka.trace)
+    {
+        CU_CHECK(c, c->d_trace.reserve(4 * (size_t)FEP_TRACE_BLOCKS));
+        CU_CHECK(c, cudaMemset(c->d_trace.ptr, 0, sizeof(unsigned long long) * 4 * FEP_TRACE_BLOCKS));
+        c->ka.trace = c->d_trace.ptr;
+    }
+    else if (!enable)
+    {
+        c->ka.trace = nullptr;
+    }
+    return n;
 }
 
 int fepb200_peer_ranges(const fepb200_ctx* c, int* pair_begin, int* pair_end, int* atom_begin, int* atom_end)

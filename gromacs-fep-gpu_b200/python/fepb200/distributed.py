@@ -3,10 +3,10 @@ the ranks, coordinates and parameters replicated.  Three ways to combine the ran
 (SURVEY.md section 8e), selected by ShardedFep.reduction:
 
   "fused" (default): no separate collective.  Every rank holds the layout of the full list and
-      evaluates its share of the pairs; the pair kernels store each force contribution over NVLink
-      straight into the atom-sorted buffer of the rank that owns the receiving atom, the small
-      scalar inputs go to every rank, and after a cross-GPU barrier inside the epilogue kernel each
-      rank sums the atoms it owns (forces: reduce-scatter) and all scalars (all-reduce).
+      evaluates its share of the pairs with the unchanged pair kernels, results staying in its own
+      exchange buffer (symmetric memory); after a cross-GPU barrier inside the epilogue kernel each
+      rank reads over NVLink, from whichever rank produced them, the contributions of the atoms it
+      owns (forces: reduce-scatter) and all scalar inputs (all-reduce).
       fepb200_set_peer_exchange().
   "p2p":  the list is split by i-entry (shard.py), every rank computes a full result block for its
       shard and ONE kernel of libfepb200 sums all blocks over NVLink peer memory

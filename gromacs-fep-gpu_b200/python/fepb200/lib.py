@@ -78,6 +78,7 @@ SYMBOLS = {
     "fepb200_exchange_bytes": (ctypes.c_size_t, [_VP, ctypes.c_int]),
     "fepb200_set_peer_exchange": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_VP), ctypes.c_size_t]),
     "fepb200_peer_ranges": (ctypes.c_int, [_VP, _IP, _IP, _IP, _IP]),
+    "fepb200_epilogue_trace": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]),
     "fepb200_download": (ctypes.c_int, [_VP, ctypes.c_int, _FP, _FP, _DP, _DP, _DP, _DP, _DP]),
     "fepb200_launch_count": (ctypes.c_longlong, [_VP]),
     "fepb200_last_launch_ms": (ctypes.c_int, [_VP, _FP]),
@@ -354,3 +355,13 @@ class FepContext:
         v = [ctypes.c_int(0) for _ in range(4)]
         self._check(self._lib.fepb200_peer_ranges(self._h, *[ctypes.byref(x) for x in v]))
         return tuple(int(x.value) for x in v)
+
+    def epilogue_trace(self, enable: bool = True, max_blocks: int = 4096) -> np.ndarray:
+        """Global-timer stamps [blocks, 4] (entry, pair kernels done, barrier passed, sums done) of the
+        epilogue blocks of the last launch (empty before tracing was enabled); see fepb200.h."""
+        buf = np.zeros((max_blocks, 4), np.uint64)
+        n = self._lib.fepb200_epilogue_trace(self._h, int(bool(enable)), buf.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)),
+                                             int(max_blocks))
+        if n < 0:
+            self._check(n)
+        return buf[:n]

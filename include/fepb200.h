@@ -233,8 +233,8 @@ int    fepb200_set_partial_result_block(fepb200_ctx* ctx, void* d_block);
 int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags,
                             int rank, unsigned int seq);
 
-/* ---- multi-GPU, fused: the pair kernels scatter over NVLink, every rank sums its own atoms -----
- * The force reduce-scatter and the scalar all-reduce of SURVEY 8e without a separate collective
+/* ---- multi-GPU, fused: no separate collective, every rank sums its own atoms ------------------
+ * The force reduce-scatter and the scalar all-reduce of SURVEY 8e inside the epilogue kernel
  * (replaces what the reference does with per-thread buffers + ThreadedForceBuffer::reduce,
  * threaded_force_buffer.cpp:320-402, across GPUs instead of across OpenMP threads):
  *   1. every rank calls fepb200_set_list() with the FULL list (rank 0 of 1), so that all ranks
@@ -243,15 +243,16 @@ int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_bl
  *      ranks of the node have mapped (CUDA VMM / symmetric memory), and calls
  *      fepb200_set_peer_exchange() with the device pointers of ALL ranks' buffers in rank order;
  *   3. from then on fepb200_launch() / fepb200_compute() of rank r evaluates the r-th share of the
- *      32-pair warps of the flat pair space; its pair kernels store each force contribution
- *      directly into the atom-sorted buffer of the rank that owns the receiving atom (contiguous
- *      atom ranges with equal numbers of contributions), and the segment shift forces / energies
- *      and per-CTA dV/dlambda and foreign-energy partials into every rank's buffer.  The epilogue
- *      first passes a cross-GPU barrier (sequence flags in the exchange buffers), then sums what
- *      arrived: forces of the atoms this rank owns (entries of all other atoms in the result block
- *      stay zero), and ALL scalars (shift forces, Vc/Vv, dV/dlambda, foreign energies) on every
- *      rank.  Forces and the job-reduced scalars are bit-identical to the single-GPU result
- *      (same slots, same summation order).
+ *      32-pair warps of the flat pair space with the unchanged pair kernels, which leave their
+ *      results (force contributions at their atom-sorted slots, segment shift forces / energies,
+ *      per-CTA dV/dlambda and foreign-energy partials) in rank r's own exchange buffer.  The
+ *      epilogue first passes a cross-GPU barrier (sequence flags in the exchange buffers), then
+ *      every rank reads over NVLink, from whichever rank produced each element, the contributions
+ *      of the atoms it owns (contiguous atom ranges with equal numbers of contributions; entries
+ *      of all other atoms in the result block stay zero) and ALL scalar inputs (shift forces,
+ *      Vc/Vv, dV/dlambda, foreign energies: summed identically on every rank).  Forces, shift
+ *      forces and Vc/Vv are bit-identical to the single-GPU result (same slots, same summation
+ *      order).
  * All ranks must call fepb200_launch()/fepb200_compute() the same number of times (lockstep); a
  * rank that waits more than 4 s for a peer traps.  fepb200_download()/fepb200_compute() add the
  * owned atoms' forces and the full scalars into the caller's arrays: sum the force arrays over
@@ -263,6 +264,14 @@ int    fepb200_set_peer_exchange(fepb200_ctx* ctx, int nranks, int rank, void* c
 /* The pairs [pair_begin, pair_end) of the flat pair space this context evaluates and the compact
  * atoms [atom_begin, atom_end) (indices into fepb200_touched_atoms()) it owns; any pointer may be NULL. */
 int    fepb200_peer_ranges(const fepb200_ctx* ctx, int* pair_begin, int* pair_end, int* atom_begin, int* atom_end);
+
+/* Diagnosis of the exchange: with enable != 0 the epilogue of every following launch records, per
+ * block, the GPU's global timer (ns) at block entry, when this rank's pair kernels had completed,
+ * when the cross-GPU barrier had been passed, and when the block's sums were done.  stamps (may be
+ * NULL) receives 4 values per block of the last launch for min(max_blocks, 4096) blocks; returns
+ * that number of blocks (>= 0) or a negative error code.  Blocks are ordered reduction jobs,
+ * scalar sums, per-atom sums. */
+int fepb200_epilogue_trace(fepb200_ctx* ctx, int enable, unsigned long long* stamps, int max_blocks);
 
 /* Copy the result block to the host and add it into the caller's arrays (same
  * semantics as the tail of fepb200_compute).  Synchronous. */

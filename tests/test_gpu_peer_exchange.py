@@ -1,7 +1,6 @@
 """The fused multi-GPU exchange (fepb200_set_peer_exchange) exercised on ONE device: N contexts of one
-process play the ranks, their exchange buffers are plain device allocations, so every "peer" store
-of the pair kernels and the cross-rank barrier of the epilogue run exactly the code they run over
-NVLink.  Forces are owned by atom range: the sum of the ranks' force arrays must be BIT-IDENTICAL to
+process play the ranks, their exchange buffers are plain device allocations, so the cross-rank
+barrier of the epilogue and its "peer" reads run exactly the code they run over NVLink.  Forces are owned by atom range: the sum of the ranks' force arrays must be BIT-IDENTICAL to
 the single-context result (same scatter slots, same summation order), as must the shift forces and
 Vc/Vv (same reduction jobs); dV/dlambda and the foreign energies are sums of per-CTA partials whose
 tiling differs with the split, so they agree to rounding; everything must match the oracle at the
