@@ -215,6 +215,11 @@ def run_ours(args, name):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever libraries print while we run (NCCL's version
+    # banner at communicator creation) goes to stderr; the descriptor is restored for the result
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -331,9 +336,23 @@ def run_ours(args, name):
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    lap = [0.0, 0.0, 0.0] if os.environ.get("FEPB200_E2E_PHASES") else None
     for _ in range(args.steps):
         flush.zero_()
-        sh.step(x_np, problem.shiftvec, flags | P.CLEAR_OUTPUTS, out)
+        if lap is None:
+            sh.step(x_np, problem.shiftvec, flags | P.CLEAR_OUTPUTS, out)
+        else:  # the same three calls step() makes, with the host clock between them (diagnosis)
+            ta = time.perf_counter()
+            ctx.upload_x(x_np, problem.shiftvec)
+            tb = time.perf_counter()
+            sh.launch(flags | P.CLEAR_OUTPUTS)
+            tc = time.perf_counter()
+            ctx.download(flags | P.CLEAR_OUTPUTS, out)
+            td = time.perf_counter()
+            lap = [lap[0] + tb - ta, lap[1] + tc - tb, lap[2] + td - tc]
+    if lap is not None:
+        print(f"[e2e phases] rank {rank}: upload_x {lap[0] / args.steps * 1e6:.1f} us, launch {lap[1] / args.steps * 1e6:.1f} us, "
+              f"download {lap[2] / args.steps * 1e6:.1f} us", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -366,7 +385,10 @@ def run_ours(args, name):
                              ms_per_step=e2e_s / args.steps * 1e3),
                     gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, cpu_baseline=cpu,
                     wall_ms_per_step_incl_flush=t_wall / args.steps * 1e3, device=ctx.describe())
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     sh.close()
     if world > 1:
         dist.destroy_process_group()

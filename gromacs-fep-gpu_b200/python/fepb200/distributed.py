@@ -2,15 +2,17 @@
 the ranks, coordinates and parameters replicated.  Three ways to combine the ranks' results
 (SURVEY.md section 8e), selected by ShardedFep.reduction:
 
-  "fused" (default): no separate collective.  Every rank holds the layout of the full list and
+  "fused": no separate collective.  Every rank holds the layout of the full list and
       evaluates its share of the pairs with the unchanged pair kernels, results staying in its own
       exchange buffer (symmetric memory); after a cross-GPU barrier inside the epilogue kernel each
       rank reads over NVLink, from whichever rank produced them, the contributions of the atoms it
       owns (forces: reduce-scatter) and all scalar inputs (all-reduce).
       fepb200_set_peer_exchange().
-  "p2p":  the list is split by i-entry (shard.py), every rank computes a full result block for its
-      shard and ONE kernel of libfepb200 sums all blocks over NVLink peer memory
+  "p2p" (default): the list is split by i-entry (shard.py), every rank computes a full result block
+      for its shard and ONE kernel of libfepb200 sums all blocks over NVLink peer memory
       (fepb200_reduce_peers; all ranks get everything).
+Measured on C5 (device time per step, B200 x N): p2p 54 / - / 53 us, fused 63 / 56 / 53 us at
+N = 2 / 4 / 8 (1 GPU: 57 us): p2p is the default; see DESIGN.md section 5.
   "nccl": same split, two ncclAllReduce calls on zero-copy views of the result block.
 
 torch.distributed is plumbing only (process group, NCCL communicator, stream); the tensors it
@@ -45,10 +47,10 @@ def result_tensors(ctx: FepContext) -> tuple[torch.Tensor, torch.Tensor]:
 class ShardedFep:
     """The per-rank object: holds this rank's shard and reduces results over the group.
 
-    reduction = "fused" (default when available): see the module docstring; step() returns the
+    reduction = "fused": see the module docstring; step() returns the
     forces of the atoms this rank owns (zeros elsewhere: the sum over ranks is the full force array)
     and the full scalars on every rank.
-    reduction = "p2p": every rank publishes its result block in
+    reduction = "p2p" (default when available): every rank publishes its result block in
     symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations every rank of the
     node has mapped over NVLink), passes a device-side barrier, and libfepb200's own kernel reads
     all blocks through the peer pointers and sums them in rank order (fepb200_reduce_peers).
@@ -66,7 +68,7 @@ class ShardedFep:
         self.reduction = "none"
         self._p2p_error = None  # why symmetric memory was not used, if it was asked for
         self._step = 0
-        want = (reduction or os.environ.get("FEPB200_REDUCTION", "fused")) if world > 1 else "none"
+        want = (reduction or os.environ.get("FEPB200_REDUCTION", "p2p")) if world > 1 else "none"
         if want == "fused":
             try:
                 self.ctx.set_problem(problem)  # the full list on every rank
