@@ -36,6 +36,49 @@ def touched_atoms(nblist) -> np.ndarray:
     return np.unique(np.concatenate([np.asarray(nblist.iinr, np.int64), np.asarray(nblist.jjnr, np.int64)])).astype(np.int32)
 
 
+# ---- the fused peer exchange (fepb200_set_peer_exchange): pairs by warp, atoms by contributions ----
+PEER_ATOM_COST = 8  # the library's fixed share per atom when it balances the atom ranges
+
+
+def peer_pair_ranges(nrj: int, nranks: int) -> list[tuple[int, int]]:
+    """Rank r evaluates the pairs [begin, end) of the flat pair space: equal shares of its 32-pair warps."""
+    n_warps = (nrj + 31) // 32
+    wpr = (n_warps + nranks - 1) // nranks
+    return [(min(r * wpr * 32, nrj), min((r + 1) * wpr * 32, nrj)) for r in range(nranks)]
+
+
+def contribution_ranges(nblist) -> tuple[np.ndarray, np.ndarray]:
+    """(touched atoms, atom_ptr): atom k of the compact numbering owns the force contributions
+    [atom_ptr[k], atom_ptr[k+1]) of the atom-sorted buffer -- one per pair it is the j atom of, and
+    one per segment (maximal run of pairs of one i-entry inside one 32-pair warp) it is the i atom of."""
+    nrj = int(nblist.nrj)
+    touched = touched_atoms(nblist)
+    if nrj == 0:
+        return touched, np.zeros(len(touched) + 1, np.int64)
+    ent = np.repeat(np.arange(nblist.nri), np.diff(np.asarray(nblist.jindex, np.int64)))
+    warp = np.arange(nrj) // 32
+    head = np.ones(nrj, bool)
+    head[1:] = (ent[1:] != ent[:-1]) | (warp[1:] != warp[:-1])
+    natoms = int(max(np.max(nblist.iinr), np.max(nblist.jjnr))) + 1
+    cnt = np.bincount(np.asarray(nblist.jjnr, np.int64), minlength=natoms)
+    cnt = cnt + np.bincount(np.asarray(nblist.iinr, np.int64)[ent[head]], minlength=natoms)
+    return touched, np.concatenate([[0], np.cumsum(cnt[touched])]).astype(np.int64)
+
+
+def peer_atom_ranges(atom_ptr, nranks: int) -> list[tuple[int, int]]:
+    """Rank r owns the compact atoms [begin, end): contiguous ranges with equal shares of
+    (contributions + PEER_ATOM_COST per atom), the rule of fepb200_set_peer_exchange()."""
+    atom_ptr = np.asarray(atom_ptr, np.int64)
+    nt = atom_ptr.shape[0] - 1
+    total = int(atom_ptr[-1]) + PEER_ATOM_COST * nt
+    cost = atom_ptr[:-1] + PEER_ATOM_COST * np.arange(nt)  # cost of everything before atom a
+    bounds = [0]
+    for r in range(1, nranks):
+        bounds.append(max(int(np.searchsorted(cost, total * r // nranks, side="left")), bounds[-1]))
+    bounds.append(nt)
+    return [(bounds[r], bounds[r + 1]) for r in range(nranks)]
+
+
 class ResultLayout:
     """Host-side mirror of `struct fepb200_layout`: where forces, shift forces, energy-group
     energies, dV/dlambda and foreign-lambda terms sit in the fp32 / fp64 result blocks."""

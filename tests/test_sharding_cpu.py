@@ -104,3 +104,97 @@ def test_sharded_reduction_matches_full_list_gloo(world, tmp_path):
     result = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(world, _free_port(), root, result), nprocs=world, join=True)
     assert open(result).read() == "ok"
+
+
+# ---- the fused peer exchange (fepb200_set_peer_exchange): host-side mirror of its split ----------
+def test_peer_ranges_are_partitions():
+    from fepb200.shard import contribution_ranges, peer_atom_ranges, peer_pair_ranges
+
+    prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=2))
+    nb = prob.nblist
+    touched, atom_ptr = contribution_ranges(nb)
+    assert np.array_equal(touched, touched_atoms(nb)) and atom_ptr[0] == 0
+    assert np.all(np.diff(atom_ptr) > 0)  # every touched atom receives at least one contribution
+    for n in (1, 2, 3, 8):
+        pr = peer_pair_ranges(nb.nrj, n)
+        assert pr[0][0] == 0 and pr[-1][1] == nb.nrj and all(a[1] == b[0] for a, b in zip(pr, pr[1:]))
+        assert all(a % 32 == 0 for a, _ in pr)  # warps of the flat pair space are never cut
+        assert max(b - a for a, b in pr) - min(b - a for a, b in pr[:-1] or pr) <= 32 * n
+        ar = peer_atom_ranges(atom_ptr, n)
+        assert ar[0][0] == 0 and ar[-1][1] == len(touched) and all(a[1] == b[0] for a, b in zip(ar, ar[1:]))
+        cost = [atom_ptr[b] - atom_ptr[a] + 8 * (b - a) for a, b in ar]
+        heaviest = int(np.max(np.diff(atom_ptr))) + 8
+        assert max(cost) - min(cost) <= 2 * heaviest  # balanced up to one atom at either end
+    # degenerate inputs
+    assert peer_pair_ranges(0, 4) == [(0, 0)] * 4
+    assert peer_pair_ranges(40, 4) == [(0, 32), (32, 40), (40, 40), (40, 40)]
+    assert peer_atom_ranges(np.array([0]), 3) == [(0, 0)] * 3
+
+
+def test_slice_pairs_cuts_entries_and_reassembles():
+    prob = make_system(scaled_spec("C2", 3.2, 1, 20, n_foreign=1))
+    nb = prob.nblist
+    cuts = [0, 32, 96, nb.nrj // 2 // 32 * 32, nb.nrj]
+    jj, ex, ii = [], [], []
+    for a, b in zip(cuts, cuts[1:]):
+        s = nb.slice_pairs(a, b)
+        assert s.nrj == b - a and np.all(np.diff(s.jindex) > 0)
+        jj.append(s.jjnr)
+        ex.append(s.excl_fep)
+        ii.append(np.repeat(s.iinr, np.diff(s.jindex)))
+    assert np.array_equal(np.concatenate(jj), nb.jjnr) and np.array_equal(np.concatenate(ex), nb.excl_fep)
+    assert np.array_equal(np.concatenate(ii), np.repeat(nb.iinr, np.diff(nb.jindex)))
+    assert nb.slice_pairs(64, 64).nri == 0
+
+
+def _fused_worker(rank, world, port, root, result_file):
+    """Every rank evaluates ITS pairs (CPU oracle = test infrastructure), the owner of an atom range
+    ends up with the sum of all ranks' contributions to its atoms (reduce-scatter), every rank with
+    the summed scalars (all-reduce): the data flow of the fused exchange, on gloo."""
+    for p in (os.path.join(root, "gromacs-fep-gpu_b200", "python"), root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import copy
+
+    from fepb200.shard import contribution_ranges, peer_atom_ranges, peer_pair_ranges
+    from oracle import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=3))
+    touched, atom_ptr = contribution_ranges(prob.nblist)
+    p0, p1 = peer_pair_ranges(prob.nblist.nrj, world)[rank]
+    a0, a1 = peer_atom_ranges(atom_ptr, world)[rank]
+    shard = copy.copy(prob)
+    shard.nblist = prob.nblist.slice_pairs(p0, p1)
+    mine = oracle.run_port(shard, ALL)
+    want = oracle.run_port(prob, ALL)
+    # forces: contributions of every rank to the atoms this rank owns
+    f = torch.from_numpy(np.asarray(mine["f"], np.float64).copy())
+    dist.all_reduce(f)
+    owned = np.zeros(prob.natoms, bool)
+    owned[touched[a0:a1]] = True
+    f_owned = np.where(owned[:, None], f.numpy(), 0.0)
+    gathered = torch.from_numpy(f_owned.copy())
+    dist.all_reduce(gathered)  # the union of the owners' slices is the full force array
+    ok = np.max(np.abs(gathered.numpy() - want["f"])) <= 1e-10 * np.max(np.abs(want["f"]))
+    ok = ok and not np.any(f_owned[~owned])
+    for k in ("fshift", "Vc", "Vv", "dvdl", "foreign_energy", "foreign_dvdl"):
+        t = torch.from_numpy(np.asarray(mine[k], np.float64).copy())
+        dist.all_reduce(t)
+        ok = ok and np.max(np.abs(t.numpy() - want[k])) <= 1e-10 * max(np.max(np.abs(want[k])), 1e-12)
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        with open(result_file, "w") as fh:
+            fh.write("ok" if int(flag.item()) == 1 else "mismatch")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_exchange_data_flow_gloo(world, tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    result = str(tmp_path / "result.txt")
+    mp.spawn(_fused_worker, args=(world, _free_port(), root, result), nprocs=world, join=True)
+    assert open(result).read() == "ok"
