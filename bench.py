@@ -12,8 +12,9 @@ P * (1 + (L+1)) pair-interactions -- the reference's own count of kernel work.
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, device time (CUDA events, max over
 ranks), L2 flushed between steps.  `e2e`: the same step through the public call with HOST buffers
-(fepb200_compute: pinned staging, H2D of the touched coordinates, kernels, D2H of the result block,
-scatter-add into the caller's force array), wall clock.  `roofline`: the dominant kernel
+(fepb200_compute: pinned staging, H2D of the touched coordinates, kernels, the result block written
+into pinned host memory by the last kernel, scatter-add into the caller's force array; at N > 1
+upload / kernels + reduction / download of the result block), wall clock.  `roofline`: the dominant kernel
 (fep_foreign_kernel) against the FP32 pipe.  `cpu_baseline` / --impl reference: the reference's
 own CPU SIMD kernel (oracle/_ref, compiled from the reference's sources) on this box's host cores.
 """
@@ -325,6 +326,13 @@ def run_ours(args, name):
                     algorithmic_flop_per_launch=alg_flop, passes_in_launch=passes_in_launch,
                     kernel_ms=dict(pass_kernel=k_pass, foreign_kernel=k_foreign, epilogue_kernel=k_epi),
                     pair_points_per_s=my_pairs * passes_in_launch / (k_foreign * 1e-3) if k_foreign > 0 else 0.0,
+                    # the whole step against the same roof: all passes the reference would run
+                    # (1 + (L+1)) at its own flop count, over the step's device time (`value`'s clock)
+                    step=dict(algorithmic_flop=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"],
+                              achieved=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"]
+                              / (ms_per_step * 1e-3) / 1e12,
+                              frac=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"]
+                              / (ms_per_step * 1e-3) / 1e12 / (fp32_peak * world)),
                     hbm=dict(algorithmic_bytes_per_step=alg_bytes,
                              achieved_gbs=alg_bytes / ((k_pass + k_foreign + k_epi) * 1e-3) / 1e9,
                              peak_gbs=peaks["hbm_gbs"]))

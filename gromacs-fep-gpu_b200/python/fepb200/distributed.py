@@ -149,6 +149,10 @@ class ShardedFep:
     def step(self, x, shiftvec, flags: int, out: dict | None = None) -> dict:
         """Host buffers in, reduced host buffers out ("fused": the forces of the atoms this rank owns and
         all scalars; "p2p" / "nccl": every rank receives the full result)."""
+        if self.world == 1:
+            # one GPU: the public call itself (fepb200_compute: the epilogue writes the result block
+            # straight into pinned host memory, no device-to-host copy)
+            return self.ctx.compute(x, shiftvec, flags, out)
         self.ctx.upload_x(x, shiftvec)
         self.launch(flags)
         return self.ctx.download(flags, out)
