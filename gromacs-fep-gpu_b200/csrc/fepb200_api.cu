@@ -413,10 +413,20 @@ int prepare_buffers(fepb200_ctx* c)
         {
             k.fuse_pass_and_foreign = std::atoi(env) != 0;
         }
-        /* occupancy of the very kernels the step will launch (cudaOccupancyMaxActiveBlocksPerMultiprocessor) */
-        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign),
+        /* occupancy of the very kernels the step will launch (cudaOccupancyMaxActiveBlocksPerMultiprocessor).
+         * FEPB200_FOREIGN_CTAS_PER_SM / FEPB200_PASS_CTAS_PER_SM size the grids for fewer resident CTAs
+         * than fit (experiment: a pass grid and a foreign grid that are co-resident on every SM and
+         * fill each other's stalls, instead of one full wave after the other) */
+        auto per_sm = [](const char* env, int occ) {
+            const char* e = std::getenv(env);
+            const int   v = e ? std::atoi(e) : 0;
+            return v > 0 ? std::min(v, occ) : occ;
+        };
+        tiles(per_sm("FEPB200_FOREIGN_CTAS_PER_SM",
+                     fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign)),
               k.tile_pairs, k.n_tiles);
-        tiles(fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1), k.pass_tile_pairs, k.pass_n_tiles);
+        tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)),
+              k.pass_tile_pairs, k.pass_n_tiles);
     }
     else
     {
@@ -1810,6 +1820,39 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
         CU_CHECK(c, cudaEventRecord(c->ev_stop, stream));
     }
     c->timed = true;
+    return FEPB200_OK;
+}
+
+int fepb200_add_forces_device(fepb200_ctx* c, float* d_f, int flags)
+{
+    if (!c || !d_f)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_add_forces_device: NULL argument");
+    }
+    int rc = check_ready(c);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    if (c->result_on_host)
+    {
+        return fail(c, FEPB200_ERR_STATE,
+                    "fepb200_add_forces_device: the last step was a fepb200_compute(), whose results live in host memory; "
+                    "use fepb200_launch()");
+    }
+    cudaSetDevice(c->device);
+    close_chain(c);
+    /* the context's own result block: what fepb200_launch() fills (unless a partial block was set
+     * for the peer reduction) and what fepb200_reduce_peers() leaves the sum over ranks in */
+    const float* r32 = c->ka.res_f32;
+    const int    k0  = c->px_on ? c->x_atom_begin : 0;
+    const int    k1  = c->px_on ? c->x_atom_end : c->layout.ntouched;
+    const int    err = fep_launch_add_forces(r32, c->d_touched.ptr, d_f, k0, k1, (flags & FEPB200_CLEAR_OUTPUTS) != 0 ? 1 : 0,
+                                             c->stream, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "force scatter launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
     return FEPB200_OK;
 }
 

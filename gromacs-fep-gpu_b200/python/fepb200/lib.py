@@ -68,6 +68,7 @@ SYMBOLS = {
     "fepb200_upload_x": (ctypes.c_int, [_VP, _FP, _FP]),
     "fepb200_gather_x_device": (ctypes.c_int, [_VP, _VP, _FP]),
     "fepb200_launch": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
+    "fepb200_add_forces_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int]),
     "fepb200_wait": (ctypes.c_int, [_VP]),
     "fepb200_result_device_ptrs": (ctypes.c_int, [_VP, ctypes.POINTER(_VP), ctypes.POINTER(_VP)]),
     "fepb200_result_block_bytes": (ctypes.c_size_t, [_VP]),
@@ -291,6 +292,10 @@ class FepContext:
 
     def launch(self, flags: int, stream: int | None = None) -> None:
         self._check(self._lib.fepb200_launch(self._h, int(flags), _VP(stream) if stream else None))
+
+    def add_forces_device(self, d_f_ptr: int, flags: int = 0) -> None:
+        """Add the forces of the last launch() into a device-resident float[natoms][3] array."""
+        self._check(self._lib.fepb200_add_forces_device(self._h, _VP(d_f_ptr), int(flags)))
 
     def wait(self) -> None:
         self._check(self._lib.fepb200_wait(self._h))

@@ -208,6 +208,16 @@ int fepb200_gather_x_device(fepb200_ctx* ctx, const float* d_x, const float* shi
 /* Launch all kernels of one step on `stream` (a cudaStream_t; NULL = the context's
  * stream).  Results stay in the device result block.  Asynchronous. */
 int fepb200_launch(fepb200_ctx* ctx, int flags, void* stream);
+/* Device-resident hand-off of the forces (replaces what the fork does with atomic adds
+ * into its nbat force buffer followed by nbnxn_gpu_add_nbat_f_to_f, nbnxm/atomdata.cpp:930-964, and
+ * the host scatter at the end of fepb200_download()): adds the forces of the last fepb200_launch()
+ * into d_f, a device-resident rvec[natoms] array in the caller's index space (the space of d_x of
+ * fepb200_gather_x_device), on the context's stream; with FEPB200_CLEAR_OUTPUTS in flags the
+ * entries of the atoms that occur in the pair list are overwritten instead.  Asynchronous.  After
+ * fepb200_reduce_peers() the sum over ranks is added; with the fused exchange the forces of the
+ * atoms this rank owns.  Energies, dV/dlambda and shift forces still come from fepb200_download()
+ * (call it with FEPB200_DO_FORCE cleared to skip the force copy). */
+int fepb200_add_forces_device(fepb200_ctx* ctx, float* d_f, int flags);
 /* Block until the context's stream is idle. */
 int fepb200_wait(fepb200_ctx* ctx);
 /* Device pointers of the result block: f32 part and f64 part (see fepb200_layout). */
