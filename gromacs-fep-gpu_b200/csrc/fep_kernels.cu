@@ -388,7 +388,7 @@ __device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
 /* PEER: the exchange of fep_types.h.  STRONG: peer data is read with system-scope strong loads
  * (ld.volatile) instead of plain loads ordered by the barrier's acquire (FEPB200_PEER_LOAD=strong;
  * measured slower by far, kept for diagnosis). */
-template<bool PEER, bool STRONG>
+template<bool PEER, bool STRONG, int LANES>
 __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_constant__ KernelArgs ka,
                                                                   const EpilogueLayout lay, const StepFlags sf)
 {
@@ -647,7 +647,6 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         /* PEER: this rank sums the atoms it owns (the forces are reduce-scattered by atom range);
          * a remote round trip costs the same for 4 lanes as for 8, and half the threads means half
          * the waves of blocks */
-        constexpr int LANES = PEER ? FEP_EPI_LANES_PEER : FEP_EPI_LANES;
         const int atom     = (PEER ? ka.px.atom_begin : 0) + b * (FEP_EPI_CTA / LANES) + (tid / LANES);
         const int atom_end = PEER ? ka.px.atom_end : ka.n_touched;
         const int sub      = tid % LANES;
@@ -989,7 +988,15 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     const int      n_atoms = peer ? ka.px.atom_end - ka.px.atom_begin : ka.n_touched;
     EpilogueLayout lay;
     const int      n_heavy = peer ? ka.px.heavy_end - ka.px.heavy_begin : ka.n_heavy;
-    const int      per_blk = FEP_EPI_CTA / (peer ? FEP_EPI_LANES_PEER : FEP_EPI_LANES);
+    /* lanes per light atom: FEP_EPI_LANES, or FEPB200_EPI_LANES = 2 | 4 | 8 (experiment: with the heavy
+     * atoms in their own role, fewer lanes mean fewer blocks and waves; the same value must be used on
+     * every rank, and it fixes the summation order, i.e. the last bits of the forces) */
+    static const int lanes = [] {
+        const char* e = std::getenv("FEPB200_EPI_LANES");
+        const int   v = e ? std::atoi(e) : 0;
+        return (v == 2 || v == 4 || v == 8) ? v : FEP_EPI_LANES;
+    }();
+    const int      per_blk = FEP_EPI_CTA / lanes;
     lay.atom_blocks   = sf.force ? (n_atoms + per_blk - 1) / per_blk : 0;
     lay.heavy_blocks  = sf.force ? (n_heavy + FEP_EPI_CTA / 32 - 1) / (FEP_EPI_CTA / 32) : 0;
     /* jobs are ordered shift jobs first, then energy-group jobs */
@@ -999,6 +1006,23 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     lay.job_blocks    = j1 > j0 ? j1 - j0 : 0;
     lay.scalar_blocks = 2 + ((sf.foreign && ka.n_points > 0) ? 3 * ka.n_points : 0);
     const int blocks  = lay.atom_blocks + lay.heavy_blocks + lay.job_blocks + lay.scalar_blocks;
+    const dim3 grid(blocks), block(FEP_EPI_CTA);
+#define FEP_EPI_LAUNCH(P, S)                                                                                 \
+    do                                                                                                       \
+    {                                                                                                        \
+        if (lanes == 2)                                                                                      \
+        {                                                                                                    \
+            fep_launch_kernel(fep_epilogue_kernel<P, S, 2>, grid, block, stream, chain, ka, lay, sf);        \
+        }                                                                                                    \
+        else if (lanes == 4)                                                                                 \
+        {                                                                                                    \
+            fep_launch_kernel(fep_epilogue_kernel<P, S, 4>, grid, block, stream, chain, ka, lay, sf);        \
+        }                                                                                                    \
+        else                                                                                                 \
+        {                                                                                                    \
+            fep_launch_kernel(fep_epilogue_kernel<P, S, FEP_EPI_LANES>, grid, block, stream, chain, ka, lay, sf); \
+        }                                                                                                    \
+    } while (0)
     if (peer)
     {
         static const bool strong = [] {
@@ -1007,17 +1031,18 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
         }();
         if (strong)
         {
-            fep_launch_kernel(fep_epilogue_kernel<true, true>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+            FEP_EPI_LAUNCH(true, true);
         }
         else
         {
-            fep_launch_kernel(fep_epilogue_kernel<true, false>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+            FEP_EPI_LAUNCH(true, false);
         }
     }
     else
     {
-        fep_launch_kernel(fep_epilogue_kernel<false, false>, dim3(blocks), dim3(FEP_EPI_CTA), stream, chain, ka, lay, sf);
+        FEP_EPI_LAUNCH(false, false);
     }
+#undef FEP_EPI_LAUNCH
     (*counter)++;
     if (ev)
     {

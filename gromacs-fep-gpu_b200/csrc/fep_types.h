@@ -43,8 +43,6 @@
 #define FEP_RED_CHUNK 2048 /* segments per reduction job of the epilogue */
 #define FEP_EPI_CTA 256
 #define FEP_EPI_LANES 8 /* lanes per touched atom in the epilogue (32 contributions per trip; 4 lanes measured slower) */
-#define FEP_EPI_LANES_PEER 8 /* the same when the contributions are read over NVLink; equal to FEP_EPI_LANES so that the
-                                summation order, and with it every force bit, is the one of the single-GPU path */
 #define FEP_HEAVY_MIN 32 /* atoms with more force contributions than this are summed by a whole warp */
 #define FEP_HEAVY_LOADS 8 /* independent 16-byte loads per lane and trip of that warp (256 contributions per trip) */
 
