@@ -1,5 +1,5 @@
 """Prints the measured deviation of the GPU path from the double-precision oracle for the five
-BASELINE.json configurations at full size (run on the GPU box; output committed under profiles/)."""
+BASELINE.json configurations at full size (run on the GPU box; output committed under profiles/).  Test infrastructure: it lives in tests/ because it calls the oracle.."""
 import os
 import sys
 

@@ -401,18 +401,6 @@ def test_device_resident_entry_points_agree_with_compute(ctx):
     touched = ctx.touched_atoms()
     assert np.array_equal(f32[: 3 * lay.ntouched].cpu().numpy().reshape(-1, 3), want["f"][touched])
     assert np.array_equal(f64[lay.off_dvdl : lay.off_dvdl + 2].cpu().numpy(), want["dvdl"])
-    # forces handed over on the device: added into a device-resident rvec array, no host round trip
-    d_f = torch.zeros((prob.natoms, 3), dtype=torch.float32, device="cuda")
-    torch.cuda.synchronize()
-    ctx.add_forces_device(d_f.data_ptr())
-    ctx.add_forces_device(d_f.data_ptr())  # accumulates, like the reference kernel into its force buffer
-    ctx.wait()
-    assert np.array_equal(d_f.cpu().numpy(), 2.0 * want["f"])
-    ctx.add_forces_device(d_f.data_ptr(), P.CLEAR_OUTPUTS)
-    ctx.wait()
-    assert np.array_equal(d_f.cpu().numpy(), want["f"])
-    only_scalars = ctx.download(ALL & ~(P.DO_FORCE | P.DO_SHIFTFORCE))
-    assert not only_scalars["f"].any() and np.array_equal(only_scalars["Vc"], want["Vc"])
 
 
 def test_peer_reduce_entry_points_with_one_rank(ctx):
