@@ -793,17 +793,18 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
 #undef FEP_EPI_SYNC_POINT
 }
 
-/* coordinates of the touched atoms from a device-resident rvec[natoms] array */
-__global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restrict__ x, const int* __restrict__ touched,
-                                                          float* __restrict__ pos3, int n)
+/* coordinates of the touched atoms from a device-resident array of `stride` floats per atom:
+ * rvec[natoms] (stride 3) or the xyzq float4[natoms] of the nbnxm GPU atom data (stride 4) */
+__global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restrict__ x, int stride,
+                                                          const int* __restrict__ touched, float* __restrict__ pos3, int n)
 {
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k < n)
     {
-        const size_t a = (size_t)touched[k];
-        pos3[3 * (size_t)k]     = x[3 * a];
-        pos3[3 * (size_t)k + 1] = x[3 * a + 1];
-        pos3[3 * (size_t)k + 2] = x[3 * a + 2];
+        const size_t a = (size_t)stride * (size_t)touched[k];
+        pos3[3 * (size_t)k]     = x[a];
+        pos3[3 * (size_t)k + 1] = x[a + 1];
+        pos3[3 * (size_t)k + 2] = x[a + 2];
     }
 }
 
@@ -1179,12 +1180,12 @@ extern "C" int fep_launch_add_forces(const float* res_f32, const int* d_touched,
     return (int)cudaGetLastError();
 }
 
-extern "C" int fep_launch_gather_x(const float* d_x, const int* d_touched, float* pos3, int n_touched,
+extern "C" int fep_launch_gather_x(const float* d_x, int stride, const int* d_touched, float* pos3, int n_touched,
                                    cudaStream_t stream, long long* counter)
 {
     if (n_touched > 0)
     {
-        fep_gather_x_kernel<<<(n_touched + 255) / 256, 256, 0, stream>>>(d_x, d_touched, pos3, n_touched);
+        fep_gather_x_kernel<<<(n_touched + 255) / 256, 256, 0, stream>>>(d_x, stride, d_touched, pos3, n_touched);
         (*counter)++;
     }
     return (int)cudaGetLastError();

@@ -203,8 +203,8 @@ struct PeerPtrs
 int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flags, int rank, unsigned int seq, int nranks,
                            double* out_f64, int n64, size_t f64_bytes, float* out_f32, long long n32,
                            cudaStream_t stream, long long* launch_counter, int chained);
-int fep_launch_gather_x(const float* d_x, const int* d_touched, float* pos3, int n_touched, cudaStream_t stream,
-                        long long* launch_counter);
+int fep_launch_gather_x(const float* d_x, int stride, const int* d_touched, float* pos3, int n_touched,
+                        cudaStream_t stream, long long* launch_counter);
 int fep_launch_add_forces(const float* res_f32, const int* d_touched, float* d_f, int k0, int k1, int overwrite,
                           cudaStream_t stream, long long* launch_counter);
 #ifdef __cplusplus

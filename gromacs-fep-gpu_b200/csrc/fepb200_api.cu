@@ -1707,7 +1707,7 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
     return FEPB200_OK;
 }
 
-int fepb200_gather_x_device(fepb200_ctx* c, const float* d_x, const float* shiftvec)
+static int gather_x_device(fepb200_ctx* c, const float* d_x, int stride, const float* shiftvec)
 {
     if (!c || !d_x || !shiftvec)
     {
@@ -1727,7 +1727,7 @@ int fepb200_gather_x_device(fepb200_ctx* c, const float* d_x, const float* shift
     CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr, c->h_step_in.ptr, sizeof(DynHead), cudaMemcpyHostToDevice,
                                 c->stream));
     c->staging_in_flight = true;
-    const int err = fep_launch_gather_x(d_x, c->d_touched.ptr,
+    const int err = fep_launch_gather_x(d_x, stride, c->d_touched.ptr,
                                         reinterpret_cast<float*>(c->d_step_in.ptr + sizeof(DynHead)),
                                         c->layout.ntouched, c->stream, &c->launches);
     if (err != 0)
@@ -1735,6 +1735,16 @@ int fepb200_gather_x_device(fepb200_ctx* c, const float* d_x, const float* shift
         return fail(c, FEPB200_ERR_CUDA, "gather kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
     }
     return FEPB200_OK;
+}
+
+int fepb200_gather_x_device(fepb200_ctx* c, const float* d_x, const float* shiftvec)
+{
+    return gather_x_device(c, d_x, 3, shiftvec);
+}
+
+int fepb200_gather_xq_device(fepb200_ctx* c, const float* d_xq, const float* shiftvec)
+{
+    return gather_x_device(c, d_xq, 4, shiftvec);
 }
 
 int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)

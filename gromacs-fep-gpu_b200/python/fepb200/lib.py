@@ -67,6 +67,7 @@ SYMBOLS = {
     "fepb200_compute": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, _FP, _DP, _DP, _DP, _DP, _DP]),
     "fepb200_upload_x": (ctypes.c_int, [_VP, _FP, _FP]),
     "fepb200_gather_x_device": (ctypes.c_int, [_VP, _VP, _FP]),
+    "fepb200_gather_xq_device": (ctypes.c_int, [_VP, _VP, _FP]),
     "fepb200_launch": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "fepb200_add_forces_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int]),
     "fepb200_wait": (ctypes.c_int, [_VP]),
@@ -289,6 +290,11 @@ class FepContext:
     def gather_x_device(self, d_x_ptr: int, shiftvec) -> None:
         sv = _f32(shiftvec)
         self._check(self._lib.fepb200_gather_x_device(self._h, _VP(d_x_ptr), _pf(sv)))
+
+    def gather_xq_device(self, d_xq_ptr: int, shiftvec) -> None:
+        """Coordinates from a device-resident float4[natoms] {x, y, z, q} array (the nbnxm GPU atom data)."""
+        sv = _f32(shiftvec)
+        self._check(self._lib.fepb200_gather_xq_device(self._h, _VP(d_xq_ptr), _pf(sv)))
 
     def launch(self, flags: int, stream: int | None = None) -> None:
         self._check(self._lib.fepb200_launch(self._h, int(flags), _VP(stream) if stream else None))

@@ -205,6 +205,12 @@ int fepb200_compute(fepb200_ctx* ctx, const float* x, const float* shiftvec, int
 int fepb200_upload_x(fepb200_ctx* ctx, const float* x, const float* shiftvec);
 /* Or gather them on the device from a device-resident rvec[natoms] array. */
 int fepb200_gather_x_device(fepb200_ctx* ctx, const float* d_x, const float* shiftvec);
+/* The same from the xyzq array of the nbnxm GPU atom data, float4[natoms] with the charge in .w
+ * (NBAtomDataGpu::xq, nbnxm/gpu_types_common.h:103-157, which the fork's FEP kernels read): with a
+ * pair list in nbat (grid) indices -- the index space the fork uses after its inverse map,
+ * nbnxm_gpu_data_mgmt.cpp:763-787 -- coordinates never leave the device.  The .w component is
+ * ignored: charges of both states come from fepb200_set_atoms(). */
+int fepb200_gather_xq_device(fepb200_ctx* ctx, const float* d_xq, const float* shiftvec);
 /* Launch all kernels of one step on `stream` (a cudaStream_t; NULL = the context's
  * stream).  Results stay in the device result block.  Asynchronous. */
 int fepb200_launch(fepb200_ctx* ctx, int flags, void* stream);

@@ -21,8 +21,10 @@
 
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "gromacs/utility/fatalerror.h"
@@ -45,13 +47,36 @@ struct Api
     decltype(&fepb200_compute)     compute     = nullptr;
     fepb200_ctx*                   ctx         = nullptr;
     bool                           tried = false, ok = false;
-    long                           calls = 0;
+    long                           calls = 0, searchCalls = 0;
+    /* what the library holds, so that only changes are handed over between search steps */
+    fepb200_params     lastParams{};
+    std::vector<float> lastLambda, lastAllCoul, lastAllVdw;
+    /* wall time spent in here, printed at exit (the same interval the "NB FEP" cycle counter sees) */
+    double secondsSearch = 0, secondsStep = 0;
 };
+
+inline double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 inline Api& api()
 {
     static Api a;
     return a;
+}
+
+inline void report()
+{
+    Api& a = api();
+    if (a.calls > 0)
+    {
+        std::fprintf(stderr,
+                     "fepb200 shim: %ld calls (%ld with a new pair list); per call %.1f us for the step "
+                     "(fepb200_compute + result routing), per new list %.1f us (set_atoms + set_list)\n",
+                     a.calls, a.searchCalls, 1e6 * a.secondsStep / a.calls,
+                     a.searchCalls > 0 ? 1e6 * a.secondsSearch / a.searchCalls : 0.0);
+    }
 }
 
 inline bool enabled()
@@ -103,6 +128,7 @@ inline void load()
         gmx_fatal(FARGS, "fepb200_create failed (%d): %s", rc, a.last_error(nullptr));
     }
     std::fprintf(stderr, "NOTE: perturbed non-bonded pairs are computed by %s\n", a.describe(a.ctx));
+    std::atexit(report);
     a.ok = true;
 }
 
@@ -160,49 +186,73 @@ inline void dispatch(const PairlistSets&                              pairlistSe
     load();
     Api& a = api();
 
-    /* constants: cheap, set every call so that nothing can go stale (lambda may change per step) */
-    const fepb200_params p = toParams(ic);
-    check(a.set_params(a.ctx, &p), "set_params");
-    check(a.set_nbfp(a.ctx, ntype, nbfp.data(), nbfp_grid.empty() ? nullptr : nbfp_grid.data()), "set_nbfp");
-    check(a.set_atoms(a.ctx, static_cast<int>(chargeA.size()), chargeA.data(), chargeB.data(), typeA.data(),
-                      typeB.data()),
-          "set_atoms");
+    const double t0 = now();
+    /* Cadence of the reference hooks these calls replace: constants when they change
+     * (PME tuning may move rcoulomb / ewaldcoeff_q), atoms and pair list on search steps
+     * (constructPairlist, pairlist.cpp:4437-4468; atom properties change with the DD partitioning,
+     * which happens on search steps only), lambdas when they change, coordinates every step. */
+    const bool           search = stepWork.doNeighborSearch || a.calls == 0;
+    const fepb200_params p      = toParams(ic);
+    if (search || std::memcmp(&p, &a.lastParams, sizeof(p)) != 0)
+    {
+        check(a.set_params(a.ctx, &p), "set_params");
+        a.lastParams = p;
+    }
+    if (search)
+    {
+        check(a.set_nbfp(a.ctx, ntype, nbfp.data(), nbfp_grid.empty() ? nullptr : nbfp_grid.data()), "set_nbfp");
+        check(a.set_atoms(a.ctx, static_cast<int>(chargeA.size()), chargeA.data(), chargeB.data(), typeA.data(),
+                          typeB.data()),
+              "set_atoms");
+    }
     const int          nLambda = fepvals->n_lambda;
-    std::vector<float> allCoul(nLambda), allVdw(nLambda);
+    std::vector<float> allCoul(nLambda), allVdw(nLambda), lam(lambda.begin(), lambda.end());
     for (int i = 0; i < nLambda; i++)
     {
         allCoul[i] = static_cast<float>(fepvals->all_lambda[FreeEnergyPerturbationCouplingType::Coul][i]);
         allVdw[i]  = static_cast<float>(fepvals->all_lambda[FreeEnergyPerturbationCouplingType::Vdw][i]);
     }
-    check(a.set_lambdas(a.ctx, lambda.data(), nLambda, allCoul.data(), allVdw.data()), "set_lambdas");
-
-    /* the FEP pair lists of all localities and threads, concatenated (what the fork's
-     * combine_fep_lists does for its GPU path, pairlist.cpp:2867) */
-    std::vector<int> iinr, gid, shift, jindex(1, 0), jjnr, excl;
-    const int        numLocalities = (pairlistSets.params().haveMultipleDomains ? 2 : 1);
-    for (int l = 0; l < numLocalities; l++)
+    if (search || lam != a.lastLambda || allCoul != a.lastAllCoul || allVdw != a.lastAllVdw)
     {
-        const auto lists = pairlistSets.pairlistSet(static_cast<gmx::InteractionLocality>(l)).fepLists();
-        for (const auto& nl : lists)
+        check(a.set_lambdas(a.ctx, lambda.data(), nLambda, allCoul.data(), allVdw.data()), "set_lambdas");
+        a.lastLambda  = lam;
+        a.lastAllCoul = allCoul;
+        a.lastAllVdw  = allVdw;
+    }
+
+    const int numGroupPairs = enerd->grpp.nener;
+    if (search)
+    {
+        /* the FEP pair lists of all localities and threads, concatenated (what the fork's
+         * combine_fep_lists does for its GPU path, pairlist.cpp:2867) */
+        std::vector<int> iinr, gid, shift, jindex(1, 0), jjnr, excl;
+        const int        numLocalities = (pairlistSets.params().haveMultipleDomains ? 2 : 1);
+        for (int l = 0; l < numLocalities; l++)
         {
-            for (int n = 0; n < nl->nri; n++)
+            const auto lists = pairlistSets.pairlistSet(static_cast<gmx::InteractionLocality>(l)).fepLists();
+            for (const auto& nl : lists)
             {
-                iinr.push_back(nl->iinr[n]);
-                gid.push_back(nl->gid[n]);
-                shift.push_back(nl->shift[n]);
-                for (int k = nl->jindex[n]; k < nl->jindex[n + 1]; k++)
+                for (int n = 0; n < nl->nri; n++)
                 {
-                    jjnr.push_back(nl->jjnr[k]);
-                    excl.push_back(nl->excl_fep[k]);
+                    iinr.push_back(nl->iinr[n]);
+                    gid.push_back(nl->gid[n]);
+                    shift.push_back(nl->shift[n]);
+                    for (int k = nl->jindex[n]; k < nl->jindex[n + 1]; k++)
+                    {
+                        jjnr.push_back(nl->jjnr[k]);
+                        excl.push_back(nl->excl_fep[k]);
+                    }
+                    jindex.push_back(static_cast<int>(jjnr.size()));
                 }
-                jindex.push_back(static_cast<int>(jjnr.size()));
             }
         }
+        check(a.set_list(a.ctx, static_cast<int>(iinr.size()), iinr.data(), gid.data(), shift.data(), jindex.data(),
+                         jjnr.data(), excl.data(), numGroupPairs, 0, 1),
+              "set_list");
+        a.searchCalls++;
     }
-    const int numGroupPairs = enerd->grpp.nener;
-    check(a.set_list(a.ctx, static_cast<int>(iinr.size()), iinr.data(), gid.data(), shift.data(), jindex.data(),
-                     jjnr.data(), excl.data(), numGroupPairs, 0, 1),
-          "set_list");
+    const double t1 = now();
+    a.secondsSearch += search ? t1 - t0 : 0.0;
 
     int flags = FEPB200_DO_SR; /* freeenergydispatch.cpp:169-184 */
     if (stepWork.computeForces)
@@ -256,6 +306,7 @@ inline void dispatch(const PairlistSets&                              pairlistSe
         }
     }
     a.calls++;
+    a.secondsStep += now() - t1;
 }
 
 } // namespace fepb200shim

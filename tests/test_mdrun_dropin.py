@@ -20,7 +20,11 @@ GMX = os.path.join(ROOT, "integration", "_gmx", "bin", "gmx")
 GMXLIBDIR = os.path.join(ROOT, "integration", "_gmx", "lib")
 TPR = os.path.join(ROOT, "tests", "golden", "mdrun_tpr")
 LIB = os.path.join(ROOT, "gromacs-fep-gpu_b200", "lib", "libfepb200.so")
-SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwtogether", "transformAtoB", "vdwalone"]
+SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwtogether", "transformAtoB", "vdwalone",
+           # BASELINE.json's configs[0] and configs[1] as real GROMACS systems (integration/systems/make_systems.py):
+           # methane decoupling in a 2.65 k-atom TIP3P box, one lambda; a 50-atom solute transformed A -> B in a
+           # 24.5 k-atom box with 20 lambda states and foreign-energy output
+           "c1_methane", "c2_hexadecane"]
 
 
 def _xvg(path):
@@ -68,6 +72,39 @@ def _run(tpr, workdir, use_gpu):
     return r.stderr, terms, _xvg(os.path.join(workdir, "terms.xvg")), _xvg(os.path.join(workdir, "dh.xvg"))
 
 
+def _nb_fep_ms_per_call(workdir):
+    """Wall time per call of the "NB FEP" (+ "NB FEP reduction") cycle sub-counters of md.log -- the
+    reference's own clock around the perturbed-pair kernels (timing/wallcycle.cpp:169-170; the hook of
+    the patch sits inside the same counter).  None when gmx was built without GMX_CYCLE_SUBCOUNTERS."""
+    total, calls = 0.0, 0
+    for line in open(os.path.join(workdir, "run.log")):
+        if line.startswith(" NB FEP"):
+            parts = line.split()
+            k = 3 if parts[2] == "reduction" else 2  # name, ranks, threads, count, wall t (s), ...
+            try:
+                calls = max(calls, int(parts[k + 2]))
+                total += float(parts[k + 3])
+            except (IndexError, ValueError):
+                return None
+    return 1e3 * total / calls if calls else None
+
+
+def _note_timing(system, cpu_dir, gpu_dir, err_gpu):
+    cpu, gpu = _nb_fep_ms_per_call(cpu_dir), _nb_fep_ms_per_call(gpu_dir)
+    shim = [ln for ln in err_gpu.splitlines() if ln.startswith("fepb200 shim:")]
+    line = (f"{system}: NB FEP per call, reference CPU kernel (2 OpenMP threads) "
+            f"{'n/a' if cpu is None else f'{cpu:.3f} ms'}, through libfepb200 {'n/a' if gpu is None else f'{gpu:.3f} ms'}"
+            f"{' | ' + shim[0] if shim else ''}")
+    print(line)
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "mdrun_dropin_timing.txt"), "a") as fh:
+            fh.write(line + "\n")
+    except OSError:
+        pass
+
+
 @pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
 @pytest.mark.parametrize("system", SYSTEMS)
 def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, tmp_path):
@@ -77,6 +114,7 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
     err_cpu, terms_cpu, e_cpu, dh_cpu = _run(tpr, str(tmp_path / "cpu"), False)
     err_gpu, terms_gpu, e_gpu, dh_gpu = _run(tpr, str(tmp_path / "gpu"), True)
     assert "computed by fepb200" in err_gpu and "computed by fepb200" not in err_cpu
+    _note_timing(system, str(tmp_path / "cpu"), str(tmp_path / "gpu"), err_gpu)
     assert terms_cpu == terms_gpu and e_cpu.shape == e_gpu.shape and e_cpu.shape[0] >= 20
     # per-step energies and dV/dlambda components (every step), relative to the size of the quantity
     for col, name in enumerate(terms_cpu, start=1):

@@ -59,3 +59,51 @@ def test_hand_off_refuses_results_that_live_in_host_memory(ctx):
     d_f = torch.zeros((prob.natoms, 3), dtype=torch.float32, device="cuda")
     with pytest.raises(FepError):
         ctx.add_forces_device(d_f.data_ptr())
+
+
+def test_nbat_style_hand_off_xyzq_in_forces_out_in_a_permuted_index_space(ctx):
+    """What the nbnxm GPU module holds: atoms in grid order, coordinates as float4
+    {x,y,z,q}, forces as float3 in the same order.  The pair list is handed over in that index space
+    (the fork remaps it the same way, nbnxm_gpu_data_mgmt.cpp:763-787); coordinates are gathered from
+    the xyzq array and forces added into the device force array without touching the host.  Compared
+    with the same problem in the original order through fepb200_compute(): the pairs and their order
+    are the same, so the results are bit-identical up to the permutation."""
+    import copy
+
+    import torch
+
+    prob = make_system(scaled_spec("C2", 3.2, 1, 20, n_foreign=4))
+    ctx.set_problem(prob)
+    want = ctx.compute(prob.x, prob.shiftvec, ALL)
+
+    rng = np.random.default_rng(7)
+    n = prob.natoms
+    new_of_old = rng.permutation(n).astype(np.int32)  # "grid" index of every atom
+    old_of_new = np.argsort(new_of_old)
+    grid = copy.copy(prob)
+    grid.nblist = copy.copy(prob.nblist)
+    grid.nblist.iinr = new_of_old[prob.nblist.iinr]
+    grid.nblist.jjnr = new_of_old[prob.nblist.jjnr]
+    for name in ("qA", "qB", "typeA", "typeB"):
+        setattr(grid, name, np.ascontiguousarray(getattr(prob, name)[old_of_new]))
+    grid.x = np.ascontiguousarray(prob.x[old_of_new])
+    ctx.set_problem(grid)
+
+    xq = np.zeros((n, 4), np.float32)
+    xq[:, :3] = grid.x
+    xq[:, 3] = 123.0  # must be ignored
+    d_xq = torch.from_numpy(xq).cuda()
+    d_f = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.gather_xq_device(d_xq.data_ptr(), prob.shiftvec)
+    ctx.launch(ALL)
+    ctx.add_forces_device(d_f.data_ptr())
+    ctx.wait()
+    got = ctx.download(ALL & ~P.DO_FORCE)
+    f_grid = d_f.cpu().numpy()
+    # the touched-atom numbering (and with it the order of the per-atom sums) follows the index
+    # space, so forces agree to rounding, not bit for bit
+    scale = np.sqrt(np.mean(want["f"] ** 2))
+    assert np.sqrt(np.mean((f_grid[new_of_old] - want["f"]) ** 2)) <= 1e-6 * scale
+    for k in ("Vc", "Vv", "dvdl", "foreign_energy"):
+        assert np.allclose(got[k], want[k], rtol=1e-6, atol=1e-6 * np.max(np.abs(want[k]))), k
