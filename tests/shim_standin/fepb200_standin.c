@@ -1,0 +1,286 @@
+/*
+ * tests/shim_standin/fepb200_standin.c -- TEST INFRASTRUCTURE, not a product path and not a CPU
+ * fallback: a stand-in for libfepb200.so that exports the nine entry points the reference-side
+ * shim binds (integration/gromacs_shim/fepb200_shim.h) and answers them with the CPU oracle
+ * (oracle/fep_oracle.c).  Its only use is tests/test_shim_cpu.py: running the reference's patched
+ * mdrun in a container without a GPU, to check what the SHIM does -- which arrays it hands over and
+ * when (search-step cadence), flag assembly, result routing -- against the reference's own CPU
+ * route.  The real library has no such path: without a CUDA device fepb200_create() fails.
+ *
+ * Semantics follow include/fepb200.h: inputs are copied at set_* time, compute() accumulates (+=).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fepb200.h"
+
+/* oracle/fep_oracle.c */
+typedef struct fep_oracle_params
+{
+    int    eeltype, vdwtype, vdw_modifier;
+    double epsfac, rcoulomb, rvdw, rvdw_switch, krf, crf;
+    double sh_ewald, sh_lj_ewald, ewaldcoeff_q, ewaldcoeff_lj, dispersion_cpot, repulsion_cpot;
+    int    softcoreType;
+    double alphaVdw, alphaCoulomb;
+    int    lambdaPower;
+    double sigma6WithInvalidSigma, sigma6Minimum, gapsysScaleVdW, gapsysScaleCoul, gapsysSigma6VdW;
+} fep_oracle_params;
+int fep_oracle_dispatch(const fep_oracle_params* p, int use_simd, int nthreads, int ntype, const double* nbfp,
+                        const double* nbfp_grid, int natoms, const double* x, const double* qA, const double* qB,
+                        const int* typeA, const int* typeB, const double* shiftvec, int nri, const int* iinr,
+                        const int* gid, const int* shift, const int* jindex, const int* jjnr, const int* excl, int ngrp,
+                        int flags, const double* lambda, int nforeign, const double* all_lambda_coul,
+                        const double* all_lambda_vdw, double* f, double* fshift, double* Vc, double* Vv, double* dvdl,
+                        double* foreign_e, double* foreign_dvdl, int repeats, double* seconds);
+
+struct fepb200_ctx
+{
+    fep_oracle_params p;
+    int               have_params, ntype, natoms, nri, nrj, ngrp, nforeign;
+    double *          nbfp, *nbfp_grid, *qA, *qB, *all_c, *all_v;
+    int *             typeA, *typeB, *iinr, *gid, *shift, *jindex, *jjnr, *excl;
+    double            lambda[FEPB200_NUM_LAMBDA_COMPONENTS];
+    long              n_set_list, n_set_atoms, n_set_params, n_set_lambdas, n_compute;
+    char              err[256];
+};
+
+static double* dup_f2d(const float* a, size_t n)
+{
+    double* d = (double*)malloc(sizeof(double) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++)
+    {
+        d[i] = a[i];
+    }
+    return d;
+}
+static int* dup_i(const int* a, size_t n) /* n is a small non-negative count */
+{
+    int* d = (int*)malloc(sizeof(int) * (n ? n : 1));
+    if (n)
+    {
+        memcpy(d, a, sizeof(int) * n);
+    }
+    return d;
+}
+
+int fepb200_create(fepb200_ctx** ctx, int device_ordinal)
+{
+    (void)device_ordinal;
+    *ctx = (fepb200_ctx*)calloc(1, sizeof(fepb200_ctx));
+    return FEPB200_OK;
+}
+
+int fepb200_destroy(fepb200_ctx* c)
+{
+    free(c);
+    return FEPB200_OK;
+}
+
+const char* fepb200_last_error(const fepb200_ctx* c)
+{
+    return c ? c->err : "";
+}
+
+const char* fepb200_describe(const fepb200_ctx* c)
+{
+    (void)c;
+    return "fepb200 CPU STAND-IN for shim tests (oracle/fep_oracle.c), not the product";
+}
+
+int fepb200_set_params(fepb200_ctx* c, const fepb200_params* q)
+{
+    fep_oracle_params* p      = &c->p;
+    p->eeltype                = q->eeltype;
+    p->vdwtype                = q->vdwtype;
+    p->vdw_modifier           = q->vdw_modifier;
+    p->epsfac                 = q->epsfac;
+    p->rcoulomb               = q->rcoulomb;
+    p->rvdw                   = q->rvdw;
+    p->rvdw_switch            = q->rvdw_switch;
+    p->krf                    = q->reactionFieldCoefficient;
+    p->crf                    = q->reactionFieldShift;
+    p->sh_ewald               = q->sh_ewald;
+    p->sh_lj_ewald            = q->sh_lj_ewald;
+    p->ewaldcoeff_q           = q->ewaldcoeff_q;
+    p->ewaldcoeff_lj          = q->ewaldcoeff_lj;
+    p->dispersion_cpot        = q->dispersion_shift_cpot;
+    p->repulsion_cpot         = q->repulsion_shift_cpot;
+    p->softcoreType           = q->softcoreType;
+    p->alphaVdw               = q->alphaVdw;
+    p->alphaCoulomb           = q->alphaCoulomb;
+    p->lambdaPower            = q->lambdaPower;
+    p->sigma6WithInvalidSigma = q->sigma6WithInvalidSigma;
+    p->sigma6Minimum          = q->sigma6Minimum;
+    p->gapsysScaleVdW         = q->gapsysScaleLinpointVdW;
+    p->gapsysScaleCoul        = q->gapsysScaleLinpointCoul;
+    p->gapsysSigma6VdW        = q->gapsysSigma6VdW;
+    c->have_params            = 1;
+    c->n_set_params++;
+    return FEPB200_OK;
+}
+
+int fepb200_set_nbfp(fepb200_ctx* c, int ntype, const float* nbfp, const float* nbfp_grid)
+{
+    const size_t n = 2 * (size_t)ntype * ntype;
+    free(c->nbfp);
+    free(c->nbfp_grid);
+    c->ntype     = ntype;
+    c->nbfp      = dup_f2d(nbfp, n);
+    c->nbfp_grid = nbfp_grid ? dup_f2d(nbfp_grid, n) : (double*)calloc(n, sizeof(double));
+    return FEPB200_OK;
+}
+
+int fepb200_set_atoms(fepb200_ctx* c, int natoms, const float* qA, const float* qB, const int* typeA, const int* typeB)
+{
+    free(c->qA);
+    free(c->qB);
+    free(c->typeA);
+    free(c->typeB);
+    c->natoms = natoms;
+    c->qA     = dup_f2d(qA, natoms);
+    c->qB     = dup_f2d(qB, natoms);
+    c->typeA  = dup_i(typeA, natoms);
+    c->typeB  = dup_i(typeB, natoms);
+    c->n_set_atoms++;
+    return FEPB200_OK;
+}
+
+int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, const int* shift, const int* jindex,
+                     const int* jjnr, const int* excl_fep, int nenergrp_pairs, int rank, int nranks)
+{
+    if (rank != 0 || nranks != 1)
+    {
+        snprintf(c->err, sizeof(c->err), "the stand-in holds one shard only");
+        return FEPB200_ERR_UNSUPPORTED;
+    }
+    free(c->iinr);
+    free(c->gid);
+    free(c->shift);
+    free(c->jindex);
+    free(c->jjnr);
+    free(c->excl);
+    const int nrj = nri > 0 ? jindex[nri] : 0;
+    c->nri        = nri;
+    c->nrj        = nrj;
+    c->ngrp       = nenergrp_pairs;
+    c->iinr       = dup_i(iinr, nri);
+    c->gid        = dup_i(gid, nri);
+    c->shift      = dup_i(shift, nri);
+    if (nri > 0)
+    {
+        c->jindex = dup_i(jindex, (size_t)nri + 1);
+    }
+    else
+    {
+        c->jindex = (int*)calloc(1, sizeof(int));
+    }
+    c->jjnr = dup_i(jjnr, nrj);
+    if (excl_fep)
+    {
+        c->excl = dup_i(excl_fep, nrj);
+    }
+    else
+    {
+        c->excl = (int*)malloc(sizeof(int) * (nrj ? nrj : 1));
+        for (int k = 0; k < nrj; k++)
+        {
+            c->excl[k] = 1;
+        }
+    }
+    c->n_set_list++;
+    return FEPB200_OK;
+}
+
+int fepb200_set_lambdas(fepb200_ctx* c, const float* lambda, int n_foreign, const float* all_lambda_coul,
+                        const float* all_lambda_vdw)
+{
+    for (int i = 0; i < FEPB200_NUM_LAMBDA_COMPONENTS; i++)
+    {
+        c->lambda[i] = lambda[i];
+    }
+    free(c->all_c);
+    free(c->all_v);
+    c->nforeign = n_foreign;
+    c->all_c    = dup_f2d(all_lambda_coul, n_foreign);
+    c->all_v    = dup_f2d(all_lambda_vdw, n_foreign);
+    c->n_set_lambdas++;
+    return FEPB200_OK;
+}
+
+int fepb200_compute(fepb200_ctx* c, const float* x, const float* shiftvec, int flags, float* f, float* fshift, double* Vc,
+                    double* Vv, double* dvdl, double* foreign_energy, double* foreign_dvdl)
+{
+    if (!c->have_params || !c->nbfp || !c->qA || !c->jindex)
+    {
+        snprintf(c->err, sizeof(c->err), "compute before params / nbfp / atoms / list were set");
+        return FEPB200_ERR_STATE;
+    }
+    const int n  = c->natoms, L = c->nforeign;
+    double*   xd = dup_f2d(x, 3 * (size_t)n);
+    double*   sv = dup_f2d(shiftvec, 3 * FEPB200_NUM_SHIFT_VECTORS);
+    double*   fd = (double*)calloc(3 * (size_t)n + 1, sizeof(double));
+    double    fs[3 * FEPB200_NUM_SHIFT_VECTORS] = { 0 };
+    double*   vc = (double*)calloc(c->ngrp + 1, sizeof(double));
+    double*   vv = (double*)calloc(c->ngrp + 1, sizeof(double));
+    double*   fe = (double*)calloc(L + 2, sizeof(double));
+    double*   fv = (double*)calloc(2 * (size_t)(L + 2), sizeof(double));
+    double    dv[2] = { 0, 0 }, secs[3] = { 0, 0, 0 };
+    const int rc = fep_oracle_dispatch(&c->p, 0, 1, c->ntype, c->nbfp, c->nbfp_grid, n, xd, c->qA, c->qB, c->typeA, c->typeB,
+                                       sv, c->nri, c->iinr, c->gid, c->shift, c->jindex, c->jjnr, c->excl, c->ngrp, flags,
+                                       c->lambda, L, c->all_c, c->all_v, fd, fs, vc, vv, dv, fe, fv, 1, secs);
+    if (rc == 0)
+    {
+        if ((flags & FEPB200_DO_FORCE) && f)
+        {
+            for (size_t i = 0; i < 3 * (size_t)n; i++)
+            {
+                f[i] += (float)fd[i];
+            }
+            if ((flags & FEPB200_DO_SHIFTFORCE) && fshift)
+            {
+                for (int i = 0; i < 3 * FEPB200_NUM_SHIFT_VECTORS; i++)
+                {
+                    fshift[i] += (float)fs[i];
+                }
+            }
+        }
+        if (flags & FEPB200_DO_POTENTIAL)
+        {
+            for (int g = 0; g < c->ngrp; g++)
+            {
+                Vc[g] += vc[g];
+                Vv[g] += vv[g];
+            }
+        }
+        dvdl[0] += dv[0];
+        dvdl[1] += dv[1];
+        if (flags & FEPB200_DO_FOREIGNLAMBDA)
+        {
+            for (int i = 0; i <= L; i++)
+            {
+                foreign_energy[i] += fe[i];
+                foreign_dvdl[2 * i] += fv[2 * i];
+                foreign_dvdl[2 * i + 1] += fv[2 * i + 1];
+            }
+        }
+    }
+    else
+    {
+        snprintf(c->err, sizeof(c->err), "oracle dispatch returned %d", rc);
+    }
+    free(xd);
+    free(sv);
+    free(fd);
+    free(vc);
+    free(vv);
+    free(fe);
+    free(fv);
+    c->n_compute++;
+    if (getenv("FEPB200_STANDIN_TRACE"))
+    {
+        fprintf(stderr, "standin: compute %ld set_list %ld set_atoms %ld set_params %ld set_lambdas %ld\n", c->n_compute,
+                c->n_set_list, c->n_set_atoms, c->n_set_params, c->n_set_lambdas);
+    }
+    return rc == 0 ? FEPB200_OK : FEPB200_ERR_INVALID_ARGUMENT;
+}

@@ -51,16 +51,18 @@ def _energy_terms(workdir, env):
     return names
 
 
-def _run(tpr, workdir, use_gpu):
+def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=()):
+    """One mdrun of the patched binary; use_gpu routes the perturbed pairs through `lib`."""
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = GMXLIBDIR + ":" + env.get("LD_LIBRARY_PATH", "")
-    env["GMX_FEPB200_LIB"] = LIB
+    env["GMX_FEPB200_LIB"] = lib
     env.pop("GMX_FEPB200", None)
+    env.update(extra_env or {})
     if use_gpu:
         env["GMX_FEPB200"] = "1"
     os.makedirs(workdir, exist_ok=True)
     r = subprocess.run([GMX, "-quiet", "mdrun", "-s", tpr, "-deffnm", "run", "-nb", "cpu", "-pme", "cpu", "-bonded", "cpu",
-                        "-update", "cpu", "-fep", "cpu", "-ntmpi", "1", "-ntomp", "2", "-notunepme"],
+                        "-update", "cpu", "-fep", "cpu", "-ntmpi", "1", "-ntomp", "2", "-notunepme"] + list(mdrun_args),
                        cwd=workdir, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     terms = [t for t in WANT if t in _energy_terms(workdir, env)]
@@ -105,16 +107,11 @@ def _note_timing(system, cpu_dir, gpu_dir, err_gpu):
         pass
 
 
-@pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
-@pytest.mark.parametrize("system", SYSTEMS)
-def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, tmp_path):
-    tpr = os.path.join(TPR, system + ".tpr")
-    if not os.path.exists(tpr):
-        pytest.skip("no run input for " + system)
-    err_cpu, terms_cpu, e_cpu, dh_cpu = _run(tpr, str(tmp_path / "cpu"), False)
-    err_gpu, terms_gpu, e_gpu, dh_gpu = _run(tpr, str(tmp_path / "gpu"), True)
+def compare_runs(system, cpu, gpu):
+    """cpu, gpu: what _run() returned for the reference route and for the route through the shim."""
+    err_cpu, terms_cpu, e_cpu, dh_cpu = cpu
+    err_gpu, terms_gpu, e_gpu, dh_gpu = gpu
     assert "computed by fepb200" in err_gpu and "computed by fepb200" not in err_cpu
-    _note_timing(system, str(tmp_path / "cpu"), str(tmp_path / "gpu"), err_gpu)
     assert terms_cpu == terms_gpu and e_cpu.shape == e_gpu.shape and e_cpu.shape[0] >= 20
     # per-step energies and dV/dlambda components (every step), relative to the size of the quantity
     for col, name in enumerate(terms_cpu, start=1):
@@ -132,3 +129,15 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
         a, b = dh_gpu[:, col], dh_cpu[:, col]
         scale = max(np.max(np.abs(b)), 50.0)
         assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, "dh column", col, np.max(np.abs(a - b)), scale)
+
+
+@pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
+@pytest.mark.parametrize("system", SYSTEMS)
+def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, tmp_path):
+    tpr = os.path.join(TPR, system + ".tpr")
+    if not os.path.exists(tpr):
+        pytest.skip("no run input for " + system)
+    cpu = _run(tpr, str(tmp_path / "cpu"), False)
+    gpu = _run(tpr, str(tmp_path / "gpu"), True)
+    compare_runs(system, cpu, gpu)
+    _note_timing(system, str(tmp_path / "cpu"), str(tmp_path / "gpu"), gpu[0])

@@ -1,0 +1,49 @@
+"""The reference-side shim (integration/gromacs_shim/fepb200_shim.h) checked without a GPU.
+
+The reference's patched mdrun runs twice: perturbed pairs on its own CPU kernel, and through the shim
+into tests/shim_standin/ -- a test-only stand-in for libfepb200.so that answers the nine entry points
+the shim binds with the CPU oracle.  What is under test is the SHIM: which arrays it hands over and
+when (atoms and pair list on search steps only), flag assembly, and where the results are added
+(forces, energy-group terms, dvdl_lin / dvdl_nonlin, ForeignLambdaTerms).  The stand-in is not a
+product path: libfepb200.so itself has no CPU route (tests/test_abi.py).
+
+Needs integration/_gmx (integration/build_patched_gmx.sh; needs /root/reference)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import test_mdrun_dropin as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STANDIN = os.path.join(HERE, "shim_standin", "libfepb200_standin.so")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(T.GMX), reason="integration/_gmx not built")
+
+
+@pytest.fixture(scope="module")
+def standin():
+    src = os.path.join(HERE, "shim_standin", "fepb200_standin.c")
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-D_POSIX_C_SOURCE=199309L", "-Wno-alloc-size-larger-than", "-Wno-stringop-overflow",
+                           "-I", os.path.join(T.ROOT, "include"), "-o", STANDIN, src,
+                           os.path.join(T.ROOT, "oracle", "fep_oracle.c"), "-lm"])
+    return STANDIN
+
+
+@pytest.mark.parametrize("system", ["coulandvdwtogether", "transformAtoB", "c1_methane"])
+def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
+    tpr = os.path.join(T.TPR, system + ".tpr")
+    # mdrun would raise nstlist to 100 for these small systems: keep a pair search every 5 steps
+    cpu = T._run(tpr, str(tmp_path / "cpu"), False, mdrun_args=("-nstlist", "5"))
+    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin, extra_env={"FEPB200_STANDIN_TRACE": "1"},
+                 mdrun_args=("-nstlist", "5"))
+    assert "CPU STAND-IN" in via[0]
+    T.compare_runs(system, cpu, via)
+    # cadence: 20 steps with nstlist = 5 are 21 force calls and 5 pair searches (steps 0, 5, ..., 20)
+    last = [ln for ln in via[0].splitlines() if ln.startswith("standin: compute")][-1]
+    n = dict(zip(("compute", "set_list", "set_atoms", "set_params", "set_lambdas"), map(int, re.findall(r"\d+", last))))
+    assert n["compute"] >= 21
+    assert n["set_list"] == n["set_atoms"] == 5, n
+    assert n["set_params"] <= 5 and n["set_lambdas"] <= 5, n
+    assert "fepb200 shim:" in via[0]  # the shim's own timing summary at exit
