@@ -250,7 +250,15 @@ EXTRA_TYPES = """
 """
 
 
-def build(name, box, solute, fep):
+def mdp_with(base, overrides):
+    """`base` with the keys of `overrides` replaced (or appended)."""
+    keys = {k.strip().lower().replace("_", "-") for k in overrides}
+    kept = [ln for ln in base.splitlines()
+            if "=" not in ln or ln.split("=")[0].strip().lower().replace("_", "-") not in keys]
+    return "\n".join(kept + [f"{k} = {v}" for k, v in overrides.items()]) + "\n"
+
+
+def build(name, box, solute, fep, variants=None):
     work = os.path.join(WORK, name)
     os.makedirs(work, exist_ok=True)
     resname, names, xyz, itp, molname = solute(box)
@@ -272,11 +280,37 @@ def build(name, box, solute, fep):
         out.write(src.read())
     natoms = int(open(os.path.join(work, "em.gro")).read().split("\n")[1])
     print(f"{name}: {natoms} atoms -> {dst}")
+    # the same relaxed system with other interaction settings
+    for suffix, overrides in (variants or {}).items():
+        with open(os.path.join(work, f"md_{suffix}.mdp"), "w") as fh:
+            fh.write(mdp_with(MD + fep, overrides))
+        gmx(["grompp", "-f", f"md_{suffix}.mdp", "-c", "em.gro", "-p", "topol.top", "-o", f"md_{suffix}.tpr", "-maxwarn", "10"],
+            work)
+        dst = os.path.join(OUT, f"{name}_{suffix}.tpr")
+        with open(os.path.join(work, f"md_{suffix}.tpr"), "rb") as src, open(dst, "wb") as out:
+            out.write(src.read())
+        print(f"{name}_{suffix}: {natoms} atoms -> {dst}")
 
+
+# BASELINE.json's configs[2] and configs[3] in kind (Gapsys soft-core with separate coul / vdw lambda
+# paths; reaction-field with 40 lambda states and energy groups), on the 24.5 k-atom system, and an
+# LJ-PME variant of the methane box
+_LAM40 = " ".join(f"{v:.4f}" for v in np.linspace(0.0, 1.0, 40))
+VARIANTS_C1 = {
+    "ljpme": {"vdwtype": "PME", "lj-pme-comb-rule": "geometric", "ewald-rtol-lj": "1e-3"},
+}
+VARIANTS_C2 = {
+    "gapsys": {"sc-function": "gapsys", "sc-gapsys-scale-linpoint-lj": "0.85", "sc-gapsys-scale-linpoint-q": "0.3",
+               "sc-gapsys-sigma-lj": "0.3", "fep-lambdas": "",
+               "coul-lambdas": "0.0 0.2 0.4 0.7 0.9 1.0 1.0 1.0", "vdw-lambdas": "0.0 0.0 0.1 0.3 0.5 0.7 0.9 1.0",
+               "init-lambda-state": "3"},
+    "rf": {"coulombtype": "reaction-field", "epsilon-rf": "78", "fep-lambdas": _LAM40, "init-lambda-state": "16",
+           "sc-coul": "yes", "energygrps": "HEX SOL"},
+}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1_methane", "c2_hexadecane"]
     if "c1_methane" in which:
-        build("c1_methane", 3.0, methane, FEP_C1)
+        build("c1_methane", 3.0, methane, FEP_C1, VARIANTS_C1)
     if "c2_hexadecane" in which:
-        build("c2_hexadecane", 6.3, hexadecane, FEP_C2)
+        build("c2_hexadecane", 6.3, hexadecane, FEP_C2, VARIANTS_C2)

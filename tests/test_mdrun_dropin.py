@@ -24,7 +24,10 @@ SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwt
            # BASELINE.json's configs[0] and configs[1] as real GROMACS systems (integration/systems/make_systems.py):
            # methane decoupling in a 2.65 k-atom TIP3P box, one lambda; a 50-atom solute transformed A -> B in a
            # 24.5 k-atom box with 20 lambda states and foreign-energy output
-           "c1_methane", "c2_hexadecane"]
+           "c1_methane", "c2_hexadecane",
+           # the same systems with LJ-PME; with the Gapsys soft-core and separate coul / vdw lambda paths (configs[2] in
+           # kind); with reaction-field, 40 lambda states, sc-coul and 2 energy groups (configs[3] in kind)
+           "c1_methane_ljpme", "c2_hexadecane_gapsys", "c2_hexadecane_rf"]
 
 
 def _xvg(path):
@@ -113,10 +116,14 @@ def compare_runs(system, cpu, gpu):
     err_gpu, terms_gpu, e_gpu, dh_gpu = gpu
     assert "computed by fepb200" in err_gpu and "computed by fepb200" not in err_cpu
     assert terms_cpu == terms_gpu and e_cpu.shape == e_gpu.shape and e_cpu.shape[0] >= 20
-    # per-step energies and dV/dlambda components (every step), relative to the size of the quantity
+    # per-step energies and dV/dlambda components (every step) at the reference test's own tolerance,
+    # relativeToleranceAsFloatingPoint(50.0, 1e-4): relative 1e-4 of the value with an absolute floor of
+    # 50 * 1e-4 kJ/mol.  The floor matters for dV/dl of the 50-atom solute (c2_hexadecane, ~15 kJ/mol as a
+    # sum of much larger cancelling terms): the reference's own mixed-precision kernel is 2.3e-3 kJ/mol
+    # away from the double-precision oracle there (tests/test_shim_cpu.py), more than 1e-4 of the value.
     for col, name in enumerate(terms_cpu, start=1):
         a, b = e_gpu[:, col], e_cpu[:, col]
-        scale = max(np.max(np.abs(b)), 1.0)
+        scale = max(np.max(np.abs(b)), 50.0)
         assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, name, np.max(np.abs(a - b)), scale)
     # dH/dlambda and the energy differences to the foreign lambda states (every nstdhdl steps)
     assert dh_cpu.shape == dh_gpu.shape and dh_cpu.shape[0] >= 2 and dh_cpu.shape[1] >= 2

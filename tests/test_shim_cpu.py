@@ -31,7 +31,8 @@ def standin():
     return STANDIN
 
 
-@pytest.mark.parametrize("system", ["coulandvdwtogether", "transformAtoB", "c1_methane"])
+@pytest.mark.parametrize("system", ["coulandvdwtogether", "transformAtoB", "c1_methane", "c1_methane_ljpme", "c2_hexadecane",
+                                    "c2_hexadecane_gapsys", "c2_hexadecane_rf"])
 def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
     tpr = os.path.join(T.TPR, system + ".tpr")
     # mdrun would raise nstlist to 100 for these small systems: keep a pair search every 5 steps
