@@ -21,6 +21,7 @@
 
 #include <dlfcn.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -53,6 +54,7 @@ struct Api
     std::vector<float> lastLambda, lastAllCoul, lastAllVdw;
     /* wall time spent in here, printed at exit (the same interval the "NB FEP" cycle counter sees) */
     double secondsSearch = 0, secondsStep = 0;
+    ~Api(); /* prints the timing summary of this rank */
 };
 
 inline double now()
@@ -60,22 +62,32 @@ inline double now()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+/* One context per calling thread: with thread-MPI the ranks of a domain-decomposed run are threads
+ * of one process, each with its own pair lists and local atom numbering. */
 inline Api& api()
 {
-    static Api a;
+    static thread_local Api a;
     return a;
 }
 
-inline void report()
+/* Device of the next context: GMX_FEPB200_DEVICES = number of GPUs to spread the ranks over
+ * (rank k of the process gets device k mod that number; default 1 = everything on device 0). */
+inline int nextDevice()
 {
-    Api& a = api();
-    if (a.calls > 0)
+    static std::atomic<int> next{ 0 };
+    const char*             e = std::getenv("GMX_FEPB200_DEVICES");
+    const int               n = e ? std::atoi(e) : 1;
+    return next.fetch_add(1) % (n > 0 ? n : 1);
+}
+
+inline Api::~Api()
+{
+    if (calls > 0)
     {
         std::fprintf(stderr,
                      "fepb200 shim: %ld calls (%ld with a new pair list); per call %.1f us for the step "
                      "(fepb200_compute + result routing), per new list %.1f us (set_atoms + set_list)\n",
-                     a.calls, a.searchCalls, 1e6 * a.secondsStep / a.calls,
-                     a.searchCalls > 0 ? 1e6 * a.secondsSearch / a.searchCalls : 0.0);
+                     calls, searchCalls, 1e6 * secondsStep / calls, searchCalls > 0 ? 1e6 * secondsSearch / searchCalls : 0.0);
     }
 }
 
@@ -122,13 +134,12 @@ inline void load()
     {
         gmx_fatal(FARGS, "libfepb200.so does not export the expected symbols");
     }
-    const int rc = a.create(&a.ctx, 0);
+    const int rc = a.create(&a.ctx, nextDevice());
     if (rc != FEPB200_OK)
     {
         gmx_fatal(FARGS, "fepb200_create failed (%d): %s", rc, a.last_error(nullptr));
     }
     std::fprintf(stderr, "NOTE: perturbed non-bonded pairs are computed by %s\n", a.describe(a.ctx));
-    std::atexit(report);
     a.ok = true;
 }
 

@@ -54,7 +54,7 @@ def _energy_terms(workdir, env):
     return names
 
 
-def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=()):
+def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=(), ntmpi=1):
     """One mdrun of the patched binary; use_gpu routes the perturbed pairs through `lib`."""
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = GMXLIBDIR + ":" + env.get("LD_LIBRARY_PATH", "")
@@ -65,7 +65,7 @@ def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=()):
         env["GMX_FEPB200"] = "1"
     os.makedirs(workdir, exist_ok=True)
     r = subprocess.run([GMX, "-quiet", "mdrun", "-s", tpr, "-deffnm", "run", "-nb", "cpu", "-pme", "cpu", "-bonded", "cpu",
-                        "-update", "cpu", "-fep", "cpu", "-ntmpi", "1", "-ntomp", "2", "-notunepme"] + list(mdrun_args),
+                        "-update", "cpu", "-fep", "cpu", "-ntmpi", str(ntmpi), "-ntomp", "2", "-notunepme"] + list(mdrun_args),
                        cwd=workdir, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     terms = [t for t in WANT if t in _energy_terms(workdir, env)]
@@ -148,3 +148,17 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
     gpu = _run(tpr, str(tmp_path / "gpu"), True)
     compare_runs(system, cpu, gpu)
     _note_timing(system, str(tmp_path / "cpu"), str(tmp_path / "gpu"), gpu[0])
+
+
+@pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
+def test_mdrun_with_two_domain_decomposition_ranks(tmp_path):
+    """Two thread-MPI ranks (domain decomposition 2x1x1) sharing the B200: each rank has its own local and
+    non-local FEP lists and its own library context (the shim keeps one per rank thread); with
+    GMX_FEPB200_DEVICES=N the ranks would be spread over N GPUs.  (Added after round 1's GPU budget was
+    spent: verified on CPU through tests/test_shim_cpu.py, first GPU run is the round-end one.)"""
+    tpr = os.path.join(TPR, "c2_hexadecane.tpr")
+    args = ("-nstlist", "5", "-dd", "2", "1", "1")
+    cpu = _run(tpr, str(tmp_path / "cpu"), False, mdrun_args=args, ntmpi=2)
+    gpu = _run(tpr, str(tmp_path / "gpu"), True, mdrun_args=args, ntmpi=2)
+    assert gpu[0].count("computed by fepb200") == 2
+    compare_runs("c2_hexadecane, 2 ranks", cpu, gpu)

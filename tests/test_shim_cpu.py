@@ -48,3 +48,15 @@ def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
     assert n["set_list"] == n["set_atoms"] == 5, n
     assert n["set_params"] <= 5 and n["set_lambdas"] <= 5, n
     assert "fepb200 shim:" in via[0]  # the shim's own timing summary at exit
+
+
+def test_shim_with_domain_decomposition_one_context_per_rank(standin, tmp_path):
+    """Two thread-MPI ranks: every rank has its own local + non-local FEP lists and local atom numbering,
+    and the shim keeps one library context per rank (thread)."""
+    tpr = os.path.join(T.TPR, "c2_hexadecane.tpr")
+    args = ("-nstlist", "5", "-dd", "2", "1", "1")
+    cpu = T._run(tpr, str(tmp_path / "cpu"), False, mdrun_args=args, ntmpi=2)
+    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin, mdrun_args=args, ntmpi=2)
+    assert via[0].count("CPU STAND-IN") == 2  # one context per rank
+    assert via[0].count("fepb200 shim:") == 2
+    T.compare_runs("c2_hexadecane, 2 ranks", cpu, via)
