@@ -183,6 +183,45 @@ def cpu_reference(problem, flags, steps, warmup, budget_s=25.0):
                 ms_per_step=t * 1e3)
 
 
+def run_reference_gpu_arm(args, name):
+    """Extra arm (not part of the driver contract): the reference fork's OWN CUDA FEP kernels, compiled in
+    place for sm_100a (oracle/_ref/libfepfork_cuda.so), on the same problem and the same GPU.  Device
+    time of its two kernels (CUDA events inside the harness, best of --steps, warm caches, no L2 flush)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fepb200 import params as P
+    from oracle import oracle
+
+    if not oracle.have_fork_cuda():
+        print(json.dumps(dict(impl="reference-gpu", unavailable="oracle/_ref/libfepfork_cuda.so not built")), flush=True)
+        return
+    import dataclasses
+
+    from fepb200.synth import SPECS, make_system
+
+    spec = dataclasses.replace(SPECS[name], n_energy_groups=1)  # the fork has no energy groups
+    if args.n_foreign is not None:
+        spec = dataclasses.replace(spec, n_foreign=args.n_foreign)
+    problem = make_system(spec)
+    why = oracle.fork_cuda_unsupported(problem)
+    if why:
+        print(json.dumps(dict(impl="reference-gpu", unavailable="the fork's GPU FEP kernels do not cover: " + why)), flush=True)
+        return
+    flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
+    r = oracle.run_fork_cuda(problem, flags, repeats=max(args.steps, 1) + max(args.warmup, 3))
+    t = sum(r["seconds"])
+    wl = _workload(problem)
+    line = dict(impl="reference-gpu", metric=METRIC, value=wl["units_per_step"] / t, unit=UNIT, n_gpus=1, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=t * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=_config(problem, name, 1, dict(parallelism="1 GPU", l2="warm (best of the repeats)",
+                                                      energy_group_pairs=1)),
+                kernel_ms=dict(current_lambda_kernel=r["seconds"][0] * 1e3, foreign_kernel=r["seconds"][1] * 1e3),
+                note="k_calc_nb_fep + k_calc_nb_fep_foreign of the fork (nbnxm/cuda/nbnxm_cuda.cu:755-851), kernels only")
+    print(json.dumps(line), flush=True)
+
+
 def run_reference_arm(args, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -408,11 +447,13 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C4", "C5"])
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n-foreign", type=int, default=None, help="override the number of foreign lambda points")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference-gpu":
+        return run_reference_gpu_arm(args, args.config)
     if args.impl == "ours" and world != args.gpus:
         if world == 1 and args.gpus > 1:
             # re-launch ourselves one rank per GPU

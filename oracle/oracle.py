@@ -9,7 +9,12 @@ import this module.  The product (gromacs-fep-gpu_b200/) never does.
     nb_free_energy.cpp compiled in place by oracle/ref_build/Makefile (present only when it was
     built in a container that has /root/reference; the .so files travel to the GPU box).
 
-Both return the same dict: f [N,3], fshift [45,3], Vc [G], Vv [G], dvdl [2] (coul, vdw),
+  * `run_fork_cuda(problem, ...)` -- oracle/_ref/libfepfork_cuda.so, the reference fork's own CUDA
+    FEP kernels compiled in place for sm_100a (oracle/ref_build/fork_cuda/): the GPU kernels "to
+    beat", run on the same device and problem; needs a GPU.  Mixed precision, fewer features than
+    the CPU kernel -- a performance baseline and a loose cross-check, not the parity oracle.
+
+All return the same dict: f [N,3], fshift [45,3], Vc [G], Vv [G], dvdl [2] (coul, vdw),
 foreign_energy [L+1], foreign_dvdl [L+1,2], all float64, for ONE step starting from zeroed
 outputs, plus `seconds` = (best current-lambda pass, best foreign sweep) wall time.
 """
@@ -186,6 +191,49 @@ def run_ref(problem, flags, *, precision="dp", nthreads=1, use_simd=True, repeat
     out = _call_dispatch(lib.fepref_dispatch, problem, flags, nthreads, use_simd, repeats)
     out["variant"] = variant
     out["simd"] = lib.fepref_simd_string().decode() if use_simd else "scalar"
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the fork's CUDA FEP kernels (oracle/_ref/libfepfork_cuda.so)
+# ---------------------------------------------------------------------------------------------
+FORK_CUDA_LIB = os.path.join(REF_DIR, "libfepfork_cuda.so")
+_fork_lib = None
+
+FORK_CUDA_UNSUPPORTED = {1: "electrostatics type", 2: "Gapsys soft-core", 3: "LJ-PME / potential-switch / force-switch",
+                         4: "energy groups", 5: "rcoulomb != rvdw"}
+
+
+def have_fork_cuda() -> bool:
+    return os.path.exists(FORK_CUDA_LIB)
+
+
+def _load_fork_cuda() -> ctypes.CDLL:
+    global _fork_lib
+    if _fork_lib is None:
+        lib = ctypes.CDLL(FORK_CUDA_LIB)
+        lib.fepfork_dispatch.argtypes = _DISPATCH_ARGTYPES
+        lib.fepfork_dispatch.restype = ctypes.c_int
+        lib.fepfork_supports.argtypes = [ctypes.POINTER(CParamsD), ctypes.c_int]
+        lib.fepfork_supports.restype = ctypes.c_int
+        lib.fepfork_describe.restype = ctypes.c_char_p
+        _fork_lib = lib
+    return _fork_lib
+
+
+def fork_cuda_unsupported(problem) -> str | None:
+    """Why the fork's GPU kernels cannot run this problem (None if they can)."""
+    cp = _params_d(problem.params)
+    code = _load_fork_cuda().fepfork_supports(ctypes.byref(cp), problem.nenergrp_pairs)
+    return FORK_CUDA_UNSUPPORTED.get(code, f"code {code}") if code else None
+
+
+def run_fork_cuda(problem, flags, *, repeats=1):
+    """One step on the current CUDA device; `seconds` = device time of (current-lambda kernel,
+    foreign-lambda kernel), best of `repeats`."""
+    lib = _load_fork_cuda()
+    out = _call_dispatch(lib.fepfork_dispatch, problem, flags, 1, 0, repeats)
+    out["variant"] = "fork_cuda"
     return out
 
 
