@@ -241,6 +241,28 @@ def run_reference_arm(args, name):
     print(json.dumps(line), flush=True)
 
 
+def _fork_gpu_beside(args, name):
+    """`bench.py --impl reference-gpu` in a subprocess; a dict for the JSON line (never raises)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--config", name, "--steps", "20"]
+    if args.n_foreign is not None:
+        cmd += ["--n-foreign", str(args.n_foreign)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return dict(unavailable=f"exit code {r.returncode}: {(r.stderr or '').strip()[-200:]}")
+        d = json.loads(lines[-1])
+        if "unavailable" in d:
+            return dict(unavailable=d["unavailable"])
+        return dict(value=d["value"], unit=d["unit"], ms_per_step=d["ms_per_step"], kernel_ms=d["kernel_ms"],
+                    what="the reference fork's own CUDA FEP kernels (nbnxm_fep_cuda_kernel.cuh + nbnxm_foreign_fep_cuda_kernel.cuh, "
+                         "compiled in place for sm_100a, oracle/_ref/libfepfork_cuda.so) with the fork's launch configuration, "
+                         "same problem with one energy group, kernels only, warm caches, best of 20 -- ours (`value`) is the "
+                         "whole step incl. the reduction epilogue with L2 flushed between steps")
+    except Exception as exc:  # noqa: BLE001 -- a reported baseline must not take the bench down
+        return dict(unavailable=f"{type(exc).__name__}: {exc}"[:300])
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -422,6 +444,12 @@ def run_ours(args, name):
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference(problem, flags, 3, 1)
             cpu.pop("ms_per_step", None)
+        # the fork's own CUDA FEP kernels on this GPU and this problem, beside ours (reported, like
+        # cpu_baseline).  After all of our timing, in a process of its own: foreign kernels stay out of
+        # this one, and whatever happens there cannot touch the numbers above.
+        fork_gpu = None
+        if world == 1 and not args.no_fork_gpu:
+            fork_gpu = _fork_gpu_beside(args, name)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
                     data="synthetic", config=_config(problem, name, world, dict(
@@ -431,6 +459,7 @@ def run_ours(args, name):
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_s / args.steps * 1e3),
                     gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, cpu_baseline=cpu,
+                    fork_gpu_baseline=fork_gpu,
                     wall_ms_per_step_incl_flush=t_wall / args.steps * 1e3, device=ctx.describe())
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
@@ -449,6 +478,7 @@ def main():
     ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fork-gpu", action="store_true", help="skip the fork's CUDA kernels beside ours (fork_gpu_baseline)")
     ap.add_argument("--n-foreign", type=int, default=None, help="override the number of foreign lambda points")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
