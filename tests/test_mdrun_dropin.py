@@ -27,7 +27,12 @@ SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwt
            "c1_methane", "c2_hexadecane",
            # the same systems with LJ-PME; with the Gapsys soft-core and separate coul / vdw lambda paths (configs[2] in
            # kind); with reaction-field, 40 lambda states, sc-coul and 2 energy groups (configs[3] in kind)
-           "c1_methane_ljpme", "c2_hexadecane_gapsys", "c2_hexadecane_rf"]
+           "c1_methane_ljpme", "c2_hexadecane_gapsys", "c2_hexadecane_rf",
+           # the rest of the reference's mdrun free-energy test systems that have perturbed non-bonded pairs
+           # (src/programs/mdrun/tests/freeenergy.cpp:217-242; "restraints" and "simtemp" have none / no dH output):
+           # intramolecular coupling, expanded ensemble (100 steps, lambda changes during the run), relative
+           # free energies with and without position restraints
+           "coulandvdwintramol", "expanded", "relative", "relative-position-restraints"]
 
 
 def _xvg(path):
