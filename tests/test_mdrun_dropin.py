@@ -75,11 +75,18 @@ def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=(), ntmpi=1)
     assert r.returncode == 0, r.stderr[-2000:]
     terms = [t for t in WANT if t in _energy_terms(workdir, env)]
     assert "Potential" in terms
-    for extra in (["-o", "terms.xvg"], ["-s", tpr, "-odh", "dh.xvg"]):  # -odh suppresses the -o output
-        e = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr", "-xvg", "none"] + extra, cwd=workdir, env=env,
+    for extra in (["-o", "terms.xvg"], ["-s", tpr, "-xvg", "none", "-odh", "dh.xvg"]):  # -odh suppresses the -o output
+        e = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr"] + extra, cwd=workdir, env=env,
                            input="\n".join(terms) + "\n\n", capture_output=True, text=True, timeout=120)
         assert e.returncode == 0, e.stderr[-2000:]
-    return r.stderr, terms, _xvg(os.path.join(workdir, "terms.xvg")), _xvg(os.path.join(workdir, "dh.xvg"))
+    # gmx energy writes the columns in energy-file order, whatever the order of the selection: take the names
+    # from the legends of the file ("LJ (SR)" there, "LJ-(SR)" in the selection)
+    legends = []
+    for line in open(os.path.join(workdir, "terms.xvg")):
+        if line.startswith("@ s") and " legend " in line:
+            legends.append(line.split('"')[1].replace(" (", "-("))
+    assert sorted(legends) == sorted(terms), (legends, terms)
+    return r.stderr, legends, _xvg(os.path.join(workdir, "terms.xvg")), _xvg(os.path.join(workdir, "dh.xvg"))
 
 
 def _nb_fep_ms_per_call(workdir):
@@ -143,6 +150,31 @@ def compare_runs(system, cpu, gpu):
         assert np.max(np.abs(a - b)) <= 1e-4 * scale, (system, "dh column", col, np.max(np.abs(a - b)), scale)
 
 
+def compare_with_reference_golden(system, run):
+    """The per-step energies of a run against the reference's OWN golden vectors for its mdrun free-energy
+    test (tests/golden/mdrun_fe_refdata.json <- src/programs/mdrun/tests/refdata/*_s.xml), at that test's
+    tolerance: relativeToleranceAsFloatingPoint(50, 1e-4), and 1e-3 for the long expanded-ensemble run
+    (src/programs/mdrun/tests/freeenergy.cpp:115-119).  Returns the number of values compared."""
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "mdrun_fe_refdata.json")) as fh:
+        golden = json.load(fh)["systems"].get(system)
+    if golden is None:
+        return 0
+    _, terms, e, _ = run
+    rtol = 1e-3 if system == "expanded" else 1e-4
+    n = 0
+    for name, g in golden.items():
+        if name not in terms:
+            continue
+        col = e[:, 1 + terms.index(name)]
+        for step, want in zip(g["steps"], g["values"]):
+            got = col[step]
+            assert abs(got - want) <= rtol * max(abs(want), 50.0), (system, name, step, got, want)
+            n += 1
+    return n
+
+
 @pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
 @pytest.mark.parametrize("system", SYSTEMS)
 def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, tmp_path):
@@ -152,6 +184,7 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
     cpu = _run(tpr, str(tmp_path / "cpu"), False)
     gpu = _run(tpr, str(tmp_path / "gpu"), True)
     compare_runs(system, cpu, gpu)
+    compare_with_reference_golden(system, gpu)
     _note_timing(system, str(tmp_path / "cpu"), str(tmp_path / "gpu"), gpu[0])
 
 

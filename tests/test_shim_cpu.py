@@ -66,3 +66,16 @@ def test_shim_with_domain_decomposition_one_context_per_rank(standin, tmp_path):
     assert via[0].count("CPU STAND-IN") == 2  # one context per rank
     assert via[0].count("fepb200 shim:") == 2
     T.compare_runs("c2_hexadecane, 2 ranks", cpu, via)
+
+
+@pytest.mark.parametrize("system", ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwtogether", "expanded",
+                                    "relative", "relative-position-restraints", "transformAtoB", "vdwalone"])
+def test_shim_route_reproduces_the_reference_golden_vectors(system, standin, tmp_path):
+    """The run through the shim against the reference's OWN golden vectors of its mdrun free-energy test
+    (tests/golden/mdrun_fe_refdata.json), at that test's tolerance.  With mdrun's default pair-list settings,
+    as in the reference's test: with -nstlist 5 the reference's own CPU route moves away from its golden
+    dV/dl by 0.57 kJ/mol on transformAtoB (the shim route moves with it)."""
+    tpr = os.path.join(T.TPR, system + ".tpr")
+    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin)
+    assert "CPU STAND-IN" in via[0]
+    assert T.compare_with_reference_golden(system, via) >= 42
