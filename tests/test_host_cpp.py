@@ -53,6 +53,23 @@ def test_host_library_builds_and_fails_loudly_without_gpu(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,groups", [("C2", 1), ("C4", 4), ("C3", 1)])
 def test_cpp_dispatch_matches_oracle(tmp_path, name, groups):
+    _check_cpp_dispatch(tmp_path, name, groups, None)
+
+
+@pytest.mark.parametrize("name,groups", [("C2", 1), ("C4", 4), ("C3", 1)])
+def test_cpp_dispatch_host_logic_on_cpu(tmp_path, name, groups):
+    """The same driver program with the test-only stand-in (tests/shim_standin: the oracle behind the entry
+    points the host layer calls) pre-loaded in place of libfepb200.so: what runs here is the C++ class itself --
+    flag assembly, dvdl_lin / dvdl_nonlin routing, ForeignLambdaTerms, the accumulate semantics."""
+    src = os.path.join(ROOT, "tests", "shim_standin", "fepb200_standin.c")
+    lib = os.path.join(ROOT, "tests", "shim_standin", "libfepb200_standin.so")
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-D_POSIX_C_SOURCE=199309L",
+                           "-Wno-alloc-size-larger-than", "-Wno-stringop-overflow", "-I", os.path.join(ROOT, "include"),
+                           "-o", lib, src, os.path.join(ROOT, "oracle", "fep_oracle.c"), "-lm"])
+    _check_cpp_dispatch(tmp_path, name, groups, dict(os.environ, LD_PRELOAD=lib))
+
+
+def _check_cpp_dispatch(tmp_path, name, groups, env):
     from oracle import oracle
 
     _build()
@@ -60,7 +77,7 @@ def test_cpp_dispatch_matches_oracle(tmp_path, name, groups):
             "C3": scaled_spec("C3", 4.0, 2, 25, n_foreign=4)}[name]
     prob = make_system(spec)
     _write_problem(prob, groups, tmp_path / "p.bin")
-    r = subprocess.run([DRIVER, str(tmp_path / "p.bin"), str(tmp_path / "r.bin")], capture_output=True, text=True)
+    r = subprocess.run([DRIVER, str(tmp_path / "p.bin"), str(tmp_path / "r.bin")], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     n, g, l = prob.natoms, prob.nenergrp_pairs, prob.n_foreign
     raw = open(tmp_path / "r.bin", "rb").read()
