@@ -394,6 +394,13 @@ def run_ours(args, name):
                               / (ms_per_step * 1e-3) / 1e12,
                               frac=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"]
                               / (ms_per_step * 1e-3) / 1e12 / (fp32_peak * world)),
+                    # executed work of the same launch: warp instructions from the ncu capture of this kernel on
+                    # this workload (profiles/README.md: 11.4 M for the 21-point foreign launch on C5) over the live
+                    # kernel time, against the issue rate of the chip (4 schedulers x 1 warp instruction per clock per SM)
+                    issue=(dict(warp_instructions=11.4e6, source="profiles/r01_ncu_full_final_raw.csv (smsp__inst_executed.sum)",
+                                peak_per_s=sms * 4 * peaks["sm_max_mhz"] * 1e6,
+                                frac=11.4e6 / (k_foreign * 1e-3) / (sms * 4 * peaks["sm_max_mhz"] * 1e6) if k_foreign > 0 else 0.0)
+                           if (name == "C5" and world == 1 and not fused and args.n_foreign is None) else None),
                     hbm=dict(algorithmic_bytes_per_step=alg_bytes,
                              achieved_gbs=alg_bytes / ((k_pass + k_foreign + k_epi) * 1e-3) / 1e9,
                              peak_gbs=peaks["hbm_gbs"]))
