@@ -47,9 +47,9 @@ def _xvg(path):
 WANT = ("Potential", "LJ-(SR)", "Coulomb-(SR)", "dVremain/dl", "dVcoul/dl", "dVvdw/dl", "dVbonded/dl", "dVrestraint/dl")
 
 
-def _energy_terms(workdir, env):
+def _energy_terms(workdir, env, gmx=None):
     """Names of the energy terms in run.edr (gmx energy prints the table before it asks)."""
-    r = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr", "-o", "none.xvg"], cwd=workdir, env=env, input="\n",
+    r = subprocess.run([gmx or GMX, "-quiet", "energy", "-f", "run.edr", "-o", "none.xvg"], cwd=workdir, env=env, input="\n",
                        capture_output=True, text=True, timeout=120)
     names = []
     for line in (r.stdout + r.stderr).splitlines():
@@ -59,24 +59,25 @@ def _energy_terms(workdir, env):
     return names
 
 
-def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=(), ntmpi=1):
+def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=(), ntmpi=1, gmx=None, nb="cpu", fep="cpu"):
     """One mdrun of the patched binary; use_gpu routes the perturbed pairs through `lib`."""
+    gmx = gmx or GMX
     env = dict(os.environ)
-    env["LD_LIBRARY_PATH"] = GMXLIBDIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    env["LD_LIBRARY_PATH"] = os.path.join(os.path.dirname(os.path.dirname(gmx)), "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
     env["GMX_FEPB200_LIB"] = lib
     env.pop("GMX_FEPB200", None)
     env.update(extra_env or {})
     if use_gpu:
         env["GMX_FEPB200"] = "1"
     os.makedirs(workdir, exist_ok=True)
-    r = subprocess.run([GMX, "-quiet", "mdrun", "-s", tpr, "-deffnm", "run", "-nb", "cpu", "-pme", "cpu", "-bonded", "cpu",
-                        "-update", "cpu", "-fep", "cpu", "-ntmpi", str(ntmpi), "-ntomp", "2", "-notunepme"] + list(mdrun_args),
+    r = subprocess.run([gmx, "-quiet", "mdrun", "-s", tpr, "-deffnm", "run", "-nb", nb, "-pme", "cpu", "-bonded", "cpu",
+                        "-update", "cpu", "-fep", fep, "-ntmpi", str(ntmpi), "-ntomp", "2", "-notunepme"] + list(mdrun_args),
                        cwd=workdir, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    terms = [t for t in WANT if t in _energy_terms(workdir, env)]
+    terms = [t for t in WANT if t in _energy_terms(workdir, env, gmx)]
     assert "Potential" in terms
     for extra in (["-o", "terms.xvg"], ["-s", tpr, "-xvg", "none", "-odh", "dh.xvg"]):  # -odh suppresses the -o output
-        e = subprocess.run([GMX, "-quiet", "energy", "-f", "run.edr"] + extra, cwd=workdir, env=env,
+        e = subprocess.run([gmx, "-quiet", "energy", "-f", "run.edr"] + extra, cwd=workdir, env=env,
                            input="\n".join(terms) + "\n\n", capture_output=True, text=True, timeout=120)
         assert e.returncode == 0, e.stderr[-2000:]
     # gmx energy writes the columns in energy-file order, whatever the order of the selection: take the names
