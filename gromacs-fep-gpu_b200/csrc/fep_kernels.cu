@@ -833,6 +833,49 @@ __global__ void __launch_bounds__(256) fep_add_forces_kernel(const float* __rest
     }
 }
 
+/* the scalars and shift forces of the result block added into the float device buffers the fork's nbnxm
+ * GPU module reduces from (NBAtomDataGpu::eLJ, eElec, dvdlLJ, dvdlElec, e*Foreign[L+1], dvdl*Foreign[L+1],
+ * fShift[45]); one block, one writer per element: nothing to synchronise */
+__global__ void __launch_bounds__(256) fep_export_scalars_kernel(const double* __restrict__ r64, const float* __restrict__ r32_fshift,
+                                                                ExportLayout lay, ExportTargets t)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0 && lay.energy)
+    {
+        double vc = 0.0, vv = 0.0;
+        for (int g = 0; g < lay.ngrp; g++)
+        {
+            vc += r64[lay.off_vc + g];
+            vv += r64[lay.off_vv + g];
+        }
+        if (t.eElec) *t.eElec += (float)vc;
+        if (t.eLJ) *t.eLJ += (float)vv;
+    }
+    if (tid == 1)
+    {
+        if (t.dvdlElec) *t.dvdlElec += (float)r64[lay.off_dvdl];
+        if (t.dvdlLJ) *t.dvdlLJ += (float)r64[lay.off_dvdl + 1];
+    }
+    if (lay.foreign)
+    {
+        /* the fork keeps a Coulomb and an LJ share per lambda point and adds both into the same foreign term
+         * (gpu_common.h:176-191); the energy of a point is exported whole through the LJ share */
+        for (int i = tid; i <= lay.nforeign; i += blockDim.x)
+        {
+            if (t.eLJForeign) t.eLJForeign[i] += (float)r64[lay.off_foreign_e + i];
+            if (t.dvdlElecForeign) t.dvdlElecForeign[i] += (float)r64[lay.off_foreign_dvdl + 2 * i];
+            if (t.dvdlLJForeign) t.dvdlLJForeign[i] += (float)r64[lay.off_foreign_dvdl + 2 * i + 1];
+        }
+    }
+    if (lay.shift && t.fShift)
+    {
+        for (int i = tid; i < 3 * FEP_NUM_SHIFT; i += blockDim.x)
+        {
+            t.fShift[i] += r32_fshift[i];
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* launchers                                                                                   */
 /* ------------------------------------------------------------------------------------------- */
@@ -1177,6 +1220,14 @@ extern "C" int fep_launch_add_forces(const float* res_f32, const int* d_touched,
         fep_add_forces_kernel<<<(k1 - k0 + 255) / 256, 256, 0, stream>>>(res_f32, d_touched, d_f, k0, k1, overwrite);
         (*counter)++;
     }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int fep_launch_export_scalars(const double* r64, const float* r32_fshift, const ExportLayout* lay,
+                                         const ExportTargets* targets, cudaStream_t stream, long long* counter)
+{
+    fep_export_scalars_kernel<<<1, 256, 0, stream>>>(r64, r32_fshift, *lay, *targets);
+    (*counter)++;
     return (int)cudaGetLastError();
 }
 

@@ -205,6 +205,19 @@ int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flags, int ran
                            cudaStream_t stream, long long* launch_counter, int chained);
 int fep_launch_gather_x(const float* d_x, int stride, const int* d_touched, float* pos3, int n_touched,
                         cudaStream_t stream, long long* launch_counter);
+/* fepb200_export_scalars_device(): where the values sit in the fp64 part of the result block, and the
+ * caller's float device buffers they are added into (any of them may be NULL) */
+struct ExportLayout
+{
+    int ngrp, nforeign, energy, foreign, shift;
+    int off_vc, off_vv, off_dvdl, off_foreign_e, off_foreign_dvdl;
+};
+struct ExportTargets
+{
+    float *eLJ, *eElec, *dvdlLJ, *dvdlElec, *eLJForeign, *eElecForeign, *dvdlLJForeign, *dvdlElecForeign, *fShift;
+};
+int fep_launch_export_scalars(const double* r64, const float* r32_fshift, const struct ExportLayout* lay,
+                              const struct ExportTargets* targets, cudaStream_t stream, long long* launch_counter);
 int fep_launch_add_forces(const float* res_f32, const int* d_touched, float* d_f, int k0, int k1, int overwrite,
                           cudaStream_t stream, long long* launch_counter);
 #ifdef __cplusplus

@@ -1866,6 +1866,50 @@ int fepb200_add_forces_device(fepb200_ctx* c, float* d_f, int flags)
     return FEPB200_OK;
 }
 
+int fepb200_export_scalars_device(fepb200_ctx* c, int flags, float* eLJ, float* eElec, float* dvdlLJ, float* dvdlElec,
+                                  float* eLJForeign, float* eElecForeign, float* dvdlLJForeign, float* dvdlElecForeign,
+                                  float* fShift)
+{
+    if (!c)
+    {
+        return FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    int rc = check_ready(c);
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    if (c->result_on_host)
+    {
+        return fail(c, FEPB200_ERR_STATE,
+                    "fepb200_export_scalars_device: the last step was a fepb200_compute(), whose results live in host memory; "
+                    "use fepb200_launch()");
+    }
+    cudaSetDevice(c->device);
+    close_chain(c);
+    const StepFlags       sf = step_flags(c, flags);
+    const fepb200_layout& l  = c->layout;
+    ExportLayout          lay;
+    lay.ngrp             = l.nenergrp;
+    lay.nforeign         = l.nforeign;
+    lay.energy           = sf.energy ? 1 : 0;
+    lay.foreign          = sf.foreign ? 1 : 0;
+    lay.shift            = (sf.force && sf.shift) ? 1 : 0;
+    lay.off_vc           = (int)l.off_vc;
+    lay.off_vv           = (int)l.off_vv;
+    lay.off_dvdl         = (int)l.off_dvdl;
+    lay.off_foreign_e    = (int)l.off_foreign_e;
+    lay.off_foreign_dvdl = (int)l.off_foreign_dvdl;
+    ExportTargets t{ eLJ, eElec, dvdlLJ, dvdlElec, eLJForeign, eElecForeign, dvdlLJForeign, dvdlElecForeign, fShift };
+    (void)eElecForeign; /* the whole energy of a point goes through eLJForeign, see the kernel */
+    const int err = fep_launch_export_scalars(c->ka.res_f64, c->ka.res_f32 + l.off_fshift, &lay, &t, c->stream, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "scalar export launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    return FEPB200_OK;
+}
+
 int fepb200_wait(fepb200_ctx* c)
 {
     if (!c)

@@ -70,6 +70,7 @@ SYMBOLS = {
     "fepb200_gather_xq_device": (ctypes.c_int, [_VP, _VP, _FP]),
     "fepb200_launch": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "fepb200_add_forces_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int]),
+    "fepb200_export_scalars_device": (ctypes.c_int, [_VP, ctypes.c_int] + [_VP] * 9),
     "fepb200_wait": (ctypes.c_int, [_VP]),
     "fepb200_result_device_ptrs": (ctypes.c_int, [_VP, ctypes.POINTER(_VP), ctypes.POINTER(_VP)]),
     "fepb200_result_block_bytes": (ctypes.c_size_t, [_VP]),
@@ -302,6 +303,17 @@ class FepContext:
     def add_forces_device(self, d_f_ptr: int, flags: int = 0) -> None:
         """Add the forces of the last launch() into a device-resident float[natoms][3] array."""
         self._check(self._lib.fepb200_add_forces_device(self._h, _VP(d_f_ptr), int(flags)))
+
+    def export_scalars_device(self, flags: int, **ptrs: int) -> None:
+        """Add the scalars of the last launch() into float device buffers laid out like the fork's NBAtomDataGpu
+        outputs; keyword arguments eLJ, eElec, dvdlLJ, dvdlElec, eLJForeign, eElecForeign, dvdlLJForeign,
+        dvdlElecForeign, fShift are device pointers (omitted = NULL)."""
+        names = ("eLJ", "eElec", "dvdlLJ", "dvdlElec", "eLJForeign", "eElecForeign", "dvdlLJForeign", "dvdlElecForeign", "fShift")
+        unknown = set(ptrs) - set(names)
+        if unknown:
+            raise TypeError(f"unknown buffers {sorted(unknown)}")
+        args = [_VP(ptrs[n]) if ptrs.get(n) else None for n in names]
+        self._check(self._lib.fepb200_export_scalars_device(self._h, int(flags), *args))
 
     def wait(self) -> None:
         self._check(self._lib.fepb200_wait(self._h))

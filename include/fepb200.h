@@ -224,6 +224,17 @@ int fepb200_launch(fepb200_ctx* ctx, int flags, void* stream);
  * atoms this rank owns.  Energies, dV/dlambda and shift forces still come from fepb200_download()
  * (call it with FEPB200_DO_FORCE cleared to skip the force copy). */
 int fepb200_add_forces_device(fepb200_ctx* ctx, float* d_f, int flags);
+/* The scalars of the last fepb200_launch() added into the float device buffers the fork's nbnxm GPU module
+ * copies back and reduces (NBAtomDataGpu::eLJ, eElec, dvdlLJ, dvdlElec, e{LJ,Elec}Foreign[L+1],
+ * dvdl{LJ,Elec}Foreign[L+1], fShift[45]; nbnxm/gpu_types_common.h:103-157, reduced at gpu_common.h:139-191), on
+ * the context's stream -- what a hook in the fork's GPU route (nbnxm/cuda/nbnxm_cuda.cu:755-851) needs so that
+ * the fork's copy-back and reduction stay as they are.  flags select the groups as in fepb200_download()
+ * (DO_POTENTIAL: eLJ / eElec, summed over energy-group pairs, which the fork does not have; DO_FOREIGNLAMBDA:
+ * the foreign arrays, the energy of a point whole in eLJForeign; DO_FORCE|DO_SHIFTFORCE: fShift; dV/dlambda
+ * always).  Any pointer may be NULL.  Asynchronous. */
+int fepb200_export_scalars_device(fepb200_ctx* ctx, int flags, float* eLJ, float* eElec, float* dvdlLJ, float* dvdlElec,
+                                  float* eLJForeign, float* eElecForeign, float* dvdlLJForeign, float* dvdlElecForeign,
+                                  float* fShift);
 /* Block until the context's stream is idle. */
 int fepb200_wait(fepb200_ctx* ctx);
 /* Device pointers of the result block: f32 part and f64 part (see fepb200_layout). */

@@ -107,3 +107,33 @@ def test_nbat_style_hand_off_xyzq_in_forces_out_in_a_permuted_index_space(ctx):
     assert np.sqrt(np.mean((f_grid[new_of_old] - want["f"]) ** 2)) <= 1e-6 * scale
     for k in ("Vc", "Vv", "dvdl", "foreign_energy"):
         assert np.allclose(got[k], want[k], rtol=1e-6, atol=1e-6 * np.max(np.abs(want[k]))), k
+
+
+def test_scalars_exported_into_the_forks_device_buffers(ctx):
+    """fepb200_export_scalars_device: energies, dV/dlambda, foreign terms and shift forces added into float
+    device buffers laid out like the outputs of the fork's NBAtomDataGpu (what a hook in its GPU route needs)."""
+    import torch
+
+    prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=6))  # 16 energy-group pairs: summed on export
+    ctx.set_problem(prob)
+    want = ctx.compute(prob.x, prob.shiftvec, ALL)
+    ctx.upload_x(prob.x, prob.shiftvec)
+    ctx.launch(ALL)
+    n_l = prob.n_foreign + 1
+    buf = {k: torch.full((n,), 1.0, dtype=torch.float32, device="cuda")  # pre-filled: the export adds
+           for k, n in dict(eLJ=1, eElec=1, dvdlLJ=1, dvdlElec=1, eLJForeign=n_l, eElecForeign=n_l, dvdlLJForeign=n_l,
+                            dvdlElecForeign=n_l, fShift=135).items()}
+    torch.cuda.synchronize()
+    ctx.export_scalars_device(ALL, **{k: v.data_ptr() for k, v in buf.items()})
+    ctx.wait()
+    got = {k: v.cpu().numpy().astype(np.float64) - 1.0 for k, v in buf.items()}
+
+    def close(a, b):
+        b = np.asarray(b, float)
+        return np.all(np.abs(a - b) <= 2e-6 * max(np.max(np.abs(b)), 1.0) + 2e-7 * np.abs(b) + 1e-6)
+
+    assert close(got["eElec"][0], want["Vc"].sum()) and close(got["eLJ"][0], want["Vv"].sum())
+    assert close(got["dvdlElec"][0], want["dvdl"][0]) and close(got["dvdlLJ"][0], want["dvdl"][1])
+    assert close(got["eLJForeign"], want["foreign_energy"]) and not got["eElecForeign"].any()
+    assert close(got["dvdlElecForeign"], want["foreign_dvdl"][:, 0]) and close(got["dvdlLJForeign"], want["foreign_dvdl"][:, 1])
+    assert close(got["fShift"], want["fshift"].reshape(-1))
