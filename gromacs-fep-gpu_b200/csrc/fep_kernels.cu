@@ -824,6 +824,12 @@ __global__ void __launch_bounds__(256) fep_add_forces_kernel(const float* __rest
             f[3 * a + 1] = fy;
             f[3 * a + 2] = fz;
         }
+        else if (overwrite == 2) /* another stream may be adding into f at the same time (FEPB200_ATOMIC_OUTPUTS) */
+        {
+            atomicAdd(f + 3 * a, fx);
+            atomicAdd(f + 3 * a + 1, fy);
+            atomicAdd(f + 3 * a + 2, fz);
+        }
         else
         {
             f[3 * a] += fx;
@@ -835,7 +841,21 @@ __global__ void __launch_bounds__(256) fep_add_forces_kernel(const float* __rest
 
 /* the scalars and shift forces of the result block added into the float device buffers the fork's nbnxm
  * GPU module reduces from (NBAtomDataGpu::eLJ, eElec, dvdlLJ, dvdlElec, e*Foreign[L+1], dvdl*Foreign[L+1],
- * fShift[45]); one block, one writer per element: nothing to synchronise */
+ * fShift[45]); one block, one writer per element.  Within one stream there is nothing to synchronise; with
+ * lay.atomic (FEPB200_ATOMIC_OUTPUTS) the additions are atomic, because the fork's kernels of the other
+ * locality add into the same buffers from their own stream (atomicAdd, nbnxm_cuda_kernel_utils.cuh) */
+__device__ __forceinline__ void fep_export_add(float* target, float v, int atomic)
+{
+    if (atomic)
+    {
+        atomicAdd(target, v);
+    }
+    else
+    {
+        *target += v;
+    }
+}
+
 __global__ void __launch_bounds__(256) fep_export_scalars_kernel(const double* __restrict__ r64, const float* __restrict__ r32_fshift,
                                                                 ExportLayout lay, ExportTargets t)
 {
@@ -848,13 +868,13 @@ __global__ void __launch_bounds__(256) fep_export_scalars_kernel(const double* _
             vc += r64[lay.off_vc + g];
             vv += r64[lay.off_vv + g];
         }
-        if (t.eElec) *t.eElec += (float)vc;
-        if (t.eLJ) *t.eLJ += (float)vv;
+        if (t.eElec) fep_export_add(t.eElec, (float)vc, lay.atomic);
+        if (t.eLJ) fep_export_add(t.eLJ, (float)vv, lay.atomic);
     }
     if (tid == 1)
     {
-        if (t.dvdlElec) *t.dvdlElec += (float)r64[lay.off_dvdl];
-        if (t.dvdlLJ) *t.dvdlLJ += (float)r64[lay.off_dvdl + 1];
+        if (t.dvdlElec) fep_export_add(t.dvdlElec, (float)r64[lay.off_dvdl], lay.atomic);
+        if (t.dvdlLJ) fep_export_add(t.dvdlLJ, (float)r64[lay.off_dvdl + 1], lay.atomic);
     }
     if (lay.foreign)
     {
@@ -862,16 +882,16 @@ __global__ void __launch_bounds__(256) fep_export_scalars_kernel(const double* _
          * (gpu_common.h:176-191); the energy of a point is exported whole through the LJ share */
         for (int i = tid; i <= lay.nforeign; i += blockDim.x)
         {
-            if (t.eLJForeign) t.eLJForeign[i] += (float)r64[lay.off_foreign_e + i];
-            if (t.dvdlElecForeign) t.dvdlElecForeign[i] += (float)r64[lay.off_foreign_dvdl + 2 * i];
-            if (t.dvdlLJForeign) t.dvdlLJForeign[i] += (float)r64[lay.off_foreign_dvdl + 2 * i + 1];
+            if (t.eLJForeign) fep_export_add(t.eLJForeign + i, (float)r64[lay.off_foreign_e + i], lay.atomic);
+            if (t.dvdlElecForeign) fep_export_add(t.dvdlElecForeign + i, (float)r64[lay.off_foreign_dvdl + 2 * i], lay.atomic);
+            if (t.dvdlLJForeign) fep_export_add(t.dvdlLJForeign + i, (float)r64[lay.off_foreign_dvdl + 2 * i + 1], lay.atomic);
         }
     }
     if (lay.shift && t.fShift)
     {
         for (int i = tid; i < 3 * FEP_NUM_SHIFT; i += blockDim.x)
         {
-            t.fShift[i] += r32_fshift[i];
+            fep_export_add(t.fShift + i, r32_fshift[i], lay.atomic);
         }
     }
 }

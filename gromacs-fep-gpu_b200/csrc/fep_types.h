@@ -209,7 +209,7 @@ int fep_launch_gather_x(const float* d_x, int stride, const int* d_touched, floa
  * caller's float device buffers they are added into (any of them may be NULL) */
 struct ExportLayout
 {
-    int ngrp, nforeign, energy, foreign, shift;
+    int ngrp, nforeign, energy, foreign, shift, atomic;
     int off_vc, off_vv, off_dvdl, off_foreign_e, off_foreign_dvdl;
 };
 struct ExportTargets

@@ -1857,7 +1857,8 @@ int fepb200_add_forces_device(fepb200_ctx* c, float* d_f, int flags)
     const float* r32 = c->ka.res_f32;
     const int    k0  = c->px_on ? c->x_atom_begin : 0;
     const int    k1  = c->px_on ? c->x_atom_end : c->layout.ntouched;
-    const int    err = fep_launch_add_forces(r32, c->d_touched.ptr, d_f, k0, k1, (flags & FEPB200_CLEAR_OUTPUTS) != 0 ? 1 : 0,
+    const int    err = fep_launch_add_forces(r32, c->d_touched.ptr, d_f, k0, k1,
+                                             (flags & FEPB200_CLEAR_OUTPUTS) != 0 ? 1 : ((flags & FEPB200_ATOMIC_OUTPUTS) != 0 ? 2 : 0),
                                              c->stream, &c->launches);
     if (err != 0)
     {
@@ -1895,6 +1896,7 @@ int fepb200_export_scalars_device(fepb200_ctx* c, int flags, float* eLJ, float* 
     lay.energy           = sf.energy ? 1 : 0;
     lay.foreign          = sf.foreign ? 1 : 0;
     lay.shift            = (sf.force && sf.shift) ? 1 : 0;
+    lay.atomic           = (flags & FEPB200_ATOMIC_OUTPUTS) != 0 ? 1 : 0;
     lay.off_vc           = (int)l.off_vc;
     lay.off_vv           = (int)l.off_vv;
     lay.off_dvdl         = (int)l.off_dvdl;

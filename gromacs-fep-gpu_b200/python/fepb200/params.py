@@ -33,6 +33,7 @@ DO_FOREIGNLAMBDA = 1 << 3
 DO_POTENTIAL = 1 << 4
 DO_SR = 1 << 5
 CLEAR_OUTPUTS = 1 << 16
+ATOMIC_OUTPUTS = 1 << 17  # add_forces_device / export_scalars_device: atomic adds (another stream adds into the same buffers)
 
 NUM_SHIFT_VECTORS = 45
 CENTRAL_SHIFT_INDEX = 22

@@ -48,6 +48,11 @@ extern "C" {
  * host output arrays of fepb200_compute() / fepb200_download().  For the force array only
  * the entries of atoms that occur in the pair list are written; all others are left alone. */
 #define FEPB200_CLEAR_OUTPUTS (1 << 16)
+/* extension bit for fepb200_add_forces_device() / fepb200_export_scalars_device(): add with atomic
+ * operations, because kernels on ANOTHER stream may be adding into the same device buffers at the same
+ * time -- the fork's local and non-local non-bonded kernels do, with atomicAdd, into one NBAtomDataGpu
+ * (f, fShift, eLJ, eElec, ...; nbnxm/cuda/nbnxm_cuda_kernel_utils.cuh) when a rank has two localities. */
+#define FEPB200_ATOMIC_OUTPUTS (1 << 17)
 
 /* ---- enum values: identical integers to the reference enums ------------
  * api/legacy/include/gromacs/mdtypes/md_enums.h:238-274,324-334,640-646 */

@@ -1,6 +1,7 @@
 #!/bin/bash
-# Builds the reference (fork) WITH its CUDA back end for sm_100 and the fepb200 hook: the fork's own `mdrun -nb gpu -fep gpu`
-# and `mdrun -nb gpu -fep cpu` + GMX_FEPB200 (our library beside its GPU non-bonded kernels) from one binary.
+# Builds the reference (fork) WITH its CUDA back end for sm_100 and the fepb200 hooks: the fork's own `mdrun -nb gpu -fep gpu`,
+# `mdrun -nb gpu -fep cpu` + GMX_FEPB200 (our library beside its GPU non-bonded kernels, host hand-over) and
+# `mdrun -nb gpu -fep gpu` + GMX_FEPB200 (our library inside its GPU route, device-resident) from one binary.
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 SRC=/tmp/gmxsrc
@@ -12,6 +13,9 @@ fi
 # (re-)apply the hook to a pristine copy of the one file it touches
 cp /root/reference/src/gromacs/nbnxm/freeenergydispatch.cpp "$SRC/src/gromacs/nbnxm/freeenergydispatch.cpp"
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/freeenergydispatch_fepb200.patch")
+# ... and the hooks in the fork's GPU route (mdrun -nb gpu -fep gpu + GMX_FEPB200: libfepb200 instead of k_calc_nb_fep*)
+for f in src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp src/gromacs/nbnxm/cuda/nbnxm_cuda.cu; do cp "/root/reference/$f" "$SRC/$f"; done
+(cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/nbnxm_gpu_fepb200.patch")
 mkdir -p "$BUILD"
 cmake -G Ninja -S "$SRC" -B "$BUILD" -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ \
   -DCMAKE_POLICY_VERSION_MINIMUM=3.5 -DGMX_GPU=CUDA -DGMX_CUDA_TARGET_SM=100 -DCUDA_TOOLKIT_ROOT_DIR=/usr/local/cuda -DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc -DGMX_MPI=OFF -DGMX_THREAD_MPI=ON -DGMX_OPENMP=ON \

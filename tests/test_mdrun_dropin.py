@@ -20,19 +20,24 @@ GMX = os.path.join(ROOT, "integration", "_gmx", "bin", "gmx")
 GMXLIBDIR = os.path.join(ROOT, "integration", "_gmx", "lib")
 TPR = os.path.join(ROOT, "tests", "golden", "mdrun_tpr")
 LIB = os.path.join(ROOT, "gromacs-fep-gpu_b200", "lib", "libfepb200.so")
-SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwtogether", "transformAtoB", "vdwalone",
-           # BASELINE.json's configs[0] and configs[1] as real GROMACS systems (integration/systems/make_systems.py):
-           # methane decoupling in a 2.65 k-atom TIP3P box, one lambda; a 50-atom solute transformed A -> B in a
-           # 24.5 k-atom box with 20 lambda states and foreign-energy output
-           "c1_methane", "c2_hexadecane",
-           # the same systems with LJ-PME; with the Gapsys soft-core and separate coul / vdw lambda paths (configs[2] in
-           # kind); with reaction-field, 40 lambda states, sc-coul and 2 energy groups (configs[3] in kind)
-           "c1_methane_ljpme", "c2_hexadecane_gapsys", "c2_hexadecane_rf",
-           # the rest of the reference's mdrun free-energy test systems that have perturbed non-bonded pairs
-           # (src/programs/mdrun/tests/freeenergy.cpp:217-242; "restraints" and "simtemp" have none / no dH output):
-           # intramolecular coupling, expanded ensemble (100 steps, lambda changes during the run), relative
-           # free energies with and without position restraints
-           "coulandvdwintramol", "expanded", "relative", "relative-position-restraints"]
+# the reference's own free-energy test systems this test has passed on a B200 with
+SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwtogether", "transformAtoB", "vdwalone"]
+# Added after round 1's GPU budget was spent (all pass through the shim on CPU, tests/test_shim_cpu.py); their
+# first GPU run is the round-end one, so they are run by tests/test_z2_mdrun_dropin_more.py, which sorts after
+# the tests that have run on a B200 (a surprise there must not hide those under `pytest -x`).
+MORE_SYSTEMS = [
+    # BASELINE.json's configs[0] and configs[1] as real GROMACS systems (integration/systems/make_systems.py):
+    # methane decoupling in a 2.65 k-atom TIP3P box, one lambda; a 50-atom solute transformed A -> B in a
+    # 24.5 k-atom box with 20 lambda states and foreign-energy output
+    "c1_methane", "c2_hexadecane",
+    # the same systems with LJ-PME; with the Gapsys soft-core and separate coul / vdw lambda paths (configs[2] in
+    # kind); with reaction-field, 40 lambda states, sc-coul and 2 energy groups (configs[3] in kind)
+    "c1_methane_ljpme", "c2_hexadecane_gapsys", "c2_hexadecane_rf",
+    # the rest of the reference's mdrun free-energy test systems that have perturbed non-bonded pairs
+    # (src/programs/mdrun/tests/freeenergy.cpp:217-242; "restraints" and "simtemp" have none / no dH output):
+    # intramolecular coupling, expanded ensemble (100 steps, lambda changes during the run), relative
+    # free energies with and without position restraints
+    "coulandvdwintramol", "expanded", "relative", "relative-position-restraints"]
 
 
 def _xvg(path):
@@ -179,6 +184,10 @@ def compare_with_reference_golden(system, run):
 @pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
 @pytest.mark.parametrize("system", SYSTEMS)
 def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, tmp_path):
+    run_both_routes_and_compare(system, tmp_path)
+
+
+def run_both_routes_and_compare(system, tmp_path):
     tpr = os.path.join(TPR, system + ".tpr")
     if not os.path.exists(tpr):
         pytest.skip("no run input for " + system)
@@ -187,17 +196,3 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
     compare_runs(system, cpu, gpu)
     compare_with_reference_golden(system, gpu)
     _note_timing(system, str(tmp_path / "cpu"), str(tmp_path / "gpu"), gpu[0])
-
-
-@pytest.mark.skipif(not os.path.exists(GMX), reason="integration/_gmx not built (integration/build_patched_gmx.sh)")
-def test_mdrun_with_two_domain_decomposition_ranks(tmp_path):
-    """Two thread-MPI ranks (domain decomposition 2x1x1) sharing the B200: each rank has its own local and
-    non-local FEP lists and its own library context (the shim keeps one per rank thread); with
-    GMX_FEPB200_DEVICES=N the ranks would be spread over N GPUs.  (Added after round 1's GPU budget was
-    spent: verified on CPU through tests/test_shim_cpu.py, first GPU run is the round-end one.)"""
-    tpr = os.path.join(TPR, "c2_hexadecane.tpr")
-    args = ("-nstlist", "5", "-dd", "2", "1", "1")
-    cpu = _run(tpr, str(tmp_path / "cpu"), False, mdrun_args=args, ntmpi=2)
-    gpu = _run(tpr, str(tmp_path / "gpu"), True, mdrun_args=args, ntmpi=2)
-    assert gpu[0].count("computed by fepb200") == 2
-    compare_runs("c2_hexadecane, 2 ranks", cpu, gpu)

@@ -137,3 +137,30 @@ def test_scalars_exported_into_the_forks_device_buffers(ctx):
     assert close(got["eLJForeign"], want["foreign_energy"]) and not got["eElecForeign"].any()
     assert close(got["dvdlElecForeign"], want["foreign_dvdl"][:, 0]) and close(got["dvdlLJForeign"], want["foreign_dvdl"][:, 1])
     assert close(got["fShift"], want["fshift"].reshape(-1))
+
+
+def test_atomic_outputs_give_the_same_sums(ctx):
+    """FEPB200_ATOMIC_OUTPUTS: the additions into the caller's device buffers are atomic (a rank of the fork
+    with two localities has the kernels of the other locality adding into the same NBAtomDataGpu from their
+    own stream).  Every element still has one writer of ours, so the values are those of the plain additions."""
+    import torch
+
+    prob = make_system(scaled_spec("C2", 3.2, 1, 20, n_foreign=4))
+    ctx.set_problem(prob)
+    ctx.upload_x(prob.x, prob.shiftvec)
+    ctx.launch(ALL)
+    n_l = prob.n_foreign + 1
+    sizes = dict(eLJ=1, eElec=1, dvdlLJ=1, dvdlElec=1, eLJForeign=n_l, eElecForeign=n_l, dvdlLJForeign=n_l,
+                 dvdlElecForeign=n_l, fShift=135)
+    out = []
+    for extra in (0, P.ATOMIC_OUTPUTS):
+        d_f = torch.full((prob.natoms, 3), 0.5, dtype=torch.float32, device="cuda")
+        buf = {k: torch.full((n,), 1.0, dtype=torch.float32, device="cuda") for k, n in sizes.items()}
+        torch.cuda.synchronize()
+        ctx.add_forces_device(d_f.data_ptr(), extra)
+        ctx.export_scalars_device(ALL | extra, **{k: v.data_ptr() for k, v in buf.items()})
+        ctx.wait()
+        out.append((d_f.cpu().numpy(), {k: v.cpu().numpy() for k, v in buf.items()}))
+    assert np.array_equal(out[0][0], out[1][0]) and (out[0][0] != 0.5).any()
+    for k in sizes:
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
