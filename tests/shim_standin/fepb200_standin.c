@@ -8,6 +8,10 @@
  * route.  The real library has no such path: without a CUDA device fepb200_create() fails.
  *
  * Semantics follow include/fepb200.h: inputs are copied at set_* time, compute() accumulates (+=).
+ *
+ * For tests/test_gpu_shim_cpu.py it also answers the five device-resident entry points the GPU-route shim
+ * binds (fepb200_set_stream, fepb200_gather_xq_device, fepb200_launch, fepb200_add_forces_device,
+ * fepb200_export_scalars_device) on host arrays.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -43,6 +47,14 @@ struct fepb200_ctx
     double            lambda[FEPB200_NUM_LAMBDA_COMPONENTS];
     long              n_set_list, n_set_atoms, n_set_params, n_set_lambdas, n_compute;
     char              err[256];
+    /* device-resident entry points (the GPU-route shim, integration/gromacs_shim/fepb200_gpu_shim.h): in a
+     * CPU test the caller's "device" arrays are host arrays */
+    float*  x_step;      /* coordinates of the step, rvec[natoms] */
+    float   sv_step[3 * FEPB200_NUM_SHIFT_VECTORS];
+    int     have_x, have_result, flags_result;
+    float * r_f, r_fshift[3 * FEPB200_NUM_SHIFT_VECTORS];
+    double *r_vc, *r_vv, r_dvdl[2], *r_fe, *r_fdvdl;
+    long    n_launch, n_set_stream;
 };
 
 static double* dup_f2d(const float* a, size_t n)
@@ -283,4 +295,126 @@ int fepb200_compute(fepb200_ctx* c, const float* x, const float* shiftvec, int f
                 c->n_set_list, c->n_set_atoms, c->n_set_params, c->n_set_lambdas);
     }
     return rc == 0 ? FEPB200_OK : FEPB200_ERR_INVALID_ARGUMENT;
+}
+
+/* ---- device-resident entry points, on host arrays (tests/test_gpu_shim_cpu.py) ------------------------- */
+int fepb200_set_stream(fepb200_ctx* c, void* stream)
+{
+    (void)stream;
+    c->n_set_stream++;
+    return FEPB200_OK;
+}
+
+int fepb200_gather_xq_device(fepb200_ctx* c, const float* d_xq, const float* shiftvec)
+{
+    if (!c->qA)
+    {
+        snprintf(c->err, sizeof(c->err), "gather before atoms were set");
+        return FEPB200_ERR_STATE;
+    }
+    free(c->x_step);
+    c->x_step = (float*)malloc(sizeof(float) * 3 * (size_t)(c->natoms ? c->natoms : 1));
+    for (int i = 0; i < c->natoms; i++)
+    {
+        for (int d = 0; d < 3; d++)
+        {
+            c->x_step[3 * (size_t)i + d] = d_xq[4 * (size_t)i + d]; /* .w (the charge) is ignored */
+        }
+    }
+    memcpy(c->sv_step, shiftvec, sizeof(c->sv_step));
+    c->have_x      = 1;
+    c->have_result = 0;
+    return FEPB200_OK;
+}
+
+int fepb200_launch(fepb200_ctx* c, int flags, void* stream)
+{
+    (void)stream;
+    if (!c->have_x)
+    {
+        snprintf(c->err, sizeof(c->err), "launch before coordinates were staged");
+        return FEPB200_ERR_STATE;
+    }
+    const int n = c->natoms, L = c->nforeign, G = c->ngrp;
+    free(c->r_f);
+    free(c->r_vc);
+    free(c->r_vv);
+    free(c->r_fe);
+    free(c->r_fdvdl);
+    c->r_f     = (float*)calloc(3 * (size_t)n + 1, sizeof(float));
+    c->r_vc    = (double*)calloc(G + 1, sizeof(double));
+    c->r_vv    = (double*)calloc(G + 1, sizeof(double));
+    c->r_fe    = (double*)calloc(L + 2, sizeof(double));
+    c->r_fdvdl = (double*)calloc(2 * (size_t)(L + 2), sizeof(double));
+    memset(c->r_fshift, 0, sizeof(c->r_fshift));
+    c->r_dvdl[0] = c->r_dvdl[1] = 0;
+    /* the host entry point with every output it can produce; flags decide what it fills */
+    const int rc = fepb200_compute(c, c->x_step, c->sv_step, flags, c->r_f, c->r_fshift, c->r_vc, c->r_vv, c->r_dvdl, c->r_fe,
+                                   c->r_fdvdl);
+    c->have_result  = rc == FEPB200_OK;
+    c->flags_result = flags;
+    c->n_launch++;
+    return rc;
+}
+
+int fepb200_add_forces_device(fepb200_ctx* c, float* d_f, int flags)
+{
+    if (!c->have_result)
+    {
+        snprintf(c->err, sizeof(c->err), "add_forces_device without a launch");
+        return FEPB200_ERR_STATE;
+    }
+    (void)flags; /* FEPB200_ATOMIC_OUTPUTS: one host thread here */
+    for (size_t i = 0; i < 3 * (size_t)c->natoms; i++)
+    {
+        d_f[i] += c->r_f[i];
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_export_scalars_device(fepb200_ctx* c, int flags, float* eLJ, float* eElec, float* dvdlLJ, float* dvdlElec,
+                                  float* eLJForeign, float* eElecForeign, float* dvdlLJForeign, float* dvdlElecForeign,
+                                  float* fShift)
+{
+    (void)eElecForeign; /* the energy of a point goes whole through eLJForeign (include/fepb200.h) */
+    if (!c->have_result)
+    {
+        snprintf(c->err, sizeof(c->err), "export_scalars_device without a launch");
+        return FEPB200_ERR_STATE;
+    }
+    if (flags & FEPB200_DO_POTENTIAL)
+    {
+        double vc = 0, vv = 0;
+        for (int g = 0; g < c->ngrp; g++)
+        {
+            vc += c->r_vc[g];
+            vv += c->r_vv[g];
+        }
+        if (eElec) *eElec += (float)vc;
+        if (eLJ) *eLJ += (float)vv;
+    }
+    if (dvdlElec) *dvdlElec += (float)c->r_dvdl[0];
+    if (dvdlLJ) *dvdlLJ += (float)c->r_dvdl[1];
+    if (flags & FEPB200_DO_FOREIGNLAMBDA)
+    {
+        for (int i = 0; i <= c->nforeign; i++)
+        {
+            if (eLJForeign) eLJForeign[i] += (float)c->r_fe[i];
+            if (dvdlElecForeign) dvdlElecForeign[i] += (float)c->r_fdvdl[2 * i];
+            if (dvdlLJForeign) dvdlLJForeign[i] += (float)c->r_fdvdl[2 * i + 1];
+        }
+    }
+    if ((flags & FEPB200_DO_FORCE) && (flags & FEPB200_DO_SHIFTFORCE) && fShift)
+    {
+        for (int i = 0; i < 3 * FEPB200_NUM_SHIFT_VECTORS; i++)
+        {
+            fShift[i] += c->r_fshift[i];
+        }
+    }
+    if (getenv("FEPB200_STANDIN_TRACE"))
+    {
+        fprintf(stderr, "standin: launch %ld set_list %ld set_atoms %ld set_params %ld set_lambdas %ld set_stream %ld\n",
+                c->n_launch, c->n_set_list, c->n_set_atoms, c->n_set_params, c->n_set_lambdas, c->n_set_stream);
+    }
+    return FEPB200_OK;
 }
