@@ -10,6 +10,11 @@ if [ ! -d "$SRC/src" ]; then
 fi
 # (re-)apply the hook to a pristine copy of the one file it touches
 cp /root/reference/src/gromacs/nbnxm/freeenergydispatch.cpp "$SRC/src/gromacs/nbnxm/freeenergydispatch.cpp"
+# the source copy is shared with build_patched_gmx_cuda.sh, whose GPU-route patch touches three more files: this build
+# takes them as they are in the reference
+for f in src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp src/gromacs/nbnxm/cuda/nbnxm_cuda.cu src/gromacs/mdlib/sim_util.cpp; do
+  cmp -s "/root/reference/$f" "$SRC/$f" || cp "/root/reference/$f" "$SRC/$f"
+done
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/freeenergydispatch_fepb200.patch")
 mkdir -p "$BUILD"
 cmake -G Ninja -S "$SRC" -B "$BUILD" -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ \

@@ -14,7 +14,7 @@ fi
 cp /root/reference/src/gromacs/nbnxm/freeenergydispatch.cpp "$SRC/src/gromacs/nbnxm/freeenergydispatch.cpp"
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/freeenergydispatch_fepb200.patch")
 # ... and the hooks in the fork's GPU route (mdrun -nb gpu -fep gpu + GMX_FEPB200: libfepb200 instead of k_calc_nb_fep*)
-for f in src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp src/gromacs/nbnxm/cuda/nbnxm_cuda.cu; do cp "/root/reference/$f" "$SRC/$f"; done
+for f in src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp src/gromacs/nbnxm/cuda/nbnxm_cuda.cu src/gromacs/mdlib/sim_util.cpp; do cp "/root/reference/$f" "$SRC/$f"; done
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/nbnxm_gpu_fepb200.patch")
 mkdir -p "$BUILD"
 cmake -G Ninja -S "$SRC" -B "$BUILD" -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ \

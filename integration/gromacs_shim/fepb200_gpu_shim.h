@@ -8,8 +8,9 @@
  *   hook                          fork function (file:line)                             what it hands over
  *   setInteractionConstants()     gpu_init                  (nbnxm_gpu_data_mgmt.cpp:538) interaction_const_t (read again every step:
  *                                                                                       PME tuning changes it in place)
- *   setLambdas()                  cuda_copy_fepparams       (:491-536)                  lambda_q, lambda_v, all_lambda -- uploaded once,
- *                                                                                       like the fork does
+ *   setLambdas()                  cuda_copy_fepparams       (:491-536)                  lambda_q, lambda_v, all_lambda at set-up
+ *   setCurrentLambdas()           do_force                  (mdlib/sim_util.cpp:1764)   lambda_q, lambda_v of the coming step (the
+ *                                                                                       fork uploads them once: SURVEY 2e-6)
  *   setAtoms()                    gpu_init_atomdata         (:990-1040)                 qA, qB, typeA, typeB and the nbfp table in
  *                                                                                       nbat (grid) order
  *   setShiftVectors()             gpu_upload_shiftvec       (:647-664)                  the 45 shift vectors
@@ -108,6 +109,24 @@ inline void setLambdas(const void* nb, float lambdaCoul, float lambdaVdw, int nL
     s.allCoul.assign(allCoul, allCoul + (nLambda > 0 ? nLambda : 0));
     s.allVdw.assign(allVdw, allVdw + (nLambda > 0 ? nLambda : 0));
     s.lambdasVersion++;
+}
+
+/* The lambdas of the coming step (hook in do_force, mdlib/sim_util.cpp, beside gpu_upload_shiftvec): closes the
+ * fork's gap that lambda is uploaded once at set-up (nbnxm_setup.cpp:465-486), so that runs whose lambda moves
+ * (delta-lambda / slow growth) see the current value, like the CPU route (freeenergydispatch.cpp:236-253). */
+inline void setCurrentLambdas(const void* nb, float lambdaCoul, float lambdaVdw)
+{
+    if (!enabled())
+    {
+        return;
+    }
+    State& s = state(nb);
+    if (s.lambda[FEPB200_LAMBDA_COUL] != lambdaCoul || s.lambda[FEPB200_LAMBDA_VDW] != lambdaVdw)
+    {
+        s.lambda[FEPB200_LAMBDA_COUL] = lambdaCoul;
+        s.lambda[FEPB200_LAMBDA_VDW]  = lambdaVdw;
+        s.lambdasVersion++;
+    }
 }
 
 template<typename RealVector, typename IntVector>

@@ -13,7 +13,8 @@
  * localities (first / second half of the i-entries).  Steps:
  *   0  search step; energies + virial + foreign lambdas
  *   1  plain force step (no energy, no virial): scalar buffers must stay as they are
- *   2  search step (atoms and lists handed over again), coordinates moved; energies + virial, no foreign
+ *   2  search step (atoms and lists handed over again), coordinates moved, lambda moved (slow growth: +0.125 on both
+ *      components, through the per-step hook of do_force); energies + virial, no foreign
  * Result file, per step: float f[3N], eLJ, eElec, dvdlLJ, dvdlElec, eLJForeign[L+1], eElecForeign[L+1],
  * dvdlLJForeign[L+1], dvdlElecForeign[L+1], fShift[135].
  */
@@ -153,6 +154,9 @@ int main(int argc, char** argv)
             xq[4 * (size_t)i + 3] = 99.0F; /* the charge slot: must be ignored */
         }
         fepb200gpu::setShiftVectors(nb, sv.data());
+        /* do_force: the lambdas of this step (unchanged on steps 0 and 1) */
+        const float dl = step == 2 ? 0.125F : 0.0F;
+        fepb200gpu::setCurrentLambdas(nb, lambda[FEPB200_LAMBDA_COUL] + dl, lambda[FEPB200_LAMBDA_VDW] + dl);
         /* gpu_clear_outputs: forces every step, scalars on virial steps, foreign arrays every step */
         std::fill(force.begin(), force.end(), 0.0F);
         if (virial)

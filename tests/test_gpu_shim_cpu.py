@@ -52,13 +52,13 @@ def test_gpu_route_shim_cadence_flags_and_routing(name, built, tmp_path):
     env = dict(os.environ, GMX_FEPB200="1", GMX_FEPB200_LIB=lib, FEPB200_STANDIN_TRACE="1")
     r = subprocess.run([drv, str(tmp_path / "p.bin"), str(tmp_path / "r.bin")], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
-    # one context per locality; per context: constants once, lambdas once (the fork uploads them once), atoms and
+    # one context per locality; per context: constants once, lambdas when they change (set-up and step 2), atoms and
     # list on the two search steps, three launches
     notes = [ln for ln in r.stderr.splitlines() if "GPU route, locality" in ln]
     assert len(notes) == 2 and all("computed by fepb200" in ln for ln in notes)
     last = [ln for ln in r.stderr.splitlines() if ln.startswith("standin: launch")][-2:]
     for ln in last:
-        assert ln.split()[1:] == "launch 3 set_list 2 set_atoms 2 set_params 1 set_lambdas 1 set_stream 1".split(), ln
+        assert ln.split()[1:] == "launch 3 set_list 2 set_atoms 2 set_params 1 set_lambdas 2 set_stream 1".split(), ln
 
     n, l = prob.natoms, prob.n_foreign
     raw = np.fromfile(tmp_path / "r.bin", dtype=np.float32)
@@ -70,6 +70,8 @@ def test_gpu_route_shim_cadence_flags_and_routing(name, built, tmp_path):
 
     moved = copy.copy(prob)
     moved.x = _moved(prob.x)
+    moved.lambda_ = np.array(prob.lambda_, dtype=np.float32).copy()  # slow growth: the per-step hook of do_force
+    moved.lambda_[[P.LAMBDA_COUL, P.LAMBDA_VDW]] += np.float32(0.125)
     ref2 = oracle.run_best(moved, ALL & ~P.DO_FOREIGNLAMBDA)
 
     def unpack(k):
@@ -100,7 +102,7 @@ def test_gpu_route_shim_cadence_flags_and_routing(name, built, tmp_path):
     assert s1["eLJ"] == 7.0 and s1["eElec"] == 7.0 and s1["dvdlLJ"] == 7.0 and s1["dvdlElec"] == 7.0
     assert np.all(s1["fShift"] == 7.0)
     assert not (s1["eLJF"].any() or s1["eElF"].any() or s1["dLJF"].any() or s1["dElF"].any())
-    # step 2: new coordinates, new hand-over; no foreign lambdas this step
+    # step 2: new coordinates, new hand-over, new lambda; no foreign lambdas this step
     assert close(s2["f"], ref2["f"]) and close(s2["fShift"], ref2["fshift"], 2e-6 * fscale)
     assert close(s2["eElec"], ref2["Vc"].sum()) and close(s2["eLJ"], ref2["Vv"].sum())
     assert close(s2["dvdlElec"], ref2["dvdl"][0]) and close(s2["dvdlLJ"], ref2["dvdl"][1])
