@@ -37,4 +37,13 @@ for sys in coulandvdwsequential_coul coulandvdwsequential_vdw coulandvdwtogether
   (cd /tmp && "$OUT/bin/gmx" -quiet grompp -f "$d/grompp.mdp" -c "$d/conf.gro" -p "$d/topol.top" -o "$TPR/$sys.tpr" \
      -po /tmp/mdout_$sys.mdp -maxwarn 10 > /tmp/grompp_$sys.log 2>&1) || { echo "grompp failed for $sys"; tail -5 /tmp/grompp_$sys.log; }
 done
+# the reference's coulandvdwtogether system as a slow-growth run: lambda moves from 0.5 by 0.005 per step, so every
+# step needs the current lambda (the fork's GPU route uploads it once)
+if [ ! -f "$TPR/coulandvdwtogether_slowgrowth.tpr" ]; then
+  d="$SRC/src/testutils/simulationdatabase/freeenergy/coulandvdwtogether"
+  sed 's/^init-lambda .*$/init-lambda              = 0.5\ndelta-lambda             = 0.005/' "$d/grompp.mdp" > /tmp/grompp_slowgrowth.mdp
+  (cd /tmp && "$OUT/bin/gmx" -quiet grompp -f /tmp/grompp_slowgrowth.mdp -c "$d/conf.gro" -p "$d/topol.top" \
+     -o "$TPR/coulandvdwtogether_slowgrowth.tpr" -po /tmp/mdout_slowgrowth.mdp -maxwarn 10 > /tmp/grompp_slowgrowth.log 2>&1) \
+    || { echo "grompp failed for the slow-growth system"; tail -5 /tmp/grompp_slowgrowth.log; }
+fi
 ls -la "$OUT/bin" "$OUT/lib" "$TPR"

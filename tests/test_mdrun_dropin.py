@@ -37,7 +37,10 @@ MORE_SYSTEMS = [
     # (src/programs/mdrun/tests/freeenergy.cpp:217-242; "restraints" and "simtemp" have none / no dH output):
     # intramolecular coupling, expanded ensemble (100 steps, lambda changes during the run), relative
     # free energies with and without position restraints
-    "coulandvdwintramol", "expanded", "relative", "relative-position-restraints"]
+    "coulandvdwintramol", "expanded", "relative", "relative-position-restraints",
+    # the reference's coulandvdwtogether system as a slow-growth run (integration/build_patched_gmx.sh): lambda moves
+    # every step
+    "coulandvdwtogether_slowgrowth"]
 
 
 def _xvg(path):

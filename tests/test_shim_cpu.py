@@ -33,7 +33,9 @@ def standin():
 
 @pytest.mark.parametrize("system", ["coulandvdwtogether", "transformAtoB", "c1_methane", "c1_methane_ljpme", "c2_hexadecane",
                                     "c2_hexadecane_gapsys", "c2_hexadecane_rf", "coulandvdwintramol", "expanded", "relative",
-                                    "relative-position-restraints"])
+                                    "relative-position-restraints",
+                                    # slow growth: lambda moves every step (0.5 + 0.005 per step)
+                                    "coulandvdwtogether_slowgrowth"])
 def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
     tpr = os.path.join(T.TPR, system + ".tpr")
     # mdrun would raise nstlist to 100 for these small systems: keep a pair search every 5 steps
@@ -51,7 +53,9 @@ def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
     searches = (n["compute"] - 1) // 5 + 1
     assert n["set_list"] == n["set_atoms"] == searches, n
     assert n["set_params"] <= searches, n
-    if system != "expanded":
+    if system == "coulandvdwtogether_slowgrowth":
+        assert n["set_lambdas"] == n["compute"], n  # a new lambda every step
+    elif system != "expanded":
         assert n["set_lambdas"] <= searches, n
     assert "fepb200 shim:" in via[0]  # the shim's own timing summary at exit
 

@@ -43,7 +43,9 @@ def _max_dev(run, ref):
 
 
 @pytest.mark.skipif(not os.path.exists(GMX_CUDA), reason="integration/_gmx_cuda not built (integration/build_patched_gmx_cuda.sh)")
-@pytest.mark.parametrize("system", ["coulandvdwtogether", "c2_hexadecane"])
+# the slow-growth system: lambda moves every step; the fork's GPU route uploads lambda once at set-up,
+# so (c) is expected to drift away from (a) there, while (b) gets the current lambda through the hook in do_force
+@pytest.mark.parametrize("system", ["coulandvdwtogether", "c2_hexadecane", "coulandvdwtogether_slowgrowth"])
 def test_library_inside_the_forks_gpu_route(system, tmp_path):
     tpr = os.path.join(T.TPR, system + ".tpr")
     try:
