@@ -74,7 +74,11 @@ def main():
                     ctx.wait()
                     (kms if profiling else step_ms).append(ctx.kernel_ms() if profiling else ctx.last_launch_ms())
             ctx.set_profiling(False)
-            fork = oracle.run_fork_cuda(prob, ALL, repeats=20)
+            try:
+                fork = oracle.run_fork_cuda(prob, ALL, repeats=20)
+            except Exception as exc:  # noqa: BLE001 -- foreign kernels in this process: a device fault of theirs is sticky, stop here
+                print(json.dumps(dict(problem=label, fork_error=f"{type(exc).__name__}: {exc}"[:800])), flush=True)
+                return
             line = dict(
                 problem=label, natoms=int(prob.natoms), pairs=int(prob.nblist.nrj), entries=int(prob.nblist.nri),
                 n_foreign=int(prob.n_foreign),
