@@ -22,6 +22,23 @@ def test_header_and_binding_agree():
     assert _declared_symbols() == sorted(L.SYMBOLS)
 
 
+def test_constants_of_header_and_python_mirror_agree():
+    """Every integer macro of include/fepb200.h (flags, enum values, error codes) that fepb200.params mirrors has
+    the same value there; the flags and extension bits must all be mirrored."""
+    from fepb200 import params as P
+
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fepb200.h")).read(), flags=re.S)
+    macros = {m.group(1): eval(m.group(2), {"__builtins__": {}})  # noqa: S307 -- "(1 << 4)", "(-3)", "45" of our own header
+              for m in re.finditer(r"^#define\s+FEPB200_([A-Z0-9_]+)\s+(\(?-?\s*[0-9][0-9 <()]*\)?)\s*$", txt, flags=re.M)}
+    assert len(macros) >= 25
+    mirrored = [k for k in macros if hasattr(P, k)]
+    for k in mirrored:
+        assert getattr(P, k) == macros[k], k
+    for k in ("DO_FORCE", "DO_SHIFTFORCE", "DO_FOREIGNLAMBDA", "DO_POTENTIAL", "DO_SR", "CLEAR_OUTPUTS", "ATOMIC_OUTPUTS",
+              "EEL_PME", "VDW_PME", "SC_GAPSYS", "LAMBDA_COUL", "LAMBDA_VDW"):
+        assert k in mirrored, k
+
+
 def test_library_exports_every_declared_symbol():
     if not os.path.exists(L.LIB_PATH):
         import __graft_entry__
