@@ -2,7 +2,8 @@
  * fepb200_shim_common.h -- what both reference-side bindings of libfepb200.so share: the dlopen()ed entry
  * points, one library context per calling thread for the CPU route (fepb200_shim.h), the translation of
  * interaction_const_t into fepb200_params.  Included by fepb200_shim.h (hook in
- * src/gromacs/nbnxm/freeenergydispatch.cpp) and fepb200_gpu_shim.h (hooks in the fork's GPU route).
+ * src/gromacs/nbnxm/freeenergydispatch.cpp), fepb200_gpu_shim.h (hooks in the fork's GPU route) and
+ * fepb200_pairs14_shim.h (hook in src/gromacs/listed_forces/pairs.cpp).
  */
 #ifndef FEPB200_SHIM_COMMON_H
 #define FEPB200_SHIM_COMMON_H
@@ -40,6 +41,12 @@ struct Api
     decltype(&fepb200_launch)                launch                = nullptr;
     decltype(&fepb200_add_forces_device)     add_forces_device     = nullptr;
     decltype(&fepb200_export_scalars_device) export_scalars_device = nullptr;
+    /* perturbed 1-4 pairs (fepb200_pairs14_shim.h) */
+    decltype(&fepb200_pairs14_create)     pairs14_create     = nullptr;
+    decltype(&fepb200_pairs14_last_error) pairs14_last_error = nullptr;
+    decltype(&fepb200_pairs14_set_params) pairs14_set_params = nullptr;
+    decltype(&fepb200_pairs14_set_pairs)  pairs14_set_pairs  = nullptr;
+    decltype(&fepb200_pairs14_compute)    pairs14_compute    = nullptr;
     fepb200_ctx*                   ctx         = nullptr;
     bool                           symbols = false, tried = false, ok = false;
     long                           calls = 0, searchCalls = 0;
@@ -129,6 +136,11 @@ inline void loadSymbols()
     FEPB200_SYM(launch);
     FEPB200_SYM(add_forces_device);
     FEPB200_SYM(export_scalars_device);
+    FEPB200_SYM(pairs14_create);
+    FEPB200_SYM(pairs14_last_error);
+    FEPB200_SYM(pairs14_set_params);
+    FEPB200_SYM(pairs14_set_pairs);
+    FEPB200_SYM(pairs14_compute);
 #undef FEPB200_SYM
     if (!a.create || !a.compute || !a.set_list)
     {

@@ -418,3 +418,139 @@ int fepb200_export_scalars_device(fepb200_ctx* c, int flags, float* eLJ, float* 
     }
     return FEPB200_OK;
 }
+
+/* ---- perturbed 1-4 pairs (integration/gromacs_shim/fepb200_pairs14_shim.h), answered by fep_oracle_pairs14 ---- */
+int fep_oracle_pairs14(const fep_oracle_params* p, double fudgeQQ, int npairs, const int* iatoms, const double* c6A,
+                       const double* c12A, const double* c6B, const double* c12B, const double* x, const double* qA,
+                       const double* qB, const double* box_diag, int pbc_type, const int* gid, double lam_c, double lam_v,
+                       double* f, double* fshift, double* Vc, double* Vv, double* dvdl);
+
+struct fepb200_pairs14
+{
+    fepb200_ctx c; /* params only */
+    double      fudge;
+    int         natoms, npairs, ntypes, ngrp;
+    int *       iatoms, *gid;
+    double *    qA, *qB, *c6A, *c12A, *c6B, *c12B;
+    long        n_set_pairs, n_compute;
+    char        err[256];
+};
+
+int fepb200_pairs14_create(fepb200_pairs14** h, int device_ordinal)
+{
+    (void)device_ordinal;
+    *h = (fepb200_pairs14*)calloc(1, sizeof(fepb200_pairs14));
+    return FEPB200_OK;
+}
+
+int fepb200_pairs14_destroy(fepb200_pairs14* h)
+{
+    free(h);
+    return FEPB200_OK;
+}
+
+const char* fepb200_pairs14_last_error(const fepb200_pairs14* h)
+{
+    return h ? h->err : "";
+}
+
+int fepb200_pairs14_set_params(fepb200_pairs14* h, const fepb200_params* ic, float fudgeQQ)
+{
+    h->fudge = fudgeQQ;
+    return fepb200_set_params(&h->c, ic);
+}
+
+int fepb200_pairs14_set_pairs(fepb200_pairs14* h, int natoms, const float* chargeA, const float* chargeB, int npairs,
+                              const int* iatoms, int ntypes, const float* c6A, const float* c12A, const float* c6B,
+                              const float* c12B, const int* gid, int nenergrp_pairs)
+{
+    free(h->iatoms);
+    free(h->gid);
+    free(h->qA);
+    free(h->qB);
+    free(h->c6A);
+    free(h->c12A);
+    free(h->c6B);
+    free(h->c12B);
+    h->natoms = natoms;
+    h->npairs = npairs;
+    h->ntypes = ntypes;
+    h->ngrp   = nenergrp_pairs;
+    h->iatoms = dup_i(iatoms, 3 * (size_t)npairs);
+    if (gid)
+    {
+        h->gid = dup_i(gid, npairs);
+    }
+    else
+    {
+        h->gid = (int*)calloc(npairs ? npairs : 1, sizeof(int));
+    }
+    h->qA   = dup_f2d(chargeA, natoms);
+    h->qB   = dup_f2d(chargeB, natoms);
+    h->c6A  = dup_f2d(c6A, ntypes);
+    h->c12A = dup_f2d(c12A, ntypes);
+    h->c6B  = dup_f2d(c6B, ntypes);
+    h->c12B = dup_f2d(c12B, ntypes);
+    h->n_set_pairs++;
+    return FEPB200_OK;
+}
+
+int fepb200_pairs14_compute(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, const float* lambda,
+                            int flags, float* f, float* fshift, double* Vc14, double* Vv14, double* dvdl)
+{
+    if (!h->c.have_params || !h->iatoms)
+    {
+        snprintf(h->err, sizeof(h->err), "pairs14 compute before params / pairs were set");
+        return FEPB200_ERR_STATE;
+    }
+    const int n  = h->natoms;
+    double*   xd = dup_f2d(x, 3 * (size_t)n);
+    double*   fd = (double*)calloc(3 * (size_t)n + 1, sizeof(double));
+    double    fs[3 * FEPB200_NUM_SHIFT_VECTORS] = { 0 }, bd[3] = { box_diag[0], box_diag[1], box_diag[2] }, dv[2] = { 0, 0 };
+    double*   vc = (double*)calloc(h->ngrp + 1, sizeof(double));
+    double*   vv = (double*)calloc(h->ngrp + 1, sizeof(double));
+    const int rc = fep_oracle_pairs14(&h->c.p, h->fudge, h->npairs, h->iatoms, h->c6A, h->c12A, h->c6B, h->c12B, xd, h->qA, h->qB,
+                                      bd, pbc_type, h->gid, lambda[FEPB200_LAMBDA_COUL], lambda[FEPB200_LAMBDA_VDW], fd, fs, vc, vv,
+                                      dv);
+    if (rc == 0)
+    {
+        if (flags & FEPB200_DO_FORCE)
+        {
+            for (size_t i = 0; i < 3 * (size_t)n; i++)
+            {
+                f[i] += (float)fd[i];
+            }
+            if ((flags & FEPB200_DO_SHIFTFORCE) && fshift)
+            {
+                for (int i = 0; i < 3 * FEPB200_NUM_SHIFT_VECTORS; i++)
+                {
+                    fshift[i] += (float)fs[i];
+                }
+            }
+        }
+        if (flags & FEPB200_DO_POTENTIAL)
+        {
+            for (int g = 0; g < h->ngrp; g++)
+            {
+                Vc14[g] += vc[g];
+                Vv14[g] += vv[g];
+            }
+        }
+        dvdl[0] += dv[0];
+        dvdl[1] += dv[1];
+    }
+    else
+    {
+        snprintf(h->err, sizeof(h->err), "oracle pairs14 returned %d", rc);
+    }
+    free(xd);
+    free(fd);
+    free(vc);
+    free(vv);
+    h->n_compute++;
+    if (getenv("FEPB200_STANDIN_TRACE"))
+    {
+        fprintf(stderr, "standin: pairs14 compute %ld set_pairs %ld npairs %d\n", h->n_compute, h->n_set_pairs, h->npairs);
+    }
+    return rc == 0 ? FEPB200_OK : FEPB200_ERR_INVALID_ARGUMENT;
+}

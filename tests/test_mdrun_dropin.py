@@ -52,7 +52,8 @@ def _xvg(path):
     return np.array(rows)
 
 
-WANT = ("Potential", "LJ-(SR)", "Coulomb-(SR)", "dVremain/dl", "dVcoul/dl", "dVvdw/dl", "dVbonded/dl", "dVrestraint/dl")
+WANT = ("Potential", "LJ-(SR)", "Coulomb-(SR)", "LJ-14", "Coulomb-14", "dVremain/dl", "dVcoul/dl", "dVvdw/dl", "dVbonded/dl",
+        "dVrestraint/dl")
 
 
 def _energy_terms(workdir, env, gmx=None):
@@ -67,8 +68,9 @@ def _energy_terms(workdir, env, gmx=None):
     return names
 
 
-def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=(), ntmpi=1, gmx=None, nb="cpu", fep="cpu"):
-    """One mdrun of the patched binary; use_gpu routes the perturbed pairs through `lib`."""
+def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=(), ntmpi=1, gmx=None, nb="cpu", fep="cpu", pairs14=False):
+    """One mdrun of the patched binary; use_gpu routes the perturbed non-bonded pairs through `lib`, pairs14 also the
+    perturbed 1-4 pairs (hook in listed_forces/pairs.cpp; GMX_FEPB200_NO_PAIRS14 keeps them on the reference code)."""
     gmx = gmx or GMX
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = os.path.join(os.path.dirname(os.path.dirname(gmx)), "lib") + ":" + env.get("LD_LIBRARY_PATH", "")
@@ -77,6 +79,8 @@ def _run(tpr, workdir, use_gpu, lib=LIB, extra_env=None, mdrun_args=(), ntmpi=1,
     env.update(extra_env or {})
     if use_gpu:
         env["GMX_FEPB200"] = "1"
+        if not pairs14:
+            env["GMX_FEPB200_NO_PAIRS14"] = "1"
     os.makedirs(workdir, exist_ok=True)
     r = subprocess.run([gmx, "-quiet", "mdrun", "-s", tpr, "-deffnm", "run", "-nb", nb, "-pme", "cpu", "-bonded", "cpu",
                         "-update", "cpu", "-fep", fep, "-ntmpi", str(ntmpi), "-ntomp", "2", "-notunepme"] + list(mdrun_args),
@@ -190,12 +194,16 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
     run_both_routes_and_compare(system, tmp_path)
 
 
-def run_both_routes_and_compare(system, tmp_path):
+def run_both_routes_and_compare(system, tmp_path, pairs14=False):
+    """pairs14: also route the perturbed 1-4 pairs through fepb200_pairs14_* (hook in listed_forces/pairs.cpp); off
+    here, tests/test_z6_mdrun_pairs14.py turns it on."""
     tpr = os.path.join(TPR, system + ".tpr")
     if not os.path.exists(tpr):
         pytest.skip("no run input for " + system)
     cpu = _run(tpr, str(tmp_path / "cpu"), False)
-    gpu = _run(tpr, str(tmp_path / "gpu"), True)
+    gpu = _run(tpr, str(tmp_path / "gpu"), True, pairs14=pairs14)
+    if pairs14:
+        assert "fepb200 pairs14 shim:" in gpu[0], "no perturbed 1-4 pairs went through the library"
     compare_runs(system, cpu, gpu)
     compare_with_reference_golden(system, gpu)
     _note_timing(system, str(tmp_path / "cpu"), str(tmp_path / "gpu"), gpu[0])

@@ -40,7 +40,7 @@ def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
     tpr = os.path.join(T.TPR, system + ".tpr")
     # mdrun would raise nstlist to 100 for these small systems: keep a pair search every 5 steps
     cpu = T._run(tpr, str(tmp_path / "cpu"), False, mdrun_args=("-nstlist", "5"))
-    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin, extra_env={"FEPB200_STANDIN_TRACE": "1"},
+    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin, pairs14=True, extra_env={"FEPB200_STANDIN_TRACE": "1"},
                  mdrun_args=("-nstlist", "5"))
     assert "CPU STAND-IN" in via[0]
     T.compare_runs(system, cpu, via)
@@ -58,6 +58,16 @@ def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
     elif system != "expanded":
         assert n["set_lambdas"] <= searches, n
     assert "fepb200 shim:" in via[0]  # the shim's own timing summary at exit
+    # the perturbed 1-4 pairs of the 50-atom solute go through fepb200_pairs14_* (hook in listed_forces/pairs.cpp;
+    # compare_runs above includes LJ-14 and Coulomb-14): one hand-over per pair list a thread sees -- its chunk of the
+    # force evaluation and, on the master thread, the list of the foreign-lambda evaluations
+    p14 = [ln for ln in via[0].splitlines() if ln.startswith("fepb200 pairs14 shim:")]
+    if system.startswith("c2_hexadecane"):
+        # never more hand-overs than pair searches (mdrun sets the bonded threading up again on search steps)
+        assert p14 and all(int(re.search(r"(\d+) pair-list uploads", ln).group(1)) <= searches for ln in p14), p14
+        assert any("135 perturbed 1-4 pairs" in ln for ln in p14), p14
+    elif system.startswith("coulandvdw") or system.startswith("c1_"):
+        assert not p14  # no perturbed 1-4 pairs in these systems
 
 
 def test_shim_with_domain_decomposition_one_context_per_rank(standin, tmp_path):
@@ -66,7 +76,7 @@ def test_shim_with_domain_decomposition_one_context_per_rank(standin, tmp_path):
     tpr = os.path.join(T.TPR, "c2_hexadecane.tpr")
     args = ("-nstlist", "5", "-dd", "2", "1", "1")
     cpu = T._run(tpr, str(tmp_path / "cpu"), False, mdrun_args=args, ntmpi=2)
-    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin, mdrun_args=args, ntmpi=2)
+    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin, pairs14=True, mdrun_args=args, ntmpi=2)
     assert via[0].count("CPU STAND-IN") == 2  # one context per rank
     assert via[0].count("fepb200 shim:") == 2
     T.compare_runs("c2_hexadecane, 2 ranks", cpu, via)
@@ -80,6 +90,6 @@ def test_shim_route_reproduces_the_reference_golden_vectors(system, standin, tmp
     as in the reference's test: with -nstlist 5 the reference's own CPU route moves away from its golden
     dV/dl by 0.57 kJ/mol on transformAtoB (the shim route moves with it)."""
     tpr = os.path.join(T.TPR, system + ".tpr")
-    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin)
+    via = T._run(tpr, str(tmp_path / "shim"), True, lib=standin, pairs14=True)
     assert "CPU STAND-IN" in via[0]
     assert T.compare_with_reference_golden(system, via) >= 42

@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 # 1. the tests that have not run on a B200 yet, in the order of tests/ (no -x: every file gets its verdict)
 python -m pytest -q -m gpu tests/test_z1_gpu_device_handoff.py tests/test_z2_mdrun_dropin_more.py tests/test_z3_fork_cuda.py \
-  tests/test_z4_mdrun_gpu_build.py tests/test_z5_mdrun_gpu_route.py -rA > gpurun_out/round2_pending_tests.log 2>&1
+  tests/test_z4_mdrun_gpu_build.py tests/test_z5_mdrun_gpu_route.py tests/test_z6_mdrun_pairs14.py -rA > gpurun_out/round2_pending_tests.log 2>&1
 tail -40 gpurun_out/round2_pending_tests.log
 # 2. the bench line with the fork's own CUDA kernels beside ours (fork_gpu_baseline) and the full-size comparison
 python bench.py --steps 50 --warmup 5 > gpurun_out/round2_bench.json 2> gpurun_out/round2_bench.err
