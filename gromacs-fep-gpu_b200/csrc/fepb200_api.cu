@@ -179,6 +179,10 @@ struct fepb200_ctx
     long long    launches = 0;
     bool         timed    = false;
     bool         staging_in_flight = false; /* an H2D copy out of h_step_in may still be running */
+    /* ... and when that copy was queued by gather_x_device(): ev_staged marks its end, so the next gather waits for
+     * the copy alone instead of draining a stream the caller shares with its own kernels (the nbnxm stream) */
+    cudaEvent_t  ev_staged       = nullptr;
+    bool         staged_by_event = false;
 
     /* constants */
     bool           have_params = false;
@@ -820,6 +824,7 @@ int fepb200_create(fepb200_ctx** out, int device_ordinal)
         || cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess
         || cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess
         || cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess
+        || cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming) != cudaSuccess
         || !create_copy_events(c)
         || c->d_counter.reserve(1) != cudaSuccess || cudaMemset(c->d_counter.ptr, 0, sizeof(unsigned int)) != cudaSuccess)
     {
@@ -918,6 +923,10 @@ int fepb200_destroy(fepb200_ctx* c)
     }
     cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_stop);
+    if (c->ev_staged)
+    {
+        cudaEventDestroy(c->ev_staged);
+    }
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->side_stream);
     cudaEventDestroy(c->fork_ev);
@@ -1704,6 +1713,7 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
     }
     lap_us(c, 1);
     c->staging_in_flight = true;
+    c->staged_by_event   = false;
     return FEPB200_OK;
 }
 
@@ -1721,12 +1731,22 @@ static int gather_x_device(fepb200_ctx* c, const float* d_x, int stride, const f
     cudaSetDevice(c->device);
     if (c->staging_in_flight)
     {
-        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+        /* the previous copy out of the pinned head must be done before the head is overwritten */
+        if (c->staged_by_event)
+        {
+            CU_CHECK(c, cudaEventSynchronize(c->ev_staged));
+        }
+        else
+        {
+            CU_CHECK(c, cudaStreamSynchronize(c->stream));
+        }
     }
     stage_head(c, shiftvec);
     CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr, c->h_step_in.ptr, sizeof(DynHead), cudaMemcpyHostToDevice,
                                 c->stream));
+    CU_CHECK(c, cudaEventRecord(c->ev_staged, c->stream));
     c->staging_in_flight = true;
+    c->staged_by_event   = true;
     const int err = fep_launch_gather_x(d_x, stride, c->d_touched.ptr,
                                         reinterpret_cast<float*>(c->d_step_in.ptr + sizeof(DynHead)),
                                         c->layout.ntouched, c->stream, &c->launches);
