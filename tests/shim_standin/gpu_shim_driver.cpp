@@ -109,9 +109,11 @@ int main(int argc, char** argv)
     float              eLJ = 0, eElec = 0, dvdlLJ = 0, dvdlElec = 0;
     std::vector<float> eLJF(l + 1, 0.0F), eElF(l + 1, 0.0F), dLJF(l + 1, 0.0F), dElF(l + 1, 0.0F);
 
-    /* two localities: the first and the second half of the i-entries */
-    const int cut = nri / 2;
-    auto      handOverLists = [&]() {
+    /* two localities: the first and the second half of the i-entries (argv[3] == "1": one locality with everything and
+     * an empty second list, the rank without domain decomposition / with an empty non-local list) */
+    const bool oneLocality = argc > 3 && argv[3][0] == '1';
+    const int  cut         = oneLocality ? nri : nri / 2;
+    auto       handOverLists = [&]() {
         for (int loc = 0; loc < 2; loc++)
         {
             const int        i0 = loc == 0 ? 0 : cut, i1 = loc == 0 ? cut : nri;
@@ -175,7 +177,11 @@ int main(int argc, char** argv)
         }
         for (int loc = 0; loc < 2; loc++)
         {
-            fepb200gpu::step(nb, loc, 0, &streams[loc], true, energy, virial, foreign, xq.data(), force.data(), &eLJ, &eElec, &dvdlLJ,
+            if ((loc == 0 ? cut : nri - cut) == 0)
+            {
+                continue; /* gpu_launch_kernel returns before the FEP launches of an empty list (nbnxm_cuda.cu:757-765) */
+            }
+            fepb200gpu::step(nb, loc, 0, &streams[loc], !oneLocality, energy, virial, foreign, xq.data(), force.data(), &eLJ, &eElec, &dvdlLJ,
                              &dvdlElec, foreign ? eLJF.data() : nullptr, foreign ? eElF.data() : nullptr,
                              foreign ? dLJF.data() : nullptr, foreign ? dElF.data() : nullptr, fShift.data());
         }

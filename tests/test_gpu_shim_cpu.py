@@ -40,8 +40,8 @@ def _moved(x):
     return (x.reshape(-1) + d).reshape(x.shape).astype(np.float32)
 
 
-@pytest.mark.parametrize("name", ["C2", "C4g1"])
-def test_gpu_route_shim_cadence_flags_and_routing(name, built, tmp_path):
+@pytest.mark.parametrize("name,localities", [("C2", 2), ("C4g1", 2), ("C2", 1)])
+def test_gpu_route_shim_cadence_flags_and_routing(name, localities, built, tmp_path):
     from oracle import oracle
 
     lib, drv = built
@@ -50,13 +50,14 @@ def test_gpu_route_shim_cadence_flags_and_routing(name, built, tmp_path):
     assert prob.nenergrp_pairs == 1  # the fork's GPU route has one energy group
     _write_problem(prob, 1, tmp_path / "p.bin")
     env = dict(os.environ, GMX_FEPB200="1", GMX_FEPB200_LIB=lib, FEPB200_STANDIN_TRACE="1")
-    r = subprocess.run([drv, str(tmp_path / "p.bin"), str(tmp_path / "r.bin")], capture_output=True, text=True, env=env)
+    r = subprocess.run([drv, str(tmp_path / "p.bin"), str(tmp_path / "r.bin"), str(localities)], capture_output=True, text=True,
+                       env=env)
     assert r.returncode == 0, r.stderr[-2000:]
-    # one context per locality; per context: constants once, lambdas when they change (set-up and step 2), atoms and
+    # one context per locality (none for a locality whose list is empty); per context: constants once, lambdas when they change (set-up and step 2), atoms and
     # list on the two search steps, three launches
     notes = [ln for ln in r.stderr.splitlines() if "GPU route, locality" in ln]
-    assert len(notes) == 2 and all("computed by fepb200" in ln for ln in notes)
-    last = [ln for ln in r.stderr.splitlines() if ln.startswith("standin: launch")][-2:]
+    assert len(notes) == localities and all("computed by fepb200" in ln for ln in notes)
+    last = [ln for ln in r.stderr.splitlines() if ln.startswith("standin: launch")][-localities:]
     for ln in last:
         assert ln.split()[1:] == "launch 3 set_list 2 set_atoms 2 set_params 1 set_lambdas 2 set_stream 1".split(), ln
 
