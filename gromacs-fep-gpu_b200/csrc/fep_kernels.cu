@@ -811,24 +811,24 @@ __global__ void __launch_bounds__(256) fep_gather_x_kernel(const float* __restri
 /* forces of the touched atoms [k0, k1) of the result block added into (or stored to) a
  * device-resident rvec[natoms] array; every atom occurs once, so there is nothing to synchronise */
 __global__ void __launch_bounds__(256) fep_add_forces_kernel(const float* __restrict__ res_f32, const int* __restrict__ touched,
-                                                            float* __restrict__ f, int k0, int k1, int overwrite)
+                                                            float* __restrict__ f, int k0, int k1, int mode)
 {
     const int k = k0 + blockIdx.x * 256 + threadIdx.x;
     if (k < k1)
     {
         const size_t a  = (size_t)touched[k];
         const float  fx = res_f32[3 * (size_t)k], fy = res_f32[3 * (size_t)k + 1], fz = res_f32[3 * (size_t)k + 2];
-        if (overwrite)
-        {
-            f[3 * a]     = fx;
-            f[3 * a + 1] = fy;
-            f[3 * a + 2] = fz;
-        }
-        else if (overwrite == 2) /* another stream may be adding into f at the same time (FEPB200_ATOMIC_OUTPUTS) */
+        if (mode == FEP_ADD_ATOMIC) /* another stream may be adding into f at the same time (FEPB200_ATOMIC_OUTPUTS) */
         {
             atomicAdd(f + 3 * a, fx);
             atomicAdd(f + 3 * a + 1, fy);
             atomicAdd(f + 3 * a + 2, fz);
+        }
+        else if (mode == FEP_ADD_OVERWRITE)
+        {
+            f[3 * a]     = fx;
+            f[3 * a + 1] = fy;
+            f[3 * a + 2] = fz;
         }
         else
         {
@@ -1232,12 +1232,12 @@ extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* fla
     return (int)cudaGetLastError();
 }
 
-extern "C" int fep_launch_add_forces(const float* res_f32, const int* d_touched, float* d_f, int k0, int k1, int overwrite,
+extern "C" int fep_launch_add_forces(const float* res_f32, const int* d_touched, float* d_f, int k0, int k1, int mode,
                                      cudaStream_t stream, long long* counter)
 {
     if (k1 > k0)
     {
-        fep_add_forces_kernel<<<(k1 - k0 + 255) / 256, 256, 0, stream>>>(res_f32, d_touched, d_f, k0, k1, overwrite);
+        fep_add_forces_kernel<<<(k1 - k0 + 255) / 256, 256, 0, stream>>>(res_f32, d_touched, d_f, k0, k1, mode);
         (*counter)++;
     }
     return (int)cudaGetLastError();

@@ -218,7 +218,9 @@ struct ExportTargets
 };
 int fep_launch_export_scalars(const double* r64, const float* r32_fshift, const struct ExportLayout* lay,
                               const struct ExportTargets* targets, cudaStream_t stream, long long* launch_counter);
-int fep_launch_add_forces(const float* res_f32, const int* d_touched, float* d_f, int k0, int k1, int overwrite,
+/* how fep_launch_add_forces() combines the result block with the caller's force array */
+enum { FEP_ADD_PLAIN = 0, FEP_ADD_OVERWRITE = 1, FEP_ADD_ATOMIC = 2 };
+int fep_launch_add_forces(const float* res_f32, const int* d_touched, float* d_f, int k0, int k1, int mode,
                           cudaStream_t stream, long long* launch_counter);
 #ifdef __cplusplus
 }

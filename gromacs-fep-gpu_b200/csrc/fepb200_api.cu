@@ -1878,7 +1878,8 @@ int fepb200_add_forces_device(fepb200_ctx* c, float* d_f, int flags)
     const int    k0  = c->px_on ? c->x_atom_begin : 0;
     const int    k1  = c->px_on ? c->x_atom_end : c->layout.ntouched;
     const int    err = fep_launch_add_forces(r32, c->d_touched.ptr, d_f, k0, k1,
-                                             (flags & FEPB200_CLEAR_OUTPUTS) != 0 ? 1 : ((flags & FEPB200_ATOMIC_OUTPUTS) != 0 ? 2 : 0),
+                                             (flags & FEPB200_CLEAR_OUTPUTS) != 0 ? FEP_ADD_OVERWRITE
+                                             : ((flags & FEPB200_ATOMIC_OUTPUTS) != 0 ? FEP_ADD_ATOMIC : FEP_ADD_PLAIN),
                                              c->stream, &c->launches);
     if (err != 0)
     {

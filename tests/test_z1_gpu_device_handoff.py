@@ -164,3 +164,45 @@ def test_atomic_outputs_give_the_same_sums(ctx):
     assert np.array_equal(out[0][0], out[1][0]) and (out[0][0] != 0.5).any()
     for k in sizes:
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+def test_atomic_outputs_with_a_second_stream_really_adding_into_the_same_array():
+    """The case FEPB200_ATOMIC_OUTPUTS exists for (fork: two localities, nbnxm_cuda_kernel_utils.cuh:765-805): two
+    contexts with their own streams add the forces of the same problem into ONE device array at the same time,
+    many times over, on top of a non-zero initial value.  Floating-point addition of the same two summands is
+    order-independent, so after every round the array must hold initial + 2 k f bit for bit; a lost update
+    (plain read-modify-write) or an overwrite shows as a mismatch."""
+    import torch
+
+    from fepb200.lib import FepContext
+
+    prob = make_system(scaled_spec("C2", 3.2, 1, 20, n_foreign=4))
+    a, b = FepContext(0), FepContext(0)
+    try:
+        for c in (a, b):
+            c.set_problem(prob)
+            c.upload_x(prob.x, prob.shiftvec)
+            c.launch(ALL)
+        want = a.download(ALL)["f"]
+        assert np.array_equal(want, b.download(ALL)["f"])
+        d_f = torch.full((prob.natoms, 3), 0.5, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        rounds = 50
+        for _ in range(rounds):  # queued back to back on two streams: the kernels overlap
+            a.add_forces_device(d_f.data_ptr(), P.ATOMIC_OUTPUTS)
+            b.add_forces_device(d_f.data_ptr(), P.ATOMIC_OUTPUTS)
+        a.wait()
+        b.wait()
+        expect = np.full((prob.natoms, 3), 0.5, np.float32)
+        for _ in range(rounds):
+            expect = (expect + want) + want
+        got = d_f.cpu().numpy()
+        touched = a.touched_atoms()
+        # (0.5 + f) + f in either order of the two adders is the same float; compare exactly on touched atoms
+        assert np.array_equal(got[touched], expect[touched])
+        untouched = np.ones(prob.natoms, bool)
+        untouched[touched] = False
+        assert np.all(got[untouched] == 0.5)
+    finally:
+        a.close()
+        b.close()
