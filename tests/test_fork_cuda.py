@@ -2,8 +2,7 @@
 run beside ours on the B200: they must agree with our path and with the fp64 oracle to the precision
 the fork's float kernels have, and their device time is printed next to ours (tests/fork_cuda_compare.py).
 
-Runs in a subprocess (the fork's kernels are foreign code in this process otherwise) and sorts last:
-it was written after round 1's GPU budget was spent, so its first GPU run is the round-end one."""
+Runs in a subprocess (the fork's kernels are foreign code in this process otherwise)."""
 import json
 import os
 import subprocess

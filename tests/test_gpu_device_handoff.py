@@ -1,8 +1,4 @@
-"""Device-resident force hand-off (fepb200_add_forces_device) through the C-ABI.
-
-This file sorts last on purpose: the entry point was written after round 1's GPU budget was spent, so
-these tests have not run on a B200 yet; under `pytest -x` a surprise here must not hide the parity
-tests that have."""
+"""Device-resident force hand-off (fepb200_add_forces_device) through the C-ABI."""
 import numpy as np
 import pytest
 

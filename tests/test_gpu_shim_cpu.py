@@ -6,7 +6,7 @@ with host arrays standing in for the fork's NBAtomDataGpu and the test-only stan
 behind the entry points) in place of libfepb200.so.  Checked: what the shim hands over and when (constants,
 atoms, lambdas, one list per locality; again on search steps only), flag assembly, and that the library is only
 allowed to add into the buffers the fork clears and copies back on that kind of step.  The real library behind
-the same header runs in tests/test_z5_mdrun_gpu_route.py (GPU)."""
+the same header runs in tests/test_mdrun_gpu_route.py (GPU)."""
 import os
 import subprocess
 

@@ -20,11 +20,9 @@ GMX = os.path.join(ROOT, "integration", "_gmx", "bin", "gmx")
 GMXLIBDIR = os.path.join(ROOT, "integration", "_gmx", "lib")
 TPR = os.path.join(ROOT, "tests", "golden", "mdrun_tpr")
 LIB = os.path.join(ROOT, "gromacs-fep-gpu_b200", "lib", "libfepb200.so")
-# the reference's own free-energy test systems this test has passed on a B200 with
+# the reference's own free-energy test systems
 SYSTEMS = ["coulandvdwsequential_coul", "coulandvdwsequential_vdw", "coulandvdwtogether", "transformAtoB", "vdwalone"]
-# Added after round 1's GPU budget was spent (all pass through the shim on CPU, tests/test_shim_cpu.py); their
-# first GPU run is the round-end one, so they are run by tests/test_z2_mdrun_dropin_more.py, which sorts after
-# the tests that have run on a B200 (a surprise there must not hide those under `pytest -x`).
+# run by tests/test_mdrun_dropin_more.py (all also pass through the shim on CPU, tests/test_shim_cpu.py)
 MORE_SYSTEMS = [
     # BASELINE.json's configs[0] and configs[1] as real GROMACS systems (integration/systems/make_systems.py):
     # methane decoupling in a 2.65 k-atom TIP3P box, one lambda; a 50-atom solute transformed A -> B in a
@@ -196,7 +194,7 @@ def test_mdrun_with_the_library_matches_mdrun_with_the_reference_kernel(system, 
 
 def run_both_routes_and_compare(system, tmp_path, pairs14=False):
     """pairs14: also route the perturbed 1-4 pairs through fepb200_pairs14_* (hook in listed_forces/pairs.cpp); off
-    here, tests/test_z6_mdrun_pairs14.py turns it on."""
+    here, tests/test_mdrun_pairs14.py turns it on."""
     tpr = os.path.join(TPR, system + ".tpr")
     if not os.path.exists(tpr):
         pytest.skip("no run input for " + system)

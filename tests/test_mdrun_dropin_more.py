@@ -1,9 +1,6 @@
-"""The mdrun drop-in test (tests/test_mdrun_dropin.py) on the systems and the domain-decomposed case that were
-added after round 1's GPU budget was spent: BASELINE.json's configurations as real GROMACS systems, the rest of
+"""The mdrun drop-in test (tests/test_mdrun_dropin.py) on more systems and a domain-decomposed case: BASELINE.json's configurations as real GROMACS systems, the rest of
 the reference's mdrun free-energy test systems, two thread-MPI ranks.  All pass through the shim on CPU
-(tests/test_shim_cpu.py: same hand-over, the fp64 oracle behind the entry points).
-
-Sorts after the tests that have run on a B200: the first GPU run of these is the round-end one."""
+(tests/test_shim_cpu.py: same hand-over, the fp64 oracle behind the entry points)."""
 import os
 
 import pytest

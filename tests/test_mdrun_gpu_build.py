@@ -9,9 +9,7 @@ cluster pairs on the GPU (`mdrun -nb gpu`) -- with the perturbed pairs
 (b) must reproduce (a) at the tolerance of the reference's own mdrun free-energy test; (c) is run for the
 record: the fork's "Nobonded FEP kernel" GPU time is noted beside our shim's wall time per step
 (gpurun_out/mdrun_gpu_build_timing.txt).  (c) failing or deviating is the fork's business and does not
-fail this test.
-
-Sorts last: written after round 1's GPU budget was spent, its first GPU run is the round-end one."""
+fail this test."""
 import os
 import re
 

@@ -15,10 +15,7 @@ reduction (nbnxm_gpu_data_mgmt.cpp:1117-1300, gpu_common.h:139-191) run unchange
 
 (b) must reproduce (a) at the tolerance of the reference's own mdrun free-energy test.  The fork sums its GPU
 energies in float together with the non-perturbed ones, so (b) is also compared with (c)'s deviation from (a) in
-the note written to gpurun_out/mdrun_gpu_route_timing.txt.
-
-Sorts last: the hooks were written after round 1's GPU budget was spent (they compile and link into the fork's
-CUDA build here); the first GPU run is the round-end one."""
+the note written to gpurun_out/mdrun_gpu_route_timing.txt."""
 import os
 
 import numpy as np

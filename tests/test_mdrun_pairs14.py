@@ -5,8 +5,7 @@ branch to the library and skips them; the run must reproduce the reference route
 the tolerance of the reference's own mdrun free-energy test.  Systems: the 50-atom solute of BASELINE configs[1]
 (135 perturbed 1-4 pairs) with Beutler / Gapsys soft-core and with reaction-field + sc-coul + two energy groups.
 
-The hook passes on CPU every round (tests/test_shim_cpu.py, the fp64 oracle behind the entry points).  Sorts last:
-written after round 1's GPU budget was spent, the first GPU run is the round-end one; the other mdrun drop-in
+The hook passes on CPU every round (tests/test_shim_cpu.py, the fp64 oracle behind the entry points).  The other mdrun drop-in
 tests keep this hook switched off (GMX_FEPB200_NO_PAIRS14) so that they test what they tested before."""
 import os
 
