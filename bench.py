@@ -355,9 +355,10 @@ def run_ours(args, name):
     my_pairs, my_entries, my_atoms = int(lay.nrj), int(lay.nri), int(lay.ntouched)
     if sh.reduction == "fused":
         # every rank holds the full layout, evaluates its share of the pairs and owns a range of atoms
+        # (its share is an equal number of trips, i.e. of pairs up to the padding of the trips)
         p0, p1, a0, a1 = ctx.peer_ranges()
-        my_entries = int(round(my_entries * (p1 - p0) / max(my_pairs, 1)))
-        my_pairs, my_atoms = p1 - p0, a1 - a0
+        my_entries = int(round(my_entries / world))
+        my_pairs, my_atoms = int(round(my_pairs / world)), a1 - a0
     points = problem.n_foreign + 1
     peaks = _peaks()
     sms = torch.cuda.get_device_properties(local).multi_processor_count

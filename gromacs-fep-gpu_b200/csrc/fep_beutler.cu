@@ -38,7 +38,10 @@
  *         Coulomb part needs d^(-1/6) = ex2(-lg2(d)/6).
  * MODE 2: separate Coulomb and LJ radii.
  */
-#include "fep_pair_math.cuh"
+#include <cstdlib>
+#include <cstring>
+
+#include "fep_front.cuh"
 
 #define FULL_MASK 0xffffffffu
 
@@ -53,7 +56,7 @@ struct BeutlerStep
     float lfv[2][FEP_FB_MAXC];
     int   p0, np;               /* first point of the chunk, valid points   */
     int   want_shift;           /* also store segment forces sorted by shift vector */
-    int   tile_pairs, n_tiles;  /* pair tile of one CTA for this launch     */
+    int   tile_trips, n_tiles;  /* tile of trips of one CTA for this launch */
     int   always_check;         /* a lambda outside [0,1]: no fast path     */
 };
 
@@ -262,7 +265,20 @@ struct AccLayout
     static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : (NACC > 30 ? 3 : 4);
 };
 
-template<bool EWALD, int MODE, int C, bool FORCE>
+/* sum of v over the warp, valid in every lane */
+__device__ __forceinline__ float fb_warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+    }
+    return v;
+}
+
+extern __shared__ __align__(128) unsigned char fep_dyn_smem[];
+
+template<bool EWALD, int MODE, int C, bool FORCE, bool STAGED>
 __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         fep_beutler_kernel(const __grid_constant__ KernelArgs ka, const __grid_constant__ BeutlerStep bs)
 {
@@ -271,19 +287,23 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     constexpr int NW   = FEP_FB_CTA / 32;
     __shared__ float  s_red[NW][N8 * 8];
     __shared__ double s_sum[N8 * 8];
+    __shared__ __align__(8) unsigned long long s_bar;
+    /* the 45 shift vectors are read once per trip with a data-dependent index: keep them on chip */
+    __shared__ float4 s_shift[FEP_NUM_SHIFT];
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     fep_pdl_launch_dependents(); /* the next kernel of the step may fill SM space we leave free */
 
-    /* the 45 shift vectors are read once per pair with a data-dependent index: keep them on chip */
-    __shared__ float4 s_shift[FEP_NUM_SHIFT];
+    /* this CTA's tile of trips: one round of bulk copies brings its records into shared memory */
+    const int     t0   = ka.trip_begin + blockIdx.x * bs.tile_trips;
+    const int     nt   = min(bs.tile_trips, ka.trip_end - t0);
+    const FepTile tile = fep_stage_tile<STAGED, FORCE>(ka, t0, nt, bs.tile_trips, fep_dyn_smem, &s_bar);
     if (tid < FEP_NUM_SHIFT)
     {
         s_shift[tid] = ka.dyn->shiftvec[tid];
     }
-    __syncthreads();
 
     /* Layout: [0,C) V_A, [C,2C) DV, MODE>0: [2C,3C) Cp_A, [3C,4C) DCp, then C_A DC G_A DG,
      * then (FORCE) dV/dlambda_coul, dV/dlambda_vdw of the current-lambda pass. */
@@ -293,105 +313,54 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     {
         acc[i] = 0.0f;
     }
-
     const float thr_v = ka.vdw_ewald ? __int_as_float(0x7f800000) : ka.rvdw6; /* LJ-PME tests r, below */
-    const int   base  = ka.pair_begin + blockIdx.x * bs.tile_pairs; /* a multiple of 32 */
-    const int   end   = min(base + bs.tile_pairs, ka.pair_end);
+    __syncthreads();
+    fep_tile_wait<STAGED>(&s_bar);
 
-    /* Software pipeline over the trips: while trip k is evaluated, the pair record of trip k+2 and
-     * the atom data of trip k+1 (whose record arrived during trip k-1) are in flight, so the
-     * dependent chain record -> atom data is paid once per thread, not once per trip. */
-    const int4 dummy  = make_int4(0, 0, -1, 0);
-    const int  slot0  = base + warp * 32 + lane;
-    int4       rec_n1 = slot0 < end ? __ldg(ka.pair4 + slot0) : dummy;
-    int4       rec_n2 = slot0 + FEP_FB_CTA < end ? __ldg(ka.pair4 + slot0 + FEP_FB_CTA) : dummy;
-    float3     xi_n   = fep_load_pos(ka.pos3, rec_n1.y & (FEP_MAX_TOUCHED - 1));
-    float3     xj_n   = fep_load_pos(ka.pos3, rec_n1.x & 0x7fffffff);
-    float4     pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
-    float4     pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
-    int        hb_n   = (FORCE && base + warp * 32 < end) ? __ldg(ka.warp_hbase + ((base + warp * 32) >> 5)) : 0;
-    for (int w0 = base + warp * 32; w0 < end; w0 += FEP_FB_CTA)
+    /* warp w takes the trips w, w + NW, ... of the tile; while trip k is evaluated the coordinates and
+     * owner data of trip k + NW are in flight */
+    FepFetch nx;
+    if (warp < nt)
     {
-        const int    slot   = w0 + lane;
-        const bool   active = slot < end;
-        const int4   rec    = rec_n1;
-        const float3 xi = xi_n, xj = xj_n;
-        const float4 pi = pi_n, pq = pq_n;
-        rec_n1 = rec_n2;
-        rec_n2 = slot + 2 * FEP_FB_CTA < end ? __ldg(ka.pair4 + slot + 2 * FEP_FB_CTA) : dummy;
-        xi_n   = fep_load_pos(ka.pos3, rec_n1.y & (FEP_MAX_TOUCHED - 1));
-        xj_n   = fep_load_pos(ka.pos3, rec_n1.x & 0x7fffffff);
-        pi_n   = __ldg(ka.par4 + (rec_n1.y & (FEP_MAX_TOUCHED - 1)));
-        pq_n   = __ldg(ka.par4 + (rec_n1.x & 0x7fffffff));
-        const int hbase = hb_n; /* first segment id of this warp trip, fetched during the previous trip */
-        if (FORCE && w0 + FEP_FB_CTA < end)
+        nx = fep_fetch<STAGED>(ka, tile, warp, lane);
+    }
+    for (int lt = warp; lt < nt; lt += NW)
+    {
+        const FepFetch cur = nx;
+        if (lt + NW < nt)
         {
-            hb_n = __ldg(ka.warp_hbase + ((w0 + FEP_FB_CTA) >> 5));
+            nx = fep_fetch<STAGED>(ka, tile, lt + NW, lane);
         }
-
-        /* segment structure of this trip and, for head lanes, where the segment sums go: known
-         * from the records alone, so these loads also overlap the evaluation */
-        int4     sd    = make_int4(0, 0, 0, 0);
-        unsigned hmask = 0;
-        int      after = 0;
-        bool     head  = false;
-        if (FORCE)
-        {
-            const int      entry    = rec.z;
-            const int      e_prev   = __shfl_up_sync(FULL_MASK, entry, 1);
-            const bool     boundary = (lane == 0) || (entry != e_prev);
-            const unsigned bmask    = __ballot_sync(FULL_MASK, boundary);
-            hmask                   = __ballot_sync(FULL_MASK, boundary && active);
-            const unsigned above    = bmask & ~((2u << lane) - 1u);
-            after                   = (above ? (__ffs(above) - 1) : 32) - 1 - lane;
-            head                    = boundary && active;
-            if (head)
-            {
-                const int h = hbase + __popc(hmask & ((1u << lane) - 1u));
-                sd          = __ldg(ka.seg_dst + h);
-            }
-        }
-
-        const bool   excluded = rec.x < 0;
-        const int    cj       = rec.x & 0x7fffffff;
-        const int    ci       = rec.y & (FEP_MAX_TOUCHED - 1);
-        const float4 sh       = s_shift[min((rec.y >> 24) & 63, FEP_NUM_SHIFT - 1)];
-        /* the reference shifts the i atom first (:478-480) */
-        const float dx = (sh.x + xi.x) - xj.x, dy = (sh.y + xi.y) - xj.y, dz = (sh.z + xi.z) - xj.z;
-        float       r2      = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        const bool  within  = r2 < ka.rcut_max2;
-        const bool  contrib = active && (within || excluded); /* :667 */
+        const FepSlot p = fep_slot<STAGED>(ka, tile, cur, lt, lane, s_shift);
 
         float fx = 0.0f, fy = 0.0f, fz = 0.0f, vctot = 0.0f, vvtot = 0.0f;
 
-        if (__any_sync(FULL_MASK, contrib))
+        if (__any_sync(FULL_MASK, p.contrib))
         {
-            const float4 ta = __ldg(ka.typetab + (ka.ntype * __float_as_int(pi.z) + __float_as_int(pq.z)));
-            const float4 tb = __ldg(ka.typetab + (ka.ntype * __float_as_int(pi.w) + __float_as_int(pq.w)));
-            const float  m  = contrib ? 1.0f : 0.0f;
-            const float  qq[2]  = { (ka.epsfac * pi.x) * pq.x * m, (ka.epsfac * pi.y) * pq.y * m };
+            const float4 ta = p.ta, tb = p.tb;
+            const float  m      = p.contrib ? 1.0f : 0.0f;
+            const float  qq[2]  = { p.qq[0], p.qq[1] };
             const float  c6[2]  = { ta.x, tb.x }, c12[2] = { ta.y, tb.y }, sig6[2] = { ta.z, tb.z };
             const float  c6g[2] = { ta.w * m, tb.w * m };
             const bool   hard   = (ta.y > 0.0f && tb.y > 0.0f); /* :597-628 */
             const float  a_v    = hard ? 0.0f : ka.alpha_v;
             const float  a_c    = hard ? 0.0f : ka.alpha_c;
-            const bool   self   = (ci == cj);
 
             FepPair pr;
-            r2      = fmaxf(r2, FEP_MIN_RSQ);
+            const float r2 = fmaxf(p.r2, FEP_MIN_RSQ);
             pr.r2   = r2;
             pr.rinv = fep_rsqrt(r2);
             pr.r    = r2 * pr.rinv;
             const float r4   = r2 * r2;
             const float r6   = r4 * r2;
-            const bool  incl = contrib && within && !excluded;
+            const bool  incl = p.contrib && p.within && !p.excluded;
 
             float fscal = 0.0f, dcur_c = 0.0f, dcur_v = 0.0f;
 
             /* lambda-independent correction terms, linear in qq[s] / c6grid[s] */
             {
                 float xc, fcorr, xv, fvcorr;
-                fep_corrections<EWALD, FORCE>(ka, pr, excluded, self, xc, fcorr, xv, fvcorr);
+                fep_corrections<EWALD, FORCE>(ka, pr, p.excluded, p.self, xc, fcorr, xv, fvcorr);
                 const float cA = qq[0] * xc, cB = qq[1] * xc, gA = c6g[0] * xv, gB = c6g[1] * xv;
                 if (C > 0)
                 {
@@ -465,11 +434,16 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
                     fb_force_state<EWALD, MODE>(st[1], bs, 1, r2, r6, r4, pr.rinv, thr_v, ka.rcoulomb6, ka.krf, ka.crf,
                                                 ka.sh_ewald, fscal, vctot, vvtot, dcur_c, dcur_v);
                 }
-                fx = fscal * dx;
-                fy = fscal * dy;
-                fz = fscal * dz;
-                acc[L::iCUR]     += dcur_c;
-                acc[L::iCUR + 1] += dcur_v;
+                /* lanes without a contributing pair carry zero coefficients; the select keeps a stray
+                 * inf * 0 of a padding slot out of the trip sums */
+                fscal = p.contrib ? fscal : 0.0f;
+                fx    = fscal * p.dx;
+                fy    = fscal * p.dy;
+                fz    = fscal * p.dz;
+                vctot = p.contrib ? vctot : 0.0f;
+                vvtot = p.contrib ? vvtot : 0.0f;
+                acc[L::iCUR]     += p.contrib ? dcur_c : 0.0f;
+                acc[L::iCUR + 1] += p.contrib ? dcur_v : 0.0f;
             }
 
             if (C > 0)
@@ -546,39 +520,31 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 
         if (FORCE)
         {
-            if (active)
+            if (p.active)
             {
-                /* the j atom receives -f: scattered to this pair's own slot in the atom-sorted
+                /* the partner receives -f: scattered to this pair's own slot in the atom-sorted
                  * buffer (unique destination, no atomics; skipped pairs write their zero) */
-                ka.fsorted[rec.w] = make_float4(-fx, -fy, -fz, 0.0f);
+                const int d = STAGED ? tile.dst[32 * lt + lane] : __ldg(tile.dst + 32 * lt + lane);
+                ka.fsorted[d] = make_float4(-fx, -fy, -fz, 0.0f);
             }
-            /* segmented sum over the lanes of one i-entry: i force and Vc/Vv of the segment */
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
+            /* the owner receives the sum over the trip; the trip's Vc/Vv go to its energy-group pair */
+            fx    = fb_warp_sum(fx);
+            fy    = fb_warp_sum(fy);
+            fz    = fb_warp_sum(fz);
+            vctot = fb_warp_sum(vctot);
+            vvtot = fb_warp_sum(vvtot);
+            if (lane == 0)
             {
-                const float ox = __shfl_down_sync(FULL_MASK, fx, o);
-                const float oy = __shfl_down_sync(FULL_MASK, fy, o);
-                const float oz = __shfl_down_sync(FULL_MASK, fz, o);
-                const float oc = __shfl_down_sync(FULL_MASK, vctot, o);
-                const float ov = __shfl_down_sync(FULL_MASK, vvtot, o);
-                if (o <= after)
-                {
-                    fx += ox;
-                    fy += oy;
-                    fz += oz;
-                    vctot += oc;
-                    vvtot += ov;
-                }
-            }
-            if (head)
-            {
-                const float4 fi  = make_float4(fx, fy, fz, 0.0f);
-                ka.fsorted[sd.x] = fi;
+                const int4 td    = STAGED ? tile.trip4[lt] : __ldg(tile.trip4 + lt);
+                ka.fsorted[td.y] = make_float4(fx, fy, fz, 0.0f);
                 if (bs.want_shift)
                 {
-                    ka.fshift_sorted[sd.y] = fi;
+                    /* nb_free_energy.cpp:1153-1164 adds the i atom's force to the entry's shift vector; for
+                     * a flipped trip the owner was the j atom, whose force is minus that */
+                    const float sg = (td.x & FEP_TRIP_FLIPPED) ? -1.0f : 1.0f;
+                    ka.fshift_sorted[td.z] = make_float4(sg * fx, sg * fy, sg * fz, 0.0f);
                 }
-                ka.ev2[sd.z] = make_float2(vctot, vvtot);
+                ka.ev2[td.w] = make_float2(vctot, vvtot);
             }
         }
     }
@@ -636,15 +602,35 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 
 /* ------------------------------------------------------------------------------------------- */
 /* occ != nullptr: only report how many CTAs of this instantiation fit on one SM */
+/* FEPB200_STAGE=direct: the A/B variant that reads the tile's records from global memory in the loop
+ * instead of staging them through shared memory with bulk copies (profiles/) */
+static bool fb_staged()
+{
+    static const bool staged = [] {
+        const char* e = std::getenv("FEPB200_STAGE");
+        return !(e && std::strcmp(e, "direct") == 0);
+    }();
+    return staged;
+}
+
 template<bool EWALD, int MODE, int C, bool FORCE>
 static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream, int* occ, bool chained)
 {
     if (occ)
     {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE>, FEP_FB_CTA, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, FEP_FB_CTA, 0);
         return;
     }
-    fep_launch_kernel(fep_beutler_kernel<EWALD, MODE, C, FORCE>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), stream, chained, ka, bs);
+    if (fb_staged())
+    {
+        fep_launch_kernel_smem(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, dim3(bs.n_tiles), dim3(FEP_FB_CTA),
+                               fep_tile_bytes(bs.tile_trips, FORCE), stream, chained, ka, bs);
+    }
+    else
+    {
+        fep_launch_kernel_smem(fep_beutler_kernel<EWALD, MODE, C, FORCE, false>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), 0,
+                               stream, chained, ka, bs);
+    }
 }
 
 template<bool EWALD, int MODE, bool FORCE>
@@ -760,7 +746,7 @@ extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mod
             }
         }
     }
-    bs.tile_pairs = do_foreign ? ka.tile_pairs : ka.pass_tile_pairs;
+    bs.tile_trips = do_foreign ? ka.tile_trips : ka.pass_tile_trips;
     bs.n_tiles    = do_foreign ? ka.n_tiles : ka.pass_n_tiles;
     bool first    = true;
     for (int p0 = 0; p0 < np || first; p0 += (c > 0 ? c : 1))

@@ -23,7 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "fep_pair_math.cuh"
+#include "fep_front.cuh"
 
 #define FULL_MASK 0xffffffffu
 
@@ -66,18 +66,19 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
     }
     __syncthreads();
 
-    const int  slot  = ka.pair_begin + blockIdx.x * FEP_CTA + tid; /* pair_begin is a multiple of 32 */
-    const bool valid = slot < ka.pair_end;
+    /* one warp per trip */
+    const int  t     = ka.trip_begin + blockIdx.x * (FEP_CTA / 32) + warp;
+    const bool valid = t < ka.trip_end;
 
     float fx = 0.0f, fy = 0.0f, fz = 0.0f, vc = 0.0f, vv = 0.0f, dc = 0.0f, dv = 0.0f;
-    int   entry = -1;
 
     if (valid)
     {
-        FepPair pr;
-        float   dx, dy, dz;
-        bool    excluded, self;
-        if (fep_load_pair<SC>(ka, slot, pr, dx, dy, dz, excluded, self, entry))
+        const FepTile  tile = fep_global_tile(ka);
+        const FepFetch ft   = fep_fetch<false>(ka, tile, t, lane);
+        const FepSlot  p    = fep_slot<false>(ka, tile, ft, t, lane, ka.dyn->shiftvec);
+        FepPair        pr;
+        if (fep_fill_pair<SC>(ka, p, pr))
         {
             float fscal = 0.0f;
             if (pr.included_within)
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
                 fep_included_terms<SC, EWALD, FORCE>(ka, s_lp, pr, vc, vv, fscal, dc, dv);
             }
             float xc, fc, xv, fv;
-            fep_corrections<EWALD, FORCE>(ka, pr, excluded, self, xc, fc, xv, fv);
+            fep_corrections<EWALD, FORCE>(ka, pr, p.excluded, p.self, xc, fc, xv, fv);
             const float cA = pr.qq[0] * xc, cB = pr.qq[1] * xc;
             const float gA = pr.c6g[0] * xv, gB = pr.c6g[1] * xv;
             vc += s_lp.lfac_c[0] * cA + s_lp.lfac_c[1] * cB;
@@ -96,16 +97,16 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
             {
                 fscal += (s_lp.lfac_c[0] * pr.qq[0] + s_lp.lfac_c[1] * pr.qq[1]) * fc;
                 fscal += (s_lp.lfac_v[0] * pr.c6g[0] + s_lp.lfac_v[1] * pr.c6g[1]) * fv;
-                fx = fscal * dx;
-                fy = fscal * dy;
-                fz = fscal * dz;
+                fx = fscal * p.dx;
+                fy = fscal * p.dy;
+                fz = fscal * p.dz;
             }
         }
-        if (FORCE)
+        if (FORCE && p.active)
         {
-            /* the j atom receives -t: scattered to this pair's own slot in the atom-sorted buffer
+            /* the partner receives -f: scattered to this pair's own slot in the atom-sorted buffer
              * (unique destination, no atomics; skipped pairs write their zero) */
-            ka.fsorted[__ldg(ka.pair4 + slot).w] = make_float4(-fx, -fy, -fz, 0.0f);
+            ka.fsorted[__ldg(ka.dst + 32 * (size_t)t + lane)] = make_float4(-fx, -fy, -fz, 0.0f);
         }
     }
 
@@ -119,46 +120,26 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         }
     }
 
-    /* segmented sum over the lanes of one i-entry: i force and Vc/Vv of the segment */
-    const int      e_prev   = __shfl_up_sync(FULL_MASK, entry, 1);
-    const bool     boundary = (lane == 0) || (entry != e_prev);
-    const unsigned bmask    = __ballot_sync(FULL_MASK, boundary);
-    const unsigned hmask    = __ballot_sync(FULL_MASK, boundary && valid);
-    const unsigned above    = bmask & ~((2u << lane) - 1u);
-    const int      seg_last = (above ? (__ffs(above) - 1) : 32) - 1; /* last lane of my segment */
-    const int      after    = seg_last - lane;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
+    /* the owner receives the sum over the trip; the trip's Vc/Vv go to its energy-group pair */
+    fx = warp_sum(fx);
+    fy = warp_sum(fy);
+    fz = warp_sum(fz);
+    vc = warp_sum(vc);
+    vv = warp_sum(vv);
+    if (valid && lane == 0)
     {
-        const float ox = __shfl_down_sync(FULL_MASK, fx, o);
-        const float oy = __shfl_down_sync(FULL_MASK, fy, o);
-        const float oz = __shfl_down_sync(FULL_MASK, fz, o);
-        const float oc = __shfl_down_sync(FULL_MASK, vc, o);
-        const float ov = __shfl_down_sync(FULL_MASK, vv, o);
-        if (o <= after)
-        {
-            fx += ox;
-            fy += oy;
-            fz += oz;
-            vc += oc;
-            vv += ov;
-        }
-    }
-    if (boundary && valid)
-    {
-        const int gw = (ka.pair_begin >> 5) + blockIdx.x * (FEP_CTA / 32) + warp;
-        const int h  = __ldg(ka.warp_hbase + gw) + __popc(hmask & ((1u << lane) - 1u));
-        const int4 sd = __ldg(ka.seg_dst + h);
+        const int4 td = __ldg(ka.trip4 + t);
         if (FORCE)
         {
-            const float4 fi = make_float4(fx, fy, fz, 0.0f);
-            ka.fsorted[sd.x] = fi;
+            ka.fsorted[td.y] = make_float4(fx, fy, fz, 0.0f);
             if (want_shift)
             {
-                ka.fshift_sorted[sd.y] = fi;
+                /* a flipped trip's owner was the reference's j atom: its force is minus the i force (:1153-1164) */
+                const float sg         = (td.x & FEP_TRIP_FLIPPED) ? -1.0f : 1.0f;
+                ka.fshift_sorted[td.z] = make_float4(sg * fx, sg * fy, sg * fz, 0.0f);
             }
         }
-        ka.ev2[sd.z] = make_float2(vc, vv);
+        ka.ev2[td.w] = make_float2(vc, vv);
     }
 
     __syncthreads();
@@ -240,20 +221,21 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
         acc_e[p] = acc_c[p] = acc_v[p] = 0.0f;
     }
 
-    const int base = ka.pair_begin + blockIdx.x * ka.tile_pairs;
-    const int end  = min(base + ka.tile_pairs, ka.pair_end);
-    for (int slot = base + tid; slot < end; slot += FEP_CTA)
+    /* a CTA takes a tile of trips, one warp per trip and round */
+    const FepTile tile = fep_global_tile(ka);
+    const int     t0   = ka.trip_begin + blockIdx.x * ka.tile_trips;
+    const int     t1   = min(t0 + ka.tile_trips, ka.trip_end);
+    for (int t = t0 + warp; t < t1; t += FEP_CTA / 32)
     {
-        FepPair pr;
-        float   dx, dy, dz;
-        bool    excluded, self;
-        int     entry;
-        if (!fep_load_pair<SC>(ka, slot, pr, dx, dy, dz, excluded, self, entry))
+        const FepFetch ft = fep_fetch<false>(ka, tile, t, lane);
+        const FepSlot  sl = fep_slot<false>(ka, tile, ft, t, lane, ka.dyn->shiftvec);
+        FepPair        pr;
+        if (!fep_fill_pair<SC>(ka, sl, pr))
         {
             continue;
         }
         float xc, fc, xv, fv;
-        fep_corrections<EWALD, false>(ka, pr, excluded, self, xc, fc, xv, fv);
+        fep_corrections<EWALD, false>(ka, pr, sl.excluded, sl.self, xc, fc, xv, fv);
         const float cA = pr.qq[0] * xc, cB = pr.qq[1] * xc;
         const float gA = pr.c6g[0] * xv, gB = pr.c6g[1] * xv;
         const float dcorr_c = cB - cA, dcorr_v = gB - gA;
@@ -758,31 +740,44 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         }
         __threadfence();
     }
-    if (sf.shift)
+    /* one warp per output value: the lanes stride over the jobs of the key, fixed butterfly at the end
+     * (a key can have dozens of jobs -- the central shift vector, a single energy-group pair -- and a
+     * serial walk over them was the tail of the whole step) */
     {
-        for (int o = tid; o < 3 * FEP_NUM_SHIFT; o += FEP_EPI_CTA)
+        const int lane = tid & 31, wrp = tid >> 5;
+        const int n_sh = sf.shift ? 3 * FEP_NUM_SHIFT : 0;
+        const int n_en = sf.energy ? 2 * ka.n_gid : 0;
+        for (int o = wrp; o < n_sh + n_en; o += FEP_EPI_CTA / 32)
         {
-            const int s = o / 3, d = o - 3 * s;
-            double    a = 0.0;
-            for (int j = ka.key_job_ptr[s]; j < ka.key_job_ptr[s + 1]; j++)
+            int key, comp;
+            if (o < n_sh)
             {
-                a += __ldcg(ka.job_part + 4 * (size_t)j + d);
+                key  = o / 3;
+                comp = o - 3 * key;
             }
-            ka.res_f32[3 * (size_t)ka.n_touched + o] = (float)a;
-        }
-    }
-    if (sf.energy)
-    {
-        for (int g = tid; g < ka.n_gid; g += FEP_EPI_CTA)
-        {
-            double a = 0.0, c = 0.0;
-            for (int j = ka.key_job_ptr[FEP_NUM_SHIFT + g]; j < ka.key_job_ptr[FEP_NUM_SHIFT + g + 1]; j++)
+            else
             {
-                a += __ldcg(ka.job_part + 4 * (size_t)j);
-                c += __ldcg(ka.job_part + 4 * (size_t)j + 1);
+                const int e = o - n_sh;
+                comp        = e >= ka.n_gid ? 1 : 0;
+                key         = FEP_NUM_SHIFT + (e - comp * ka.n_gid);
             }
-            ka.res_f64[g]          = a;
-            ka.res_f64[off_vv + g] = c;
+            double a = 0.0;
+            for (int j = ka.key_job_ptr[key] + lane; j < ka.key_job_ptr[key + 1]; j += 32)
+            {
+                a += __ldcg(ka.job_part + 4 * (size_t)j + comp);
+            }
+            a = warp_sum_d(a);
+            if (lane == 0)
+            {
+                if (o < n_sh)
+                {
+                    ka.res_f32[3 * (size_t)ka.n_touched + o] = (float)a;
+                }
+                else
+                {
+                    ka.res_f64[(comp ? off_vv : 0) + (key - FEP_NUM_SHIFT)] = a;
+                }
+            }
         }
     }
     if (tid == 0 && lay.job_blocks != 0)

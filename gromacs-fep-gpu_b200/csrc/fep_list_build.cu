@@ -2,20 +2,22 @@
  * fep_list_build.cu -- builds the device layout of fep_types.h from the raw FEP t_nblist ON THE
  * GPU (search-step work).  Replaces, for this library, what the reference fork does on the host in
  * gpu_init_feppairlist() (nbnxm/nbnxm_gpu_data_mgmt.cpp:761-871: index remap + five H2D copies)
- * after combine_fep_lists() (nbnxm/pairlist.cpp:2867-2961), plus the preparation of the
- * atomic-free scatter (sorted destinations) that the fork does not have.
+ * after combine_fep_lists() (nbnxm/pairlist.cpp:2867-2961), plus the regrouping into trips and the
+ * preparation of the atomic-free scatter (sorted destinations) that the fork does not have.
  *
  * The raw arrays are copied to the device once; everything else is kernels, prefix sums and stable
  * radix sorts (CUB):
- *   marks + scan           -> compact numbering of the touched atoms (ascending atom index)
- *   one thread per pair    -> 16-byte pair records (entry found by binary search in jindex),
- *                             segment-head flags
- *   scan of the head flags -> segment numbering, warp_hbase
- *   stable sort of {pairs by j atom, then segments by i atom} -> every force contribution's slot
- *                             in the atom-sorted buffer, atom_ptr
- *   stable sorts of the segments by shift index and by energy-group pair -> reduction ranges
- * All orders are the ones the host path of fepb200_set_list() produces (stable sorts keep the
- * slot / segment order inside one key), so both paths give bit-identical device structures.
+ *   marks + scan            -> compact numbering of the touched atoms (ascending atom index)
+ *   one thread per pair     -> both ends in compact numbering (entry found by binary search in
+ *                              jindex), number of pairs every atom takes part in
+ *   one thread per pair     -> owner = the end with more pairs; key = (owner, gid, shift, flipped)
+ *   stable sort by key      -> groups; positions inside a group -> trips of <= 32 pairs -> slots
+ *   one thread per pair     -> per-slot records (partner, pre-gathered partner parameters)
+ *   stable sort of {pairs by partner atom, then trips by owner atom} -> every force contribution's
+ *                              slot in the atom-sorted buffer, atom_ptr
+ *   stable sorts of the trips by shift index and by energy-group pair -> reduction ranges
+ * Stable sorts make the layout (and with it the order of every floating-point sum) a function of
+ * the list alone.
  */
 #include <cub/cub.cuh>
 
@@ -57,18 +59,14 @@ __global__ void k_entries(const int* __restrict__ iinr, const int* __restrict__ 
     }
 }
 
-/* one thread per pair slot of this rank's shard */
-__global__ void k_pairs(const int* __restrict__ jindex, const int* __restrict__ jjnr, const int* __restrict__ excl,
-                        const int* __restrict__ cscan, const int4* __restrict__ ent4, int e0, int E, int j0, int P,
-                        int4* __restrict__ pair4, int* __restrict__ keys, int* __restrict__ head)
+/* one thread per pair of this rank's shard: its two ends, its entry, and the pair counts of both ends */
+__global__ void k_pair_ends(const int* __restrict__ jindex, const int* __restrict__ jjnr, const int* __restrict__ cscan,
+                            const int4* __restrict__ ent4, int e0, int E, int j0, int P, int* __restrict__ pj,
+                            int* __restrict__ pn, int* __restrict__ deg)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P)
     {
-        if (s == P)
-        {
-            head[P] = 0; /* terminator of the exclusive scan */
-        }
         return;
     }
     const int k = j0 + s;
@@ -86,33 +84,114 @@ __global__ void k_pairs(const int* __restrict__ jindex, const int* __restrict__ 
             hi = mid;
         }
     }
-    const int  n        = lo;
-    const int4 en       = ent4[n];
-    const int  cj       = cscan[jjnr[k]];
-    const bool excluded = excl != nullptr && excl[k] == 0;
-    pair4[s]            = make_int4(cj | (excluded ? (int)0x80000000u : 0), en.x | (en.y << 24), n, 0);
-    keys[s]             = cj;
-    head[s]             = ((s & 31) == 0 || k == jindex[e0 + n]) ? 1 : 0;
+    const int ci = ent4[lo].x;
+    const int cj = cscan[jjnr[k]];
+    pj[s]        = cj;
+    pn[s]        = lo;
+    atomicAdd(deg + ci, 1);
+    atomicAdd(deg + cj, 1);
 }
 
-/* one thread per pair slot: the heads fill the per-segment arrays */
-__global__ void k_segments(const int4* __restrict__ pair4, const int4* __restrict__ ent4, const int* __restrict__ head,
-                           const int* __restrict__ hscan, int P, int* __restrict__ keys_seg /* = keys + P */,
-                           int* __restrict__ seg_shift, int* __restrict__ seg_gid, int* __restrict__ warp_hbase)
+/* key = (((owner * G + gid) * 64 + shift) * 2 + flipped); the owner is the end that takes part in more
+ * pairs (ties: the reference's i atom) */
+template<typename K>
+__global__ void k_pair_keys(const int* __restrict__ pj, const int* __restrict__ pn, const int4* __restrict__ ent4,
+                            const int* __restrict__ deg, int G, int P, K* __restrict__ keys, int* __restrict__ vals)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P || !head[s])
+    if (s >= P)
     {
         return;
     }
-    const int  h  = hscan[s];
-    const int4 en = ent4[pair4[s].z];
-    keys_seg[h]   = en.x;
-    seg_shift[h]  = en.y;
-    seg_gid[h]    = en.z;
-    if ((s & 31) == 0)
+    const int4 en   = ent4[pn[s]];
+    const int  ci   = en.x, cj = pj[s];
+    const bool flip = deg[cj] > deg[ci];
+    const K    og   = (K)(flip ? cj : ci) * (K)G + (K)en.z;
+    keys[s]         = (og * 64 + (K)en.y) * 2 + (flip ? 1 : 0);
+    vals[s]         = s;
+}
+
+template<typename K>
+__global__ void k_group_marks(const K* __restrict__ keys_sorted, int P, int* __restrict__ gmark)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < P)
     {
-        warp_hbase[s >> 5] = h;
+        gmark[r] = (r == 0 || keys_sorted[r] != keys_sorted[r - 1]) ? r : 0;
+    }
+}
+
+/* a trip starts every 32 pairs of a group */
+__global__ void k_trip_heads(const int* __restrict__ gstart, int P, int* __restrict__ th)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < P)
+    {
+        th[r] = (((r - gstart[r]) & 31) == 0) ? 1 : 0;
+    }
+    else if (r == P)
+    {
+        th[P] = 0; /* terminator of the exclusive scan: tsc[P] = number of trips */
+    }
+}
+
+__global__ void k_clear_slots(int n_slots, int* __restrict__ cjx, int* __restrict__ dst, float2* __restrict__ qj,
+                              int* __restrict__ tj, int* __restrict__ orig)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots)
+    {
+        cjx[i]  = FEP_SLOT_PADDING;
+        dst[i]  = 0;
+        qj[i]   = make_float2(0.0f, 0.0f);
+        tj[i]   = 0;
+        orig[i] = -1;
+    }
+}
+
+/* r-th pair of the group-sorted order -> its slot; the first pair of a trip also fills the trip's record */
+template<typename K>
+__global__ void k_fill_slots(const K* __restrict__ keys_sorted, const int* __restrict__ vals_sorted,
+                             const int* __restrict__ gstart, const int* __restrict__ th, const int* __restrict__ tsc,
+                             const int* __restrict__ pj, const int* __restrict__ pn, const int4* __restrict__ ent4,
+                             const int* __restrict__ excl, int j0, const float4* __restrict__ par4, int G, int P, int NT,
+                             int* __restrict__ cjx, float2* __restrict__ qj, int* __restrict__ tj, int* __restrict__ orig,
+                             int4* __restrict__ trip4, int* __restrict__ tshift, int* __restrict__ tgid,
+                             int* __restrict__ akeys, int* __restrict__ avals)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P)
+    {
+        return;
+    }
+    const K    key    = keys_sorted[r];
+    const int  s      = vals_sorted[r];
+    const int  flip   = (int)(key & 1);
+    const int  sh     = (int)((key >> 1) & 63);
+    const K    og     = key >> 7;
+    const int  owner  = (int)(og / (K)G);
+    const int  g      = (int)(og - (K)owner * (K)G);
+    const int  ci     = ent4[pn[s]].x, cj = pj[s];
+    const int  other  = flip ? ci : cj;
+    const int  t      = tsc[r] + th[r] - 1;
+    const int  lane   = (r - gstart[r]) & 31;
+    const int  slot   = 32 * t + lane;
+    const bool excluded = excl != nullptr && excl[j0 + s] == 0;
+    const float4 p    = par4[other];
+    cjx[slot]         = other | (excluded ? (int)0x80000000u : 0);
+    qj[slot]          = make_float2(p.x, p.y);
+    tj[slot]          = __float_as_int(p.z) | (__float_as_int(p.w) << 16);
+    orig[slot]        = s;
+    akeys[r]          = other;
+    avals[r]          = slot;
+    if (lane == 0)
+    {
+        const int sh_eff = flip ? (FEP_NUM_SHIFT - 1 - sh) : sh;
+        trip4[t]         = make_int4(owner | (sh_eff << 24) | (flip ? FEP_TRIP_FLIPPED : 0), 0, 0, 0);
+        tshift[t]        = sh;
+        tgid[t]          = g;
+        akeys[P + t]     = owner;
+        avals[P + t]     = 32 * NT + t;
     }
 }
 
@@ -127,8 +206,8 @@ __global__ void k_iota(int* __restrict__ v, int n)
 
 /* r-th element of the atom-sorted order: tell the contribution its slot, and fill atom_ptr at the
  * boundaries between different atoms (atoms without contributions get empty ranges) */
-__global__ void k_atom_slots(const int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, int n, int P, int nT,
-                             int4* __restrict__ pair4, int4* __restrict__ seg_dst, int* __restrict__ atom_ptr)
+__global__ void k_atom_slots(const int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, int n, int n_slots,
+                             int nT, int* __restrict__ dst, int4* __restrict__ trip4, int* __restrict__ atom_ptr)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n)
@@ -136,13 +215,13 @@ __global__ void k_atom_slots(const int* __restrict__ keys_sorted, const int* __r
         return;
     }
     const int idx = vals_sorted[r];
-    if (idx < P)
+    if (idx < n_slots)
     {
-        pair4[idx].w = r;
+        dst[idx] = r;
     }
     else
     {
-        seg_dst[idx - P].x = r;
+        trip4[idx - n_slots].y = r;
     }
     const int cur  = keys_sorted[r];
     const int prev = r > 0 ? keys_sorted[r - 1] : -1;
@@ -159,24 +238,24 @@ __global__ void k_atom_slots(const int* __restrict__ keys_sorted, const int* __r
     }
 }
 
-/* r-th element of the segments sorted by `which` key (1: shift index -> seg_dst.y, 2: gid -> .z);
+/* r-th element of the trips sorted by `which` key (1: shift index -> trip4.z, 2: gid -> .w);
  * key_ptr[k] = first rank of key k, key_ptr[nkeys] = n */
-__global__ void k_seg_slots(const int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, int n, int nkeys,
-                            int which, int4* __restrict__ seg_dst, int* __restrict__ key_ptr)
+__global__ void k_trip_slots(const int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, int n, int nkeys,
+                             int which, int4* __restrict__ trip4, int* __restrict__ key_ptr)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n)
     {
         return;
     }
-    const int h = vals_sorted[r];
+    const int t = vals_sorted[r];
     if (which == 1)
     {
-        seg_dst[h].y = r;
+        trip4[t].z = r;
     }
     else
     {
-        seg_dst[h].z = r;
+        trip4[t].w = r;
     }
     const int cur  = keys_sorted[r];
     const int prev = r > 0 ? keys_sorted[r - 1] : -1;
@@ -193,26 +272,34 @@ __global__ void k_seg_slots(const int* __restrict__ keys_sorted, const int* __re
     }
 }
 
-int bits_for(int n)
+int bits_for(unsigned long long n)
 {
     int b = 1;
-    while ((1LL << b) < n && b < 31)
+    while (b < 63 && (1ULL << b) < n)
     {
         b++;
     }
     return b;
 }
 
+struct MaxOp
+{
+    __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; }
+};
+
 } // namespace
 
 extern "C" size_t fep_list_build_temp_bytes(int natoms, long long n_sort_max)
 {
-    size_t a = 0, b = 0, c = 0;
+    size_t a = 0, b = 0, c = 0, d = 0, e = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, a, (const int*)nullptr, (int*)nullptr, natoms + 1);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, (int)n_sort_max + 1);
     cub::DeviceRadixSort::SortPairs(nullptr, c, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr,
                                     (int)n_sort_max, 0, 31);
-    return std::max(a, std::max(b, c)) + 256;
+    cub::DeviceRadixSort::SortPairs(nullptr, d, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int*)nullptr, (int*)nullptr, (int)n_sort_max, 0, 63);
+    cub::DeviceScan::InclusiveScan(nullptr, e, (const int*)nullptr, (int*)nullptr, MaxOp(), (int)n_sort_max + 1);
+    return std::max(std::max(a, e), std::max(b, std::max(c, d))) + 256;
 }
 
 /* Phase 1: compact numbering.  mark/cscan: int[natoms+1]; returns after queuing (nT = cscan[natoms]). */
@@ -236,106 +323,137 @@ extern "C" int fep_list_build_touched(const int* d_iinr, int nri_total, const in
     return (int)cudaGetLastError();
 }
 
-/* Phase 2: pair records, head flags and their scan (H = hscan[P]). */
-extern "C" int fep_list_build_pairs(const int* d_iinr, const int* d_gid, const int* d_shift, const int* d_jindex,
-                                    const int* d_jjnr, const int* d_excl, const int* d_cscan, int e0, int E, int j0,
-                                    int P, int4* d_ent4, int4* d_pair4, int* d_keys, int* d_head, int* d_hscan,
-                                    void* d_tmp, size_t tmp_bytes, cudaStream_t stream, long long* counter)
+template<typename K>
+static void groups_typed(const ListBuild& b, int P, int G, int end_bit, cudaStream_t stream)
 {
+    K*     keys      = reinterpret_cast<K*>(b.keys);
+    K*     keys_out  = reinterpret_cast<K*>(b.keys_out);
+    size_t tmp_bytes = b.tmp_bytes;
+    k_pair_keys<K><<<(P + 255) / 256, 256, 0, stream>>>(b.pj, b.pn, b.ent4, b.deg, G, P, keys, b.vals);
+    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, keys, keys_out, b.vals, b.vals_out, P, 0, end_bit, stream);
+    k_group_marks<K><<<(P + 255) / 256, 256, 0, stream>>>(keys_out, P, b.gmark);
+}
+
+/* Phase 2: ends + pair counts, keys, the group sort and the trip numbering (NT = tsc[P]).
+ * wide_keys: 64-bit sort keys (needed when nT * G * 128 does not fit 32 bits). */
+extern "C" int fep_list_build_groups(const ListBuild* bp, const int* d_iinr, const int* d_gid, const int* d_shift,
+                                     const int* d_jindex, const int* d_jjnr, const int* d_cscan, int e0, int E, int j0,
+                                     int P, int nT, int G, int wide_keys, cudaStream_t stream, long long* counter)
+{
+    const ListBuild& b         = *bp;
+    size_t           tmp_bytes = b.tmp_bytes;
     if (E > 0)
     {
-        k_entries<<<(E + 255) / 256, 256, 0, stream>>>(d_iinr, d_gid, d_shift, d_cscan, e0, E, d_ent4);
+        k_entries<<<(E + 255) / 256, 256, 0, stream>>>(d_iinr, d_gid, d_shift, d_cscan, e0, E, b.ent4);
         (*counter)++;
     }
-    k_pairs<<<(P + 1 + 255) / 256, 256, 0, stream>>>(d_jindex, d_jjnr, d_excl, d_cscan, d_ent4, e0, E, j0, P, d_pair4,
-                                                      d_keys, d_head);
-    (*counter)++;
-    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_head, d_hscan, P + 1, stream);
+    if (P <= 0)
+    {
+        cudaMemsetAsync(b.tsc, 0, sizeof(int), stream);
+        return (int)cudaGetLastError();
+    }
+    cudaMemsetAsync(b.deg, 0, sizeof(int) * ((size_t)nT + 1), stream);
+    k_pair_ends<<<(P + 255) / 256, 256, 0, stream>>>(d_jindex, d_jjnr, d_cscan, b.ent4, e0, E, j0, P, b.pj, b.pn, b.deg);
+    const int end_bit = bits_for((unsigned long long)nT * (unsigned long long)G * 128ULL);
+    if (wide_keys)
+    {
+        groups_typed<unsigned long long>(b, P, G, end_bit, stream);
+    }
+    else
+    {
+        groups_typed<unsigned int>(b, P, G, end_bit, stream);
+    }
+    cub::DeviceScan::InclusiveScan(b.tmp, tmp_bytes, b.gmark, b.gstart, MaxOp(), P, stream);
+    k_trip_heads<<<(P + 1 + 255) / 256, 256, 0, stream>>>(b.gstart, P, b.th);
+    cub::DeviceScan::ExclusiveSum(b.tmp, tmp_bytes, b.th, b.tsc, P + 1, stream);
+    (*counter) += 4;
     return (int)cudaGetLastError();
 }
 
-/* Phase 3 (H known): segments, the three stable sorts and the slot assignments.
- * keys: int[P+H] (first P filled by phase 2); scratch a/b: int[P+H] each for values, keys_out int[P+H];
- * seg_shift/seg_gid: int[H]; key_ptr: int[46 + G + 1] (shift_ptr then gid_ptr). */
-extern "C" int fep_list_build_slots(const int4* d_ent4, int4* d_pair4, const int* d_head, const int* d_hscan, int P, int H,
-                                    int nT, int ngrp, int* d_keys, int* d_keys_out, int* d_vals, int* d_vals_out,
-                                    int* d_seg_shift, int* d_seg_gid, int* d_warp_hbase, int4* d_seg_dst, int* d_atom_ptr,
-                                    int* d_key_ptr, void* d_tmp, size_t tmp_bytes, cudaStream_t stream,
-                                    long long* counter)
+/* Phase 3 (NT known): slot records, the atom sort and the two trip sorts.
+ * key_ptr: int[46 + G + 1] (shift_ptr then gid_ptr). */
+extern "C" int fep_list_build_slots(const ListBuild* bp, const int* d_excl, int j0, const float4* d_par4, int P, int NT,
+                                    int nT, int G, int wide_keys, cudaStream_t stream, long long* counter)
 {
-    const int n = P + H;
-    if (P > 0)
+    const ListBuild& b         = *bp;
+    size_t           tmp_bytes = b.tmp_bytes;
+    const int        n_slots   = 32 * NT;
+    const int        n       = P + NT;
+    cudaMemsetAsync(b.atom_ptr, 0, sizeof(int) * ((size_t)nT + 1), stream);
+    cudaMemsetAsync(b.key_ptr, 0, sizeof(int) * (FEP_NUM_SHIFT + 1 + G + 1), stream);
+    if (P <= 0)
     {
-        k_segments<<<(P + 255) / 256, 256, 0, stream>>>(d_pair4, d_ent4, d_head, d_hscan, P, d_keys + P, d_seg_shift,
-                                                       d_seg_gid, d_warp_hbase);
-        (*counter)++;
+        return (int)cudaGetLastError();
     }
-    cudaMemsetAsync(d_atom_ptr, 0, sizeof(int) * ((size_t)nT + 1), stream);
-    cudaMemsetAsync(d_key_ptr, 0, sizeof(int) * (FEP_NUM_SHIFT + 1 + ngrp + 1), stream);
-    if (n > 0)
+    k_clear_slots<<<(n_slots + 255) / 256, 256, 0, stream>>>(n_slots, b.cjx, b.dst, b.qj, b.tj, b.orig);
+    if (wide_keys)
     {
-        k_iota<<<(n + 255) / 256, 256, 0, stream>>>(d_vals, n);
-        cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_out, d_vals, d_vals_out, n, 0, bits_for(nT),
-                                        stream);
-        k_atom_slots<<<(n + 255) / 256, 256, 0, stream>>>(d_keys_out, d_vals_out, n, P, nT, d_pair4, d_seg_dst,
-                                                         d_atom_ptr);
-        (*counter) += 2;
+        k_fill_slots<unsigned long long><<<(P + 255) / 256, 256, 0, stream>>>(
+                reinterpret_cast<const unsigned long long*>(b.keys_out), b.vals_out, b.gstart, b.th, b.tsc, b.pj, b.pn, b.ent4,
+                d_excl, j0, d_par4, G, P, NT, b.cjx, b.qj, b.tj, b.orig, b.trip4, b.tshift, b.tgid, b.akeys, b.avals);
     }
-    if (H > 0)
+    else
     {
-        k_iota<<<(H + 255) / 256, 256, 0, stream>>>(d_vals, H);
-        cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_seg_shift, d_keys_out, d_vals, d_vals_out, H, 0, 6, stream);
-        k_seg_slots<<<(H + 255) / 256, 256, 0, stream>>>(d_keys_out, d_vals_out, H, FEP_NUM_SHIFT, 1, d_seg_dst, d_key_ptr);
-        cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_seg_gid, d_keys_out, d_vals, d_vals_out, H, 0,
-                                        bits_for(ngrp), stream);
-        k_seg_slots<<<(H + 255) / 256, 256, 0, stream>>>(d_keys_out, d_vals_out, H, ngrp, 2, d_seg_dst,
-                                                        d_key_ptr + FEP_NUM_SHIFT + 1);
-        (*counter) += 3;
+        k_fill_slots<unsigned int><<<(P + 255) / 256, 256, 0, stream>>>(
+                reinterpret_cast<const unsigned int*>(b.keys_out), b.vals_out, b.gstart, b.th, b.tsc, b.pj, b.pn, b.ent4, d_excl,
+                j0, d_par4, G, P, NT, b.cjx, b.qj, b.tj, b.orig, b.trip4, b.tshift, b.tgid, b.akeys, b.avals);
     }
+    /* every force contribution's slot in the atom-sorted buffer: pairs (to their partner) in slot order, then
+     * trips (to their owner) */
+    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.akeys, b.akeys_out, b.avals, b.avals_out, n, 0,
+                                    bits_for((unsigned long long)nT), stream);
+    k_atom_slots<<<(n + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, n, n_slots, nT, b.dst, b.trip4, b.atom_ptr);
+    /* trips by shift index and by energy-group pair */
+    k_iota<<<(NT + 255) / 256, 256, 0, stream>>>(b.avals, NT);
+    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.tshift, b.akeys_out, b.avals, b.avals_out, NT, 0, 6, stream);
+    k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, FEP_NUM_SHIFT, 1, b.trip4, b.key_ptr);
+    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.tgid, b.akeys_out, b.avals, b.avals_out, NT, 0,
+                                    bits_for((unsigned long long)G), stream);
+    k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, G, 2, b.trip4,
+                                                     b.key_ptr + FEP_NUM_SHIFT + 1);
+    (*counter) += 6;
     return (int)cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------------------------------- */
 /* peer exchange (fep_types.h): which rank PRODUCES every element of the atom-sorted contribution
- * buffer, of the shift-sorted segment forces and of the group-sorted segment energies, when rank r
- * evaluates the 32-pair warps [r * wpr, (r + 1) * wpr) of the flat pair space.  One byte per
- * element; the epilogue of the exchange reads each element from its producer's memory. */
-__global__ void __launch_bounds__(256) k_source_tables(const int4* __restrict__ pair4, int P, const int4* __restrict__ seg_dst,
-                                                       int H, const int* __restrict__ warp_hbase, int n_warps, int wpr,
+ * buffer, of the shift-sorted trip sums and of the group-sorted trip energies, when rank r
+ * evaluates the trips [r * tpr, (r + 1) * tpr).  One byte per element; the epilogue of the
+ * exchange reads each element from its producer's memory. */
+__global__ void __launch_bounds__(256) k_source_tables(const int* __restrict__ cjx, const int* __restrict__ dst,
+                                                       const int4* __restrict__ trip4, int NT, int tpr,
                                                        unsigned char* __restrict__ slot_src,
                                                        unsigned char* __restrict__ fshift_src,
                                                        unsigned char* __restrict__ ev2_src)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < P)
+    if (i >= 32 * NT)
     {
-        slot_src[pair4[i].w] = (unsigned char)((i >> 5) / wpr);
+        return;
     }
-    if (i < n_warps)
+    const int           t = i >> 5;
+    const unsigned char r = (unsigned char)(t / tpr);
+    if (!(cjx[i] & FEP_SLOT_PADDING))
     {
-        /* the segments of warp i (at most 32) */
-        const int           h0 = warp_hbase[i];
-        const int           h1 = (i + 1 < n_warps) ? warp_hbase[i + 1] : H;
-        const unsigned char r  = (unsigned char)(i / wpr);
-        for (int h = h0; h < h1; h++)
-        {
-            const int4 sd    = seg_dst[h];
-            slot_src[sd.x]   = r;
-            fshift_src[sd.y] = r;
-            ev2_src[sd.z]    = r;
-        }
+        slot_src[dst[i]] = r;
+    }
+    if ((i & 31) == 0)
+    {
+        const int4 td    = trip4[t];
+        slot_src[td.y]   = r;
+        fshift_src[td.z] = r;
+        ev2_src[td.w]    = r;
     }
 }
 
-extern "C" int fep_launch_source_tables(const int4* d_pair4, int P, const int4* d_seg_dst, int H, const int* d_warp_hbase,
-                                        int wpr, unsigned char* d_slot_src, unsigned char* d_fshift_src,
-                                        unsigned char* d_ev2_src, cudaStream_t stream, long long* counter)
+extern "C" int fep_launch_source_tables(const int* d_cjx, const int* d_dst, const int4* d_trip4, int NT, int tpr,
+                                        unsigned char* d_slot_src, unsigned char* d_fshift_src, unsigned char* d_ev2_src,
+                                        cudaStream_t stream, long long* counter)
 {
-    const int n_warps = (P + 31) / 32;
-    if (P > 0 && wpr > 0)
+    if (NT > 0 && tpr > 0)
     {
-        k_source_tables<<<(P + 255) / 256, 256, 0, stream>>>(d_pair4, P, d_seg_dst, H, d_warp_hbase, n_warps, wpr, d_slot_src,
-                                                            d_fshift_src, d_ev2_src);
+        k_source_tables<<<(32 * NT + 255) / 256, 256, 0, stream>>>(d_cjx, d_dst, d_trip4, NT, tpr, d_slot_src, d_fshift_src,
+                                                                  d_ev2_src);
         (*counter)++;
     }
     return (int)cudaGetLastError();

@@ -383,79 +383,6 @@ __device__ __forceinline__ void fep_included_terms(const KernelArgs& ka, const L
     }
 }
 
-/* Loads one pair and derives its lambda-independent data.  Returns false when the pair
- * contributes nothing (included and beyond the cut-off sphere, reference :667). */
-template<int SC>
-__device__ __forceinline__ bool fep_load_pair(const KernelArgs& ka, int slot, FepPair& pr, float& dx, float& dy,
-                                              float& dz, bool& excluded, bool& self, int& entry)
-{
-    const int4 rec = __ldg(ka.pair4 + slot);
-    entry          = rec.z;
-    excluded       = rec.x < 0;
-    const int cj   = rec.x & 0x7fffffff;
-    const int ci   = rec.y & (FEP_MAX_TOUCHED - 1);
-    self           = (ci == cj);
-
-    const float3 xi = fep_load_pos(ka.pos3, ci);
-    const float4 sh = ka.dyn->shiftvec[rec.y >> 24];
-    const float3 xj = fep_load_pos(ka.pos3, cj);
-    /* the reference shifts the i atom first (:478-480) */
-    dx = (sh.x + xi.x) - xj.x;
-    dy = (sh.y + xi.y) - xj.y;
-    dz = (sh.z + xi.z) - xj.z;
-    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const bool within = r2 < ka.rcut_max2;
-    if (!(within || excluded))
-    {
-        return false;
-    }
-    const float4 pi = __ldg(ka.par4 + ci);
-    const float4 pq = __ldg(ka.par4 + cj);
-    pr.qq[0]        = (ka.epsfac * pi.x) * pq.x;
-    pr.qq[1]        = (ka.epsfac * pi.y) * pq.y;
-    const int tA    = ka.ntype * __float_as_int(pi.z) + __float_as_int(pq.z);
-    const int tB    = ka.ntype * __float_as_int(pi.w) + __float_as_int(pq.w);
-    const float4 a  = __ldg(ka.typetab + tA);
-    const float4 b  = __ldg(ka.typetab + tB);
-    pr.c6[0] = a.x, pr.c12[0] = a.y, pr.sig6[0] = a.z, pr.c6g[0] = a.w;
-    pr.c6[1] = b.x, pr.c12[1] = b.y, pr.sig6[1] = b.z, pr.c6g[1] = b.w;
-    /* soft-core only if one end state has no repulsion (:597-628) */
-    const bool hard = (a.y > 0.0f && b.y > 0.0f);
-    if (SC == FEP_SC_BEUTLER)
-    {
-        pr.a_c = hard ? 0.0f : ka.alpha_c;
-        pr.a_v = hard ? 0.0f : ka.alpha_v;
-    }
-    else if (SC == FEP_SC_GAPSYS)
-    {
-        pr.a_c      = hard ? 0.0f : ka.gscale_c;
-        pr.a_v      = hard ? 0.0f : ka.gscale_v;
-        pr.gbase[0] = fep_sixth_root((26.0f / 7.0f) * a.z);
-        pr.gbase[1] = fep_sixth_root((26.0f / 7.0f) * b.z);
-    }
-    else
-    {
-        pr.a_c = pr.a_v = 0.0f;
-    }
-    r2      = fmaxf(r2, FEP_MIN_RSQ);
-    pr.r2   = r2;
-    pr.rinv = fep_rsqrt(r2);
-    pr.r    = r2 * pr.rinv;
-    if (SC == FEP_SC_BEUTLER)
-    {
-        pr.rpm2 = r2 * r2;
-        pr.r6   = pr.rpm2 * r2;
-    }
-    else
-    {
-        pr.rpm2 = pr.rinv * pr.rinv;
-    }
-    pr.nonzero[0]      = (pr.qq[0] != 0.0f || a.x != 0.0f || a.y != 0.0f);
-    pr.nonzero[1]      = (pr.qq[1] != 0.0f || b.x != 0.0f || b.y != 0.0f);
-    pr.included_within = within && !excluded;
-    return true;
-}
-
 /* Lambda-independent correction factors of one pair (reference :1023-1136):
  *   xc / fc multiply qq[s]  (excluded-pair reaction field, Ewald real-space correction)
  *   xv / fv multiply c6grid[s] (LJ-PME grid correction)                                   */

@@ -1,30 +1,44 @@
 /*
- * fep_types.h -- data layout shared by the host side (fepb200_api.cu) and the sm_100a kernels
- * (fep_kernels.cu).  Vocabulary follows the reference: i-entries, j atoms, pairs, energy-group
- * pairs (gid), shift vectors, lambda states A/B.
+ * fep_types.h -- data layout shared by the host side (fepb200_api.cu) and the sm_100a kernels.
+ * Vocabulary follows the reference: i-entries, j atoms, pairs, energy-group pairs (gid), shift
+ * vectors, lambda states A/B.
  *
- * Device layout of one context (all arrays in HBM; "compact" = index into the ascending list of
- * atoms that occur anywhere in the FULL FEP list, so that every rank uses the same numbering):
+ * The t_nblist handed over at a search step is regrouped ON THE DEVICE (fep_list_build.cu) into
+ * TRIPS: a trip is the work of one warp at one time, 32 pair slots that share
+ *   - an OWNER atom: the end of the pair that occurs in more pairs of the list (for an FEP list:
+ *     the perturbed atom, whichever side of the reference's half list it sits on),
+ *   - the energy-group pair, the shift vector, and the orientation (owner was i / owner was j).
+ * Everything that the reference looks up per i-entry (nb_free_energy.cpp:466-503) is therefore
+ * warp-uniform, the owner's force is one warp reduction per trip, and the segmented sums, per-pair
+ * i-atom gathers and head searches of a flat i-entry-major pair space are gone.  A pair whose owner
+ * was the reference's j atom is evaluated with the negated shift vector (index 44 - s), which gives
+ * the negated distance vector: same energies, same forces on both atoms; its contribution to the
+ * shift force is booked with the opposite sign under the original shift index.
+ *
+ * Device layout of one context ("compact" = index into the ascending list of atoms that occur
+ * anywhere in the FULL list, so that every rank uses the same numbering; "slot" = 32 * trip + lane):
  *
  *   dyn          DynHead           per step: shift vectors + constants of the current lambda
  *   pts[L+1]     LambdaPoint       per set_lambdas: point 0 = current lambda, 1.. = foreign
  *   pos3[nT]     float[3] {x,y,z}  per step: coordinates of the touched atoms (compact order),
  *                                  packed: 12 bytes per atom cross PCIe, not 16
- *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step
+ *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step (read per trip: owner)
  *   typetab[T*T] float4 {c6,c12,sigma6,c6grid}               per nbfp upload
- *   pair4[P]     int4   {compact j | excluded << 31, compact i | shift << 24, local i-entry
- *                       index, pair_dst}: everything a pair needs in ONE coalesced 16-byte load, so the
- *                       dependent chain is record -> atom data -> type table  per search step
+ *   trip4[NT]    int4 {owner | shift_eff << 24 | flipped << 30, slot of the owner's force sum in
+ *                fsorted, slot in fshift_sorted, slot in ev2}                per search step
+ *   per slot, SoA, streamed coalesced (staged through shared memory by one bulk copy per CTA tile):
+ *     cjx[ ]     int    compact partner | excluded << 31 | padding << 30
+ *     dst[ ]     int    where the force on the partner goes in fsorted
+ *     qj[ ]      float2 partner charges {qA, qB}     (pre-gathered: no dependent per-pair load
+ *     tj[ ]      int    partner types  A | B << 16    except the partner's coordinates)
+ *     orig[ ]    int    index of the pair in the shard's t_nblist (list read-back only)
  *   ent4[E]      int4   {compact i, shift index, gid, 0}  (list read-back only) per search step
- *   warp_hbase[ceil(P/32)]  index of the first "segment" of each warp of the flat pair space;
- *                a segment is a maximal run of pairs of one i-entry inside one warp
- *                (pair4[].w is where the pair's force on its j atom goes in fsorted)
- *   seg_dst[H]   int4   {slot in fsorted, slot in fshift_sorted, slot in ev2, 0} per search step
- *   fsorted[P+H] float4 force contributions SORTED BY RECEIVING ATOM: atom k owns the contiguous
- *                range [atom_ptr[k], atom_ptr[k+1]); the pass kernel scatters -t (pairs, as j) and
- *                +f_i (segments, as i) to precomputed unique slots, the epilogue streams ranges
- *   fshift_sorted[H] float4 segment i-forces sorted by shift index;  ev2[H] float2 segment
- *                {Vc,Vv} sorted by energy-group pair; red_jobs = chunks of those ranges
+ *   fsorted[P+NT] float4 force contributions SORTED BY RECEIVING ATOM: atom k owns the contiguous
+ *                range [atom_ptr[k], atom_ptr[k+1]); the pass kernel scatters -f (pairs, to the
+ *                partner) and the trip's sum (to the owner) to precomputed unique slots, the
+ *                epilogue streams ranges: no atomics, bit-reproducible
+ *   fshift_sorted[NT] float4 trip sums sorted by shift index;  ev2[NT] float2 trip {Vc,Vv} sorted
+ *                by energy-group pair; red_jobs = chunks of those ranges
  *   cta_part[nCta][2]        fp64 per-CTA partial dV/dlambda of the current-lambda pass
  *   for_part[3*(L+1)][nTile] fp64 per-CTA partial foreign energies / dV/dlambda
  *   result block: res_f32[3*nT + 3*45], res_f64[2G + 2 + 3(L+1)]   (include/fepb200.h)
@@ -35,7 +49,9 @@
 #include <cuda_runtime.h>
 
 #define FEP_NUM_SHIFT 45
-#define FEP_MAX_TOUCHED (1 << 24) /* compact atom index and shift index share one word of pair4 */
+#define FEP_MAX_TOUCHED (1 << 24) /* compact atom index, shift index and flags share one word */
+#define FEP_SLOT_PADDING 0x40000000 /* cjx: the slot holds no pair (tail of a trip) */
+#define FEP_TRIP_FLIPPED 0x40000000 /* trip4.x: the owner was the j atom of the reference's pairs */
 #define FEP_CENTRAL_SHIFT 22
 #define FEP_MAX_POINTS 256 /* L+1 <= 256 lambda points per step */
 #define FEP_CTA 256        /* threads per CTA of the pair kernels */
@@ -79,8 +95,8 @@ struct RedJob
 };
 
 /* Multi-GPU "owner computes" exchange (fepb200_set_peer_exchange): every rank holds the layout of
- * the FULL list and evaluates a contiguous range of 32-pair warps of the flat pair space with the
- * unchanged single-GPU pair kernels; they store force contributions, segment values and per-CTA
+ * the FULL list and evaluates a contiguous range of its trips with the
+ * unchanged single-GPU pair kernels; they store force contributions, trip sums and per-CTA
  * partials at their usual places in the rank's OWN exchange slot, which every rank of the node has
  * mapped (NVLink peer memory).  Nothing is sent: after a cross-GPU barrier at the top of the
  * epilogue each rank PULLS what it needs -- the contributions of the atoms it owns (a contiguous
@@ -123,10 +139,10 @@ struct KernelArgs
     float sw_v3, sw_v4, sw_v5, sw_f2, sw_f3, sw_f4;
     int   vdw_ewald, pot_switch, rf_type, ntype;
     /* sizes */
-    int n_pairs, n_entries, n_segments, n_touched, n_gid, n_cta, n_tiles, tile_pairs;
-    int pair_begin, pair_end; /* the pairs this context evaluates ([0, n_pairs) unless the list is split over peers) */
+    int n_pairs, n_entries, n_trips, n_touched, n_gid, n_cta, n_tiles, tile_trips;
+    int trip_begin, trip_end; /* the trips this context evaluates ([0, n_trips) unless the list is split over peers) */
     int n_points, n_chunks, chunk_points;
-    int pass_tile_pairs, pass_n_tiles; /* tiles of the force-only Beutler kernel */
+    int pass_tile_trips, pass_n_tiles; /* tiles of the force-only Beutler kernel */
     int n_parts;                       /* per-CTA dV/dlambda partials written by the pass of this step */
     int fuse_pass_and_foreign;         /* Beutler path: pass + first foreign chunk in one launch */
     int n_red_jobs, n_shift_jobs;
@@ -137,9 +153,11 @@ struct KernelArgs
     const float*    pos3;
     const float4*   par4;
     const float4*   typetab;
-    const int4*     pair4;
-    const int*      warp_hbase;
-    const int4*     seg_dst;
+    const int4*     trip4;
+    const int*      cjx;
+    const int*      dst;
+    const float2*   qj;
+    const int*      tj;
     /* intermediates */
     float4* fsorted;
     float4* fshift_sorted;
@@ -167,6 +185,20 @@ struct StepFlags
     int force, shift, energy, foreign;
 };
 
+/* Device buffers of the list builder (fep_list_build.cu); ints unless noted.  Scratch: pj, pn [P]; deg [nT+1];
+ * keys, keys_out [P] of 4- or 8-byte keys; vals, vals_out, gmark, gstart [P]; th, tsc [P+1]; akeys, akeys_out,
+ * avals, avals_out [P+NT]; tshift [NT]; key_ptr [46 + G + 1].  Results: ent4 [E]; trip4, tgid [NT]; cjx, dst, qj,
+ * tj, orig [32 NT]; atom_ptr [nT+1]. */
+struct ListBuild
+{
+    int *  pj, *pn, *deg, *vals, *vals_out, *gmark, *gstart, *th, *tsc, *akeys, *akeys_out, *avals, *avals_out, *tshift, *key_ptr;
+    void * keys, *keys_out, *tmp;
+    size_t tmp_bytes;
+    int4 * ent4, *trip4;
+    int *  tgid, *cjx, *dst, *tj, *orig, *atom_ptr;
+    float2* qj;
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -181,6 +213,7 @@ int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlag
                     const LambdaPoint* host_pts, int beutler_mode, cudaStream_t side_stream, cudaEvent_t fork_ev,
                     cudaEvent_t join_ev);
 #define FEP_FB_CTA 128
+#define FEP_TILE_SMEM_MAX (44 * 1024) /* dynamic shared memory of a pair kernel: the staged tile */
 #define FEP_FB_MAXC 24
 int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
 int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force);
@@ -246,13 +279,13 @@ __device__ __forceinline__ void fep_pdl_wait()
 }
 
 template<typename... KArgs, typename... Args>
-static inline cudaError_t fep_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream,
-                                            bool chained, Args&&... args)
+static inline cudaError_t fep_launch_kernel_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes,
+                                                 cudaStream_t stream, bool chained, Args&&... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim            = grid;
     cfg.blockDim           = block;
-    cfg.dynamicSmemBytes   = 0;
+    cfg.dynamicSmemBytes   = smem_bytes;
     cfg.stream             = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -260,6 +293,13 @@ static inline cudaError_t fep_launch_kernel(void (*kernel)(KArgs...), dim3 grid,
     cfg.attrs                                          = attr;
     cfg.numAttrs                                       = chained ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template<typename... KArgs, typename... Args>
+static inline cudaError_t fep_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream,
+                                            bool chained, Args&&... args)
+{
+    return fep_launch_kernel_smem(kernel, grid, block, 0, stream, chained, static_cast<Args&&>(args)...);
 }
 #endif
 

@@ -33,18 +33,14 @@ extern "C" size_t fep_list_build_temp_bytes(int natoms, long long n_sort_max);
 extern "C" int    fep_list_build_touched(const int* d_iinr, int nri_total, const int* d_jjnr, long long nrj_total, int natoms,
                                          int* d_mark, int* d_cscan, int* d_touched, void* d_tmp, size_t tmp_bytes,
                                          cudaStream_t stream, long long* counter);
-extern "C" int    fep_list_build_pairs(const int* d_iinr, const int* d_gid, const int* d_shift, const int* d_jindex,
-                                       const int* d_jjnr, const int* d_excl, const int* d_cscan, int e0, int E, int j0, int P,
-                                       int4* d_ent4, int4* d_pair4, int* d_keys, int* d_head, int* d_hscan, void* d_tmp,
-                                       size_t tmp_bytes, cudaStream_t stream, long long* counter);
-extern "C" int    fep_launch_source_tables(const int4* d_pair4, int P, const int4* d_seg_dst, int H, const int* d_warp_hbase,
-                                           int wpr, unsigned char* d_slot_src, unsigned char* d_fshift_src,
-                                           unsigned char* d_ev2_src, cudaStream_t stream, long long* counter);
-extern "C" int    fep_list_build_slots(const int4* d_ent4, int4* d_pair4, const int* d_head, const int* d_hscan, int P, int H,
-                                       int nT, int ngrp, int* d_keys, int* d_keys_out, int* d_vals, int* d_vals_out,
-                                       int* d_seg_shift, int* d_seg_gid, int* d_warp_hbase, int4* d_seg_dst, int* d_atom_ptr,
-                                       int* d_key_ptr, void* d_tmp, size_t tmp_bytes, cudaStream_t stream,
-                                       long long* counter);
+extern "C" int    fep_list_build_groups(const ListBuild* b, const int* d_iinr, const int* d_gid, const int* d_shift,
+                                        const int* d_jindex, const int* d_jjnr, const int* d_cscan, int e0, int E, int j0, int P,
+                                        int nT, int G, int wide_keys, cudaStream_t stream, long long* counter);
+extern "C" int    fep_list_build_slots(const ListBuild* b, const int* d_excl, int j0, const float4* d_par4, int P, int NT, int nT,
+                                       int G, int wide_keys, cudaStream_t stream, long long* counter);
+extern "C" int    fep_launch_source_tables(const int* d_cjx, const int* d_dst, const int4* d_trip4, int NT, int tpr,
+                                           unsigned char* d_slot_src, unsigned char* d_fshift_src, unsigned char* d_ev2_src,
+                                           cudaStream_t stream, long long* counter);
 
 namespace
 {
@@ -220,24 +216,25 @@ struct fepb200_ctx
     /* fepb200_compute(): the epilogue writes the result block into the pinned host buffer itself */
     bool             zc_out = true, zc_next = false, result_on_host = false;
     unsigned char*   h_result_dev = nullptr; /* device view of the pinned result buffer (zero-copy output) */
-    std::vector<int> compact_of; /* atom -> compact or -1 */
     /* work arrays of fepb200_set_list(), kept between calls so that a search step does not pay for
      * page faults of fresh allocations */
-    std::vector<int>    w_pair_j, w_pair_e, w_warp_hbase, w_seg_entry, w_atom_ptr, w_fill;
-    std::vector<int4>   w_ent4, w_pair4, w_seg_dst;
+    std::vector<int>    w_atom_ptr;
     std::vector<float4> w_par4;
-    int              n_segments = 0;
+    int              n_trips = 0;
 
-    DeviceArray<int>    d_touched, d_warp_hbase, d_atom_ptr, d_key_job_ptr;
-    DeviceArray<int4>   d_ent4, d_seg_dst, d_pair4;
+    DeviceArray<int>    d_touched, d_atom_ptr, d_key_job_ptr;
+    DeviceArray<int4>   d_ent4, d_trip4;
+    DeviceArray<int>    d_cjx, d_dst, d_tj, d_orig, d_tgid;
+    DeviceArray<float2> d_qj;
     DeviceArray<RedJob> d_red_jobs;
     DeviceArray<float4> d_par4, d_fsorted, d_fshift_sorted;
     DeviceArray<float2> d_ev2;
     DeviceArray<double> d_cta_part, d_for_part, d_job_part;
     DeviceArray<unsigned int> d_counter;
     /* raw list + scratch of the device-side list build (fep_list_build.cu) */
-    DeviceArray<int> d_raw_iinr, d_raw_gid, d_raw_shift, d_raw_jindex, d_raw_jjnr, d_raw_excl, d_mark, d_cscan, d_keys,
-            d_keys_out, d_vals, d_vals_out, d_head, d_hscan, d_seg_shift, d_seg_gid, d_key_ptr;
+    DeviceArray<int> d_raw_iinr, d_raw_gid, d_raw_shift, d_raw_jindex, d_raw_jjnr, d_raw_excl, d_mark, d_cscan, d_pj, d_pn, d_deg,
+            d_vals, d_vals_out, d_gmark, d_gstart, d_th, d_tsc, d_akeys, d_akeys_out, d_avals, d_avals_out, d_tshift, d_key_ptr;
+    DeviceArray<unsigned long long> d_keys, d_keys_out;
     DeviceArray<unsigned char> d_cub_tmp;
     DeviceArray<unsigned char> d_step_in; /* [DynHead | pos3[nT]] */
     DeviceArray<unsigned char> d_result;  /* [f64 block | f32 block] */
@@ -249,8 +246,8 @@ struct fepb200_ctx
      * takes a range of pairs and owns a range of atoms */
     bool           px_on = false;
     int            x_nranks = 1, x_rank = 0;
-    int            x_range_pairs = 0;   /* pairs per rank, rounded up (same on every rank) */
-    int            x_pair_begin = 0, x_pair_end = 0, x_atom_begin = 0, x_atom_end = 0, x_heavy_begin = 0, x_heavy_end = 0;
+    int            x_range_trips = 0;   /* trips per rank, rounded up (same on every rank) */
+    int            x_trip_begin = 0, x_trip_end = 0, x_atom_begin = 0, x_atom_end = 0, x_heavy_begin = 0, x_heavy_end = 0;
     DeviceArray<unsigned char> d_slot_src, d_fshift_src, d_ev2_src; /* producer rank of every sorted element */
     DeviceArray<int>    d_heavy;      /* atoms with more than FEP_HEAVY_MIN force contributions, ascending */
     std::vector<int>    heavy_atoms;  /* host copy */
@@ -370,12 +367,12 @@ int prepare_buffers(fepb200_ctx* c)
     k.n_points = np;
     int sms    = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    /* the pairs this context evaluates: all of its list, or its share of it (peer exchange); every
+    /* the trips this context evaluates: all of its list, or its share of it (peer exchange); every
      * launch size below follows from `range`, which is the same on all ranks of an exchange */
-    const int range = c->px_on ? c->x_range_pairs : k.n_pairs;
-    k.pair_begin    = c->px_on ? c->x_pair_begin : 0;
-    k.pair_end      = c->px_on ? c->x_pair_end : k.n_pairs;
-    k.n_cta         = (range + FEP_CTA - 1) / FEP_CTA;
+    const int range = c->px_on ? c->x_range_trips : k.n_trips;
+    k.trip_begin    = c->px_on ? c->x_trip_begin : 0;
+    k.trip_end      = c->px_on ? c->x_trip_end : k.n_trips;
+    k.n_cta         = (range + FEP_CTA / 32 - 1) / (FEP_CTA / 32); /* generic pass kernel: one warp per trip */
     c->foreign_mode = -1;
     if (c->softcore == FEP_SC_BEUTLER && !k.pot_switch)
     {
@@ -394,8 +391,8 @@ int prepare_buffers(fepb200_ctx* c)
             }
             c->foreign_mode = same ? 1 : 2;
         }
-        /* one launch per chunk; split the points only when the pair CTAs alone cannot fill the GPU */
-        const long long pair_ctas = (range + FEP_FB_CTA - 1) / FEP_FB_CTA;
+        /* one launch per chunk; split the points only when the trips alone cannot fill the GPU */
+        const long long pair_ctas = (range + FEP_FB_CTA / 32 - 1) / (FEP_FB_CTA / 32);
         int             want      = 1;
         if (pair_ctas > 0 && pair_ctas < 2LL * sms)
         {
@@ -403,13 +400,16 @@ int prepare_buffers(fepb200_ctx* c)
         }
         k.chunk_points = fep_beutler_chunk_size(np, want);
         k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
-        /* one wave: as many pair tiles as CTAs can be resident */
-        auto tiles = [&](long long ctas_per_sm, int& tile_pairs, int& n_tiles) {
-            const long long target     = (long long)sms * ctas_per_sm;
-            long long       per_thread = ((long long)range + target * FEP_FB_CTA - 1) / (target * FEP_FB_CTA);
-            per_thread                 = std::max(1LL, std::min(per_thread, 32LL));
-            tile_pairs                 = (int)per_thread * FEP_FB_CTA;
-            n_tiles                    = (range + tile_pairs - 1) / tile_pairs;
+        /* one wave: as many tiles as CTAs can be resident, at least one trip per warp; a tile is staged in
+         * shared memory as a whole, which bounds its size (larger lists take more than one wave) */
+        auto tiles = [&](long long ctas_per_sm, bool with_dst, int& tile_trips, int& n_tiles) {
+            const long long target  = (long long)sms * ctas_per_sm;
+            const long long per_trip = (long long)(sizeof(int4) + 32 * (with_dst ? 20 : 16));
+            const long long cap     = std::max(1LL, std::min<long long>(FEP_TILE_SMEM_MAX, 200 * 1024 / ctas_per_sm) / per_trip);
+            long long       tt      = ((long long)range + target - 1) / target;
+            tt                      = std::max<long long>(FEP_FB_CTA / 32, std::min(tt, cap));
+            tile_trips              = (int)tt;
+            n_tiles                 = (range + tile_trips - 1) / tile_trips;
         };
         /* fuse pass + foreign when the list is too small to fill the GPU anyway */
         k.fuse_pass_and_foreign = pair_ctas < 16LL * sms;
@@ -428,9 +428,9 @@ int prepare_buffers(fepb200_ctx* c)
         };
         tiles(per_sm("FEPB200_FOREIGN_CTAS_PER_SM",
                      fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign)),
-              k.tile_pairs, k.n_tiles);
-        tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)),
-              k.pass_tile_pairs, k.pass_n_tiles);
+              k.fuse_pass_and_foreign != 0, k.tile_trips, k.n_tiles);
+        tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)), true,
+              k.pass_tile_trips, k.pass_n_tiles);
     }
     else
     {
@@ -438,21 +438,21 @@ int prepare_buffers(fepb200_ctx* c)
         k.n_chunks     = (np + FEP_LCHUNK - 1) / FEP_LCHUNK;
         k.chunk_points = (np + k.n_chunks - 1) / k.n_chunks;
         k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
-        /* pair tiles: enough CTAs to fill the GPU several times over, but several pairs per thread
+        /* tiles of trips: enough CTAs to fill the GPU several times over, but several trips per warp
          * on large lists to amortise the final reduction */
         const long long target_ctas = 8LL * sms;
-        long long       per_thread  = ((long long)range * k.n_chunks + target_ctas * FEP_CTA - 1)
-                               / (target_ctas * FEP_CTA);
-        per_thread   = std::max(1LL, std::min(per_thread, 8LL));
-        k.tile_pairs = (int)per_thread * FEP_CTA;
-        k.n_tiles    = (range + k.tile_pairs - 1) / k.tile_pairs;
+        long long       per_warp    = ((long long)range * k.n_chunks + target_ctas * (FEP_CTA / 32) - 1)
+                             / (target_ctas * (FEP_CTA / 32));
+        per_warp     = std::max(1LL, std::min(per_warp, 8LL));
+        k.tile_trips = (int)per_warp * (FEP_CTA / 32);
+        k.n_tiles    = (range + k.tile_trips - 1) / k.tile_trips;
     }
     if (c->px_on)
     {
         /* carve one exchange slot: [fsorted | fshift_sorted | ev2 | cta_part | for_part], every part
          * 256-byte aligned; identical on all ranks because every input of the sizes is */
         auto         up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t P       = (size_t)k.n_pairs, H = (size_t)k.n_segments;
+        const size_t P       = (size_t)k.n_pairs, H = (size_t)k.n_trips;
         const size_t n_parts = (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1));
         c->x_off_fsorted     = 0;
         c->x_off_fshift      = c->x_off_fsorted + up((P + H) * sizeof(float4));
@@ -671,11 +671,13 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
         CU_CHECK(c, cudaMemcpyAsync(c->d_raw_excl.ptr, excl_fep, sizeof(int) * nrj_total, cudaMemcpyHostToDevice, st));
         d_excl = c->d_raw_excl.ptr;
     }
-    /* scratch */
-    const int       n_warps = (P + 31) / 32;
-    const long long h_max   = (long long)E + n_warps; /* a segment starts at an entry start or a warp start */
-    const long long n_max   = P + h_max;
-    if (n_max >= (1LL << 31) - 64)
+    if (c->ntype > 65535)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than 65535 atom types");
+    }
+    /* compact numbering of the atoms of the FULL list */
+    const long long n_max     = 2LL * P + 64; /* P pairs + at most P trips */
+    if (n_max >= (1LL << 31) - 64 || 33LL * P >= (1LL << 31) - 64)
     {
         return fail(c, FEPB200_ERR_UNSUPPORTED, "list too large");
     }
@@ -690,60 +692,51 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
     {
         return fail(c, FEPB200_ERR_CUDA, "list build (touched) failed: %s", cudaGetErrorString((cudaError_t)err));
     }
-    /* pair records and segment heads do not need nT on the host: queue them before the first sync */
-    CU_CHECK(c, c->d_ent4.reserve(std::max(E, 1)));
-    CU_CHECK(c, c->d_pair4.reserve(std::max(P, 1)));
-    CU_CHECK(c, c->d_keys.reserve(std::max<long long>(n_max, 1)));
-    CU_CHECK(c, c->d_head.reserve((size_t)P + 1));
-    CU_CHECK(c, c->d_hscan.reserve((size_t)P + 1));
-    err = fep_list_build_pairs(c->d_raw_iinr.ptr, c->d_raw_gid.ptr, c->d_raw_shift.ptr, c->d_raw_jindex.ptr,
-                               c->d_raw_jjnr.ptr, d_excl, c->d_cscan.ptr, e0, E, j0, P, c->d_ent4.ptr, c->d_pair4.ptr,
-                               c->d_keys.ptr, c->d_head.ptr, c->d_hscan.ptr, c->d_cub_tmp.ptr, tmp_bytes, st, &c->launches);
-    if (err != 0)
-    {
-        return fail(c, FEPB200_ERR_CUDA, "list build (pairs) failed: %s", cudaGetErrorString((cudaError_t)err));
-    }
-    int nT = 0, H = 0;
+    int nT = 0, NT = 0;
     CU_CHECK(c, cudaMemcpyAsync(&nT, c->d_cscan.ptr + c->natoms, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU_CHECK(c, cudaMemcpyAsync(&H, c->d_hscan.ptr + P, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_CHECK(c, cudaStreamSynchronize(st));
     if (nT >= FEP_MAX_TOUCHED)
     {
         return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d distinct atoms in one FEP list", FEP_MAX_TOUCHED);
     }
-    const int n = P + H;
-    CU_CHECK(c, c->d_keys_out.reserve(std::max(n, 1)));
-    CU_CHECK(c, c->d_vals.reserve(std::max(n, 1)));
-    CU_CHECK(c, c->d_vals_out.reserve(std::max(n, 1)));
-    CU_CHECK(c, c->d_seg_shift.reserve(std::max(H, 1)));
-    CU_CHECK(c, c->d_seg_gid.reserve(std::max(H, 1)));
-    CU_CHECK(c, c->d_warp_hbase.reserve(std::max(n_warps, 1)));
-    CU_CHECK(c, c->d_seg_dst.reserve(std::max(H, 1)));
+    /* scratch and the buffers whose size follows from P and nT; the group sort does not need the atom parameters,
+     * so it is queued before the host prepares them */
+    const bool wide = (unsigned long long)std::max(nT, 1) * (unsigned long long)ngrp * 128ULL >= (1ULL << 32);
+    CU_CHECK(c, c->d_ent4.reserve(std::max(E, 1)));
+    CU_CHECK(c, c->d_pj.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_pn.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_deg.reserve((size_t)nT + 1));
+    CU_CHECK(c, c->d_keys.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_keys_out.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_vals.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_vals_out.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_gmark.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_gstart.reserve(std::max(P, 1)));
+    CU_CHECK(c, c->d_th.reserve((size_t)P + 1));
+    CU_CHECK(c, c->d_tsc.reserve((size_t)P + 1));
     CU_CHECK(c, c->d_atom_ptr.reserve((size_t)nT + 1));
     CU_CHECK(c, c->d_key_ptr.reserve(FEP_NUM_SHIFT + 1 + ngrp + 1));
-    err = fep_list_build_slots(c->d_ent4.ptr, c->d_pair4.ptr, c->d_head.ptr, c->d_hscan.ptr, P, H, nT, ngrp, c->d_keys.ptr,
-                               c->d_keys_out.ptr, c->d_vals.ptr, c->d_vals_out.ptr, c->d_seg_shift.ptr, c->d_seg_gid.ptr,
-                               c->d_warp_hbase.ptr, c->d_seg_dst.ptr, c->d_atom_ptr.ptr, c->d_key_ptr.ptr, c->d_cub_tmp.ptr,
-                               tmp_bytes, st, &c->launches);
+    ListBuild b{};
+    b.pj = c->d_pj.ptr, b.pn = c->d_pn.ptr, b.deg = c->d_deg.ptr;
+    b.keys = c->d_keys.ptr, b.keys_out = c->d_keys_out.ptr, b.vals = c->d_vals.ptr, b.vals_out = c->d_vals_out.ptr;
+    b.gmark = c->d_gmark.ptr, b.gstart = c->d_gstart.ptr, b.th = c->d_th.ptr, b.tsc = c->d_tsc.ptr;
+    b.tmp = c->d_cub_tmp.ptr, b.tmp_bytes = tmp_bytes;
+    b.ent4 = c->d_ent4.ptr, b.atom_ptr = c->d_atom_ptr.ptr, b.key_ptr = c->d_key_ptr.ptr;
+    err = fep_list_build_groups(&b, c->d_raw_iinr.ptr, c->d_raw_gid.ptr, c->d_raw_shift.ptr, c->d_raw_jindex.ptr,
+                                c->d_raw_jjnr.ptr, c->d_cscan.ptr, e0, E, j0, P, nT, ngrp, wide ? 1 : 0, st, &c->launches);
     if (err != 0)
     {
-        return fail(c, FEPB200_ERR_CUDA, "list build (slots) failed: %s", cudaGetErrorString((cudaError_t)err));
+        return fail(c, FEPB200_ERR_CUDA, "list build (groups) failed: %s", cudaGetErrorString((cudaError_t)err));
     }
-    /* back to the host: the touched atoms (for the coordinate gather / force scatter of every
-     * step) and the per-key counts (for the reduction jobs) */
-    std::vector<int> key_ptr(FEP_NUM_SHIFT + 1 + ngrp + 1, 0);
+    CU_CHECK(c, cudaMemcpyAsync(&NT, c->d_tsc.ptr + P, sizeof(int), cudaMemcpyDeviceToHost, st));
+    /* while the GPU sorts: the touched atoms (for the coordinate gather / force scatter of every step) and the
+     * per-atom parameters in compact order (the per-atom arrays of set_atoms live on the host) */
     c->touched.resize(nT);
     if (nT > 0)
     {
         CU_CHECK(c, cudaMemcpyAsync(c->touched.data(), c->d_touched.ptr, sizeof(int) * nT, cudaMemcpyDeviceToHost, st));
     }
-    CU_CHECK(c, cudaMemcpyAsync(key_ptr.data(), c->d_key_ptr.ptr, sizeof(int) * key_ptr.size(), cudaMemcpyDeviceToHost, st));
-    /* range of every touched atom in the atom-sorted buffer: the host picks the heavy atoms from it */
-    c->w_atom_ptr.resize((size_t)nT + 1);
-    CU_CHECK(c, cudaMemcpyAsync(c->w_atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost, st));
     CU_CHECK(c, cudaStreamSynchronize(st));
-    build_jobs(key_ptr.data(), key_ptr.data() + FEP_NUM_SHIFT + 1, ngrp, jobs, key_job_ptr, &c->ka.n_shift_jobs);
-    /* per-atom parameters in compact order (the per-atom arrays of set_atoms live on the host) */
     std::vector<float4>& par4 = c->w_par4;
     par4.resize(nT);
 #pragma omp parallel for schedule(static) num_threads(host_threads(nT)) if (nT > c_host_grain)
@@ -753,13 +746,45 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
         par4[k]     = make_float4(c->qA[a], c->qB[a], int_bits_as_float(c->typeA[a]), int_bits_as_float(c->typeB[a]));
     }
     int rc;
-    if ((rc = to_device(c, c->d_red_jobs, *jobs)) || (rc = to_device(c, c->d_key_job_ptr, *key_job_ptr))
-        || (rc = to_device(c, c->d_par4, par4)))
+    if ((rc = to_device(c, c->d_par4, par4)))
+    {
+        return rc;
+    }
+    const size_t n_slots = 32 * (size_t)NT;
+    CU_CHECK(c, c->d_trip4.reserve(std::max(NT, 1)));
+    CU_CHECK(c, c->d_tgid.reserve(std::max(NT, 1)));
+    CU_CHECK(c, c->d_tshift.reserve(std::max(NT, 1)));
+    CU_CHECK(c, c->d_cjx.reserve(std::max<size_t>(n_slots, 1)));
+    CU_CHECK(c, c->d_dst.reserve(std::max<size_t>(n_slots, 1)));
+    CU_CHECK(c, c->d_qj.reserve(std::max<size_t>(n_slots, 1)));
+    CU_CHECK(c, c->d_tj.reserve(std::max<size_t>(n_slots, 1)));
+    CU_CHECK(c, c->d_orig.reserve(std::max<size_t>(n_slots, 1)));
+    CU_CHECK(c, c->d_akeys.reserve(std::max(P + NT, 1)));
+    CU_CHECK(c, c->d_akeys_out.reserve(std::max(P + NT, 1)));
+    CU_CHECK(c, c->d_avals.reserve(std::max(P + NT, 1)));
+    CU_CHECK(c, c->d_avals_out.reserve(std::max(P + NT, 1)));
+    b.trip4 = c->d_trip4.ptr, b.tgid = c->d_tgid.ptr, b.tshift = c->d_tshift.ptr;
+    b.cjx = c->d_cjx.ptr, b.dst = c->d_dst.ptr, b.qj = c->d_qj.ptr, b.tj = c->d_tj.ptr, b.orig = c->d_orig.ptr;
+    b.akeys = c->d_akeys.ptr, b.akeys_out = c->d_akeys_out.ptr, b.avals = c->d_avals.ptr, b.avals_out = c->d_avals_out.ptr;
+    err = fep_list_build_slots(&b, d_excl, j0, c->d_par4.ptr, P, NT, nT, ngrp, wide ? 1 : 0, st, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "list build (slots) failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    /* back to the host: the per-key counts (for the reduction jobs) and the range of every touched atom in the
+     * atom-sorted buffer (the host picks the heavy atoms from it) */
+    std::vector<int> key_ptr(FEP_NUM_SHIFT + 1 + ngrp + 1, 0);
+    CU_CHECK(c, cudaMemcpyAsync(key_ptr.data(), c->d_key_ptr.ptr, sizeof(int) * key_ptr.size(), cudaMemcpyDeviceToHost, st));
+    c->w_atom_ptr.resize((size_t)nT + 1);
+    CU_CHECK(c, cudaMemcpyAsync(c->w_atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaStreamSynchronize(st));
+    build_jobs(key_ptr.data(), key_ptr.data() + FEP_NUM_SHIFT + 1, ngrp, jobs, key_job_ptr, &c->ka.n_shift_jobs);
+    if ((rc = to_device(c, c->d_red_jobs, *jobs)) || (rc = to_device(c, c->d_key_job_ptr, *key_job_ptr)))
     {
         return rc;
     }
     *nT_out = nT;
-    *H_out  = H;
+    *H_out  = NT;
     return FEPB200_OK;
 }
 
@@ -865,10 +890,14 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_pts.release();
     c->h_pts.release();
     c->d_touched.release();
-    c->d_pair4.release();
-    c->d_warp_hbase.release();
+    c->d_trip4.release();
+    c->d_cjx.release();
+    c->d_dst.release();
+    c->d_qj.release();
+    c->d_tj.release();
+    c->d_orig.release();
+    c->d_tgid.release();
     c->d_atom_ptr.release();
-    c->d_seg_dst.release();
     c->d_key_job_ptr.release();
     c->d_ent4.release();
     c->d_red_jobs.release();
@@ -897,10 +926,18 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_keys_out.release();
     c->d_vals.release();
     c->d_vals_out.release();
-    c->d_head.release();
-    c->d_hscan.release();
-    c->d_seg_shift.release();
-    c->d_seg_gid.release();
+    c->d_pj.release();
+    c->d_pn.release();
+    c->d_deg.release();
+    c->d_gmark.release();
+    c->d_gstart.release();
+    c->d_th.release();
+    c->d_tsc.release();
+    c->d_akeys.release();
+    c->d_akeys_out.release();
+    c->d_avals.release();
+    c->d_avals_out.release();
+    c->d_tshift.release();
     c->d_key_ptr.release();
     c->d_cub_tmp.release();
     c->d_step_in.release();
@@ -1222,204 +1259,18 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     const int P  = E > 0 ? jindex[e1] - j0 : 0;
 
 
-    /* Two builders of the device layout with identical results: kernels + scans + stable sorts
-     * on the GPU (default), or loops on the host (FEPB200_SETLIST=host). */
-    bool device_build = true;
-    if (const char* env = std::getenv("FEPB200_SETLIST"))
-    {
-        device_build = std::string(env) != "host";
-    }
+    /* the device layout is built on the GPU: kernels + scans + stable sorts (fep_list_build.cu) */
     int                 nT = 0, H = 0, rc = 0;
     std::vector<RedJob> jobs;
     std::vector<int>    key_job_ptr;
-    if (device_build)
+    rc = build_list_device(c, nri, iinr, gid, shift, jindex, jjnr, excl_fep, nrj_total, ngrp, e0, E, j0, P, &nT, &H, &jobs,
+                           &key_job_ptr);
+    if (rc != FEPB200_OK)
     {
-        rc = build_list_device(c, nri, iinr, gid, shift, jindex, jjnr, excl_fep, nrj_total, ngrp, e0, E, j0, P, &nT, &H,
-                               &jobs, &key_job_ptr);
-        if (rc != FEPB200_OK)
-        {
-            return rc;
-        }
-        lap("device build");
+        return rc;
     }
-    else
-    {
-        /* touched atoms of the FULL list (same numbering on every rank; mirrors the reduction mask
-         * of setReductionMaskFromFepPairlist, freeenergydispatch.cpp:74-89) */
-        c->compact_of.assign(c->natoms, -1);
-        for (int n = 0; n < nri; n++)
-        {
-            c->compact_of[iinr[n]] = 0;
-        }
-        for (long long k = 0; k < nrj_total; k++)
-        {
-            c->compact_of[jjnr[k]] = 0;
-        }
-        c->touched.clear();
-        for (int a = 0; a < c->natoms; a++)
-        {
-            if (c->compact_of[a] == 0)
-            {
-                c->compact_of[a] = (int)c->touched.size();
-                c->touched.push_back(a);
-            }
-        }
-        nT = (int)c->touched.size();
-
-        if (nT >= FEP_MAX_TOUCHED)
-        {
-            return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d distinct atoms in one FEP list", FEP_MAX_TOUCHED);
-        }
-        std::vector<int>&  pair_j = c->w_pair_j;
-        std::vector<int>&  pair_e = c->w_pair_e;
-        std::vector<int4>& ent4   = c->w_ent4;
-        std::vector<int4>& pair4  = c->w_pair4;
-        pair_j.resize(P);
-        pair_e.resize(P);
-        ent4.resize(E);
-        pair4.resize(P);
-        const int         nthr = std::min(8, std::max(1, omp_get_max_threads()));
-    #pragma omp parallel for schedule(static) num_threads(nthr) if (P > 65536)
-        for (int n = 0; n < E; n++)
-        {
-            const int g = e0 + n;
-            ent4[n]     = make_int4(c->compact_of[iinr[g]], shift[g], gid[g], 0);
-            for (int k = jindex[g]; k < jindex[g + 1]; k++)
-            {
-                const bool excluded = excl_fep && excl_fep[k] == 0;
-                pair_j[k - j0]      = c->compact_of[jjnr[k]] | (excluded ? (int)0x80000000u : 0);
-                pair_e[k - j0]      = n;
-                pair4[k - j0]       = make_int4(pair_j[k - j0], ent4[n].x | (shift[g] << 24), n, 0);
-            }
-        }
-
-        lap("pair records");
-        /* segments: maximal runs of one i-entry inside one 32-pair warp */
-        const int        n_warps = (P + 31) / 32;
-        std::vector<int>& warp_hbase = c->w_warp_hbase;
-        std::vector<int>& seg_entry  = c->w_seg_entry;
-        warp_hbase.assign(std::max(n_warps, 1), 0);
-        seg_entry.clear();
-        seg_entry.reserve((size_t)E + n_warps);
-        for (int w = 0; w < n_warps; w++)
-        {
-            warp_hbase[w]  = (int)seg_entry.size();
-            const int last = std::min(P, 32 * w + 32);
-            for (int s = 32 * w; s < last; s++)
-            {
-                if (s == 32 * w || pair_e[s] != pair_e[s - 1])
-                {
-                    seg_entry.push_back(pair_e[s]);
-                }
-            }
-        }
-        H = (int)seg_entry.size();
-
-        lap("segments");
-        /* Atom-sorted contribution buffer: atom k owns [atom_ptr[k], atom_ptr[k+1]); within a range
-         * the pair contributions (as j) come first in slot order, then the segments (as i). */
-        std::vector<int>&  atom_ptr = c->w_atom_ptr;
-        std::vector<int4>& seg_dst  = c->w_seg_dst;
-        atom_ptr.assign(nT + 1, 0);
-        seg_dst.resize(H);
-        for (int s = 0; s < P; s++)
-        {
-            atom_ptr[(pair_j[s] & 0x7fffffff) + 1]++;
-        }
-        for (int h = 0; h < H; h++)
-        {
-            atom_ptr[ent4[seg_entry[h]].x + 1]++;
-        }
-        for (int a = 0; a < nT; a++)
-        {
-            atom_ptr[a + 1] += atom_ptr[a];
-        }
-        {
-            std::vector<int>& fill = c->w_fill;
-            fill.assign(atom_ptr.begin(), atom_ptr.end() - 1);
-            for (int s = 0; s < P; s++)
-            {
-                pair4[s].w = fill[pair_j[s] & 0x7fffffff]++; /* the record carries the pair's scatter slot */
-            }
-            for (int h = 0; h < H; h++)
-            {
-                seg_dst[h] = make_int4(fill[ent4[seg_entry[h]].x]++, 0, 0, 0);
-            }
-        }
-
-        lap("atom-sorted slots");
-        /* segments sorted by shift vector (-> fshift_sorted) and by energy-group pair (-> ev2); the
-         * reduction jobs are chunks of those ranges */
-        key_job_ptr.assign(FEP_NUM_SHIFT + ngrp + 1, 0);
-        for (int kind = 0; kind < 2; kind++)
-        {
-            const int        nkeys = kind == 0 ? FEP_NUM_SHIFT : ngrp;
-            std::vector<int> cnt(nkeys + 1, 0);
-            for (int h = 0; h < H; h++)
-            {
-                const int4 e = ent4[seg_entry[h]];
-                cnt[(kind == 0 ? e.y : e.z) + 1]++;
-            }
-            for (int k = 0; k < nkeys; k++)
-            {
-                cnt[k + 1] += cnt[k];
-            }
-            std::vector<int> fill(cnt.begin(), cnt.end() - 1);
-            for (int h = 0; h < H; h++)
-            {
-                const int4 e   = ent4[seg_entry[h]];
-                const int  pos = fill[kind == 0 ? e.y : e.z]++;
-                if (kind == 0)
-                {
-                    seg_dst[h].y = pos;
-                }
-                else
-                {
-                    seg_dst[h].z = pos;
-                }
-            }
-            for (int k = 0; k < nkeys; k++)
-            {
-                key_job_ptr[(kind == 0 ? 0 : FEP_NUM_SHIFT) + k] = (int)jobs.size();
-                for (int b = cnt[k]; b < cnt[k + 1]; b += FEP_RED_CHUNK)
-                {
-                    RedJob j;
-                    j.begin = b;
-                    j.end   = std::min(cnt[k + 1], b + FEP_RED_CHUNK);
-                    j.key   = k;
-                    j.kind  = kind;
-                    jobs.push_back(j);
-                }
-            }
-            if (kind == 0)
-            {
-                c->ka.n_shift_jobs = (int)jobs.size();
-            }
-        }
-        key_job_ptr[FEP_NUM_SHIFT + ngrp] = (int)jobs.size();
-
-        lap("reduction jobs");
-        /* per-atom parameters in compact order */
-        std::vector<float4>& par4 = c->w_par4;
-        par4.resize(nT);
-        for (int k = 0; k < nT; k++)
-        {
-            const int a = c->touched[k];
-            par4[k]     = make_float4(c->qA[a], c->qB[a], int_bits_as_float(c->typeA[a]), int_bits_as_float(c->typeB[a]));
-        }
-
-        lap("atom parameters");
-        if ((rc = to_device(c, c->d_touched, c->touched)) || (rc = to_device(c, c->d_pair4, pair4))
-            || (rc = to_device(c, c->d_ent4, ent4))
-            || (rc = to_device(c, c->d_warp_hbase, warp_hbase)) || (rc = to_device(c, c->d_atom_ptr, atom_ptr))
-            || (rc = to_device(c, c->d_red_jobs, jobs))
-            || (rc = to_device(c, c->d_seg_dst, seg_dst)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr))
-            || (rc = to_device(c, c->d_par4, par4)))
-        {
-            return rc;
-        }
-    }
-    /* atoms with long contribution ranges get a whole warp in the epilogue (both builders leave
+    lap("device build");
+    /* atoms with long contribution ranges get a whole warp in the epilogue (the builder leaves
      * atom_ptr in w_atom_ptr) */
     c->heavy_atoms.clear();
     for (int a = 0; a < nT; a++)
@@ -1445,17 +1296,18 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     k.px          = PeerExchange{};
     k.n_pairs     = P;
     k.n_entries   = E;
-    k.n_segments  = H;
+    k.n_trips     = H;
     k.n_touched   = nT;
     k.n_gid       = ngrp;
-    k.n_cta       = (P + FEP_CTA - 1) / FEP_CTA;
     k.n_red_jobs  = (int)jobs.size();
     k.par4        = c->d_par4.ptr;
-    k.pair4       = c->d_pair4.ptr;
-    k.warp_hbase  = c->d_warp_hbase.ptr;
+    k.trip4       = c->d_trip4.ptr;
+    k.cjx         = c->d_cjx.ptr;
+    k.dst         = c->d_dst.ptr;
+    k.qj          = c->d_qj.ptr;
+    k.tj          = c->d_tj.ptr;
     k.fsorted       = c->d_fsorted.ptr;
     k.fshift_sorted = c->d_fshift_sorted.ptr;
-    k.seg_dst       = c->d_seg_dst.ptr;
     k.ev2         = c->d_ev2.ptr;
     k.job_part    = c->d_job_part.ptr;
     k.atom_ptr    = c->d_atom_ptr.ptr;
@@ -1474,7 +1326,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     l.nenergrp        = ngrp;
     l.nforeign        = (int)c->all_c.size();
     c->first_entry    = e0;
-    c->n_segments     = H;
+    c->n_trips        = H;
     c->have_list      = true;
     if ((rc = prepare_buffers(c)) != FEPB200_OK)
     {
@@ -1529,39 +1381,79 @@ int fepb200_get_list(const fepb200_ctx* cc, int* first_entry, int* iinr, int* gi
     }
     if (jindex || jjnr || excl_fep)
     {
-        std::vector<int>  pair_j(P), pair_e(P);
-        std::vector<int4> pair4(P);
-        if (P > 0)
+        /* jindex comes back from the raw copy the builder worked on; jjnr and excl_fep are RECONSTRUCTED from the
+         * trip layout the kernels evaluate (slot -> original pair), and every pair's trip must agree with its
+         * i-entry on (i atom, shift, gid): the read-back proves that the regrouping lost or changed nothing */
+        const int           NT = c->n_trips;
+        std::vector<int>    jraw((size_t)E + 1, 0), cjx(32 * (size_t)NT), orig(32 * (size_t)NT), tgid(NT);
+        std::vector<int4>   trip4(NT), ent4(E);
+        if (E > 0)
         {
-            CU_CHECK(c, cudaMemcpy(pair4.data(), c->d_pair4.ptr, P * sizeof(int4), cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(jraw.data(), c->d_raw_jindex.ptr + c->first_entry, ((size_t)E + 1) * sizeof(int),
+                                   cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(ent4.data(), c->d_ent4.ptr, E * sizeof(int4), cudaMemcpyDeviceToHost));
         }
-        for (int s = 0; s < P; s++)
+        if (NT > 0)
         {
-            pair_j[s] = pair4[s].x;
-            pair_e[s] = pair4[s].z;
+            CU_CHECK(c, cudaMemcpy(cjx.data(), c->d_cjx.ptr, cjx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(orig.data(), c->d_orig.ptr, orig.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(trip4.data(), c->d_trip4.ptr, NT * sizeof(int4), cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(tgid.data(), c->d_tgid.ptr, NT * sizeof(int), cudaMemcpyDeviceToHost));
         }
+        const int j0 = jraw[0];
         if (jindex)
         {
-            std::fill(jindex, jindex + E + 1, 0);
-            for (int s = 0; s < P; s++)
+            for (int n = 0; n <= E; n++)
             {
-                jindex[pair_e[s] + 1]++;
-            }
-            for (int n = 0; n < E; n++)
-            {
-                jindex[n + 1] += jindex[n];
+                jindex[n] = jraw[n] - j0;
             }
         }
-        for (int s = 0; s < P; s++)
+        std::vector<int>  entry_of(P);
+        for (int n = 0; n < E; n++)
         {
+            for (int k = jraw[n] - j0; k < jraw[n + 1] - j0; k++)
+            {
+                entry_of[k] = n;
+            }
+        }
+        std::vector<char> seen(P, 0);
+        long long         found = 0;
+        for (size_t slot = 0; slot < cjx.size(); slot++)
+        {
+            if (cjx[slot] & FEP_SLOT_PADDING)
+            {
+                continue;
+            }
+            const int  sidx  = orig[slot];
+            const int4 td    = trip4[slot >> 5];
+            const bool flip  = (td.x & FEP_TRIP_FLIPPED) != 0;
+            const int  owner = td.x & (FEP_MAX_TOUCHED - 1), other = cjx[slot] & (FEP_MAX_TOUCHED - 1);
+            const int  sh_e  = (td.x >> 24) & 63;
+            const int  ci = flip ? other : owner, cj = flip ? owner : other;
+            const int  sh = flip ? FEP_NUM_SHIFT - 1 - sh_e : sh_e;
+            if (sidx < 0 || sidx >= P || seen[sidx])
+            {
+                return fail(c, FEPB200_ERR_STATE, "list layout is inconsistent: slot %zu names pair %d", slot, sidx);
+            }
+            const int4 en = ent4[entry_of[sidx]];
+            if (en.x != ci || en.y != sh || en.z != tgid[slot >> 5])
+            {
+                return fail(c, FEPB200_ERR_STATE, "list layout is inconsistent: pair %d sits in a trip of another i-entry", sidx);
+            }
+            seen[sidx] = 1;
+            found++;
             if (jjnr)
             {
-                jjnr[s] = c->touched[pair_j[s] & 0x7fffffff];
+                jjnr[sidx] = c->touched[cj];
             }
             if (excl_fep)
             {
-                excl_fep[s] = pair_j[s] < 0 ? 0 : 1;
+                excl_fep[sidx] = cjx[slot] < 0 ? 0 : 1;
             }
+        }
+        if (found != P)
+        {
+            return fail(c, FEPB200_ERR_STATE, "list layout is inconsistent: %lld of %d pairs found", found, P);
         }
     }
     return FEPB200_OK;
@@ -2053,10 +1945,9 @@ size_t fepb200_exchange_bytes(const fepb200_ctx* c, int nranks)
     /* upper bound that does not depend on the launch geometry: at most one CTA per 128 pairs of a
      * rank's range, room for 32 lambda points (or the current number if larger) */
     auto            up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t    P       = (size_t)c->ka.n_pairs, H = (size_t)c->ka.n_segments;
-    const long long n_warps = ((long long)P + 31) / 32;
-    const long long wpr     = (n_warps + nranks - 1) / nranks;
-    const size_t    ctas    = (size_t)((wpr * 32 + 127) / 128 + 1);
+    const size_t    P       = (size_t)c->ka.n_pairs, H = (size_t)c->ka.n_trips;
+    const long long tpr     = ((long long)H + nranks - 1) / nranks;
+    const size_t    ctas    = (size_t)((tpr + 3) / 4 + 1);
     const size_t    np      = (size_t)std::max(c->layout.nforeign + 1, 32);
     const size_t    slot    = up((P + H) * sizeof(float4)) + up(H * sizeof(float4)) + up(H * sizeof(float2))
                         + up(2 * ctas * sizeof(double)) + up(3 * np * ctas * sizeof(double));
@@ -2081,7 +1972,7 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
     cudaSetDevice(c->device);
     close_chain(c);
     KernelArgs& k = c->ka;
-    const int   P = k.n_pairs, H = k.n_segments, nT = k.n_touched;
+    const int   P = k.n_pairs, H = k.n_trips, nT = k.n_touched;
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     if (nranks == 1)
     {
@@ -2103,13 +1994,11 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
             c->x_base[r] = static_cast<unsigned char*>(d_peer_bufs[r]);
         }
         c->x_bytes = bytes;
-        /* pairs: equal shares of the 32-pair warps of the flat pair space (an i-entry may straddle
-         * two ranks: its segments are separate contributions anyway) */
-        const long long n_warps = ((long long)P + 31) / 32;
-        const long long wpr     = (n_warps + nranks - 1) / nranks;
-        c->x_range_pairs        = (int)(wpr * 32);
-        c->x_pair_begin         = (int)std::min<long long>((long long)rank * wpr * 32, P);
-        c->x_pair_end           = (int)std::min<long long>((long long)(rank + 1) * wpr * 32, P);
+        /* pairs: equal shares of the trips (every trip is a contribution of its own to its owner atom) */
+        const long long tpr     = ((long long)H + nranks - 1) / nranks;
+        c->x_range_trips        = (int)tpr;
+        c->x_trip_begin         = (int)std::min<long long>((long long)rank * tpr, H);
+        c->x_trip_end           = (int)std::min<long long>((long long)(rank + 1) * tpr, H);
         /* atoms: contiguous ranges with equal shares of the force contributions */
         const std::vector<int>& atom_ptr = c->w_atom_ptr; /* kept by fepb200_set_list() */
         /* cost of an atom = its contributions + a fixed share for the lanes that serve it (a range
@@ -2139,9 +2028,8 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
         CU_CHECK(c, c->d_slot_src.reserve(std::max<size_t>((size_t)P + H, 1)));
         CU_CHECK(c, c->d_fshift_src.reserve(std::max(H, 1)));
         CU_CHECK(c, c->d_ev2_src.reserve(std::max(H, 1)));
-        const int err = fep_launch_source_tables(c->d_pair4.ptr, P, c->d_seg_dst.ptr, H, c->d_warp_hbase.ptr, (int)wpr,
-                                                 c->d_slot_src.ptr, c->d_fshift_src.ptr, c->d_ev2_src.ptr, c->stream,
-                                                 &c->launches);
+        const int err = fep_launch_source_tables(c->d_cjx.ptr, c->d_dst.ptr, c->d_trip4.ptr, H, (int)tpr, c->d_slot_src.ptr,
+                                                 c->d_fshift_src.ptr, c->d_ev2_src.ptr, c->stream, &c->launches);
         if (err != 0)
         {
             c->px_on = false;
@@ -2201,8 +2089,9 @@ int fepb200_peer_ranges(const fepb200_ctx* c, int* pair_begin, int* pair_end, in
     {
         return fail(const_cast<fepb200_ctx*>(c), FEPB200_ERR_STATE, "no list has been set");
     }
-    if (pair_begin) *pair_begin = c->px_on ? c->x_pair_begin : 0;
-    if (pair_end) *pair_end = c->px_on ? c->x_pair_end : c->ka.n_pairs;
+    /* the range of trips (32 pair slots each) this context evaluates */
+    if (pair_begin) *pair_begin = c->px_on ? c->x_trip_begin : 0;
+    if (pair_end) *pair_end = c->px_on ? c->x_trip_end : c->ka.n_trips;
     if (atom_begin) *atom_begin = c->px_on ? c->x_atom_begin : 0;
     if (atom_end) *atom_end = c->px_on ? c->x_atom_end : c->ka.n_touched;
     return FEPB200_OK;

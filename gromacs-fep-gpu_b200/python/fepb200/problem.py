@@ -76,15 +76,16 @@ class FepList:
         )
 
 
-    def slice_pairs(self, p0: int, p1: int) -> "FepList":
-        """Pairs [p0, p1) of the flat pair space as an independent list; an i-entry that straddles
-        a boundary is cut (the fused multi-GPU exchange splits by 32-pair warps, not by entries)."""
-        jindex = np.asarray(self.jindex, np.int64)
-        e0 = int(np.searchsorted(jindex, p0, side="right") - 1) if p1 > p0 else 0
-        e1 = int(np.searchsorted(jindex, p1, side="left")) if p1 > p0 else 0
-        ji = np.clip(jindex[e0 : e1 + 1], p0, p1) - p0
-        return FepList(self.iinr[e0:e1], self.gid[e0:e1], self.shift[e0:e1], ji.astype(self.jindex.dtype),
-                       self.jjnr[p0:p1], self.excl_fep[p0:p1])
+    def select_pairs(self, keep) -> "FepList":
+        """The pairs with keep[k] true as an independent list; entries keep their order and are cut where pairs
+        drop out, entries left without pairs disappear (the fused multi-GPU exchange splits the list by trips of
+        the device layout, which gather pairs from many i-entries)."""
+        keep = np.asarray(keep, bool)
+        ent = np.repeat(np.arange(self.nri), np.diff(np.asarray(self.jindex, np.int64)))
+        cnt = np.bincount(ent[keep], minlength=self.nri)
+        live = cnt > 0
+        jindex = np.concatenate([[0], np.cumsum(cnt[live])]).astype(self.jindex.dtype)
+        return FepList(self.iinr[live], self.gid[live], self.shift[live], jindex, self.jjnr[keep], self.excl_fep[keep])
 
 
 @dataclass

@@ -40,29 +40,65 @@ def touched_atoms(nblist) -> np.ndarray:
 PEER_ATOM_COST = 8  # the library's fixed share per atom when it balances the atom ranges
 
 
-def peer_pair_ranges(nrj: int, nranks: int) -> list[tuple[int, int]]:
-    """Rank r evaluates the pairs [begin, end) of the flat pair space: equal shares of its 32-pair warps."""
-    n_warps = (nrj + 31) // 32
-    wpr = (n_warps + nranks - 1) // nranks
-    return [(min(r * wpr * 32, nrj), min((r + 1) * wpr * 32, nrj)) for r in range(nranks)]
-
-
-def contribution_ranges(nblist) -> tuple[np.ndarray, np.ndarray]:
-    """(touched atoms, atom_ptr): atom k of the compact numbering owns the force contributions
-    [atom_ptr[k], atom_ptr[k+1]) of the atom-sorted buffer -- one per pair it is the j atom of, and
-    one per segment (maximal run of pairs of one i-entry inside one 32-pair warp) it is the i atom of."""
+def trip_layout(nblist, ngrp: int = 1) -> dict:
+    """Host-side mirror of the regrouping fepb200_set_list() does on the GPU (csrc/fep_list_build.cu): every pair is
+    given to its OWNER, the end that takes part in more pairs of the list (ties: the i atom); pairs are grouped by
+    (owner, energy-group pair, shift index, flipped = the owner was the j atom) with a stable sort, and every group is
+    cut into TRIPS of at most 32 pairs, the unit of work of one warp.  Returns
+      touched      compact -> atom
+      trip_of_pair trip of every pair of the list (list order)
+      n_trips
+      trip_owner, trip_gid, trip_shift, trip_flipped   per trip (shift = the index the list gave)
+      atom_ptr     atom k of the compact numbering owns the force contributions [atom_ptr[k], atom_ptr[k+1]) of the
+                   atom-sorted buffer: one per pair it is the partner of, one per trip it owns."""
     nrj = int(nblist.nrj)
     touched = touched_atoms(nblist)
+    nt = len(touched)
+    empty = np.zeros(0, np.int64)
     if nrj == 0:
-        return touched, np.zeros(len(touched) + 1, np.int64)
+        return dict(touched=touched, trip_of_pair=empty, n_trips=0, trip_owner=empty, trip_gid=empty, trip_shift=empty,
+                    trip_flipped=empty.astype(bool), atom_ptr=np.zeros(nt + 1, np.int64))
+    natoms = int(touched[-1]) + 1
+    compact = np.full(natoms, -1, np.int64)
+    compact[touched] = np.arange(nt)
     ent = np.repeat(np.arange(nblist.nri), np.diff(np.asarray(nblist.jindex, np.int64)))
-    warp = np.arange(nrj) // 32
-    head = np.ones(nrj, bool)
-    head[1:] = (ent[1:] != ent[:-1]) | (warp[1:] != warp[:-1])
-    natoms = int(max(np.max(nblist.iinr), np.max(nblist.jjnr))) + 1
-    cnt = np.bincount(np.asarray(nblist.jjnr, np.int64), minlength=natoms)
-    cnt = cnt + np.bincount(np.asarray(nblist.iinr, np.int64)[ent[head]], minlength=natoms)
-    return touched, np.concatenate([[0], np.cumsum(cnt[touched])]).astype(np.int64)
+    ci = compact[np.asarray(nblist.iinr, np.int64)[ent]]
+    cj = compact[np.asarray(nblist.jjnr, np.int64)]
+    deg = np.bincount(ci, minlength=nt) + np.bincount(cj, minlength=nt)
+    flip = deg[cj] > deg[ci]
+    owner = np.where(flip, cj, ci)
+    other = np.where(flip, ci, cj)
+    gid = np.asarray(nblist.gid, np.int64)[ent]
+    shift = np.asarray(nblist.shift, np.int64)[ent]
+    key = ((owner * ngrp + gid) * 64 + shift) * 2 + flip
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    gstart = np.zeros(nrj, np.int64)
+    heads = np.flatnonzero(np.concatenate([[True], ks[1:] != ks[:-1]]))
+    gstart[heads] = heads
+    gstart = np.maximum.accumulate(gstart)
+    trip_head = (np.arange(nrj) - gstart) % 32 == 0
+    trip_sorted = np.cumsum(trip_head) - 1
+    n_trips = int(trip_sorted[-1]) + 1
+    trip_of_pair = np.empty(nrj, np.int64)
+    trip_of_pair[order] = trip_sorted
+    first = order[trip_head]  # the pair that opens each trip
+    cnt = np.bincount(other, minlength=nt) + np.bincount(owner[first], minlength=nt)
+    return dict(touched=touched, trip_of_pair=trip_of_pair, n_trips=n_trips, trip_owner=owner[first], trip_gid=gid[first],
+                trip_shift=shift[first], trip_flipped=flip[first],
+                atom_ptr=np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64))
+
+
+def peer_trip_ranges(n_trips: int, nranks: int) -> list[tuple[int, int]]:
+    """Rank r evaluates the trips [begin, end): equal shares, the rule of fepb200_set_peer_exchange()."""
+    tpr = (n_trips + nranks - 1) // nranks
+    return [(min(r * tpr, n_trips), min((r + 1) * tpr, n_trips)) for r in range(nranks)]
+
+
+def contribution_ranges(nblist, ngrp: int = 1) -> tuple[np.ndarray, np.ndarray]:
+    """(touched atoms, atom_ptr) of trip_layout()."""
+    lay = trip_layout(nblist, ngrp)
+    return lay["touched"], lay["atom_ptr"]
 
 
 def peer_atom_ranges(atom_ptr, nranks: int) -> list[tuple[int, int]]:

@@ -293,7 +293,8 @@ int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_bl
  * off as well: call fepb200_set_peer_exchange() again after every search step. */
 size_t fepb200_exchange_bytes(const fepb200_ctx* ctx, int nranks);
 int    fepb200_set_peer_exchange(fepb200_ctx* ctx, int nranks, int rank, void* const* d_peer_bufs, size_t bytes);
-/* The pairs [pair_begin, pair_end) of the flat pair space this context evaluates and the compact
+/* The trips [pair_begin, pair_end) (groups of <= 32 pairs that share an owner atom, the unit of the device
+ * layout) this context evaluates and the compact
  * atoms [atom_begin, atom_end) (indices into fepb200_touched_atoms()) it owns; any pointer may be NULL. */
 int    fepb200_peer_ranges(const fepb200_ctx* ctx, int* pair_begin, int* pair_end, int* atom_begin, int* atom_end);
 

@@ -268,6 +268,18 @@ def test_layout_matches_host_mirror(ctx):
         assert getattr(lay, k) == getattr(mirror, k), k
 
 
+def test_device_layout_matches_its_host_side_mirror(ctx):
+    """Number of trips and every atom's share of the force contributions, device builder vs the numpy mirror."""
+    from fepb200.shard import peer_atom_ranges, trip_layout
+
+    for name in ("C4", "C2"):
+        prob = make_system(SMALL[name])
+        ctx.set_problem(prob)
+        lay = trip_layout(prob.nblist, prob.nenergrp_pairs)
+        t0, t1, a0, a1 = ctx.peer_ranges()
+        assert (t0, t1, a0, a1) == (0, lay["n_trips"], 0, len(lay["touched"]))
+
+
 def test_list_round_trip_is_bit_exact(ctx):
     prob = make_system(SMALL["C4"])
     ctx.set_problem(prob)
@@ -313,28 +325,31 @@ def test_shards_partition_the_list_bit_exactly_and_sum_to_the_whole(nranks):
 
 @pytest.mark.parametrize("name", ["C4", "C3", "C1"])
 @pytest.mark.parametrize("nranks", [1, 3])
-def test_device_and_host_list_builders_agree_bit_for_bit(name, nranks, monkeypatch):
-    """fepb200_set_list() builds the device layout with kernels, scans and stable sorts on the GPU
-    (default) or with loops on the host (FEPB200_SETLIST=host).  Both follow the same ordering
-    rules, so every result -- including the order of the floating-point additions -- is identical."""
+def test_device_list_builder_is_a_function_of_the_list_alone(name, nranks):
+    """fepb200_set_list() regroups the list into trips on the GPU with kernels, scans and stable sorts (the only
+    atomics are integer pair counts, whose result does not depend on their order).  Two independent builds of the
+    same shard therefore give the same layout and bit-identical results -- including the order of every
+    floating-point addition -- and the read-back, which is reconstructed from the trip layout and checks every
+    pair against its i-entry, returns the shard that was handed over."""
     from fepb200.lib import FepContext
+    from fepb200.shard import balanced_ranges
 
     prob = make_system(SMALL[name])
-    results = {}
-    for mode in ("device", "host"):
-        monkeypatch.setenv("FEPB200_SETLIST", mode)
+    ranges = balanced_ranges(prob.nblist.jindex, nranks)
+    results = []
+    for _ in range(2):
         outs = []
         for r in range(nranks):
             with FepContext(0) as c:
                 c.set_problem(prob, rank=r, nranks=nranks)
                 first, back = c.get_list()
+                _assert_lists_equal(back, prob.nblist.slice_entries(*ranges[r]))
                 lay = c.layout()
-                outs.append((first, back, (lay.ntouched, lay.nri, lay.nrj), c.touched_atoms().copy(),
+                outs.append((first, (lay.ntouched, lay.nri, lay.nrj), c.touched_atoms().copy(),
                              c.compute(prob.x, prob.shiftvec, ALL)))
-        results[mode] = outs
-    for (fa, la, sa, ta, oa), (fb, lb, sb, tb, ob) in zip(results["device"], results["host"]):
+        results.append(outs)
+    for (fa, sa, ta, oa), (fb, sb, tb, ob) in zip(*results):
         assert fa == fb and sa == sb
-        _assert_lists_equal(la, lb)
         assert np.array_equal(ta, tb)
         for k in oa:
             assert np.array_equal(oa[k], ob[k]), k

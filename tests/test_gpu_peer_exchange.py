@@ -74,8 +74,10 @@ def test_ranks_on_one_device_reproduce_the_single_context_result(kind, nranks):
     prob = _problem(kind)
     one = _single(prob, ALL)
     outs, ranges, touched = _run_ranks(prob, nranks, ALL, steps=3)
-    # the ranges are partitions of the pairs and of the touched atoms
-    assert ranges[0][0] == 0 and ranges[-1][1] == prob.nblist.nrj
+    # the ranges are partitions of the trips (the mirror of the device layout tells how many) and of the touched atoms
+    from fepb200.shard import trip_layout
+
+    assert ranges[0][0] == 0 and ranges[-1][1] == trip_layout(prob.nblist, prob.nenergrp_pairs)["n_trips"]
     assert ranges[0][2] == 0 and ranges[-1][3] == len(touched[0])
     for a, b in zip(ranges, ranges[1:]):
         assert a[1] == b[0] and a[3] == b[2]

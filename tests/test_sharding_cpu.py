@@ -107,44 +107,59 @@ def test_sharded_reduction_matches_full_list_gloo(world, tmp_path):
 
 
 # ---- the fused peer exchange (fepb200_set_peer_exchange): host-side mirror of its split ----------
-def test_peer_ranges_are_partitions():
-    from fepb200.shard import contribution_ranges, peer_atom_ranges, peer_pair_ranges
+def test_trip_layout_and_peer_ranges_are_partitions():
+    from fepb200.shard import peer_atom_ranges, peer_trip_ranges, trip_layout
 
     prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=2))
     nb = prob.nblist
-    touched, atom_ptr = contribution_ranges(nb)
+    lay = trip_layout(nb, prob.nenergrp_pairs)
+    touched, atom_ptr = lay["touched"], lay["atom_ptr"]
     assert np.array_equal(touched, touched_atoms(nb)) and atom_ptr[0] == 0
     assert np.all(np.diff(atom_ptr) > 0)  # every touched atom receives at least one contribution
+    assert atom_ptr[-1] == nb.nrj + lay["n_trips"]  # one per pair (partner) + one per trip (owner)
+    # every pair sits in exactly one trip of at most 32 pairs, and a trip is uniform in (owner, gid, shift, side)
+    top = lay["trip_of_pair"]
+    sizes = np.bincount(top, minlength=lay["n_trips"])
+    assert sizes.min() >= 1 and sizes.max() <= 32
+    ent = np.repeat(np.arange(nb.nri), np.diff(nb.jindex))
+    compact = np.full(prob.natoms, -1)
+    compact[touched] = np.arange(len(touched))
+    ci, cj = compact[nb.iinr[ent]], compact[nb.jjnr]
+    own = lay["trip_owner"][top]
+    flipped = lay["trip_flipped"][top]
+    assert np.all(np.where(flipped, cj, ci) == own)
+    assert np.array_equal(nb.gid[ent], lay["trip_gid"][top]) and np.array_equal(nb.shift[ent], lay["trip_shift"][top])
+    # the regrouping pays: far fewer trips than the i-entry-major layout has runs, and they are nearly full
+    assert lay["n_trips"] < 1.35 * nb.nrj / 32 + 8 * prob.nenergrp_pairs
     for n in (1, 2, 3, 8):
-        pr = peer_pair_ranges(nb.nrj, n)
-        assert pr[0][0] == 0 and pr[-1][1] == nb.nrj and all(a[1] == b[0] for a, b in zip(pr, pr[1:]))
-        assert all(a % 32 == 0 for a, _ in pr)  # warps of the flat pair space are never cut
-        assert max(b - a for a, b in pr) - min(b - a for a, b in pr[:-1] or pr) <= 32 * n
+        pr = peer_trip_ranges(lay["n_trips"], n)
+        assert pr[0][0] == 0 and pr[-1][1] == lay["n_trips"] and all(a[1] == b[0] for a, b in zip(pr, pr[1:]))
+        assert max(b - a for a, b in pr) - min(b - a for a, b in pr[:-1] or pr) <= n
         ar = peer_atom_ranges(atom_ptr, n)
         assert ar[0][0] == 0 and ar[-1][1] == len(touched) and all(a[1] == b[0] for a, b in zip(ar, ar[1:]))
         cost = [atom_ptr[b] - atom_ptr[a] + 8 * (b - a) for a, b in ar]
         heaviest = int(np.max(np.diff(atom_ptr))) + 8
         assert max(cost) - min(cost) <= 2 * heaviest  # balanced up to one atom at either end
     # degenerate inputs
-    assert peer_pair_ranges(0, 4) == [(0, 0)] * 4
-    assert peer_pair_ranges(40, 4) == [(0, 32), (32, 40), (40, 40), (40, 40)]
-    assert peer_atom_ranges(np.array([0]), 3) == [(0, 0)] * 3
+    assert peer_trip_ranges(0, 4) == [(0, 0)] * 4
+    assert peer_trip_ranges(5, 4) == [(0, 2), (2, 4), (4, 5), (5, 5)]
 
 
-def test_slice_pairs_cuts_entries_and_reassembles():
+def test_select_pairs_keeps_order_and_reassembles():
     prob = make_system(scaled_spec("C2", 3.2, 1, 20, n_foreign=1))
     nb = prob.nblist
-    cuts = [0, 32, 96, nb.nrj // 2 // 32 * 32, nb.nrj]
-    jj, ex, ii = [], [], []
-    for a, b in zip(cuts, cuts[1:]):
-        s = nb.slice_pairs(a, b)
-        assert s.nrj == b - a and np.all(np.diff(s.jindex) > 0)
-        jj.append(s.jjnr)
-        ex.append(s.excl_fep)
-        ii.append(np.repeat(s.iinr, np.diff(s.jindex)))
-    assert np.array_equal(np.concatenate(jj), nb.jjnr) and np.array_equal(np.concatenate(ex), nb.excl_fep)
-    assert np.array_equal(np.concatenate(ii), np.repeat(nb.iinr, np.diff(nb.jindex)))
-    assert nb.slice_pairs(64, 64).nri == 0
+    rng = np.random.default_rng(3)
+    part = rng.integers(0, 3, nb.nrj)
+    ent = np.repeat(np.arange(nb.nri), np.diff(nb.jindex))
+    seen = np.zeros(nb.nrj, int)
+    for r in range(3):
+        s = nb.select_pairs(part == r)
+        assert s.nrj == int(np.sum(part == r)) and np.all(np.diff(s.jindex) > 0)
+        assert np.array_equal(s.jjnr, nb.jjnr[part == r]) and np.array_equal(s.excl_fep, nb.excl_fep[part == r])
+        assert np.array_equal(np.repeat(s.iinr, np.diff(s.jindex)), nb.iinr[ent[part == r]])
+        seen[part == r] += 1
+    assert np.all(seen == 1)
+    assert nb.select_pairs(np.zeros(nb.nrj, bool)).nri == 0
 
 
 def _fused_worker(rank, world, port, root, result_file):
@@ -156,18 +171,19 @@ def _fused_worker(rank, world, port, root, result_file):
             sys.path.insert(0, p)
     import copy
 
-    from fepb200.shard import contribution_ranges, peer_atom_ranges, peer_pair_ranges
+    from fepb200.shard import peer_atom_ranges, peer_trip_ranges, trip_layout
     from oracle import oracle
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=3))
-    touched, atom_ptr = contribution_ranges(prob.nblist)
-    p0, p1 = peer_pair_ranges(prob.nblist.nrj, world)[rank]
+    lay = trip_layout(prob.nblist, prob.nenergrp_pairs)
+    touched, atom_ptr = lay["touched"], lay["atom_ptr"]
+    t0, t1 = peer_trip_ranges(lay["n_trips"], world)[rank]
     a0, a1 = peer_atom_ranges(atom_ptr, world)[rank]
     shard = copy.copy(prob)
-    shard.nblist = prob.nblist.slice_pairs(p0, p1)
+    shard.nblist = prob.nblist.select_pairs((lay["trip_of_pair"] >= t0) & (lay["trip_of_pair"] < t1))
     mine = oracle.run_port(shard, ALL)
     want = oracle.run_port(prob, ALL)
     # forces: contributions of every rank to the atoms this rank owns
