@@ -55,7 +55,8 @@ struct BeutlerStep
     float lfc[2][FEP_FB_MAXC];  /* {1-lambda_c, lambda_c}                   */
     float lfv[2][FEP_FB_MAXC];
     int   p0, np;               /* first point of the chunk, valid points   */
-    int   want_shift;           /* also store segment forces sorted by shift vector */
+    int   want_shift;           /* also store the trips' forces sorted by shift vector */
+    int   per_trip_energy;      /* more than one energy-group pair: Vc/Vv per trip instead of per CTA */
     int   tile_trips, n_tiles;  /* tile of trips of one CTA for this launch */
     int   always_check;         /* a lambda outside [0,1]: no fast path     */
 };
@@ -257,12 +258,12 @@ struct AccLayout
 {
     static constexpr int NPER = (MODE == 0) ? 2 : 4; /* per-point: V_A DV (Cp_A DCp)                */
     static constexpr int NFOR = C > 0 ? NPER * C + 4 : 0; /* + C_A DC G_A DG                         */
-    static constexpr int NACC = NFOR + (FORCE ? 2 : 0);  /* + dV/dlambda coul, vdw at current lambda */
+    static constexpr int NACC = NFOR + (FORCE ? 4 : 0);  /* + dV/dlambda coul, vdw, Vc, Vv at current lambda */
     static constexpr int N8   = (NACC + 7) / 8;
     static constexpr int iCA = NPER * C, iDC = iCA + 1, iGA = iCA + 2, iDG = iCA + 3;
     static constexpr int iCUR = NFOR;
     /* register budget: 4 CTAs of 128 threads per SM up to ~56 accumulators, else 2 */
-    static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : (NACC > 30 ? 3 : 4);
+    static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : (NACC > 30 ? 3 : (NACC > 8 ? 4 : 8));
 };
 
 /* sum of v over the warp, valid in every lane */
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     constexpr int NW   = FEP_FB_CTA / 32;
     __shared__ float  s_red[NW][N8 * 8];
     __shared__ double s_sum[N8 * 8];
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(8) unsigned long long s_bars[FEP_STAGE_CHUNKS];
     /* the 45 shift vectors are read once per trip with a data-dependent index: keep them on chip */
     __shared__ float4 s_shift[FEP_NUM_SHIFT];
 
@@ -296,17 +297,18 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     const int warp = tid >> 5;
     fep_pdl_launch_dependents(); /* the next kernel of the step may fill SM space we leave free */
 
-    /* this CTA's tile of trips: one round of bulk copies brings its records into shared memory */
-    const int     t0   = ka.trip_begin + blockIdx.x * bs.tile_trips;
-    const int     nt   = min(bs.tile_trips, ka.trip_end - t0);
-    const FepTile tile = fep_stage_tile<STAGED, FORCE>(ka, t0, nt, bs.tile_trips, fep_dyn_smem, &s_bar);
+    /* this CTA's tile of trips: bulk copies bring its records into shared memory */
+    const int           t0    = ka.trip_begin + blockIdx.x * bs.tile_trips;
+    const int           nt    = min(bs.tile_trips, ka.trip_end - t0);
+    const FepStage      stage = fep_stage_tile<STAGED>(ka, t0, nt, NW, fep_dyn_smem, s_bars);
+    const unsigned int* tile  = stage.tile;
     if (tid < FEP_NUM_SHIFT)
     {
         s_shift[tid] = ka.dyn->shiftvec[tid];
     }
 
     /* Layout: [0,C) V_A, [C,2C) DV, MODE>0: [2C,3C) Cp_A, [3C,4C) DCp, then C_A DC G_A DG,
-     * then (FORCE) dV/dlambda_coul, dV/dlambda_vdw of the current-lambda pass. */
+     * then (FORCE) dV/dlambda_coul, dV/dlambda_vdw, Vc, Vv of the current-lambda pass. */
     float acc[N8 * 8];
 #pragma unroll
     for (int i = 0; i < N8 * 8; i++)
@@ -315,34 +317,35 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     }
     const float thr_v = ka.vdw_ewald ? __int_as_float(0x7f800000) : ka.rvdw6; /* LJ-PME tests r, below */
     __syncthreads();
-    fep_tile_wait<STAGED>(&s_bar);
 
     /* warp w takes the trips w, w + NW, ... of the tile; while trip k is evaluated the coordinates and
-     * owner data of trip k + NW are in flight */
+     * type-table rows of trip k + NW are in flight */
     FepFetch nx;
     if (warp < nt)
     {
-        nx = fep_fetch<STAGED>(ka, tile, warp, lane);
+        fep_stage_wait<STAGED>(stage, s_bars, warp, NW, ka.fault);
+        nx = fep_fetch<STAGED>(ka, tile + warp * FEP_TRIP_WORDS, lane);
     }
     for (int lt = warp; lt < nt; lt += NW)
     {
-        const FepFetch cur = nx;
+        const unsigned int* tb  = tile + lt * FEP_TRIP_WORDS;
+        const FepFetch      cur = nx;
         if (lt + NW < nt)
         {
-            nx = fep_fetch<STAGED>(ka, tile, lt + NW, lane);
+            fep_stage_wait<STAGED>(stage, s_bars, lt + NW, NW, ka.fault);
+            nx = fep_fetch<STAGED>(ka, tb + NW * FEP_TRIP_WORDS, lane);
         }
-        const FepSlot p = fep_slot<STAGED>(ka, tile, cur, lt, lane, s_shift);
+        FepSlot p = fep_slot<STAGED>(ka, tb, cur, lane, s_shift);
+        /* a padding slot is "a pair far beyond every cut-off": all of its terms vanish below without masks */
+        p.r2 = p.active ? p.r2 : 1.0e6f;
 
-        float fx = 0.0f, fy = 0.0f, fz = 0.0f, vctot = 0.0f, vvtot = 0.0f;
-
-        if (__any_sync(FULL_MASK, p.contrib))
+        float nfx, nfy, nfz, vctot = 0.0f, vvtot = 0.0f; /* nf = MINUS the force on the owner = force on the partner */
         {
-            const float4 ta = p.ta, tb = p.tb;
-            const float  m      = p.contrib ? 1.0f : 0.0f;
+            const float4 ta = p.ta, tb4 = p.tb;
             const float  qq[2]  = { p.qq[0], p.qq[1] };
-            const float  c6[2]  = { ta.x, tb.x }, c12[2] = { ta.y, tb.y }, sig6[2] = { ta.z, tb.z };
-            const float  c6g[2] = { ta.w * m, tb.w * m };
-            const bool   hard   = (ta.y > 0.0f && tb.y > 0.0f); /* :597-628 */
+            const float  c6[2]  = { ta.x, tb4.x }, c12[2] = { ta.y, tb4.y }, sig6[2] = { ta.z, tb4.z };
+            const float  c6g[2] = { ta.w, tb4.w };
+            const bool   hard   = (ta.y > 0.0f && tb4.y > 0.0f); /* :597-628 */
             const float  a_v    = hard ? 0.0f : ka.alpha_v;
             const float  a_c    = hard ? 0.0f : ka.alpha_c;
 
@@ -357,7 +360,8 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 
             float fscal = 0.0f, dcur_c = 0.0f, dcur_v = 0.0f;
 
-            /* lambda-independent correction terms, linear in qq[s] / c6grid[s] */
+            /* lambda-independent correction terms, linear in qq[s] / c6grid[s]; zero beyond the cut-offs
+             * unless the pair is an exclusion (:1023-1136) */
             {
                 float xc, fcorr, xv, fvcorr;
                 fep_corrections<EWALD, FORCE>(ka, pr, p.excluded, p.self, xc, fcorr, xv, fvcorr);
@@ -385,10 +389,11 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
 #pragma unroll
             for (int s = 0; s < 2; s++)
             {
-                const bool nz = incl && (qq[s] != 0.0f || c6[s] != 0.0f || c12[s] != 0.0f); /* :747-752 */
-                /* lambda-independent parts of the interaction tests (:805-812, :880-890) */
-                elec_on[s] = nz && qq[s] != 0.0f;
-                vdw_on[s]  = nz && (c6[s] != 0.0f || c12[s] != 0.0f);
+                /* the state takes part if any of qq, c6, c12 is non-zero (:747-752), which each of the two
+                 * tests below implies; then the lambda-independent parts of the interaction tests (:805-812,
+                 * :880-890) */
+                elec_on[s] = incl && qq[s] != 0.0f;
+                vdw_on[s]  = incl && (c6[s] != 0.0f || c12[s] != 0.0f);
                 if (EWALD || MODE == 0)
                 {
                     elec_on[s] = elec_on[s] && pr.r < ka.rcoulomb;
@@ -434,16 +439,12 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
                     fb_force_state<EWALD, MODE>(st[1], bs, 1, r2, r6, r4, pr.rinv, thr_v, ka.rcoulomb6, ka.krf, ka.crf,
                                                 ka.sh_ewald, fscal, vctot, vvtot, dcur_c, dcur_v);
                 }
-                /* lanes without a contributing pair carry zero coefficients; the select keeps a stray
-                 * inf * 0 of a padding slot out of the trip sums */
-                fscal = p.contrib ? fscal : 0.0f;
-                fx    = fscal * p.dx;
-                fy    = fscal * p.dy;
-                fz    = fscal * p.dz;
-                vctot = p.contrib ? vctot : 0.0f;
-                vvtot = p.contrib ? vvtot : 0.0f;
-                acc[L::iCUR]     += p.contrib ? dcur_c : 0.0f;
-                acc[L::iCUR + 1] += p.contrib ? dcur_v : 0.0f;
+                const float nfs = -fscal;
+                nfx             = nfs * p.dx;
+                nfy             = nfs * p.dy;
+                nfz             = nfs * p.dz;
+                acc[L::iCUR]     += dcur_c;
+                acc[L::iCUR + 1] += dcur_v;
             }
 
             if (C > 0)
@@ -524,27 +525,37 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
             {
                 /* the partner receives -f: scattered to this pair's own slot in the atom-sorted
                  * buffer (unique destination, no atomics; skipped pairs write their zero) */
-                const int d = STAGED ? tile.dst[32 * lt + lane] : __ldg(tile.dst + 32 * lt + lane);
-                ka.fsorted[d] = make_float4(-fx, -fy, -fz, 0.0f);
+                ka.fsorted[fep_tw<STAGED>(tb + FEP_TW_DST + lane)] = make_float4(nfx, nfy, nfz, 0.0f);
             }
-            /* the owner receives the sum over the trip; the trip's Vc/Vv go to its energy-group pair */
-            fx    = fb_warp_sum(fx);
-            fy    = fb_warp_sum(fy);
-            fz    = fb_warp_sum(fz);
-            vctot = fb_warp_sum(vctot);
-            vvtot = fb_warp_sum(vvtot);
+            /* the owner receives the sum over the trip */
+            nfx = fb_warp_sum(nfx);
+            nfy = fb_warp_sum(nfy);
+            nfz = fb_warp_sum(nfz);
+            if (bs.per_trip_energy)
+            {
+                /* several energy-group pairs: the trip's Vc/Vv go to the trip's pair */
+                vctot = fb_warp_sum(vctot);
+                vvtot = fb_warp_sum(vvtot);
+            }
+            else
+            {
+                acc[L::iCUR + 2] += vctot;
+                acc[L::iCUR + 3] += vvtot;
+            }
             if (lane == 0)
             {
-                const int4 td    = STAGED ? tile.trip4[lt] : __ldg(tile.trip4 + lt);
-                ka.fsorted[td.y] = make_float4(fx, fy, fz, 0.0f);
+                ka.fsorted[fep_tw<STAGED>(tb + FEP_TH_SLOT_F)] = make_float4(-nfx, -nfy, -nfz, 0.0f);
                 if (bs.want_shift)
                 {
                     /* nb_free_energy.cpp:1153-1164 adds the i atom's force to the entry's shift vector; for
                      * a flipped trip the owner was the j atom, whose force is minus that */
-                    const float sg = (td.x & FEP_TRIP_FLIPPED) ? -1.0f : 1.0f;
-                    ka.fshift_sorted[td.z] = make_float4(sg * fx, sg * fy, sg * fz, 0.0f);
+                    const float sg = (cur.head & FEP_TRIP_FLIPPED) ? 1.0f : -1.0f;
+                    ka.fshift_sorted[fep_tw<STAGED>(tb + FEP_TH_SLOT_SHIFT)] = make_float4(sg * nfx, sg * nfy, sg * nfz, 0.0f);
                 }
-                ka.ev2[td.w] = make_float2(vctot, vvtot);
+                if (bs.per_trip_energy)
+                {
+                    ka.ev2[fep_tw<STAGED>(tb + FEP_TH_SLOT_EV)] = make_float2(vctot, vvtot);
+                }
             }
         }
     }
@@ -577,8 +588,9 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
         s_sum[tid] = s;
     }
     __syncthreads();
-    if (FORCE && tid < 2)
+    if (FORCE && tid < 4)
     {
+        /* rows: dV/dlambda coul, vdw; Vc, Vv (the latter two only meaningful with one energy-group pair) */
         ka.cta_part[(size_t)tid * bs.n_tiles + blockIdx.x] = s_sum[L::iCUR + tid];
     }
     if (C > 0 && tid < bs.np)
@@ -623,8 +635,17 @@ static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t
     }
     if (fb_staged())
     {
-        fep_launch_kernel_smem(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, dim3(bs.n_tiles), dim3(FEP_FB_CTA),
-                               fep_tile_bytes(bs.tile_trips, FORCE), stream, chained, ka, bs);
+        /* tiles beyond the default 48 kB of dynamic shared memory need the opt-in, once per instantiation and size */
+        static size_t allowed = 48 * 1024 - 4096;
+        const size_t  smem    = fep_tile_bytes(bs.tile_trips);
+        if (smem > allowed)
+        {
+            cudaFuncSetAttribute(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+            allowed = smem;
+        }
+        fep_launch_kernel_smem(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), smem,
+                               stream, chained, ka, bs);
     }
     else
     {
@@ -733,6 +754,7 @@ extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mod
         bs.cur_scdlv[s] = cur->scdl_v[s];
     }
     bs.want_shift   = want_shift;
+    bs.per_trip_energy = ka.n_gid > 1 ? 1 : 0;
     /* the fast path of the point loop assumes 0 <= soft-core lambda factor <= 1 */
     bs.always_check = 0;
     for (int q = 0; q < np; q++)

@@ -4,11 +4,12 @@
  *
  *   - A CTA owns a contiguous tile of trips.  The per-slot records of the tile (partner index, scatter
  *     destination, partner charges, partner types) and the trip records are contiguous in global
- *     memory, so the whole tile is brought into shared memory by at most five bulk copies
- *     (cp.async.bulk, completion on an mbarrier) issued by one thread before anything else happens:
+ *     memory (one block of FEP_TRIP_WORDS words per trip), so the whole tile is brought into shared
+ *     memory by ONE bulk copy (cp.async.bulk, completion on an mbarrier) issued by one thread before anything else happens:
  *     the list stream costs no registers, no address arithmetic and no load instructions in the loop.
- *   - Per trip the warp-uniform data (owner coordinates + shift vector, owner charges, owner rows of
- *     the type table) replace what the reference sets up per i-entry (nb_free_energy.cpp:466-503).
+ *   - Per trip the warp-uniform data (owner coordinates + shift vector; owner charges and owner rows of
+ *     the type table, pre-gathered into the trip's header) replace what the reference sets up per
+ *     i-entry (nb_free_energy.cpp:466-503).
  *   - The only dependent per-pair load is the partner's coordinates; it is issued one trip ahead.
  */
 #ifndef FEPB200_FEP_FRONT_CUH
@@ -39,111 +40,146 @@ __device__ __forceinline__ void fep_bulk_g2s(void* smem_dst, const void* gmem_sr
                  "l"(gmem_src), "r"(bytes), "r"(fep_smem_addr(bar))
                  : "memory");
 }
-__device__ __forceinline__ void fep_mbar_wait(unsigned long long* bar, unsigned parity)
+/* try_wait suspends the thread for a hardware-chosen time slice; a copy that has not landed after 2 s of
+ * them is not coming (bad source range): say so and trap instead of hanging the GPU */
+__device__ __forceinline__ bool fep_mbar_try_wait(unsigned long long* bar, unsigned parity)
 {
+    unsigned ok;
     asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "FEP_WAIT_%=:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra FEP_DONE_%=;\n"
-            "bra FEP_WAIT_%=;\n"
-            "FEP_DONE_%=:\n"
-            "}\n" ::"r"(fep_smem_addr(bar)),
-            "r"(parity)
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(fep_smem_addr(bar)), "r"(parity)
             : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fep_mbar_wait(unsigned long long* bar, unsigned parity, unsigned int* fault)
+{
+    if (fep_mbar_try_wait(bar, parity))
+    {
+        return;
+    }
+    unsigned long long t0 = 0;
+    for (unsigned spins = 1; !fep_mbar_try_wait(bar, parity); spins++)
+    {
+        if ((spins & 255u) == 0u)
+        {
+            const unsigned long long now = fep_globaltimer();
+            if (t0 == 0)
+            {
+                t0 = now;
+            }
+            else if (now - t0 > 2000000000ull)
+            {
+                fep_fault(fault, FEP_FAULT_STAGE_TIMEOUT, blockIdx.x, threadIdx.x, parity);
+            }
+        }
+    }
 }
 
 /* ---- the tile of one CTA in shared memory ------------------------------------------------------- */
-/* dynamic shared memory: [trip4: tt int4][cjx: 32 tt int][qj: 32 tt float2][tj: 32 tt int]([dst: 32 tt int]) */
-struct FepTile
+/* trip blocks (fep_types.h) are contiguous: a tile of nt trips is one copy of nt * FEP_TRIP_WORDS words */
+__host__ __device__ __forceinline__ size_t fep_tile_bytes(int tile_trips)
 {
-    const int4*   trip4;
-    const int*    cjx;
-    const float2* qj;
-    const int*    tj;
-    const int*    dst;
+    return (size_t)tile_trips * FEP_TRIP_WORDS * sizeof(unsigned int);
+}
+
+/* The tile arrives in up to FEP_STAGE_CHUNKS pieces, each a whole number of rounds (a round = one trip per
+ * warp of the CTA), each with its own mbarrier: the first round can start as soon as the first piece is in
+ * shared memory while the rest of the tile is still on its way. */
+#define FEP_STAGE_CHUNKS 8
+
+struct FepStage
+{
+    const unsigned int* tile;        /* first word of the tile (shared memory, or global when not staged) */
+    int                 chunk_trips; /* trips per piece */
 };
 
-__host__ __device__ __forceinline__ size_t fep_tile_bytes(int tile_trips, bool with_dst)
-{
-    return (size_t)tile_trips * (sizeof(int4) + 32 * (sizeof(int) + sizeof(float2) + sizeof(int) + (with_dst ? sizeof(int) : 0)));
-}
-
 /* Stages trips [t0, t0 + nt) (nt >= 1).  STAGED = false is the A/B variant without shared memory: the
- * "tile" then points at global memory (profiles/: staged vs direct).  `bar` and `smem` are the CTA's
- * mbarrier and dynamic shared memory; every thread of the CTA must call this. */
-template<bool STAGED, bool WITH_DST>
-__device__ __forceinline__ FepTile fep_stage_tile(const KernelArgs& ka, int t0, int nt, int tile_trips, unsigned char* smem,
-                                                  unsigned long long* bar)
+ * "tile" then points at global memory (profiles/: staged vs direct).  `bars` (FEP_STAGE_CHUNKS mbarriers)
+ * and `smem` are the CTA's; every thread of the CTA must call this, then __syncthreads() (which publishes
+ * the barriers' initialisation); a warp calls fep_stage_wait() before the first trip of every piece. */
+template<bool STAGED>
+__device__ __forceinline__ FepStage fep_stage_tile(const KernelArgs& ka, int t0, int nt, int warps, unsigned char* smem,
+                                                   unsigned long long* bars)
 {
-    FepTile t;
+    FepStage            st;
+    const unsigned int* src = ka.trips + (size_t)t0 * FEP_TRIP_WORDS;
+    const int           rounds = (nt + warps - 1) / warps;
+    st.chunk_trips             = warps * ((rounds + FEP_STAGE_CHUNKS - 1) / FEP_STAGE_CHUNKS);
     if (!STAGED)
     {
-        t.trip4 = ka.trip4 + t0;
-        t.cjx   = ka.cjx + 32 * (size_t)t0;
-        t.qj    = ka.qj + 32 * (size_t)t0;
-        t.tj    = ka.tj + 32 * (size_t)t0;
-        t.dst   = ka.dst + 32 * (size_t)t0;
-        return t;
+        st.tile = src;
+        return st;
     }
-    int4*   s_trip4 = reinterpret_cast<int4*>(smem);
-    int*    s_cjx   = reinterpret_cast<int*>(s_trip4 + tile_trips);
-    float2* s_qj    = reinterpret_cast<float2*>(s_cjx + 32 * tile_trips);
-    int*    s_tj    = reinterpret_cast<int*>(s_qj + 32 * tile_trips);
-    int*    s_dst   = s_tj + 32 * tile_trips;
     if (threadIdx.x == 0)
     {
-        fep_mbar_init(bar, 1);
-        const unsigned n4 = (unsigned)nt * 32u * 4u, n8 = 2u * n4, n16 = (unsigned)nt * 16u;
-        fep_mbar_expect_tx(bar, n16 + 2u * n4 + n8 + (WITH_DST ? n4 : 0u));
-        fep_bulk_g2s(s_trip4, ka.trip4 + t0, n16, bar);
-        fep_bulk_g2s(s_cjx, ka.cjx + 32 * (size_t)t0, n4, bar);
-        fep_bulk_g2s(s_qj, ka.qj + 32 * (size_t)t0, n8, bar);
-        fep_bulk_g2s(s_tj, ka.tj + 32 * (size_t)t0, n4, bar);
-        if (WITH_DST)
+        for (int c = 0; c < FEP_STAGE_CHUNKS; c++)
         {
-            fep_bulk_g2s(s_dst, ka.dst + 32 * (size_t)t0, n4, bar);
+            fep_mbar_init(bars + c, 1);
+        }
+        for (int c = 0, b = 0; b < nt; c++, b += st.chunk_trips)
+        {
+            const unsigned bytes = (unsigned)min(st.chunk_trips, nt - b) * FEP_TRIP_WORDS * 4u;
+            fep_mbar_expect_tx(bars + c, bytes);
+            fep_bulk_g2s(smem + (size_t)b * FEP_TRIP_WORDS * 4u, src + (size_t)b * FEP_TRIP_WORDS, bytes, bars + c);
         }
     }
-    t.trip4 = s_trip4;
-    t.cjx   = s_cjx;
-    t.qj    = s_qj;
-    t.tj    = s_tj;
-    t.dst   = s_dst;
-    return t;
+    st.tile = reinterpret_cast<const unsigned int*>(smem);
+    return st;
 }
 
-/* call after fep_stage_tile() and a __syncthreads() that makes the barrier's initialisation visible */
+/* before local trip lt is read: waits for its piece when lt is the warp's first trip in it */
 template<bool STAGED>
-__device__ __forceinline__ void fep_tile_wait(unsigned long long* bar)
+__device__ __forceinline__ void fep_stage_wait(const FepStage& st, unsigned long long* bars, int lt, int warps,
+                                               unsigned int* fault)
 {
     if (STAGED)
     {
-        fep_mbar_wait(bar, 0);
+        const int c = lt / st.chunk_trips;
+        if (lt - c * st.chunk_trips < warps)
+        {
+            fep_mbar_wait(bars + c, 0, fault);
+        }
     }
 }
 
+template<bool STAGED>
+__device__ __forceinline__ unsigned int fep_tw(const unsigned int* p)
+{
+    return STAGED ? *p : __ldg(p);
+}
+
 /* ---- per trip / per slot ------------------------------------------------------------------------ */
-/* what a lane has in flight for the NEXT trip: its record and the three dependent gathers */
+/* what a lane has in flight for the NEXT trip: its record and the two dependent gathers */
 struct FepFetch
 {
-    int    td_x;   /* trip4.x */
-    int    cjx;
-    float3 xo, xj; /* owner and partner coordinates */
-    float4 po;     /* owner parameters */
+    unsigned int head; /* owner | shift_eff << 24 | flipped << 30 */
+    unsigned int cjx;
+    float3       xo, xj; /* owner and partner coordinates */
+    float4       ta, tb; /* type-table rows of states A and B: {c6, c12, sigma6, c6grid} */
 };
 
+/* tb = first word of the trip's block */
 template<bool STAGED>
-__device__ __forceinline__ FepFetch fep_fetch(const KernelArgs& ka, const FepTile& tile, int lt, int lane)
+__device__ __forceinline__ FepFetch fep_fetch(const KernelArgs& ka, const unsigned int* tb, int lane)
 {
     FepFetch f;
-    f.td_x = STAGED ? tile.trip4[lt].x : __ldg(&tile.trip4[lt].x);
-    f.cjx  = STAGED ? tile.cjx[32 * lt + lane] : __ldg(tile.cjx + 32 * lt + lane);
-    const int owner = f.td_x & (FEP_MAX_TOUCHED - 1);
-    f.xo   = fep_load_pos(ka.pos3, owner);
-    f.po   = __ldg(ka.par4 + owner);
-    f.xj   = fep_load_pos(ka.pos3, f.cjx & (FEP_MAX_TOUCHED - 1));
+    f.head = fep_tw<STAGED>(tb + FEP_TH_OWNER);
+    f.cjx  = fep_tw<STAGED>(tb + FEP_TW_CJX + lane);
+    f.xo   = fep_load_pos(ka.pos3, (int)(f.head & (FEP_MAX_TOUCHED - 1)));
+    f.xj   = fep_load_pos(ka.pos3, (int)(f.cjx & (FEP_MAX_TOUCHED - 1)));
+    /* nbfp row = type of the reference's i atom (:499-500), column = type of its j atom (:560-563): for a
+     * flipped trip the partner is the i atom */
+    const unsigned int tt  = fep_tw<STAGED>(tb + FEP_TW_TJ + lane);
+    const int          mul = (f.head & FEP_TRIP_FLIPPED) ? ka.ntype : 1;
+    const int          iA  = mul * (int)(tt & 0xffffu) + (int)fep_tw<STAGED>(tb + FEP_TH_TADD_A);
+    const int          iB  = mul * (int)(tt >> 16) + (int)fep_tw<STAGED>(tb + FEP_TH_TADD_B);
+    f.ta                   = __ldg(ka.typetab + iA);
+    f.tb                   = __ldg(ka.typetab + iB);
     return f;
 }
 
@@ -152,22 +188,21 @@ struct FepSlot
 {
     bool   active, excluded, self, within, contrib;
     float  dx, dy, dz, r2; /* r2 not yet clamped */
-    float  qq[2];
+    float  qq[2];          /* NOT masked: lanes without a contributing pair must be masked by the caller */
     float4 ta, tb;         /* type-table rows of states A and B: {c6, c12, sigma6, c6grid} */
 };
 
 template<bool STAGED>
-__device__ __forceinline__ FepSlot fep_slot(const KernelArgs& ka, const FepTile& tile, const FepFetch& f, int lt, int lane,
+__device__ __forceinline__ FepSlot fep_slot(const KernelArgs& ka, const unsigned int* tb, const FepFetch& f, int lane,
                                             const float4* s_shift)
 {
-    FepSlot   p;
-    const int owner = f.td_x & (FEP_MAX_TOUCHED - 1);
-    const int cj    = f.cjx & (FEP_MAX_TOUCHED - 1);
-    const bool flip = (f.td_x & FEP_TRIP_FLIPPED) != 0;
-    p.active        = (f.cjx & FEP_SLOT_PADDING) == 0;
-    p.excluded      = f.cjx < 0;
-    p.self          = owner == cj;
-    const float4 sh = s_shift[min((f.td_x >> 24) & 63, FEP_NUM_SHIFT - 1)];
+    FepSlot            p;
+    const unsigned int owner = f.head & (FEP_MAX_TOUCHED - 1);
+    const unsigned int cj    = f.cjx & (FEP_MAX_TOUCHED - 1);
+    p.active                 = (f.cjx & FEP_SLOT_PADDING) == 0;
+    p.excluded               = (int)f.cjx < 0;
+    p.self                   = owner == cj;
+    const float4 sh          = s_shift[min((f.head >> 24) & 63u, (unsigned)(FEP_NUM_SHIFT - 1))];
     /* the reference shifts the i atom first (:478-480); here the owner plays that part */
     p.dx = (sh.x + f.xo.x) - f.xj.x;
     p.dy = (sh.y + f.xo.y) - f.xj.y;
@@ -175,18 +210,13 @@ __device__ __forceinline__ FepSlot fep_slot(const KernelArgs& ka, const FepTile&
     p.r2 = fmaf(p.dz, p.dz, fmaf(p.dy, p.dy, p.dx * p.dx));
     p.within  = p.r2 < ka.rcut_max2;
     p.contrib = p.active && (p.within || p.excluded); /* :667 */
-    const float2 q  = STAGED ? tile.qj[32 * lt + lane] : __ldg(tile.qj + 32 * lt + lane);
-    const int    tt = STAGED ? tile.tj[32 * lt + lane] : __ldg(tile.tj + 32 * lt + lane);
-    const float  m  = p.contrib ? 1.0f : 0.0f;
-    p.qq[0]         = (ka.epsfac * f.po.x) * q.x * m;
-    p.qq[1]         = (ka.epsfac * f.po.y) * q.y * m;
-    /* nbfp row = type of the reference's i atom (:499-500), column = type of its j atom (:560-563) */
-    const int toA = __float_as_int(f.po.z), toB = __float_as_int(f.po.w);
-    const int tjA = tt & 0xffff, tjB = (tt >> 16) & 0xffff;
-    const int iA  = flip ? ka.ntype * tjA + toA : ka.ntype * toA + tjA;
-    const int iB  = flip ? ka.ntype * tjB + toB : ka.ntype * toB + tjB;
-    p.ta          = __ldg(ka.typetab + iA);
-    p.tb          = __ldg(ka.typetab + iB);
+    const float qoA = __uint_as_float(fep_tw<STAGED>(tb + FEP_TH_QA)), qoB = __uint_as_float(fep_tw<STAGED>(tb + FEP_TH_QB));
+    const float qjA = __uint_as_float(fep_tw<STAGED>(tb + FEP_TW_QA + lane));
+    const float qjB = __uint_as_float(fep_tw<STAGED>(tb + FEP_TW_QB + lane));
+    p.qq[0]         = (ka.epsfac * qoA) * qjA;
+    p.qq[1]         = (ka.epsfac * qoB) * qjB;
+    p.ta            = f.ta;
+    p.tb            = f.tb;
     return p;
 }
 
@@ -239,18 +269,6 @@ __device__ __forceinline__ bool fep_fill_pair(const KernelArgs& ka, const FepSlo
     pr.nonzero[1]      = (pr.qq[1] != 0.0f || b.x != 0.0f || b.y != 0.0f);
     pr.included_within = p.within && !p.excluded;
     return true;
-}
-
-/* the whole list as one "tile" in global memory (kernels that do not stage) */
-__device__ __forceinline__ FepTile fep_global_tile(const KernelArgs& ka)
-{
-    FepTile t;
-    t.trip4 = ka.trip4;
-    t.cjx   = ka.cjx;
-    t.qj    = ka.qj;
-    t.tj    = ka.tj;
-    t.dst   = ka.dst;
-    return t;
 }
 
 #endif

@@ -54,7 +54,7 @@ template<int SC, bool EWALD, bool FORCE>
 __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant__ KernelArgs ka, const int want_shift)
 {
     __shared__ LambdaPoint s_lp;
-    __shared__ float       s_red[FEP_CTA / 32][2];
+    __shared__ float       s_red[FEP_CTA / 32][4];
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
@@ -72,11 +72,11 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
 
     float fx = 0.0f, fy = 0.0f, fz = 0.0f, vc = 0.0f, vv = 0.0f, dc = 0.0f, dv = 0.0f;
 
+    const unsigned int* tb = ka.trips + (size_t)(valid ? t : 0) * FEP_TRIP_WORDS;
     if (valid)
     {
-        const FepTile  tile = fep_global_tile(ka);
-        const FepFetch ft   = fep_fetch<false>(ka, tile, t, lane);
-        const FepSlot  p    = fep_slot<false>(ka, tile, ft, t, lane, ka.dyn->shiftvec);
+        const FepFetch ft = fep_fetch<false>(ka, tb, lane);
+        const FepSlot  p  = fep_slot<false>(ka, tb, ft, lane, ka.dyn->shiftvec);
         FepPair        pr;
         if (fep_fill_pair<SC>(ka, p, pr))
         {
@@ -106,17 +106,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
         {
             /* the partner receives -f: scattered to this pair's own slot in the atom-sorted buffer
              * (unique destination, no atomics; skipped pairs write their zero) */
-            ka.fsorted[__ldg(ka.dst + 32 * (size_t)t + lane)] = make_float4(-fx, -fy, -fz, 0.0f);
-        }
-    }
-
-    /* dV/dlambda of this CTA (the reference accumulates one scalar per call, :1170-1178) */
-    {
-        const float wc = warp_sum(dc), wv = warp_sum(dv);
-        if (lane == 0)
-        {
-            s_red[warp][0] = wc;
-            s_red[warp][1] = wv;
+            ka.fsorted[__ldg(tb + FEP_TW_DST + lane)] = make_float4(-fx, -fy, -fz, 0.0f);
         }
     }
 
@@ -126,24 +116,38 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
     fz = warp_sum(fz);
     vc = warp_sum(vc);
     vv = warp_sum(vv);
+    /* dV/dlambda of this CTA (the reference accumulates one scalar per call, :1170-1178); with a single
+     * energy-group pair also Vc and Vv */
+    {
+        const float wc = warp_sum(dc), wv = warp_sum(dv);
+        if (lane == 0)
+        {
+            s_red[warp][0] = wc;
+            s_red[warp][1] = wv;
+            s_red[warp][2] = vc;
+            s_red[warp][3] = vv;
+        }
+    }
     if (valid && lane == 0)
     {
-        const int4 td = __ldg(ka.trip4 + t);
         if (FORCE)
         {
-            ka.fsorted[td.y] = make_float4(fx, fy, fz, 0.0f);
+            ka.fsorted[__ldg(tb + FEP_TH_SLOT_F)] = make_float4(fx, fy, fz, 0.0f);
             if (want_shift)
             {
                 /* a flipped trip's owner was the reference's j atom: its force is minus the i force (:1153-1164) */
-                const float sg         = (td.x & FEP_TRIP_FLIPPED) ? -1.0f : 1.0f;
-                ka.fshift_sorted[td.z] = make_float4(sg * fx, sg * fy, sg * fz, 0.0f);
+                const float sg = (__ldg(tb + FEP_TH_OWNER) & FEP_TRIP_FLIPPED) ? -1.0f : 1.0f;
+                ka.fshift_sorted[__ldg(tb + FEP_TH_SLOT_SHIFT)] = make_float4(sg * fx, sg * fy, sg * fz, 0.0f);
             }
         }
-        ka.ev2[td.w] = make_float2(vc, vv);
+        if (ka.n_gid > 1)
+        {
+            ka.ev2[__ldg(tb + FEP_TH_SLOT_EV)] = make_float2(vc, vv);
+        }
     }
 
     __syncthreads();
-    if (tid < 2)
+    if (tid < 4)
     {
         double s = 0.0;
 #pragma unroll
@@ -222,13 +226,13 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
     }
 
     /* a CTA takes a tile of trips, one warp per trip and round */
-    const FepTile tile = fep_global_tile(ka);
-    const int     t0   = ka.trip_begin + blockIdx.x * ka.tile_trips;
-    const int     t1   = min(t0 + ka.tile_trips, ka.trip_end);
+    const int t0 = ka.trip_begin + blockIdx.x * ka.tile_trips;
+    const int t1 = min(t0 + ka.tile_trips, ka.trip_end);
     for (int t = t0 + warp; t < t1; t += FEP_CTA / 32)
     {
-        const FepFetch ft = fep_fetch<false>(ka, tile, t, lane);
-        const FepSlot  sl = fep_slot<false>(ka, tile, ft, t, lane, ka.dyn->shiftvec);
+        const unsigned int* tb = ka.trips + (size_t)t * FEP_TRIP_WORDS;
+        const FepFetch      ft = fep_fetch<false>(ka, tb, lane);
+        const FepSlot       sl = fep_slot<false>(ka, tb, ft, lane, ka.dyn->shiftvec);
         FepPair        pr;
         if (!fep_fill_pair<SC>(ka, sl, pr))
         {
@@ -291,7 +295,7 @@ struct EpilogueLayout
     int heavy_blocks;  /* blocks of the heavy atoms' force sums, one warp per atom       */
     int job_begin;     /* first reduction job handled (skips shift jobs when not asked)  */
     int job_blocks;    /* blocks for reduction jobs                                      */
-    int scalar_blocks; /* blocks for dvdl (2) + foreign (3*(L+1)) partial arrays         */
+    int scalar_blocks; /* blocks for dvdl (2) + Vc, Vv (2) + foreign (3*(L+1)) partial arrays */
 };
 
 __device__ __forceinline__ double block_sum_d(double v, double* s_buf)
@@ -322,31 +326,30 @@ __device__ __forceinline__ double block_sum_d(double v, double* s_buf)
  * slots may be read.  Exactly one kernel per GPU spins and its producers have already finished, so
  * the spin cannot starve anybody; a peer that never arrives (a rank that did not launch) trips the
  * time-out and the kernel traps instead of hanging the GPU. */
-__device__ __forceinline__ unsigned long long fep_globaltimer()
+/* Threads 0..nranks-1 of the calling block: (announce) release-store `seq` into slot `rank` of peer
+ * threadIdx.x's flag array, then poll slot threadIdx.x of the own array until that peer has announced
+ * `seq` or a later step.  All ranks must launch their steps in lockstep with the same `seq`; a peer that
+ * never arrives within 4 s makes the kernel record the reason and trap (FEP_FAULT_PEER_TIMEOUT) instead
+ * of hanging every GPU of the node.  Ends with a block-wide barrier. */
+template<typename FlagsOf>
+__device__ __forceinline__ void fep_flag_barrier(FlagsOf flags_of, int rank, int nranks, unsigned int seq, bool announce,
+                                                 unsigned int* fault)
 {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-__device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
-{
-    const int nr = ka.px.nranks;
-    if (threadIdx.x < nr)
+    if (threadIdx.x < nranks)
     {
-        if (blockIdx.x == 0)
+        if (announce)
         {
             __threadfence_system();
-            unsigned int* dst = ka.px.flags[threadIdx.x] + ka.px.rank;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(ka.px.seq) : "memory");
+            unsigned int* dst = flags_of(threadIdx.x) + rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
         }
-        const unsigned int* src = ka.px.flags[ka.px.rank] + threadIdx.x;
+        const unsigned int* src = flags_of(rank) + threadIdx.x;
         unsigned int        v;
         unsigned long long  t0 = 0;
         for (unsigned int spins = 0;; spins++)
         {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-            if ((int)(v - ka.px.seq) >= 0)
+            if ((int)(v - seq) >= 0)
             {
                 break;
             }
@@ -359,12 +362,17 @@ __device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
                 }
                 else if (now - t0 > 4000000000ull) /* 4 s */
                 {
-                    __trap();
+                    fep_fault(fault, FEP_FAULT_PEER_TIMEOUT, (unsigned)rank, threadIdx.x, seq);
                 }
             }
         }
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void fep_peer_barrier(const KernelArgs& ka)
+{
+    fep_flag_barrier([&](int r) { return ka.px.flags[r]; }, ka.px.rank, ka.px.nranks, ka.px.seq, blockIdx.x == 0, ka.fault);
 }
 
 /* PEER: the exchange of fep_types.h.  STRONG: peer data is read with system-scope strong loads
@@ -482,25 +490,26 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
     }
     else if ((b -= lay.job_blocks) < lay.scalar_blocks)
     {
-        /* b = 0,1: dV/dlambda coul, vdw of the current-lambda pass; b = 2 + 3p + k: point p */
+        /* b = 0,1: dV/dlambda coul, vdw of the current-lambda pass; b = 2,3: its Vc, Vv (used with a single
+         * energy-group pair); b = 4 + 3p + k: point p */
         const double* src;
         int           n;
         FEP_EPI_SYNC_POINT();
-        if (b < 2)
+        if (b < 4)
         {
             src = ka.cta_part + (size_t)b * ka.n_parts;
             n   = ka.n_parts;
         }
         else
         {
-            src = ka.for_part + (size_t)(b - 2) * ka.n_tiles;
+            src = ka.for_part + (size_t)(b - 4) * ka.n_tiles;
             n   = ka.n_tiles;
         }
         double a = 0.0;
         if (PEER)
         {
             /* row b of every rank's partial array, ranks in order (all ranks launch the same grids) */
-            const size_t row = b < 2 ? (size_t)b * ka.n_parts : (size_t)(b - 2) * ka.n_tiles;
+            const size_t row = b < 4 ? (size_t)b * ka.n_parts : (size_t)(b - 4) * ka.n_tiles;
             /* four independent (possibly remote) loads in flight per thread, summed in index order */
             const int total = n * ka.px.nranks;
             for (int k = tid; k < total; k += 4 * FEP_EPI_CTA)
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
                     if (kk < total)
                     {
                         const int     r = kk / n;
-                        const double* q = (b < 2 ? ka.px.cta_part[r] : ka.px.for_part[r]) + row + (kk - r * n);
+                        const double* q = (b < 4 ? ka.px.cta_part[r] : ka.px.for_part[r]) + row + (kk - r * n);
                         v[u]            = STRONG ? __ldcv(q) : __ldcs(q);
                     }
                 }
@@ -539,9 +548,16 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             {
                 ka.res_f64[off_dvdl + b] = a;
             }
+            else if (b < 4)
+            {
+                if (sf.energy && ka.n_gid == 1)
+                {
+                    ka.res_f64[b == 2 ? 0 : off_vv] = a;
+                }
+            }
             else
             {
-                const int p = (b - 2) / 3, k = (b - 2) - 3 * p;
+                const int p = (b - 4) / 3, k = (b - 4) - 3 * p;
                 if (k == 0)
                 {
                     ka.res_f64[off_fe + p] = a;
@@ -740,14 +756,13 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         }
         __threadfence();
     }
-    /* one warp per output value: the lanes stride over the jobs of the key, fixed butterfly at the end
-     * (a key can have dozens of jobs -- the central shift vector, a single energy-group pair -- and a
-     * serial walk over them was the tail of the whole step) */
+    /* one thread per output value, four loads of job partials in flight at a time (a key can have dozens of
+     * jobs -- the central shift vector, a populated energy-group pair -- and a serial walk over them by a few
+     * threads was the tail of the whole step); energy-group sums only when there is more than one pair */
     {
-        const int lane = tid & 31, wrp = tid >> 5;
         const int n_sh = sf.shift ? 3 * FEP_NUM_SHIFT : 0;
-        const int n_en = sf.energy ? 2 * ka.n_gid : 0;
-        for (int o = wrp; o < n_sh + n_en; o += FEP_EPI_CTA / 32)
+        const int n_en = (sf.energy && ka.n_gid > 1) ? 2 * ka.n_gid : 0;
+        for (int o = tid; o < n_sh + n_en; o += FEP_EPI_CTA)
         {
             int key, comp;
             if (o < n_sh)
@@ -761,22 +776,25 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
                 comp        = e >= ka.n_gid ? 1 : 0;
                 key         = FEP_NUM_SHIFT + (e - comp * ka.n_gid);
             }
-            double a = 0.0;
-            for (int j = ka.key_job_ptr[key] + lane; j < ka.key_job_ptr[key + 1]; j += 32)
+            const int j1 = ka.key_job_ptr[key + 1];
+            double    a  = 0.0;
+            for (int j = ka.key_job_ptr[key]; j < j1; j += 4)
             {
-                a += __ldcg(ka.job_part + 4 * (size_t)j + comp);
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    v[u] = (j + u < j1) ? __ldcg(ka.job_part + 4 * (size_t)(j + u) + comp) : 0.0;
+                }
+                a += (v[0] + v[1]) + (v[2] + v[3]);
             }
-            a = warp_sum_d(a);
-            if (lane == 0)
+            if (o < n_sh)
             {
-                if (o < n_sh)
-                {
-                    ka.res_f32[3 * (size_t)ka.n_touched + o] = (float)a;
-                }
-                else
-                {
-                    ka.res_f64[(comp ? off_vv : 0) + (key - FEP_NUM_SHIFT)] = a;
-                }
+                ka.res_f32[3 * (size_t)ka.n_touched + o] = (float)a;
+            }
+            else
+            {
+                ka.res_f64[(comp ? off_vv : 0) + (key - FEP_NUM_SHIFT)] = a;
             }
         }
     }
@@ -1060,10 +1078,10 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
     lay.heavy_blocks  = sf.force ? (n_heavy + FEP_EPI_CTA / 32 - 1) / (FEP_EPI_CTA / 32) : 0;
     /* jobs are ordered shift jobs first, then energy-group jobs */
     const int j0      = sf.shift ? 0 : ka.n_shift_jobs;
-    const int j1      = sf.energy ? ka.n_red_jobs : ka.n_shift_jobs;
+    const int j1      = (sf.energy && ka.n_gid > 1) ? ka.n_red_jobs : ka.n_shift_jobs; /* one pair: summed per CTA instead */
     lay.job_begin     = j0;
     lay.job_blocks    = j1 > j0 ? j1 - j0 : 0;
-    lay.scalar_blocks = 2 + ((sf.foreign && ka.n_points > 0) ? 3 * ka.n_points : 0);
+    lay.scalar_blocks = 4 + ((sf.foreign && ka.n_points > 0) ? 3 * ka.n_points : 0);
     const int blocks  = lay.atom_blocks + lay.heavy_blocks + lay.job_blocks + lay.scalar_blocks;
     const dim3 grid(blocks), block(FEP_EPI_CTA);
 #define FEP_EPI_LAUNCH(P, S)                                                                                 \
@@ -1122,7 +1140,7 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
                                                              const __grid_constant__ PeerPtrs flags, int rank,
                                                              unsigned int seq, int nranks, double* __restrict__ out_f64,
                                                              int n64, size_t f64_bytes, float* __restrict__ out_f32,
-                                                             long long n32)
+                                                             long long n32, unsigned int* fault)
 {
     fep_pdl_wait(); /* chained behind the epilogue that completes this rank's block */
     if (flags.p[0] != nullptr)
@@ -1131,22 +1149,8 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
          * previous kernel on this stream; announce step `seq` in every peer's flag array (slot
          * `rank`), then wait until every peer's announcement has arrived in ours.  One kernel per
          * GPU takes part, so the spin cannot starve a producer on the same device. */
-        if (blockIdx.x == 0 && threadIdx.x < nranks)
-        {
-            __threadfence_system();
-            unsigned int* dst = static_cast<unsigned int*>(const_cast<void*>(flags.p[threadIdx.x])) + rank;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
-        }
-        if (threadIdx.x < nranks)
-        {
-            const unsigned int* src = static_cast<const unsigned int*>(flags.p[rank]) + threadIdx.x;
-            unsigned int        v;
-            do
-            {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-            } while ((int)(v - seq) < 0);
-        }
-        __syncthreads();
+        fep_flag_barrier([&](int r) { return static_cast<unsigned int*>(const_cast<void*>(flags.p[r])); }, rank, nranks, seq,
+                         blockIdx.x == 0, fault);
     }
     /* NR > 0: compile-time rank count, all NR remote loads are in flight before the first add
      * (a peer load is ~1.5 us; serialising them would cost NR times that) */
@@ -1210,7 +1214,8 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
 
 extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flagsp, int rank, unsigned int seq,
                                       int nranks, double* out_f64, int n64, size_t f64_bytes, float* out_f32,
-                                      long long n32, cudaStream_t stream, long long* counter, int chained)
+                                      long long n32, cudaStream_t stream, long long* counter, int chained,
+                                      unsigned int* fault)
 {
     PeerPtrs noflags{};
     const PeerPtrs* flags = flagsp ? flagsp : &noflags;
@@ -1218,10 +1223,10 @@ extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* fla
     const unsigned  blocks = (unsigned)((std::max<long long>(items, n64) + 255) / 256);
     switch (nranks)
     {
-        case 2: fep_launch_kernel(fep_peer_reduce_kernel<2>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
-        case 4: fep_launch_kernel(fep_peer_reduce_kernel<4>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
-        case 8: fep_launch_kernel(fep_peer_reduce_kernel<8>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
-        default: fep_launch_kernel(fep_peer_reduce_kernel<0>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32); break;
+        case 2: fep_launch_kernel(fep_peer_reduce_kernel<2>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
+        case 4: fep_launch_kernel(fep_peer_reduce_kernel<4>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
+        case 8: fep_launch_kernel(fep_peer_reduce_kernel<8>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
+        default: fep_launch_kernel(fep_peer_reduce_kernel<0>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
     }
     (*counter)++;
     return (int)cudaGetLastError();

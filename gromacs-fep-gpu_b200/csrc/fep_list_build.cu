@@ -135,17 +135,23 @@ __global__ void k_trip_heads(const int* __restrict__ gstart, int P, int* __restr
     }
 }
 
-__global__ void k_clear_slots(int n_slots, int* __restrict__ cjx, int* __restrict__ dst, float2* __restrict__ qj,
-                              int* __restrict__ tj, int* __restrict__ orig)
+__global__ void k_clear_trips(int NT, unsigned int* __restrict__ trips, int* __restrict__ orig)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_slots)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x; /* one thread per lane slot */
+    if (i < 32 * NT)
     {
-        cjx[i]  = FEP_SLOT_PADDING;
-        dst[i]  = 0;
-        qj[i]   = make_float2(0.0f, 0.0f);
-        tj[i]   = 0;
-        orig[i] = -1;
+        unsigned int* tb = trips + (size_t)(i >> 5) * FEP_TRIP_WORDS;
+        const int     l  = i & 31;
+        if (l < 16)
+        {
+            tb[l] = 0u;
+        }
+        tb[FEP_TW_CJX + l] = FEP_SLOT_PADDING;
+        tb[FEP_TW_DST + l] = 0u;
+        tb[FEP_TW_QA + l]  = 0u;
+        tb[FEP_TW_QB + l]  = 0u;
+        tb[FEP_TW_TJ + l]  = 0u;
+        orig[i]            = -1;
     }
 }
 
@@ -154,10 +160,9 @@ template<typename K>
 __global__ void k_fill_slots(const K* __restrict__ keys_sorted, const int* __restrict__ vals_sorted,
                              const int* __restrict__ gstart, const int* __restrict__ th, const int* __restrict__ tsc,
                              const int* __restrict__ pj, const int* __restrict__ pn, const int4* __restrict__ ent4,
-                             const int* __restrict__ excl, int j0, const float4* __restrict__ par4, int G, int P, int NT,
-                             int* __restrict__ cjx, float2* __restrict__ qj, int* __restrict__ tj, int* __restrict__ orig,
-                             int4* __restrict__ trip4, int* __restrict__ tshift, int* __restrict__ tgid,
-                             int* __restrict__ akeys, int* __restrict__ avals)
+                             const int* __restrict__ excl, int j0, const float4* __restrict__ par4, int ntype, int G, int P,
+                             int NT, unsigned int* __restrict__ trips, int* __restrict__ orig, int* __restrict__ tshift,
+                             int* __restrict__ tgid, int* __restrict__ akeys, int* __restrict__ avals)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P)
@@ -175,23 +180,31 @@ __global__ void k_fill_slots(const K* __restrict__ keys_sorted, const int* __res
     const int  other  = flip ? ci : cj;
     const int  t      = tsc[r] + th[r] - 1;
     const int  lane   = (r - gstart[r]) & 31;
-    const int  slot   = 32 * t + lane;
     const bool excluded = excl != nullptr && excl[j0 + s] == 0;
-    const float4 p    = par4[other];
-    cjx[slot]         = other | (excluded ? (int)0x80000000u : 0);
-    qj[slot]          = make_float2(p.x, p.y);
-    tj[slot]          = __float_as_int(p.z) | (__float_as_int(p.w) << 16);
-    orig[slot]        = s;
-    akeys[r]          = other;
-    avals[r]          = slot;
+    const float4  p   = par4[other];
+    unsigned int* tb  = trips + (size_t)t * FEP_TRIP_WORDS;
+    tb[FEP_TW_CJX + lane] = (unsigned int)other | (excluded ? 0x80000000u : 0u);
+    tb[FEP_TW_QA + lane]  = __float_as_uint(p.x);
+    tb[FEP_TW_QB + lane]  = __float_as_uint(p.y);
+    tb[FEP_TW_TJ + lane]  = (unsigned int)__float_as_int(p.z) | ((unsigned int)__float_as_int(p.w) << 16);
+    orig[32 * t + lane]   = s;
+    akeys[r]              = other;
+    avals[r]              = 32 * t + lane;
     if (lane == 0)
     {
-        const int sh_eff = flip ? (FEP_NUM_SHIFT - 1 - sh) : sh;
-        trip4[t]         = make_int4(owner | (sh_eff << 24) | (flip ? FEP_TRIP_FLIPPED : 0), 0, 0, 0);
-        tshift[t]        = sh;
-        tgid[t]          = g;
-        akeys[P + t]     = owner;
-        avals[P + t]     = 32 * NT + t;
+        const int    sh_eff = flip ? (FEP_NUM_SHIFT - 1 - sh) : sh;
+        const float4 po     = par4[owner];
+        const int    toA = __float_as_int(po.z), toB = __float_as_int(po.w);
+        tb[FEP_TH_OWNER]  = (unsigned int)owner | ((unsigned int)sh_eff << 24) | (flip ? (unsigned int)FEP_TRIP_FLIPPED : 0u);
+        /* nbfp row = type of the reference's i atom (:499-500), column = type of its j atom (:560-563) */
+        tb[FEP_TH_TADD_A] = (unsigned int)(flip ? toA : ntype * toA);
+        tb[FEP_TH_TADD_B] = (unsigned int)(flip ? toB : ntype * toB);
+        tb[FEP_TH_QA]     = __float_as_uint(po.x);
+        tb[FEP_TH_QB]     = __float_as_uint(po.y);
+        tshift[t]         = sh;
+        tgid[t]           = g;
+        akeys[P + t]      = owner;
+        avals[P + t]      = 32 * NT + t;
     }
 }
 
@@ -207,7 +220,7 @@ __global__ void k_iota(int* __restrict__ v, int n)
 /* r-th element of the atom-sorted order: tell the contribution its slot, and fill atom_ptr at the
  * boundaries between different atoms (atoms without contributions get empty ranges) */
 __global__ void k_atom_slots(const int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, int n, int n_slots,
-                             int nT, int* __restrict__ dst, int4* __restrict__ trip4, int* __restrict__ atom_ptr)
+                             int nT, unsigned int* __restrict__ trips, int* __restrict__ atom_ptr)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n)
@@ -217,11 +230,11 @@ __global__ void k_atom_slots(const int* __restrict__ keys_sorted, const int* __r
     const int idx = vals_sorted[r];
     if (idx < n_slots)
     {
-        dst[idx] = r;
+        trips[(size_t)(idx >> 5) * FEP_TRIP_WORDS + FEP_TW_DST + (idx & 31)] = (unsigned int)r;
     }
     else
     {
-        trip4[idx - n_slots].y = r;
+        trips[(size_t)(idx - n_slots) * FEP_TRIP_WORDS + FEP_TH_SLOT_F] = (unsigned int)r;
     }
     const int cur  = keys_sorted[r];
     const int prev = r > 0 ? keys_sorted[r - 1] : -1;
@@ -238,10 +251,10 @@ __global__ void k_atom_slots(const int* __restrict__ keys_sorted, const int* __r
     }
 }
 
-/* r-th element of the trips sorted by `which` key (1: shift index -> trip4.z, 2: gid -> .w);
+/* r-th element of the trips sorted by `which` key (1: shift index, 2: gid) -> the trip's slot in that order;
  * key_ptr[k] = first rank of key k, key_ptr[nkeys] = n */
 __global__ void k_trip_slots(const int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, int n, int nkeys,
-                             int which, int4* __restrict__ trip4, int* __restrict__ key_ptr)
+                             int which, unsigned int* __restrict__ trips, int* __restrict__ key_ptr)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n)
@@ -249,14 +262,7 @@ __global__ void k_trip_slots(const int* __restrict__ keys_sorted, const int* __r
         return;
     }
     const int t = vals_sorted[r];
-    if (which == 1)
-    {
-        trip4[t].z = r;
-    }
-    else
-    {
-        trip4[t].w = r;
-    }
+    trips[(size_t)t * FEP_TRIP_WORDS + (which == 1 ? FEP_TH_SLOT_SHIFT : FEP_TH_SLOT_EV)] = (unsigned int)r;
     const int cur  = keys_sorted[r];
     const int prev = r > 0 ? keys_sorted[r - 1] : -1;
     for (int k = prev + 1; k <= cur; k++)
@@ -372,8 +378,8 @@ extern "C" int fep_list_build_groups(const ListBuild* bp, const int* d_iinr, con
 
 /* Phase 3 (NT known): slot records, the atom sort and the two trip sorts.
  * key_ptr: int[46 + G + 1] (shift_ptr then gid_ptr). */
-extern "C" int fep_list_build_slots(const ListBuild* bp, const int* d_excl, int j0, const float4* d_par4, int P, int NT,
-                                    int nT, int G, int wide_keys, cudaStream_t stream, long long* counter)
+extern "C" int fep_list_build_slots(const ListBuild* bp, const int* d_excl, int j0, const float4* d_par4, int ntype, int P,
+                                    int NT, int nT, int G, int wide_keys, cudaStream_t stream, long long* counter)
 {
     const ListBuild& b         = *bp;
     size_t           tmp_bytes = b.tmp_bytes;
@@ -385,31 +391,31 @@ extern "C" int fep_list_build_slots(const ListBuild* bp, const int* d_excl, int 
     {
         return (int)cudaGetLastError();
     }
-    k_clear_slots<<<(n_slots + 255) / 256, 256, 0, stream>>>(n_slots, b.cjx, b.dst, b.qj, b.tj, b.orig);
+    k_clear_trips<<<(n_slots + 255) / 256, 256, 0, stream>>>(NT, b.trips, b.orig);
     if (wide_keys)
     {
         k_fill_slots<unsigned long long><<<(P + 255) / 256, 256, 0, stream>>>(
                 reinterpret_cast<const unsigned long long*>(b.keys_out), b.vals_out, b.gstart, b.th, b.tsc, b.pj, b.pn, b.ent4,
-                d_excl, j0, d_par4, G, P, NT, b.cjx, b.qj, b.tj, b.orig, b.trip4, b.tshift, b.tgid, b.akeys, b.avals);
+                d_excl, j0, d_par4, ntype, G, P, NT, b.trips, b.orig, b.tshift, b.tgid, b.akeys, b.avals);
     }
     else
     {
         k_fill_slots<unsigned int><<<(P + 255) / 256, 256, 0, stream>>>(
                 reinterpret_cast<const unsigned int*>(b.keys_out), b.vals_out, b.gstart, b.th, b.tsc, b.pj, b.pn, b.ent4, d_excl,
-                j0, d_par4, G, P, NT, b.cjx, b.qj, b.tj, b.orig, b.trip4, b.tshift, b.tgid, b.akeys, b.avals);
+                j0, d_par4, ntype, G, P, NT, b.trips, b.orig, b.tshift, b.tgid, b.akeys, b.avals);
     }
     /* every force contribution's slot in the atom-sorted buffer: pairs (to their partner) in slot order, then
      * trips (to their owner) */
     cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.akeys, b.akeys_out, b.avals, b.avals_out, n, 0,
                                     bits_for((unsigned long long)nT), stream);
-    k_atom_slots<<<(n + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, n, n_slots, nT, b.dst, b.trip4, b.atom_ptr);
+    k_atom_slots<<<(n + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, n, n_slots, nT, b.trips, b.atom_ptr);
     /* trips by shift index and by energy-group pair */
     k_iota<<<(NT + 255) / 256, 256, 0, stream>>>(b.avals, NT);
     cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.tshift, b.akeys_out, b.avals, b.avals_out, NT, 0, 6, stream);
-    k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, FEP_NUM_SHIFT, 1, b.trip4, b.key_ptr);
+    k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, FEP_NUM_SHIFT, 1, b.trips, b.key_ptr);
     cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.tgid, b.akeys_out, b.avals, b.avals_out, NT, 0,
                                     bits_for((unsigned long long)G), stream);
-    k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, G, 2, b.trip4,
+    k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, G, 2, b.trips,
                                                      b.key_ptr + FEP_NUM_SHIFT + 1);
     (*counter) += 6;
     return (int)cudaGetLastError();
@@ -420,8 +426,7 @@ extern "C" int fep_list_build_slots(const ListBuild* bp, const int* d_excl, int 
  * buffer, of the shift-sorted trip sums and of the group-sorted trip energies, when rank r
  * evaluates the trips [r * tpr, (r + 1) * tpr).  One byte per element; the epilogue of the
  * exchange reads each element from its producer's memory. */
-__global__ void __launch_bounds__(256) k_source_tables(const int* __restrict__ cjx, const int* __restrict__ dst,
-                                                       const int4* __restrict__ trip4, int NT, int tpr,
+__global__ void __launch_bounds__(256) k_source_tables(const unsigned int* __restrict__ trips, int NT, int tpr,
                                                        unsigned char* __restrict__ slot_src,
                                                        unsigned char* __restrict__ fshift_src,
                                                        unsigned char* __restrict__ ev2_src)
@@ -431,29 +436,28 @@ __global__ void __launch_bounds__(256) k_source_tables(const int* __restrict__ c
     {
         return;
     }
-    const int           t = i >> 5;
-    const unsigned char r = (unsigned char)(t / tpr);
-    if (!(cjx[i] & FEP_SLOT_PADDING))
+    const int           t  = i >> 5, l = i & 31;
+    const unsigned int* tb = trips + (size_t)t * FEP_TRIP_WORDS;
+    const unsigned char r  = (unsigned char)(t / tpr);
+    if (!(tb[FEP_TW_CJX + l] & FEP_SLOT_PADDING))
     {
-        slot_src[dst[i]] = r;
+        slot_src[tb[FEP_TW_DST + l]] = r;
     }
-    if ((i & 31) == 0)
+    if (l == 0)
     {
-        const int4 td    = trip4[t];
-        slot_src[td.y]   = r;
-        fshift_src[td.z] = r;
-        ev2_src[td.w]    = r;
+        slot_src[tb[FEP_TH_SLOT_F]]       = r;
+        fshift_src[tb[FEP_TH_SLOT_SHIFT]] = r;
+        ev2_src[tb[FEP_TH_SLOT_EV]]       = r;
     }
 }
 
-extern "C" int fep_launch_source_tables(const int* d_cjx, const int* d_dst, const int4* d_trip4, int NT, int tpr,
-                                        unsigned char* d_slot_src, unsigned char* d_fshift_src, unsigned char* d_ev2_src,
-                                        cudaStream_t stream, long long* counter)
+extern "C" int fep_launch_source_tables(const unsigned int* d_trips, int NT, int tpr, unsigned char* d_slot_src,
+                                        unsigned char* d_fshift_src, unsigned char* d_ev2_src, cudaStream_t stream,
+                                        long long* counter)
 {
     if (NT > 0 && tpr > 0)
     {
-        k_source_tables<<<(32 * NT + 255) / 256, 256, 0, stream>>>(d_cjx, d_dst, d_trip4, NT, tpr, d_slot_src, d_fshift_src,
-                                                                  d_ev2_src);
+        k_source_tables<<<(32 * NT + 255) / 256, 256, 0, stream>>>(d_trips, NT, tpr, d_slot_src, d_fshift_src, d_ev2_src);
         (*counter)++;
     }
     return (int)cudaGetLastError();

@@ -24,14 +24,16 @@
  *                                  packed: 12 bytes per atom cross PCIe, not 16
  *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step (read per trip: owner)
  *   typetab[T*T] float4 {c6,c12,sigma6,c6grid}               per nbfp upload
- *   trip4[NT]    int4 {owner | shift_eff << 24 | flipped << 30, slot of the owner's force sum in
- *                fsorted, slot in fshift_sorted, slot in ev2}                per search step
- *   per slot, SoA, streamed coalesced (staged through shared memory by one bulk copy per CTA tile):
- *     cjx[ ]     int    compact partner | excluded << 31 | padding << 30
- *     dst[ ]     int    where the force on the partner goes in fsorted
- *     qj[ ]      float2 partner charges {qA, qB}     (pre-gathered: no dependent per-pair load
- *     tj[ ]      int    partner types  A | B << 16    except the partner's coordinates)
- *     orig[ ]    int    index of the pair in the shard's t_nblist (list read-back only)
+ *   trips[NT]    one contiguous block of FEP_TRIP_WORDS 32-bit words per trip, so that the tile of a
+ *                CTA is ONE bulk copy into shared memory and every field is base + constant offset:
+ *                  header (16 words): owner | shift_eff << 24 | flipped << 30; slot of the owner's force
+ *                    sum in fsorted; slot in fshift_sorted; slot in ev2; type-table index terms of the
+ *                    owner for states A, B; owner charges qA, qB; padding
+ *                  cjx[32]  compact partner | excluded << 31 | padding << 30
+ *                  dst[32]  where the force on the partner goes in fsorted
+ *                  qA[32], qB[32]  partner charges       (pre-gathered: the only dependent per-pair load
+ *                  tj[32]   partner types A | B << 16     left is the partner's coordinates)
+ *   orig[32 NT]  index of the pair in the shard's t_nblist; tgid[NT] (list read-back only)
  *   ent4[E]      int4   {compact i, shift index, gid, 0}  (list read-back only) per search step
  *   fsorted[P+NT] float4 force contributions SORTED BY RECEIVING ATOM: atom k owns the contiguous
  *                range [atom_ptr[k], atom_ptr[k+1]); the pass kernel scatters -f (pairs, to the
@@ -47,10 +49,31 @@
 #define FEPB200_FEP_TYPES_H
 
 #include <cuda_runtime.h>
+#ifdef __cplusplus
+#include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
+#endif
 
 #define FEP_NUM_SHIFT 45
 #define FEP_MAX_TOUCHED (1 << 24) /* compact atom index, shift index and flags share one word */
 #define FEP_SLOT_PADDING 0x40000000 /* cjx: the slot holds no pair (tail of a trip) */
+/* layout of a trip block, in 32-bit words */
+#define FEP_TRIP_WORDS 176
+#define FEP_TH_OWNER 0
+#define FEP_TH_SLOT_F 1
+#define FEP_TH_SLOT_SHIFT 2
+#define FEP_TH_SLOT_EV 3
+#define FEP_TH_TADD_A 4 /* flipped ? typeA(owner) : ntype * typeA(owner) */
+#define FEP_TH_TADD_B 5
+#define FEP_TH_QA 6
+#define FEP_TH_QB 7
+#define FEP_TW_CJX 16
+#define FEP_TW_DST 48
+#define FEP_TW_QA 80
+#define FEP_TW_QB 112
+#define FEP_TW_TJ 144
 #define FEP_TRIP_FLIPPED 0x40000000 /* trip4.x: the owner was the j atom of the reference's pairs */
 #define FEP_CENTRAL_SHIFT 22
 #define FEP_MAX_POINTS 256 /* L+1 <= 256 lambda points per step */
@@ -153,11 +176,7 @@ struct KernelArgs
     const float*    pos3;
     const float4*   par4;
     const float4*   typetab;
-    const int4*     trip4;
-    const int*      cjx;
-    const int*      dst;
-    const float2*   qj;
-    const int*      tj;
+    const unsigned int* trips; /* [n_trips][FEP_TRIP_WORDS] */
     /* intermediates */
     float4* fsorted;
     float4* fshift_sorted;
@@ -177,7 +196,14 @@ struct KernelArgs
     double* res_f64;
     PeerExchange px;
     unsigned long long* trace; /* NULL, or FEP_TRACE_BLOCKS x 4 global-timer stamps of the epilogue's blocks */
+    unsigned int*       fault; /* host-mapped FEP_FAULT_WORDS words: why a kernel of this context trapped (fep_fault) */
 };
+
+/* A kernel that gives up (a peer that never announces its step, a bulk copy that never lands) says why in
+ * host-mapped memory before it traps, so that the error the host reports names the cause instead of
+ * "unspecified launch failure".  Word 0: code; 1..3: details (see fail() in fepb200_api.cu). */
+#define FEP_FAULT_WORDS 4
+enum { FEP_FAULT_NONE = 0, FEP_FAULT_PEER_TIMEOUT = 1, FEP_FAULT_STAGE_TIMEOUT = 2 };
 
 /* what one step has to produce */
 struct StepFlags
@@ -187,16 +213,16 @@ struct StepFlags
 
 /* Device buffers of the list builder (fep_list_build.cu); ints unless noted.  Scratch: pj, pn [P]; deg [nT+1];
  * keys, keys_out [P] of 4- or 8-byte keys; vals, vals_out, gmark, gstart [P]; th, tsc [P+1]; akeys, akeys_out,
- * avals, avals_out [P+NT]; tshift [NT]; key_ptr [46 + G + 1].  Results: ent4 [E]; trip4, tgid [NT]; cjx, dst, qj,
- * tj, orig [32 NT]; atom_ptr [nT+1]. */
+ * avals, avals_out [P+NT]; tshift [NT]; key_ptr [46 + G + 1].  Results: ent4 [E]; trips [NT][FEP_TRIP_WORDS];
+ * tgid [NT]; orig [32 NT]; atom_ptr [nT+1]. */
 struct ListBuild
 {
     int *  pj, *pn, *deg, *vals, *vals_out, *gmark, *gstart, *th, *tsc, *akeys, *akeys_out, *avals, *avals_out, *tshift, *key_ptr;
     void * keys, *keys_out, *tmp;
     size_t tmp_bytes;
-    int4 * ent4, *trip4;
-    int *  tgid, *cjx, *dst, *tj, *orig, *atom_ptr;
-    float2* qj;
+    int4 *        ent4;
+    unsigned int* trips;
+    int *         tgid, *orig, *atom_ptr;
 };
 
 #ifdef __cplusplus
@@ -213,7 +239,7 @@ int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlag
                     const LambdaPoint* host_pts, int beutler_mode, cudaStream_t side_stream, cudaEvent_t fork_ev,
                     cudaEvent_t join_ev);
 #define FEP_FB_CTA 128
-#define FEP_TILE_SMEM_MAX (44 * 1024) /* dynamic shared memory of a pair kernel: the staged tile */
+#define FEP_TILE_SMEM_SM (200 * 1024) /* shared memory of one SM that the staged tiles of its resident CTAs may fill */
 #define FEP_FB_MAXC 24
 int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
 int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force);
@@ -235,7 +261,7 @@ struct PeerPtrs
  * (the cross-GPU barrier is part of the reduction kernel). */
 int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flags, int rank, unsigned int seq, int nranks,
                            double* out_f64, int n64, size_t f64_bytes, float* out_f32, long long n32,
-                           cudaStream_t stream, long long* launch_counter, int chained);
+                           cudaStream_t stream, long long* launch_counter, int chained, unsigned int* fault);
 int fep_launch_gather_x(const float* d_x, int stride, const int* d_touched, float* pos3, int n_touched,
                         cudaStream_t stream, long long* launch_counter);
 /* fepb200_export_scalars_device(): where the values sit in the fp64 part of the result block, and the
@@ -278,6 +304,60 @@ __device__ __forceinline__ void fep_pdl_wait()
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long fep_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+/* records the reason (first writer wins) where the host can still read it after the trap, then traps */
+static __device__ __noinline__ void fep_fault(unsigned int* fault, unsigned int code, unsigned int a, unsigned int b, unsigned int c)
+{
+    if (fault && atomicCAS_system(fault, 0u, code) == 0u)
+    {
+        fault[1] = a;
+        fault[2] = b;
+        fault[3] = c;
+        __threadfence_system();
+    }
+    __trap();
+}
+
+/* Shared-memory carve-out of every kernel of a step.  The driver picks a carve-out per kernel from its shared-memory
+ * needs, and an SM can only change it when it is empty: a kernel whose choice differs from that of the CTAs resident
+ * on an SM waits for them to drain.  That costs the overlap of a chained (PDL) kernel with its predecessor's tail,
+ * and it deadlocks ranks that share one device in the tests (their epilogues spin in the cross-rank barrier while
+ * another rank's pair kernel waits for the SMs to drain).  All kernels of a step therefore ask for the same one:
+ * FEPB200_CARVEOUT = percent of the L1/shared array used as shared memory (default: the maximum, which the staged
+ * tiles of the pair kernels want anyway); -1 = leave the choice to the driver. */
+static inline int fep_carveout_percent()
+{
+    static const int v = [] {
+        const char* e = std::getenv("FEPB200_CARVEOUT");
+        return e ? std::atoi(e) : 100;
+    }();
+    return v;
+}
+/* once per kernel and device (the attribute belongs to the device's copy of the function) */
+static inline void fep_prefer_carveout(const void* kernel)
+{
+    const int v = fep_carveout_percent();
+    if (v < 0)
+    {
+        return;
+    }
+    static std::mutex                                 mtx;
+    static std::set<std::pair<const void*, int>>      done;
+    int                                               dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mtx);
+    if (done.insert(std::make_pair(kernel, dev)).second)
+    {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v > 100 ? 100 : v);
+    }
+}
+
 template<typename... KArgs, typename... Args>
 static inline cudaError_t fep_launch_kernel_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes,
                                                  cudaStream_t stream, bool chained, Args&&... args)
@@ -292,6 +372,7 @@ static inline cudaError_t fep_launch_kernel_smem(void (*kernel)(KArgs...), dim3 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs                                          = attr;
     cfg.numAttrs                                       = chained ? 1 : 0;
+    fep_prefer_carveout(reinterpret_cast<const void*>(kernel));
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -36,11 +36,11 @@ extern "C" int    fep_list_build_touched(const int* d_iinr, int nri_total, const
 extern "C" int    fep_list_build_groups(const ListBuild* b, const int* d_iinr, const int* d_gid, const int* d_shift,
                                         const int* d_jindex, const int* d_jjnr, const int* d_cscan, int e0, int E, int j0, int P,
                                         int nT, int G, int wide_keys, cudaStream_t stream, long long* counter);
-extern "C" int    fep_list_build_slots(const ListBuild* b, const int* d_excl, int j0, const float4* d_par4, int P, int NT, int nT,
-                                       int G, int wide_keys, cudaStream_t stream, long long* counter);
-extern "C" int    fep_launch_source_tables(const int* d_cjx, const int* d_dst, const int4* d_trip4, int NT, int tpr,
-                                           unsigned char* d_slot_src, unsigned char* d_fshift_src, unsigned char* d_ev2_src,
-                                           cudaStream_t stream, long long* counter);
+extern "C" int    fep_list_build_slots(const ListBuild* b, const int* d_excl, int j0, const float4* d_par4, int ntype, int P, int NT,
+                                       int nT, int G, int wide_keys, cudaStream_t stream, long long* counter);
+extern "C" int    fep_launch_source_tables(const unsigned int* d_trips, int NT, int tpr, unsigned char* d_slot_src,
+                                           unsigned char* d_fshift_src, unsigned char* d_ev2_src, cudaStream_t stream,
+                                           long long* counter);
 
 namespace
 {
@@ -223,9 +223,9 @@ struct fepb200_ctx
     int              n_trips = 0;
 
     DeviceArray<int>    d_touched, d_atom_ptr, d_key_job_ptr;
-    DeviceArray<int4>   d_ent4, d_trip4;
-    DeviceArray<int>    d_cjx, d_dst, d_tj, d_orig, d_tgid;
-    DeviceArray<float2> d_qj;
+    DeviceArray<int4>   d_ent4;
+    DeviceArray<unsigned int> d_trips; /* [n_trips][FEP_TRIP_WORDS] */
+    DeviceArray<int>    d_orig, d_tgid;
     DeviceArray<RedJob> d_red_jobs;
     DeviceArray<float4> d_par4, d_fsorted, d_fshift_sorted;
     DeviceArray<float2> d_ev2;
@@ -257,6 +257,8 @@ struct fepb200_ctx
     unsigned char* x_base[FEP_XMAX] = {};
     size_t         x_bytes = 0; /* size of each rank's exchange buffer */
     size_t         x_off_fsorted = 0, x_off_fshift = 0, x_off_ev2 = 0, x_off_cta = 0, x_off_for = 0, x_slot_bytes = 0;
+    /* why a kernel trapped (fep_fault in fep_types.h): pinned, mapped into the device, readable after the trap */
+    unsigned int* h_fault = nullptr;
 };
 
 namespace
@@ -272,6 +274,28 @@ int fail(fepb200_ctx* ctx, int code, const char* fmt, ...)
     if (ctx)
     {
         ctx->error = buf;
+        if (code == FEPB200_ERR_CUDA && ctx->h_fault && ctx->h_fault[0] != FEP_FAULT_NONE)
+        {
+            const unsigned int* w = ctx->h_fault;
+            char                why[256];
+            if (w[0] == FEP_FAULT_PEER_TIMEOUT)
+            {
+                snprintf(why, sizeof(why),
+                         " [device: rank %u waited 4 s for rank %u to announce step %u of the peer exchange -- all ranks must "
+                         "launch every step, in the same order]",
+                         w[1], w[2], w[3]);
+            }
+            else if (w[0] == FEP_FAULT_STAGE_TIMEOUT)
+            {
+                snprintf(why, sizeof(why), " [device: the staged tile of CTA %u never arrived in shared memory (thread %u)]", w[1],
+                         w[2]);
+            }
+            else
+            {
+                snprintf(why, sizeof(why), " [device fault %u: %u %u %u]", w[0], w[1], w[2], w[3]);
+            }
+            ctx->error += why;
+        }
     }
     else
     {
@@ -402,11 +426,13 @@ int prepare_buffers(fepb200_ctx* c)
         k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
         /* one wave: as many tiles as CTAs can be resident, at least one trip per warp; a tile is staged in
          * shared memory as a whole, which bounds its size (larger lists take more than one wave) */
-        auto tiles = [&](long long ctas_per_sm, bool with_dst, int& tile_trips, int& n_tiles) {
+        auto tiles = [&](long long ctas_per_sm, int& tile_trips, int& n_tiles) {
             const long long target  = (long long)sms * ctas_per_sm;
-            const long long per_trip = (long long)(sizeof(int4) + 32 * (with_dst ? 20 : 16));
-            const long long cap     = std::max(1LL, std::min<long long>(FEP_TILE_SMEM_MAX, 200 * 1024 / ctas_per_sm) / per_trip);
-            long long       tt      = ((long long)range + target - 1) / target;
+            const long long per_trip = (long long)(FEP_TRIP_WORDS * sizeof(unsigned int));
+            const long long cap     = std::max(1LL, (long long)(FEP_TILE_SMEM_SM / ctas_per_sm) / per_trip);
+            /* whole waves: when one wave of full tiles cannot hold the list, split it evenly over more waves */
+            const long long waves   = std::max(1LL, ((long long)range + target * cap - 1) / (target * cap));
+            long long       tt      = ((long long)range + target * waves - 1) / (target * waves);
             tt                      = std::max<long long>(FEP_FB_CTA / 32, std::min(tt, cap));
             tile_trips              = (int)tt;
             n_tiles                 = (range + tile_trips - 1) / tile_trips;
@@ -428,8 +454,8 @@ int prepare_buffers(fepb200_ctx* c)
         };
         tiles(per_sm("FEPB200_FOREIGN_CTAS_PER_SM",
                      fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign)),
-              k.fuse_pass_and_foreign != 0, k.tile_trips, k.n_tiles);
-        tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)), true,
+              k.tile_trips, k.n_tiles);
+        tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)),
               k.pass_tile_trips, k.pass_n_tiles);
     }
     else
@@ -458,7 +484,7 @@ int prepare_buffers(fepb200_ctx* c)
         c->x_off_fshift      = c->x_off_fsorted + up((P + H) * sizeof(float4));
         c->x_off_ev2         = c->x_off_fshift + up(H * sizeof(float4));
         c->x_off_cta         = c->x_off_ev2 + up(H * sizeof(float2));
-        c->x_off_for         = c->x_off_cta + up(2 * n_parts * sizeof(double));
+        c->x_off_for         = c->x_off_cta + up(4 * n_parts * sizeof(double));
         c->x_slot_bytes      = c->x_off_for + up(3 * (size_t)np * (size_t)std::max(k.n_tiles, 1) * sizeof(double));
         if (2 * c->x_slot_bytes + 256 > c->x_bytes)
         {
@@ -471,7 +497,7 @@ int prepare_buffers(fepb200_ctx* c)
 
     CU_CHECK(c, c->d_pts.reserve(np));
     CU_CHECK(c, c->h_pts.reserve(np));
-    CU_CHECK(c, c->d_cta_part.reserve(2 * (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1))));
+    CU_CHECK(c, c->d_cta_part.reserve(4 * (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1))));
     CU_CHECK(c, c->d_for_part.reserve(3 * (size_t)np * std::max(k.n_tiles, 1)));
     c->res_f64_bytes = ((size_t)l.f64_words * sizeof(double) + 15) & ~(size_t)15;
     c->res_f32_bytes = (size_t)l.f32_words * sizeof(float);
@@ -751,22 +777,17 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
         return rc;
     }
     const size_t n_slots = 32 * (size_t)NT;
-    CU_CHECK(c, c->d_trip4.reserve(std::max(NT, 1)));
+    CU_CHECK(c, c->d_trips.reserve(std::max<size_t>((size_t)NT * FEP_TRIP_WORDS, 1)));
     CU_CHECK(c, c->d_tgid.reserve(std::max(NT, 1)));
     CU_CHECK(c, c->d_tshift.reserve(std::max(NT, 1)));
-    CU_CHECK(c, c->d_cjx.reserve(std::max<size_t>(n_slots, 1)));
-    CU_CHECK(c, c->d_dst.reserve(std::max<size_t>(n_slots, 1)));
-    CU_CHECK(c, c->d_qj.reserve(std::max<size_t>(n_slots, 1)));
-    CU_CHECK(c, c->d_tj.reserve(std::max<size_t>(n_slots, 1)));
     CU_CHECK(c, c->d_orig.reserve(std::max<size_t>(n_slots, 1)));
     CU_CHECK(c, c->d_akeys.reserve(std::max(P + NT, 1)));
     CU_CHECK(c, c->d_akeys_out.reserve(std::max(P + NT, 1)));
     CU_CHECK(c, c->d_avals.reserve(std::max(P + NT, 1)));
     CU_CHECK(c, c->d_avals_out.reserve(std::max(P + NT, 1)));
-    b.trip4 = c->d_trip4.ptr, b.tgid = c->d_tgid.ptr, b.tshift = c->d_tshift.ptr;
-    b.cjx = c->d_cjx.ptr, b.dst = c->d_dst.ptr, b.qj = c->d_qj.ptr, b.tj = c->d_tj.ptr, b.orig = c->d_orig.ptr;
+    b.trips = c->d_trips.ptr, b.tgid = c->d_tgid.ptr, b.tshift = c->d_tshift.ptr, b.orig = c->d_orig.ptr;
     b.akeys = c->d_akeys.ptr, b.akeys_out = c->d_akeys_out.ptr, b.avals = c->d_avals.ptr, b.avals_out = c->d_avals_out.ptr;
-    err = fep_list_build_slots(&b, d_excl, j0, c->d_par4.ptr, P, NT, nT, ngrp, wide ? 1 : 0, st, &c->launches);
+    err = fep_list_build_slots(&b, d_excl, j0, c->d_par4.ptr, c->ntype, P, NT, nT, ngrp, wide ? 1 : 0, st, &c->launches);
     if (err != 0)
     {
         return fail(c, FEPB200_ERR_CUDA, "list build (slots) failed: %s", cudaGetErrorString((cudaError_t)err));
@@ -860,6 +881,26 @@ int fepb200_create(fepb200_ctx** out, int device_ordinal)
     }
     c->ka.done_counter = c->d_counter.ptr;
     c->own_stream      = c->stream;
+    {
+        /* best effort: without it kernels still trap, only the reason is not reported */
+        void* hp = nullptr;
+        void* dp = nullptr;
+        if (cudaHostAlloc(&hp, FEP_FAULT_WORDS * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess
+            && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess)
+        {
+            c->h_fault = static_cast<unsigned int*>(hp);
+            std::memset(c->h_fault, 0, FEP_FAULT_WORDS * sizeof(unsigned int));
+            c->ka.fault = static_cast<unsigned int*>(dp);
+        }
+        else
+        {
+            if (hp)
+            {
+                cudaFreeHost(hp);
+            }
+            cudaGetLastError();
+        }
+    }
     char buf[256];
     snprintf(buf, sizeof(buf), "fepb200 0.1 sm_100a %s %d SMs", prop.name, prop.multiProcessorCount);
     c->description = buf;
@@ -875,6 +916,11 @@ int fepb200_destroy(fepb200_ctx* c)
     }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->h_fault)
+    {
+        cudaFreeHost(c->h_fault);
+        c->h_fault = nullptr;
+    }
     if (c->lap_on && c->lap_n > 0)
     {
         const double n = (double)c->lap_n;
@@ -890,11 +936,7 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_pts.release();
     c->h_pts.release();
     c->d_touched.release();
-    c->d_trip4.release();
-    c->d_cjx.release();
-    c->d_dst.release();
-    c->d_qj.release();
-    c->d_tj.release();
+    c->d_trips.release();
     c->d_orig.release();
     c->d_tgid.release();
     c->d_atom_ptr.release();
@@ -1301,11 +1343,7 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     k.n_gid       = ngrp;
     k.n_red_jobs  = (int)jobs.size();
     k.par4        = c->d_par4.ptr;
-    k.trip4       = c->d_trip4.ptr;
-    k.cjx         = c->d_cjx.ptr;
-    k.dst         = c->d_dst.ptr;
-    k.qj          = c->d_qj.ptr;
-    k.tj          = c->d_tj.ptr;
+    k.trips       = c->d_trips.ptr;
     k.fsorted       = c->d_fsorted.ptr;
     k.fshift_sorted = c->d_fshift_sorted.ptr;
     k.ev2         = c->d_ev2.ptr;
@@ -1385,8 +1423,9 @@ int fepb200_get_list(const fepb200_ctx* cc, int* first_entry, int* iinr, int* gi
          * trip layout the kernels evaluate (slot -> original pair), and every pair's trip must agree with its
          * i-entry on (i atom, shift, gid): the read-back proves that the regrouping lost or changed nothing */
         const int           NT = c->n_trips;
-        std::vector<int>    jraw((size_t)E + 1, 0), cjx(32 * (size_t)NT), orig(32 * (size_t)NT), tgid(NT);
-        std::vector<int4>   trip4(NT), ent4(E);
+        std::vector<int>          jraw((size_t)E + 1, 0), orig(32 * (size_t)NT), tgid(NT);
+        std::vector<unsigned int> trips((size_t)NT * FEP_TRIP_WORDS);
+        std::vector<int4>         ent4(E);
         if (E > 0)
         {
             CU_CHECK(c, cudaMemcpy(jraw.data(), c->d_raw_jindex.ptr + c->first_entry, ((size_t)E + 1) * sizeof(int),
@@ -1395,9 +1434,8 @@ int fepb200_get_list(const fepb200_ctx* cc, int* first_entry, int* iinr, int* gi
         }
         if (NT > 0)
         {
-            CU_CHECK(c, cudaMemcpy(cjx.data(), c->d_cjx.ptr, cjx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            CU_CHECK(c, cudaMemcpy(trips.data(), c->d_trips.ptr, trips.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost));
             CU_CHECK(c, cudaMemcpy(orig.data(), c->d_orig.ptr, orig.size() * sizeof(int), cudaMemcpyDeviceToHost));
-            CU_CHECK(c, cudaMemcpy(trip4.data(), c->d_trip4.ptr, NT * sizeof(int4), cudaMemcpyDeviceToHost));
             CU_CHECK(c, cudaMemcpy(tgid.data(), c->d_tgid.ptr, NT * sizeof(int), cudaMemcpyDeviceToHost));
         }
         const int j0 = jraw[0];
@@ -1418,17 +1456,19 @@ int fepb200_get_list(const fepb200_ctx* cc, int* first_entry, int* iinr, int* gi
         }
         std::vector<char> seen(P, 0);
         long long         found = 0;
-        for (size_t slot = 0; slot < cjx.size(); slot++)
+        for (size_t slot = 0; slot < orig.size(); slot++)
         {
-            if (cjx[slot] & FEP_SLOT_PADDING)
+            const unsigned int* tb  = trips.data() + (slot >> 5) * FEP_TRIP_WORDS;
+            const unsigned int  cjx = tb[FEP_TW_CJX + (slot & 31)];
+            if (cjx & FEP_SLOT_PADDING)
             {
                 continue;
             }
-            const int  sidx  = orig[slot];
-            const int4 td    = trip4[slot >> 5];
-            const bool flip  = (td.x & FEP_TRIP_FLIPPED) != 0;
-            const int  owner = td.x & (FEP_MAX_TOUCHED - 1), other = cjx[slot] & (FEP_MAX_TOUCHED - 1);
-            const int  sh_e  = (td.x >> 24) & 63;
+            const int          sidx  = orig[slot];
+            const unsigned int head  = tb[FEP_TH_OWNER];
+            const bool         flip  = (head & FEP_TRIP_FLIPPED) != 0;
+            const int          owner = (int)(head & (FEP_MAX_TOUCHED - 1)), other = (int)(cjx & (FEP_MAX_TOUCHED - 1));
+            const int          sh_e  = (int)((head >> 24) & 63);
             const int  ci = flip ? other : owner, cj = flip ? owner : other;
             const int  sh = flip ? FEP_NUM_SHIFT - 1 - sh_e : sh_e;
             if (sidx < 0 || sidx >= P || seen[sidx])
@@ -1448,7 +1488,7 @@ int fepb200_get_list(const fepb200_ctx* cc, int* first_entry, int* iinr, int* gi
             }
             if (excl_fep)
             {
-                excl_fep[sidx] = cjx[slot] < 0 ? 0 : 1;
+                excl_fep[sidx] = (cjx & 0x80000000u) ? 0 : 1;
             }
         }
         if (found != P)
@@ -1905,7 +1945,7 @@ int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks,
     }
     const int err = fep_launch_peer_reduce(&pp, d_peer_flags ? &ff : nullptr, rank, seq, nranks, c->ka.res_f64,
                                            (int)c->layout.f64_words, c->res_f64_bytes, c->ka.res_f32,
-                                           c->layout.f32_words, c->stream, &c->launches, c->chain_open ? 1 : 0);
+                                           c->layout.f32_words, c->stream, &c->launches, c->chain_open ? 1 : 0, c->ka.fault);
     if (c->chain_open)
     {
         c->chain_open = false;
@@ -1950,7 +1990,7 @@ size_t fepb200_exchange_bytes(const fepb200_ctx* c, int nranks)
     const size_t    ctas    = (size_t)((tpr + 3) / 4 + 1);
     const size_t    np      = (size_t)std::max(c->layout.nforeign + 1, 32);
     const size_t    slot    = up((P + H) * sizeof(float4)) + up(H * sizeof(float4)) + up(H * sizeof(float2))
-                        + up(2 * ctas * sizeof(double)) + up(3 * np * ctas * sizeof(double));
+                        + up(4 * ctas * sizeof(double)) + up(3 * np * ctas * sizeof(double));
     return 2 * slot + 256;
 }
 
@@ -2028,8 +2068,8 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
         CU_CHECK(c, c->d_slot_src.reserve(std::max<size_t>((size_t)P + H, 1)));
         CU_CHECK(c, c->d_fshift_src.reserve(std::max(H, 1)));
         CU_CHECK(c, c->d_ev2_src.reserve(std::max(H, 1)));
-        const int err = fep_launch_source_tables(c->d_cjx.ptr, c->d_dst.ptr, c->d_trip4.ptr, H, (int)tpr, c->d_slot_src.ptr,
-                                                 c->d_fshift_src.ptr, c->d_ev2_src.ptr, c->stream, &c->launches);
+        const int err = fep_launch_source_tables(c->d_trips.ptr, H, (int)tpr, c->d_slot_src.ptr, c->d_fshift_src.ptr,
+                                                 c->d_ev2_src.ptr, c->stream, &c->launches);
         if (err != 0)
         {
             c->px_on = false;

@@ -92,10 +92,14 @@ def test_ranks_on_one_device_reproduce_the_single_context_result(kind, nranks):
     want = oracle.run_best(prob, ALL)
     rms = np.sqrt(np.mean((f_sum - want["f"]) ** 2) / np.mean(want["f"] ** 2))
     assert rms < 1e-5
+    # sums over sorted slots (shift forces; Vc/Vv per energy-group pair when there are several) are bit-identical to the
+    # single-GPU result; sums over per-CTA partials (dV/dlambda, foreign energies, Vc/Vv of a single energy-group
+    # pair) follow the launch geometry, which differs between one GPU and a share of the list
+    exact = ("fshift", "Vc", "Vv") if prob.nenergrp_pairs > 1 else ("fshift",)
     for out in outs:
-        for k in ("fshift", "Vc", "Vv"):
+        for k in exact:
             assert np.array_equal(out[k], one[k]), k
-        for k in ("dvdl", "foreign_energy", "foreign_dvdl"):
+        for k in ("dvdl", "foreign_energy", "foreign_dvdl") + (() if prob.nenergrp_pairs > 1 else ("Vc", "Vv")):
             scale = np.maximum(np.abs(want[k]), 1e-2 * np.max(np.abs(want[k])))
             assert np.all(np.abs(out[k] - want[k]) <= 1e-4 * scale), k
             assert np.allclose(out[k], one[k], rtol=1e-6, atol=1e-6 * np.max(np.abs(one[k]))), k
@@ -110,9 +114,9 @@ def test_flag_subsets_and_switching_the_exchange_off():
         one = _single(prob, flags)
         outs, _, _ = _run_ranks(prob, 2, flags)
         assert np.array_equal(outs[0]["f"] + outs[1]["f"], one["f"])
-        for k in ("Vc", "Vv", "fshift"):
-            assert np.array_equal(outs[1][k], one[k]), (flags, k)
-        assert np.allclose(outs[0]["dvdl"], one["dvdl"], rtol=1e-6, atol=1e-6 * np.max(np.abs(one["dvdl"])) + 1e-30)
+        assert np.array_equal(outs[1]["fshift"], one["fshift"]), flags
+        for k in ("Vc", "Vv", "dvdl"):
+            assert np.allclose(outs[1][k], one[k], rtol=1e-6, atol=1e-6 * np.max(np.abs(one[k])) + 1e-30), (flags, k)
     # nranks = 1 restores the plain single-GPU path on the same context
     import torch
 
