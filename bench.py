@@ -14,13 +14,18 @@ Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, device time (CU
 ranks), L2 flushed between steps.  `e2e`: the same step through the public call with HOST buffers
 (fepb200_compute: pinned staging, H2D of the touched coordinates, kernels, the result block written
 into pinned host memory by the last kernel, scatter-add into the caller's force array; at N > 1
-upload / kernels + reduction / download of the result block), wall clock.  `roofline`: the dominant kernel
-(fep_foreign_kernel) against the FP32 pipe.  `cpu_baseline` / --impl reference: the reference's
-own CPU SIMD kernel (oracle/_ref, compiled from the reference's sources) on this box's host cores.
+upload / kernels + reduction / download of the result block), wall clock.  `roofline`: the kernel that took
+longest in THIS run (per-kernel CUDA events) against the FP32 pipe by the reference's own flop count, every kernel
+of the step beside it, each with the executed-instruction view from the committed ncu capture of the same sources
+(profiles/r02_ncu_counters.json, tools/ncu_counters.py; ignored when the kernel sources have changed since).
+`every_step`: the force-only step (L = 0), what a production run pays on every MD step.  `configs`: C1-C4 on the
+same GPU (N = 1).  `cpu_baseline` / --impl reference: the reference's own CPU SIMD kernel (oracle/_ref, compiled
+from the reference's sources) on this box's host cores.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -118,18 +123,43 @@ def _workload(problem):
     return dict(pairs=nb.nrj, entries=nb.nri, passes=passes, units_per_step=nb.nrj * passes)
 
 
-def _config(problem, name, world, extra=None):
+def _config(problem, name, extra=None):
+    """What is computed: the same for every arm and every N (how it is run is under `run`)."""
     nb = problem.nblist
     cfg = dict(workload=f"{name}: {problem.natoms}-atom synthetic water box, {len(problem.perturbed)} perturbed atoms, "
                         f"{nb.nrj} perturbed pairs in {nb.nri} i-entries, {problem.n_foreign} foreign lambda",
                natoms=problem.natoms, pairs=nb.nrj, entries=nb.nri, n_foreign=problem.n_foreign,
                energy_group_pairs=problem.nenergrp_pairs,
                passes_per_step=1 + problem.n_foreign + 1,
-               flags="FORCE|SHIFTFORCE|POTENTIAL|FOREIGNLAMBDA",
-               parallelism=f"pair-list shards x{world}", l2="flushed between timed steps (512 MiB write)")
+               flags="FORCE|SHIFTFORCE|POTENTIAL|FOREIGNLAMBDA")
     if extra:
         cfg.update(extra)
     return cfg
+
+
+def _source_hash():
+    """sha256 over the kernel sources: ties profiles/r02_ncu_counters.json to the code it was captured from."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "gromacs-fep-gpu_b200", "csrc")
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, fn), "rb") as fh:
+                h.update(fn.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def _ncu_counters(name):
+    """Per-kernel counters of the committed ncu capture for this workload, or (None, why)."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_counters.json")
+    if not os.path.exists(path):
+        return None, "profiles/r02_ncu_counters.json not present"
+    with open(path) as fh:
+        d = json.load(fh)
+    if d.get("source_hash") != _source_hash():
+        return None, f"profiles/r02_ncu_counters.json was captured from other kernel sources ({d.get('source_hash')} != {_source_hash()})"
+    if name not in d.get("workloads", {}):
+        return None, f"no ncu capture of {name} in profiles/r02_ncu_counters.json"
+    return d["workloads"][name], d.get("captured_with", "")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -215,8 +245,8 @@ def run_reference_gpu_arm(args, name):
     line = dict(impl="reference-gpu", metric=METRIC, value=wl["units_per_step"] / t, unit=UNIT, n_gpus=1, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=t * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="f32", data="synthetic",
-                config=_config(problem, name, 1, dict(parallelism="1 GPU", l2="warm (best of the repeats)",
-                                                      energy_group_pairs=1)),
+                config=_config(problem, name, dict(energy_group_pairs=1)),
+                run=dict(parallelism="1 GPU", l2="warm (best of the repeats)"),
                 kernel_ms=dict(current_lambda_kernel=r["seconds"][0] * 1e3, foreign_kernel=r["seconds"][1] * 1e3),
                 note="k_calc_nb_fep + k_calc_nb_fep_foreign of the fork (nbnxm/cuda/nbnxm_cuda.cu:755-851), kernels only")
     print(json.dumps(line), flush=True)
@@ -234,8 +264,8 @@ def run_reference_arm(args, name):
     cpu = cpu_reference(problem, flags, args.steps, args.warmup, budget_s=120.0)
     line = dict(impl="reference", metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=cpu.pop("ms_per_step"), higher_is_better=True, scaling="strong",
-                vs_baseline=None, dtype="f32", data="synthetic", config=_config(problem, name, 1, dict(
-                    parallelism=f"OpenMP x{cpu['cores']} host threads", l2="n/a (CPU)")),
+                vs_baseline=None, dtype="f32", data="synthetic", config=_config(problem, name),
+                run=dict(parallelism=f"OpenMP x{cpu['cores']} host threads", l2="n/a (CPU)"),
                 cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -261,6 +291,64 @@ def _fork_gpu_beside(args, name):
                          "whole step incl. the reduction epilogue with L2 flushed between steps")
     except Exception as exc:  # noqa: BLE001 -- a reported baseline must not take the bench down
         return dict(unavailable=f"{type(exc).__name__}: {exc}"[:300])
+
+
+def _side_config(name, device, flush, steps):
+    """One more BASELINE.json configuration on this GPU: device time per step (L2 flushed between steps, inputs resident),
+    the same through fepb200_compute with host buffers, per-kernel times."""
+    import torch
+
+    from fepb200 import params as P
+    from fepb200.lib import FepContext
+    from fepb200.synth import make_system
+
+    prob = make_system(name)
+    wl = _workload(prob)
+    flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
+    with FepContext(device) as ctx:
+        ctx.set_problem(prob)
+        ctx.upload_x(prob.x, prob.shiftvec)
+        for _ in range(3):
+            ctx.launch(flags)
+        ctx.wait()
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ctx.launch(flags)
+            ctx.wait()
+            ms.append(ctx.last_launch_ms())
+        fo = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ctx.launch(P.DO_FORCE)
+            ctx.wait()
+            fo.append(ctx.last_launch_ms())
+        ctx.set_profiling(True)
+        rows = []
+        for _ in range(min(steps, 10)):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ctx.launch(flags)
+            ctx.wait()
+            rows.append(ctx.kernel_ms())
+        ctx.set_profiling(False)
+        out = ctx.new_outputs()
+        x = np.ascontiguousarray(prob.x)
+        for _ in range(3):
+            ctx.compute(x, prob.shiftvec, flags | P.CLEAR_OUTPUTS, out)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.compute(x, prob.shiftvec, flags | P.CLEAR_OUTPUTS, out)
+        e2e = (time.perf_counter() - t0) / steps
+    t = sum(ms) / len(ms)
+    return dict(config=_config(prob, name), ms_per_step=t, value=wl["units_per_step"] / (t * 1e-3), unit=UNIT,
+                force_only_ms_per_step=sum(fo) / len(fo),
+                kernel_ms=dict(zip(("pass_kernel", "foreign_kernel", "epilogue_kernel"),
+                                   (sum(r[j] for r in rows) / len(rows) for j in range(3)))),
+                e2e=dict(ms_per_step=e2e * 1e3, value=wl["units_per_step"] / e2e, note="host buffers, L2 not flushed"),
+                steps=steps)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -342,16 +430,36 @@ def run_ours(args, name):
     ms_per_step = dev_ms / args.steps
     value = wl["units_per_step"] / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel: per-kernel CUDA events, same launches -----------
-    ctx.set_profiling(True)
-    kms = []
-    for i in range(args.steps):
-        flush.zero_()
-        sh.launch(flags)
+    # ---- per-kernel times of the same launches: CUDA events of the library around every kernel ------
+    def kernel_times(fl, steps):
+        ctx.set_profiling(True)
+        rows = []
+        for _ in range(steps):
+            flush.zero_()
+            sh.launch(fl)
+            torch.cuda.synchronize()
+            rows.append(ctx.kernel_ms())
+        ctx.set_profiling(False)
+        return [sum(k[j] for k in rows) / len(rows) for j in range(3)]
+
+    def device_ms(fl, steps):
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for _ in range(3):
+            flush.zero_()
+            sh.launch(fl)
+        barrier()
         torch.cuda.synchronize()
-        kms.append(ctx.kernel_ms())
-    ctx.set_profiling(False)
-    k_pass, k_foreign, k_epi = (sum(k[j] for k in kms) / len(kms) for j in range(3))
+        for i in range(steps):
+            flush.zero_()
+            ev0[i].record()
+            sh.launch(fl)
+            ev1[i].record()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))) / steps
+
+    k_pass, k_foreign, k_epi = kernel_times(flags, args.steps)
     my_pairs, my_entries, my_atoms = int(lay.nrj), int(lay.nri), int(lay.ntouched)
     if sh.reduction == "fused":
         # every rank holds the full layout, evaluates its share of the pairs and owns a range of atoms
@@ -363,48 +471,82 @@ def run_ours(args, name):
     peaks = _peaks()
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     fp32_peak = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    # The dominant kernel is the one that evaluates the L+1 foreign-lambda passes.  On small lists the
-    # library fuses the current-lambda pass into the same launch (then k_pass ~ 0 and the launch does
-    # L+2 passes); algorithmic flop = the reference's own count per pass (nb_free_energy.cpp:1181-1186).
+    issue_peak = sms * 4 * peaks["sm_max_mhz"] * 1e6  # warp instructions per second: 4 schedulers per SM, 1 per clock
+    # On small lists the library fuses the current-lambda pass into the launch of the foreign passes (then the
+    # "pass" events bracket nothing and the launch does L+2 passes).
     fused = k_pass < 0.25 * k_foreign and k_pass < 0.004
-    passes_in_launch = points + (1 if fused else 0)
-    alg_flop = (FLOP_PER_PAIR * my_pairs + FLOP_PER_ENTRY * my_entries) * passes_in_launch
-    achieved = alg_flop / (k_foreign * 1e-3) / 1e12 if k_foreign > 0 else 0.0
-    # algorithmic bytes of the step (pair records + touched-atom data + result), for the HBM view
-    alg_bytes = my_pairs * 16 + int(lay.ntouched) * (12 + 16 + 12)
-    dominant = "fep_beutler_kernel" if problem.params.softcoreType == 0 and problem.params.alphaVdw != 0 \
-        and problem.params.vdw_modifier != 3 else "fep_foreign_kernel"
-    roofline = dict(bound="fp32", kernel=dominant + (" (current-lambda pass fused in)" if fused else " (foreign-lambda passes)"),
-                    achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
-                    frac=achieved / fp32_peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
-                    # ncu --set full capture committed as profiles/r01_ncu_full_final_raw.csv (C5, 1 GPU)
-                    traffic=17102080 if (name == "C5" and world == 1) else None,
-                    note="achieved = ALGORITHMIC flop (150/pair + 12/i-entry per lambda pass, the reference's count) / kernel time; "
-                         "the kernel hoists everything lambda-independent out of the pass loop, so the executed "
-                         "FP32 instruction count per pass is far below 150 and frac can exceed 1; "
-                         "see profiles/ for executed-instruction pipe utilisation",
-                    peak_source=f"{sms} SMs x 128 lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
-                    algorithmic_flop_per_launch=alg_flop, passes_in_launch=passes_in_launch,
-                    kernel_ms=dict(pass_kernel=k_pass, foreign_kernel=k_foreign, epilogue_kernel=k_epi),
-                    pair_points_per_s=my_pairs * passes_in_launch / (k_foreign * 1e-3) if k_foreign > 0 else 0.0,
-                    # the whole step against the same roof: all passes the reference would run
-                    # (1 + (L+1)) at its own flop count, over the step's device time (`value`'s clock)
-                    step=dict(algorithmic_flop=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"],
-                              achieved=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"]
-                              / (ms_per_step * 1e-3) / 1e12,
-                              frac=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"]
-                              / (ms_per_step * 1e-3) / 1e12 / (fp32_peak * world)),
-                    # executed work of the same launch: warp instructions from the ncu capture of this kernel on
-                    # this workload (profiles/README.md: 11.4 M for the 21-point foreign launch on C5) over the live
-                    # kernel time, against the issue rate of the chip (4 schedulers x 1 warp instruction per clock per SM)
-                    issue=(dict(warp_instructions=11.4e6, source="profiles/r01_ncu_full_final_raw.csv (smsp__inst_executed.sum)",
-                                peak_per_s=sms * 4 * peaks["sm_max_mhz"] * 1e6,
-                                frac=11.4e6 / (k_foreign * 1e-3) / (sms * 4 * peaks["sm_max_mhz"] * 1e6) if k_foreign > 0 else 0.0)
-                           if (name == "C5" and world == 1 and not fused and args.n_foreign is None) else None),
-                    hbm=dict(algorithmic_bytes_per_step=alg_bytes,
-                             achieved_gbs=alg_bytes / ((k_pass + k_foreign + k_epi) * 1e-3) / 1e9,
+    flop_pass = FLOP_PER_PAIR * my_pairs + FLOP_PER_ENTRY * my_entries  # the reference's count, one lambda pass
+    counters, counters_note = (None, "multi-GPU run") if world > 1 or args.n_foreign is not None else _ncu_counters(name)
+
+    def kernel_view(key, label, ms, passes):
+        """One kernel of the step: algorithmic flop (the reference's count x passes) over the live time, and -- when the
+        committed ncu capture belongs to these sources -- executed warp instructions over the live time."""
+        v = dict(kernel=label, ms=ms, passes=passes)
+        if passes > 0 and ms > 0:
+            v["algorithmic_flop"] = flop_pass * passes
+            v["achieved_tflops"] = flop_pass * passes / (ms * 1e-3) / 1e12
+            v["flop_frac_of_fp32_peak"] = v["achieved_tflops"] / fp32_peak
+        c = (counters or {}).get(key)
+        if c and ms > 0:
+            v["ncu"] = c
+            v["issue_frac_live"] = c["inst_executed"] / (ms * 1e-3) / issue_peak
+        return v
+
+    views = []
+    if not fused:
+        views.append(kernel_view("pass", "current-lambda force pass (fep_beutler_kernel<C=0,FORCE> / fep_pass_kernel)", k_pass, 1))
+    views.append(kernel_view("foreign", "foreign-lambda passes" + (" + current-lambda pass, one launch" if fused else ""),
+                             k_foreign, points + (1 if fused else 0)))
+    views.append(kernel_view("epilogue", "fep_epilogue_kernel (per-atom force sums, shift forces, scalars)", k_epi, 0))
+    dominant = max(views, key=lambda v: v["ms"])
+    # epilogue: a streaming sum, bounded by bytes -- contributions read + forces written
+    epi_bytes = 16 * (my_pairs + my_pairs // 32 + 1) + 12 * my_atoms
+    views[-1]["algorithmic_bytes"] = epi_bytes
+    views[-1]["achieved_gbs"] = epi_bytes / (k_epi * 1e-3) / 1e9 if k_epi > 0 else 0.0
+    views[-1]["frac_of_hbm_peak"] = views[-1]["achieved_gbs"] / peaks["hbm_gbs"]
+    step_flop = (FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) * wl["passes"]
+    if "achieved_tflops" in dominant:
+        d_ach, d_frac = dominant["achieved_tflops"], dominant["flop_frac_of_fp32_peak"]
+    else:
+        d_ach, d_frac = views[-1]["achieved_gbs"], views[-1]["frac_of_hbm_peak"]
+    frac_kind = "algorithmic flop / FP32 peak"
+    if d_frac > 1.0:
+        # The foreign-lambda launch hoists everything lambda-independent out of its point loop, so it EXECUTES far
+        # fewer than 150 flop per pair-point and the flop count says nothing about hardware use: report what the
+        # hardware did instead (issue slots used while the kernel ran), and keep the flop figure beside it.
+        if "issue_frac_live" in dominant:
+            d_frac, frac_kind = dominant["issue_frac_live"], "executed warp instructions (ncu) / live time / issue peak"
+        else:
+            d_frac, frac_kind = None, "algorithmic flop exceeds the FP32 peak (hoisted lambda loop); no ncu counters for these sources"
+    roofline = dict(bound="fp32" if "achieved_tflops" in dominant else "hbm", kernel=dominant["kernel"],
+                    achieved=d_ach, peak=fp32_peak if "achieved_tflops" in dominant else peaks["hbm_gbs"],
+                    unit="TFLOP/s" if "achieved_tflops" in dominant else "GB/s", frac=d_frac, frac_is=frac_kind,
+                    algorithmic_frac=dominant.get("flop_frac_of_fp32_peak"),
+                    traffic=(dominant.get("ncu") or {}).get("dram_bytes"),
+                    kernels=views, counters_note=counters_note,
+                    note="achieved = ALGORITHMIC flop (150 per pair + 12 per i-entry per lambda pass, the reference's own count, "
+                         "nb_free_energy.cpp:1181-1186) / live kernel time (CUDA events of this run); `kernel` is the kernel that took "
+                         "longest in this run",
+                    peak_source=f"{sms} SMs x 128 lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz; "
+                                "MEASURED_PEAKS.json has no FP32 entry)",
+                    step=dict(algorithmic_flop=step_flop, achieved=step_flop / (ms_per_step * 1e-3) / 1e12,
+                              frac=step_flop / (ms_per_step * 1e-3) / 1e12 / (fp32_peak * world)),
+                    hbm=dict(algorithmic_bytes_per_step=my_pairs * 22 + int(lay.ntouched) * (12 + 12) + epi_bytes,
                              peak_gbs=peaks["hbm_gbs"]))
+
+    # ---- the every-step path: forces only, no foreign lambda (L = 0) ---------------------------------------------
+    f_only = P.DO_FORCE
+    fo_ms = device_ms(f_only, args.steps)
+    fo_k = kernel_times(f_only, min(args.steps, 20))
+    every_step = dict(flags="FORCE", ms_per_step=fo_ms, pairs_per_s=wl["pairs"] / (fo_ms * 1e-3),
+                      kernel_ms=dict(pass_kernel=fo_k[0], epilogue_kernel=fo_k[2]),
+                      achieved_tflops=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) / (fo_ms * 1e-3) / 1e12,
+                      frac_of_fp32_peak=(FLOP_PER_PAIR * wl["pairs"] + FLOP_PER_ENTRY * wl["entries"]) / (fo_ms * 1e-3) / 1e12
+                      / (fp32_peak * world),
+                      note="what a production FEP run pays on every MD step (foreign energies only every nstdhdl steps): device "
+                           "time of pass + epilogue, L2 flushed between steps")
+    fv_ms = device_ms(P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL, min(args.steps, 50))
+    every_step["with_energies_and_virial_ms"] = fv_ms
 
     # ---- e2e: host buffers through the public call ------------------------------------------
     out = ctx.new_outputs()
@@ -458,16 +600,30 @@ def run_ours(args, name):
         fork_gpu = None
         if world == 1 and not args.no_fork_gpu:
             fork_gpu = _fork_gpu_beside(args, name)
+        # C1-C4 on the same GPU (N = 1 only): their own ms_per_step, value and e2e
+        side = None
+        if world == 1 and not args.no_side_configs and args.n_foreign is None:
+            side = {}
+            for other in ("C1", "C2", "C3", "C4", "C5"):
+                if other != name:
+                    try:
+                        side[other] = _side_config(other, local, flush, min(args.steps, 30))
+                    except Exception as exc:  # noqa: BLE001 -- a side line must not take the bench down
+                        side[other] = dict(unavailable=f"{type(exc).__name__}: {exc}"[:300])
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
-                    data="synthetic", config=_config(problem, name, world, dict(
-                        reduction=sh.reduction if world > 1 else "none",
-                        outputs="forces reduce-scattered by atom range, scalars on every rank" if sh.reduction == "fused"
-                        else "full result on every rank")),
+                    data="synthetic", config=_config(problem, name),
+                    run=dict(parallelism=f"pair-list shards x{world}", l2="flushed between timed steps (512 MiB write)",
+                             reduction=sh.reduction if world > 1 else "none",
+                             outputs="forces reduce-scattered by atom range, scalars on every rank" if sh.reduction == "fused"
+                             else "full result on every rank"),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=e2e_s / args.steps * 1e3),
-                    gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, cpu_baseline=cpu,
-                    fork_gpu_baseline=fork_gpu,
+                             ms_per_step=e2e_s / args.steps * 1e3,
+                             note="wall clock of the public call with host buffers; the device time of the L2 flush between "
+                                  "steps (measured separately) is subtracted"),
+                    gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, every_step=every_step,
+                    kernel_ms=dict(pass_kernel=k_pass, foreign_kernel=k_foreign, epilogue_kernel=k_epi),
+                    configs=side, cpu_baseline=cpu, fork_gpu_baseline=fork_gpu,
                     wall_ms_per_step_incl_flush=t_wall / args.steps * 1e3, device=ctx.describe())
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
@@ -487,6 +643,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fork-gpu", action="store_true", help="skip the fork's CUDA kernels beside ours (fork_gpu_baseline)")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the C1-C4 sub-lines (configs)")
     ap.add_argument("--n-foreign", type=int, default=None, help="override the number of foreign lambda points")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -38,660 +38,35 @@
  *         Coulomb part needs d^(-1/6) = ex2(-lg2(d)/6).
  * MODE 2: separate Coulomb and LJ radii.
  */
-#include <cstdlib>
-#include <cstring>
+#include "fep_beutler_kernel.cuh"
 
-#include "fep_front.cuh"
+FB_INST_DECL(0, 0);
+FB_INST_DECL(0, 1);
+FB_INST_DECL(0, 2);
+FB_INST_DECL(1, 0);
+FB_INST_DECL(1, 1);
+FB_INST_DECL(1, 2);
+FB_INST_DECL(2, 0);
+FB_INST_DECL(2, 1);
+FB_INST_DECL(2, 2);
 
-#define FULL_MASK 0xffffffffu
-
-struct BeutlerStep
+static bool launch_any(const KernelArgs& ka, const BeutlerStep& bs, bool ewald, int mode, int c, bool force, cudaStream_t stream,
+                       int* occ, bool chained = false)
 {
-    /* current lambda (nb_free_energy.cpp:420-449) */
-    float cur_lfc[2], cur_lfv[2], cur_sclc[2], cur_sclv[2], cur_scdlc[2], cur_scdlv[2];
-    /* chunk of foreign lambda points */
-    float sclv[2][FEP_FB_MAXC]; /* soft-core lambda factor, vdw, per state */
-    float sclc[2][FEP_FB_MAXC]; /* same for coulomb                         */
-    float lfc[2][FEP_FB_MAXC];  /* {1-lambda_c, lambda_c}                   */
-    float lfv[2][FEP_FB_MAXC];
-    int   p0, np;               /* first point of the chunk, valid points   */
-    int   want_shift;           /* also store the trips' forces sorted by shift vector */
-    int   per_trip_energy;      /* more than one energy-group pair: Vc/Vv per trip instead of per CTA */
-    int   tile_trips, n_tiles;  /* tile of trips of one CTA for this launch */
-    int   always_check;         /* a lambda outside [0,1]: no fast path     */
-};
-
-/* sums N8*8 per-lane values over the warp; afterwards lane l < 8 holds, for group g, the value
- * with index 8*g + 4*(l&1) + 2*((l>>1)&1) + ((l>>2)&1) */
-template<int N8>
-__device__ __forceinline__ void warp_sum_groups(float (&v)[N8 * 8], float (&out)[N8], int lane)
-{
-#pragma unroll
-    for (int g = 0; g < N8; g++)
+    /* LJ-PME implies PME electrostatics (the reference's grompp insists) */
+    switch ((ewald ? (ka.vdw_ewald ? 6 : 3) : 0) + mode)
     {
-        float a[4], b[2], c;
-        {
-            const bool up = lane & 1;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-            {
-                const float send = up ? v[8 * g + i] : v[8 * g + i + 4];
-                const float keep = up ? v[8 * g + i + 4] : v[8 * g + i];
-                a[i]             = keep + __shfl_xor_sync(FULL_MASK, send, 1);
-            }
-        }
-        {
-            const bool up = lane & 2;
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-            {
-                const float send = up ? a[i] : a[i + 2];
-                const float keep = up ? a[i + 2] : a[i];
-                b[i]             = keep + __shfl_xor_sync(FULL_MASK, send, 2);
-            }
-        }
-        {
-            const bool  up   = lane & 4;
-            const float send = up ? b[0] : b[1];
-            const float keep = up ? b[1] : b[0];
-            c                = keep + __shfl_xor_sync(FULL_MASK, send, 4);
-        }
-        c += __shfl_xor_sync(FULL_MASK, c, 8);
-        c += __shfl_xor_sync(FULL_MASK, c, 16);
-        out[g] = c;
-    }
-}
-
-/* lambda-independent data of one state of one pair; every coefficient is zero when the term it
- * multiplies does not apply */
-struct StateConsts
-{
-    float c6_6, c12_12, shiftc, kv, kc, qe, qsh, qkrf;
-};
-
-/* One foreign lambda point of one state: LJ energy vv (and Coulomb energy vc when the Coulomb
- * radius is soft-cored).  CHECK = false is the fast path for warps in which no lane needs the
- * lambda-dependent cut-off tests or the r^-6 clamp (see the caller): 5 instructions in MODE 0
- * (FFMA, MUFU.RCP, FFMA, FFMA + the caller's FADD); CHECK = true adds clamp, compare and select. */
-template<bool EWALD, int MODE, bool CHECK>
-__device__ __forceinline__ void fb_point(const StateConsts& st, float r6, float sclv, float sclc, float thr_v,
-                                         float rcoulomb6, float& vv, float& vc)
-{
-    const float dv  = fmaf(st.kv, sclv, r6);
-    float       ri6 = fep_rcp(dv);
-    if (CHECK)
-    {
-        ri6 = fminf(ri6, FEP_MAX_RINV6);
-    }
-    vv = fmaf(ri6, fmaf(st.c12_12, ri6, -st.c6_6), st.shiftc);
-    if (CHECK)
-    {
-        vv = dv < thr_v ? vv : 0.0f;
-    }
-    if (MODE != 0)
-    {
-        const float dc  = (MODE == 1) ? dv : fmaf(st.kc, sclc, r6);
-        const float lg  = fep_lg2(dc);
-        const float ric = fep_ex2(lg * (-1.0f / 6.0f));
-        if (EWALD)
-        {
-            vc = fmaf(st.qe, ric, st.qsh);
-        }
-        else
-        {
-            const float rc2 = fep_ex2(lg * (1.0f / 3.0f));
-            vc              = fmaf(st.qe, ric, fmaf(st.qkrf, rc2, st.qsh));
-            if (CHECK)
-            {
-                vc = dc < rcoulomb6 ? vc : 0.0f;
-            }
-        }
-    }
-}
-
-/* the loop over the C lambda points of a chunk for the states the warp needs */
-template<bool EWALD, int MODE, int C, bool CHECK, bool DO_A, bool DO_B>
-__device__ __forceinline__ void fb_points(const StateConsts (&st)[2], const BeutlerStep& bs, float r6, float thr_v,
-                                          float rcoulomb6, float* acc)
-{
-#pragma unroll
-    for (int p = 0; p < C; p++)
-    {
-        float vvA = 0.0f, vvB = 0.0f, vcA = 0.0f, vcB = 0.0f;
-        if (DO_A)
-        {
-            fb_point<EWALD, MODE, CHECK>(st[0], r6, bs.sclv[0][p], bs.sclc[0][p], thr_v, rcoulomb6, vvA, vcA);
-        }
-        if (DO_B)
-        {
-            fb_point<EWALD, MODE, CHECK>(st[1], r6, bs.sclv[1][p], bs.sclc[1][p], thr_v, rcoulomb6, vvB, vcB);
-        }
-        if (DO_A)
-        {
-            acc[p] += vvA;
-        }
-        acc[C + p] += DO_A ? (DO_B ? vvB - vvA : -vvA) : vvB;
-        if (MODE != 0)
-        {
-            if (DO_A)
-            {
-                acc[2 * C + p] += vcA;
-            }
-            acc[3 * C + p] += DO_A ? (DO_B ? vcB - vcA : -vcA) : vcB;
-        }
-    }
-}
-
-/* One state at the current lambda WITH forces (:747-1020).  Adds to the scalar force (already
- * multiplied by r^(p-2)), the lambda-weighted energies and dV/dlambda incl. the soft-core term. */
-template<bool EWALD, int MODE>
-__device__ __forceinline__ void fb_force_state(const StateConsts& st, const BeutlerStep& bs, int s, float r2, float r6,
-                                               float r4, float rinv, float thr_v, float rcoulomb6, float krf,
-                                               float crf, float sh_ewald, float& fscal, float& vctot, float& vvtot,
-                                               float& dc, float& dv)
-{
-    const float sign = s == 0 ? -1.0f : 1.0f;
-    /* Lennard-Jones with the soft-core radius rV^6 = alpha sigma6 sclfac + r^6 */
-    const float d_v  = fmaf(st.kv, bs.cur_sclv[s], r6);
-    const float rp_v = fep_rcp(d_v);
-    const float ri6  = fminf(rp_v, FEP_MAX_RINV6);
-    const float t12  = st.c12_12 * ri6;
-    float       vv   = fmaf(ri6, t12 - st.c6_6, st.shiftc);
-    float       fv   = ri6 * fmaf(12.0f, t12, -6.0f * st.c6_6); /* V12 - V6 */
-    const bool  on_v = d_v < thr_v;
-    vv               = on_v ? vv : 0.0f;
-    fv               = on_v ? fv : 0.0f;
-    /* F rV^-6 r^4, the two factors combined first (stays in fp32 range for hard cores at r -> 0) */
-    fscal = fmaf(bs.cur_lfv[s] * fv, rp_v * r4, fscal);
-    vvtot = fmaf(bs.cur_lfv[s], vv, vvtot);
-    dv    = fmaf(sign, vv, dv);
-    dv    = fmaf((bs.cur_lfv[s] * bs.cur_scdlv[s] * st.kv) * fv, rp_v, dv); /* (:1010-1012), kv = alphaEff sigma6 */
-
-    float vc, fc, w_c;
-    if (MODE == 0)
-    {
-        /* rC == r */
-        if (EWALD)
-        {
-            vc = st.qe * (rinv - sh_ewald);
-            fc = st.qe * rinv;
-        }
-        else
-        {
-            const float k2 = krf * r2;
-            vc             = st.qe * (rinv + k2 - crf);
-            fc             = st.qe * (rinv - 2.0f * k2);
-        }
-        w_c = rinv * rinv; /* r^-6 r^4 */
-    }
-    else
-    {
-        const float d_c  = (MODE == 1) ? d_v : fmaf(st.kc, bs.cur_sclc[s], r6);
-        const float rp_c = (MODE == 1) ? rp_v : fep_rcp(d_c);
-        const float lg   = fep_lg2(d_c);
-        const float ric  = fep_ex2(lg * (-1.0f / 6.0f));
-        if (EWALD)
-        {
-            vc = fmaf(st.qe, ric, st.qsh);
-            fc = st.qe * ric;
-        }
-        else
-        {
-            const float rc2 = fep_ex2(lg * (1.0f / 3.0f));
-            const float k2  = st.qkrf * rc2;
-            vc              = fmaf(st.qe, ric, k2 + st.qsh);
-            fc              = fmaf(st.qe, ric, -2.0f * k2);
-            const bool on_c = d_c < rcoulomb6;
-            vc              = on_c ? vc : 0.0f;
-            fc              = on_c ? fc : 0.0f;
-        }
-        w_c = rp_c * r4;
-        dc  = fmaf((bs.cur_lfc[s] * bs.cur_scdlc[s] * st.kc) * fc, rp_c, dc); /* (:1007-1009) */
-    }
-    fscal = fmaf(bs.cur_lfc[s] * fc, w_c, fscal);
-    vctot = fmaf(bs.cur_lfc[s], vc, vctot);
-    dc    = fmaf(sign, vc, dc);
-}
-
-template<int MODE, int C, bool FORCE>
-struct AccLayout
-{
-    static constexpr int NPER = (MODE == 0) ? 2 : 4; /* per-point: V_A DV (Cp_A DCp)                */
-    static constexpr int NFOR = C > 0 ? NPER * C + 4 : 0; /* + C_A DC G_A DG                         */
-    static constexpr int NACC = NFOR + (FORCE ? 4 : 0);  /* + dV/dlambda coul, vdw, Vc, Vv at current lambda */
-    static constexpr int N8   = (NACC + 7) / 8;
-    static constexpr int iCA = NPER * C, iDC = iCA + 1, iGA = iCA + 2, iDG = iCA + 3;
-    static constexpr int iCUR = NFOR;
-    /* register budget: 4 CTAs of 128 threads per SM up to ~56 accumulators, else 2 */
-    static constexpr int MINB = (NACC + (FORCE ? 10 : 0) > 56) ? 2 : (NACC > 30 ? 3 : (NACC > 8 ? 4 : 8));
-};
-
-/* sum of v over the warp, valid in every lane */
-__device__ __forceinline__ float fb_warp_sum(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-        v += __shfl_xor_sync(FULL_MASK, v, o);
-    }
-    return v;
-}
-
-extern __shared__ __align__(128) unsigned char fep_dyn_smem[];
-
-template<bool EWALD, int MODE, int C, bool FORCE, bool STAGED>
-__global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
-        fep_beutler_kernel(const __grid_constant__ KernelArgs ka, const __grid_constant__ BeutlerStep bs)
-{
-    using L            = AccLayout<MODE, C, FORCE>;
-    constexpr int N8   = L::N8 > 0 ? L::N8 : 1;
-    constexpr int NW   = FEP_FB_CTA / 32;
-    __shared__ float  s_red[NW][N8 * 8];
-    __shared__ double s_sum[N8 * 8];
-    __shared__ __align__(8) unsigned long long s_bars[FEP_STAGE_CHUNKS];
-    /* the 45 shift vectors are read once per trip with a data-dependent index: keep them on chip */
-    __shared__ float4 s_shift[FEP_NUM_SHIFT];
-
-    const int tid  = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    fep_pdl_launch_dependents(); /* the next kernel of the step may fill SM space we leave free */
-
-    /* this CTA's tile of trips: bulk copies bring its records into shared memory */
-    const int           t0    = ka.trip_begin + blockIdx.x * bs.tile_trips;
-    const int           nt    = min(bs.tile_trips, ka.trip_end - t0);
-    const FepStage      stage = fep_stage_tile<STAGED>(ka, t0, nt, NW, fep_dyn_smem, s_bars);
-    const unsigned int* tile  = stage.tile;
-    if (tid < FEP_NUM_SHIFT)
-    {
-        s_shift[tid] = ka.dyn->shiftvec[tid];
-    }
-
-    /* Layout: [0,C) V_A, [C,2C) DV, MODE>0: [2C,3C) Cp_A, [3C,4C) DCp, then C_A DC G_A DG,
-     * then (FORCE) dV/dlambda_coul, dV/dlambda_vdw, Vc, Vv of the current-lambda pass. */
-    float acc[N8 * 8];
-#pragma unroll
-    for (int i = 0; i < N8 * 8; i++)
-    {
-        acc[i] = 0.0f;
-    }
-    const float thr_v = ka.vdw_ewald ? __int_as_float(0x7f800000) : ka.rvdw6; /* LJ-PME tests r, below */
-    __syncthreads();
-
-    /* warp w takes the trips w, w + NW, ... of the tile; while trip k is evaluated the coordinates and
-     * type-table rows of trip k + NW are in flight */
-    FepFetch nx;
-    if (warp < nt)
-    {
-        fep_stage_wait<STAGED>(stage, s_bars, warp, NW, ka.fault);
-        nx = fep_fetch<STAGED>(ka, tile + warp * FEP_TRIP_WORDS, lane);
-    }
-    for (int lt = warp; lt < nt; lt += NW)
-    {
-        const unsigned int* tb  = tile + lt * FEP_TRIP_WORDS;
-        const FepFetch      cur = nx;
-        if (lt + NW < nt)
-        {
-            fep_stage_wait<STAGED>(stage, s_bars, lt + NW, NW, ka.fault);
-            nx = fep_fetch<STAGED>(ka, tb + NW * FEP_TRIP_WORDS, lane);
-        }
-        FepSlot p = fep_slot<STAGED>(ka, tb, cur, lane, s_shift);
-        /* a padding slot is "a pair far beyond every cut-off": all of its terms vanish below without masks */
-        p.r2 = p.active ? p.r2 : 1.0e6f;
-
-        float nfx, nfy, nfz, vctot = 0.0f, vvtot = 0.0f; /* nf = MINUS the force on the owner = force on the partner */
-        {
-            const float4 ta = p.ta, tb4 = p.tb;
-            const float  qq[2]  = { p.qq[0], p.qq[1] };
-            const float  c6[2]  = { ta.x, tb4.x }, c12[2] = { ta.y, tb4.y }, sig6[2] = { ta.z, tb4.z };
-            const float  c6g[2] = { ta.w, tb4.w };
-            const bool   hard   = (ta.y > 0.0f && tb4.y > 0.0f); /* :597-628 */
-            const float  a_v    = hard ? 0.0f : ka.alpha_v;
-            const float  a_c    = hard ? 0.0f : ka.alpha_c;
-
-            FepPair pr;
-            const float r2 = fmaxf(p.r2, FEP_MIN_RSQ);
-            pr.r2   = r2;
-            pr.rinv = fep_rsqrt(r2);
-            pr.r    = r2 * pr.rinv;
-            const float r4   = r2 * r2;
-            const float r6   = r4 * r2;
-            const bool  incl = p.contrib && p.within && !p.excluded;
-
-            float fscal = 0.0f, dcur_c = 0.0f, dcur_v = 0.0f;
-
-            /* lambda-independent correction terms, linear in qq[s] / c6grid[s]; zero beyond the cut-offs
-             * unless the pair is an exclusion (:1023-1136) */
-            {
-                float xc, fcorr, xv, fvcorr;
-                fep_corrections<EWALD, FORCE>(ka, pr, p.excluded, p.self, xc, fcorr, xv, fvcorr);
-                const float cA = qq[0] * xc, cB = qq[1] * xc, gA = c6g[0] * xv, gB = c6g[1] * xv;
-                if (C > 0)
-                {
-                    acc[L::iCA] += cA;
-                    acc[L::iDC] += cB - cA;
-                    acc[L::iGA] += gA;
-                    acc[L::iDG] += gB - gA;
-                }
-                if (FORCE)
-                {
-                    vctot  = bs.cur_lfc[0] * cA + bs.cur_lfc[1] * cB;
-                    vvtot  = bs.cur_lfv[0] * gA + bs.cur_lfv[1] * gB;
-                    dcur_c = cB - cA;
-                    dcur_v = gB - gA;
-                    fscal  = (bs.cur_lfc[0] * qq[0] + bs.cur_lfc[1] * qq[1]) * fcorr
-                            + (bs.cur_lfv[0] * c6g[0] + bs.cur_lfv[1] * c6g[1]) * fvcorr;
-                }
-            }
-
-            StateConsts st[2];
-            bool        elec_on[2], vdw_on[2];
-#pragma unroll
-            for (int s = 0; s < 2; s++)
-            {
-                /* the state takes part if any of qq, c6, c12 is non-zero (:747-752), which each of the two
-                 * tests below implies; then the lambda-independent parts of the interaction tests (:805-812,
-                 * :880-890) */
-                elec_on[s] = incl && qq[s] != 0.0f;
-                vdw_on[s]  = incl && (c6[s] != 0.0f || c12[s] != 0.0f);
-                if (EWALD || MODE == 0)
-                {
-                    elec_on[s] = elec_on[s] && pr.r < ka.rcoulomb;
-                }
-                if (ka.vdw_ewald)
-                {
-                    vdw_on[s] = vdw_on[s] && pr.r < ka.rvdw;
-                }
-                st[s].qe     = elec_on[s] ? qq[s] : 0.0f;
-                st[s].c6_6   = vdw_on[s] ? c6[s] * (1.0f / 6.0f) : 0.0f;
-                st[s].c12_12 = vdw_on[s] ? c12[s] * (1.0f / 12.0f) : 0.0f;
-                st[s].shiftc = st[s].c12_12 * ka.rep_cpot - st[s].c6_6 * ka.disp_cpot;
-                if (ka.vdw_ewald)
-                {
-                    st[s].shiftc = fmaf(vdw_on[s] ? c6g[s] : 0.0f, ka.sh_lj_ewald * (1.0f / 6.0f), st[s].shiftc);
-                }
-                st[s].kv   = a_v * sig6[s];
-                st[s].kc   = a_c * sig6[s];
-                st[s].qsh  = EWALD ? -st[s].qe * ka.sh_ewald : -st[s].qe * ka.crf;
-                st[s].qkrf = st[s].qe * ka.krf;
-            }
-            if (C > 0 && MODE == 0)
-            {
-                /* Coulomb radius not soft-cored: rC == r, the whole term is lambda-independent */
-                const float k2  = EWALD ? -ka.sh_ewald : fmaf(ka.krf, r2, -ka.crf);
-                const float vcA = st[0].qe * (pr.rinv + k2), vcB = st[1].qe * (pr.rinv + k2);
-                acc[L::iCA] += vcA;
-                acc[L::iDC] += vcB - vcA;
-            }
-            /* a state nobody in the warp needs is skipped; the choice is made once per 32 pairs */
-            const bool needA = __any_sync(FULL_MASK, vdw_on[0] || elec_on[0]);
-            const bool needB = __any_sync(FULL_MASK, vdw_on[1] || elec_on[1]);
-
-            if (FORCE)
-            {
-                if (needA)
-                {
-                    fb_force_state<EWALD, MODE>(st[0], bs, 0, r2, r6, r4, pr.rinv, thr_v, ka.rcoulomb6, ka.krf, ka.crf,
-                                                ka.sh_ewald, fscal, vctot, vvtot, dcur_c, dcur_v);
-                }
-                if (needB)
-                {
-                    fb_force_state<EWALD, MODE>(st[1], bs, 1, r2, r6, r4, pr.rinv, thr_v, ka.rcoulomb6, ka.krf, ka.crf,
-                                                ka.sh_ewald, fscal, vctot, vvtot, dcur_c, dcur_v);
-                }
-                const float nfs = -fscal;
-                nfx             = nfs * p.dx;
-                nfy             = nfs * p.dy;
-                nfz             = nfs * p.dz;
-                acc[L::iCUR]     += dcur_c;
-                acc[L::iCUR + 1] += dcur_v;
-            }
-
-            if (C > 0)
-            {
-                /* Per lane and state the lambda-dependent tests fall in one of three classes, because
-                 * the soft-core radius satisfies r^6 <= rV^6 <= r^6 + alphaEff sigma6 for every lambda:
-                 * always outside (r^6 >= rc^6: coefficients zeroed here), always inside, or borderline.
-                 * Only warps with a borderline lane, or a lane so close that r^-6 needs its clamp,
-                 * take the loop with the per-point tests. */
-                bool slow = (r6 < 1.0e-15f && incl) || bs.always_check != 0;
-#pragma unroll
-                for (int s = 0; s < 2; s++)
-                {
-                    if (vdw_on[s])
-                    {
-                        if (r6 >= thr_v)
-                        {
-                            st[s].c6_6 = st[s].c12_12 = st[s].shiftc = 0.0f;
-                            vdw_on[s]                                = false;
-                        }
-                        else
-                        {
-                            slow = slow || (r6 + st[s].kv >= thr_v);
-                        }
-                    }
-                    if (MODE != 0 && !EWALD && elec_on[s])
-                    {
-                        if (r6 >= ka.rcoulomb6)
-                        {
-                            st[s].qe = st[s].qsh = st[s].qkrf = 0.0f;
-                            elec_on[s]                        = false;
-                        }
-                        else
-                        {
-                            slow = slow || (r6 + st[s].kc >= ka.rcoulomb6);
-                        }
-                    }
-                }
-                const bool pA   = __any_sync(FULL_MASK, vdw_on[0] || (MODE != 0 && elec_on[0]));
-                const bool pB   = __any_sync(FULL_MASK, vdw_on[1] || (MODE != 0 && elec_on[1]));
-                const bool chk  = __any_sync(FULL_MASK, slow);
-                if (!chk)
-                {
-                    if (pA && pB)
-                    {
-                        fb_points<EWALD, MODE, C, false, true, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
-                    }
-                    else if (pA)
-                    {
-                        fb_points<EWALD, MODE, C, false, true, false>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
-                    }
-                    else if (pB)
-                    {
-                        fb_points<EWALD, MODE, C, false, false, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
-                    }
-                }
-                else
-                {
-                    if (pA && pB)
-                    {
-                        fb_points<EWALD, MODE, C, true, true, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
-                    }
-                    else if (pA)
-                    {
-                        fb_points<EWALD, MODE, C, true, true, false>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
-                    }
-                    else if (pB)
-                    {
-                        fb_points<EWALD, MODE, C, true, false, true>(st, bs, r6, thr_v, ka.rcoulomb6, acc);
-                    }
-                }
-            }
-        }
-
-        if (FORCE)
-        {
-            if (p.active)
-            {
-                /* the partner receives -f: scattered to this pair's own slot in the atom-sorted
-                 * buffer (unique destination, no atomics; skipped pairs write their zero) */
-                ka.fsorted[fep_tw<STAGED>(tb + FEP_TW_DST + lane)] = make_float4(nfx, nfy, nfz, 0.0f);
-            }
-            /* the owner receives the sum over the trip */
-            nfx = fb_warp_sum(nfx);
-            nfy = fb_warp_sum(nfy);
-            nfz = fb_warp_sum(nfz);
-            if (bs.per_trip_energy)
-            {
-                /* several energy-group pairs: the trip's Vc/Vv go to the trip's pair */
-                vctot = fb_warp_sum(vctot);
-                vvtot = fb_warp_sum(vvtot);
-            }
-            else
-            {
-                acc[L::iCUR + 2] += vctot;
-                acc[L::iCUR + 3] += vvtot;
-            }
-            if (lane == 0)
-            {
-                ka.fsorted[fep_tw<STAGED>(tb + FEP_TH_SLOT_F)] = make_float4(-nfx, -nfy, -nfz, 0.0f);
-                if (bs.want_shift)
-                {
-                    /* nb_free_energy.cpp:1153-1164 adds the i atom's force to the entry's shift vector; for
-                     * a flipped trip the owner was the j atom, whose force is minus that */
-                    const float sg = (cur.head & FEP_TRIP_FLIPPED) ? 1.0f : -1.0f;
-                    ka.fshift_sorted[fep_tw<STAGED>(tb + FEP_TH_SLOT_SHIFT)] = make_float4(sg * nfx, sg * nfy, sg * nfz, 0.0f);
-                }
-                if (bs.per_trip_energy)
-                {
-                    ka.ev2[fep_tw<STAGED>(tb + FEP_TH_SLOT_EV)] = make_float2(vctot, vvtot);
-                }
-            }
-        }
-    }
-
-    if (L::NACC == 0)
-    {
-        fep_pdl_wait();
-        return;
-    }
-    float red[N8];
-    warp_sum_groups<N8>(acc, red, lane);
-    if (lane < 8)
-    {
-        const int k = 4 * (lane & 1) + 2 * ((lane >> 1) & 1) + ((lane >> 2) & 1);
-#pragma unroll
-        for (int g = 0; g < N8; g++)
-        {
-            s_red[warp][8 * g + k] = red[g];
-        }
-    }
-    __syncthreads();
-    if (tid < L::NACC)
-    {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; w++)
-        {
-            s += (double)s_red[w][tid];
-        }
-        s_sum[tid] = s;
-    }
-    __syncthreads();
-    if (FORCE && tid < 4)
-    {
-        /* rows: dV/dlambda coul, vdw; Vc, Vv (the latter two only meaningful with one energy-group pair) */
-        ka.cta_part[(size_t)tid * bs.n_tiles + blockIdx.x] = s_sum[L::iCUR + tid];
-    }
-    if (C > 0 && tid < bs.np)
-    {
-        const int    p  = tid;
-        const double CA = s_sum[L::iCA] + (MODE != 0 ? s_sum[2 * C + p] : 0.0);
-        const double DC = s_sum[L::iDC] + (MODE != 0 ? s_sum[3 * C + p] : 0.0);
-        const double GA = s_sum[L::iGA] + s_sum[p];
-        const double DG = s_sum[L::iDG] + s_sum[C + p];
-        /* E = lfacC[A] C_A + lfacC[B] C_B + lfacV[A] G_A + lfacV[B] G_B with X_B = X_A + DX */
-        const double e = (double)bs.lfc[0][p] * CA + (double)bs.lfc[1][p] * (CA + DC) + (double)bs.lfv[0][p] * GA
-                         + (double)bs.lfv[1][p] * (GA + DG);
-        const size_t o = (size_t)(3 * (bs.p0 + p)) * bs.n_tiles + blockIdx.x;
-        ka.for_part[o]                  = e;
-        ka.for_part[o + bs.n_tiles]     = DC;
-        ka.for_part[o + 2 * bs.n_tiles] = DG;
-    }
-    /* nothing here depends on the preceding kernel; completing after it keeps the chain ordered */
-    fep_pdl_wait();
-}
-
-/* ------------------------------------------------------------------------------------------- */
-/* occ != nullptr: only report how many CTAs of this instantiation fit on one SM */
-/* FEPB200_STAGE=direct: the A/B variant that reads the tile's records from global memory in the loop
- * instead of staging them through shared memory with bulk copies (profiles/) */
-static bool fb_staged()
-{
-    static const bool staged = [] {
-        const char* e = std::getenv("FEPB200_STAGE");
-        return !(e && std::strcmp(e, "direct") == 0);
-    }();
-    return staged;
-}
-
-template<bool EWALD, int MODE, int C, bool FORCE>
-static void launch_one(const KernelArgs& ka, const BeutlerStep& bs, cudaStream_t stream, int* occ, bool chained)
-{
-    if (occ)
-    {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, FEP_FB_CTA, 0);
-        return;
-    }
-    if (fb_staged())
-    {
-        /* tiles beyond the default 48 kB of dynamic shared memory need the opt-in, once per instantiation and size */
-        static size_t allowed = 48 * 1024 - 4096;
-        const size_t  smem    = fep_tile_bytes(bs.tile_trips);
-        if (smem > allowed)
-        {
-            cudaFuncSetAttribute(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
-            allowed = smem;
-        }
-        fep_launch_kernel_smem(fep_beutler_kernel<EWALD, MODE, C, FORCE, true>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), smem,
-                               stream, chained, ka, bs);
-    }
-    else
-    {
-        fep_launch_kernel_smem(fep_beutler_kernel<EWALD, MODE, C, FORCE, false>, dim3(bs.n_tiles), dim3(FEP_FB_CTA), 0,
-                               stream, chained, ka, bs);
-    }
-}
-
-template<bool EWALD, int MODE, bool FORCE>
-static bool launch_size(const KernelArgs& ka, const BeutlerStep& bs, int c, cudaStream_t stream, int* occ, bool chained)
-{
-    switch (c)
-    {
-#define FEP_FB_CASE(N) \
-    case N: launch_one<EWALD, MODE, N, FORCE>(ka, bs, stream, occ, chained); return true;
-        FEP_FB_CASE(1)
-        FEP_FB_CASE(2)
-        FEP_FB_CASE(3)
-        FEP_FB_CASE(4)
-        FEP_FB_CASE(6)
-        FEP_FB_CASE(7)
-        FEP_FB_CASE(8)
-        FEP_FB_CASE(11)
-        FEP_FB_CASE(14)
-        FEP_FB_CASE(16)
-        FEP_FB_CASE(21)
-        FEP_FB_CASE(24)
-#undef FEP_FB_CASE
-        case 0:
-            if (FORCE)
-            {
-                launch_one<EWALD, MODE, 0, true>(ka, bs, stream, occ, chained);
-                return true;
-            }
-            return false;
+        case 0: return fb_launch_e0_m0(ka, bs, c, force, stream, occ, chained);
+        case 1: return fb_launch_e0_m1(ka, bs, c, force, stream, occ, chained);
+        case 2: return fb_launch_e0_m2(ka, bs, c, force, stream, occ, chained);
+        case 3: return fb_launch_e1_m0(ka, bs, c, force, stream, occ, chained);
+        case 4: return fb_launch_e1_m1(ka, bs, c, force, stream, occ, chained);
+        case 5: return fb_launch_e1_m2(ka, bs, c, force, stream, occ, chained);
+        case 6: return fb_launch_e2_m0(ka, bs, c, force, stream, occ, chained);
+        case 7: return fb_launch_e2_m1(ka, bs, c, force, stream, occ, chained);
+        case 8: return fb_launch_e2_m2(ka, bs, c, force, stream, occ, chained);
         default: return false;
     }
-}
-
-template<bool EWALD, bool FORCE>
-static bool launch_mode(const KernelArgs& ka, const BeutlerStep& bs, int mode, int c, cudaStream_t stream, int* occ,
-                        bool chained = false)
-{
-    return mode == 0   ? launch_size<EWALD, 0, FORCE>(ka, bs, c, stream, occ, chained)
-           : mode == 1 ? launch_size<EWALD, 1, FORCE>(ka, bs, c, stream, occ, chained)
-                       : launch_size<EWALD, 2, FORCE>(ka, bs, c, stream, occ, chained);
 }
 
 static const int c_sizes[] = { 1, 2, 3, 4, 6, 7, 8, 11, 14, 16, 21, 24 };
@@ -719,17 +94,7 @@ extern "C" int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int c, int forc
     KernelArgs  ka{};
     BeutlerStep bs{};
     int         occ = 0;
-    bool        ok;
-    if (force)
-    {
-        ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, nullptr, &occ)
-                        : launch_mode<false, true>(ka, bs, mode, c, nullptr, &occ);
-    }
-    else
-    {
-        ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, nullptr, &occ)
-                        : launch_mode<false, false>(ka, bs, mode, c, nullptr, &occ);
-    }
+    const bool  ok = launch_any(ka, bs, elec_ewald != 0, mode, c, force != 0, nullptr, &occ);
     return (ok && occ > 0) ? occ : 1;
 }
 
@@ -768,8 +133,9 @@ extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mod
             }
         }
     }
-    bs.tile_trips = do_foreign ? ka.tile_trips : ka.pass_tile_trips;
-    bs.n_tiles    = do_foreign ? ka.n_tiles : ka.pass_n_tiles;
+    bs.n_tiles = do_foreign ? ka.n_tiles : ka.pass_n_tiles;
+    /* the force-only pass writes its four sums per warp, the fused pass per CTA */
+    bs.n_parts = do_foreign ? ka.n_tiles : ka.pass_n_tiles * (FEP_FB_CTA / 32);
     bool first    = true;
     for (int p0 = 0; p0 < np || first; p0 += (c > 0 ? c : 1))
     {
@@ -788,17 +154,7 @@ extern "C" int fep_launch_beutler(const KernelArgs* kap, int elec_ewald, int mod
             }
         }
         const bool force = first && do_force;
-        bool       ok;
-        if (force)
-        {
-            ok = elec_ewald ? launch_mode<true, true>(ka, bs, mode, c, stream, nullptr, chained != 0)
-                            : launch_mode<false, true>(ka, bs, mode, c, stream, nullptr, chained != 0);
-        }
-        else
-        {
-            ok = elec_ewald ? launch_mode<true, false>(ka, bs, mode, c, stream, nullptr, chained != 0)
-                            : launch_mode<false, false>(ka, bs, mode, c, stream, nullptr, chained != 0);
-        }
+        const bool ok    = launch_any(ka, bs, elec_ewald != 0, mode, c, force, stream, nullptr, chained != 0);
         if (!ok)
         {
             return (int)cudaErrorInvalidValue;

@@ -66,18 +66,21 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
     }
     __syncthreads();
 
-    /* one warp per trip */
-    const int  t     = ka.trip_begin + blockIdx.x * (FEP_CTA / 32) + warp;
-    const bool valid = t < ka.trip_end;
+    /* one warp per run of trips (fep_types.h): the owner's sums are kept per lane over a segment */
+    const int  t0  = ka.trip_begin + (blockIdx.x * (FEP_CTA / 32) + warp) * ka.run_trips;
+    const int  t1  = min(t0 + ka.run_trips, ka.trip_end);
+    const bool per_segment_energy = ka.n_gid > 1;
 
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f, vc = 0.0f, vv = 0.0f, dc = 0.0f, dv = 0.0f;
-
-    const unsigned int* tb = ka.trips + (size_t)(valid ? t : 0) * FEP_TRIP_WORDS;
-    if (valid)
+    float      dc = 0.0f, dv = 0.0f, vc1 = 0.0f, vv1 = 0.0f;
+    FepSegment seg;
+    fep_segment_clear(seg);
+    for (int t = t0; t < t1; t++)
     {
-        const FepFetch ft = fep_fetch<false>(ka, tb, lane);
-        const FepSlot  p  = fep_slot<false>(ka, tb, ft, lane, ka.dyn->shiftvec);
-        FepPair        pr;
+        const unsigned int* tb = ka.trips + (size_t)t * FEP_TRIP_WORDS;
+        const FepFetch      ft = fep_fetch<false>(ka, tb, lane);
+        const FepSlot       p  = fep_slot<false>(ka, tb, ft, lane);
+        float               fx = 0.0f, fy = 0.0f, fz = 0.0f, vc = 0.0f, vv = 0.0f;
+        FepPair             pr;
         if (fep_fill_pair<SC>(ka, p, pr))
         {
             float fscal = 0.0f;
@@ -108,44 +111,54 @@ __global__ void __launch_bounds__(FEP_CTA) fep_pass_kernel(const __grid_constant
              * (unique destination, no atomics; skipped pairs write their zero) */
             ka.fsorted[__ldg(tb + FEP_TW_DST + lane)] = make_float4(-fx, -fy, -fz, 0.0f);
         }
+        /* the owner receives the sum over its segment; the segment's Vc/Vv go to its energy-group pair */
+        seg.fx -= fx;
+        seg.fy -= fy;
+        seg.fz -= fz;
+        if (per_segment_energy)
+        {
+            seg.vc += vc;
+            seg.vv += vv;
+        }
+        else
+        {
+            vc1 += vc;
+            vv1 += vv;
+        }
+        if (__ldg(tb + FEP_TH_FLAGS) & FEP_TRIP_LAST)
+        {
+            if (FORCE || per_segment_energy)
+            {
+                /* energy-only passes have no force slots to fill */
+                if (FORCE)
+                {
+                    fep_segment_flush<false>(ka, tb, ft.head, seg, want_shift != 0, per_segment_energy, lane);
+                }
+                else
+                {
+                    const float svc = fep_warp_sum(seg.vc), svv = fep_warp_sum(seg.vv);
+                    if (lane == 0)
+                    {
+                        ka.ev2[__ldg(tb + FEP_TH_SLOT_EV)] = make_float2(svc, svv);
+                    }
+                    fep_segment_clear(seg);
+                }
+            }
+        }
     }
 
-    /* the owner receives the sum over the trip; the trip's Vc/Vv go to its energy-group pair */
-    fx = warp_sum(fx);
-    fy = warp_sum(fy);
-    fz = warp_sum(fz);
-    vc = warp_sum(vc);
-    vv = warp_sum(vv);
     /* dV/dlambda of this CTA (the reference accumulates one scalar per call, :1170-1178); with a single
      * energy-group pair also Vc and Vv */
     {
-        const float wc = warp_sum(dc), wv = warp_sum(dv);
+        const float wc = warp_sum(dc), wv = warp_sum(dv), w2 = warp_sum(vc1), w3 = warp_sum(vv1);
         if (lane == 0)
         {
             s_red[warp][0] = wc;
             s_red[warp][1] = wv;
-            s_red[warp][2] = vc;
-            s_red[warp][3] = vv;
+            s_red[warp][2] = w2;
+            s_red[warp][3] = w3;
         }
     }
-    if (valid && lane == 0)
-    {
-        if (FORCE)
-        {
-            ka.fsorted[__ldg(tb + FEP_TH_SLOT_F)] = make_float4(fx, fy, fz, 0.0f);
-            if (want_shift)
-            {
-                /* a flipped trip's owner was the reference's j atom: its force is minus the i force (:1153-1164) */
-                const float sg = (__ldg(tb + FEP_TH_OWNER) & FEP_TRIP_FLIPPED) ? -1.0f : 1.0f;
-                ka.fshift_sorted[__ldg(tb + FEP_TH_SLOT_SHIFT)] = make_float4(sg * fx, sg * fy, sg * fz, 0.0f);
-            }
-        }
-        if (ka.n_gid > 1)
-        {
-            ka.ev2[__ldg(tb + FEP_TH_SLOT_EV)] = make_float2(vc, vv);
-        }
-    }
-
     __syncthreads();
     if (tid < 4)
     {
@@ -232,7 +245,7 @@ __global__ void __launch_bounds__(FEP_CTA) fep_foreign_kernel(const __grid_const
     {
         const unsigned int* tb = ka.trips + (size_t)t * FEP_TRIP_WORDS;
         const FepFetch      ft = fep_fetch<false>(ka, tb, lane);
-        const FepSlot       sl = fep_slot<false>(ka, tb, ft, lane, ka.dyn->shiftvec);
+        const FepSlot       sl = fep_slot<false>(ka, tb, ft, lane);
         FepPair        pr;
         if (!fep_fill_pair<SC>(ka, sl, pr))
         {
@@ -645,19 +658,18 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         /* PEER: this rank sums the atoms it owns (the forces are reduce-scattered by atom range);
          * a remote round trip costs the same for 4 lanes as for 8, and half the threads means half
          * the waves of blocks */
-        const int atom     = (PEER ? ka.px.atom_begin : 0) + b * (FEP_EPI_CTA / LANES) + (tid / LANES);
-        const int atom_end = PEER ? ka.px.atom_end : ka.n_touched;
-        const int sub      = tid % LANES;
+        const int li   = (PEER ? ka.px.light_begin : 0) + b * (FEP_EPI_CTA / LANES) + (tid / LANES);
+        const int lend = PEER ? ka.px.light_end : ka.n_light;
+        const int sub  = tid % LANES;
         float     fx = 0.0f, fy = 0.0f, fz = 0.0f;
-        int       k0 = 0, k1 = 0;
+        int       atom = 0, k0 = 0, k1 = 0;
         int       sr[4] = { 0, 0, 0, 0 }; /* producer ranks of the first trip's elements (static) */
-        bool      mine  = false;
-        if (atom < atom_end)
+        const bool mine = li < lend;
+        if (mine)
         {
+            atom = __ldg(ka.light_atoms + li);
             k0   = __ldg(ka.atom_ptr + atom);
             k1   = __ldg(ka.atom_ptr + atom + 1);
-            mine = k1 - k0 <= FEP_HEAVY_MIN; /* the others belong to the heavy role above */
-            k1   = mine ? k1 : k0;
             if (PEER)
             {
 #pragma unroll
@@ -669,7 +681,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             }
         }
         FEP_EPI_SYNC_POINT();
-        if (atom < atom_end)
+        if (mine)
         {
             /* the atom's contributions are contiguous in fsorted: the lanes stream them, four
              * independent 16-byte loads per lane and trip (most atoms need a single trip) */
@@ -967,7 +979,7 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
         if (beutler && sf.force)
         {
             rc = fep_launch_beutler(&ka, EWALD ? 1 : 0, beutler_mode, host_cur, host_pts, 1, 0, sf.shift, stream, counter, 0);
-            ka.n_parts = ka.pass_n_tiles;
+            ka.n_parts = ka.pass_n_tiles * (FEP_FB_CTA / 32); /* four sums per warp */
         }
         else
         {
@@ -1062,7 +1074,7 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
         return (int)err;
     }
     const bool     peer    = ka.px.nranks > 1;
-    const int      n_atoms = peer ? ka.px.atom_end - ka.px.atom_begin : ka.n_touched;
+    const int      n_atoms = peer ? ka.px.light_end - ka.px.light_begin : ka.n_light;
     EpilogueLayout lay;
     const int      n_heavy = peer ? ka.px.heavy_end - ka.px.heavy_begin : ka.n_heavy;
     /* lanes per light atom: FEP_EPI_LANES, or FEPB200_EPI_LANES = 2 | 4 | 8 (experiment: with the heavy

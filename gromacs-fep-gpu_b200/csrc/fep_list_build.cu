@@ -12,10 +12,13 @@
  *                              jindex), number of pairs every atom takes part in
  *   one thread per pair     -> owner = the end with more pairs; key = (owner, gid, shift, flipped)
  *   stable sort by key      -> groups; positions inside a group -> trips of <= 32 pairs -> slots
- *   one thread per pair     -> per-slot records (partner, pre-gathered partner parameters)
- *   stable sort of {pairs by partner atom, then trips by owner atom} -> every force contribution's
+ *   one thread per pair     -> per-slot records (partner, pre-gathered partner parameters, the pair's
+ *                              two type-table indices)
+ *   one thread per trip     -> segments (runs of run_trips trips cut at group boundaries): the last
+ *                              trip of a segment carries the owner's contribution
+ *   stable sort of {pairs by partner atom, then segments by owner atom} -> every force contribution's
  *                              slot in the atom-sorted buffer, atom_ptr
- *   stable sorts of the trips by shift index and by energy-group pair -> reduction ranges
+ *   stable sorts of the segments by shift index and by energy-group pair -> reduction ranges
  * Stable sorts make the layout (and with it the order of every floating-point sum) a function of
  * the list alone.
  */
@@ -161,8 +164,9 @@ __global__ void k_fill_slots(const K* __restrict__ keys_sorted, const int* __res
                              const int* __restrict__ gstart, const int* __restrict__ th, const int* __restrict__ tsc,
                              const int* __restrict__ pj, const int* __restrict__ pn, const int4* __restrict__ ent4,
                              const int* __restrict__ excl, int j0, const float4* __restrict__ par4, int ntype, int G, int P,
-                             int NT, unsigned int* __restrict__ trips, int* __restrict__ orig, int* __restrict__ tshift,
-                             int* __restrict__ tgid, int* __restrict__ akeys, int* __restrict__ avals)
+                             int run_mask, unsigned int* __restrict__ trips, int* __restrict__ orig, int* __restrict__ tshift,
+                             int* __restrict__ tgid, int* __restrict__ tfirst, int* __restrict__ akeys,
+                             int* __restrict__ avals)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P)
@@ -182,30 +186,49 @@ __global__ void k_fill_slots(const K* __restrict__ keys_sorted, const int* __res
     const int  lane   = (r - gstart[r]) & 31;
     const bool excluded = excl != nullptr && excl[j0 + s] == 0;
     const float4  p   = par4[other];
+    const float4  po  = par4[owner];
     unsigned int* tb  = trips + (size_t)t * FEP_TRIP_WORDS;
     tb[FEP_TW_CJX + lane] = (unsigned int)other | (excluded ? 0x80000000u : 0u);
     tb[FEP_TW_QA + lane]  = __float_as_uint(p.x);
     tb[FEP_TW_QB + lane]  = __float_as_uint(p.y);
-    tb[FEP_TW_TJ + lane]  = (unsigned int)__float_as_int(p.z) | ((unsigned int)__float_as_int(p.w) << 16);
+    /* nbfp row = type of the reference's i atom (:499-500), column = type of its j atom (:560-563) */
+    const int tiA = __float_as_int(flip ? p.z : po.z), tjA = __float_as_int(flip ? po.z : p.z);
+    const int tiB = __float_as_int(flip ? p.w : po.w), tjB = __float_as_int(flip ? po.w : p.w);
+    tb[FEP_TW_TJ + lane]  = (unsigned int)(ntype * tiA + tjA) | ((unsigned int)(ntype * tiB + tjB) << 16);
     orig[32 * t + lane]   = s;
     akeys[r]              = other;
     avals[r]              = 32 * t + lane;
     if (lane == 0)
     {
-        const int    sh_eff = flip ? (FEP_NUM_SHIFT - 1 - sh) : sh;
-        const float4 po     = par4[owner];
-        const int    toA = __float_as_int(po.z), toB = __float_as_int(po.w);
-        tb[FEP_TH_OWNER]  = (unsigned int)owner | ((unsigned int)sh_eff << 24) | (flip ? (unsigned int)FEP_TRIP_FLIPPED : 0u);
-        /* nbfp row = type of the reference's i atom (:499-500), column = type of its j atom (:560-563) */
-        tb[FEP_TH_TADD_A] = (unsigned int)(flip ? toA : ntype * toA);
-        tb[FEP_TH_TADD_B] = (unsigned int)(flip ? toB : ntype * toB);
-        tb[FEP_TH_QA]     = __float_as_uint(po.x);
-        tb[FEP_TH_QB]     = __float_as_uint(po.y);
-        tshift[t]         = sh;
-        tgid[t]           = g;
-        akeys[P + t]      = owner;
-        avals[P + t]      = 32 * NT + t;
+        const int sh_eff = flip ? (FEP_NUM_SHIFT - 1 - sh) : sh;
+        tb[FEP_TH_OWNER] = (unsigned int)owner | ((unsigned int)sh_eff << 24) | (flip ? (unsigned int)FEP_TRIP_FLIPPED : 0u);
+        tb[FEP_TH_QA]    = __float_as_uint(po.x);
+        tb[FEP_TH_QB]    = __float_as_uint(po.y);
+        tshift[t]        = sh;
+        tgid[t]          = g;
+        /* a segment starts with every run and with every group */
+        tfirst[t]        = ((t & run_mask) == 0 || r == gstart[r]) ? 1 : 0;
     }
+}
+
+/* one thread per trip: the last trip of a segment carries the owner's contribution, the keys of the others sort
+ * behind every real key (atom nT, shift 45, energy-group pair G) */
+__global__ void k_segments(const int* __restrict__ tfirst, const int* __restrict__ tshift, const int* __restrict__ tgid, int NT,
+                           int P, int nT, int G, unsigned int* __restrict__ trips, int* __restrict__ akeys,
+                           int* __restrict__ avals, int* __restrict__ kshift, int* __restrict__ kgid)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NT)
+    {
+        return;
+    }
+    const bool    last = t == NT - 1 || tfirst[t + 1] != 0;
+    unsigned int* tb   = trips + (size_t)t * FEP_TRIP_WORDS;
+    tb[FEP_TH_FLAGS]   = last ? FEP_TRIP_LAST : 0u;
+    akeys[P + t]       = last ? (int)(tb[FEP_TH_OWNER] & (FEP_MAX_TOUCHED - 1)) : nT;
+    avals[P + t]       = 32 * NT + t;
+    kshift[t]          = last ? tshift[t] : FEP_NUM_SHIFT;
+    kgid[t]            = last ? tgid[t] : G;
 }
 
 __global__ void k_iota(int* __restrict__ v, int n)
@@ -376,10 +399,12 @@ extern "C" int fep_list_build_groups(const ListBuild* bp, const int* d_iinr, con
     return (int)cudaGetLastError();
 }
 
-/* Phase 3 (NT known): slot records, the atom sort and the two trip sorts.
- * key_ptr: int[46 + G + 1] (shift_ptr then gid_ptr). */
+/* Phase 3 (NT known): slot records, segments, the atom sort and the two segment sorts.  Can be repeated with another
+ * run_trips (a power of two) as long as the results of phase 2 are in place.
+ * key_ptr: int[46 + G + 1] (shift_ptr then gid_ptr); key_ptr[45] = key_ptr[46 + G] = atom_ptr[nT] - P = segments. */
 extern "C" int fep_list_build_slots(const ListBuild* bp, const int* d_excl, int j0, const float4* d_par4, int ntype, int P,
-                                    int NT, int nT, int G, int wide_keys, cudaStream_t stream, long long* counter)
+                                    int NT, int nT, int G, int wide_keys, int run_trips, cudaStream_t stream,
+                                    long long* counter)
 {
     const ListBuild& b         = *bp;
     size_t           tmp_bytes = b.tmp_bytes;
@@ -396,28 +421,30 @@ extern "C" int fep_list_build_slots(const ListBuild* bp, const int* d_excl, int 
     {
         k_fill_slots<unsigned long long><<<(P + 255) / 256, 256, 0, stream>>>(
                 reinterpret_cast<const unsigned long long*>(b.keys_out), b.vals_out, b.gstart, b.th, b.tsc, b.pj, b.pn, b.ent4,
-                d_excl, j0, d_par4, ntype, G, P, NT, b.trips, b.orig, b.tshift, b.tgid, b.akeys, b.avals);
+                d_excl, j0, d_par4, ntype, G, P, run_trips - 1, b.trips, b.orig, b.tshift, b.tgid, b.tfirst, b.akeys, b.avals);
     }
     else
     {
         k_fill_slots<unsigned int><<<(P + 255) / 256, 256, 0, stream>>>(
                 reinterpret_cast<const unsigned int*>(b.keys_out), b.vals_out, b.gstart, b.th, b.tsc, b.pj, b.pn, b.ent4, d_excl,
-                j0, d_par4, ntype, G, P, NT, b.trips, b.orig, b.tshift, b.tgid, b.akeys, b.avals);
+                j0, d_par4, ntype, G, P, run_trips - 1, b.trips, b.orig, b.tshift, b.tgid, b.tfirst, b.akeys, b.avals);
     }
+    k_segments<<<(NT + 255) / 256, 256, 0, stream>>>(b.tfirst, b.tshift, b.tgid, NT, P, nT, G, b.trips, b.akeys, b.avals,
+                                                     b.kshift, b.kgid);
     /* every force contribution's slot in the atom-sorted buffer: pairs (to their partner) in slot order, then
-     * trips (to their owner) */
+     * segments (to their owner); trips that do not end a segment sort behind the last atom */
     cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.akeys, b.akeys_out, b.avals, b.avals_out, n, 0,
-                                    bits_for((unsigned long long)nT), stream);
+                                    bits_for((unsigned long long)nT + 1), stream);
     k_atom_slots<<<(n + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, n, n_slots, nT, b.trips, b.atom_ptr);
-    /* trips by shift index and by energy-group pair */
+    /* segments by shift index and by energy-group pair */
     k_iota<<<(NT + 255) / 256, 256, 0, stream>>>(b.avals, NT);
-    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.tshift, b.akeys_out, b.avals, b.avals_out, NT, 0, 6, stream);
+    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.kshift, b.akeys_out, b.avals, b.avals_out, NT, 0, 6, stream);
     k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, FEP_NUM_SHIFT, 1, b.trips, b.key_ptr);
-    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.tgid, b.akeys_out, b.avals, b.avals_out, NT, 0,
-                                    bits_for((unsigned long long)G), stream);
+    cub::DeviceRadixSort::SortPairs(b.tmp, tmp_bytes, b.kgid, b.akeys_out, b.avals, b.avals_out, NT, 0,
+                                    bits_for((unsigned long long)G + 1), stream);
     k_trip_slots<<<(NT + 255) / 256, 256, 0, stream>>>(b.akeys_out, b.avals_out, NT, G, 2, b.trips,
                                                      b.key_ptr + FEP_NUM_SHIFT + 1);
-    (*counter) += 6;
+    (*counter) += 7;
     return (int)cudaGetLastError();
 }
 
@@ -443,7 +470,7 @@ __global__ void __launch_bounds__(256) k_source_tables(const unsigned int* __res
     {
         slot_src[tb[FEP_TW_DST + l]] = r;
     }
-    if (l == 0)
+    if (l == 0 && (tb[FEP_TH_FLAGS] & FEP_TRIP_LAST))
     {
         slot_src[tb[FEP_TH_SLOT_F]]       = r;
         fshift_src[tb[FEP_TH_SLOT_SHIFT]] = r;

@@ -386,7 +386,8 @@ __device__ __forceinline__ void fep_included_terms(const KernelArgs& ka, const L
 /* Lambda-independent correction factors of one pair (reference :1023-1136):
  *   xc / fc multiply qq[s]  (excluded-pair reaction field, Ewald real-space correction)
  *   xv / fv multiply c6grid[s] (LJ-PME grid correction)                                   */
-template<bool EWALD, bool FORCE>
+/* LJPME: 1 / 0 = LJ-PME known at compile time, -1 = ask ka.vdw_ewald */
+template<bool EWALD, bool FORCE, int LJPME = -1>
 __device__ __forceinline__ void fep_corrections(const KernelArgs& ka, const FepPair& pr, bool excluded, bool self,
                                                 float& xc, float& fc, float& xv, float& fv)
 {
@@ -415,7 +416,7 @@ __device__ __forceinline__ void fep_corrections(const KernelArgs& ka, const FepP
         xc = -v_lr;
         fc = -f_lr;
     }
-    if (ka.vdw_ewald && (excluded || pr.r < ka.rvdw))
+    if ((LJPME < 0 ? ka.vdw_ewald != 0 : LJPME != 0) && (excluded || pr.r < ka.rvdw))
     {
         float pot, force = 0.0f;
         fep_ljpme_correction<FORCE>(pr.r2, pr.rinv, ka.lj_coeff_sq, ka.lj_coeff6_div6, self, &pot, &force);

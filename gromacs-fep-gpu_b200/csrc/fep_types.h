@@ -9,11 +9,19 @@
  *     the perturbed atom, whichever side of the reference's half list it sits on),
  *   - the energy-group pair, the shift vector, and the orientation (owner was i / owner was j).
  * Everything that the reference looks up per i-entry (nb_free_energy.cpp:466-503) is therefore
- * warp-uniform, the owner's force is one warp reduction per trip, and the segmented sums, per-pair
- * i-atom gathers and head searches of a flat i-entry-major pair space are gone.  A pair whose owner
- * was the reference's j atom is evaluated with the negated shift vector (index 44 - s), which gives
- * the negated distance vector: same energies, same forces on both atoms; its contribution to the
- * shift force is booked with the opposite sign under the original shift index.
+ * warp-uniform.  A pair whose owner was the reference's j atom is evaluated with the negated shift
+ * vector (index 44 - s), which gives the negated distance vector: same energies, same forces on both
+ * atoms; its contribution to the shift force is booked with the opposite sign under the original
+ * shift index.
+ *
+ * RUNS and SEGMENTS.  The trips are cut into runs of `run_trips` consecutive trips (a power of two,
+ * chosen per list so that one wave of resident warps covers it); a warp evaluates whole runs, one
+ * trip after the other.  A SEGMENT is a maximal sequence of trips of one group (owner, energy-group
+ * pair, shift, orientation) inside a run.  The warp keeps the owner's force (and the segment's
+ * Vc/Vv) in per-lane accumulators over the segment and reduces them ONCE, at the segment's last
+ * trip -- C5: 30 944 trips, 4 712 groups, 8 005 segments at run_trips = 8 -- so the owner's sum
+ * costs a quarter of a warp reduction per trip, and the atom-sorted buffer holds one contribution
+ * per segment instead of one per trip.
  *
  * Device layout of one context ("compact" = index into the ascending list of atoms that occur
  * anywhere in the FULL list, so that every rank uses the same numbering; "slot" = 32 * trip + lane):
@@ -22,26 +30,27 @@
  *   pts[L+1]     LambdaPoint       per set_lambdas: point 0 = current lambda, 1.. = foreign
  *   pos3[nT]     float[3] {x,y,z}  per step: coordinates of the touched atoms (compact order),
  *                                  packed: 12 bytes per atom cross PCIe, not 16
- *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step (read per trip: owner)
+ *   par4[nT]     float4 {qA,qB,bits(typeA),bits(typeB)}      per search step (list build only)
  *   typetab[T*T] float4 {c6,c12,sigma6,c6grid}               per nbfp upload
- *   trips[NT]    one contiguous block of FEP_TRIP_WORDS 32-bit words per trip, so that the tile of a
- *                CTA is ONE bulk copy into shared memory and every field is base + constant offset:
- *                  header (16 words): owner | shift_eff << 24 | flipped << 30; slot of the owner's force
- *                    sum in fsorted; slot in fshift_sorted; slot in ev2; type-table index terms of the
- *                    owner for states A, B; owner charges qA, qB; padding
+ *   trips[NT]    one contiguous block of FEP_TRIP_WORDS 32-bit words per trip, so that a trip is ONE
+ *                bulk copy into shared memory and every field is base + constant offset:
+ *                  header (16 words): owner | shift_eff << 24 | flipped << 30; flags (last trip of
+ *                    its segment); the segment's slots in fsorted / fshift_sorted / ev2 (valid in
+ *                    the segment's last trip); owner charges qA, qB; padding
  *                  cjx[32]  compact partner | excluded << 31 | padding << 30
  *                  dst[32]  where the force on the partner goes in fsorted
- *                  qA[32], qB[32]  partner charges       (pre-gathered: the only dependent per-pair load
- *                  tj[32]   partner types A | B << 16     left is the partner's coordinates)
+ *                  qA[32], qB[32]  partner charges       (pre-gathered: the only dependent per-pair
+ *                  tj[32]   type-table index of the pair  loads left are the partner's coordinates
+ *                           in state A | state B << 16     and the two type-table rows)
  *   orig[32 NT]  index of the pair in the shard's t_nblist; tgid[NT] (list read-back only)
  *   ent4[E]      int4   {compact i, shift index, gid, 0}  (list read-back only) per search step
- *   fsorted[P+NT] float4 force contributions SORTED BY RECEIVING ATOM: atom k owns the contiguous
+ *   fsorted[P+NS] float4 force contributions SORTED BY RECEIVING ATOM: atom k owns the contiguous
  *                range [atom_ptr[k], atom_ptr[k+1]); the pass kernel scatters -f (pairs, to the
- *                partner) and the trip's sum (to the owner) to precomputed unique slots, the
+ *                partner) and the segment's sum (to the owner) to precomputed unique slots, the
  *                epilogue streams ranges: no atomics, bit-reproducible
- *   fshift_sorted[NT] float4 trip sums sorted by shift index;  ev2[NT] float2 trip {Vc,Vv} sorted
- *                by energy-group pair; red_jobs = chunks of those ranges
- *   cta_part[nCta][2]        fp64 per-CTA partial dV/dlambda of the current-lambda pass
+ *   fshift_sorted[NS] float4 segment sums sorted by shift index;  ev2[NS] float2 segment {Vc,Vv}
+ *                sorted by energy-group pair; red_jobs = chunks of those ranges
+ *   cta_part[4][nPart]       fp64 partial dV/dlambda (and Vc, Vv) of the current-lambda pass
  *   for_part[3*(L+1)][nTile] fp64 per-CTA partial foreign energies / dV/dlambda
  *   result block: res_f32[3*nT + 3*45], res_f64[2G + 2 + 3(L+1)]   (include/fepb200.h)
  */
@@ -65,8 +74,7 @@
 #define FEP_TH_SLOT_F 1
 #define FEP_TH_SLOT_SHIFT 2
 #define FEP_TH_SLOT_EV 3
-#define FEP_TH_TADD_A 4 /* flipped ? typeA(owner) : ntype * typeA(owner) */
-#define FEP_TH_TADD_B 5
+#define FEP_TH_FLAGS 4 /* FEP_TRIP_LAST: last trip of its segment (reduce and store the owner's sums) */
 #define FEP_TH_QA 6
 #define FEP_TH_QB 7
 #define FEP_TW_CJX 16
@@ -74,7 +82,10 @@
 #define FEP_TW_QA 80
 #define FEP_TW_QB 112
 #define FEP_TW_TJ 144
-#define FEP_TRIP_FLIPPED 0x40000000 /* trip4.x: the owner was the j atom of the reference's pairs */
+#define FEP_TRIP_FLIPPED 0x40000000 /* header word 0: the owner was the j atom of the reference's pairs */
+#define FEP_TRIP_LAST 1u
+#define FEP_MAX_RUN_TRIPS 8 /* run_trips is a power of two <= this */
+#define FEP_MAX_NTYPE 256   /* both type-table indices of a pair share one word */
 #define FEP_CENTRAL_SHIFT 22
 #define FEP_MAX_POINTS 256 /* L+1 <= 256 lambda points per step */
 #define FEP_CTA 256        /* threads per CTA of the pair kernels */
@@ -135,6 +146,7 @@ struct PeerExchange
     int          nranks, rank;
     int          atom_begin, atom_end;   /* compact atoms whose forces this rank sums */
     int          heavy_begin, heavy_end; /* the part of heavy_atoms[] inside that range */
+    int          light_begin, light_end; /* the part of light_atoms[] inside that range */
     unsigned int seq;                    /* step number announced in the barrier (set per launch) */
     int          pad;
     /* producer rank of every element of fsorted / fshift_sorted / ev2 (local, static per list) */
@@ -162,11 +174,14 @@ struct KernelArgs
     float sw_v3, sw_v4, sw_v5, sw_f2, sw_f3, sw_f4;
     int   vdw_ewald, pot_switch, rf_type, ntype;
     /* sizes */
-    int n_pairs, n_entries, n_trips, n_touched, n_gid, n_cta, n_tiles, tile_trips;
-    int trip_begin, trip_end; /* the trips this context evaluates ([0, n_trips) unless the list is split over peers) */
+    int n_pairs, n_entries, n_trips, n_segs, n_touched, n_gid, n_cta, n_tiles;
+    int tile_trips;           /* generic foreign kernel: trips per CTA */
+    int run_trips;            /* trips per run (power of two) */
+    int trip_begin, trip_end; /* the trips this context evaluates ([0, n_trips) unless the list is split over peers);
+                                 trip_begin is a multiple of run_trips */
     int n_points, n_chunks, chunk_points;
-    int pass_tile_trips, pass_n_tiles; /* tiles of the force-only Beutler kernel */
-    int n_parts;                       /* per-CTA dV/dlambda partials written by the pass of this step */
+    int pass_n_tiles; /* CTAs of the force-only Beutler kernel */
+    int n_parts;      /* partial dV/dlambda sums written by the pass of this step */
     int fuse_pass_and_foreign;         /* Beutler path: pass + first foreign chunk in one launch */
     int n_red_jobs, n_shift_jobs;
     int pdl_chain;                     /* set per step by the launcher: kernels after the first are chained (PDL) */
@@ -189,6 +204,10 @@ struct KernelArgs
     const int*    atom_ptr;
     const int*    heavy_atoms; /* [n_heavy] atoms with more than FEP_HEAVY_MIN contributions, ascending */
     int           n_heavy;
+    const int*    light_atoms; /* [n_light] the other atoms that receive contributions FROM THIS CONTEXT'S LIST, ascending;
+                                  atoms of the compact numbering without any (a rank's shard of a split list) are never
+                                  visited: their words of the result block stay zero */
+    int           n_light;
     const RedJob* red_jobs;
     const int*    key_job_ptr; /* [45 + G + 1]: jobs of each key, shift keys first */
     /* outputs */
@@ -213,11 +232,12 @@ struct StepFlags
 
 /* Device buffers of the list builder (fep_list_build.cu); ints unless noted.  Scratch: pj, pn [P]; deg [nT+1];
  * keys, keys_out [P] of 4- or 8-byte keys; vals, vals_out, gmark, gstart [P]; th, tsc [P+1]; akeys, akeys_out,
- * avals, avals_out [P+NT]; tshift [NT]; key_ptr [46 + G + 1].  Results: ent4 [E]; trips [NT][FEP_TRIP_WORDS];
- * tgid [NT]; orig [32 NT]; atom_ptr [nT+1]. */
+ * avals, avals_out [P+NT]; tshift, tfirst, kshift, kgid [NT]; key_ptr [47 + G + 2].  Results: ent4 [E];
+ * trips [NT][FEP_TRIP_WORDS]; tgid [NT]; orig [32 NT]; atom_ptr [nT+1] (atom_ptr[nT] = P + NS). */
 struct ListBuild
 {
     int *  pj, *pn, *deg, *vals, *vals_out, *gmark, *gstart, *th, *tsc, *akeys, *akeys_out, *avals, *avals_out, *tshift, *key_ptr;
+    int *  tfirst, *kshift, *kgid;
     void * keys, *keys_out, *tmp;
     size_t tmp_bytes;
     int4 *        ent4;
@@ -239,7 +259,7 @@ int fep_launch_step(const KernelArgs* ka, int softcore, int elec_ewald, StepFlag
                     const LambdaPoint* host_pts, int beutler_mode, cudaStream_t side_stream, cudaEvent_t fork_ev,
                     cudaEvent_t join_ev);
 #define FEP_FB_CTA 128
-#define FEP_TILE_SMEM_SM (200 * 1024) /* shared memory of one SM that the staged tiles of its resident CTAs may fill */
+#define FEP_RING_DEPTH 4 /* trips of a warp's ring in shared memory: one evaluated, one fetched from, two on their way */
 #define FEP_FB_MAXC 24
 int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
 int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force);

@@ -37,7 +37,7 @@ extern "C" int    fep_list_build_groups(const ListBuild* b, const int* d_iinr, c
                                         const int* d_jindex, const int* d_jjnr, const int* d_cscan, int e0, int E, int j0, int P,
                                         int nT, int G, int wide_keys, cudaStream_t stream, long long* counter);
 extern "C" int    fep_list_build_slots(const ListBuild* b, const int* d_excl, int j0, const float4* d_par4, int ntype, int P, int NT,
-                                       int nT, int G, int wide_keys, cudaStream_t stream, long long* counter);
+                                       int nT, int G, int wide_keys, int run_trips, cudaStream_t stream, long long* counter);
 extern "C" int    fep_launch_source_tables(const unsigned int* d_trips, int NT, int tpr, unsigned char* d_slot_src,
                                            unsigned char* d_fshift_src, unsigned char* d_ev2_src, cudaStream_t stream,
                                            long long* counter);
@@ -234,8 +234,17 @@ struct fepb200_ctx
     /* raw list + scratch of the device-side list build (fep_list_build.cu) */
     DeviceArray<int> d_raw_iinr, d_raw_gid, d_raw_shift, d_raw_jindex, d_raw_jjnr, d_raw_excl, d_mark, d_cscan, d_pj, d_pn, d_deg,
             d_vals, d_vals_out, d_gmark, d_gstart, d_th, d_tsc, d_akeys, d_akeys_out, d_avals, d_avals_out, d_tshift, d_key_ptr;
+    DeviceArray<int> d_tfirst, d_kshift, d_kgid;
     DeviceArray<unsigned long long> d_keys, d_keys_out;
     DeviceArray<unsigned char> d_cub_tmp;
+    /* what phase 3 of the list build (slots + segments, build_segments()) needs to run again with another run length */
+    struct
+    {
+        ListBuild  b{};
+        const int* d_excl = nullptr;
+        int        j0 = 0, P = 0, NT = 0, nT = 0, ngrp = 1, wide = 0;
+    } lb;
+    int n_segs = 0;
     DeviceArray<unsigned char> d_step_in; /* [DynHead | pos3[nT]] */
     DeviceArray<unsigned char> d_result;  /* [f64 block | f32 block] */
     PinnedArray<unsigned char> h_step_in, h_result;
@@ -251,6 +260,13 @@ struct fepb200_ctx
     DeviceArray<unsigned char> d_slot_src, d_fshift_src, d_ev2_src; /* producer rank of every sorted element */
     DeviceArray<int>    d_heavy;      /* atoms with more than FEP_HEAVY_MIN force contributions, ascending */
     std::vector<int>    heavy_atoms;  /* host copy */
+    DeviceArray<int>    d_light;      /* the other atoms with contributions from this context's list, ascending */
+    std::vector<int>    light_atoms;
+    int                 x_light_begin = 0, x_light_end = 0;
+    /* atoms of the compact numbering that receive nothing from this context's list are never written by the epilogue:
+     * every result block is zeroed once per list (own blocks in prepare_buffers, a caller's block at its first step) */
+    bool                result_needs_zero = true;
+    std::vector<void*>  zeroed_targets;
     DeviceArray<unsigned long long> d_trace;                        /* fepb200_epilogue_trace() */
     int                             trace_blocks = 0;               /* epilogue blocks of the last traced launch */
     unsigned int   x_seq = 0;
@@ -396,7 +412,8 @@ int prepare_buffers(fepb200_ctx* c)
     const int range = c->px_on ? c->x_range_trips : k.n_trips;
     k.trip_begin    = c->px_on ? c->x_trip_begin : 0;
     k.trip_end      = c->px_on ? c->x_trip_end : k.n_trips;
-    k.n_cta         = (range + FEP_CTA / 32 - 1) / (FEP_CTA / 32); /* generic pass kernel: one warp per trip */
+    const int runs  = (range + k.run_trips - 1) / std::max(k.run_trips, 1);
+    k.n_cta         = (runs + FEP_CTA / 32 - 1) / (FEP_CTA / 32); /* generic pass kernel: one warp per run */
     c->foreign_mode = -1;
     if (c->softcore == FEP_SC_BEUTLER && !k.pot_switch)
     {
@@ -424,18 +441,11 @@ int prepare_buffers(fepb200_ctx* c)
         }
         k.chunk_points = fep_beutler_chunk_size(np, want);
         k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
-        /* one wave: as many tiles as CTAs can be resident, at least one trip per warp; a tile is staged in
-         * shared memory as a whole, which bounds its size (larger lists take more than one wave) */
-        auto tiles = [&](long long ctas_per_sm, int& tile_trips, int& n_tiles) {
-            const long long target  = (long long)sms * ctas_per_sm;
-            const long long per_trip = (long long)(FEP_TRIP_WORDS * sizeof(unsigned int));
-            const long long cap     = std::max(1LL, (long long)(FEP_TILE_SMEM_SM / ctas_per_sm) / per_trip);
-            /* whole waves: when one wave of full tiles cannot hold the list, split it evenly over more waves */
-            const long long waves   = std::max(1LL, ((long long)range + target * cap - 1) / (target * cap));
-            long long       tt      = ((long long)range + target * waves - 1) / (target * waves);
-            tt                      = std::max<long long>(FEP_FB_CTA / 32, std::min(tt, cap));
-            tile_trips              = (int)tt;
-            n_tiles                 = (range + tile_trips - 1) / tile_trips;
+        /* a warp evaluates whole runs, run after run with a grid-wide stride: one wave of resident CTAs, or fewer
+         * when there are not enough runs for all of their warps */
+        auto tiles = [&](long long ctas_per_sm, int& n_tiles) {
+            const long long by_runs = ((long long)runs + FEP_FB_CTA / 32 - 1) / (FEP_FB_CTA / 32);
+            n_tiles                 = runs > 0 ? (int)std::max(1LL, std::min(by_runs, (long long)sms * ctas_per_sm)) : 0;
         };
         /* fuse pass + foreign when the list is too small to fill the GPU anyway */
         k.fuse_pass_and_foreign = pair_ctas < 16LL * sms;
@@ -454,9 +464,9 @@ int prepare_buffers(fepb200_ctx* c)
         };
         tiles(per_sm("FEPB200_FOREIGN_CTAS_PER_SM",
                      fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign)),
-              k.tile_trips, k.n_tiles);
+              k.n_tiles);
         tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)),
-              k.pass_tile_trips, k.pass_n_tiles);
+              k.pass_n_tiles);
     }
     else
     {
@@ -478,8 +488,8 @@ int prepare_buffers(fepb200_ctx* c)
         /* carve one exchange slot: [fsorted | fshift_sorted | ev2 | cta_part | for_part], every part
          * 256-byte aligned; identical on all ranks because every input of the sizes is */
         auto         up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t P       = (size_t)k.n_pairs, H = (size_t)k.n_trips;
-        const size_t n_parts = (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1));
+        const size_t P       = (size_t)k.n_pairs, H = (size_t)k.n_segs;
+        const size_t n_parts = (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles * (FEP_FB_CTA / 32), 1));
         c->x_off_fsorted     = 0;
         c->x_off_fshift      = c->x_off_fsorted + up((P + H) * sizeof(float4));
         c->x_off_ev2         = c->x_off_fshift + up(H * sizeof(float4));
@@ -497,12 +507,24 @@ int prepare_buffers(fepb200_ctx* c)
 
     CU_CHECK(c, c->d_pts.reserve(np));
     CU_CHECK(c, c->h_pts.reserve(np));
-    CU_CHECK(c, c->d_cta_part.reserve(4 * (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles, 1))));
+    CU_CHECK(c, c->d_cta_part.reserve(
+                        4 * (size_t)std::max(std::max(k.n_cta, k.n_tiles), std::max(k.pass_n_tiles * (FEP_FB_CTA / 32), 1))));
     CU_CHECK(c, c->d_for_part.reserve(3 * (size_t)np * std::max(k.n_tiles, 1)));
     c->res_f64_bytes = ((size_t)l.f64_words * sizeof(double) + 15) & ~(size_t)15;
     c->res_f32_bytes = (size_t)l.f32_words * sizeof(float);
-    CU_CHECK(c, c->d_result.reserve(c->res_f64_bytes + c->res_f32_bytes));
-    CU_CHECK(c, c->h_result.reserve(c->res_f64_bytes + c->res_f32_bytes));
+    {
+        const unsigned char* before_d = c->d_result.ptr;
+        const unsigned char* before_h = c->h_result.ptr;
+        CU_CHECK(c, c->d_result.reserve(c->res_f64_bytes + c->res_f32_bytes));
+        CU_CHECK(c, c->h_result.reserve(c->res_f64_bytes + c->res_f32_bytes));
+        if (c->result_needs_zero || before_d != c->d_result.ptr || before_h != c->h_result.ptr)
+        {
+            CU_CHECK(c, cudaStreamSynchronize(c->stream)); /* nobody reads or writes the blocks any more */
+            CU_CHECK(c, cudaMemsetAsync(c->d_result.ptr, 0, c->res_f64_bytes + c->res_f32_bytes, c->stream));
+            std::memset(c->h_result.ptr, 0, c->res_f64_bytes + c->res_f32_bytes);
+            c->result_needs_zero = false;
+        }
+    }
     {
         void* dp = nullptr;
         c->h_result_dev =
@@ -665,8 +687,7 @@ static void build_jobs(const int* shift_ptr /*[46]*/, const int* gid_ptr /*[G+1]
  * counters come back to the host. */
 static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int* gid, const int* shift,
                              const int* jindex, const int* jjnr, const int* excl_fep, long long nrj_total, int ngrp, int e0,
-                             int E, int j0, int P, int* nT_out, int* H_out, std::vector<RedJob>* jobs,
-                             std::vector<int>* key_job_ptr)
+                             int E, int j0, int P)
 {
     cudaStream_t st = c->stream;
     /* raw list */
@@ -697,9 +718,9 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
         CU_CHECK(c, cudaMemcpyAsync(c->d_raw_excl.ptr, excl_fep, sizeof(int) * nrj_total, cudaMemcpyHostToDevice, st));
         d_excl = c->d_raw_excl.ptr;
     }
-    if (c->ntype > 65535)
+    if (c->ntype > FEP_MAX_NTYPE)
     {
-        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than 65535 atom types");
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than %d atom types", FEP_MAX_NTYPE);
     }
     /* compact numbering of the atoms of the FULL list */
     const long long n_max     = 2LL * P + 64; /* P pairs + at most P trips */
@@ -780,14 +801,56 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
     CU_CHECK(c, c->d_trips.reserve(std::max<size_t>((size_t)NT * FEP_TRIP_WORDS, 1)));
     CU_CHECK(c, c->d_tgid.reserve(std::max(NT, 1)));
     CU_CHECK(c, c->d_tshift.reserve(std::max(NT, 1)));
+    CU_CHECK(c, c->d_tfirst.reserve((size_t)NT + 1));
+    CU_CHECK(c, c->d_kshift.reserve(std::max(NT, 1)));
+    CU_CHECK(c, c->d_kgid.reserve(std::max(NT, 1)));
     CU_CHECK(c, c->d_orig.reserve(std::max<size_t>(n_slots, 1)));
     CU_CHECK(c, c->d_akeys.reserve(std::max(P + NT, 1)));
     CU_CHECK(c, c->d_akeys_out.reserve(std::max(P + NT, 1)));
     CU_CHECK(c, c->d_avals.reserve(std::max(P + NT, 1)));
     CU_CHECK(c, c->d_avals_out.reserve(std::max(P + NT, 1)));
     b.trips = c->d_trips.ptr, b.tgid = c->d_tgid.ptr, b.tshift = c->d_tshift.ptr, b.orig = c->d_orig.ptr;
+    b.tfirst = c->d_tfirst.ptr, b.kshift = c->d_kshift.ptr, b.kgid = c->d_kgid.ptr;
     b.akeys = c->d_akeys.ptr, b.akeys_out = c->d_akeys_out.ptr, b.avals = c->d_avals.ptr, b.avals_out = c->d_avals_out.ptr;
-    err = fep_list_build_slots(&b, d_excl, j0, c->d_par4.ptr, c->ntype, P, NT, nT, ngrp, wide ? 1 : 0, st, &c->launches);
+    c->lb.b      = b;
+    c->lb.d_excl = d_excl;
+    c->lb.j0 = j0, c->lb.P = P, c->lb.NT = NT, c->lb.nT = nT, c->lb.ngrp = ngrp, c->lb.wide = wide ? 1 : 0;
+    return FEPB200_OK;
+}
+
+/* trips per run (fep_types.h): the smallest power of two with which one wave of the pass kernel's resident
+ * warps covers `trips`, at most FEP_MAX_RUN_TRIPS -- long runs mean few segments (few reductions, few owner
+ * contributions), short runs mean parallelism for short lists */
+static int choose_run_trips(const fepb200_ctx* c, long long trips)
+{
+    if (const char* e = std::getenv("FEPB200_RUN_TRIPS"))
+    {
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8)
+        {
+            return v;
+        }
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const long long warps = (long long)sms * 8 * (FEP_FB_CTA / 32);
+    int             r     = 1;
+    while (r < FEP_MAX_RUN_TRIPS && trips > warps * r)
+    {
+        r *= 2;
+    }
+    return r;
+}
+
+/* Phase 3 of the list build for runs of `run_trips` trips, and everything that follows from it: segment slots,
+ * atom ranges, reduction jobs, heavy atoms, the intermediate buffers.  set_list() calls it once; the peer
+ * exchange calls it again when a rank's share of the trips wants shorter runs. */
+static int build_segments(fepb200_ctx* c, int run_trips)
+{
+    cudaStream_t st = c->stream;
+    const int    P = c->lb.P, NT = c->lb.NT, nT = c->lb.nT, ngrp = c->lb.ngrp;
+    int          err = fep_list_build_slots(&c->lb.b, c->lb.d_excl, c->lb.j0, c->d_par4.ptr, c->ntype, P, NT, nT, ngrp, c->lb.wide,
+                                            run_trips, st, &c->launches);
     if (err != 0)
     {
         return fail(c, FEPB200_ERR_CUDA, "list build (slots) failed: %s", cudaGetErrorString((cudaError_t)err));
@@ -799,13 +862,62 @@ static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int
     c->w_atom_ptr.resize((size_t)nT + 1);
     CU_CHECK(c, cudaMemcpyAsync(c->w_atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost, st));
     CU_CHECK(c, cudaStreamSynchronize(st));
-    build_jobs(key_ptr.data(), key_ptr.data() + FEP_NUM_SHIFT + 1, ngrp, jobs, key_job_ptr, &c->ka.n_shift_jobs);
-    if ((rc = to_device(c, c->d_red_jobs, *jobs)) || (rc = to_device(c, c->d_key_job_ptr, *key_job_ptr)))
+    const int NS = P > 0 ? c->w_atom_ptr[nT] - P : 0;
+    if (NS < 0 || NS > NT || key_ptr[FEP_NUM_SHIFT] != NS || key_ptr[FEP_NUM_SHIFT + 1 + ngrp] != NS)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "list build: inconsistent segment counts (%d, %d, %d of %d trips)", NS,
+                    key_ptr[FEP_NUM_SHIFT], key_ptr[FEP_NUM_SHIFT + 1 + ngrp], NT);
+    }
+    std::vector<RedJob> jobs;
+    std::vector<int>    key_job_ptr;
+    build_jobs(key_ptr.data(), key_ptr.data() + FEP_NUM_SHIFT + 1, ngrp, &jobs, &key_job_ptr, &c->ka.n_shift_jobs);
+    int rc;
+    if ((rc = to_device(c, c->d_red_jobs, jobs)) || (rc = to_device(c, c->d_key_job_ptr, key_job_ptr)))
     {
         return rc;
     }
-    *nT_out = nT;
-    *H_out  = NT;
+    /* atoms with long contribution ranges get a whole warp in the epilogue */
+    c->heavy_atoms.clear();
+    c->light_atoms.clear();
+    for (int a = 0; a < nT; a++)
+    {
+        const int n = c->w_atom_ptr[a + 1] - c->w_atom_ptr[a];
+        if (n > FEP_HEAVY_MIN)
+        {
+            c->heavy_atoms.push_back(a);
+        }
+        else if (n > 0)
+        {
+            c->light_atoms.push_back(a);
+        }
+    }
+    if ((rc = to_device(c, c->d_heavy, c->heavy_atoms)) != FEPB200_OK || (rc = to_device(c, c->d_light, c->light_atoms)) != FEPB200_OK)
+    {
+        return rc;
+    }
+    CU_CHECK(c, c->d_fsorted.reserve(std::max(P + NS, 1)));
+    CU_CHECK(c, c->d_fshift_sorted.reserve(std::max(NS, 1)));
+    CU_CHECK(c, c->d_ev2.reserve(std::max(NS, 1)));
+    CU_CHECK(c, c->d_job_part.reserve(4 * std::max<size_t>(jobs.size(), 1)));
+    CU_CHECK(c, cudaStreamSynchronize(st)); /* host vectors go out of scope */
+    KernelArgs& k   = c->ka;
+    c->result_needs_zero = true;
+    c->zeroed_targets.clear();
+    c->n_segs       = NS;
+    k.n_segs        = NS;
+    k.run_trips     = run_trips;
+    k.n_red_jobs    = (int)jobs.size();
+    k.fsorted       = c->d_fsorted.ptr;
+    k.fshift_sorted = c->d_fshift_sorted.ptr;
+    k.ev2           = c->d_ev2.ptr;
+    k.job_part      = c->d_job_part.ptr;
+    k.atom_ptr      = c->d_atom_ptr.ptr;
+    k.heavy_atoms   = c->d_heavy.ptr;
+    k.n_heavy       = (int)c->heavy_atoms.size();
+    k.light_atoms   = c->d_light.ptr;
+    k.n_light       = (int)c->light_atoms.size();
+    k.red_jobs      = c->d_red_jobs.ptr;
+    k.key_job_ptr   = c->d_key_job_ptr.ptr;
     return FEPB200_OK;
 }
 
@@ -946,6 +1058,7 @@ int fepb200_destroy(fepb200_ctx* c)
     c->d_par4.release();
     c->d_trace.release();
     c->d_heavy.release();
+    c->d_light.release();
     c->d_slot_src.release();
     c->d_fshift_src.release();
     c->d_ev2_src.release();
@@ -1302,37 +1415,13 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
 
 
     /* the device layout is built on the GPU: kernels + scans + stable sorts (fep_list_build.cu) */
-    int                 nT = 0, H = 0, rc = 0;
-    std::vector<RedJob> jobs;
-    std::vector<int>    key_job_ptr;
-    rc = build_list_device(c, nri, iinr, gid, shift, jindex, jjnr, excl_fep, nrj_total, ngrp, e0, E, j0, P, &nT, &H, &jobs,
-                           &key_job_ptr);
+    int rc = build_list_device(c, nri, iinr, gid, shift, jindex, jjnr, excl_fep, nrj_total, ngrp, e0, E, j0, P);
     if (rc != FEPB200_OK)
     {
         return rc;
     }
+    const int nT = c->lb.nT, H = c->lb.NT;
     lap("device build");
-    /* atoms with long contribution ranges get a whole warp in the epilogue (the builder leaves
-     * atom_ptr in w_atom_ptr) */
-    c->heavy_atoms.clear();
-    for (int a = 0; a < nT; a++)
-    {
-        if (c->w_atom_ptr[a + 1] - c->w_atom_ptr[a] > FEP_HEAVY_MIN)
-        {
-            c->heavy_atoms.push_back(a);
-        }
-    }
-    if ((rc = to_device(c, c->d_heavy, c->heavy_atoms)) != FEPB200_OK)
-    {
-        return rc;
-    }
-    CU_CHECK(c, c->d_fsorted.reserve(std::max(P + H, 1)));
-    CU_CHECK(c, c->d_fshift_sorted.reserve(std::max(H, 1)));
-    CU_CHECK(c, c->d_ev2.reserve(std::max(H, 1)));
-    CU_CHECK(c, c->d_job_part.reserve(4 * std::max<size_t>(jobs.size(), 1)));
-    CU_CHECK(c, cudaStreamSynchronize(c->stream)); /* host vectors go out of scope */
-    lap("buffers");
-
     KernelArgs& k = c->ka;
     c->px_on      = false; /* a new list has a new slot layout: the peer exchange must be set up again */
     k.px          = PeerExchange{};
@@ -1341,18 +1430,13 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     k.n_trips     = H;
     k.n_touched   = nT;
     k.n_gid       = ngrp;
-    k.n_red_jobs  = (int)jobs.size();
     k.par4        = c->d_par4.ptr;
     k.trips       = c->d_trips.ptr;
-    k.fsorted       = c->d_fsorted.ptr;
-    k.fshift_sorted = c->d_fshift_sorted.ptr;
-    k.ev2         = c->d_ev2.ptr;
-    k.job_part    = c->d_job_part.ptr;
-    k.atom_ptr    = c->d_atom_ptr.ptr;
-    k.heavy_atoms = c->d_heavy.ptr;
-    k.n_heavy     = (int)c->heavy_atoms.size();
-    k.red_jobs    = c->d_red_jobs.ptr;
-    k.key_job_ptr = c->d_key_job_ptr.ptr;
+    if ((rc = build_segments(c, choose_run_trips(c, H))) != FEPB200_OK)
+    {
+        return rc;
+    }
+    lap("segments + buffers");
 
     fepb200_layout& l = c->layout;
     l.natoms          = c->natoms;
@@ -1719,6 +1803,11 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     c->result_on_host  = false;
     if (c->res_target)
     {
+        if (std::find(c->zeroed_targets.begin(), c->zeroed_targets.end(), (void*)c->res_target) == c->zeroed_targets.end())
+        {
+            CU_CHECK(c, cudaMemsetAsync(c->res_target, 0, c->res_f64_bytes + c->res_f32_bytes, stream));
+            c->zeroed_targets.push_back(c->res_target);
+        }
         ka_step.res_f64 = reinterpret_cast<double*>(c->res_target);
         ka_step.res_f32 = reinterpret_cast<float*>(c->res_target + c->res_f64_bytes);
     }
@@ -1745,6 +1834,8 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
         px.atom_end             = c->x_atom_end;
         px.heavy_begin          = c->x_heavy_begin;
         px.heavy_end            = c->x_heavy_end;
+        px.light_begin          = c->x_light_begin;
+        px.light_end            = c->x_light_end;
         px.seq                  = seq;
         px.slot_src             = c->d_slot_src.ptr;
         px.fshift_src           = c->d_fshift_src.ptr;
@@ -1964,7 +2055,12 @@ static int peer_exchange_off(fepb200_ctx* c)
     c->px_on    = false;
     c->x_nranks = 1;
     c->x_rank   = 0;
-    const int rc = prepare_buffers(c);
+    int rc      = FEPB200_OK;
+    if (choose_run_trips(c, c->ka.n_trips) != c->ka.run_trips && (rc = build_segments(c, choose_run_trips(c, c->ka.n_trips))) != FEPB200_OK)
+    {
+        return rc;
+    }
+    rc = prepare_buffers(c);
     if (rc != FEPB200_OK)
     {
         return rc;
@@ -1982,12 +2078,12 @@ size_t fepb200_exchange_bytes(const fepb200_ctx* c, int nranks)
     {
         return 0;
     }
-    /* upper bound that does not depend on the launch geometry: at most one CTA per 128 pairs of a
-     * rank's range, room for 32 lambda points (or the current number if larger) */
+    /* upper bound that does not depend on the launch geometry or the run length: at most one partial sum per
+     * trip of a rank's share, room for 32 lambda points (or the current number if larger), one segment per trip */
     auto            up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t    P       = (size_t)c->ka.n_pairs, H = (size_t)c->ka.n_trips;
-    const long long tpr     = ((long long)H + nranks - 1) / nranks;
-    const size_t    ctas    = (size_t)((tpr + 3) / 4 + 1);
+    const long long tpr     = ((long long)H + nranks - 1) / nranks + FEP_MAX_RUN_TRIPS;
+    const size_t    ctas    = (size_t)(tpr + 1);
     const size_t    np      = (size_t)std::max(c->layout.nforeign + 1, 32);
     const size_t    slot    = up((P + H) * sizeof(float4)) + up(H * sizeof(float4)) + up(H * sizeof(float2))
                         + up(4 * ctas * sizeof(double)) + up(3 * np * ctas * sizeof(double));
@@ -2034,8 +2130,22 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
             c->x_base[r] = static_cast<unsigned char*>(d_peer_bufs[r]);
         }
         c->x_bytes = bytes;
-        /* pairs: equal shares of the trips (every trip is a contribution of its own to its owner atom) */
-        const long long tpr     = ((long long)H + nranks - 1) / nranks;
+        /* pairs: equal shares of the trips, in whole runs; a rank's share of the list may want shorter runs than
+         * the whole list did (parallelism), which changes the segments and with them every slot */
+        {
+            const int want = choose_run_trips(c, ((long long)H + nranks - 1) / nranks);
+            if (want != k.run_trips)
+            {
+                const int rc_seg = build_segments(c, want);
+                if (rc_seg != FEPB200_OK)
+                {
+                    c->px_on = false;
+                    return rc_seg;
+                }
+            }
+        }
+        const long long R       = k.run_trips;
+        const long long tpr     = (((long long)H + nranks - 1) / nranks + R - 1) / R * R;
         c->x_range_trips        = (int)tpr;
         c->x_trip_begin         = (int)std::min<long long>((long long)rank * tpr, H);
         c->x_trip_end           = (int)std::min<long long>((long long)(rank + 1) * tpr, H);
@@ -2044,7 +2154,7 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
         /* cost of an atom = its contributions + a fixed share for the lanes that serve it (a range
          * of many light atoms needs more blocks than a range of few heavy ones with the same volume) */
         const long long per_atom = 8;
-        const long long total    = (long long)P + H + per_atom * nT;
+        const long long total    = (long long)P + c->n_segs + per_atom * nT;
         int             a_of[FEP_XMAX + 1];
         a_of[0]      = 0;
         a_of[nranks] = nT;
@@ -2064,6 +2174,8 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
         c->x_atom_end    = a_of[rank + 1];
         c->x_heavy_begin = (int)(std::lower_bound(c->heavy_atoms.begin(), c->heavy_atoms.end(), a_of[rank]) - c->heavy_atoms.begin());
         c->x_heavy_end   = (int)(std::lower_bound(c->heavy_atoms.begin(), c->heavy_atoms.end(), a_of[rank + 1]) - c->heavy_atoms.begin());
+        c->x_light_begin = (int)(std::lower_bound(c->light_atoms.begin(), c->light_atoms.end(), a_of[rank]) - c->light_atoms.begin());
+        c->x_light_end   = (int)(std::lower_bound(c->light_atoms.begin(), c->light_atoms.end(), a_of[rank + 1]) - c->light_atoms.begin());
         /* producer rank of every element of the sorted arrays */
         CU_CHECK(c, c->d_slot_src.reserve(std::max<size_t>((size_t)P + H, 1)));
         CU_CHECK(c, c->d_fshift_src.reserve(std::max(H, 1)));

@@ -40,24 +40,41 @@ def touched_atoms(nblist) -> np.ndarray:
 PEER_ATOM_COST = 8  # the library's fixed share per atom when it balances the atom ranges
 
 
-def trip_layout(nblist, ngrp: int = 1) -> dict:
+MAX_RUN_TRIPS = 8
+PASS_WARPS_PER_SM = 32  # resident warps of the force-pass kernel: 8 CTAs of 4 warps
+
+
+def run_trips_for(n_trips: int, sms: int = 148) -> int:
+    """Trips per run, the rule of choose_run_trips() in csrc/fepb200_api.cu: the smallest power of two with which one
+    wave of the pass kernel's resident warps covers the trips, at most MAX_RUN_TRIPS (148 SMs on a B200)."""
+    r = 1
+    while r < MAX_RUN_TRIPS and n_trips > sms * PASS_WARPS_PER_SM * r:
+        r *= 2
+    return r
+
+
+def trip_layout(nblist, ngrp: int = 1, run_trips: int | None = None) -> dict:
     """Host-side mirror of the regrouping fepb200_set_list() does on the GPU (csrc/fep_list_build.cu): every pair is
     given to its OWNER, the end that takes part in more pairs of the list (ties: the i atom); pairs are grouped by
     (owner, energy-group pair, shift index, flipped = the owner was the j atom) with a stable sort, and every group is
-    cut into TRIPS of at most 32 pairs, the unit of work of one warp.  Returns
+    cut into TRIPS of at most 32 pairs, the unit of work of one warp.  The trips are cut into runs of `run_trips`
+    (default: run_trips_for(n_trips)); a SEGMENT is a maximal sequence of trips of one group inside a run, and
+    carries ONE force contribution to its owner.  Returns
       touched      compact -> atom
       trip_of_pair trip of every pair of the list (list order)
-      n_trips
+      n_trips, run_trips, n_segments
       trip_owner, trip_gid, trip_shift, trip_flipped   per trip (shift = the index the list gave)
+      trip_last    the trip ends a segment
       atom_ptr     atom k of the compact numbering owns the force contributions [atom_ptr[k], atom_ptr[k+1]) of the
-                   atom-sorted buffer: one per pair it is the partner of, one per trip it owns."""
+                   atom-sorted buffer: one per pair it is the partner of, one per segment it owns."""
     nrj = int(nblist.nrj)
     touched = touched_atoms(nblist)
     nt = len(touched)
     empty = np.zeros(0, np.int64)
     if nrj == 0:
-        return dict(touched=touched, trip_of_pair=empty, n_trips=0, trip_owner=empty, trip_gid=empty, trip_shift=empty,
-                    trip_flipped=empty.astype(bool), atom_ptr=np.zeros(nt + 1, np.int64))
+        return dict(touched=touched, trip_of_pair=empty, n_trips=0, run_trips=run_trips or 1, n_segments=0, trip_owner=empty,
+                    trip_gid=empty, trip_shift=empty, trip_flipped=empty.astype(bool), trip_last=empty.astype(bool),
+                    atom_ptr=np.zeros(nt + 1, np.int64))
     natoms = int(touched[-1]) + 1
     compact = np.full(natoms, -1, np.int64)
     compact[touched] = np.arange(nt)
@@ -83,15 +100,25 @@ def trip_layout(nblist, ngrp: int = 1) -> dict:
     trip_of_pair = np.empty(nrj, np.int64)
     trip_of_pair[order] = trip_sorted
     first = order[trip_head]  # the pair that opens each trip
-    cnt = np.bincount(other, minlength=nt) + np.bincount(owner[first], minlength=nt)
-    return dict(touched=touched, trip_of_pair=trip_of_pair, n_trips=n_trips, trip_owner=owner[first], trip_gid=gid[first],
-                trip_shift=shift[first], trip_flipped=flip[first],
+    if run_trips is None:
+        run_trips = run_trips_for(n_trips)
+    # a segment starts with every run and with every group
+    group_head = np.zeros(nrj, bool)
+    group_head[heads] = True
+    seg_first = (np.arange(n_trips) % run_trips == 0) | group_head[np.flatnonzero(trip_head)]
+    trip_last = np.concatenate([seg_first[1:], [True]])
+    cnt = np.bincount(other, minlength=nt) + np.bincount(owner[first][trip_last], minlength=nt)
+    return dict(touched=touched, trip_of_pair=trip_of_pair, n_trips=n_trips, run_trips=run_trips,
+                n_segments=int(trip_last.sum()), trip_owner=owner[first], trip_gid=gid[first], trip_shift=shift[first],
+                trip_flipped=flip[first], trip_last=trip_last,
                 atom_ptr=np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64))
 
 
-def peer_trip_ranges(n_trips: int, nranks: int) -> list[tuple[int, int]]:
-    """Rank r evaluates the trips [begin, end): equal shares, the rule of fepb200_set_peer_exchange()."""
+def peer_trip_ranges(n_trips: int, nranks: int, run_trips: int = 1) -> list[tuple[int, int]]:
+    """Rank r evaluates the trips [begin, end): equal shares in whole runs, the rule of fepb200_set_peer_exchange()
+    (which picks run_trips = run_trips_for(a rank's share))."""
     tpr = (n_trips + nranks - 1) // nranks
+    tpr = (tpr + run_trips - 1) // run_trips * run_trips
     return [(min(r * tpr, n_trips), min((r + 1) * tpr, n_trips)) for r in range(nranks)]
 
 

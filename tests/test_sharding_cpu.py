@@ -116,7 +116,17 @@ def test_trip_layout_and_peer_ranges_are_partitions():
     touched, atom_ptr = lay["touched"], lay["atom_ptr"]
     assert np.array_equal(touched, touched_atoms(nb)) and atom_ptr[0] == 0
     assert np.all(np.diff(atom_ptr) > 0)  # every touched atom receives at least one contribution
-    assert atom_ptr[-1] == nb.nrj + lay["n_trips"]  # one per pair (partner) + one per trip (owner)
+    assert atom_ptr[-1] == nb.nrj + lay["n_segments"]  # one per pair (partner) + one per segment (owner)
+    assert lay["run_trips"] == 1 and lay["n_segments"] == lay["n_trips"]  # a list this small: every trip its own run
+    for rt in (2, 4, 8):
+        l2 = trip_layout(nb, prob.nenergrp_pairs, rt)
+        last = l2["trip_last"]
+        assert last[-1] and np.all(last[rt - 1 :: rt])  # every run ends a segment
+        key = np.stack([l2["trip_owner"], l2["trip_gid"], l2["trip_shift"], l2["trip_flipped"]], 1)
+        change = np.any(key[1:] != key[:-1], axis=1)
+        assert np.all(last[:-1][change])  # so does every change of group
+        assert lay["n_trips"] / rt <= l2["n_segments"] <= lay["n_segments"]
+        assert l2["atom_ptr"][-1] == nb.nrj + l2["n_segments"]
     # every pair sits in exactly one trip of at most 32 pairs, and a trip is uniform in (owner, gid, shift, side)
     top = lay["trip_of_pair"]
     sizes = np.bincount(top, minlength=lay["n_trips"])
@@ -143,6 +153,7 @@ def test_trip_layout_and_peer_ranges_are_partitions():
     # degenerate inputs
     assert peer_trip_ranges(0, 4) == [(0, 0)] * 4
     assert peer_trip_ranges(5, 4) == [(0, 2), (2, 4), (4, 5), (5, 5)]
+    assert peer_trip_ranges(21, 3, 4) == [(0, 8), (8, 16), (16, 21)]
 
 
 def test_select_pairs_keeps_order_and_reassembles():
