@@ -467,6 +467,9 @@ def run_ours(args, name):
         p0, p1, a0, a1 = ctx.peer_ranges()
         my_entries = int(round(my_entries / world))
         my_pairs, my_atoms = int(round(my_pairs / world)), a1 - a0
+    elif sh.reduction == "p2p":
+        p0, p1, a0, a1 = ctx.peer_ranges()  # the atoms this rank owns after the reduce-scatter
+        my_atoms = a1 - a0
     points = problem.n_foreign + 1
     peaks = _peaks()
     sms = torch.cuda.get_device_properties(local).multi_processor_count
@@ -615,8 +618,8 @@ def run_ours(args, name):
                     data="synthetic", config=_config(problem, name),
                     run=dict(parallelism=f"pair-list shards x{world}", l2="flushed between timed steps (512 MiB write)",
                              reduction=sh.reduction if world > 1 else "none",
-                             outputs="forces reduce-scattered by atom range, scalars on every rank" if sh.reduction == "fused"
-                             else "full result on every rank"),
+                             outputs="forces reduce-scattered by atom range, scalars on every rank"
+                             if sh.reduction in ("fused", "p2p") else "full result on every rank"),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_s / args.steps * 1e3,
                              note="wall clock of the public call with host buffers; the device time of the L2 flush between "

@@ -276,8 +276,10 @@ __global__ void __launch_bounds__(FEP_FB_CTA, (AccLayout<MODE, C, FORCE>::MINB))
     fep_pdl_launch_dependents(); /* the next kernel of the step may fill SM space we leave free */
 
     /* this warp's runs of trips; its ring of trip blocks in shared memory is filled by bulk copies */
-    const FepWalk         walk  = fep_walk(ka, gridDim.x * NW);
-    FepCursor             issue = fep_cursor(ka, walk, blockIdx.x * NW + warp); /* next trip to bring into the ring */
+    const FepWalk         walk  = fep_walk(ka, gridDim.x * NW, FORCE ? ka.run_trips : 1);
+    /* warp-major numbering: the CTAs' first warps take the first gridDim.x runs, their second warps the next ones, ...:
+     * when there are fewer runs than warps, the busy warps are spread evenly over the CTAs (and with them over the SMs) */
+    FepCursor             issue = fep_cursor(ka, walk, warp * gridDim.x + blockIdx.x); /* next trip to bring into the ring */
     FepCursor             ahead = issue;                                        /* next trip to fetch the gathers of */
     const FepRing<STAGED> ring  = fep_ring_open<STAGED>(ka, walk, issue, fep_dyn_smem, s_bars, warp);
 

@@ -93,11 +93,13 @@ struct FepCursor
 {
     int t, left;
 };
-__device__ __forceinline__ FepWalk fep_walk(const KernelArgs& ka, int warps_of_grid)
+/* run_trips: ka.run_trips for a kernel that keeps per-segment sums, 1 for one that does not (any split of the trips
+ * will do: single trips balance best) */
+__device__ __forceinline__ FepWalk fep_walk(const KernelArgs& ka, int warps_of_grid, int run_trips)
 {
     FepWalk w;
-    w.run_trips = ka.run_trips;
-    w.jump      = warps_of_grid * ka.run_trips;
+    w.run_trips = run_trips;
+    w.jump      = warps_of_grid * run_trips;
     w.end       = ka.trip_end;
     return w;
 }

@@ -599,9 +599,8 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         }
         if (hi < hend)
         {
-            atom = __ldg(ka.heavy_atoms + hi);
-            k0   = __ldg(ka.atom_ptr + atom);
-            k1   = __ldg(ka.atom_ptr + atom + 1);
+            const int4 rec = __ldg(ka.heavy_atoms + hi);
+            atom = rec.x, k0 = rec.y, k1 = rec.z;
             if (PEER)
             {
 #pragma unroll
@@ -667,9 +666,8 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         const bool mine = li < lend;
         if (mine)
         {
-            atom = __ldg(ka.light_atoms + li);
-            k0   = __ldg(ka.atom_ptr + atom);
-            k1   = __ldg(ka.atom_ptr + atom + 1);
+            const int4 rec = __ldg(ka.light_atoms + li);
+            atom = rec.x, k0 = rec.y, k1 = rec.z;
             if (PEER)
             {
 #pragma unroll
@@ -1025,6 +1023,10 @@ static cudaError_t launch_variants(KernelArgs& ka, StepFlags sf, cudaStream_t st
                 ka.n_parts = ka.n_tiles;
             }
         }
+        else if (SC == FEP_SC_GAPSYS && ka.gapsys_hoisted)
+        {
+            rc = fep_launch_gapsys_foreign(&ka, EWALD ? 1 : 0, host_pts, stream, counter, (pdl && queued) ? 1 : 0);
+        }
         else
         {
             const dim3 grid(ka.n_tiles, ka.n_chunks);
@@ -1240,6 +1242,100 @@ extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* fla
         case 8: fep_launch_kernel(fep_peer_reduce_kernel<8>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
         default: fep_launch_kernel(fep_peer_reduce_kernel<0>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
     }
+    (*counter)++;
+    return (int)cudaGetLastError();
+}
+
+/* Reduce-scatter of the ranks' partial result blocks over NVLink peer memory, with the all-reduce of everything that
+ * is small: rank r sums the forces of ITS atoms (compact range [a0, a1), a0 a multiple of 4) over all ranks' blocks --
+ * (N-1)/N of one block crosses NVLink per rank, where the all-reduce of fep_peer_reduce_kernel pulls N-1 whole
+ * blocks -- and every rank sums the 45 shift forces and the fp64 scalars of all blocks.  Sums in rank order, so the
+ * shift forces and scalars are bit-identical on all ranks.  The barrier is the one of fep_peer_reduce_kernel.
+ * Items: [0, n4) float4 of the owned force range, [n4, n4 + n_tail) its last words when the range does not end on a
+ * 16-byte boundary, then 135 shift-force words, then n64 doubles. */
+template<int NR>
+__global__ void __launch_bounds__(256) fep_peer_reduce_scatter_kernel(const __grid_constant__ PeerPtrs peers,
+                                                                     const __grid_constant__ PeerPtrs flags, int rank,
+                                                                     unsigned int seq, int nranks, double* __restrict__ out_f64,
+                                                                     int n64, size_t f64_bytes, float* __restrict__ out_f32,
+                                                                     long long w0, long long w1, long long off_fshift,
+                                                                     unsigned int* fault)
+{
+    fep_pdl_wait(); /* chained behind the epilogue that completes this rank's block */
+    if (flags.p[0] != nullptr)
+    {
+        fep_flag_barrier([&](int r) { return static_cast<unsigned int*>(const_cast<void*>(flags.p[r])); }, rank, nranks, seq,
+                         blockIdx.x == 0, fault);
+    }
+    const int       nr     = NR > 0 ? NR : nranks;
+    const long long n4     = (w1 - w0) >> 2;
+    const long long n_tail = (w1 - w0) & 3;
+    const long long i      = (long long)blockIdx.x * 256 + threadIdx.x;
+    auto            f32_of = [&](int r) { return reinterpret_cast<const float*>(static_cast<const char*>(peers.p[r]) + f64_bytes); };
+    if (i < n4)
+    {
+        float4 v[NR > 0 ? NR : FEP_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < (NR > 0 ? NR : FEP_MAX_PEERS); r++)
+        {
+            /* all loads in flight before the first add (a peer load is ~1.5 us); written by another GPU: never
+             * from a stale cache line */
+            v[r] = r < nr ? __ldcv(reinterpret_cast<const float4*>(f32_of(r) + w0) + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int r = 0; r < (NR > 0 ? NR : FEP_MAX_PEERS); r++)
+        {
+            a.x += v[r].x;
+            a.y += v[r].y;
+            a.z += v[r].z;
+            a.w += v[r].w;
+        }
+        reinterpret_cast<float4*>(out_f32 + w0)[i] = a;
+    }
+    else if (i < n4 + n_tail + 3 * FEP_NUM_SHIFT)
+    {
+        const long long j = i - n4;
+        const long long w = j < n_tail ? w0 + 4 * n4 + j : off_fshift + (j - n_tail);
+        float           a = 0.0f;
+        for (int r = 0; r < nr; r++)
+        {
+            a += __ldcv(f32_of(r) + w);
+        }
+        out_f32[w] = a;
+    }
+    else if (i < n4 + n_tail + 3 * FEP_NUM_SHIFT + n64)
+    {
+        const long long j = i - (n4 + n_tail + 3 * FEP_NUM_SHIFT);
+        double          a = 0.0;
+        for (int r = 0; r < nr; r++)
+        {
+            a += __ldcv(static_cast<const double*>(peers.p[r]) + j);
+        }
+        out_f64[j] = a;
+    }
+}
+
+extern "C" int fep_launch_peer_reduce_scatter(const PeerPtrs* peers, const PeerPtrs* flagsp, int rank, unsigned int seq,
+                                              int nranks, double* out_f64, int n64, size_t f64_bytes, float* out_f32,
+                                              long long w0, long long w1, long long off_fshift, cudaStream_t stream,
+                                              long long* counter, int chained, unsigned int* fault)
+{
+    PeerPtrs        noflags{};
+    const PeerPtrs* flags  = flagsp ? flagsp : &noflags;
+    const long long items  = ((w1 - w0) >> 2) + ((w1 - w0) & 3) + 3 * FEP_NUM_SHIFT + n64;
+    const unsigned  blocks = (unsigned)((items + 255) / 256);
+#define FEP_RS_LAUNCH(N)                                                                                                  \
+    fep_launch_kernel(fep_peer_reduce_scatter_kernel<N>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, \
+                      seq, nranks, out_f64, n64, f64_bytes, out_f32, w0, w1, off_fshift, fault)
+    switch (nranks)
+    {
+        case 2: FEP_RS_LAUNCH(2); break;
+        case 4: FEP_RS_LAUNCH(4); break;
+        case 8: FEP_RS_LAUNCH(8); break;
+        default: FEP_RS_LAUNCH(0); break;
+    }
+#undef FEP_RS_LAUNCH
     (*counter)++;
     return (int)cudaGetLastError();
 }

@@ -318,9 +318,107 @@ struct MaxOp
 
 } // namespace
 
+/* ---- hand-over of per-thread lists (fepb200_set_lists) ---------------------------------------- */
+__global__ void k_add_offset(int* __restrict__ v, int n, int offset)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        v[i] += offset;
+    }
+}
+
+/* atom indices of the lists -> indices of set_atoms through `map` (out-of-range entries become -1, which the range
+ * check reports), then the range check: bad[0] counts the offending entries */
+__global__ void k_remap_and_check(int* __restrict__ iinr, int nri, int* __restrict__ jjnr, long long nrj,
+                                  const int* __restrict__ map, int n_map, int natoms, int* __restrict__ bad)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int which = 0; which < 2; which++)
+    {
+        int* v = which == 0 ? iinr : jjnr;
+        if (i < (which == 0 ? (long long)nri : nrj))
+        {
+            int a = v[i];
+            if (map != nullptr)
+            {
+                a    = (a >= 0 && a < n_map) ? map[a] : -1;
+                v[i] = a;
+            }
+            if (a < 0 || a >= natoms)
+            {
+                atomicAdd(bad, 1);
+            }
+        }
+    }
+}
+
+extern "C" int fep_list_add_offset(int* d_v, int n, int offset, cudaStream_t stream, long long* counter)
+{
+    if (n > 0 && offset != 0)
+    {
+        k_add_offset<<<(n + 255) / 256, 256, 0, stream>>>(d_v, n, offset);
+        (*counter)++;
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int fep_list_remap_and_check(int* d_iinr, int nri, int* d_jjnr, long long nrj, const int* d_map, int n_map, int natoms,
+                                        int* d_bad, cudaStream_t stream, long long* counter)
+{
+    cudaMemsetAsync(d_bad, 0, sizeof(int), stream);
+    const long long n = std::max<long long>(nri, nrj);
+    if (n > 0)
+    {
+        k_remap_and_check<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_iinr, nri, d_jjnr, nrj, d_map, n_map, natoms, d_bad);
+        (*counter)++;
+    }
+    return (int)cudaGetLastError();
+}
+
+/* ---- the epilogue's atom records (fep_types.h): {atom, first contribution, one past the last, 0} of every atom
+ * that receives contributions from this context's list, light and heavy atoms compacted into two arrays -------- */
+struct RecIsLight
+{
+    __device__ __forceinline__ bool operator()(const int4& r) const
+    {
+        const int n = r.z - r.y;
+        return n > 0 && n <= FEP_HEAVY_MIN;
+    }
+};
+struct RecIsHeavy
+{
+    __device__ __forceinline__ bool operator()(const int4& r) const { return r.z - r.y > FEP_HEAVY_MIN; }
+};
+
+__global__ void k_atom_records(const int* __restrict__ atom_ptr, int nT, int4* __restrict__ rec)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < nT)
+    {
+        rec[a] = make_int4(a, atom_ptr[a], atom_ptr[a + 1], 0);
+    }
+}
+
+/* d_counts[0] = light atoms, d_counts[1] = heavy atoms */
+extern "C" int fep_list_build_records(const int* d_atom_ptr, int nT, int4* d_rec, int4* d_light, int4* d_heavy, int* d_counts,
+                                      void* d_tmp, size_t tmp_bytes, cudaStream_t stream, long long* counter)
+{
+    cudaMemsetAsync(d_counts, 0, 2 * sizeof(int), stream);
+    if (nT > 0)
+    {
+        k_atom_records<<<(nT + 255) / 256, 256, 0, stream>>>(d_atom_ptr, nT, d_rec);
+        cub::DeviceSelect::If(d_tmp, tmp_bytes, d_rec, d_light, d_counts, nT, RecIsLight(), stream);
+        cub::DeviceSelect::If(d_tmp, tmp_bytes, d_rec, d_heavy, d_counts + 1, nT, RecIsHeavy(), stream);
+        (*counter) += 3;
+    }
+    return (int)cudaGetLastError();
+}
+
 extern "C" size_t fep_list_build_temp_bytes(int natoms, long long n_sort_max)
 {
-    size_t a = 0, b = 0, c = 0, d = 0, e = 0;
+    size_t a = 0, b = 0, c = 0, d = 0, e = 0, f = 0;
+    cub::DeviceSelect::If(nullptr, f, (const int4*)nullptr, (int4*)nullptr, (int*)nullptr, natoms + 1, RecIsLight());
     cub::DeviceScan::ExclusiveSum(nullptr, a, (const int*)nullptr, (int*)nullptr, natoms + 1);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, (int)n_sort_max + 1);
     cub::DeviceRadixSort::SortPairs(nullptr, c, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr,
@@ -328,7 +426,7 @@ extern "C" size_t fep_list_build_temp_bytes(int natoms, long long n_sort_max)
     cub::DeviceRadixSort::SortPairs(nullptr, d, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                     (const int*)nullptr, (int*)nullptr, (int)n_sort_max, 0, 63);
     cub::DeviceScan::InclusiveScan(nullptr, e, (const int*)nullptr, (int*)nullptr, MaxOp(), (int)n_sort_max + 1);
-    return std::max(std::max(a, e), std::max(b, std::max(c, d))) + 256;
+    return std::max(std::max(std::max(a, e), f), std::max(b, std::max(c, d))) + 256;
 }
 
 /* Phase 1: compact numbering.  mark/cscan: int[natoms+1]; returns after queuing (nT = cscan[natoms]). */

@@ -183,6 +183,7 @@ struct KernelArgs
     int pass_n_tiles; /* CTAs of the force-only Beutler kernel */
     int n_parts;      /* partial dV/dlambda sums written by the pass of this step */
     int fuse_pass_and_foreign;         /* Beutler path: pass + first foreign chunk in one launch */
+    int gapsys_hoisted;                /* Gapsys without potential switch: foreign passes by fep_gapsys.cu */
     int n_red_jobs, n_shift_jobs;
     int pdl_chain;                     /* set per step by the launcher: kernels after the first are chained (PDL) */
     /* inputs */
@@ -202,11 +203,14 @@ struct KernelArgs
     unsigned int* done_counter;
     /* epilogue inputs */
     const int*    atom_ptr;
-    const int*    heavy_atoms; /* [n_heavy] atoms with more than FEP_HEAVY_MIN contributions, ascending */
+    /* the atoms that receive contributions FROM THIS CONTEXT'S LIST as records {atom, first contribution, one past the
+     * last, 0}, ascending by atom: one coalesced 16-byte load tells an epilogue thread all it needs (fetched before it
+     * waits for the pair kernels).  heavy: more than FEP_HEAVY_MIN contributions, light: the others.  Atoms of the
+     * compact numbering without any contribution (a rank's shard of a split list) are never visited: their words of
+     * the result block stay zero. */
+    const int4*   heavy_atoms;
     int           n_heavy;
-    const int*    light_atoms; /* [n_light] the other atoms that receive contributions FROM THIS CONTEXT'S LIST, ascending;
-                                  atoms of the compact numbering without any (a rank's shard of a split list) are never
-                                  visited: their words of the result block stay zero */
+    const int4*   light_atoms;
     int           n_light;
     const RedJob* red_jobs;
     const int*    key_job_ptr; /* [45 + G + 1]: jobs of each key, shift keys first */
@@ -265,6 +269,11 @@ int fep_beutler_chunk_size(int n_points, int n_chunks_wanted);
 int fep_beutler_ctas_per_sm(int elec_ewald, int mode, int chunk_points, int force);
 /* chained != 0: a kernel of this step is already queued on `stream` and the launches may start
  * before it has completed (programmatic dependent launch, see fep_launch_kernel below) */
+/* fep_gapsys.cu: the energy-only foreign-lambda passes of the Gapsys soft-core with the lambda-independent part hoisted */
+int fep_gapsys_chunk_size(int n_points);
+int fep_gapsys_ctas_per_sm(int elec_ewald, int chunk_points);
+int fep_launch_gapsys_foreign(const KernelArgs* ka, int elec_ewald, const LambdaPoint* host_pts, cudaStream_t stream,
+                              long long* launch_counter, int chained);
 int fep_launch_beutler(const KernelArgs* ka, int elec_ewald, int mode, const LambdaPoint* host_cur,
                        const LambdaPoint* host_pts, int do_force, int do_foreign, int want_shift, cudaStream_t stream,
                        long long* launch_counter, int chained);
@@ -282,6 +291,12 @@ struct PeerPtrs
 int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* flags, int rank, unsigned int seq, int nranks,
                            double* out_f64, int n64, size_t f64_bytes, float* out_f32, long long n32,
                            cudaStream_t stream, long long* launch_counter, int chained, unsigned int* fault);
+/* the reduce-scatter flavour: this rank keeps the sum of the fp32 words [w0, w1) (its atoms' forces), of the 135
+ * shift-force words at off_fshift and of the n64 doubles */
+int fep_launch_peer_reduce_scatter(const PeerPtrs* peers, const PeerPtrs* flags, int rank, unsigned int seq, int nranks,
+                                   double* out_f64, int n64, size_t f64_bytes, float* out_f32, long long w0, long long w1,
+                                   long long off_fshift, cudaStream_t stream, long long* launch_counter, int chained,
+                                   unsigned int* fault);
 int fep_launch_gather_x(const float* d_x, int stride, const int* d_touched, float* pos3, int n_touched,
                         cudaStream_t stream, long long* launch_counter);
 /* fepb200_export_scalars_device(): where the values sit in the fp64 part of the result block, and the

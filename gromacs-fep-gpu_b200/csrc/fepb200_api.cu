@@ -38,6 +38,11 @@ extern "C" int    fep_list_build_groups(const ListBuild* b, const int* d_iinr, c
                                         int nT, int G, int wide_keys, cudaStream_t stream, long long* counter);
 extern "C" int    fep_list_build_slots(const ListBuild* b, const int* d_excl, int j0, const float4* d_par4, int ntype, int P, int NT,
                                        int nT, int G, int wide_keys, int run_trips, cudaStream_t stream, long long* counter);
+extern "C" int    fep_list_build_records(const int* d_atom_ptr, int nT, int4* d_rec, int4* d_light, int4* d_heavy, int* d_counts,
+                                         void* d_tmp, size_t tmp_bytes, cudaStream_t stream, long long* counter);
+extern "C" int    fep_list_add_offset(int* d_v, int n, int offset, cudaStream_t stream, long long* counter);
+extern "C" int    fep_list_remap_and_check(int* d_iinr, int nri, int* d_jjnr, long long nrj, const int* d_map, int n_map, int natoms,
+                                           int* d_bad, cudaStream_t stream, long long* counter);
 extern "C" int    fep_launch_source_tables(const unsigned int* d_trips, int NT, int tpr, unsigned char* d_slot_src,
                                            unsigned char* d_fshift_src, unsigned char* d_ev2_src, cudaStream_t stream,
                                            long long* counter);
@@ -234,7 +239,7 @@ struct fepb200_ctx
     /* raw list + scratch of the device-side list build (fep_list_build.cu) */
     DeviceArray<int> d_raw_iinr, d_raw_gid, d_raw_shift, d_raw_jindex, d_raw_jjnr, d_raw_excl, d_mark, d_cscan, d_pj, d_pn, d_deg,
             d_vals, d_vals_out, d_gmark, d_gstart, d_th, d_tsc, d_akeys, d_akeys_out, d_avals, d_avals_out, d_tshift, d_key_ptr;
-    DeviceArray<int> d_tfirst, d_kshift, d_kgid;
+    DeviceArray<int> d_tfirst, d_kshift, d_kgid, d_atom_map, d_bad;
     DeviceArray<unsigned long long> d_keys, d_keys_out;
     DeviceArray<unsigned char> d_cub_tmp;
     /* what phase 3 of the list build (slots + segments, build_segments()) needs to run again with another run length */
@@ -258,13 +263,25 @@ struct fepb200_ctx
     int            x_range_trips = 0;   /* trips per rank, rounded up (same on every rank) */
     int            x_trip_begin = 0, x_trip_end = 0, x_atom_begin = 0, x_atom_end = 0, x_heavy_begin = 0, x_heavy_end = 0;
     DeviceArray<unsigned char> d_slot_src, d_fshift_src, d_ev2_src; /* producer rank of every sorted element */
-    DeviceArray<int>    d_heavy;      /* atoms with more than FEP_HEAVY_MIN force contributions, ascending */
-    std::vector<int>    heavy_atoms;  /* host copy */
-    DeviceArray<int>    d_light;      /* the other atoms with contributions from this context's list, ascending */
-    std::vector<int>    light_atoms;
+    DeviceArray<int4>   d_heavy;      /* atoms with more than FEP_HEAVY_MIN force contributions, ascending: {atom, k0, k1, 0} */
+    std::vector<int4>   heavy_atoms;  /* host copy */
+    DeviceArray<int4>   d_light;      /* the other atoms with contributions from this context's list, ascending */
+    std::vector<int4>   light_atoms;
+    std::vector<int>    local_atoms;  /* compact atoms that occur in THIS context's pairs (= light + heavy), ascending: the
+                                         only coordinates its kernels read */
+    /* the records are built on the device; the host copies above (and w_atom_ptr) are fetched only by those who need
+     * them: a shard of a split list (its gather) and the peer exchange (its atom ranges) */
+    DeviceArray<int4>   d_atom_rec;
+    DeviceArray<int>    d_rec_counts;
+    bool                host_lists_valid = false;
+    bool                shard_local      = false; /* upload_x gathers the atoms of local_atoms only */
     int                 x_light_begin = 0, x_light_end = 0;
     /* atoms of the compact numbering that receive nothing from this context's list are never written by the epilogue:
      * every result block is zeroed once per list (own blocks in prepare_buffers, a caller's block at its first step) */
+    /* fepb200_reduce_scatter_peers(): after the reduction this context holds the forces of the compact atoms
+     * [own_begin, own_end) only (zeros elsewhere) and all scalars */
+    bool                own_on = false;
+    int                 own_begin = 0, own_end = 0;
     bool                result_needs_zero = true;
     std::vector<void*>  zeroed_targets;
     DeviceArray<unsigned long long> d_trace;                        /* fepb200_epilogue_trace() */
@@ -415,6 +432,7 @@ int prepare_buffers(fepb200_ctx* c)
     const int runs  = (range + k.run_trips - 1) / std::max(k.run_trips, 1);
     k.n_cta         = (runs + FEP_CTA / 32 - 1) / (FEP_CTA / 32); /* generic pass kernel: one warp per run */
     c->foreign_mode = -1;
+    k.gapsys_hoisted = 0;
     if (c->softcore == FEP_SC_BEUTLER && !k.pot_switch)
     {
         /* nb_free_energy.cpp:1405-1419 decides per call whether the Coulomb and LJ soft-core radii
@@ -441,11 +459,12 @@ int prepare_buffers(fepb200_ctx* c)
         }
         k.chunk_points = fep_beutler_chunk_size(np, want);
         k.n_chunks     = (np + k.chunk_points - 1) / k.chunk_points;
-        /* a warp evaluates whole runs, run after run with a grid-wide stride: one wave of resident CTAs, or fewer
-         * when there are not enough runs for all of their warps */
-        auto tiles = [&](long long ctas_per_sm, int& n_tiles) {
-            const long long by_runs = ((long long)runs + FEP_FB_CTA / 32 - 1) / (FEP_FB_CTA / 32);
-            n_tiles                 = runs > 0 ? (int)std::max(1LL, std::min(by_runs, (long long)sms * ctas_per_sm)) : 0;
+        /* a warp evaluates whole runs, run after run with a grid-wide stride, warp-major (the first warps of all CTAs
+         * first): one full wave of resident CTAs whenever there is a run for every CTA, so that the busy warps are
+         * spread evenly over the SMs; fewer CTAs only for lists with fewer runs than that */
+        auto tiles = [&](long long ctas_per_sm, bool with_force, int& n_tiles) {
+            const long long units = with_force ? runs : range; /* energy-only launches walk single trips */
+            n_tiles               = units > 0 ? (int)std::max(1LL, std::min(units, (long long)sms * ctas_per_sm)) : 0;
         };
         /* fuse pass + foreign when the list is too small to fill the GPU anyway */
         k.fuse_pass_and_foreign = pair_ctas < 16LL * sms;
@@ -464,9 +483,20 @@ int prepare_buffers(fepb200_ctx* c)
         };
         tiles(per_sm("FEPB200_FOREIGN_CTAS_PER_SM",
                      fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, k.chunk_points, k.fuse_pass_and_foreign)),
-              k.n_tiles);
-        tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)),
+              k.fuse_pass_and_foreign != 0, k.n_tiles);
+        tiles(per_sm("FEPB200_PASS_CTAS_PER_SM", fep_beutler_ctas_per_sm(c->elec_ewald, c->foreign_mode, 0, 1)), true,
               k.pass_n_tiles);
+    }
+    else if (c->softcore == FEP_SC_GAPSYS && !k.pot_switch && std::getenv("FEPB200_GAPSYS_GENERIC") == nullptr)
+    {
+        /* fep_gapsys.cu: single trips dealt to the warps of one wave of CTAs, chunks of at most 8 points */
+        k.gapsys_hoisted = 1;
+        k.chunk_points   = fep_gapsys_chunk_size(np);
+        k.n_chunks       = (np + k.chunk_points - 1) / k.chunk_points;
+        k.tile_trips     = 0;
+        /* grid = n_tiles x n_chunks CTAs: about one wave in total */
+        const long long wave = (long long)sms * fep_gapsys_ctas_per_sm(c->elec_ewald, k.chunk_points);
+        k.n_tiles            = range > 0 ? (int)std::max(1LL, std::min<long long>(range, (wave + k.n_chunks - 1) / k.n_chunks)) : 0;
     }
     else
     {
@@ -685,38 +715,79 @@ static void build_jobs(const int* shift_ptr /*[46]*/, const int* gid_ptr /*[G+1]
 /* The device-side builder of the list layout (fep_list_build.cu): raw list to the GPU, then
  * kernels, scans and stable sorts; only two scalars (nT, H), the touched-atom list and 47 + G
  * counters come back to the host. */
-static int build_list_device(fepb200_ctx* c, int nri, const int* iinr, const int* gid, const int* shift,
-                             const int* jindex, const int* jjnr, const int* excl_fep, long long nrj_total, int ngrp, int e0,
-                             int E, int j0, int P)
+static int build_list_device(fepb200_ctx* c, int n_lists, const fepb200_list_view* lists, const int* atom_map, int n_map, int nri,
+                             long long nrj_total, int ngrp, int e0, int E, int j0, int P)
 {
     cudaStream_t st = c->stream;
-    /* raw list */
+    /* raw lists: every list's arrays go straight to their place in the concatenated device arrays */
     CU_CHECK(c, c->d_raw_iinr.reserve(std::max(nri, 1)));
     CU_CHECK(c, c->d_raw_gid.reserve(std::max(nri, 1)));
     CU_CHECK(c, c->d_raw_shift.reserve(std::max(nri, 1)));
     CU_CHECK(c, c->d_raw_jindex.reserve((size_t)nri + 1));
     CU_CHECK(c, c->d_raw_jjnr.reserve(std::max<long long>(nrj_total, 1)));
-    if (nri > 0)
-    {
-        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_iinr.ptr, iinr, sizeof(int) * nri, cudaMemcpyHostToDevice, st));
-        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_gid.ptr, gid, sizeof(int) * nri, cudaMemcpyHostToDevice, st));
-        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_shift.ptr, shift, sizeof(int) * nri, cudaMemcpyHostToDevice, st));
-        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_jindex.ptr, jindex, sizeof(int) * ((size_t)nri + 1), cudaMemcpyHostToDevice, st));
-    }
-    else
-    {
-        CU_CHECK(c, cudaMemsetAsync(c->d_raw_jindex.ptr, 0, sizeof(int), st));
-    }
-    if (nrj_total > 0)
-    {
-        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_jjnr.ptr, jjnr, sizeof(int) * nrj_total, cudaMemcpyHostToDevice, st));
-    }
-    const int* d_excl = nullptr;
-    if (excl_fep && nrj_total > 0)
+    CU_CHECK(c, c->d_bad.reserve(1));
+    const bool have_excl = n_lists > 0 && lists[0].excl_fep != nullptr && nrj_total > 0;
+    if (have_excl)
     {
         CU_CHECK(c, c->d_raw_excl.reserve(nrj_total));
-        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_excl.ptr, excl_fep, sizeof(int) * nrj_total, cudaMemcpyHostToDevice, st));
-        d_excl = c->d_raw_excl.ptr;
+    }
+    {
+        int       eo = 0;
+        long long po = 0;
+        for (int l = 0; l < n_lists; l++)
+        {
+            const fepb200_list_view& v = lists[l];
+            const long long          np = v.nri > 0 ? v.jindex[v.nri] : 0;
+            if (v.nri > 0)
+            {
+                CU_CHECK(c, cudaMemcpyAsync(c->d_raw_iinr.ptr + eo, v.iinr, sizeof(int) * v.nri, cudaMemcpyHostToDevice, st));
+                CU_CHECK(c, cudaMemcpyAsync(c->d_raw_gid.ptr + eo, v.gid, sizeof(int) * v.nri, cudaMemcpyHostToDevice, st));
+                CU_CHECK(c, cudaMemcpyAsync(c->d_raw_shift.ptr + eo, v.shift, sizeof(int) * v.nri, cudaMemcpyHostToDevice, st));
+                CU_CHECK(c, cudaMemcpyAsync(c->d_raw_jindex.ptr + eo, v.jindex, sizeof(int) * v.nri, cudaMemcpyHostToDevice, st));
+                const int err = fep_list_add_offset(c->d_raw_jindex.ptr + eo, v.nri, (int)po, st, &c->launches);
+                if (err != 0)
+                {
+                    return fail(c, FEPB200_ERR_CUDA, "list hand-over failed: %s", cudaGetErrorString((cudaError_t)err));
+                }
+            }
+            if (np > 0)
+            {
+                CU_CHECK(c, cudaMemcpyAsync(c->d_raw_jjnr.ptr + po, v.jjnr, sizeof(int) * np, cudaMemcpyHostToDevice, st));
+                if (have_excl)
+                {
+                    CU_CHECK(c, cudaMemcpyAsync(c->d_raw_excl.ptr + po, v.excl_fep, sizeof(int) * np, cudaMemcpyHostToDevice, st));
+                }
+            }
+            eo += v.nri;
+            po += np;
+        }
+        const int last = (int)nrj_total;
+        CU_CHECK(c, cudaMemcpyAsync(c->d_raw_jindex.ptr + nri, &last, sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    const int* d_excl = have_excl ? c->d_raw_excl.ptr : nullptr;
+    /* index space of the lists -> index space of set_atoms, and the range check of every atom index, on the device */
+    const int* d_map = nullptr;
+    if (atom_map != nullptr && n_map > 0)
+    {
+        CU_CHECK(c, c->d_atom_map.reserve(n_map));
+        CU_CHECK(c, cudaMemcpyAsync(c->d_atom_map.ptr, atom_map, sizeof(int) * (size_t)n_map, cudaMemcpyHostToDevice, st));
+        d_map = c->d_atom_map.ptr;
+    }
+    {
+        const int err = fep_list_remap_and_check(c->d_raw_iinr.ptr, nri, c->d_raw_jjnr.ptr, nrj_total, d_map, n_map, c->natoms,
+                                                 c->d_bad.ptr, st, &c->launches);
+        if (err != 0)
+        {
+            return fail(c, FEPB200_ERR_CUDA, "list hand-over failed: %s", cudaGetErrorString((cudaError_t)err));
+        }
+        int bad = 0;
+        CU_CHECK(c, cudaMemcpyAsync(&bad, c->d_bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(c, cudaStreamSynchronize(st));
+        if (bad != 0)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: %d atom indices of the list%s are outside [0,%d)", bad,
+                        d_map ? " (after the atom map)" : "", c->natoms);
+        }
     }
     if (c->ntype > FEP_MAX_NTYPE)
     {
@@ -842,6 +913,51 @@ static int choose_run_trips(const fepb200_ctx* c, long long trips)
     return r;
 }
 
+/* host copies of what the device built: every atom's range in the atom-sorted buffer, the records of the light and
+ * heavy atoms, and the atoms this context's pairs touch */
+static int fetch_atom_lists(fepb200_ctx* c)
+{
+    if (c->host_lists_valid)
+    {
+        return FEPB200_OK;
+    }
+    const int nT = c->lb.nT;
+    c->w_atom_ptr.assign((size_t)nT + 1, 0);
+    c->light_atoms.resize(c->ka.n_light);
+    c->heavy_atoms.resize(c->ka.n_heavy);
+    if (c->lb.P > 0)
+    {
+        CU_CHECK(c, cudaMemcpyAsync(c->w_atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost, c->stream));
+        if (c->ka.n_light > 0)
+        {
+            CU_CHECK(c, cudaMemcpyAsync(c->light_atoms.data(), c->d_light.ptr, sizeof(int4) * (size_t)c->ka.n_light, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (c->ka.n_heavy > 0)
+        {
+            CU_CHECK(c, cudaMemcpyAsync(c->heavy_atoms.data(), c->d_heavy.ptr, sizeof(int4) * (size_t)c->ka.n_heavy, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    }
+    c->local_atoms.resize(c->light_atoms.size() + c->heavy_atoms.size());
+    {
+        /* merge of two ascending lists */
+        size_t i = 0, j = 0, o = 0;
+        while (i < c->light_atoms.size() || j < c->heavy_atoms.size())
+        {
+            if (j >= c->heavy_atoms.size() || (i < c->light_atoms.size() && c->light_atoms[i].x < c->heavy_atoms[j].x))
+            {
+                c->local_atoms[o++] = c->light_atoms[i++].x;
+            }
+            else
+            {
+                c->local_atoms[o++] = c->heavy_atoms[j++].x;
+            }
+        }
+    }
+    c->host_lists_valid = true;
+    return FEPB200_OK;
+}
+
 /* Phase 3 of the list build for runs of `run_trips` trips, and everything that follows from it: segment slots,
  * atom ranges, reduction jobs, heavy atoms, the intermediate buffers.  set_list() calls it once; the peer
  * exchange calls it again when a rank's share of the trips wants shorter runs. */
@@ -855,14 +971,25 @@ static int build_segments(fepb200_ctx* c, int run_trips)
     {
         return fail(c, FEPB200_ERR_CUDA, "list build (slots) failed: %s", cudaGetErrorString((cudaError_t)err));
     }
-    /* back to the host: the per-key counts (for the reduction jobs) and the range of every touched atom in the
-     * atom-sorted buffer (the host picks the heavy atoms from it) */
+    /* the epilogue's atom records, light and heavy, compacted on the device */
+    CU_CHECK(c, c->d_atom_rec.reserve(std::max(nT, 1)));
+    CU_CHECK(c, c->d_light.reserve(std::max(nT, 1)));
+    CU_CHECK(c, c->d_heavy.reserve(std::max(nT, 1)));
+    CU_CHECK(c, c->d_rec_counts.reserve(2));
+    err = fep_list_build_records(c->d_atom_ptr.ptr, P > 0 ? nT : 0, c->d_atom_rec.ptr, c->d_light.ptr, c->d_heavy.ptr,
+                                 c->d_rec_counts.ptr, c->lb.b.tmp, c->lb.b.tmp_bytes, st, &c->launches);
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "list build (records) failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    /* back to the host: the per-key counts (for the reduction jobs), the number of contributions and of records */
     std::vector<int> key_ptr(FEP_NUM_SHIFT + 1 + ngrp + 1, 0);
+    int              n_contrib = 0, counts[2] = { 0, 0 };
     CU_CHECK(c, cudaMemcpyAsync(key_ptr.data(), c->d_key_ptr.ptr, sizeof(int) * key_ptr.size(), cudaMemcpyDeviceToHost, st));
-    c->w_atom_ptr.resize((size_t)nT + 1);
-    CU_CHECK(c, cudaMemcpyAsync(c->w_atom_ptr.data(), c->d_atom_ptr.ptr, sizeof(int) * ((size_t)nT + 1), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaMemcpyAsync(&n_contrib, c->d_atom_ptr.ptr + nT, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaMemcpyAsync(counts, c->d_rec_counts.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_CHECK(c, cudaStreamSynchronize(st));
-    const int NS = P > 0 ? c->w_atom_ptr[nT] - P : 0;
+    const int NS = P > 0 ? n_contrib - P : 0;
     if (NS < 0 || NS > NT || key_ptr[FEP_NUM_SHIFT] != NS || key_ptr[FEP_NUM_SHIFT + 1 + ngrp] != NS)
     {
         return fail(c, FEPB200_ERR_CUDA, "list build: inconsistent segment counts (%d, %d, %d of %d trips)", NS,
@@ -876,25 +1003,8 @@ static int build_segments(fepb200_ctx* c, int run_trips)
     {
         return rc;
     }
-    /* atoms with long contribution ranges get a whole warp in the epilogue */
-    c->heavy_atoms.clear();
-    c->light_atoms.clear();
-    for (int a = 0; a < nT; a++)
-    {
-        const int n = c->w_atom_ptr[a + 1] - c->w_atom_ptr[a];
-        if (n > FEP_HEAVY_MIN)
-        {
-            c->heavy_atoms.push_back(a);
-        }
-        else if (n > 0)
-        {
-            c->light_atoms.push_back(a);
-        }
-    }
-    if ((rc = to_device(c, c->d_heavy, c->heavy_atoms)) != FEPB200_OK || (rc = to_device(c, c->d_light, c->light_atoms)) != FEPB200_OK)
-    {
-        return rc;
-    }
+    c->host_lists_valid = false;
+    c->shard_local      = false;
     CU_CHECK(c, c->d_fsorted.reserve(std::max(P + NS, 1)));
     CU_CHECK(c, c->d_fshift_sorted.reserve(std::max(NS, 1)));
     CU_CHECK(c, c->d_ev2.reserve(std::max(NS, 1)));
@@ -902,6 +1012,7 @@ static int build_segments(fepb200_ctx* c, int run_trips)
     CU_CHECK(c, cudaStreamSynchronize(st)); /* host vectors go out of scope */
     KernelArgs& k   = c->ka;
     c->result_needs_zero = true;
+    c->own_on            = false;
     c->zeroed_targets.clear();
     c->n_segs       = NS;
     k.n_segs        = NS;
@@ -913,9 +1024,9 @@ static int build_segments(fepb200_ctx* c, int run_trips)
     k.job_part      = c->d_job_part.ptr;
     k.atom_ptr      = c->d_atom_ptr.ptr;
     k.heavy_atoms   = c->d_heavy.ptr;
-    k.n_heavy       = (int)c->heavy_atoms.size();
+    k.n_heavy       = counts[1];
     k.light_atoms   = c->d_light.ptr;
-    k.n_light       = (int)c->light_atoms.size();
+    k.n_light       = counts[0];
     k.red_jobs      = c->d_red_jobs.ptr;
     k.key_job_ptr   = c->d_key_job_ptr.ptr;
     return FEPB200_OK;
@@ -1328,18 +1439,51 @@ int fepb200_set_atoms(fepb200_ctx* c, int natoms, const float* qA, const float* 
 int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, const int* shift, const int* jindex,
                      const int* jjnr, const int* excl_fep, int ngrp, int rank, int nranks)
 {
-    if (!c || nri < 0 || ngrp < 1 || nranks < 1 || rank < 0 || rank >= nranks)
-    {
-        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: bad arguments");
-    }
     if (nri > 0 && (!iinr || !gid || !shift || !jindex))
     {
         return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: NULL list array");
     }
-    if (c->natoms == 0 && nri > 0)
+    fepb200_list_view v;
+    v.nri = nri, v.iinr = iinr, v.gid = gid, v.shift = shift, v.jindex = jindex, v.jjnr = jjnr, v.excl_fep = excl_fep;
+    return fepb200_set_lists(c, 1, &v, nullptr, 0, ngrp, rank, nranks);
+}
+
+int fepb200_set_lists(fepb200_ctx* c, int n_lists, const fepb200_list_view* lists, const int* atom_map, int n_map, int ngrp,
+                      int rank, int nranks)
+{
+    if (!c || n_lists < 0 || (n_lists > 0 && !lists) || ngrp < 1 || nranks < 1 || rank < 0 || rank >= nranks || n_map < 0)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: bad arguments");
+    }
+    long long nri_ll = 0, nrj_total = 0;
+    for (int l = 0; l < n_lists; l++)
+    {
+        const fepb200_list_view& v = lists[l];
+        if (v.nri < 0 || (v.nri > 0 && (!v.iinr || !v.gid || !v.shift || !v.jindex)))
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: NULL list array");
+        }
+        const long long np = v.nri > 0 ? v.jindex[v.nri] : 0;
+        if (v.nri > 0 && (v.jindex[0] != 0 || np < 0 || (np > 0 && !v.jjnr)))
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: jindex must start at 0");
+        }
+        if ((v.excl_fep != nullptr) != (lists[0].excl_fep != nullptr) && np > 0)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_lists: excl_fep must be given for all lists or for none");
+        }
+        nri_ll += v.nri;
+        nrj_total += np;
+    }
+    if (c->natoms == 0 && nri_ll > 0)
     {
         return fail(c, FEPB200_ERR_STATE, "fepb200_set_atoms() must precede fepb200_set_list()");
     }
+    if (nrj_total >= (1LL << 31) - 64 || nri_ll >= (1LL << 31) - 64)
+    {
+        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than 2^31 pairs in one list");
+    }
+    const int nri = (int)nri_ll;
     cudaSetDevice(c->device);
     const bool  timing = std::getenv("FEPB200_TIMING") != nullptr;
     const auto  t_begin = std::chrono::steady_clock::now();
@@ -1352,70 +1496,58 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
             last = now;
         }
     };
-    const long long nrj_total = nri > 0 ? jindex[nri] : 0;
-    if (nri > 0 && (jindex[0] != 0 || nrj_total < 0 || (nrj_total > 0 && !jjnr)))
+    /* per i-entry checks on the host (O(nri)); the atom indices of the pairs are checked on the device */
+    for (int l = 0; l < n_lists; l++)
     {
-        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: jindex must start at 0");
-    }
-    if (nrj_total >= (1LL << 31) - 64)
-    {
-        return fail(c, FEPB200_ERR_UNSUPPORTED, "more than 2^31 pairs in one list");
-    }
-    for (int n = 0; n < nri; n++)
-    {
-        if (jindex[n + 1] < jindex[n] || iinr[n] < 0 || iinr[n] >= c->natoms || gid[n] < 0 || gid[n] >= ngrp
-            || shift[n] < 0 || shift[n] >= FEP_NUM_SHIFT)
+        const fepb200_list_view& v = lists[l];
+        for (int n = 0; n < v.nri; n++)
         {
-            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: i-entry %d is malformed", n);
-        }
-    }
-    {
-        long long bad = -1;
-#pragma omp parallel for schedule(static) reduction(max : bad) num_threads(std::min(8, std::max(1, omp_get_max_threads()))) if (nrj_total > 65536)
-        for (long long k = 0; k < nrj_total; k++)
-        {
-            if (jjnr[k] < 0 || jjnr[k] >= c->natoms)
+            if (v.jindex[n + 1] < v.jindex[n] || v.gid[n] < 0 || v.gid[n] >= ngrp || v.shift[n] < 0 || v.shift[n] >= FEP_NUM_SHIFT)
             {
-                bad = std::max(bad, k);
+                return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: i-entry %d of list %d is malformed", n, l);
             }
-        }
-        if (bad >= 0)
-        {
-            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_list: jjnr[%lld] out of range", bad);
         }
     }
 
     lap("validate");
-    /* this rank's contiguous range of i-entries, balanced by pair count */
-    int e0 = 0, e1 = nri;
+    /* this rank's contiguous range of i-entries of the concatenation, balanced by pair count */
+    int       e0 = 0, e1 = nri;
+    long long j0_ll = 0, j1_ll = nrj_total;
     if (nranks > 1)
     {
-        std::vector<int> first(nranks + 1, nri);
+        std::vector<int>       first(nranks + 1, nri);
+        std::vector<long long> first_pair(nranks + 1, nrj_total);
         first[0]               = 0;
+        first_pair[0]          = 0;
         const long long target = (nrj_total + nranks - 1) / nranks;
-        int             dest   = 0;
-        long long       have   = 0;
-        for (int n = 0; n < nri; n++)
+        int             dest   = 0, n_glob = 0;
+        long long       have   = 0, pairs_before = 0;
+        for (int l = 0; l < n_lists; l++)
         {
-            const long long nrj = jindex[n + 1] - jindex[n];
-            if (dest + 1 < nranks && have > 0 && have + nrj - target > target - have)
+            const fepb200_list_view& v = lists[l];
+            for (int n = 0; n < v.nri; n++, n_glob++)
             {
-                dest++;
-                first[dest] = n;
-                have        = 0;
+                const long long nrj = v.jindex[n + 1] - v.jindex[n];
+                if (dest + 1 < nranks && have > 0 && have + nrj - target > target - have)
+                {
+                    dest++;
+                    first[dest]      = n_glob;
+                    first_pair[dest] = pairs_before;
+                    have             = 0;
+                }
+                have += nrj;
+                pairs_before += nrj;
             }
-            have += nrj;
         }
-        e0 = first[rank];
-        e1 = first[rank + 1];
+        e0 = first[rank], e1 = first[rank + 1];
+        j0_ll = first_pair[rank], j1_ll = first_pair[rank + 1];
     }
     const int E  = e1 - e0;
-    const int j0 = E > 0 ? jindex[e0] : 0;
-    const int P  = E > 0 ? jindex[e1] - j0 : 0;
-
+    const int j0 = E > 0 ? (int)j0_ll : 0;
+    const int P  = E > 0 ? (int)(j1_ll - j0_ll) : 0;
 
     /* the device layout is built on the GPU: kernels + scans + stable sorts (fep_list_build.cu) */
-    int rc = build_list_device(c, nri, iinr, gid, shift, jindex, jjnr, excl_fep, nrj_total, ngrp, e0, E, j0, P);
+    int rc = build_list_device(c, n_lists, lists, atom_map, n_map, nri, nrj_total, ngrp, e0, E, j0, P);
     if (rc != FEPB200_OK)
     {
         return rc;
@@ -1435,6 +1567,15 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     if ((rc = build_segments(c, choose_run_trips(c, H))) != FEPB200_OK)
     {
         return rc;
+    }
+    if (nranks > 1)
+    {
+        /* a shard of a split list gathers and uploads the coordinates of ITS atoms only */
+        if ((rc = fetch_atom_lists(c)) != FEPB200_OK)
+        {
+            return rc;
+        }
+        c->shard_local = (int)c->local_atoms.size() < nT;
     }
     lap("segments + buffers");
 
@@ -1697,6 +1838,34 @@ int fepb200_upload_x(fepb200_ctx* c, const float* x, const float* shiftvec)
     const int* t   = c->touched.data();
     /* Pipelined: the touched coordinates are gathered into pinned memory chunk by chunk and each
      * chunk's H2D copy is queued at once, so the DMA of chunk k runs while the host gathers k+1. */
+    if (c->shard_local && !c->px_on)
+    {
+        /* a shard of a split list: its kernels read the coordinates of the atoms of ITS pairs only -- gather those, and
+         * copy the span of the compact array that holds them */
+        const int* la = c->local_atoms.data();
+        const int  nL = (int)c->local_atoms.size();
+#pragma omp parallel for schedule(static) num_threads(host_threads(nT)) if (nL > c_host_grain)
+        for (int i = 0; i < nL; i++)
+        {
+            const int    k  = la[i];
+            const float* xa = x + 3 * (size_t)t[k];
+            pos[3 * (size_t)k]     = xa[0];
+            pos[3 * (size_t)k + 1] = xa[1];
+            pos[3 * (size_t)k + 2] = xa[2];
+        }
+        lap_us(c, 0);
+        CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr, c->h_step_in.ptr, sizeof(DynHead), cudaMemcpyHostToDevice, c->stream));
+        if (nL > 0)
+        {
+            const size_t b0 = sizeof(DynHead) + 3 * sizeof(float) * (size_t)la[0];
+            const size_t b1 = sizeof(DynHead) + 3 * sizeof(float) * ((size_t)la[nL - 1] + 1);
+            CU_CHECK(c, cudaMemcpyAsync(c->d_step_in.ptr + b0, c->h_step_in.ptr + b0, b1 - b0, cudaMemcpyHostToDevice, c->stream));
+        }
+        lap_us(c, 1);
+        c->staging_in_flight = true;
+        c->staged_by_event   = false;
+        return FEPB200_OK;
+    }
     const int nchunks = nT > 32768 ? c_copy_chunks : 1;
     size_t    done    = 0; /* bytes of [DynHead | pos3] already queued */
     for (int ch = 0; ch < nchunks; ch++)
@@ -1898,8 +2067,8 @@ int fepb200_add_forces_device(fepb200_ctx* c, float* d_f, int flags)
     /* the context's own result block: what fepb200_launch() fills (unless a partial block was set
      * for the peer reduction) and what fepb200_reduce_peers() leaves the sum over ranks in */
     const float* r32 = c->ka.res_f32;
-    const int    k0  = c->px_on ? c->x_atom_begin : 0;
-    const int    k1  = c->px_on ? c->x_atom_end : c->layout.ntouched;
+    const int    k0  = c->px_on ? c->x_atom_begin : (c->own_on ? c->own_begin : 0);
+    const int    k1  = c->px_on ? c->x_atom_end : (c->own_on ? c->own_end : c->layout.ntouched);
     const int    err = fep_launch_add_forces(r32, c->d_touched.ptr, d_f, k0, k1,
                                              (flags & FEPB200_CLEAR_OUTPUTS) != 0 ? FEP_ADD_OVERWRITE
                                              : ((flags & FEPB200_ATOMIC_OUTPUTS) != 0 ? FEP_ADD_ATOMIC : FEP_ADD_PLAIN),
@@ -2028,6 +2197,7 @@ int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks,
                     FEP_MAX_PEERS);
     }
     cudaSetDevice(c->device);
+    c->own_on = false; /* every rank receives everything */
     PeerPtrs pp{}, ff{};
     for (int r = 0; r < nranks; r++)
     {
@@ -2045,6 +2215,56 @@ int fepb200_reduce_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks,
     if (err != 0)
     {
         return fail(c, FEPB200_ERR_CUDA, "peer reduce launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    }
+    return FEPB200_OK;
+}
+
+int fepb200_reduce_scatter_peers(fepb200_ctx* c, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags, int rank,
+                                 unsigned int seq)
+{
+    if (!c || !c->have_list || !d_peer_blocks || nranks < 1 || nranks > FEP_MAX_PEERS || rank < 0 || rank >= nranks)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_reduce_scatter_peers: bad arguments (at most %d ranks)",
+                    FEP_MAX_PEERS);
+    }
+    if (c->px_on)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_reduce_scatter_peers: the fused peer exchange is on (it is the reduction)");
+    }
+    cudaSetDevice(c->device);
+    PeerPtrs pp{}, ff{};
+    for (int r = 0; r < nranks; r++)
+    {
+        pp.p[r] = d_peer_blocks[r];
+        ff.p[r] = d_peer_flags ? d_peer_flags[r] : nullptr;
+    }
+    /* equal atom ranges, starting on multiples of four atoms (so that a range of 3-word forces starts on a 16-byte
+     * boundary): the compact numbering is the one of the full list on every rank */
+    const long long nT  = c->layout.ntouched;
+    const long long per = ((nT + nranks - 1) / nranks + 3) / 4 * 4;
+    const int       a0  = (int)std::min(nT, per * rank), a1 = (int)std::min(nT, per * (rank + 1));
+    bool chained = c->chain_open;
+    if (!c->own_on || c->own_begin != a0 || c->own_end != a1)
+    {
+        /* forces of atoms other ranks own are never written here: keep them zero (something between the epilogue
+         * and the reduction: this one launch is not chained) */
+        CU_CHECK(c, cudaMemsetAsync(c->d_result.ptr, 0, c->res_f64_bytes + c->res_f32_bytes, c->stream));
+        chained      = false;
+        c->own_on    = true;
+        c->own_begin = a0;
+        c->own_end   = a1;
+    }
+    const int err = fep_launch_peer_reduce_scatter(&pp, d_peer_flags ? &ff : nullptr, rank, seq, nranks, c->ka.res_f64,
+                                                   (int)c->layout.f64_words, c->res_f64_bytes, c->ka.res_f32, 3LL * a0, 3LL * a1,
+                                                   c->layout.off_fshift, c->stream, &c->launches, chained ? 1 : 0, c->ka.fault);
+    if (c->chain_open)
+    {
+        c->chain_open = false;
+        cudaEventRecord(c->ev_stop, c->stream);
+    }
+    if (err != 0)
+    {
+        return fail(c, FEPB200_ERR_CUDA, "peer reduce-scatter launch failed: %s", cudaGetErrorString((cudaError_t)err));
     }
     return FEPB200_OK;
 }
@@ -2083,7 +2303,7 @@ size_t fepb200_exchange_bytes(const fepb200_ctx* c, int nranks)
     auto            up      = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t    P       = (size_t)c->ka.n_pairs, H = (size_t)c->ka.n_trips;
     const long long tpr     = ((long long)H + nranks - 1) / nranks + FEP_MAX_RUN_TRIPS;
-    const size_t    ctas    = (size_t)(tpr + 1);
+    const size_t    ctas    = (size_t)(4 * (tpr + 1)); /* the force-only pass writes four sums per warp */
     const size_t    np      = (size_t)std::max(c->layout.nforeign + 1, 32);
     const size_t    slot    = up((P + H) * sizeof(float4)) + up(H * sizeof(float4)) + up(H * sizeof(float2))
                         + up(4 * ctas * sizeof(double)) + up(3 * np * ctas * sizeof(double));
@@ -2150,7 +2370,15 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
         c->x_trip_begin         = (int)std::min<long long>((long long)rank * tpr, H);
         c->x_trip_end           = (int)std::min<long long>((long long)(rank + 1) * tpr, H);
         /* atoms: contiguous ranges with equal shares of the force contributions */
-        const std::vector<int>& atom_ptr = c->w_atom_ptr; /* kept by fepb200_set_list() */
+        {
+            const int rc_lists = fetch_atom_lists(c);
+            if (rc_lists != FEPB200_OK)
+            {
+                c->px_on = false;
+                return rc_lists;
+            }
+        }
+        const std::vector<int>& atom_ptr = c->w_atom_ptr;
         /* cost of an atom = its contributions + a fixed share for the lanes that serve it (a range
          * of many light atoms needs more blocks than a range of few heavy ones with the same volume) */
         const long long per_atom = 8;
@@ -2172,10 +2400,13 @@ int fepb200_set_peer_exchange(fepb200_ctx* c, int nranks, int rank, void* const*
         }
         c->x_atom_begin  = a_of[rank];
         c->x_atom_end    = a_of[rank + 1];
-        c->x_heavy_begin = (int)(std::lower_bound(c->heavy_atoms.begin(), c->heavy_atoms.end(), a_of[rank]) - c->heavy_atoms.begin());
-        c->x_heavy_end   = (int)(std::lower_bound(c->heavy_atoms.begin(), c->heavy_atoms.end(), a_of[rank + 1]) - c->heavy_atoms.begin());
-        c->x_light_begin = (int)(std::lower_bound(c->light_atoms.begin(), c->light_atoms.end(), a_of[rank]) - c->light_atoms.begin());
-        c->x_light_end   = (int)(std::lower_bound(c->light_atoms.begin(), c->light_atoms.end(), a_of[rank + 1]) - c->light_atoms.begin());
+        auto first_at = [](const std::vector<int4>& v, int atom) {
+            return (int)(std::lower_bound(v.begin(), v.end(), atom, [](const int4& r, int a) { return r.x < a; }) - v.begin());
+        };
+        c->x_heavy_begin = first_at(c->heavy_atoms, a_of[rank]);
+        c->x_heavy_end   = first_at(c->heavy_atoms, a_of[rank + 1]);
+        c->x_light_begin = first_at(c->light_atoms, a_of[rank]);
+        c->x_light_end   = first_at(c->light_atoms, a_of[rank + 1]);
         /* producer rank of every element of the sorted arrays */
         CU_CHECK(c, c->d_slot_src.reserve(std::max<size_t>((size_t)P + H, 1)));
         CU_CHECK(c, c->d_fshift_src.reserve(std::max(H, 1)));
@@ -2244,8 +2475,8 @@ int fepb200_peer_ranges(const fepb200_ctx* c, int* pair_begin, int* pair_end, in
     /* the range of trips (32 pair slots each) this context evaluates */
     if (pair_begin) *pair_begin = c->px_on ? c->x_trip_begin : 0;
     if (pair_end) *pair_end = c->px_on ? c->x_trip_end : c->ka.n_trips;
-    if (atom_begin) *atom_begin = c->px_on ? c->x_atom_begin : 0;
-    if (atom_end) *atom_end = c->px_on ? c->x_atom_end : c->ka.n_touched;
+    if (atom_begin) *atom_begin = c->px_on ? c->x_atom_begin : (c->own_on ? c->own_begin : 0);
+    if (atom_end) *atom_end = c->px_on ? c->x_atom_end : (c->own_on ? c->own_end : c->ka.n_touched);
     return FEPB200_OK;
 }
 
@@ -2275,12 +2506,13 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
      * event; the host scatter-adds chunk k while the DMA of chunk k+1 runs. */
     const int    nT      = l.ntouched;
     /* peer exchange: this rank holds the forces of the atoms it owns (and all scalars) */
-    const int    ka0     = c->px_on ? c->x_atom_begin : 0;
-    const int    ka1     = c->px_on ? c->x_atom_end : nT;
+    const bool   owned   = c->px_on || c->own_on;
+    const int    ka0     = c->px_on ? c->x_atom_begin : (c->own_on ? c->own_begin : 0);
+    const int    ka1     = c->px_on ? c->x_atom_end : (c->own_on ? c->own_end : nT);
     const int    nA      = ka1 - ka0;
     const int    nchunks = (sf.force && nA > 32768) ? c_copy_chunks : 1;
     const size_t f32_off = c->res_f64_bytes;
-    if (c->px_on && !c->result_on_host)
+    if (owned && !c->result_on_host)
     {
         /* fp64 block and shift forces, then the owned force range in chunks */
         CU_CHECK(c, cudaMemcpyAsync(c->h_result.ptr, c->d_result.ptr, f32_off, cudaMemcpyDeviceToHost, c->stream));
@@ -2296,10 +2528,10 @@ int fepb200_download(fepb200_ctx* c, int flags, float* f, float* fshift, double*
             if (sf.force)
             {
                 const int k1 = ka0 + (int)((long long)nA * (ch + 1) / nchunks);
-                upto         = (ch == nchunks - 1 && !c->px_on) ? f32_off + c->res_f32_bytes
+                upto         = (ch == nchunks - 1 && !owned) ? f32_off + c->res_f32_bytes
                                                                 : f32_off + sizeof(float) * 3 * (size_t)k1;
             }
-            if (c->px_on && ch == 0)
+            if (owned && ch == 0)
             {
                 done = f32_off + sizeof(float) * 3 * (size_t)ka0;
             }

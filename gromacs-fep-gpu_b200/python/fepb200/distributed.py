@@ -8,12 +8,13 @@ the ranks, coordinates and parameters replicated.  Three ways to combine the ran
       rank reads over NVLink, from whichever rank produced them, the contributions of the atoms it
       owns (forces: reduce-scatter) and all scalar inputs (all-reduce).
       fepb200_set_peer_exchange().
-  "p2p" (default): the list is split by i-entry (shard.py), every rank computes a full result block
-      for its shard and ONE kernel of libfepb200 sums all blocks over NVLink peer memory
-      (fepb200_reduce_peers; all ranks get everything).
-Measured on C5 (device time per step, B200 x N): p2p 54 / - / 53 us, fused 63 / 56 / 53 us at
-N = 2 / 4 / 8 (1 GPU: 57 us): p2p is the default; see DESIGN.md section 5.
+  "p2p" (default): the list is split by i-entry (shard.py), every rank computes the result block of its
+      shard (its epilogue visits only the atoms its shard touches) and ONE kernel of libfepb200 does the
+      force REDUCE-SCATTER over NVLink peer memory -- each rank sums the atoms it owns over all ranks'
+      blocks -- together with the all-reduce of shift forces and scalars (fepb200_reduce_scatter_peers).
+  "p2p-allreduce": the same split, every rank sums everything (fepb200_reduce_peers; round-1 default).
   "nccl": same split, two ncclAllReduce calls on zero-copy views of the result block.
+See DESIGN.md section 5 for the measurements.
 
 torch.distributed is plumbing only (process group, NCCL communicator, stream); the tensors it
 reduces are zero-copy views of the library's device result block.
@@ -50,10 +51,12 @@ class ShardedFep:
     reduction = "fused": see the module docstring; step() returns the
     forces of the atoms this rank owns (zeros elsewhere: the sum over ranks is the full force array)
     and the full scalars on every rank.
-    reduction = "p2p" (default when available): every rank publishes its result block in
+    reduction = "p2p" (default when available): every rank writes its result block into
     symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations every rank of the
-    node has mapped over NVLink), passes a device-side barrier, and libfepb200's own kernel reads
-    all blocks through the peer pointers and sums them in rank order (fepb200_reduce_peers).
+    node has mapped over NVLink), passes a device-side barrier, and libfepb200's own kernel sums, through
+    the peer pointers and in rank order, the forces of the atoms this rank owns and all scalars
+    (fepb200_reduce_scatter_peers); step() returns what "fused" returns.  "p2p-allreduce": every rank sums
+    everything (fepb200_reduce_peers).
     reduction = "nccl": two ncclAllReduce calls on zero-copy views of the result block.
     """
 
@@ -82,10 +85,10 @@ class ShardedFep:
         self.f32, self.f64 = result_tensors(self.ctx)
         if world > 1 and self.reduction != "fused":
             self.reduction = "nccl"
-            if want == "p2p":
+            if want in ("p2p", "p2p-allreduce"):
                 try:
                     self._setup_p2p(device)
-                    self.reduction = "p2p"
+                    self.reduction = want
                 except Exception as exc:  # no symmetric memory on this system: NCCL does the same job
                     self._p2p_error = repr(exc)
 
@@ -129,26 +132,35 @@ class ShardedFep:
         if self.reduction == "fused":
             self.ctx.launch(flags)  # the exchange is part of the pair kernels and the epilogue
             return
-        if self.reduction == "p2p":
+        if self.reduction in ("p2p", "p2p-allreduce"):
             k = self._step & 1
             self._step += 1
             # the epilogue writes this rank's partial result straight into its symmetric slot
             self.ctx.set_partial_result_block(self._slots[k][self.rank])
             self.ctx.launch(flags)
-            # one kernel: announce the step to all peers, wait for theirs, sum all blocks over NVLink
-            self.ctx.reduce_peers(self._slots[k], self._flags, self.rank, self._step)
+            # one kernel: announce the step to all peers, wait for theirs, sum over NVLink -- the atoms this rank
+            # owns and the scalars ("p2p"), or everything ("p2p-allreduce")
+            if self.reduction == "p2p":
+                self.ctx.reduce_scatter_peers(self._slots[k], self._flags, self.rank, self._step)
+            else:
+                self.ctx.reduce_peers(self._slots[k], self._flags, self.rank, self._step)
             return
-        self.ctx.launch(flags)
         if self.reduction == "nccl":
             import torch.distributed as dist
 
             with torch.cuda.stream(self.stream):
+                # the all-reduce works in place: the words of atoms this rank's shard does not touch (which the epilogue
+                # never writes) would keep the previous step's sums
+                self.f32.zero_()
+                self.ctx.launch(flags)
                 dist.all_reduce(self.f64, group=self.group)
                 dist.all_reduce(self.f32, group=self.group)
+            return
+        self.ctx.launch(flags)
 
     def step(self, x, shiftvec, flags: int, out: dict | None = None) -> dict:
-        """Host buffers in, reduced host buffers out ("fused": the forces of the atoms this rank owns and
-        all scalars; "p2p" / "nccl": every rank receives the full result)."""
+        """Host buffers in, reduced host buffers out ("fused" / "p2p": the forces of the atoms this rank owns and
+        all scalars; "p2p-allreduce" / "nccl": every rank receives the full result)."""
         if self.world == 1:
             # one GPU: the public call itself (fepb200_compute: the epilogue writes the result block
             # straight into pinned host memory, no device-to-host copy)

@@ -25,6 +25,13 @@ _IP = ctypes.POINTER(ctypes.c_int)
 _VP = ctypes.c_void_p
 
 
+class CListView(ctypes.Structure):
+    """struct fepb200_list_view"""
+
+    _fields_ = [("nri", ctypes.c_int), ("iinr", _IP), ("gid", _IP), ("shift", _IP), ("jindex", _IP), ("jjnr", _IP),
+                ("excl_fep", _IP)]
+
+
 class CLayout(ctypes.Structure):
     """`struct fepb200_layout`."""
 
@@ -60,6 +67,7 @@ SYMBOLS = {
     "fepb200_set_atoms": (ctypes.c_int, [_VP, ctypes.c_int, _FP, _FP, _IP, _IP]),
     "fepb200_set_list": (ctypes.c_int, [_VP, ctypes.c_int, _IP, _IP, _IP, _IP, _IP, _IP, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int]),
+    "fepb200_set_lists": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _IP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "fepb200_get_list": (ctypes.c_int, [_VP, _IP, _IP, _IP, _IP, _IP, _IP, _IP]),
     "fepb200_touched_atoms": (ctypes.c_int, [_VP, _IP]),
     "fepb200_result_layout": (ctypes.c_int, [_VP, ctypes.POINTER(CLayout)]),
@@ -77,6 +85,8 @@ SYMBOLS = {
     "fepb200_publish_result": (ctypes.c_int, [_VP, _VP]),
     "fepb200_set_partial_result_block": (ctypes.c_int, [_VP, _VP]),
     "fepb200_reduce_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int,
+                                            ctypes.c_uint]),
+    "fepb200_reduce_scatter_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int,
                                             ctypes.c_uint]),
     "fepb200_exchange_bytes": (ctypes.c_size_t, [_VP, ctypes.c_int]),
     "fepb200_set_peer_exchange": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_VP), ctypes.c_size_t]),
@@ -212,6 +222,23 @@ class FepContext:
                 int(nenergrp_pairs), int(rank), int(nranks),
             )
         )  # fmt: skip
+
+    def set_lists(self, nblists, nenergrp_pairs: int = 1, rank: int = 0, nranks: int = 1, atom_map=None) -> None:
+        """The per-thread lists as the reference holds them (fepb200_set_lists): concatenated, mapped through `atom_map`
+        (list atom index -> set_atoms index) and checked on the device."""
+        views = (CListView * max(len(nblists), 1))()
+        keep = []
+        for v, nb in zip(views, nblists):
+            arrs = [np.ascontiguousarray(a, np.int32) for a in (nb.iinr, nb.gid, nb.shift, nb.jindex, nb.jjnr)]
+            excl = np.ascontiguousarray(nb.excl_fep, np.int32) if nb.excl_fep is not None else None
+            keep += arrs + [excl]
+            v.nri = int(nb.nri)
+            v.iinr, v.gid, v.shift, v.jindex, v.jjnr = [_pi(a) for a in arrs]
+            v.excl_fep = _pi(excl) if excl is not None else None
+        amap = np.ascontiguousarray(atom_map, np.int32) if atom_map is not None else None
+        self._check(self._lib.fepb200_set_lists(self._h, len(nblists), ctypes.cast(views, _VP),
+                                                _pi(amap) if amap is not None else None, int(amap.shape[0]) if amap is not None else 0,
+                                                int(nenergrp_pairs), int(rank), int(nranks)))
 
     def set_lambdas(self, lambda_, all_lambda_coul=(), all_lambda_vdw=()) -> None:
         lam = _f32(lambda_)
@@ -364,6 +391,14 @@ class FepContext:
         arr = (_VP * len(peer_blocks))(*[_VP(p) for p in peer_blocks])
         flg = (_VP * len(peer_flags))(*[_VP(p) for p in peer_flags]) if peer_flags else None
         self._check(self._lib.fepb200_reduce_peers(self._h, len(peer_blocks), arr, flg, int(rank), int(seq) & 0xFFFFFFFF))
+
+    def reduce_scatter_peers(self, peer_blocks: list[int], peer_flags: list[int] | None = None, rank: int = 0,
+                             seq: int = 0) -> None:
+        """Force reduce-scatter + all-reduce of the scalars over peer memory: afterwards this context holds the forces of
+        the atoms it owns (peer_ranges()) and all scalars."""
+        arr = (_VP * len(peer_blocks))(*[_VP(p) for p in peer_blocks])
+        flg = (_VP * len(peer_flags))(*[_VP(p) for p in peer_flags]) if peer_flags else None
+        self._check(self._lib.fepb200_reduce_scatter_peers(self._h, len(peer_blocks), arr, flg, int(rank), int(seq) & 0xFFFFFFFF))
 
     # ---- fused peer exchange (pair kernels scatter over NVLink, every rank sums its atoms) ----
     def exchange_bytes(self, nranks: int) -> int:

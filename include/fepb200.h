@@ -170,6 +170,29 @@ int fepb200_set_atoms(fepb200_ctx* ctx, int natoms, const float* chargeA, const 
 int fepb200_set_list(fepb200_ctx* ctx, int nri, const int* iinr, const int* gid, const int* shift,
                      const int* jindex, const int* jjnr, const int* excl_fep, int nenergrp_pairs,
                      int rank, int nranks);
+/* The same from the lists as the reference holds them: one t_nblist per OpenMP thread and locality
+ * (nbnxm/pairlistset.h fepLists()), optionally in another index space than fepb200_set_atoms().  Replaces what the
+ * fork does on the HOST before its GPU FEP kernels can run -- combine_fep_lists() (nbnxm/pairlist.cpp:2867-2961:
+ * element-wise concatenation of the per-thread lists) and the index remap loops of gpu_init_feppairlist()
+ * (nbnxm_gpu_data_mgmt.cpp:763-787: local atom index -> nbat index through the inverse of nbat->cell) -- by
+ * n_lists bulk copies straight into the concatenated device arrays and three small kernels (jindex offsets,
+ * remap, range check).  The list the context holds afterwards (fepb200_get_list) is the concatenation in list
+ * order, in the index space of fepb200_set_atoms().
+ *   lists[l]   as in fepb200_set_list(); excl_fep must be given for all lists or for none
+ *   atom_map   NULL, or int[n_map]: atom index used by the lists -> atom index of fepb200_set_atoms()
+ *              (the GPU route passes the fork's atomIndicesInv here) */
+typedef struct fepb200_list_view
+{
+    int        nri;
+    const int* iinr;
+    const int* gid;
+    const int* shift;
+    const int* jindex; /* [nri + 1], jindex[0] == 0 */
+    const int* jjnr;
+    const int* excl_fep;
+} fepb200_list_view;
+int fepb200_set_lists(fepb200_ctx* ctx, int n_lists, const fepb200_list_view* lists, const int* atom_map, int n_map,
+                      int nenergrp_pairs, int rank, int nranks);
 /* Round trip of the shard this context holds, bit-exact (tests).
  * Call with NULL arrays to query sizes through fepb200_result_layout(). */
 int fepb200_get_list(const fepb200_ctx* ctx, int* first_entry, int* iinr, int* gid, int* shift,
@@ -264,6 +287,16 @@ int    fepb200_publish_result(fepb200_ctx* ctx, void* d_block);
 int    fepb200_set_partial_result_block(fepb200_ctx* ctx, void* d_block);
 int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags,
                             int rank, unsigned int seq);
+/* The same with the split BASELINE.json's north_star names: a force REDUCE-SCATTER plus an all-reduce of what is small.
+ * Afterwards this context's result block holds the forces of the atoms it OWNS -- the compact atoms
+ * [atom_begin, atom_end) of fepb200_peer_ranges(): equal ranges of the full list's touched atoms, starting on
+ * multiples of four -- summed over all ranks (zeros elsewhere: the sum over ranks of what fepb200_download() /
+ * fepb200_add_forces_device() deliver is the full force array), and the shift forces, Vc/Vv, dV/dlambda and foreign
+ * terms summed over all ranks on every rank.  (N-1)/N of ONE block crosses NVLink per rank instead of N-1 blocks, and
+ * only a rank's own atoms cross PCIe afterwards.  Same arguments, barrier and slot discipline as fepb200_reduce_peers();
+ * replaces ThreadedForceBuffer::reduce (mdtypes/threaded_force_buffer.cpp:320-402) across GPUs. */
+int    fepb200_reduce_scatter_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags,
+                                    int rank, unsigned int seq);
 
 /* ---- multi-GPU, fused: no separate collective, every rank sums its own atoms ------------------
  * The force reduce-scatter and the scalar all-reduce of SURVEY 8e inside the epilogue kernel

@@ -47,12 +47,13 @@ struct LocalityState
     fepb200_ctx*     ctx = nullptr;
     void*            stream = nullptr;
     std::vector<int> iinr, shift, jindex, jjnr, excl, gid;
+    std::vector<int> atomMap; /* index used by the list -> nbat index (empty: the list is in nbat indices already) */
     /* versions of the list / of the shared state this context holds (0 = nothing yet) */
     long   listVersion = 0, listApplied = 0, atomsApplied = 0, lambdasApplied = 0;
     bool   haveParams = false, lambdasSent = false;
     fepb200_params lastParams{};
-    long   steps = 0;
-    double seconds = 0;
+    long   steps = 0, handovers = 0;
+    double seconds = 0, secondsHandover = 0;
 };
 
 struct State
@@ -156,8 +157,10 @@ inline void setShiftVectors(const void* nb, const float* shiftVec)
     }
 }
 
+/* atomMap (may be NULL): the list's atom index -> nbat index, the fork's atomIndicesInv; the library applies it on the
+ * device (fepb200_set_lists) instead of the host loops of gpu_init_feppairlist (nbnxm_gpu_data_mgmt.cpp:763-787) */
 inline void setList(const void* nb, int iloc, int nri, const int* iinr, const int* shift, const int* jindex, int nrj,
-                    const int* jjnr, const int* excl)
+                    const int* jjnr, const int* excl, const int* atomMap = nullptr, int nMap = 0)
 {
     if (!enabled())
     {
@@ -170,6 +173,7 @@ inline void setList(const void* nb, int iloc, int nri, const int* iinr, const in
     l.jjnr.assign(jjnr, jjnr + nrj);
     l.excl.assign(excl, excl + nrj);
     l.gid.assign(nri, 0); /* the GPU route has one energy group */
+    l.atomMap.assign(atomMap, atomMap + (atomMap ? nMap : 0));
     l.listVersion++;
 }
 
@@ -241,14 +245,24 @@ inline void step(const void* nb, int iloc, int device, void* stream, bool twoStr
         l.lambdasApplied = s.lambdasVersion;
         l.lambdasSent    = true;
     }
+    bool handover = newAtoms;
     if (newAtoms || l.listApplied != l.listVersion)
     {
+        fepb200_list_view v;
+        v.nri      = static_cast<int>(l.iinr.size());
+        v.iinr     = l.iinr.data();
+        v.gid      = l.gid.data();
+        v.shift    = l.shift.data();
+        v.jindex   = l.jindex.data();
+        v.jjnr     = l.jjnr.data();
+        v.excl_fep = l.excl.data();
         check(a, l.ctx,
-              a.set_list(l.ctx, static_cast<int>(l.iinr.size()), l.iinr.data(), l.gid.data(), l.shift.data(), l.jindex.data(),
-                         l.jjnr.data(), l.excl.data(), 1, 0, 1),
-              "set_list");
+              a.set_lists(l.ctx, 1, &v, l.atomMap.empty() ? nullptr : l.atomMap.data(), static_cast<int>(l.atomMap.size()), 1, 0, 1),
+              "set_lists");
         l.listApplied = l.listVersion;
+        handover      = true;
     }
+    const double tHandover = fepb200shim::now();
 
     int flags = FEPB200_DO_SR | FEPB200_DO_FORCE; /* the fork's FEP kernels always compute forces */
     flags |= computeEnergy ? FEPB200_DO_POTENTIAL : 0;
@@ -268,11 +282,18 @@ inline void step(const void* nb, int iloc, int device, void* stream, bool twoStr
                                   computeVirial ? fShift : nullptr),
           "export_scalars_device");
     l.steps++;
-    l.seconds += fepb200shim::now() - t0;
+    l.seconds += fepb200shim::now() - tHandover;
+    if (handover)
+    {
+        l.handovers++;
+        l.secondsHandover += tHandover - t0;
+    }
     if (l.steps == 20 || l.steps == 1000)
     {
-        std::fprintf(stderr, "fepb200 GPU route: locality %d, %ld steps, %.1f us of host time per step to enqueue\n", iloc,
-                     l.steps, 1e6 * l.seconds / l.steps);
+        std::fprintf(stderr,
+                     "fepb200 GPU route: locality %d, %ld steps, %.1f us of host time per step to enqueue (gather, kernels, "
+                     "force and scalar hand-off); %ld hand-overs of atoms / list, %.1f us each\n",
+                     iloc, l.steps, 1e6 * l.seconds / l.steps, l.handovers, l.handovers ? 1e6 * l.secondsHandover / l.handovers : 0.0);
     }
 }
 

@@ -84,32 +84,31 @@ inline void dispatch(const PairlistSets&                              pairlistSe
     const int numGroupPairs = enerd->grpp.nener;
     if (search)
     {
-        /* the FEP pair lists of all localities and threads, concatenated (what the fork's
-         * combine_fep_lists does for its GPU path, pairlist.cpp:2867) */
-        std::vector<int> iinr, gid, shift, jindex(1, 0), jjnr, excl;
-        const int        numLocalities = (pairlistSets.params().haveMultipleDomains ? 2 : 1);
+        /* the FEP pair lists of all localities and threads as they are: the library concatenates them on the device
+         * (what the fork's combine_fep_lists does element by element on the host for its GPU path, pairlist.cpp:2867) */
+        std::vector<fepb200_list_view> views;
+        const int                      numLocalities = (pairlistSets.params().haveMultipleDomains ? 2 : 1);
         for (int l = 0; l < numLocalities; l++)
         {
             const auto lists = pairlistSets.pairlistSet(static_cast<gmx::InteractionLocality>(l)).fepLists();
             for (const auto& nl : lists)
             {
-                for (int n = 0; n < nl->nri; n++)
+                if (nl->nri == 0)
                 {
-                    iinr.push_back(nl->iinr[n]);
-                    gid.push_back(nl->gid[n]);
-                    shift.push_back(nl->shift[n]);
-                    for (int k = nl->jindex[n]; k < nl->jindex[n + 1]; k++)
-                    {
-                        jjnr.push_back(nl->jjnr[k]);
-                        excl.push_back(nl->excl_fep[k]);
-                    }
-                    jindex.push_back(static_cast<int>(jjnr.size()));
+                    continue;
                 }
+                fepb200_list_view v;
+                v.nri      = nl->nri;
+                v.iinr     = nl->iinr.data();
+                v.gid      = nl->gid.data();
+                v.shift    = nl->shift.data();
+                v.jindex   = nl->jindex.data();
+                v.jjnr     = nl->jjnr.data();
+                v.excl_fep = nl->excl_fep.data();
+                views.push_back(v);
             }
         }
-        check(a.set_list(a.ctx, static_cast<int>(iinr.size()), iinr.data(), gid.data(), shift.data(), jindex.data(),
-                         jjnr.data(), excl.data(), numGroupPairs, 0, 1),
-              "set_list");
+        check(a.set_lists(a.ctx, static_cast<int>(views.size()), views.data(), nullptr, 0, numGroupPairs, 0, 1), "set_lists");
         a.searchCalls++;
     }
     const double t1 = now();

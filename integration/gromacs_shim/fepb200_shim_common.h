@@ -33,6 +33,7 @@ struct Api
     decltype(&fepb200_set_nbfp)    set_nbfp    = nullptr;
     decltype(&fepb200_set_atoms)   set_atoms   = nullptr;
     decltype(&fepb200_set_list)    set_list    = nullptr;
+    decltype(&fepb200_set_lists)   set_lists   = nullptr;
     decltype(&fepb200_set_lambdas) set_lambdas = nullptr;
     decltype(&fepb200_compute)     compute     = nullptr;
     /* device-resident entry points (GPU route, fepb200_gpu_shim.h) */
@@ -129,6 +130,7 @@ inline void loadSymbols()
     FEPB200_SYM(set_nbfp);
     FEPB200_SYM(set_atoms);
     FEPB200_SYM(set_list);
+    FEPB200_SYM(set_lists);
     FEPB200_SYM(set_lambdas);
     FEPB200_SYM(compute);
     FEPB200_SYM(set_stream);
@@ -142,7 +144,7 @@ inline void loadSymbols()
     FEPB200_SYM(pairs14_set_pairs);
     FEPB200_SYM(pairs14_compute);
 #undef FEPB200_SYM
-    if (!a.create || !a.compute || !a.set_list)
+    if (!a.create || !a.compute || !a.set_list || !a.set_lists)
     {
         gmx_fatal(FARGS, "libfepb200.so does not export the expected symbols");
     }

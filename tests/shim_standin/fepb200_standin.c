@@ -204,6 +204,72 @@ int fepb200_set_list(fepb200_ctx* c, int nri, const int* iinr, const int* gid, c
     return FEPB200_OK;
 }
 
+/* the per-thread lists of the reference, concatenated (and mapped) on the host: the stand-in has no device */
+int fepb200_set_lists(fepb200_ctx* c, int n_lists, const fepb200_list_view* lists, const int* atom_map, int n_map,
+                      int nenergrp_pairs, int rank, int nranks)
+{
+    long nri = 0, nrj = 0;
+    for (int l = 0; l < n_lists; l++)
+    {
+        nri += lists[l].nri;
+        nrj += lists[l].nri > 0 ? lists[l].jindex[lists[l].nri] : 0;
+    }
+    int* iinr   = (int*)malloc(sizeof(int) * (nri ? nri : 1));
+    int* gid    = (int*)malloc(sizeof(int) * (nri ? nri : 1));
+    int* shift  = (int*)malloc(sizeof(int) * (nri ? nri : 1));
+    int* jindex = (int*)malloc(sizeof(int) * (nri + 1));
+    int* jjnr   = (int*)malloc(sizeof(int) * (nrj ? nrj : 1));
+    int* excl   = (int*)malloc(sizeof(int) * (nrj ? nrj : 1));
+    long e = 0, k = 0;
+    int  bad = 0;
+    jindex[0] = 0;
+    for (int l = 0; l < n_lists; l++)
+    {
+        const fepb200_list_view* v = &lists[l];
+        for (int n = 0; n < v->nri; n++, e++)
+        {
+            int a = v->iinr[n];
+            if (atom_map)
+            {
+                a = (a >= 0 && a < n_map) ? atom_map[a] : -1;
+            }
+            bad += a < 0 || a >= c->natoms;
+            iinr[e]  = a;
+            gid[e]   = v->gid[n];
+            shift[e] = v->shift[n];
+            for (int j = v->jindex[n]; j < v->jindex[n + 1]; j++, k++)
+            {
+                int b = v->jjnr[j];
+                if (atom_map)
+                {
+                    b = (b >= 0 && b < n_map) ? atom_map[b] : -1;
+                }
+                bad += b < 0 || b >= c->natoms;
+                jjnr[k] = b;
+                excl[k] = v->excl_fep ? v->excl_fep[j] : 1;
+            }
+            jindex[e + 1] = (int)k;
+        }
+    }
+    int rc;
+    if (bad)
+    {
+        snprintf(c->err, sizeof(c->err), "%d atom indices of the lists are outside [0,%d)", bad, c->natoms);
+        rc = FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    else
+    {
+        rc = fepb200_set_list(c, (int)nri, iinr, gid, shift, jindex, jjnr, excl, nenergrp_pairs, rank, nranks);
+    }
+    free(iinr);
+    free(gid);
+    free(shift);
+    free(jindex);
+    free(jjnr);
+    free(excl);
+    return rc;
+}
+
 int fepb200_set_lambdas(fepb200_ctx* c, const float* lambda, int n_foreign, const float* all_lambda_coul,
                         const float* all_lambda_vdw)
 {

@@ -380,6 +380,50 @@ def test_empty_and_ragged_lists(ctx):
     _assert_lists_equal(back, prob.nblist)
 
 
+def test_per_thread_lists_are_concatenated_and_mapped_on_the_device(ctx):
+    """fepb200_set_lists: the reference's per-thread t_nblists, in another index space (the GPU route's nbat order), give
+    the list -- and bit for bit the results -- of the one concatenated, remapped list (what
+    combine_fep_lists + the remap loops of gpu_init_feppairlist do on the host)."""
+    from fepb200.lib import FepError
+    from fepb200.problem import FepList
+
+    prob = make_system(SMALL["C4"])
+    nb = prob.nblist
+    ctx.set_problem(prob)
+    want = ctx.compute(prob.x, prob.shiftvec, ALL)
+    rng = np.random.default_rng(5)
+    atom_map = rng.permutation(prob.natoms).astype(np.int32)  # list index -> atom
+    inv = np.empty_like(atom_map)
+    inv[atom_map] = np.arange(prob.natoms, dtype=np.int32)
+    cuts = [0, nb.nri // 3, nb.nri // 3, (2 * nb.nri) // 3, nb.nri]  # four lists, the second one empty
+    parts = []
+    for a, b in zip(cuts, cuts[1:]):
+        sl = nb.slice_entries(a, b)
+        parts.append(FepList(inv[sl.iinr], sl.gid, sl.shift, sl.jindex, inv[sl.jjnr], sl.excl_fep))
+    ctx.set_lists(parts, prob.nenergrp_pairs, atom_map=atom_map)
+    first, back = ctx.get_list()
+    assert first == 0
+    _assert_lists_equal(back, nb)
+    got = ctx.compute(prob.x, prob.shiftvec, ALL)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    # shards of the concatenation are cut like shards of the single list
+    ctx.set_lists(parts, prob.nenergrp_pairs, rank=1, nranks=3, atom_map=atom_map)
+    first_s, back_s = ctx.get_list()
+    ctx.set_list(nb, prob.nenergrp_pairs, rank=1, nranks=3)
+    first_1, back_1 = ctx.get_list()
+    assert first_s == first_1
+    _assert_lists_equal(back_s, back_1)
+    # an index the map does not cover, and a mapped index beyond the atoms, are refused
+    bad = FepList(parts[0].iinr, parts[0].gid, parts[0].shift, parts[0].jindex, parts[0].jjnr.copy(), parts[0].excl_fep)
+    bad.jjnr[3] = prob.natoms + 7
+    with pytest.raises(FepError, match="outside"):
+        ctx.set_lists([bad], prob.nenergrp_pairs, atom_map=atom_map)
+    with pytest.raises(FepError, match="outside"):
+        ctx.set_lists(parts, prob.nenergrp_pairs, atom_map=atom_map + 1)
+    ctx.set_problem(prob)  # leave the shared context usable
+
+
 def test_outputs_accumulate_like_the_reference_and_clear_flag(ctx):
     prm = P.make_params(coulombtype="rf", softcore="beutler", sc_coul=True)
     prob = random_problem(11, prm, natoms=200, nri=50, n_foreign=2, frac_overlap=0.0)

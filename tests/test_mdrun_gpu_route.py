@@ -26,6 +26,8 @@ import test_mdrun_dropin as T
 pytestmark = pytest.mark.gpu
 
 GMX_CUDA = os.path.join(T.ROOT, "integration", "_gmx_cuda", "bin", "gmx")
+# the "GPU timings" table of md.log (timing/wallcycle.cpp:1009-1060) is only written with GPU timing on
+TIMING = {"GMX_ENABLE_GPU_TIMING": "1"}
 
 
 def _gpu_fep_row(workdir):
@@ -49,13 +51,13 @@ def test_library_inside_the_forks_gpu_route(system, tmp_path):
         cpu = T._run(tpr, str(tmp_path / "a"), False, gmx=GMX_CUDA, nb="gpu", fep="cpu")
     except AssertionError as exc:  # the fork's GPU build itself does not run on this box: nothing of ours was involved yet
         pytest.skip("the fork's CUDA build does not run here: " + str(exc)[-400:])
-    ours = T._run(tpr, str(tmp_path / "b"), True, gmx=GMX_CUDA, nb="gpu", fep="gpu")
+    ours = T._run(tpr, str(tmp_path / "b"), True, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=TIMING)
     assert "GPU route" in ours[0], "the hook in gpu_launch_kernel was not reached"
     note = [f"{system}: -nb gpu -fep gpu through libfepb200; max |dE| vs the reference CPU FEP kernel {_max_dev(ours, cpu)}; "
             f"GPU timing row (our kernels inside the fork's fep_k timer): {_gpu_fep_row(str(tmp_path / 'b'))}"]
     note += [ln for ln in ours[0].splitlines() if ln.startswith("fepb200 GPU route:")]
     try:  # (c): the fork's own kernels on the same route, for the record
-        fork = T._run(tpr, str(tmp_path / "c"), False, gmx=GMX_CUDA, nb="gpu", fep="gpu")
+        fork = T._run(tpr, str(tmp_path / "c"), False, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=TIMING)
         note.append(f"{system}: fork's own FEP kernels: max |dE| vs its CPU route {_max_dev(fork, cpu)}; "
                     f"GPU timing row: {_gpu_fep_row(str(tmp_path / 'c'))}")
     except BaseException as exc:  # noqa: BLE001

@@ -46,12 +46,13 @@ def _worker(rank, world, port, root, result_file, reduction):
     out2 = sh.step(prob.x, prob.shiftvec, flags | P.CLEAR_OUTPUTS, out={k: v.copy() for k, v in out.items()})
     want = oracle.run_best(prob, flags)
     f_full = out["f"]
-    if used == "fused":
+    if used in ("fused", "p2p"):
         # every rank returns the forces of the atoms it owns: the sum over ranks is the force array
         p0, p1, a0, a1 = sh.ctx.peer_ranges()
         owned = np.zeros(prob.natoms, bool)
         owned[sh.ctx.touched_atoms()[a0:a1]] = True
-        split_ok = 0 < p1 - p0 < prob.nblist.nrj and 0 < a1 - a0 and not np.any(out["f"][~owned])
+        split_ok = 0 < a1 - a0 < len(sh.ctx.touched_atoms()) and not np.any(out["f"][~owned])
+        split_ok = split_ok and (0 < p1 - p0 < prob.nblist.nrj if used == "fused" else 0 < int(lay.nri) < prob.nblist.nri)
         t = torch.from_numpy(out["f"].copy()).cuda()
         dist.all_reduce(t)
         f_full = t.cpu().numpy()
@@ -90,7 +91,7 @@ def _worker(rank, world, port, root, result_file, reduction):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("reduction", ["fused", "p2p", "nccl"])
+@pytest.mark.parametrize("reduction", ["fused", "p2p", "p2p-allreduce", "nccl"])
 def test_two_ranks_match_oracle(tmp_path, reduction):
     import torch
     import torch.multiprocessing as mp
@@ -104,6 +105,6 @@ def test_two_ranks_match_oracle(tmp_path, reduction):
     assert got.startswith("ok"), got
     if reduction == "nccl":
         assert got == "ok nccl"
-    if reduction == "fused":
-        assert got == "ok fused"  # symmetric memory is available on an NVLink box: no silent downgrade
+    if reduction in ("fused", "p2p", "p2p-allreduce"):
+        assert got == "ok " + reduction  # symmetric memory is available on an NVLink box: no silent downgrade
     print(got)
