@@ -2906,6 +2906,94 @@ int fepb200_pairs14_set_pairs(fepb200_pairs14* h, int natoms, const float* charg
     return FEPB200_OK;
 }
 
+/* per-pair copies of the coordinates; the minimum-image shift goes onto the i copy (pbc_dx_aiuc, pbcutil/pbc.cpp:825-851) */
+static void stage_pairs14(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type)
+{
+    for (int p = 0; p < h->npairs; p++)
+    {
+        const float* xi = x + 3 * (size_t)h->ai[p];
+        const float* xj = x + 3 * (size_t)h->aj[p];
+        int          is[3] = { 0, 0, 0 };
+        for (int d = 0; d < 3; d++)
+        {
+            float sh = 0.0f;
+            if (pbc_type == 1 || (pbc_type == 2 && d < 2))
+            {
+                const float dx = xi[d] - xj[d], hbox = 0.5f * box_diag[d];
+                if (dx > hbox)
+                {
+                    sh = -box_diag[d];
+                    is[d]--;
+                }
+                else if (dx <= -hbox)
+                {
+                    sh = box_diag[d];
+                    is[d]++;
+                }
+            }
+            h->xp[6 * (size_t)p + d]     = xi[d] + sh;
+            h->xp[6 * (size_t)p + 3 + d] = xj[d];
+        }
+        h->shift_idx[p] = 5 * (3 * (is[2] + 1) + (is[1] + 1)) + (is[0] + 2);
+    }
+}
+
+/* All foreign lambda points of the perturbed 1-4 pairs in ONE evaluation: the reference calls the pair code once per
+ * point (calc_listed_lambda inside the loop of ListedForces::calculate, listed_forces/listed_forces.cpp:760-800); here
+ * the points go through the foreign-lambda machinery of the non-bonded kernels (one load of every pair, the
+ * lambda-independent part evaluated once).  energy[i] = Coulomb-14 + LJ-14 energy at point i summed over the
+ * energy-group pairs (what sum_epot makes of them), dvdl[2 i + {0, 1}] = dV/dlambda coul / vdw at point i (energy-only
+ * semantics, like the reference's foreign evaluations).  Stored, not accumulated. */
+int fepb200_pairs14_compute_foreign(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, int n_points,
+                                    const float* lambda_coul, const float* lambda_vdw, double* energy, double* dvdl)
+{
+    if (!h || !x || n_points < 1 || !lambda_coul || !lambda_vdw || !energy || !dvdl || (pbc_type != 0 && !box_diag)
+        || pbc_type < 0 || pbc_type > 2)
+    {
+        return fail14(h, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_pairs14_compute_foreign: bad arguments");
+    }
+    if (!h->have_pairs)
+    {
+        return fail14(h, FEPB200_ERR_STATE, "fepb200_pairs14_set_pairs() has not been called");
+    }
+    for (int i = 0; i < n_points; i++)
+    {
+        energy[i] = dvdl[2 * i] = dvdl[2 * i + 1] = 0.0;
+    }
+    if (h->npairs == 0)
+    {
+        return FEPB200_OK;
+    }
+    /* the points as the foreign list of the private context (its "current lambda" = the first point; the current-lambda
+     * pass is not run) */
+    float lam[FEPB200_NUM_LAMBDA_COMPONENTS] = {};
+    lam[FEPB200_LAMBDA_COUL]                 = lambda_coul[0];
+    lam[FEPB200_LAMBDA_VDW]                  = lambda_vdw[0];
+    int rc = inner14(h, fepb200_set_lambdas(h->ctx, lam, n_points, lambda_coul, lambda_vdw));
+    h->have_lambda = false; /* fepb200_pairs14_compute() must set its own lambda again */
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    stage_pairs14(h, x, box_diag, pbc_type);
+    std::vector<double> fe((size_t)n_points + 1), fd(2 * ((size_t)n_points + 1));
+    double              dv[2] = { 0.0, 0.0 };
+    rc = inner14(h, fepb200_compute(h->ctx, h->xp.data(), h->zero_shift.data(), FEPB200_DO_FOREIGNLAMBDA | FEPB200_CLEAR_OUTPUTS,
+                                    nullptr, nullptr, nullptr, nullptr, dv, fe.data(), fd.data()));
+    if (rc != FEPB200_OK)
+    {
+        return rc;
+    }
+    /* point 0 of the context repeats its current lambda (freeenergydispatch.cpp:247-253); the caller's points follow */
+    for (int i = 0; i < n_points; i++)
+    {
+        energy[i]       = fe[i + 1];
+        dvdl[2 * i]     = fd[2 * (i + 1)];
+        dvdl[2 * i + 1] = fd[2 * (i + 1) + 1];
+    }
+    return FEPB200_OK;
+}
+
 int fepb200_pairs14_compute(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, const float* lambda,
                             int flags, float* f, float* fshift, double* Vc14, double* Vv14, double* dvdl)
 {
@@ -2937,34 +3025,7 @@ int fepb200_pairs14_compute(fepb200_pairs14* h, const float* x, const float* box
     {
         return FEPB200_OK;
     }
-    /* per-pair copies of the coordinates; the minimum-image shift goes onto the i copy */
-    for (int p = 0; p < h->npairs; p++)
-    {
-        const float* xi = x + 3 * (size_t)h->ai[p];
-        const float* xj = x + 3 * (size_t)h->aj[p];
-        int          is[3] = { 0, 0, 0 };
-        for (int d = 0; d < 3; d++)
-        {
-            float sh = 0.0f;
-            if (pbc_type == 1 || (pbc_type == 2 && d < 2))
-            {
-                const float dx = xi[d] - xj[d], hbox = 0.5f * box_diag[d];
-                if (dx > hbox)
-                {
-                    sh = -box_diag[d];
-                    is[d]--;
-                }
-                else if (dx <= -hbox)
-                {
-                    sh = box_diag[d];
-                    is[d]++;
-                }
-            }
-            h->xp[6 * (size_t)p + d]     = xi[d] + sh;
-            h->xp[6 * (size_t)p + 3 + d] = xj[d];
-        }
-        h->shift_idx[p] = 5 * (3 * (is[2] + 1) + (is[1] + 1)) + (is[0] + 2);
-    }
+    stage_pairs14(h, x, box_diag, pbc_type);
     const int inner_flags = (flags & (FEPB200_DO_FORCE | FEPB200_DO_POTENTIAL)) | FEPB200_CLEAR_OUTPUTS;
     double    dv[2]       = { 0.0, 0.0 };
     rc = inner14(h, fepb200_compute(h->ctx, h->xp.data(), h->zero_shift.data(), inner_flags, h->fp.data(), nullptr,

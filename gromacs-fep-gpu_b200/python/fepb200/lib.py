@@ -104,6 +104,7 @@ SYMBOLS = {
     "fepb200_pairs14_set_pairs": (ctypes.c_int, [_VP, ctypes.c_int, _FP, _FP, ctypes.c_int, _IP, ctypes.c_int, _FP, _FP,
                                                  _FP, _FP, _IP, ctypes.c_int]),
     "fepb200_pairs14_compute": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, ctypes.c_int, _FP, _FP, _DP, _DP, _DP]),
+    "fepb200_pairs14_compute_foreign": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, ctypes.c_int, _FP, _FP, _DP, _DP]),
 }  # fmt: skip
 
 _lib = None

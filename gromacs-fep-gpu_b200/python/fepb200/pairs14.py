@@ -113,3 +113,17 @@ class Pairs14Context:
                                                       fp(out["f"]), fp(out["fshift"]), dp(out["Vc"]), dp(out["Vv"]),
                                                       dp(out["dvdl"])))
         return out
+
+    def compute_foreign(self, p: Pairs14Problem, lambda_coul, lambda_vdw) -> tuple[np.ndarray, np.ndarray]:
+        """(energy[n], dvdl[n, 2]) of the energy-only evaluations at all the given lambda points, one library call
+        (fepb200_pairs14_compute_foreign)."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
+        fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))  # noqa: E731
+        dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+        lc, lv = f32(lambda_coul), f32(lambda_vdw)
+        assert lc.shape == lv.shape and lc.ndim == 1
+        e, d = np.zeros(lc.shape[0]), np.zeros((lc.shape[0], 2))
+        x, box = f32(p.x), f32(p.box_diag)
+        self._check(self._lib.fepb200_pairs14_compute_foreign(self._h, fp(x), fp(box), int(p.pbc_type), int(lc.shape[0]), fp(lc),
+                                                              fp(lv), dp(e), dp(d)))
+        return e, d

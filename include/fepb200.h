@@ -381,6 +381,13 @@ int fepb200_pairs14_set_pairs(fepb200_pairs14* h, int natoms, const float* charg
  * Vc14/Vv14[G] (Coulomb-14 / LJ-14 energy terms), dvdl[2] (coul, vdw). */
 int fepb200_pairs14_compute(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, const float* lambda,
                             int flags, float* f, float* fshift, double* Vc14, double* Vv14, double* dvdl);
+/* The energy-only evaluations at ALL foreign lambda points in one call: replaces the n_points calls of the pair code that
+ * the reference makes from calc_listed_lambda (listed_forces/listed_forces.cpp:554-640, called per point at :760-800).
+ * lambda_coul / lambda_vdw: float[n_points] = fepvals->all_lambda[Coul | Vdw]; energy: double[n_points], Coulomb-14 +
+ * LJ-14 at each point summed over the energy-group pairs; dvdl: double[2 n_points] = {coul, vdw} per point.  Outputs are
+ * STORED.  The pairs go through the foreign-lambda machinery of the non-bonded kernels (one load of every pair). */
+int fepb200_pairs14_compute_foreign(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, int n_points,
+                                    const float* lambda_coul, const float* lambda_vdw, double* energy, double* dvdl);
 
 #ifdef __cplusplus
 }

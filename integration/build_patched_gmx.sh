@@ -19,6 +19,9 @@ done
 # ... and the hook for the perturbed 1-4 pairs (listed_forces/pairs.cpp -> fepb200_pairs14_*)
 cp /root/reference/src/gromacs/listed_forces/pairs.cpp "$SRC/src/gromacs/listed_forces/pairs.cpp"
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/pairs_fepb200.patch")
+# ... and the scope around the foreign-lambda loop of the listed forces (all points of the 1-4 pairs in one library call)
+cp /root/reference/src/gromacs/listed_forces/listed_forces.cpp "$SRC/src/gromacs/listed_forces/listed_forces.cpp"
+(cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/listed_forces_fepb200.patch")
 mkdir -p "$BUILD"
 cmake -G Ninja -S "$SRC" -B "$BUILD" -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ \
   -DCMAKE_POLICY_VERSION_MINIMUM=3.5 -DGMX_GPU=OFF -DGMX_MPI=OFF -DGMX_THREAD_MPI=ON -DGMX_OPENMP=ON \

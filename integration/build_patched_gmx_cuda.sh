@@ -16,6 +16,9 @@ cp /root/reference/src/gromacs/nbnxm/freeenergydispatch.cpp "$SRC/src/gromacs/nb
 # ... and the hook for the perturbed 1-4 pairs (listed_forces/pairs.cpp -> fepb200_pairs14_*)
 cp /root/reference/src/gromacs/listed_forces/pairs.cpp "$SRC/src/gromacs/listed_forces/pairs.cpp"
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/pairs_fepb200.patch")
+# ... and the scope around the foreign-lambda loop of the listed forces (all points of the 1-4 pairs in one library call)
+cp /root/reference/src/gromacs/listed_forces/listed_forces.cpp "$SRC/src/gromacs/listed_forces/listed_forces.cpp"
+(cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/listed_forces_fepb200.patch")
 # ... and the hooks in the fork's GPU route (mdrun -nb gpu -fep gpu + GMX_FEPB200: libfepb200 instead of k_calc_nb_fep*)
 for f in src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp src/gromacs/nbnxm/cuda/nbnxm_cuda.cu src/gromacs/mdlib/sim_util.cpp; do cp "/root/reference/$f" "$SRC/$f"; done
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/nbnxm_gpu_fepb200.patch")

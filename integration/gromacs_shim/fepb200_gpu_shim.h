@@ -288,7 +288,7 @@ inline void step(const void* nb, int iloc, int device, void* stream, bool twoStr
         l.handovers++;
         l.secondsHandover += tHandover - t0;
     }
-    if (l.steps == 20 || l.steps == 1000)
+    if (l.steps == 20 || l.steps == 600 || l.steps == 5000)
     {
         std::fprintf(stderr,
                      "fepb200 GPU route: locality %d, %ld steps, %.1f us of host time per step to enqueue (gather, kernels, "

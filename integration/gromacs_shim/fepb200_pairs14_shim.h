@@ -24,6 +24,16 @@
 #include <algorithm>
 #include <map>
 
+/* what the two files that include this header (pairs.cpp, listed_forces.cpp) do not both include themselves */
+#include "gromacs/math/vec.h"
+#include "gromacs/mdtypes/forcerec.h"
+#include "gromacs/mdtypes/group.h"
+#include "gromacs/mdtypes/interaction_const.h"
+#include "gromacs/mdtypes/md_enums.h"
+#include "gromacs/pbcutil/pbc.h"
+#include "gromacs/topology/idef.h"
+#include "gromacs/utility/arrayref.h"
+
 #include "fepb200_shim_common.h"
 
 namespace fepb200pairs
@@ -41,13 +51,18 @@ struct Handle
     std::vector<int>   gids;     /* the energy-group-pair indices of those pairs, unique */
     int                ngrp = 1; /* largest of them + 1: the size of the library's energy arrays */
     std::vector<float> fTmp;     /* rvec[natoms], zero outside a call */
-    long               calls = 0, uploads = 0;
+    long               calls = 0, uploads = 0, foreignCalls = 0, foreignLookups = 0;
+    /* all foreign lambda points of the current dH/dlambda step, evaluated in one library call (ForeignScope) */
+    long                foreignGeneration = -1;
+    std::vector<double> foreignE, foreignDvdl;
     ~Handle()
     {
         if (calls > 0)
         {
-            std::fprintf(stderr, "fepb200 pairs14 shim: %ld calls, %ld pair-list uploads, %zu perturbed 1-4 pairs in the last list\n",
-                         calls, uploads, key.size() / 3);
+            std::fprintf(stderr,
+                         "fepb200 pairs14 shim: %ld calls, %ld pair-list uploads, %zu perturbed 1-4 pairs in the last list; "
+                         "foreign lambda: %ld library calls served %ld evaluations\n",
+                         calls, uploads, key.size() / 3, foreignCalls, foreignLookups);
         }
     }
 };
@@ -82,6 +97,48 @@ inline bool enabled()
     static const bool on = fepb200shim::enabled() && std::getenv("GMX_FEPB200_NO_PAIRS14") == nullptr;
     return on;
 }
+
+/* The foreign-lambda evaluations of a dH/dlambda step (the loop over lambda points in ListedForces::calculate,
+ * listed_forces.cpp:760-800, each calling calc_listed_lambda -> do_pairs_general for the perturbed 1-4 pairs): the hook of
+ * listed_forces_fepb200.patch opens a scope around that loop and names all points; the first evaluation inside it asks
+ * the library for ALL points at once (fepb200_pairs14_compute_foreign: one load of every pair instead of one call per
+ * point), the others are served from that result.  One scope per rank at a time (the loop is serial). */
+struct ForeignState
+{
+    bool               active = false;
+    long               generation = 0;
+    int                served = 0; /* evaluations of the perturbed 1-4 pairs seen in this scope: the next one is point `served` */
+    std::vector<float> lamCoul, lamVdw;
+};
+inline ForeignState& foreignState()
+{
+    static thread_local ForeignState st;
+    return st;
+}
+struct ForeignScope
+{
+    /* lambda: the current lambdas (point 0); allCoul / allVdw[numForeign]: fepvals->all_lambda[Coul | Vdw] */
+    template<typename Lambda, typename All>
+    ForeignScope(const Lambda& lambda, const All& allCoul, const All& allVdw, int numForeign)
+    {
+        if (!enabled() || std::getenv("GMX_FEPB200_PAIRS14_PER_POINT") != nullptr)
+        {
+            return;
+        }
+        ForeignState& st = foreignState();
+        st.active = true;
+        st.generation++;
+        st.served = 0;
+        st.lamCoul.assign(1, static_cast<float>(lambda[static_cast<int>(FreeEnergyPerturbationCouplingType::Coul)]));
+        st.lamVdw.assign(1, static_cast<float>(lambda[static_cast<int>(FreeEnergyPerturbationCouplingType::Vdw)]));
+        for (int i = 0; i < numForeign; i++)
+        {
+            st.lamCoul.push_back(static_cast<float>(allCoul[i]));
+            st.lamVdw.push_back(static_cast<float>(allVdw[i]));
+        }
+    }
+    ~ForeignScope() { foreignState().active = false; }
+};
 
 /* Returns true when the perturbed pairs of this chunk were computed by the library (the caller's loop then skips
  * them), false when they are left to the reference code. */
@@ -233,6 +290,36 @@ inline bool dispatch(bool                                computeVirial,
     for (int i = 0; i < FEPB200_NUM_LAMBDA_COMPONENTS; i++)
     {
         lam[i] = lambda[i];
+    }
+    ForeignState& fs_ = foreignState();
+    if (fs_.active && a.pairs14_compute_foreign != nullptr)
+    {
+        /* an energy-only evaluation of the loop over lambda points: all points come from ONE library call */
+        const int np = static_cast<int>(fs_.lamCoul.size());
+        const int i  = fs_.served++;
+        if (i < np && lam[static_cast<int>(FreeEnergyPerturbationCouplingType::Coul)] == fs_.lamCoul[i]
+            && lam[static_cast<int>(FreeEnergyPerturbationCouplingType::Vdw)] == fs_.lamVdw[i])
+        {
+            if (hd.foreignGeneration != fs_.generation)
+            {
+                hd.foreignE.assign(np, 0.0);
+                hd.foreignDvdl.assign(2 * static_cast<size_t>(np), 0.0);
+                check(a.pairs14_compute_foreign(hd.h, reinterpret_cast<const float*>(x), boxDiag, pbcType, np, fs_.lamCoul.data(),
+                                                fs_.lamVdw.data(), hd.foreignE.data(), hd.foreignDvdl.data()),
+                      "compute_foreign");
+                hd.foreignGeneration = fs_.generation;
+                hd.foreignCalls++;
+            }
+            /* only the sum over energy-group pairs and terms is used of a foreign evaluation (sum_epot into
+             * foreign_term[F_EPOT], listed_forces.cpp:797-798): the point's Coulomb-14 + LJ-14 energy goes to one pair */
+            energygrp_vdw[hd.gids.front()] += static_cast<real>(hd.foreignE[i]);
+            dvdl[static_cast<int>(FreeEnergyPerturbationCouplingType::Coul)] += static_cast<real>(hd.foreignDvdl[2 * i]);
+            dvdl[static_cast<int>(FreeEnergyPerturbationCouplingType::Vdw)] += static_cast<real>(hd.foreignDvdl[2 * i + 1]);
+            hd.foreignLookups++;
+            hd.calls++;
+            return true;
+        }
+        /* not the evaluation the scope expected (another caller inside the loop): evaluate it the plain way */
     }
     std::vector<double> vc(hd.ngrp, 0.0), vv(hd.ngrp, 0.0);
     double              dv[2] = { 0, 0 };

@@ -48,6 +48,7 @@ struct Api
     decltype(&fepb200_pairs14_set_params) pairs14_set_params = nullptr;
     decltype(&fepb200_pairs14_set_pairs)  pairs14_set_pairs  = nullptr;
     decltype(&fepb200_pairs14_compute)    pairs14_compute    = nullptr;
+    decltype(&fepb200_pairs14_compute_foreign) pairs14_compute_foreign = nullptr;
     fepb200_ctx*                   ctx         = nullptr;
     bool                           symbols = false, tried = false, ok = false;
     long                           calls = 0, searchCalls = 0;
@@ -143,6 +144,7 @@ inline void loadSymbols()
     FEPB200_SYM(pairs14_set_params);
     FEPB200_SYM(pairs14_set_pairs);
     FEPB200_SYM(pairs14_compute);
+    FEPB200_SYM(pairs14_compute_foreign);
 #undef FEPB200_SYM
     if (!a.create || !a.compute || !a.set_list || !a.set_lists)
     {

@@ -498,7 +498,7 @@ struct fepb200_pairs14
     int         natoms, npairs, ntypes, ngrp;
     int *       iatoms, *gid;
     double *    qA, *qB, *c6A, *c12A, *c6B, *c12B;
-    long        n_set_pairs, n_compute;
+    long        n_set_pairs, n_compute, n_compute_foreign;
     char        err[256];
 };
 
@@ -559,6 +559,53 @@ int fepb200_pairs14_set_pairs(fepb200_pairs14* h, int natoms, const float* charg
     h->c12B = dup_f2d(c12B, ntypes);
     h->n_set_pairs++;
     return FEPB200_OK;
+}
+
+/* all foreign points in one call: the oracle, point after point */
+int fepb200_pairs14_compute_foreign(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, int n_points,
+                                    const float* lambda_coul, const float* lambda_vdw, double* energy, double* dvdl)
+{
+    if (!h->c.have_params || !h->iatoms)
+    {
+        snprintf(h->err, sizeof(h->err), "pairs14 compute_foreign before params / pairs were set");
+        return FEPB200_ERR_STATE;
+    }
+    const int n  = h->natoms;
+    double*   xd = dup_f2d(x, 3 * (size_t)n);
+    double*   fd = (double*)calloc(3 * (size_t)n + 1, sizeof(double));
+    double*   vc = (double*)calloc(h->ngrp + 1, sizeof(double));
+    double*   vv = (double*)calloc(h->ngrp + 1, sizeof(double));
+    double    bd[3] = { box_diag ? box_diag[0] : 0, box_diag ? box_diag[1] : 0, box_diag ? box_diag[2] : 0 };
+    int       rc = 0;
+    for (int i = 0; i < n_points && rc == 0; i++)
+    {
+        double fs[3 * FEPB200_NUM_SHIFT_VECTORS] = { 0 }, dv[2] = { 0, 0 };
+        memset(vc, 0, sizeof(double) * (h->ngrp + 1));
+        memset(vv, 0, sizeof(double) * (h->ngrp + 1));
+        rc = fep_oracle_pairs14(&h->c.p, h->fudge, h->npairs, h->iatoms, h->c6A, h->c12A, h->c6B, h->c12B, xd, h->qA, h->qB, bd,
+                                pbc_type, h->gid, lambda_coul[i], lambda_vdw[i], fd, fs, vc, vv, dv);
+        energy[i] = 0.0;
+        for (int g = 0; g < h->ngrp; g++)
+        {
+            energy[i] += vc[g] + vv[g];
+        }
+        dvdl[2 * i]     = dv[0];
+        dvdl[2 * i + 1] = dv[1];
+    }
+    free(xd);
+    free(fd);
+    free(vc);
+    free(vv);
+    h->n_compute_foreign++;
+    if (getenv("FEPB200_STANDIN_TRACE"))
+    {
+        fprintf(stderr, "standin: pairs14 compute_foreign %ld (%d points) npairs %d\n", h->n_compute_foreign, n_points, h->npairs);
+    }
+    if (rc != 0)
+    {
+        snprintf(h->err, sizeof(h->err), "oracle pairs14 returned %d", rc);
+    }
+    return rc == 0 ? FEPB200_OK : FEPB200_ERR_INVALID_ARGUMENT;
 }
 
 int fepb200_pairs14_compute(fepb200_pairs14* h, const float* x, const float* box_diag, int pbc_type, const float* lambda,

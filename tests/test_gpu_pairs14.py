@@ -58,6 +58,40 @@ def test_random_lists_match_oracle(ctx, softcore, sc_power, sc_coul, pbc):
         assert np.all(np.abs(out[k] - ref[k]) <= 1e-4 * scale), k
 
 
+@pytest.mark.parametrize("softcore", ["beutler", "gapsys"])
+@pytest.mark.parametrize("pbc", [PBC_NONE, PBC_XYZ])
+def test_all_foreign_lambda_points_in_one_call(ctx, softcore, pbc):
+    """fepb200_pairs14_compute_foreign: what the reference gets from one call of the pair code per lambda point
+    (calc_listed_lambda, listed_forces.cpp:554-640) from ONE evaluation.  Energies against the oracle at every point;
+    dV/dlambda against the energy-only evaluation of the same point (the semantics of the foreign passes of the
+    non-bonded kernel: without the radius-derivative term of the Beutler soft-core, which is built from forces) and,
+    for Gapsys -- whose dV/dlambda has no such term -- against the oracle as well."""
+    import copy
+
+    from oracle import oracle
+
+    prob = random_pairs14(31 + pbc, softcore, sc_coul=True, pbc_type=pbc)
+    ctx.set_problem(prob)
+    lc = np.linspace(0.0, 1.0, 9).astype(np.float32)
+    lv = (lc**2).astype(np.float32)  # separate coul / vdw paths
+    e, d = ctx.compute_foreign(prob, lc, lv)
+    for i in range(len(lc)):
+        q = copy.copy(prob)
+        q.lambda_ = prob.lambda_.copy()
+        q.lambda_[P.LAMBDA_COUL], q.lambda_[P.LAMBDA_VDW] = lc[i], lv[i]
+        ref = oracle.run_pairs14(q)
+        want = float(np.sum(ref["Vc"]) + np.sum(ref["Vv"]))
+        assert abs(e[i] - want) <= 1e-4 * max(abs(want), 1e-2 * np.max(np.abs(e))), (i, e[i], want)
+        only_e = ctx.compute(q, P.DO_POTENTIAL)
+        assert np.allclose(d[i], only_e["dvdl"], rtol=1e-5, atol=1e-5 * np.max(np.abs(d))), (i, d[i], only_e["dvdl"])
+        if softcore == "gapsys":
+            assert np.allclose(d[i], ref["dvdl"], rtol=1e-4, atol=1e-4 * np.max(np.abs(d))), (i, d[i], ref["dvdl"])
+    # the plain evaluation still works afterwards, with its own lambda
+    out = ctx.compute(prob, FLAGS)
+    ref = oracle.run_pairs14(prob)
+    assert np.sqrt(np.mean((out["f"] - ref["f"]) ** 2) / np.mean(ref["f"] ** 2)) <= 1e-5
+
+
 def test_outputs_accumulate_and_flag_subsets(ctx):
     from oracle import oracle
 

@@ -72,3 +72,32 @@ def test_library_inside_the_forks_gpu_route(system, tmp_path):
         pass
     T.compare_runs(system, cpu, ours)
     T.compare_with_reference_golden(system, ours)
+
+
+@pytest.mark.skipif(not os.path.exists(GMX_CUDA), reason="integration/_gmx_cuda not built (integration/build_patched_gmx_cuda.sh)")
+def test_gpu_route_steady_state_timing_beside_the_forks_kernels(tmp_path):
+    """The fork's own GPU timing table ("Nobonded FEP kernel", timing/wallcycle.cpp:1032-1037: its fep_k timer around the
+    FEP launches of gpu_launch_kernel) for libfepb200 inside the route and for the fork's kernels, on c2_hexadecane
+    (BASELINE configs[1] as a real system), 600 steps with the counters reset half way so that context creation and the
+    first list hand-over are not in the row.  A measurement, not a parity test: it fails only if a run fails."""
+    tpr = os.path.join(T.TPR, "c2_hexadecane.tpr")
+    args = ("-nsteps", "600", "-resethway")
+    try:
+        ours = T._run(tpr, str(tmp_path / "b"), True, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=TIMING, mdrun_args=args)
+    except AssertionError as exc:
+        pytest.skip("the fork's CUDA build does not run here: " + str(exc)[-400:])
+    note = ["c2_hexadecane, 600 steps, counters reset half way (steady state):",
+            f"  libfepb200 inside the fork's fep_k timer: {_gpu_fep_row(str(tmp_path / 'b'))}"]
+    note += ["  " + ln for ln in ours[0].splitlines() if ln.startswith("fepb200 GPU route:")]
+    try:
+        T._run(tpr, str(tmp_path / "c"), False, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=TIMING, mdrun_args=args)
+        note.append(f"  the fork's own FEP kernels:               {_gpu_fep_row(str(tmp_path / 'c'))}")
+    except BaseException as exc:  # noqa: BLE001
+        note.append(f"  fork -fep gpu did not complete: {type(exc).__name__}: {str(exc)[:300]}")
+    print("\n".join(note))
+    try:
+        with open(os.path.join(T.ROOT, "gpurun_out", "mdrun_gpu_route_timing.txt"), "a") as fh:
+            fh.write("\n".join(note) + "\n")
+    except OSError:
+        pass
+    assert _gpu_fep_row(str(tmp_path / "b")) is not None

@@ -66,6 +66,11 @@ def test_shim_hands_over_what_the_cpu_route_gets(system, standin, tmp_path):
         # never more hand-overs than pair searches (mdrun sets the bonded threading up again on search steps)
         assert p14 and all(int(re.search(r"(\d+) pair-list uploads", ln).group(1)) <= searches for ln in p14), p14
         assert any("135 perturbed 1-4 pairs" in ln for ln in p14), p14
+        # the foreign-lambda evaluations of a dH/dlambda step come from ONE library call (ForeignScope, hook in
+        # listed_forces.cpp): n_lambda + 1 evaluations served per call
+        m = [re.search(r"foreign lambda: (\d+) library calls served (\d+) evaluations", ln) for ln in p14]
+        calls, served = max((int(x.group(1)), int(x.group(2))) for x in m if x)
+        assert calls >= 5 and served % calls == 0 and served // calls >= 5, p14  # 21 / 9 / 41 lambda points per call
     elif system.startswith("coulandvdw") or system.startswith("c1_"):
         assert not p14  # no perturbed 1-4 pairs in these systems
 
