@@ -49,9 +49,10 @@ def role(kernel_name: str) -> str | None:
         return "epilogue"
     if "fep_beutler_kernel" in n:
         # template arguments <ELEC, MODE, C, FORCE, STAGED>
-        args = n[n.index("<") + 1 : n.index(">")].split(",")
-        c, force = int(args[2]), args[3].strip() in ("1", "true")
-        return "pass" if c == 0 else ("foreign" if not force else "foreign")
+        args = [a.split(")")[-1].strip() for a in n[n.index("<") + 1 : n.index(">")].split(",")]
+        return "pass" if int(args[2]) == 0 else "foreign"  # C > 0: the foreign passes (with the pass fused in when FORCE)
+    if "fep_gapsys_foreign_kernel" in n:
+        return "foreign"
     if "fep_pass_kernel" in n:
         return "pass"
     if "fep_foreign_kernel" in n:
