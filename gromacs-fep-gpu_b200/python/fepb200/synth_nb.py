@@ -49,6 +49,7 @@ class ClusterSystem:
     perturbed_slots: np.ndarray  # int32, slots of the perturbed atoms
     q_unmasked: np.ndarray  # float32 [natoms]
     type_unmasked: np.ndarray  # int32 [natoms]
+    pairs_in_cutoff: int = 0  # atom pairs of the list inside rcoulomb (real atoms, each pair once): the unit of the flop count
 
     @property
     def n_cluster_pairs(self) -> int:
@@ -140,12 +141,18 @@ def build_cluster_system(problem, rlist: float = 1.1, extra_excluded_pairs=None,
     k = np.rint((ctr[c2] - ctr[c1]) / box).astype(np.int64)  # image of c1 closest to c2
     keep = np.zeros(c1.shape[0], bool)
     rl2 = rlist * rlist
+    rc2 = float(problem.params.rcoulomb) ** 2
+    upper = np.triu(np.ones((CL, CL), bool), 1)
+    n_in_cutoff = 0
     for lo in range(0, c1.shape[0], 1 << 18):
         hi = min(lo + (1 << 18), c1.shape[0])
         d = xc[c1[lo:hi]][:, :, None, :] + (k[lo:hi] * box)[:, None, None, :] - xc[c2[lo:hi]][:, None, :, :]
         r2 = (d * d).sum(axis=3)
         ok = rc[c1[lo:hi]][:, :, None] & rc[c2[lo:hi]][:, None, :]
-        keep[lo:hi] = (np.where(ok, r2, np.inf).min(axis=(1, 2)) < rl2)
+        r2 = np.where(ok, r2, np.inf)
+        keep[lo:hi] = r2.min(axis=(1, 2)) < rl2
+        same = (c1[lo:hi] == c2[lo:hi])[:, None, None]
+        n_in_cutoff += int(((r2 < rc2) & (~same | upper[None])).sum())
     c1, c2, k = c1[keep], c2[keep], k[keep]
     sh = _shift_index(k)
     # orientation: central shift -> cj >= ci; otherwise the shift index must be > 22
@@ -243,7 +250,7 @@ def build_cluster_system(problem, rlist: float = 1.1, extra_excluded_pairs=None,
     return ClusterSystem(natoms=natoms, atom_index=atom_index, slot_of_atom=slot_of_atom, xq=xq, type=typ,
                          ntype=problem.ntype, nbfp=np.asarray(problem.nbfp, np.float32), shiftvec=problem.shiftvec,
                          sci=sci, cj=cj, excl=excl, rlist=rlist, perturbed_slots=pslots, q_unmasked=q_unmasked,
-                         type_unmasked=type_unmasked)
+                         type_unmasked=type_unmasked, pairs_in_cutoff=n_in_cutoff)
 
 
 def fep_list_in_slots(problem, cs: ClusterSystem):

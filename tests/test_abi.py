@@ -39,6 +39,29 @@ def test_constants_of_header_and_python_mirror_agree():
         assert k in mirrored, k
 
 
+def _declared_nb_symbols():
+    txt = open(os.path.join(ROOT, "include", "fepb200_nb.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fepb200_nb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_nb_header_binding_and_library_agree():
+    """include/fepb200_nb.h (the non-perturbed cluster-pair kernel): every declared entry point is bound in
+    fepb200.nb and exported by the library; the list structures have the reference's sizes."""
+    from fepb200 import nb as NB
+    from fepb200 import synth_nb
+
+    assert _declared_nb_symbols() == sorted(NB.SYMBOLS)
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in _declared_nb_symbols():
+        assert hasattr(lib, name), name
+    assert (synth_nb.SCI_DTYPE.itemsize, synth_nb.CJ_DTYPE.itemsize, synth_nb.EXCL_DTYPE.itemsize) == (16, 32, 128)
+
+
 def test_library_exports_every_declared_symbol():
     if not os.path.exists(L.LIB_PATH):
         import __graft_entry__

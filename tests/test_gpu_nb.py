@@ -1,0 +1,232 @@
+"""Parity of the non-perturbed cluster-pair kernel (include/fepb200_nb.h) with its pinned CPU checker
+(oracle/nb_oracle.c, tests/test_oracle_nb.py), through the C-ABI, and the device-resident hand-off with the perturbed-pair
+kernels: both add into ONE force buffer in grid order on the device.
+
+Tolerances (fp32 pair maths against the fp64 oracle; the reference's own float build deviates by 1e-6 rel-RMS in the forces,
+test_oracle_nb.py::test_float_build_of_the_reference_sets_the_error_budget):
+  forces        rel-RMS <= 2e-6 of the oracle's (analytical Ewald on both sides), max deviation <= 2e-5 of the largest force
+  shift forces  <= 2e-5 of the largest component
+  energies      <= 1e-5 relative (sums of ~1e6 cancelling terms in fp32 lanes, fp64 across warps)
+"""
+import numpy as np
+import pytest
+
+from fepb200 import params as P
+from fepb200 import synth_nb
+from fepb200.synth import make_system, scaled_spec
+from oracle import nb_oracle
+
+pytestmark = pytest.mark.gpu
+
+ALL = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL
+
+CASES = {
+    "ewald": dict(name="C2", box=4.2, n_blobs=1),
+    "rf": dict(name="C4", box=4.2, n_blobs=1, n_energy_groups=1),
+    "ewald_split_entries": dict(name="C1", box=3.6, n_blobs=1, split=3),
+    "ewald_larger": dict(name="C3", box=6.0, n_blobs=2),
+}
+
+
+def _system(name, box, n_blobs, seed=5, split=0, **kw):
+    pr = make_system(scaled_spec(name, box, n_blobs, **kw), seed=seed)
+    return pr, synth_nb.build_cluster_system(pr, rlist=1.1, max_cj_groups_per_sci=split)
+
+
+@pytest.fixture(scope="module")
+def nb():
+    from fepb200.nb import NbContext
+
+    c = NbContext(0)
+    yield c
+    c.close()
+
+
+def _check(got, want, what=""):
+    f, fw = np.asarray(got["f"], np.float64), want["f"]
+    rms = np.sqrt(np.mean((f - fw) ** 2) / np.mean(fw**2))
+    assert rms <= 2e-6, f"{what}: force rel-RMS {rms:.2e}"
+    assert np.max(np.abs(f - fw)) <= 2e-5 * np.max(np.abs(fw)), what
+    return rms
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_forces_shift_forces_and_energies_match_the_oracle(nb, case):
+    pr, cs = _system(**CASES[case])
+    nb.setup(cs, pr.params)
+    want = nb_oracle.run_port(cs, pr.params, table=None)
+    got = nb.compute(cs.xq[:, :3], cs.shiftvec, ALL)
+    _check(got, want, case)
+    assert np.max(np.abs(got["fshift"] - want["fshift"])) <= 2e-5 * np.max(np.abs(want["fshift"]))
+    assert abs(got["vc"] - want["vc"]) <= 1e-5 * abs(want["vc"])
+    assert abs(got["vvdw"] - want["vvdw"]) <= 1e-5 * abs(want["vvdw"])
+    assert nb.cluster_pairs == cs.n_cluster_pairs
+    # masked and filler atoms receive nothing
+    assert not got["f"][cs.perturbed_slots].any() and not got["f"][cs.atom_index < 0].any()
+
+
+def test_force_only_pass_and_output_semantics(nb):
+    pr, cs = _system(**CASES["ewald"])
+    nb.setup(cs, pr.params)
+    x = cs.xq[:, :3]
+    full = nb.compute(x, cs.shiftvec, ALL)
+    fo = nb.compute(x, cs.shiftvec, P.DO_FORCE)
+    assert fo["vc"] == 0 and fo["vvdw"] == 0 and not fo["fshift"].any()
+    # float atomics: the order of the additions differs from launch to launch
+    scale = np.max(np.abs(full["f"]))
+    assert np.max(np.abs(fo["f"] - full["f"])) <= 2e-6 * scale
+    # accumulate (default) and overwrite
+    out = dict(f=np.full((cs.natoms, 3), 0.5, np.float32), fshift=np.full((45, 3), 0.25, np.float32), vc=1.0, vvdw=2.0)
+    nb.compute(x, cs.shiftvec, ALL, out=out)
+    assert np.max(np.abs(out["f"] - 0.5 - full["f"])) <= 4e-6 * scale
+    assert abs(out["vc"] - 1.0 - full["vc"]) <= 1e-6 * abs(full["vc"]) and abs(out["vvdw"] - 2.0 - full["vvdw"]) <= 1e-6 * abs(full["vvdw"])
+    nb.compute(x, cs.shiftvec, ALL | P.CLEAR_OUTPUTS, out=out)
+    assert np.max(np.abs(out["f"] - full["f"])) <= 2e-6 * scale
+    assert abs(out["vc"] - full["vc"]) <= 1e-6 * abs(full["vc"])
+
+
+def test_masking_on_the_device_is_the_reference_s(nb):
+    pr, cs = _system(**CASES["ewald"])
+    nb.set_params(pr.params)
+    nb.set_nbfp(cs.ntype, cs.nbfp)
+    nb.set_atoms(cs.type_unmasked, cs.q_unmasked)
+    t, q = nb.get_atoms()
+    assert np.array_equal(t, cs.type_unmasked) and np.array_equal(q, cs.q_unmasked)
+    nb.mask_perturbed(cs.perturbed_slots)
+    t, q = nb.get_atoms()
+    xq_u = cs.xq.copy()
+    xq_u[:, 3] = cs.q_unmasked
+    xq_m, t_m = nb_oracle.mask_perturbed(xq_u, cs.type_unmasked, cs.ntype, cs.perturbed_slots)
+    assert np.array_equal(t, t_m) and np.array_equal(q, xq_m[:, 3].astype(np.float32))
+    # without the mask the perturbed atoms would interact here AND in the FEP kernel
+    nb.set_pairlist(cs.sci, cs.cj, cs.excl)
+    masked = nb.compute(cs.xq[:, :3], cs.shiftvec, ALL)
+    nb.set_atoms(cs.type_unmasked, cs.q_unmasked)
+    nb.set_pairlist(cs.sci, cs.cj, cs.excl)
+    unmasked = nb.compute(cs.xq[:, :3], cs.shiftvec, ALL)
+    assert abs(unmasked["vc"] - masked["vc"]) > 1e-3 * abs(masked["vc"])
+
+
+def test_malformed_input_is_refused(nb):
+    from fepb200.lib import FepError
+
+    pr, cs = _system(**CASES["ewald"])
+    nb.setup(cs, pr.params)
+    bad = cs.cj.copy()
+    bad["cj"][5, 2] = cs.natoms  # a j-cluster beyond the atoms
+    with pytest.raises(FepError):
+        nb.set_pairlist(cs.sci, bad, cs.excl)
+    bad = cs.sci.copy()
+    bad["shift"][0] = 45
+    with pytest.raises(FepError):
+        nb.set_pairlist(bad, cs.cj, cs.excl)
+    bad = cs.cj.copy()
+    bad["excl1"][0] = cs.excl.shape[0]
+    with pytest.raises(FepError):
+        nb.set_pairlist(cs.sci, bad, cs.excl)
+    with pytest.raises(FepError):
+        nb.set_atoms(cs.type_unmasked[:-3], cs.q_unmasked[:-3])  # not whole clusters
+    nbfp = cs.nbfp.copy()
+    nbfp[-1] = 1.0  # the last type must not interact
+    with pytest.raises(FepError):
+        nb.set_nbfp(cs.ntype, nbfp)
+    nb.setup(cs, pr.params)  # still usable
+    nb.compute(cs.xq[:, :3], cs.shiftvec, P.DO_FORCE)
+
+
+def test_empty_list(nb):
+    pr, cs = _system(**CASES["ewald"])
+    nb.setup(cs, pr.params)
+    nb.set_pairlist(cs.sci[:0], cs.cj[:0], cs.excl[:1])
+    out = nb.compute(cs.xq[:, :3], cs.shiftvec, ALL)
+    assert not out["f"].any() and out["vc"] == 0 and out["vvdw"] == 0
+
+
+@pytest.mark.parametrize("case", ["ewald", "rf"])
+def test_perturbed_and_non_perturbed_kernels_share_one_device_force_buffer(nb, case):
+    """The whole short-range non-bonded force of a system with perturbed atoms, on the device in grid order: the cluster
+    kernel (masked atoms) and the perturbed-pair kernels (list in grid indices, original parameters) add into the same
+    float3 array; energies of both from device-resident results.  Against the sum of the two CPU checkers."""
+    import torch
+
+    from fepb200.lib import FepContext
+    from oracle import oracle
+
+    pr, cs = _system(**CASES[case])
+    nb.setup(cs, pr.params)
+    fl, qA, qB, tA, tB = synth_nb.fep_list_in_slots(pr, cs)
+    import copy
+
+    grid = copy.copy(pr)
+    grid.nblist, grid.qA, grid.qB, grid.typeA, grid.typeB = fl, qA, qB, tA, tB
+    grid.x = np.ascontiguousarray(cs.xq[:, :3])
+    fep = FepContext(0)
+    try:
+        fep.set_problem(grid)
+        xq = cs.xq.copy()
+        xq[:, 3] = 77.0  # neither kernel may read the charge from here
+        d_xq = torch.from_numpy(xq).cuda()
+        d_f = torch.zeros((cs.natoms, 3), dtype=torch.float32, device="cuda")
+        d_fshift = torch.zeros(135, dtype=torch.float32, device="cuda")
+        d_e = torch.zeros(2, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        flags = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL
+        nb.launch_device(d_xq.data_ptr(), cs.shiftvec, flags, d_f.data_ptr(), d_fshift.data_ptr(), d_e.data_ptr())
+        nb.wait()
+        fep.gather_xq_device(d_xq.data_ptr(), cs.shiftvec)
+        fep.launch(flags)
+        fep.add_forces_device(d_f.data_ptr(), P.ATOMIC_OUTPUTS)
+        fep.wait()
+        got_fep = fep.download(flags & ~P.DO_FORCE)
+        f = d_f.cpu().numpy().astype(np.float64)
+    finally:
+        fep.close()
+    want_nb = nb_oracle.run_port(cs, pr.params, table=None)
+    want_fep = oracle.run_port(grid, flags)
+    want_f = want_nb["f"] + want_fep["f"]
+    rms = np.sqrt(np.mean((f - want_f) ** 2) / np.mean(want_f**2))
+    assert rms <= 2e-6
+    assert np.abs(want_fep["f"][cs.perturbed_slots]).max() > 1.0  # the perturbed atoms do feel forces, from the FEP side
+    e = d_e.cpu().numpy()
+    assert abs(e[0] - want_nb["vc"]) <= 1e-5 * abs(want_nb["vc"]) and abs(e[1] - want_nb["vvdw"]) <= 1e-5 * abs(want_nb["vvdw"])
+    fsh = d_fshift.cpu().numpy().reshape(45, 3)
+    assert np.max(np.abs(fsh - want_nb["fshift"])) <= 2e-5 * np.max(np.abs(want_nb["fshift"]))
+    assert np.allclose(got_fep["Vc"], want_fep["Vc"], rtol=1e-4, atol=1e-4 * np.max(np.abs(want_fep["Vc"])))
+
+
+def test_charges_can_come_from_the_caller_s_xq(nb):
+    """FEPB200_NB_Q_FROM_XQ: the fork keeps masked charges in NBAtomDataGpu::xq.w; the kernel then reads the caller's
+    array directly (no packing pass)."""
+    import torch
+
+    from fepb200.nb import NB_Q_FROM_XQ
+
+    pr, cs = _system(**CASES["ewald"])
+    nb.setup(cs, pr.params)
+    d_xq = torch.from_numpy(cs.xq).cuda()  # masked charges in .w
+    d_f = torch.zeros((cs.natoms, 3), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    n0 = nb.launch_count
+    nb.launch_device(d_xq.data_ptr(), cs.shiftvec, P.DO_FORCE | NB_Q_FROM_XQ, d_f.data_ptr())
+    nb.wait()
+    assert nb.launch_count == n0 + 1
+    want = nb_oracle.run_port(cs, pr.params, table=None, energy=False)
+    _check(dict(f=d_f.cpu().numpy()), want)
+    assert nb.last_kernel_ms() > 0
+
+
+def test_medium_system_properties(nb):
+    """C3-sized (100 k atoms): too slow for the CPU checker in a unit test, so size-independent properties: Newton's third
+    law (the forces sum to zero), two launches agree to the rounding of the atomic additions' order, and so do their
+    energies."""
+    pr = make_system("C3")
+    cs = synth_nb.build_cluster_system(pr, rlist=1.1)
+    nb.setup(cs, pr.params)
+    x = cs.xq[:, :3]
+    a = nb.compute(x, cs.shiftvec, ALL)
+    b = nb.compute(x, cs.shiftvec, ALL)
+    scale = np.max(np.abs(a["f"]))
+    assert np.max(np.abs(a["f"].astype(np.float64).sum(axis=0))) <= 1e-4 * scale
+    assert np.max(np.abs(a["f"] - b["f"])) <= 4e-6 * scale
+    assert abs(a["vc"] - b["vc"]) <= 1e-9 * abs(a["vc"]) + 1e-3
+    assert nb.cluster_pairs == cs.n_cluster_pairs > 1_000_000
