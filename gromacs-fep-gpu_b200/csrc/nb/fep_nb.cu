@@ -242,8 +242,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
             const unsigned int imask = (unsigned int)ime.x;
             const unsigned int wex0  = __ldg(&a.excl[ime.y].pair[lane]);
             const unsigned int wex1  = __ldg(&a.excl[ime.w].pair[lane]);
-            const int          cjs[4] = { cjv.x, cjv.y, cjv.z, cjv.w };
-#pragma unroll
+            /* NOT unrolled: the body below (8 i-clusters x 2 atom pairs, straight line) is 14 KB of code; four copies
+             * of it do not fit the 32 KB instruction cache level and the warps of an SM then wait for fetches */
+#pragma unroll 1
             for (int jm = 0; jm < FEPB200_NB_JGROUP_SIZE; jm++)
             {
                 const unsigned int m8 = (imask >> (NCL * jm)) & 0xffu;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
                 {
                     continue;
                 }
-                const int    cjn = cjs[jm];
+                const int    cjn = jm == 0 ? cjv.x : (jm == 1 ? cjv.y : (jm == 2 ? cjv.z : cjv.w));
                 const int    ja  = cjn * CL + jq;
                 const float4 xa  = __ldg(a.xq + ja);
                 const float4 xb  = __ldg(a.xq + ja + CL / 2);
@@ -364,8 +365,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
 }
 
 /* x rvec[natoms] + masked charges -> float4; or the caller's xq with the masked charge put in */
-__global__ void fep_nb_pack_kernel(int n, const float* __restrict__ x3, const float4* __restrict__ x4,
-                                   const float* __restrict__ q, float4* __restrict__ out)
+__global__ void fep_nb_pack_kernel(int n, const float* __restrict__ x3, const float4* x4, const float* __restrict__ q,
+                                   float4* out) /* x4 may be out */
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
@@ -952,8 +953,8 @@ int fepb200_nb_launch_device(fepb200_nb* h, const float* d_xq, const float* shif
     return nb_launch(h, xq, flags, d_f, d_fshift, d_energies);
 }
 
-int fepb200_nb_compute(fepb200_nb* h, const float* x, const float* shiftvec, int flags, float* f, float* fshift, double* vc,
-                       double* vvdw)
+static int nb_compute_host(fepb200_nb* h, const float* x, int xstride, const float* shiftvec, int flags, float* f,
+                           float* fshift, double* vc, double* vvdw)
 {
     if (h == nullptr || x == nullptr || f == nullptr)
     {
@@ -974,7 +975,8 @@ int fepb200_nb_compute(fepb200_nb* h, const float* x, const float* shiftvec, int
         return rc;
     }
     const size_t n3    = 3 * (size_t)h->natoms;
-    const size_t words = 2 * n3 + 3 * FEPB200_NUM_SHIFT_VECTORS + 4;
+    const size_t nx    = (size_t)xstride * h->natoms;
+    const size_t words = nx + n3 + 3 * FEPB200_NUM_SHIFT_VECTORS + 4;
     if (words > h->cap_pinned)
     {
         if (h->h_pinned)
@@ -988,13 +990,26 @@ int fepb200_nb_compute(fepb200_nb* h, const float* x, const float* shiftvec, int
     /* pinned staging block: {vc, vvdw} as doubles first (alignment), then x in, f out, shift forces out */
     double* he  = reinterpret_cast<double*>(h->h_pinned);
     float*  hx  = h->h_pinned + 4;
-    float*  hf  = hx + n3;
+    float*  hf  = hx + nx;
     float*  hfs = hf + n3;
-    std::memcpy(hx, x, n3 * sizeof(float));
-    NB_CUDA(cudaMemcpyAsync(h->d_x3, hx, n3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    fep_nb_pack_kernel<<<(h->natoms + 255) / 256, 256, 0, h->stream>>>(h->natoms, h->d_x3, nullptr, h->d_q, h->d_xq);
-    NB_CUDA(cudaGetLastError());
-    h->launches++;
+    std::memcpy(hx, x, nx * sizeof(float));
+    if (xstride == 3)
+    {
+        NB_CUDA(cudaMemcpyAsync(h->d_x3, hx, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        fep_nb_pack_kernel<<<(h->natoms + 255) / 256, 256, 0, h->stream>>>(h->natoms, h->d_x3, nullptr, h->d_q, h->d_xq);
+        NB_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    else
+    {
+        NB_CUDA(cudaMemcpyAsync(h->d_xq, hx, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        if (!(flags & FEPB200_NB_Q_FROM_XQ))
+        {
+            fep_nb_pack_kernel<<<(h->natoms + 255) / 256, 256, 0, h->stream>>>(h->natoms, nullptr, h->d_xq, h->d_q, h->d_xq);
+            NB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+    }
     NB_CUDA(cudaMemsetAsync(h->d_f, 0, n3 * sizeof(float), h->stream));
     NB_CUDA(cudaMemsetAsync(h->d_fshift, 0, sizeof(h->h_shift), h->stream));
     NB_CUDA(cudaMemsetAsync(h->d_energies, 0, 2 * sizeof(double), h->stream));
@@ -1039,6 +1054,18 @@ int fepb200_nb_compute(fepb200_nb* h, const float* x, const float* shiftvec, int
         *vvdw = clear ? he[1] : *vvdw + he[1];
     }
     return FEPB200_OK;
+}
+
+int fepb200_nb_compute(fepb200_nb* h, const float* x, const float* shiftvec, int flags, float* f, float* fshift, double* vc,
+                       double* vvdw)
+{
+    return nb_compute_host(h, x, 3, shiftvec, flags & ~FEPB200_NB_Q_FROM_XQ, f, fshift, vc, vvdw);
+}
+
+int fepb200_nb_compute_xyzq(fepb200_nb* h, const float* xq, const float* shiftvec, int flags, float* f, float* fshift,
+                            double* vc, double* vvdw)
+{
+    return nb_compute_host(h, xq, 4, shiftvec, flags, f, fshift, vc, vvdw);
 }
 
 int fepb200_nb_wait(fepb200_nb* h)

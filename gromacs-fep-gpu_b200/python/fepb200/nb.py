@@ -28,6 +28,7 @@ SYMBOLS = {
     "fepb200_nb_get_atoms": (ctypes.c_int, [_VP, _IP, _FP]),
     "fepb200_nb_set_pairlist": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, ctypes.c_int, _VP]),
     "fepb200_nb_compute": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, _FP, _DP, _DP]),
+    "fepb200_nb_compute_xyzq": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, _FP, _DP, _DP]),
     "fepb200_nb_launch_device": (ctypes.c_int, [_VP, _VP, _FP, ctypes.c_int, _VP, _VP, _VP]),
     "fepb200_nb_wait": (ctypes.c_int, [_VP]),
     "fepb200_nb_launch_count": (ctypes.c_longlong, [_VP]),
@@ -126,6 +127,16 @@ class NbContext:
             vc, vv = ctypes.c_double(out.get("vc", 0.0)), ctypes.c_double(out.get("vvdw", 0.0))
         self._check(self._lib.fepb200_nb_compute(self._h, L._pf(x), L._pf(sv), int(flags), L._pf(out["f"]),
                                                  L._pf(out["fshift"]), ctypes.byref(vc), ctypes.byref(vv)))
+        out["vc"], out["vvdw"] = vc.value, vv.value
+        return out
+
+    def compute_xyzq(self, xq, shiftvec, flags=DO_FORCE | DO_SHIFTFORCE | DO_POTENTIAL):
+        """Host buffers, coordinates as float4 {x, y, z, q} (nbat->x() of the reference, nbatXYZQ)."""
+        xq, sv = L._f32(xq).reshape(-1, 4), L._f32(shiftvec).reshape(NUM_SHIFT_VECTORS, 3)
+        out = dict(f=np.zeros((self.natoms, 3), np.float32), fshift=np.zeros((NUM_SHIFT_VECTORS, 3), np.float32))
+        vc, vv = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self._lib.fepb200_nb_compute_xyzq(self._h, L._pf(xq), L._pf(sv), int(flags), L._pf(out["f"]),
+                                                      L._pf(out["fshift"]), ctypes.byref(vc), ctypes.byref(vv)))
         out["vc"], out["vvdw"] = vc.value, vv.value
         return out
 

@@ -90,18 +90,23 @@ int fepb200_nb_set_pairlist(fepb200_nb* h, int nsci, const fepb200_nb_sci* sci, 
                             int nexcl, const fepb200_nb_excl* excl);
 
 /* ---- the hot call ------------------------------------------------------ */
+#define FEPB200_NB_Q_FROM_XQ (1 << 20) /* extension bit: charges come from the .w of the caller's xyzq array */
 /* One evaluation with host buffers: x = rvec[natoms] in grid order (what nbnxn_atomdata_copy_x_to_nbat_x produces),
  * shiftvec rvec[45].  flags: FEPB200_DO_FORCE (always implied), FEPB200_DO_SHIFTFORCE, FEPB200_DO_POTENTIAL,
  * FEPB200_CLEAR_OUTPUTS.  Outputs are ACCUMULATED like the reference kernel does with clearF = enbvClearFNo:
  * f rvec[natoms], fshift rvec[45], vc[1], vvdw[1].  Host -> device copy of x and device -> host copy of f inside the call. */
 int fepb200_nb_compute(fepb200_nb* h, const float* x, const float* shiftvec, int flags, float* f, float* fshift,
                        double* vc, double* vvdw);
+/* The same with the coordinates as the reference holds them for its GPU-layout kernels: xq = float4[natoms], nbat->x() in
+ * nbatXYZQ format (atomdata.h:77-96).  With FEPB200_NB_Q_FROM_XQ the charge is taken from .w -- the reference masks it
+ * there itself -- otherwise from the masked device copy. */
+int fepb200_nb_compute_xyzq(fepb200_nb* h, const float* xq, const float* shiftvec, int flags, float* f, float* fshift,
+                            double* vc, double* vvdw);
 /* Device-resident: d_xq = float4[natoms] (NBAtomDataGpu::xq; .w is ignored unless FEPB200_NB_Q_FROM_XQ is set -- the
  * charge normally comes from the masked device copy), d_f = float3[natoms] (NBAtomDataGpu::f) that the kernel ADDS into
  * with atomic operations -- the same buffer fepb200_add_forces_device() adds the perturbed pairs' forces into --,
  * d_fshift float[135], d_energies double[2] = {vc, vvdw}; the last three may be NULL when the flag is not set.
  * shiftvec is a HOST pointer (uploaded when it changed).  Asynchronous on the handle's stream. */
-#define FEPB200_NB_Q_FROM_XQ (1 << 20)
 int fepb200_nb_launch_device(fepb200_nb* h, const float* d_xq, const float* shiftvec, int flags, float* d_f,
                              float* d_fshift, double* d_energies);
 int fepb200_nb_wait(fepb200_nb* h);

@@ -22,6 +22,9 @@ cp /root/reference/src/gromacs/listed_forces/pairs.cpp "$SRC/src/gromacs/listed_
 # ... and the scope around the foreign-lambda loop of the listed forces (all points of the 1-4 pairs in one library call)
 cp /root/reference/src/gromacs/listed_forces/listed_forces.cpp "$SRC/src/gromacs/listed_forces/listed_forces.cpp"
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/listed_forces_fepb200.patch")
+# ... and the hook for the non-perturbed cluster-pair kernel (nbnxm/kerneldispatch.cpp -> fepb200_nb_*)
+cp /root/reference/src/gromacs/nbnxm/kerneldispatch.cpp "$SRC/src/gromacs/nbnxm/kerneldispatch.cpp"
+(cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/kerneldispatch_fepb200.patch")
 mkdir -p "$BUILD"
 cmake -G Ninja -S "$SRC" -B "$BUILD" -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ \
   -DCMAKE_POLICY_VERSION_MINIMUM=3.5 -DGMX_GPU=OFF -DGMX_MPI=OFF -DGMX_THREAD_MPI=ON -DGMX_OPENMP=ON \
