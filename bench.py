@@ -293,6 +293,27 @@ def _fork_gpu_beside(args, name):
         return dict(unavailable=f"{type(exc).__name__}: {exc}"[:300])
 
 
+def _nb_beside(args):
+    """the non-perturbed cluster-pair kernel (include/fepb200_nb.h) timed on C3's atoms in the reference's
+    GPU cluster layout, device-resident, L2 flushed between launches; tools/nb_bench.py in a subprocess (never raises).
+    Roofline by the reference's own flop accounting for these kernels (nrnb.cpp:90-95 x listed atom pairs)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "nb_bench.py"), "C3", "--steps", "20"]
+    try:
+        out = {}
+        for key, extra in (("force", []), ("force_energy_virial", ["--energy"])):
+            r = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=600)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not lines:
+                return dict(unavailable=f"exit code {r.returncode}: {(r.stderr or '').strip()[-200:]}")
+            d = json.loads(lines[-1])
+            peak = 148 * 128 * 2 * _peaks()["sm_max_mhz"] * 1e-6  # TFLOP/s, like the FEP kernels' roofline
+            d["frac_of_fp32_peak"] = d["algorithmic_tflops"] / peak
+            out[key] = d
+        return out
+    except Exception as exc:  # noqa: BLE001 -- a reported side line must not take the bench down
+        return dict(unavailable=f"{type(exc).__name__}: {exc}"[:300])
+
+
 def _side_config(name, device, flush, steps):
     """One more BASELINE.json configuration on this GPU: device time per step (L2 flushed between steps, inputs resident),
     the same through fepb200_compute with host buffers, per-kernel times."""
@@ -613,6 +634,9 @@ def run_ours(args, name):
                         side[other] = _side_config(other, local, flush, min(args.steps, 30))
                     except Exception as exc:  # noqa: BLE001 -- a side line must not take the bench down
                         side[other] = dict(unavailable=f"{type(exc).__name__}: {exc}"[:300])
+        nb_line = None
+        if world == 1 and not args.no_side_configs and args.n_foreign is None:
+            nb_line = _nb_beside(args)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
                     data="synthetic", config=_config(problem, name),
@@ -626,7 +650,7 @@ def run_ours(args, name):
                                   "steps (measured separately) is subtracted"),
                     gpu_launches=int(launches) * world, clocks=clocks, roofline=roofline, every_step=every_step,
                     kernel_ms=dict(pass_kernel=k_pass, foreign_kernel=k_foreign, epilogue_kernel=k_epi),
-                    configs=side, cpu_baseline=cpu, fork_gpu_baseline=fork_gpu,
+                    configs=side, cluster_pair_kernel=nb_line, cpu_baseline=cpu, fork_gpu_baseline=fork_gpu,
                     wall_ms_per_step_incl_flush=t_wall / args.steps * 1e3, device=ctx.describe())
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)

@@ -183,6 +183,7 @@ struct fepb200_ctx
     /* ... and when that copy was queued by gather_x_device(): ev_staged marks its end, so the next gather waits for
      * the copy alone instead of draining a stream the caller shares with its own kernels (the nbnxm stream) */
     cudaEvent_t  ev_staged       = nullptr;
+    cudaEvent_t  ev_handoff      = nullptr; /* fepb200_launch() on a stream of the caller's: orders it behind the context's stream */
     bool         staged_by_event = false;
 
     /* constants */
@@ -1094,6 +1095,7 @@ int fepb200_create(fepb200_ctx** out, int device_ordinal)
         || cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess
         || cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess
         || cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&c->ev_handoff, cudaEventDisableTiming) != cudaSuccess
         || !create_copy_events(c)
         || c->d_counter.reserve(1) != cudaSuccess || cudaMemset(c->d_counter.ptr, 0, sizeof(unsigned int)) != cudaSuccess)
     {
@@ -1226,6 +1228,10 @@ int fepb200_destroy(fepb200_ctx* c)
     }
     cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_stop);
+    if (c->ev_handoff)
+    {
+        cudaEventDestroy(c->ev_handoff);
+    }
     if (c->ev_staged)
     {
         cudaEventDestroy(c->ev_staged);
@@ -1967,6 +1973,13 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     close_chain(c);
     cudaStream_t    stream = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
     const StepFlags sf     = step_flags(c, flags);
+    if (stream != c->stream)
+    {
+        /* a launch stream of the caller's: the staging copies of upload_x / gather_x* (and the constants set earlier)
+         * were queued on the context's stream -- the kernels must not start before them */
+        CU_CHECK(c, cudaEventRecord(c->ev_handoff, c->stream));
+        CU_CHECK(c, cudaStreamWaitEvent(stream, c->ev_handoff, 0));
+    }
     CU_CHECK(c, cudaEventRecord(c->ev_start, stream));
     KernelArgs ka_step = c->ka;
     c->result_on_host  = false;
@@ -2040,6 +2053,12 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     if (!c->chain_open)
     {
         CU_CHECK(c, cudaEventRecord(c->ev_stop, stream));
+    }
+    if (stream != c->stream)
+    {
+        /* ... and every consumer (add_forces_device, export_scalars_device, download, the next staging copy) runs on
+         * the context's stream: it must not start before the kernels are done */
+        CU_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_stop, 0));
     }
     c->timed = true;
     return FEPB200_OK;

@@ -70,6 +70,7 @@ struct NbArgs
     const fepb200_nb_excl* __restrict__ excl;
     const NbItem* __restrict__ items;
     int      nitems;
+    unsigned int* next_item; /* work queue head, zeroed before the launch */
     float*   f;      /* float3[natoms], added into */
     float*   fshift; /* float[135] or NULL */
     double*  energies; /* {vc, vvdw} or NULL */
@@ -125,28 +126,34 @@ __device__ __forceinline__ float nb_ewald_B(float w)
     return p * nb_rcp(q);
 }
 
+__device__ __forceinline__ void nb_prefetch_l1(const void* p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 struct F3
 {
     float x, y, z;
 };
 
-/* One atom pair.  `bit` = 1.0f when the pair interacts (0: excluded pair, which still gets the reaction-field / Ewald
- * correction), `skip` = lower triangle of a cluster against itself in the central cell. */
-template<bool EWALD, bool ENERGY>
-__device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restrict__ nbfp, float xi, float yi, float zi,
-                                        float qi, int ti, const float4& xj, int tj, float bit, bool skip, F3& fi, F3& fj,
+/* One atom pair.  `bit`: the pair interacts (false: excluded pair, which still gets the reaction-field / Ewald
+ * correction); `skip`: lower triangle of a cluster against itself in the central cell.  Everything a pair can be ruled out by
+ * is a select on the result, never a factor: a pair far outside the cut-off (filler atoms) may produce inf / NaN on the way.
+ * SAMECUT: rvdw == rcoulomb, one test for both.  `nb`: the {6 C6, 12 C12} table, in shared memory when TABSMEM. */
+template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM>
+__device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restrict__ nb, float xi, float yi, float zi,
+                                        float qi, int ti, const float4& xj, int tj, bool bit, bool skip, F3& fi, F3& fj,
                                         float& e_el, float& e_lj)
 {
-    const float dx = xi - xj.x, dy = yi - xj.y, dz = zi - xj.z;
-    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-    const bool  in = (r2 < c.rc2) && !skip;
-    /* pairs outside the cut-off are evaluated like the others and dropped by a select: keep their arguments in range */
-    const float  r2c   = fminf(fmaxf(r2, MIN_RSQ), c.rc2);
+    const float  dx = xi - xj.x, dy = yi - xj.y, dz = zi - xj.z;
+    const float  r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    const bool   in = (r2 < c.rc2) && !skip;
+    const float  r2c   = fmaxf(r2, MIN_RSQ);
     const float  rinv  = nb_rsqrt(r2c);
     const float  rinv2 = rinv * rinv;
     const float  qq    = qi * xj.w;
-    const float2 cc    = __ldg(nbfp + ti + tj);
-    const float  brinv = bit * rinv;
+    const float2 cc    = TABSMEM ? nb[ti + tj] : __ldg(nb + ti + tj);
+    const float  brinv = bit ? rinv : 0.0f;
     float        fs, v_el;
     if (EWALD)
     {
@@ -155,7 +162,7 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
         fs = qq * fmaf(brinv, rinv2, c.beta3 * nb_ewald_B(w));
         if (ENERGY)
         {
-            v_el = qq * (brinv - c.beta * nb_ewald_V(w) - bit * c.sh_ewald);
+            v_el = qq * (brinv - c.beta * nb_ewald_V(w) - (bit ? c.sh_ewald : 0.0f));
         }
     }
     else
@@ -167,43 +174,70 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
             v_el = qq * (brinv + kr2 - c.c_rf);
         }
     }
-    const bool  inlj = in && (r2c < c.rv2);
-    const float r6   = bit * rinv2 * rinv2 * rinv2;
+    const bool  inlj = SAMECUT ? in : (in && (r2c < c.rv2));
+    const float r6   = bit ? rinv2 * rinv2 * rinv2 : 0.0f;
     const float v6   = cc.x * r6;
     const float v12  = cc.y * r6 * r6;
-    fs += inlj ? (v12 - v6) * rinv2 : 0.0f;
-    fs = in ? fs : 0.0f;
+    const float flj  = (v12 - v6) * rinv2;
+    if (SAMECUT)
+    {
+        fs = in ? fs + flj : 0.0f;
+    }
+    else
+    {
+        fs += inlj ? flj : 0.0f;
+        fs = in ? fs : 0.0f;
+    }
     if (ENERGY)
     {
         /* the reference books the Coulomb energy inside its `rsq < rvdw2` branch (kernel_gpu_ref.cpp:264-287) */
         e_el += inlj ? v_el : 0.0f;
-        const float vlj = fmaf(bit * cc.y, c.rep_cpot, v12) * (1.0f / 12.0f) - fmaf(bit * cc.x, c.disp_cpot, v6) * (1.0f / 6.0f);
+        const float vlj = fmaf(bit ? cc.y : 0.0f, c.rep_cpot, v12) * (1.0f / 12.0f)
+                          - fmaf(bit ? cc.x : 0.0f, c.disp_cpot, v6) * (1.0f / 6.0f);
         e_lj += inlj ? vlj : 0.0f;
     }
-    const float fx = fs * dx, fy = fs * dy, fz = fs * dz;
-    fi.x += fx;
-    fi.y += fy;
-    fi.z += fz;
-    fj.x -= fx;
-    fj.y -= fy;
-    fj.z -= fz;
+    fi.x = fmaf(fs, dx, fi.x);
+    fi.y = fmaf(fs, dy, fi.y);
+    fi.z = fmaf(fs, dz, fi.z);
+    fj.x = fmaf(-fs, dx, fj.x);
+    fj.y = fmaf(-fs, dy, fj.y);
+    fj.z = fmaf(-fs, dz, fj.z);
 }
 
 #define FULL 0xffffffffu
 
-template<bool EWALD, bool ENERGY>
+template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbArgs a)
 {
+    extern __shared__ float2 s_nbfp[];
+    if (TABSMEM)
+    {
+        for (int k = threadIdx.x; k < a.c.ntype * a.c.ntype; k += blockDim.x)
+        {
+            s_nbfp[k] = a.nbfp[k];
+        }
+        __syncthreads();
+    }
+    const float2* __restrict__ nbtab = TABSMEM ? s_nbfp : a.nbfp;
     const int lane   = threadIdx.x & 31;
     const int ii     = lane & 7;
     const int jq     = lane >> 3;
-    const int nwarps = gridDim.x * WARPS_PER_CTA;
-    /* warp-major: the first warps of all CTAs take the first items, so a short list spreads over all SMs */
-    const int w0 = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     const NbConsts& c = a.c;
 
-    for (int item = w0; item < a.nitems; item += nwarps)
+    /* items differ in cost (how many of the 8 x 4 cluster pairs of a packed entry are listed): every warp takes the next
+     * item from one queue, so that all SMs finish together */
+    for (;;)
     {
+        int item = 0;
+        if (lane == 0)
+        {
+            item = (int)atomicAdd(a.next_item, 1u);
+        }
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= a.nitems)
+        {
+            break;
+        }
         const NbItem         it    = a.items[item];
         const fepb200_nb_sci e     = a.sci[it.entry];
         const float          shx   = __ldg(a.shiftvec + 3 * e.shift);
@@ -258,20 +292,35 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
                 const float4 xb  = __ldg(a.xq + ja + CL / 2);
                 const int    ta  = __ldg(a.type + ja);
                 const int    tb  = __ldg(a.type + ja + CL / 2);
+                {
+                    /* the atoms of the next j-cluster -- of this packed entry, or the first of the next one, whose 32 bytes
+                     * follow this one's -- on their way into L1 while this one is evaluated: one 128-byte line of
+                     * coordinates, one 32-byte sector of types */
+                    const int* nxt = reinterpret_cast<const int*>(a.cj + 2 * g) + (jm < 3 ? jm + 1 : 8);
+                    if (jm < 3 || g + 1 < it.cj_end)
+                    {
+                        const int cjp = __ldg(nxt);
+                        nb_prefetch_l1(a.xq + cjp * CL + (lane & 7));
+                        nb_prefetch_l1(a.type + cjp * CL + (lane & 7));
+                    }
+                }
                 F3           fa = { 0.0f, 0.0f, 0.0f }, fb = { 0.0f, 0.0f, 0.0f };
                 const unsigned int ea = wex0 >> (NCL * jm), eb = wex1 >> (NCL * jm);
+                /* a cluster against itself in the central cell (at most one i-cluster of the eight): only the upper
+                 * triangle of its atom pairs exists (kernel_gpu_ref.cpp:196-199).  One bit mask per lane and j atom,
+                 * tested with the i-cluster's bit like the exclusion words. */
+                const int          dself = centr ? cjn - ci0 : NCL;
+                const unsigned int sbit  = (dself >= 0 && dself < NCL) ? (1u << dself) : 0u;
+                const unsigned int ska = (jq <= ii) ? sbit : 0u, skb = (jq + CL / 2 <= ii) ? sbit : 0u;
 #pragma unroll
                 for (int im = 0; im < NCL; im++)
                 {
                     if (m8 & (1u << im))
                     {
-                        const bool  diag = centr && (ci0 + im == cjn);
-                        const float ba   = (float)((ea >> im) & 1u);
-                        const float bb   = (float)((eb >> im) & 1u);
-                        nb_pair<EWALD, ENERGY>(c, a.nbfp, xi[im], yi[im], zi[im], qi[im], ti[im], xa, ta, ba,
-                                               diag && (jq <= ii), fi[im], fa, e_el, e_lj);
-                        nb_pair<EWALD, ENERGY>(c, a.nbfp, xi[im], yi[im], zi[im], qi[im], ti[im], xb, tb, bb,
-                                               diag && (jq + CL / 2 <= ii), fi[im], fb, e_el, e_lj);
+                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, xi[im], yi[im], zi[im], qi[im], ti[im], xa, ta,
+                                                                 (ea >> im) & 1u, (ska >> im) & 1u, fi[im], fa, e_el, e_lj);
+                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, xi[im], yi[im], zi[im], qi[im], ti[im], xb, tb,
+                                                                 (eb >> im) & 1u, (skb >> im) & 1u, fi[im], fb, e_el, e_lj);
                     }
                 }
                 /* j forces: reduce {fa, fb} over the 8 lanes ii = 0..7 that hold the same two j atoms, leaving each of
@@ -425,6 +474,7 @@ struct fepb200_nb
     fepb200_nb_cj_packed* d_cj = nullptr;
     fepb200_nb_excl*      d_excl = nullptr;
     NbItem*        d_items = nullptr;
+    unsigned int*  d_next = nullptr; /* head of the kernel's work queue */
     size_t         cap_sci = 0, cap_cj = 0, cap_excl = 0, cap_items = 0, cap_atoms = 0;
     float*         h_pinned = nullptr; /* x in / f out staging */
     size_t         cap_pinned = 0;
@@ -493,6 +543,7 @@ int nb_launch(fepb200_nb* h, const float4* d_xq, int flags, float* d_f, float* d
     a.excl     = h->d_excl;
     a.items    = h->d_items;
     a.nitems   = h->nitems;
+    a.next_item = h->d_next;
     a.f        = d_f;
     a.fshift   = (flags & FEPB200_DO_SHIFTFORCE) ? d_fshift : nullptr;
     a.energies = d_energies;
@@ -501,27 +552,43 @@ int nb_launch(fepb200_nb* h, const float4* d_xq, int flags, float* d_f, float* d
     NB_CUDA(cudaEventRecord(h->ev0, h->stream));
     if (h->nitems > 0)
     {
+        NB_CUDA(cudaMemsetAsync(h->d_next, 0, sizeof(unsigned int), h->stream));
         const int per_sm = 4;
         int       grid   = (h->nitems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         if (grid > h->sm_count * per_sm)
         {
             grid = h->sm_count * per_sm;
         }
-        const dim3 block(WARPS_PER_CTA * 32);
-        if (h->ewald)
+        const dim3   block(WARPS_PER_CTA * 32);
+        const bool   same   = h->c.rc2 == h->c.rv2;
+        const size_t tab    = sizeof(float2) * h->ntype * h->ntype;
+        const bool   smem   = tab <= 16384;
+        const int    which  = (h->ewald ? 8 : 0) | (energy ? 4 : 0) | (same ? 2 : 0) | (smem ? 1 : 0);
+        const size_t shared = smem ? tab : 0;
+#define NB_CASE(E, V, S, T)                                                                  \
+    case ((E) ? 8 : 0) | ((V) ? 4 : 0) | ((S) ? 2 : 0) | ((T) ? 1 : 0):                      \
+        fep_nb_kernel<E, V, S, T><<<grid, block, shared, h->stream>>>(a);                    \
+        break;
+        switch (which)
         {
-            if (energy)
-                fep_nb_kernel<true, true><<<grid, block, 0, h->stream>>>(a);
-            else
-                fep_nb_kernel<true, false><<<grid, block, 0, h->stream>>>(a);
+            NB_CASE(false, false, false, false)
+            NB_CASE(false, false, false, true)
+            NB_CASE(false, false, true, false)
+            NB_CASE(false, false, true, true)
+            NB_CASE(false, true, false, false)
+            NB_CASE(false, true, false, true)
+            NB_CASE(false, true, true, false)
+            NB_CASE(false, true, true, true)
+            NB_CASE(true, false, false, false)
+            NB_CASE(true, false, false, true)
+            NB_CASE(true, false, true, false)
+            NB_CASE(true, false, true, true)
+            NB_CASE(true, true, false, false)
+            NB_CASE(true, true, false, true)
+            NB_CASE(true, true, true, false)
+            NB_CASE(true, true, true, true)
         }
-        else
-        {
-            if (energy)
-                fep_nb_kernel<false, true><<<grid, block, 0, h->stream>>>(a);
-            else
-                fep_nb_kernel<false, false><<<grid, block, 0, h->stream>>>(a);
-        }
+#undef NB_CASE
         NB_CUDA(cudaGetLastError());
         h->launches++;
     }
@@ -595,6 +662,7 @@ int fepb200_nb_create(fepb200_nb** out, int device_ordinal)
     NB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_shift), sizeof(h->h_shift)));
     NB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_fshift), sizeof(h->h_shift)));
     NB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_energies), 2 * sizeof(double)));
+    NB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_next), sizeof(unsigned int)));
     *out = h;
     return FEPB200_OK;
 }
@@ -620,6 +688,7 @@ int fepb200_nb_destroy(fepb200_nb* h)
     cudaFree(h->d_cj);
     cudaFree(h->d_excl);
     cudaFree(h->d_items);
+    cudaFree(h->d_next);
     if (h->h_pinned)
     {
         cudaFreeHost(h->h_pinned);

@@ -120,12 +120,15 @@ typedef struct fepb200_layout
     long long nrj_total;   /* pairs of the full list                            */
     int       nenergrp;    /* energy-group pairs G                              */
     int       nforeign;    /* L (foreign lambda points, without the current one) */
-    /* Device result block (fp32 words unless noted), identical on every rank so it
-     * can be handed to ncclAllReduce / ncclReduceScatter as is:
-     *   [0, 3*ntouched)          compact forces, atom k of fepb200_touched_atoms()
-     *   then 3*45                shift forces
-     * followed by an fp64 block (see offsets, in units of doubles from its start):
-     *   Vc[G] Vv[G] dvdl[2] foreign_E[L+1] foreign_dvdl[(L+1)][2]               */
+    /* Device result block, identical on every rank so it can be combined across GPUs as it is.  It is ONE contiguous
+     * allocation laid out [f64 part | f32 part] (fepb200_result_block_bytes() bytes; this is also the layout of a
+     * published block, fepb200_publish_result() / fepb200_set_partial_result_block()); fepb200_result_device_ptrs()
+     * returns the start of each part.
+     *   f64 part (offsets below in units of doubles from its start):
+     *     Vc[G] Vv[G] dvdl[2] foreign_E[L+1] foreign_dvdl[(L+1)][2]
+     *   f32 part (fp32 words from its start):
+     *     [0, 3*ntouched)          compact forces, atom k of fepb200_touched_atoms()
+     *     [off_fshift, +3*45)      shift forces                                                  */
     long long f32_words;
     long long f64_words;
     long long off_fshift; /* in f32 words */

@@ -26,6 +26,7 @@
 
 /* what the two files that include this header (pairs.cpp, listed_forces.cpp) do not both include themselves */
 #include "gromacs/math/vec.h"
+#include "gromacs/tables/forcetable.h"
 #include "gromacs/mdtypes/forcerec.h"
 #include "gromacs/mdtypes/group.h"
 #include "gromacs/mdtypes/interaction_const.h"
@@ -47,6 +48,8 @@ struct Handle
     float              lastFudge = 0;
     int                natoms    = -1;
     std::vector<int>   key;      /* {itype, ai, aj} of the perturbed pairs the library holds */
+    std::vector<float> qkey;     /* {qA[ai], qB[ai], qA[aj], qB[aj]} of those pairs as uploaded: same local indices after a
+                                  * repartitioning can be other atoms */
     std::vector<int>   touched;  /* the atoms of those pairs, unique */
     std::vector<int>   gids;     /* the energy-group-pair indices of those pairs, unique */
     int                ngrp = 1; /* largest of them + 1: the size of the library's energy arrays */
@@ -203,6 +206,36 @@ inline bool dispatch(bool                                computeVirial,
     {
         return true; /* nothing takes the branch: nothing to skip either */
     }
+    /* The reference warns about and DROPS pairs beyond the range of its pair table (pairs.cpp:673-684); the library has
+     * no such limit.  A chunk that holds such a pair stays on the reference code, warning included. */
+    if (fr->pairsTable != nullptr)
+    {
+        const real range2 = fr->pairsTable->interactionRange * fr->pairsTable->interactionRange;
+        for (size_t k = 0; k < key.size(); k += 3)
+        {
+            rvec dx;
+            if (fr->bMolPBC)
+            {
+                pbc_dx_aiuc(pbc, x[key[k + 1]], x[key[k + 2]], dx);
+            }
+            else
+            {
+                rvec_sub(x[key[k + 1]], x[key[k + 2]], dx);
+            }
+            if (iprod(dx, dx) >= range2)
+            {
+                return false;
+            }
+        }
+    }
+    /* the charges of both states of the pairs' atoms, part of what identifies the list the library holds */
+    const real*        qBk = chargeB.empty() ? chargeA.data() : chargeB.data();
+    std::vector<float> qkey;
+    qkey.reserve(4 * key.size() / 3);
+    for (size_t k = 0; k < key.size(); k += 3)
+    {
+        qkey.insert(qkey.end(), { chargeA[key[k + 1]], qBk[key[k + 1]], chargeA[key[k + 2]], qBk[key[k + 2]] });
+    }
     fepb200shim::loadSymbols();
     fepb200shim::Api& a  = fepb200shim::api();
     Handle&           hd = handle(key);
@@ -218,7 +251,7 @@ inline bool dispatch(bool                                computeVirial,
     };
     if (!hd.h)
     {
-        const int rc = a.pairs14_create(&hd.h, fepb200shim::nextDevice());
+        const int rc = a.pairs14_create(&hd.h, fepb200shim::deviceForRank(fr->ic.get()));
         if (rc != FEPB200_OK)
         {
             gmx_fatal(FARGS, "fepb200_pairs14_create failed (%d): %s", rc, a.pairs14_last_error(nullptr));
@@ -239,7 +272,7 @@ inline bool dispatch(bool                                computeVirial,
         hd.haveParams = true;
     }
     const int natoms = static_cast<int>(chargeA.size());
-    if (key != hd.key || natoms != hd.natoms)
+    if (key != hd.key || natoms != hd.natoms || qkey != hd.qkey)
     {
         /* the 1-4 types of these pairs, renumbered 0..k-1, with their lj14 parameters */
         std::map<int, int> localType;
@@ -282,6 +315,7 @@ inline bool dispatch(bool                                computeVirial,
                                   hd.ngrp),
               "set_pairs");
         hd.key    = key;
+        hd.qkey   = qkey;
         hd.natoms = natoms;
         hd.fTmp.assign(3 * static_cast<size_t>(natoms), 0.0F);
         hd.uploads++;

@@ -44,7 +44,7 @@ inline void dispatch(const PairlistSets&                              pairlistSe
                      const bool                                       softCore)
 {
     static_assert(sizeof(real) == sizeof(float), "the fepb200 shim needs a mixed-precision build");
-    load();
+    load(&ic);
     Api& a = api();
 
     const double t0 = now();

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "gromacs/utility/fatalerror.h"
@@ -73,14 +75,24 @@ inline Api& api()
     return a;
 }
 
-/* Device of the next context: GMX_FEPB200_DEVICES = number of GPUs to spread the ranks over
- * (rank k of the process gets device k mod that number; default 1 = everything on device 0). */
-inline int nextDevice()
+/* Device of a rank's contexts.  GMX_FEPB200_DEVICES = number of GPUs to spread the ranks over (default 1 = everything on
+ * device 0): the k-th rank to ask gets device k mod that number, and EVERY context of that rank -- the non-bonded one and the
+ * per-OpenMP-thread handles of the perturbed 1-4 pairs -- gets the same one.  A rank is identified by the address of its
+ * interaction_const_t (one per t_forcerec, i.e. per thread-MPI rank; all its OpenMP threads see the same object).  The GPU
+ * route does not come here: it passes the device GROMACS assigned to the rank (fepb200_gpu_shim.h). */
+inline int deviceForRank(const void* rankKey)
 {
-    static std::atomic<int> next{ 0 };
-    const char*             e = std::getenv("GMX_FEPB200_DEVICES");
-    const int               n = e ? std::atoi(e) : 1;
-    return next.fetch_add(1) % (n > 0 ? n : 1);
+    static std::mutex                 mutex;
+    static std::map<const void*, int> assigned;
+    std::lock_guard<std::mutex>       guard(mutex);
+    auto                              it = assigned.find(rankKey);
+    if (it == assigned.end())
+    {
+        const char* e = std::getenv("GMX_FEPB200_DEVICES");
+        const int   n = e ? std::atoi(e) : 1;
+        it            = assigned.emplace(rankKey, static_cast<int>(assigned.size()) % (n > 0 ? n : 1)).first;
+    }
+    return it->second;
 }
 
 inline Api::~Api()
@@ -153,7 +165,7 @@ inline void loadSymbols()
 }
 
 /* ... and the context of the CPU route of this thread */
-inline void load()
+inline void load(const void* rankKey)
 {
     Api& a = api();
     if (a.tried)
@@ -162,7 +174,7 @@ inline void load()
     }
     a.tried = true;
     loadSymbols();
-    const int rc = a.create(&a.ctx, nextDevice());
+    const int rc = a.create(&a.ctx, deviceForRank(rankKey));
     if (rc != FEPB200_OK)
     {
         gmx_fatal(FARGS, "fepb200_create failed (%d): %s", rc, a.last_error(nullptr));

@@ -202,3 +202,28 @@ def test_atomic_outputs_with_a_second_stream_really_adding_into_the_same_array()
     finally:
         a.close()
         b.close()
+
+
+def test_launch_on_a_stream_of_the_caller_s_is_ordered_against_the_context_s_stream(ctx):
+    """fepb200_launch(ctx, flags, stream) with a stream that is not the context's: the staging copy of upload_x (context
+    stream) must have landed before the kernels start, and the consumers (add_forces_device, download: context stream) must
+    wait for the kernels.  A long-running kernel in front of the staging copy makes a missing dependency visible."""
+    import torch
+
+    prob = make_system(scaled_spec("C2", 3.2, 1, 20, n_foreign=4))
+    ctx.set_problem(prob)
+    want = ctx.compute(prob.x, prob.shiftvec, ALL)
+    other = torch.cuda.Stream()
+    x2 = prob.x + np.float32(0.01)
+    want2 = ctx.compute(x2, prob.shiftvec, ALL)
+    assert not np.array_equal(want["f"], want2["f"])
+    d_f = torch.zeros((prob.natoms, 3), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for x, w in ((prob.x, want), (x2, want2), (prob.x, want)):
+        ctx.upload_x(x, prob.shiftvec)
+        ctx.launch(ALL, stream=other.cuda_stream)
+        ctx.add_forces_device(d_f.data_ptr(), P.CLEAR_OUTPUTS)
+        got = ctx.download(ALL & ~P.DO_FORCE)
+        ctx.wait()
+        assert np.array_equal(d_f.cpu().numpy(), w["f"])
+        assert np.array_equal(got["Vc"], w["Vc"]) and np.array_equal(got["foreign_energy"], w["foreign_energy"])

@@ -41,7 +41,7 @@ def test_cluster_pairs_through_the_library_inside_mdrun(system, tmp_path):
     with open(os.path.join(out, "mdrun_nb_dropin_timing.txt"), "a") as fh:
         shim = [ln for ln in via[0].splitlines() if ln.startswith("fepb200 nb shim:")]
         fh.write(f"{system}: md.log 'Nonbonded F' per call: reference kernel_gpu_ref {_wall_ms(a, 'Nonbonded F')} ms, "
-                 f"through libfepb200 {_wall_ms(b, 'Nonbonded F')} ms; {shim[-1] if shim else ''}\n")
+                 f"through libfepb200 {_wall_ms(b, 'Nonbonded F')} ms ('Force': {_wall_ms(a, 'Force')} vs {_wall_ms(b, 'Force')} ms); {shim[-1] if shim else ''}\n")
 
 
 def test_all_short_range_pairs_through_the_library(tmp_path):

@@ -3,7 +3,7 @@
 set -u
 out=gpurun_out/r02_call22
 mkdir -p $out
-timeout 900 python -m pytest -q -m gpu tests/test_gpu_nb.py -p no:cacheprovider -x > $out/pytest_nb.log 2>&1
+timeout 1200 python -m pytest -q -m gpu tests/test_gpu_nb.py tests/test_mdrun_nb.py -p no:cacheprovider -x > $out/pytest_nb.log 2>&1
 echo "pytest nb rc=$?"; tail -5 $out/pytest_nb.log | cut -c1-400
 for c in C3 C2; do
 timeout 600 python tools/nb_bench.py $c --steps 20 > $out/nb_$c.json 2> $out/nb_$c.err; echo "nb bench $c rc=$?"; cat $out/nb_$c.json | cut -c1-1200; tail -3 $out/nb_$c.err
