@@ -300,7 +300,7 @@ def _nb_beside(args):
     cmd = [sys.executable, os.path.join(ROOT, "tools", "nb_bench.py"), "C3", "--steps", "20"]
     try:
         out = {}
-        for key, extra in (("force", []), ("force_energy_virial", ["--energy"])):
+        for key, extra in (("force", ["--cpu-baseline", "--fork-gpu"]), ("force_energy_virial", ["--energy", "--fork-gpu"])):
             r = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=600)
             lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             if r.returncode != 0 or not lines:

@@ -26,6 +26,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -126,11 +127,6 @@ __device__ __forceinline__ float nb_ewald_B(float w)
     return p * nb_rcp(q);
 }
 
-__device__ __forceinline__ void nb_prefetch_l1(const void* p)
-{
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
 struct F3
 {
     float x, y, z;
@@ -176,9 +172,17 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
     }
     const bool  inlj = SAMECUT ? in : (in && (r2c < c.rv2));
     const float r6   = bit ? rinv2 * rinv2 * rinv2 : 0.0f;
-    const float v6   = cc.x * r6;
-    const float v12  = cc.y * r6 * r6;
-    const float flj  = (v12 - v6) * rinv2;
+    float       v6 = 0.0f, v12 = 0.0f, flj;
+    if (ENERGY)
+    {
+        v6  = cc.x * r6;
+        v12 = cc.y * r6 * r6;
+        flj = (v12 - v6) * rinv2;
+    }
+    else
+    {
+        flj = fmaf(cc.y, r6, -cc.x) * (r6 * rinv2); /* (12 C12 r^-12 - 6 C6 r^-6) r^-2 */
+    }
     if (SAMECUT)
     {
         fs = in ? fs + flj : 0.0f;
@@ -206,10 +210,17 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
 
 #define FULL 0xffffffffu
 
-template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbArgs a)
+constexpr int ATOMS_SC = CL * NCL; /* 64 atoms per super-cluster */
+
+/* MINB: CTAs per SM the register allocation aims at -- 4 (128 registers: every per-lane constant stays in a register) or
+ * 5 (96: a fifth CTA per SM, at the price of recomputing some of them in every i-cluster block) */
+template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fep_nb_kernel(const NbArgs a)
 {
-    extern __shared__ float2 s_nbfp[];
+    /* per warp: the 64 i atoms of its item (shifted x, y, z and epsfac q; type row offset); then the LJ table */
+    extern __shared__ float4 s_dyn[];
+    int*    s_ti_all = reinterpret_cast<int*>(s_dyn + WARPS_PER_CTA * ATOMS_SC);
+    float2* s_nbfp   = reinterpret_cast<float2*>(s_ti_all + WARPS_PER_CTA * ATOMS_SC);
     if (TABSMEM)
     {
         for (int k = threadIdx.x; k < a.c.ntype * a.c.ntype; k += blockDim.x)
@@ -222,6 +233,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
     const int lane   = threadIdx.x & 31;
     const int ii     = lane & 7;
     const int jq     = lane >> 3;
+    float4*   s_xi   = s_dyn + (threadIdx.x >> 5) * ATOMS_SC;
+    int*      s_ti   = s_ti_all + (threadIdx.x >> 5) * ATOMS_SC;
     const NbConsts& c = a.c;
 
     /* items differ in cost (how many of the 8 x 4 cluster pairs of a packed entry are listed): every warp takes the next
@@ -246,63 +259,86 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
         const int            ci0   = e.sci * NCL;
         const bool           centr = e.shift == CENTRAL_SHIFT;
 
-        float xi[NCL], yi[NCL], zi[NCL], qi[NCL];
-        int   ti[NCL];
-        F3    fi[NCL];
+        /* the first packed entry and the atoms of its first j-cluster are on their way while the i atoms are staged */
+        int          g    = it.cj_begin;
+        int4         cjv  = __ldg(a.cj + 2 * g);
+        int4         ime  = __ldg(a.cj + 2 * g + 1);
+        unsigned int wex0 = __ldg(&a.excl[ime.y].pair[lane]);
+        unsigned int wex1 = __ldg(&a.excl[ime.w].pair[lane]);
+        int          cjn_n = cjv.x;
+        float4       xa_n  = __ldg(a.xq + cjn_n * CL + jq);
+        float4       xb_n  = __ldg(a.xq + cjn_n * CL + jq + CL / 2);
+        int          ta_n  = __ldg(a.type + cjn_n * CL + jq);
+        int          tb_n  = __ldg(a.type + cjn_n * CL + jq + CL / 2);
+
+        /* i atoms: two per lane, coalesced, into this warp's shared-memory block */
+        __syncwarp();
         float q2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ATOMS_SC / 32; k++)
+        {
+            const int ia = ci0 * CL + lane + 32 * k;
+            float4    v  = __ldg(a.xq + ia);
+            q2           = fmaf(v.w, v.w, q2);
+            v.x += shx;
+            v.y += shy;
+            v.z += shz;
+            v.w *= c.epsfac;
+            s_xi[lane + 32 * k] = v;
+            s_ti[lane + 32 * k] = c.ntype * __ldg(a.type + ia);
+        }
+        __syncwarp();
+        F3 fi[NCL];
 #pragma unroll
         for (int im = 0; im < NCL; im++)
         {
-            const int    ia = (ci0 + im) * CL + ii;
-            const float4 v  = __ldg(a.xq + ia);
-            xi[im]          = v.x + shx;
-            yi[im]          = v.y + shy;
-            zi[im]          = v.z + shz;
-            qi[im]          = c.epsfac * v.w;
-            q2              = fmaf(v.w, v.w, q2);
-            ti[im]          = c.ntype * __ldg(a.type + ia);
             fi[im].x = fi[im].y = fi[im].z = 0.0f;
         }
         float e_el = 0.0f, e_lj = 0.0f;
-        if (ENERGY && it.self && jq == 0)
+        if (ENERGY && it.self)
         {
-            e_el = c.self_coef * q2;
+            e_el = c.self_coef * q2; /* every lane holds two of the 64 atoms */
         }
 
-        for (int g = it.cj_begin; g < it.cj_end; g++)
+        for (; g < it.cj_end; g++)
         {
-            const int4         cjv   = __ldg(a.cj + 2 * g);
-            const int4         ime   = __ldg(a.cj + 2 * g + 1);
+            /* the next packed entry is fetched a whole entry ahead, its exclusion words half an entry ahead */
+            const bool   more  = g + 1 < it.cj_end;
+            int4         cjv_n = cjv, ime_n = ime;
+            unsigned int wex0_n = wex0, wex1_n = wex1;
+            if (more)
+            {
+                cjv_n = __ldg(a.cj + 2 * (g + 1));
+                ime_n = __ldg(a.cj + 2 * (g + 1) + 1);
+            }
             const unsigned int imask = (unsigned int)ime.x;
-            const unsigned int wex0  = __ldg(&a.excl[ime.y].pair[lane]);
-            const unsigned int wex1  = __ldg(&a.excl[ime.w].pair[lane]);
             /* NOT unrolled: the body below (8 i-clusters x 2 atom pairs, straight line) is 14 KB of code; four copies
              * of it do not fit the 32 KB instruction cache level and the warps of an SM then wait for fetches */
 #pragma unroll 1
             for (int jm = 0; jm < FEPB200_NB_JGROUP_SIZE; jm++)
             {
+                /* this j-cluster's two atoms per lane were loaded one j-cluster ago; now the next one's */
+                const int    cjn = cjn_n;
+                const float4 xa = xa_n, xb = xb_n;
+                const int    ta = ta_n, tb = tb_n;
+                const int    ja = cjn * CL + jq;
+                if (jm < 3 || more)
+                {
+                    cjn_n = jm == 0 ? cjv.y : (jm == 1 ? cjv.z : (jm == 2 ? cjv.w : cjv_n.x));
+                    xa_n  = __ldg(a.xq + cjn_n * CL + jq);
+                    xb_n  = __ldg(a.xq + cjn_n * CL + jq + CL / 2);
+                    ta_n  = __ldg(a.type + cjn_n * CL + jq);
+                    tb_n  = __ldg(a.type + cjn_n * CL + jq + CL / 2);
+                }
+                if (jm == 2 && more)
+                {
+                    wex0_n = __ldg(&a.excl[ime_n.y].pair[lane]);
+                    wex1_n = __ldg(&a.excl[ime_n.w].pair[lane]);
+                }
                 const unsigned int m8 = (imask >> (NCL * jm)) & 0xffu;
                 if (m8 == 0)
                 {
                     continue;
-                }
-                const int    cjn = jm == 0 ? cjv.x : (jm == 1 ? cjv.y : (jm == 2 ? cjv.z : cjv.w));
-                const int    ja  = cjn * CL + jq;
-                const float4 xa  = __ldg(a.xq + ja);
-                const float4 xb  = __ldg(a.xq + ja + CL / 2);
-                const int    ta  = __ldg(a.type + ja);
-                const int    tb  = __ldg(a.type + ja + CL / 2);
-                {
-                    /* the atoms of the next j-cluster -- of this packed entry, or the first of the next one, whose 32 bytes
-                     * follow this one's -- on their way into L1 while this one is evaluated: one 128-byte line of
-                     * coordinates, one 32-byte sector of types */
-                    const int* nxt = reinterpret_cast<const int*>(a.cj + 2 * g) + (jm < 3 ? jm + 1 : 8);
-                    if (jm < 3 || g + 1 < it.cj_end)
-                    {
-                        const int cjp = __ldg(nxt);
-                        nb_prefetch_l1(a.xq + cjp * CL + (lane & 7));
-                        nb_prefetch_l1(a.type + cjp * CL + (lane & 7));
-                    }
                 }
                 F3           fa = { 0.0f, 0.0f, 0.0f }, fb = { 0.0f, 0.0f, 0.0f };
                 const unsigned int ea = wex0 >> (NCL * jm), eb = wex1 >> (NCL * jm);
@@ -317,9 +353,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
                 {
                     if (m8 & (1u << im))
                     {
-                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, xi[im], yi[im], zi[im], qi[im], ti[im], xa, ta,
+                        const float4 vi = s_xi[im * CL + ii];
+                        const int    ti = s_ti[im * CL + ii];
+                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, vi.x, vi.y, vi.z, vi.w, ti, xa, ta,
                                                                  (ea >> im) & 1u, (ska >> im) & 1u, fi[im], fa, e_el, e_lj);
-                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, xi[im], yi[im], zi[im], qi[im], ti[im], xb, tb,
+                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, vi.x, vi.y, vi.z, vi.w, ti, xb, tb,
                                                                  (eb >> im) & 1u, (skb >> im) & 1u, fi[im], fb, e_el, e_lj);
                     }
                 }
@@ -346,6 +384,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbA
                     atomicAdd(a.f + 3 * (size_t)atom + comp, sum);
                 }
             }
+            cjv  = cjv_n;
+            ime  = ime_n;
+            wex0 = wex0_n;
+            wex1 = wex1_n;
         }
 
         /* shift force of the item: everything its i atoms received */
@@ -553,7 +595,10 @@ int nb_launch(fepb200_nb* h, const float4* d_xq, int flags, float* d_f, float* d
     if (h->nitems > 0)
     {
         NB_CUDA(cudaMemsetAsync(h->d_next, 0, sizeof(unsigned int), h->stream));
-        const int per_sm = 4;
+        /* four CTAs of four warps per SM with 122 registers per thread; FEPB200_NB_CTAS_PER_SM=5 selects the 96-register
+         * build (A/B on C3: 0.175 ms against 0.209 ms, profiles/r02_nb_kernel_variants.txt) */
+        const char* env    = std::getenv("FEPB200_NB_CTAS_PER_SM");
+        const int   per_sm = (env && std::atoi(env) == 5) ? 5 : 4;
         int       grid   = (h->nitems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         if (grid > h->sm_count * per_sm)
         {
@@ -564,10 +609,13 @@ int nb_launch(fepb200_nb* h, const float4* d_xq, int flags, float* d_f, float* d
         const size_t tab    = sizeof(float2) * h->ntype * h->ntype;
         const bool   smem   = tab <= 16384;
         const int    which  = (h->ewald ? 8 : 0) | (energy ? 4 : 0) | (same ? 2 : 0) | (smem ? 1 : 0);
-        const size_t shared = smem ? tab : 0;
+        const size_t shared = WARPS_PER_CTA * ATOMS_SC * (sizeof(float4) + sizeof(int)) + (smem ? tab : 0);
 #define NB_CASE(E, V, S, T)                                                                  \
     case ((E) ? 8 : 0) | ((V) ? 4 : 0) | ((S) ? 2 : 0) | ((T) ? 1 : 0):                      \
-        fep_nb_kernel<E, V, S, T><<<grid, block, shared, h->stream>>>(a);                    \
+        if (per_sm == 4)                                                                     \
+            fep_nb_kernel<E, V, S, T, 4><<<grid, block, shared, h->stream>>>(a);             \
+        else                                                                                 \
+            fep_nb_kernel<E, V, S, T, 5><<<grid, block, shared, h->stream>>>(a);             \
         break;
         switch (which)
         {

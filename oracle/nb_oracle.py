@@ -165,3 +165,43 @@ def mask_perturbed(xq, typ, ntype, atoms):
     lib.nbo_mask_perturbed(_pd(xq.reshape(-1)), typ.ctypes.data_as(ctypes.c_void_p), int(ntype), int(atoms.shape[0]),
                            atoms.ctypes.data_as(ctypes.c_void_p))
     return xq, typ
+
+
+# ---- the reference's own CUDA cluster-pair kernels, compiled in place for sm_100a (GPU baseline; needs a GPU) ----
+FORK_CUDA_LIB = os.path.join(REF_DIR, "libnbfork_cuda.so")
+_FP = ctypes.POINTER(ctypes.c_float)
+
+
+class ForkParams(ctypes.Structure):
+    _fields_ = [("eeltype", ctypes.c_int)] + [(n, ctypes.c_double) for n in (
+        "epsfac", "rcoulomb", "rvdw", "krf", "crf", "sh_ewald", "ewaldcoeff_q", "dispersion_cpot", "repulsion_cpot")]  # fmt: skip
+
+
+def have_fork_cuda() -> bool:
+    return os.path.exists(FORK_CUDA_LIB)
+
+
+def run_fork_cuda(cs, params, *, energy=False, repeats=5):
+    """oracle/_ref/libnbfork_cuda.so: nbnxn_kernel_Elec{Ew,RF}_VdwLJ_{F,VF}_cuda of the reference on the same list.
+    Returns dict(f, fshift, vc, vvdw, ms) -- ms = device time of the kernel alone, warm caches, best of `repeats`."""
+    lib = ctypes.CDLL(FORK_CUDA_LIB)
+    p = ForkParams(int(params.eeltype), params.epsfac, params.rcoulomb, params.rvdw, params.reactionFieldCoefficient,
+                   params.reactionFieldShift, params.sh_ewald, params.ewaldcoeff_q, params.dispersion_shift_cpot,
+                   params.repulsion_shift_cpot)
+    xq = np.ascontiguousarray(cs.xq, np.float32)
+    typ = np.ascontiguousarray(cs.type, np.int32)
+    nbfp = _d(cs.nbfp)
+    sv = np.ascontiguousarray(cs.shiftvec, np.float32)
+    sci, cj, excl = np.ascontiguousarray(cs.sci), np.ascontiguousarray(cs.cj), np.ascontiguousarray(cs.excl)
+    f = np.zeros((cs.natoms, 3), np.float32)
+    fsh = np.zeros((45, 3), np.float32)
+    e = np.zeros(2, np.float32)
+    ms = ctypes.c_float(0)
+    rc = lib.nbfork_run(ctypes.byref(p), cs.ntype, _pd(nbfp), cs.natoms, xq.ctypes.data_as(_FP),
+                        typ.ctypes.data_as(ctypes.c_void_p), sci.shape[0], sci.ctypes.data_as(ctypes.c_void_p), cj.shape[0],
+                        cj.ctypes.data_as(ctypes.c_void_p), excl.shape[0], excl.ctypes.data_as(ctypes.c_void_p),
+                        sv.ctypes.data_as(_FP), int(energy), int(repeats), f.ctypes.data_as(_FP), fsh.ctypes.data_as(_FP),
+                        e.ctypes.data_as(_FP), ctypes.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"nbfork_run failed ({rc})")
+    return dict(f=f.astype(np.float64), fshift=fsh.astype(np.float64), vvdw=float(e[0]), vc=float(e[1]), ms=float(ms.value))

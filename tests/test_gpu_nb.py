@@ -230,3 +230,26 @@ def test_medium_system_properties(nb):
     assert np.max(np.abs(a["f"] - b["f"])) <= 4e-6 * scale
     assert abs(a["vc"] - b["vc"]) <= 1e-9 * abs(a["vc"]) + 1e-3
     assert nb.cluster_pairs == cs.n_cluster_pairs > 1_000_000
+
+
+def test_reference_cuda_kernel_on_the_same_list(nb):
+    """The reference's own CUDA cluster-pair kernel (nbnxm_cuda_kernel.cuh compiled in place, oracle/_ref/libnbfork_cuda.so)
+    on the same list and the same B200: a second, independent implementation of the reference that must agree with the
+    oracle and with us (its analytical Ewald is the reference's own rational fit, ours is another: 5e-6 rel-RMS)."""
+    if not nb_oracle.have_fork_cuda():
+        pytest.skip("oracle/_ref/libnbfork_cuda.so not built")
+    for case in ("ewald", "rf"):
+        pr, cs = _system(**CASES[case])
+        nb.setup(cs, pr.params)
+        want = nb_oracle.run_port(cs, pr.params, table=None)
+        fork = nb_oracle.run_fork_cuda(cs, pr.params, energy=True, repeats=2)
+        ours = nb.compute(cs.xq[:, :3], cs.shiftvec, ALL)
+        for got in (fork, ours):
+            rms = np.sqrt(np.mean((np.asarray(got["f"], np.float64) - want["f"]) ** 2) / np.mean(want["f"] ** 2))
+            assert rms <= 5e-6, (case, rms)
+            assert abs(got["vc"] - want["vc"]) <= 5e-5 * abs(want["vc"]) and abs(got["vvdw"] - want["vvdw"]) <= 5e-5 * abs(want["vvdw"])
+        # the CUDA kernel leaves out the shift force of the central cell, which multiplies a zero shift vector in the virial
+        # (nbnxm_cuda_kernel.cuh: `if (nb_sci.shift == c_centralShiftIndex) bCalcFshift = false`)
+        rows = np.arange(45) != 22
+        assert not fork["fshift"][22].any()
+        assert np.max(np.abs(fork["fshift"][rows] - want["fshift"][rows])) <= 1e-4 * np.max(np.abs(want["fshift"][rows]))

@@ -20,7 +20,7 @@ for p in (os.path.join(ROOT, "gromacs-fep-gpu_b200", "python"), ROOT):
 FLOP_PER_PAIR = {("ewald", False): 66, ("ewald", True): 107, ("rf", False): 38, ("rf", True): 54}
 
 
-def run(name="C3", steps=20, warmup=3, energy=False, cache_dir=None):
+def run(name="C3", steps=20, warmup=3, energy=False, cpu_baseline=False, fork_gpu=False):
     import torch
 
     from fepb200 import params as P
@@ -62,6 +62,38 @@ def run(name="C3", steps=20, warmup=3, energy=False, cache_dir=None):
                flop_per_listed_atom_pair=FLOP_PER_PAIR[(elec, energy)],
                algorithmic_tflops=evals * FLOP_PER_PAIR[(elec, energy)] / (ms.mean() * 1e-3) / 1e12)
     nb.close()
+    if cpu_baseline:
+        # the reference's own kernel for these lists (kernel_gpu_ref.cpp compiled in place, mixed precision, plain C, one
+        # thread -- it has no threaded or SIMD variant), timed on this host on the same list
+        from oracle import nb_oracle
+
+        if nb_oracle.have_ref("sp"):
+            r = nb_oracle.run_ref(cs, pr.params, energy=energy, precision="sp", repeats=2)
+            out["cpu_baseline"] = dict(kind="reference", cores=1, ms=r["seconds"] * 1e3,
+                                       atom_pair_evals_per_s=evals / r["seconds"],
+                                       sample=f"the whole {name} list, best of 2",
+                                       what="nbnxn_kernel_gpu_ref (oracle/_ref/libnbref_sp.so)")
+        else:
+            out["cpu_baseline"] = dict(unavailable="oracle/_ref/libnbref_sp.so not built")
+    if fork_gpu:
+        # the reference's own CUDA cluster-pair kernel on this GPU and this list (compiled in place for sm_100a); its lists
+        # are split on the host for load balance (nbnxm/pairlist.cpp: sci entries of at most a few packed j entries), so it
+        # gets the list cut into the same chunk sizes our work items have
+        from oracle import nb_oracle
+
+        if nb_oracle.have_fork_cuda():
+            cs_split = synth_nb.build_cluster_system(pr, rlist=1.1, max_cj_groups_per_sci=16)
+            best = None
+            for label, c in (("list as searched", cs), ("entries split at 16 packed j entries", cs_split)):
+                r = nb_oracle.run_fork_cuda(c, pr.params, energy=energy, repeats=10)
+                if best is None or r["ms"] < best["ms"]:
+                    best = dict(ms=r["ms"], list=label, atom_pair_evals_per_s=evals / (r["ms"] * 1e-3))
+            best["what"] = ("nbnxn_kernel_Elec%s_VdwLJ_%s_cuda of the reference (nbnxm_cuda_kernel.cuh compiled in place, "
+                            "oracle/_ref/libnbfork_cuda.so), kernel only, warm caches, best of 10 -- ours above has the L2 "
+                            "flushed before every launch" % ("Ew" if elec == "ewald" else "RF", "VF" if energy else "F"))
+            out["reference_gpu_kernel"] = best
+        else:
+            out["reference_gpu_kernel"] = dict(unavailable="oracle/_ref/libnbfork_cuda.so not built")
     return out, cs, pr
 
 
@@ -71,6 +103,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--energy", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--fork-gpu", action="store_true")
     a = ap.parse_args()
-    out, _, _ = run(a.name, a.steps, a.warmup, a.energy)
+    out, _, _ = run(a.name, a.steps, a.warmup, a.energy, a.cpu_baseline, a.fork_gpu)
     print(json.dumps(out))
