@@ -489,6 +489,20 @@ __global__ void fep_nb_mask_kernel(int n, const int* __restrict__ atoms, int dum
     }
 }
 
+/* {vc, vvdw} of the handle's accumulator added into the float buffers the fork's nbnxm GPU module reduces from
+ * (NBAtomDataGpu::eElec, eLJ) */
+__global__ void fep_nb_export_energies_kernel(const double* __restrict__ e, float* eLJ, float* eElec)
+{
+    if (threadIdx.x == 0 && eElec != nullptr)
+    {
+        atomicAdd(eElec, (float)e[0]);
+    }
+    if (threadIdx.x == 1 && eLJ != nullptr)
+    {
+        atomicAdd(eLJ, (float)e[1]);
+    }
+}
+
 thread_local std::string g_nb_create_error;
 
 } // namespace
@@ -573,13 +587,14 @@ bool full_electrostatics(int eeltype)
     return (eeltype >= 3 && eeltype <= 6) || (eeltype >= 13 && eeltype <= 15);
 }
 
-int nb_launch(fepb200_nb* h, const float4* d_xq, int flags, float* d_f, float* d_fshift, double* d_energies)
+int nb_launch(fepb200_nb* h, const float4* d_xq, const float* d_shift, int flags, float* d_f, float* d_fshift,
+              double* d_energies)
 {
     NbArgs a;
     a.xq       = d_xq;
     a.type     = h->d_type;
     a.nbfp     = h->d_nbfp;
-    a.shiftvec = h->d_shift;
+    a.shiftvec = d_shift;
     a.sci      = h->d_sci;
     a.cj       = reinterpret_cast<const int4*>(h->d_cj);
     a.excl     = h->d_excl;
@@ -1045,7 +1060,7 @@ int fepb200_nb_launch_device(fepb200_nb* h, const float* d_xq, const float* shif
     {
         return nb_fail(h, FEPB200_ERR_INVALID_ARGUMENT, "d_xq and d_f must be given");
     }
-    if (((flags & FEPB200_DO_SHIFTFORCE) && d_fshift == nullptr) || ((flags & FEPB200_DO_POTENTIAL) && d_energies == nullptr))
+    if ((flags & FEPB200_DO_SHIFTFORCE) && d_fshift == nullptr)
     {
         return nb_fail(h, FEPB200_ERR_INVALID_ARGUMENT, "an output selected by flags is NULL");
     }
@@ -1055,9 +1070,24 @@ int fepb200_nb_launch_device(fepb200_nb* h, const float* d_xq, const float* shif
         return rc;
     }
     NB_CUDA(cudaSetDevice(h->device));
-    if ((rc = nb_upload_shift(h, shiftvec)) != FEPB200_OK)
+    const float* d_shift = h->d_shift;
+    if (flags & FEPB200_NB_SHIFTVEC_ON_DEVICE)
+    {
+        if (shiftvec == nullptr)
+        {
+            return nb_fail(h, FEPB200_ERR_INVALID_ARGUMENT, "shiftvec is NULL");
+        }
+        d_shift = shiftvec;
+    }
+    else if ((rc = nb_upload_shift(h, shiftvec)) != FEPB200_OK)
     {
         return rc;
+    }
+    if ((flags & FEPB200_DO_POTENTIAL) && d_energies == nullptr)
+    {
+        /* the handle's own accumulator, for fepb200_nb_export_energies_device() */
+        NB_CUDA(cudaMemsetAsync(h->d_energies, 0, 2 * sizeof(double), h->stream));
+        d_energies = h->d_energies;
     }
     const float4* xq = reinterpret_cast<const float4*>(d_xq);
     if (!(flags & FEPB200_NB_Q_FROM_XQ))
@@ -1067,7 +1097,20 @@ int fepb200_nb_launch_device(fepb200_nb* h, const float* d_xq, const float* shif
         h->launches++;
         xq = h->d_xq;
     }
-    return nb_launch(h, xq, flags, d_f, d_fshift, d_energies);
+    return nb_launch(h, xq, d_shift, flags, d_f, d_fshift, d_energies);
+}
+
+int fepb200_nb_export_energies_device(fepb200_nb* h, float* d_eLJ, float* d_eElec)
+{
+    if (h == nullptr)
+    {
+        return FEPB200_ERR_INVALID_ARGUMENT;
+    }
+    NB_CUDA(cudaSetDevice(h->device));
+    fep_nb_export_energies_kernel<<<1, 32, 0, h->stream>>>(h->d_energies, d_eLJ, d_eElec);
+    NB_CUDA(cudaGetLastError());
+    h->launches++;
+    return FEPB200_OK;
 }
 
 static int nb_compute_host(fepb200_nb* h, const float* x, int xstride, const float* shiftvec, int flags, float* f,
@@ -1130,7 +1173,7 @@ static int nb_compute_host(fepb200_nb* h, const float* x, int xstride, const flo
     NB_CUDA(cudaMemsetAsync(h->d_f, 0, n3 * sizeof(float), h->stream));
     NB_CUDA(cudaMemsetAsync(h->d_fshift, 0, sizeof(h->h_shift), h->stream));
     NB_CUDA(cudaMemsetAsync(h->d_energies, 0, 2 * sizeof(double), h->stream));
-    if ((rc = nb_launch(h, h->d_xq, flags, h->d_f, h->d_fshift, (flags & FEPB200_DO_POTENTIAL) ? h->d_energies : nullptr))
+    if ((rc = nb_launch(h, h->d_xq, h->d_shift, flags, h->d_f, h->d_fshift, (flags & FEPB200_DO_POTENTIAL) ? h->d_energies : nullptr))
         != FEPB200_OK)
     {
         return rc;

@@ -14,6 +14,7 @@ from .params import CParams, DO_FORCE, DO_POTENTIAL, DO_SHIFTFORCE, CLEAR_OUTPUT
 
 _FP, _DP, _IP, _VP = L._FP, L._DP, L._IP, L._VP
 NB_Q_FROM_XQ = 1 << 20
+NB_SHIFTVEC_ON_DEVICE = 1 << 21
 
 # every symbol include/fepb200_nb.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -30,6 +31,7 @@ SYMBOLS = {
     "fepb200_nb_compute": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, _FP, _DP, _DP]),
     "fepb200_nb_compute_xyzq": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, _FP, _DP, _DP]),
     "fepb200_nb_launch_device": (ctypes.c_int, [_VP, _VP, _FP, ctypes.c_int, _VP, _VP, _VP]),
+    "fepb200_nb_export_energies_device": (ctypes.c_int, [_VP, _VP, _VP]),
     "fepb200_nb_wait": (ctypes.c_int, [_VP]),
     "fepb200_nb_launch_count": (ctypes.c_longlong, [_VP]),
     "fepb200_nb_last_kernel_ms": (ctypes.c_int, [_VP, _FP]),
@@ -145,6 +147,15 @@ class NbContext:
         self._check(self._lib.fepb200_nb_launch_device(self._h, _VP(d_xq), L._pf(sv), int(flags), _VP(d_f),
                                                        _VP(d_fshift) if d_fshift else None,
                                                        _VP(d_energies) if d_energies else None))
+
+    def launch_device_raw(self, d_xq: int, d_shiftvec: int, flags, d_f: int, d_fshift: int = 0, d_energies: int = 0) -> None:
+        """As launch_device, with the shift vectors on the device (flags must carry NB_SHIFTVEC_ON_DEVICE)."""
+        self._check(self._lib.fepb200_nb_launch_device(self._h, _VP(d_xq), ctypes.cast(_VP(d_shiftvec), _FP), int(flags), _VP(d_f),
+                                                       _VP(d_fshift) if d_fshift else None,
+                                                       _VP(d_energies) if d_energies else None))
+
+    def export_energies_device(self, d_elj: int, d_eelec: int) -> None:
+        self._check(self._lib.fepb200_nb_export_energies_device(self._h, _VP(d_elj), _VP(d_eelec)))
 
     def wait(self) -> None:
         self._check(self._lib.fepb200_nb_wait(self._h))

@@ -91,6 +91,7 @@ int fepb200_nb_set_pairlist(fepb200_nb* h, int nsci, const fepb200_nb_sci* sci, 
 
 /* ---- the hot call ------------------------------------------------------ */
 #define FEPB200_NB_Q_FROM_XQ (1 << 20) /* extension bit: charges come from the .w of the caller's xyzq array */
+#define FEPB200_NB_SHIFTVEC_ON_DEVICE (1 << 21) /* fepb200_nb_launch_device: shiftvec is a device pointer (NBAtomDataGpu::shiftVec) */
 /* One evaluation with host buffers: x = rvec[natoms] in grid order (what nbnxn_atomdata_copy_x_to_nbat_x produces),
  * shiftvec rvec[45].  flags: FEPB200_DO_FORCE (always implied), FEPB200_DO_SHIFTFORCE, FEPB200_DO_POTENTIAL,
  * FEPB200_CLEAR_OUTPUTS.  Outputs are ACCUMULATED like the reference kernel does with clearF = enbvClearFNo:
@@ -109,6 +110,10 @@ int fepb200_nb_compute_xyzq(fepb200_nb* h, const float* xq, const float* shiftve
  * shiftvec is a HOST pointer (uploaded when it changed).  Asynchronous on the handle's stream. */
 int fepb200_nb_launch_device(fepb200_nb* h, const float* d_xq, const float* shiftvec, int flags, float* d_f,
                              float* d_fshift, double* d_energies);
+/* With FEPB200_DO_POTENTIAL and d_energies == NULL the launch accumulates {vc, vvdw} in a buffer of the handle's; this adds
+ * them (atomically) into the float buffers the fork's nbnxm GPU module copies back and reduces (NBAtomDataGpu::eLJ, eElec;
+ * nbnxm/gpu_types_common.h:120-122, gpu_common.h:139-191).  Asynchronous on the handle's stream. */
+int fepb200_nb_export_energies_device(fepb200_nb* h, float* d_eLJ, float* d_eElec);
 int fepb200_nb_wait(fepb200_nb* h);
 
 /* Evidence for bench.py: kernel launches so far, device time of the last cluster kernel (CUDA events on the launching

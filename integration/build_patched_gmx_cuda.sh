@@ -22,6 +22,8 @@ cp /root/reference/src/gromacs/listed_forces/listed_forces.cpp "$SRC/src/gromacs
 # ... and the hooks in the fork's GPU route (mdrun -nb gpu -fep gpu + GMX_FEPB200: libfepb200 instead of k_calc_nb_fep*)
 for f in src/gromacs/nbnxm/nbnxm_gpu_data_mgmt.cpp src/gromacs/nbnxm/cuda/nbnxm_cuda.cu src/gromacs/mdlib/sim_util.cpp; do cp "/root/reference/$f" "$SRC/$f"; done
 (cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/nbnxm_gpu_fepb200.patch")
+# ... and, on top of them, the hooks for the cluster-pair kernel of the library (GMX_FEPB200_NB: fepb200_nb_* instead of nbnxn_kernel_*_cuda)
+(cd "$SRC" && patch -p1 < "$ROOT/integration/gromacs_shim/nbnxm_gpu_nb_fepb200.patch")
 mkdir -p "$BUILD"
 cmake -G Ninja -S "$SRC" -B "$BUILD" -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ \
   -DCMAKE_POLICY_VERSION_MINIMUM=3.5 -DGMX_GPU=CUDA -DGMX_CUDA_TARGET_SM=100 -DCUDA_TOOLKIT_ROOT_DIR=/usr/local/cuda -DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc -DGMX_MPI=OFF -DGMX_THREAD_MPI=ON -DGMX_OPENMP=ON \

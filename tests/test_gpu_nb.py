@@ -253,3 +253,30 @@ def test_reference_cuda_kernel_on_the_same_list(nb):
         rows = np.arange(45) != 22
         assert not fork["fshift"][22].any()
         assert np.max(np.abs(fork["fshift"][rows] - want["fshift"][rows])) <= 1e-4 * np.max(np.abs(want["fshift"][rows]))
+
+
+def test_device_shift_vectors_and_energies_into_float_buffers(nb):
+    """What a hook in the fork's GPU route hands over: shift vectors on the device (NBAtomDataGpu::shiftVec), masked charges in
+    xq.w, energies added into the fork's float accumulators eLJ / eElec."""
+    import torch
+
+    from fepb200.nb import NB_Q_FROM_XQ, NB_SHIFTVEC_ON_DEVICE
+
+    pr, cs = _system(**CASES["ewald"])
+    nb.setup(cs, pr.params)
+    d_xq = torch.from_numpy(cs.xq).cuda()
+    d_sv = torch.from_numpy(np.ascontiguousarray(cs.shiftvec, np.float32)).cuda()
+    d_f = torch.zeros((cs.natoms, 3), dtype=torch.float32, device="cuda")
+    d_fs = torch.zeros(135, dtype=torch.float32, device="cuda")
+    d_e = torch.full((2,), 0.5, dtype=torch.float32, device="cuda")  # {eLJ, eElec}, not cleared by us
+    torch.cuda.synchronize()
+    flags = ALL | NB_Q_FROM_XQ | NB_SHIFTVEC_ON_DEVICE
+    nb.launch_device_raw(d_xq.data_ptr(), d_sv.data_ptr(), flags, d_f.data_ptr(), d_fs.data_ptr(), 0)
+    nb.export_energies_device(d_e.data_ptr(), d_e.data_ptr() + 4)
+    nb.wait()
+    want = nb_oracle.run_port(cs, pr.params, table=None)
+    _check(dict(f=d_f.cpu().numpy()), want)
+    e = d_e.cpu().numpy().astype(np.float64)
+    assert abs(e[0] - 0.5 - want["vvdw"]) <= 1e-5 * abs(want["vvdw"]) and abs(e[1] - 0.5 - want["vc"]) <= 1e-5 * abs(want["vc"])
+    fsh = d_fs.cpu().numpy().reshape(45, 3)
+    assert np.max(np.abs(fsh - want["fshift"])) <= 2e-5 * np.max(np.abs(want["fshift"]))

@@ -1,0 +1,57 @@
+"""The cluster-pair kernel of libfepb200.so INSIDE the fork's GPU route (`mdrun -nb gpu`): with GMX_FEPB200_NB set the hook of
+integration/gromacs_shim/nbnxm_gpu_nb_fepb200.patch replaces the launch of the fork's nbnxn_kernel_*_cuda
+(nbnxm/cuda/nbnxm_cuda.cu:738-750) by fepb200_nb_launch_device on the nbnxm stream: coordinates (adat->xq, charges masked in
+.w), shift vectors, forces (adat->f), shift forces and energies (adat->eLJ / eElec) stay in the fork's device buffers.
+
+  (a) mdrun -nb gpu -fep gpu                                 the fork's own kernels (cluster pairs + perturbed pairs)
+  (b) the same with GMX_FEPB200_NB=1                          cluster pairs through libfepb200
+  (c) the same with GMX_FEPB200_NB=1 and GMX_FEPB200=1        EVERY short-range non-bonded pair through libfepb200, device-
+                                                              resident, both kernels adding into the fork's adat->f
+(b) and (c) must reproduce (a) step by step at the tolerance of the reference's own mdrun free-energy test; (c) also the
+reference's CPU FEP route.  The fork's GPU timing table ("Nonbonded F kernel" rows of md.log) is noted for (a) and (b)."""
+import os
+
+import pytest
+
+import test_mdrun_dropin as T
+from test_mdrun_gpu_route import GMX_CUDA, TIMING
+from test_nb_shim_cpu import compare_nb_runs
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(GMX_CUDA), reason="integration/_gmx_cuda not built")]
+
+
+def _gpu_rows(workdir):
+    rows = []
+    for line in open(os.path.join(workdir, "run.log")):
+        if "Nonbonded F" in line or "FEP kernel" in line or "Pruning kernel" in line:
+            rows.append(" ".join(line.split()))
+    return rows
+
+
+@pytest.mark.parametrize("system", ["coulandvdwtogether", "c1_methane", "c2_hexadecane"])
+def test_cluster_pairs_through_the_library_inside_the_forks_gpu_route(system, tmp_path):
+    tpr = os.path.join(T.TPR, system + ".tpr")
+    a, b, c = str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "c")
+    try:
+        fork = T._run(tpr, a, False, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=TIMING)
+    except AssertionError as exc:
+        pytest.skip("the fork's CUDA build does not run here: " + str(exc)[-400:])
+    ours = T._run(tpr, b, False, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=dict(TIMING, GMX_FEPB200_NB="1"))
+    assert "non-perturbed cluster pairs (GPU route) are computed by libfepb200" in ours[0]
+    assert "fepb200 nb GPU route:" in ours[0]
+    compare_nb_runs(system, fork, ours, (a, b))
+    both = T._run(tpr, c, True, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=dict(TIMING, GMX_FEPB200_NB="1"))
+    assert "non-perturbed cluster pairs (GPU route)" in both[0] and "GPU route" in both[0] and "fepb200 GPU route:" in both[0]
+    compare_nb_runs(system, fork, both, (a, c))
+    note = [f"{system}: mdrun -nb gpu -fep gpu, GPU timing rows of md.log",
+            "  the fork's own kernels:          " + " | ".join(_gpu_rows(a)),
+            "  cluster pairs through libfepb200: " + " | ".join(_gpu_rows(b)),
+            "  all pairs through libfepb200:     " + " | ".join(_gpu_rows(c))]
+    note += ["  " + ln for ln in both[0].splitlines() if ln.startswith("fepb200 nb GPU route:")]
+    print("\n".join(note))
+    try:
+        with open(os.path.join(T.ROOT, "gpurun_out", "mdrun_nb_gpu_route_timing.txt"), "a") as fh:
+            fh.write("\n".join(note) + "\n")
+    except OSError:
+        pass
