@@ -115,6 +115,17 @@ inline Api& api()
     return a;
 }
 
+/* said once when a run stays with the fork's kernel although GMX_FEPB200_NB is set */
+inline void noteDeclined(const char* why)
+{
+    static thread_local bool said = false;
+    if (!said)
+    {
+        std::fprintf(stderr, "NOTE: GMX_FEPB200_NB is set but the cluster pairs stay on the fork's kernel: %s\n", why);
+        said = true;
+    }
+}
+
 /* one state per NbnxmGpu (= per rank) */
 inline State& state(const void* nb)
 {
