@@ -28,9 +28,11 @@ SYMBOLS = {
     "fepb200_nb_mask_perturbed": (ctypes.c_int, [_VP, ctypes.c_int, _IP]),
     "fepb200_nb_get_atoms": (ctypes.c_int, [_VP, _IP, _FP]),
     "fepb200_nb_set_pairlist": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, ctypes.c_int, _VP]),
+    "fepb200_nb_use_device_list": (ctypes.c_int, [_VP, _VP, _VP, _VP]),
     "fepb200_nb_compute": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, _FP, _DP, _DP]),
     "fepb200_nb_compute_xyzq": (ctypes.c_int, [_VP, _FP, _FP, ctypes.c_int, _FP, _FP, _DP, _DP]),
     "fepb200_nb_launch_device": (ctypes.c_int, [_VP, _VP, _FP, ctypes.c_int, _VP, _VP, _VP]),
+    "fepb200_nb_launch_device_float_energies": (ctypes.c_int, [_VP, _VP, _FP, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "fepb200_nb_export_energies_device": (ctypes.c_int, [_VP, _VP, _VP]),
     "fepb200_nb_wait": (ctypes.c_int, [_VP]),
     "fepb200_nb_launch_count": (ctypes.c_longlong, [_VP]),
@@ -110,6 +112,10 @@ class NbContext:
         self._check(self._lib.fepb200_nb_set_pairlist(self._h, int(sci.shape[0]), sci.ctypes.data_as(_VP), int(cj.shape[0]),
                                                       cj.ctypes.data_as(_VP), int(excl.shape[0]), excl.ctypes.data_as(_VP)))
 
+    def use_device_list(self, d_sci: int, d_cj: int, d_excl: int) -> None:
+        self._check(self._lib.fepb200_nb_use_device_list(self._h, _VP(d_sci) if d_sci else None, _VP(d_cj) if d_cj else None,
+                                                         _VP(d_excl) if d_excl else None))
+
     def setup(self, cs, params, mask: bool = True) -> None:
         """Everything of a `synth_nb.ClusterSystem`: constants, unmasked atoms, the mask, the list."""
         self.set_params(params)
@@ -153,6 +159,11 @@ class NbContext:
         self._check(self._lib.fepb200_nb_launch_device(self._h, _VP(d_xq), ctypes.cast(_VP(d_shiftvec), _FP), int(flags), _VP(d_f),
                                                        _VP(d_fshift) if d_fshift else None,
                                                        _VP(d_energies) if d_energies else None))
+
+    def launch_device_float_energies(self, d_xq: int, d_shiftvec: int, flags, d_f: int, d_fshift: int, d_elj: int, d_eelec: int) -> None:
+        self._check(self._lib.fepb200_nb_launch_device_float_energies(
+            self._h, _VP(d_xq), ctypes.cast(_VP(d_shiftvec), _FP), int(flags), _VP(d_f), _VP(d_fshift) if d_fshift else None,
+            _VP(d_elj) if d_elj else None, _VP(d_eelec) if d_eelec else None))
 
     def export_energies_device(self, d_elj: int, d_eelec: int) -> None:
         self._check(self._lib.fepb200_nb_export_energies_device(self._h, _VP(d_elj), _VP(d_eelec)))

@@ -89,6 +89,14 @@ int fepb200_nb_get_atoms(const fepb200_nb* h, int* type, float* charge);
 int fepb200_nb_set_pairlist(fepb200_nb* h, int nsci, const fepb200_nb_sci* sci, int ncj, const fepb200_nb_cj_packed* cj,
                             int nexcl, const fepb200_nb_excl* excl);
 
+/* Read the list from the CALLER's device copies from now on (until the next fepb200_nb_set_pairlist): d_sci / d_cj / d_excl
+ * must be device arrays with the layout and sizes of the host list given to fepb200_nb_set_pairlist -- the fork's
+ * gpu_plist::sci / cjPacked / excl (nbnxm/gpu_types_common.h:297-340).  The work items stay those of the host list, but the
+ * i-cluster masks are taken from the device copy at kernel time: what the fork's dynamic pruning kernels clear there
+ * (nbnxm/cuda/nbnxm_cuda_kernel_pruneonly.cuh) is skipped here too.  NULL, NULL, NULL: back to the library's own copies. */
+int fepb200_nb_use_device_list(fepb200_nb* h, const fepb200_nb_sci* d_sci, const fepb200_nb_cj_packed* d_cj,
+                               const fepb200_nb_excl* d_excl);
+
 /* ---- the hot call ------------------------------------------------------ */
 #define FEPB200_NB_Q_FROM_XQ (1 << 20) /* extension bit: charges come from the .w of the caller's xyzq array */
 #define FEPB200_NB_SHIFTVEC_ON_DEVICE (1 << 21) /* fepb200_nb_launch_device: shiftvec is a device pointer (NBAtomDataGpu::shiftVec) */
@@ -110,6 +118,11 @@ int fepb200_nb_compute_xyzq(fepb200_nb* h, const float* xq, const float* shiftve
  * shiftvec is a HOST pointer (uploaded when it changed).  Asynchronous on the handle's stream. */
 int fepb200_nb_launch_device(fepb200_nb* h, const float* d_xq, const float* shiftvec, int flags, float* d_f,
                              float* d_fshift, double* d_energies);
+/* The same with the energies added (float atomics, like the fork's own kernels do) straight into the float accumulators the
+ * fork's nbnxm GPU module copies back and reduces (NBAtomDataGpu::eLJ, eElec; nbnxm/gpu_types_common.h:120-122): one kernel
+ * launch per step, nothing else on the stream. */
+int fepb200_nb_launch_device_float_energies(fepb200_nb* h, const float* d_xq, const float* shiftvec, int flags, float* d_f,
+                                            float* d_fshift, float* d_eLJ, float* d_eElec);
 /* With FEPB200_DO_POTENTIAL and d_energies == NULL the launch accumulates {vc, vvdw} in a buffer of the handle's; this adds
  * them (atomically) into the float buffers the fork's nbnxm GPU module copies back and reduces (NBAtomDataGpu::eLJ, eElec;
  * nbnxm/gpu_types_common.h:120-122, gpu_common.h:139-191).  Asynchronous on the handle's stream. */

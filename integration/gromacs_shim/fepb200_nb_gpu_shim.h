@@ -6,13 +6,13 @@
  *   gpu_init_atomdata  (nbnxm_gpu_data_mgmt.cpp:873-988)  -> setAtoms(): masked types + nbfp as the reference holds them
  *   gpu_init_pairlist  (nbnxm_gpu_data_mgmt.cpp:667-759)  -> setList(): NbnxnPairlistGpu::sci / cjPacked / excl of the locality
  *   gpu_launch_kernel  (cuda/nbnxm_cuda.cu:738-750)       -> step(): instead of the launch of nbnxn_kernel_*_cuda
- *        fepb200_nb_launch_device(adat->xq [charges masked in .w], adat->shiftVec, adat->f, adat->fShift)
- *        fepb200_nb_export_energies_device(adat->eLJ, adat->eElec)
+ *        fepb200_nb_launch_device_float_energies(adat->xq [charges masked in .w], adat->shiftVec, adat->f, adat->fShift,
+ *                                                adat->eLJ, adat->eElec)   -- ONE kernel launch per step
  *     on the locality's nbnxm stream, inside the fork's nb_k GPU timer.  Coordinates, forces, shift forces and energies stay
  *     in the fork's device buffers: its copy-back and reduction (gpu_launch_cpyback, gpu_common.h:139-191) run unchanged, and
  *     with GMX_FEPB200 set as well the perturbed pairs are added into the same adat->f by fepb200_gpu_shim.h.
- * The library evaluates the list as the search made it (list radius rlistOuter); the fork's dynamic pruning of its own device
- * copy of the list is not used by this route.  Flavours the library does not cover (LJ switch functions, LJ-PME, combination
+ * The kernel reads the fork's own device copy of the list (fepb200_nb_use_device_list), so the cluster pairs the fork's dynamic
+ * pruning kernels clear there are skipped by it too.  Flavours the library does not cover (LJ switch functions, LJ-PME, combination
  * rules are irrelevant -- plain table look-up) fall through to the fork's kernel: step() returns false.
  */
 #ifndef FEPB200_NB_GPU_SHIM_H
@@ -41,8 +41,10 @@ struct Api
     decltype(&fepb200_nb_set_nbfp)               set_nbfp      = nullptr;
     decltype(&fepb200_nb_set_atoms)              set_atoms     = nullptr;
     decltype(&fepb200_nb_set_pairlist)           set_pairlist  = nullptr;
+    decltype(&fepb200_nb_use_device_list)        use_device_list = nullptr;
     decltype(&fepb200_nb_launch_device)          launch_device = nullptr;
     decltype(&fepb200_nb_export_energies_device) export_energies_device = nullptr;
+    decltype(&fepb200_nb_launch_device_float_energies) launch_device_float_energies = nullptr;
     bool                                         loaded = false;
 };
 
@@ -104,8 +106,10 @@ inline Api& api()
         FEPB200_NB_SYM(set_nbfp);
         FEPB200_NB_SYM(set_atoms);
         FEPB200_NB_SYM(set_pairlist);
+        FEPB200_NB_SYM(use_device_list);
         FEPB200_NB_SYM(launch_device);
         FEPB200_NB_SYM(export_energies_device);
+        FEPB200_NB_SYM(launch_device_float_energies);
 #undef FEPB200_NB_SYM
         if (!a.create || !a.set_stream || !a.set_pairlist || !a.launch_device || !a.export_energies_device)
         {
@@ -176,7 +180,7 @@ inline void setList(const void* nb, int iloc, int nsci, const void* sci, int ncj
 /* gpu_launch_kernel.  Returns false when this launch stays with the fork's kernel. */
 inline bool step(const void* nb, int iloc, int device, void* stream, const fepb200_params& p, bool computeEnergy,
                  bool computeVirial, const float* d_xq, const float* d_shiftVec, float* d_f, float* d_fShift, float* d_eLJ,
-                 float* d_eElec)
+                 float* d_eElec, const void* d_sci, const void* d_cjPacked, const void* d_excl)
 {
     if (!enabled())
     {
@@ -219,14 +223,33 @@ inline bool step(const void* nb, int iloc, int device, void* stream, const fepb2
         check(l, a.set_pairlist(l.h, l.nsci, l.sci, l.ncj, l.cj, l.nexcl, l.excl), "set_pairlist");
         l.listDirty = false;
         l.lists++;
+        /* the kernel reads the FORK's device copy of the list (same structure, uploaded by gpu_init_pairlist on this stream):
+         * the i-cluster masks its dynamic pruning kernels clear are then skipped by our kernel as well.
+         * GMX_FEPB200_NB_OWN_LIST keeps the library's own (unpruned) copy. */
+        if (a.use_device_list && d_sci && d_cjPacked && d_excl && std::getenv("GMX_FEPB200_NB_OWN_LIST") == nullptr)
+        {
+            check(l, a.use_device_list(l.h, static_cast<const fepb200_nb_sci*>(d_sci),
+                                       static_cast<const fepb200_nb_cj_packed*>(d_cjPacked),
+                                       static_cast<const fepb200_nb_excl*>(d_excl)),
+                  "use_device_list");
+        }
     }
     int flags = FEPB200_DO_FORCE | FEPB200_NB_Q_FROM_XQ | FEPB200_NB_SHIFTVEC_ON_DEVICE;
     flags |= computeVirial ? FEPB200_DO_SHIFTFORCE : 0;
     flags |= computeEnergy ? FEPB200_DO_POTENTIAL : 0;
-    check(l, a.launch_device(l.h, d_xq, d_shiftVec, flags, d_f, d_fShift, nullptr), "launch_device");
-    if (computeEnergy)
+    if (a.launch_device_float_energies)
     {
-        check(l, a.export_energies_device(l.h, d_eLJ, d_eElec), "export_energies_device");
+        /* one kernel launch, energies added into the fork's float accumulators by the kernel itself */
+        check(l, a.launch_device_float_energies(l.h, d_xq, d_shiftVec, flags, d_f, d_fShift, d_eLJ, d_eElec),
+              "launch_device_float_energies");
+    }
+    else
+    {
+        check(l, a.launch_device(l.h, d_xq, d_shiftVec, flags, d_f, d_fShift, nullptr), "launch_device");
+        if (computeEnergy)
+        {
+            check(l, a.export_energies_device(l.h, d_eLJ, d_eElec), "export_energies_device");
+        }
     }
     l.steps++;
     return true;

@@ -3,6 +3,7 @@
 
   c1_methane     methane decoupling in a 3.0 nm TIP3P box (~2.7 k atoms), Beutler soft-core
                  (sc-alpha 0.5), PME real space, one lambda (no foreign states)
+  c3_hexadecane  the solute of c2_hexadecane in a 10 nm box (~100 k atoms), same settings (made on request only)
   c2_hexadecane  a 50-atom solute (hexadecane, C16H34) transformed A -> B (hydrogens vanish, carbons
                  become united atoms with half the charge) in a 6.3 nm TIP3P box (~25 k atoms), PME,
                  20 lambda states with foreign-energy output
@@ -314,3 +315,7 @@ if __name__ == "__main__":
         build("c1_methane", 3.0, methane, FEP_C1, VARIANTS_C1)
     if "c2_hexadecane" in which:
         build("c2_hexadecane", 6.3, hexadecane, FEP_C2, VARIANTS_C2)
+    # the same solute in a 10 nm box (~100 k atoms, BASELINE configs[2] in size): for timings inside mdrun at a size where
+    # the kernels, not the launches, dominate (tests/test_mdrun_nb_gpu_route.py)
+    if "c3_hexadecane" in which:
+        build("c3_hexadecane", 10.0, hexadecane, FEP_C2)

@@ -280,3 +280,66 @@ def test_device_shift_vectors_and_energies_into_float_buffers(nb):
     assert abs(e[0] - 0.5 - want["vvdw"]) <= 1e-5 * abs(want["vvdw"]) and abs(e[1] - 0.5 - want["vc"]) <= 1e-5 * abs(want["vc"])
     fsh = d_fs.cpu().numpy().reshape(45, 3)
     assert np.max(np.abs(fsh - want["fshift"])) <= 2e-5 * np.max(np.abs(want["fshift"]))
+    # the same in ONE launch: the kernel adds its energies into the float accumulators itself; three launches in a row use
+    # the two work-queue heads in turn
+    for _ in range(3):
+        d_f.zero_()
+        d_fs.zero_()
+        d_e.fill_(0.5)
+        torch.cuda.synchronize()
+        n0 = nb.launch_count
+        nb.launch_device_float_energies(d_xq.data_ptr(), d_sv.data_ptr(), flags, d_f.data_ptr(), d_fs.data_ptr(), d_e.data_ptr(),
+                                        d_e.data_ptr() + 4)
+        nb.wait()
+        assert nb.launch_count == n0 + 1
+        _check(dict(f=d_f.cpu().numpy()), want)
+        e = d_e.cpu().numpy().astype(np.float64)
+        assert abs(e[0] - 0.5 - want["vvdw"]) <= 2e-5 * abs(want["vvdw"]) and abs(e[1] - 0.5 - want["vc"]) <= 2e-5 * abs(want["vc"])
+
+
+def test_list_read_from_the_caller_s_device_copy_with_pruned_masks(nb):
+    """fepb200_nb_use_device_list: the kernel reads the caller's device copy of the list (the fork's gpu_plist) -- work items from
+    the host list, i-cluster masks from the device copy at kernel time.  The fork's pruning kernels clear mask bits there, per
+    HALF of a cluster pair (each of its two warps prunes its own half): the kernel must take the union of the two halves."""
+    import copy
+
+    import torch
+
+    from fepb200.nb import NB_Q_FROM_XQ
+
+    pr, cs = _system(**CASES["ewald"])
+    nb.setup(cs, pr.params)
+    rng = np.random.default_rng(3)
+    cj = cs.cj.copy()
+    n = cj.shape[0]
+    pick = rng.random(n)
+    drop = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    a = pick < 0.3  # one half pruned away, the other kept: nothing may change for these
+    cj["imask0"][a] &= drop[a]
+    b = (pick >= 0.3) & (pick < 0.6)  # both halves pruned alike: these cluster pairs are gone
+    cj["imask0"][b] &= drop[b]
+    cj["imask1"][b] &= drop[b]
+    pruned = copy.copy(cs)
+    pruned.cj = cs.cj.copy()
+    pruned.cj["imask0"] = cj["imask0"] | cj["imask1"]
+    pruned.cj["imask1"] = pruned.cj["imask0"]
+    want = nb_oracle.run_port(pruned, pr.params, table=None, energy=False)
+    full = nb_oracle.run_port(cs, pr.params, table=None, energy=False)
+    assert np.max(np.abs(want["f"] - full["f"])) > 1e-3 * np.max(np.abs(full["f"]))  # the pruning does remove interactions
+    d_sci = torch.from_numpy(cs.sci.view(np.int32).reshape(-1, 4).copy()).cuda()
+    d_cj = torch.from_numpy(cj.view(np.int32).reshape(-1, 8).copy()).cuda()
+    d_excl = torch.from_numpy(cs.excl.view(np.int32).reshape(-1, 32).copy()).cuda()
+    d_xq = torch.from_numpy(cs.xq).cuda()
+    d_f = torch.zeros((cs.natoms, 3), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    nb.use_device_list(d_sci.data_ptr(), d_cj.data_ptr(), d_excl.data_ptr())
+    nb.launch_device(d_xq.data_ptr(), cs.shiftvec, P.DO_FORCE | NB_Q_FROM_XQ, d_f.data_ptr())
+    nb.wait()
+    _check(dict(f=d_f.cpu().numpy()), want, "pruned device list")
+    # back to the library's own copy of the host list
+    nb.use_device_list(0, 0, 0)
+    d_f.zero_()
+    torch.cuda.synchronize()
+    nb.launch_device(d_xq.data_ptr(), cs.shiftvec, P.DO_FORCE | NB_Q_FROM_XQ, d_f.data_ptr())
+    nb.wait()
+    _check(dict(f=d_f.cpu().numpy()), full, "own list")

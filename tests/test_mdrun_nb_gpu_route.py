@@ -71,12 +71,15 @@ def test_uncovered_flavour_stays_with_the_forks_kernel(tmp_path):
     compare_nb_runs("coulandvdwtogether", fork, ours, (a, b))
 
 
-def test_steady_state_timing_beside_the_forks_kernel(tmp_path):
-    """The fork's own GPU timing table for its cluster kernel and for ours inside the same route, c2_hexadecane (24.5 k atoms),
-    600 steps with the counters reset half way (context creation and the first list hand-over are not in the rows).  A
-    measurement: it fails only if a run fails.  Note that the fork's kernel works on its dynamically pruned device list, ours on
-    the list as searched (list radius rlistOuter)."""
-    tpr = os.path.join(T.TPR, "c2_hexadecane.tpr")
+@pytest.mark.parametrize("system", ["c2_hexadecane", "c3_hexadecane"])
+def test_steady_state_timing_beside_the_forks_kernel(system, tmp_path):
+    """The fork's own GPU timing table for its cluster kernel and for ours inside the same route -- c2_hexadecane (24.5 k atoms)
+    and c3_hexadecane (the same solute in a 10 nm box, 100 k atoms) -- 600 steps with the counters reset half way (context
+    creation and the first list hand-over are not in the rows).  A measurement: it fails only if a run fails.  Both kernels work
+    on the fork's dynamically pruned device list (fepb200_nb_use_device_list)."""
+    tpr = os.path.join(T.TPR, system + ".tpr")
+    if not os.path.exists(tpr):
+        pytest.skip(system + ".tpr not made (integration/systems/make_systems.py " + system + ")")
     args = ("-nsteps", "600", "-resethway")
     a, b = str(tmp_path / "a"), str(tmp_path / "b")
     try:
@@ -84,7 +87,7 @@ def test_steady_state_timing_beside_the_forks_kernel(tmp_path):
     except AssertionError as exc:
         pytest.skip("the fork's CUDA build does not run here: " + str(exc)[-400:])
     ours = T._run(tpr, b, True, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env=dict(TIMING, GMX_FEPB200_NB="1"), mdrun_args=args)
-    note = ["c2_hexadecane, 600 steps, counters reset half way (steady state), GPU timing rows of md.log:",
+    note = [system + ", 600 steps, counters reset half way (steady state), GPU timing rows of md.log:",
             "  the fork's own kernels:       " + " | ".join(_gpu_rows(a)),
             "  all pairs through libfepb200: " + " | ".join(_gpu_rows(b))]
     note += ["  " + ln for ln in ours[0].splitlines() if ln.startswith(("fepb200 nb GPU route:", "fepb200 GPU route:"))]

@@ -1,9 +1,9 @@
 #!/bin/bash
 set -u
-out=gpurun_out/r02_call28
+out=gpurun_out/r02_call30
 mkdir -p $out
-timeout 1500 python -m pytest -q -m gpu tests/test_gpu_direct_forces.py tests/test_gpu_parity.py tests/test_gpu_device_handoff.py -p no:cacheprovider -x -rA > $out/pytest.log 2>&1
+timeout 1500 python -m pytest -q -m gpu tests/test_gpu_nb.py tests/test_mdrun_nb_gpu_route.py -p no:cacheprovider -x -rA > $out/pytest.log 2>&1
 echo "pytest rc=$?"; grep -E "^(PASSED|FAILED|ERROR|SKIPPED)" $out/pytest.log | cut -d' ' -f1 | sort | uniq -c; grep -E "^(FAILED|ERROR)" $out/pytest.log | cut -c1-250; grep -E "^E  " $out/pytest.log | head -20 | cut -c1-300
 cat gpurun_out/direct_forces_timing.txt 2>/dev/null
-timeout 900 python -m pytest -q -m gpu tests/test_mdrun_nb_gpu_route.py -k steady -p no:cacheprovider -x > $out/pytest_nb_route.log 2>&1; echo "nb route steady rc=$?"
+
 tail -6 gpurun_out/mdrun_nb_gpu_route_timing.txt | cut -c1-500
