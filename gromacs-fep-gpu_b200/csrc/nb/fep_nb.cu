@@ -130,6 +130,11 @@ __device__ __forceinline__ float nb_ewald_B(float w)
     return p * nb_rcp(q);
 }
 
+#ifndef NB_ROWSKIP
+#define NB_ROWSKIP 1
+#endif
+#define FULL 0xffffffffu
+
 struct F3
 {
     float x, y, z;
@@ -147,6 +152,14 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
     const float  dx = xi - xj.x, dy = yi - xj.y, dz = zi - xj.z;
     const float  r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
     const bool   in = (r2 < c.rc2) && !skip;
+#if NB_ROWSKIP
+    /* the 32 atom pairs of this warp instruction (8 i atoms x 4 j atoms) are often all outside the cut-off -- a list is
+     * made with a buffer around it: then the whole evaluation is skipped (one vote, one uniform branch) */
+    if (!__any_sync(FULL, in))
+    {
+        return;
+    }
+#endif
     const float  r2c   = fmaxf(r2, MIN_RSQ);
     const float  rinv  = nb_rsqrt(r2c);
     const float  rinv2 = rinv * rinv;
@@ -211,7 +224,6 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
     fj.z = fmaf(-fs, dz, fj.z);
 }
 
-#define FULL 0xffffffffu
 
 constexpr int ATOMS_SC = CL * NCL; /* 64 atoms per super-cluster */
 
