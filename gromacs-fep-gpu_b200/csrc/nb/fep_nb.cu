@@ -57,6 +57,9 @@ struct NbConsts
     float sh_ewald, beta, beta2, beta3;
     float disp_cpot, rep_cpot;
     float self_coef; /* -epsfac beta / sqrt(pi)  or  -epsfac c_rf / 2 */
+    /* Lennard-Jones modifiers of the reference's CUDA kernels (nbnxm_cuda_kernel_utils.cuh:104-211): force switch
+     * (dispersion / repulsion c2, c3 of mdtypes/interaction_const.cpp:216-230) and potential switch (c3, c4, c5 of :232-245) */
+    float rvdw_switch, dsp_c2, dsp_c3, rep_c2, rep_c3, sw_c3, sw_c4, sw_c5;
     int   ntype;
 };
 
@@ -144,7 +147,7 @@ struct F3
  * correction); `skip`: lower triangle of a cluster against itself in the central cell.  Everything a pair can be ruled out by
  * is a select on the result, never a factor: a pair far outside the cut-off (filler atoms) may produce inf / NaN on the way.
  * SAMECUT: rvdw == rcoulomb, one test for both.  `nb`: the {6 C6, 12 C12} table, in shared memory when TABSMEM. */
-template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM>
+template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM, int VDWMOD>
 __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restrict__ nb, float xi, float yi, float zi,
                                         float qi, int ti, const float4& xj, int tj, bool bit, bool skip, F3& fi, F3& fj,
                                         float& e_el, float& e_lj)
@@ -188,16 +191,40 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
     }
     const bool  inlj = SAMECUT ? in : (in && (r2c < c.rv2));
     const float r6   = bit ? rinv2 * rinv2 * rinv2 : 0.0f;
-    float       v6 = 0.0f, v12 = 0.0f, flj;
-    if (ENERGY)
+    float       v6 = 0.0f, v12 = 0.0f, flj, vlj = 0.0f;
+    if (ENERGY || VDWMOD == 2)
     {
         v6  = cc.x * r6;
         v12 = cc.y * r6 * r6;
         flj = (v12 - v6) * rinv2;
+        vlj = fmaf(bit ? cc.y : 0.0f, c.rep_cpot, v12) * (1.0f / 12.0f) - fmaf(bit ? cc.x : 0.0f, c.disp_cpot, v6) * (1.0f / 6.0f);
     }
     else
     {
         flj = fmaf(cc.y, r6, -cc.x) * (r6 * rinv2); /* (12 C12 r^-12 - 6 C6 r^-6) r^-2 */
+    }
+    if (VDWMOD != 0)
+    {
+        /* like the reference's CUDA kernels: cc = {6 C6, 12 C12} are their c6 / c12, the switch terms do not carry the
+         * interaction bit (an excluded pair in the switching region has zero parameters or is a bonded neighbour) */
+        const float sd = fmaxf(fmaf(r2c, rinv, -c.rvdw_switch), 0.0f);
+        if (VDWMOD == 1)
+        {
+            flj += (cc.y * fmaf(c.rep_c3, sd, c.rep_c2) - cc.x * fmaf(c.dsp_c3, sd, c.dsp_c2)) * (sd * sd * rinv);
+            if (ENERGY)
+            {
+                vlj += (cc.x * fmaf(c.dsp_c3 * 0.25f, sd, c.dsp_c2 * (1.0f / 3.0f))
+                        - cc.y * fmaf(c.rep_c3 * 0.25f, sd, c.rep_c2 * (1.0f / 3.0f)))
+                       * (sd * sd * sd);
+            }
+        }
+        else
+        {
+            const float sw  = fmaf(fmaf(fmaf(c.sw_c5, sd, c.sw_c4), sd, c.sw_c3), sd * sd * sd, 1.0f);
+            const float dsw = fmaf(fmaf(5.0f * c.sw_c5, sd, 4.0f * c.sw_c4), sd, 3.0f * c.sw_c3) * (sd * sd);
+            flj             = fmaf(flj, sw, -rinv * vlj * dsw);
+            vlj *= sw;
+        }
     }
     if (SAMECUT)
     {
@@ -212,8 +239,6 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
     {
         /* the reference books the Coulomb energy inside its `rsq < rvdw2` branch (kernel_gpu_ref.cpp:264-287) */
         e_el += inlj ? v_el : 0.0f;
-        const float vlj = fmaf(bit ? cc.y : 0.0f, c.rep_cpot, v12) * (1.0f / 12.0f)
-                          - fmaf(bit ? cc.x : 0.0f, c.disp_cpot, v6) * (1.0f / 6.0f);
         e_lj += inlj ? vlj : 0.0f;
     }
     fi.x = fmaf(fs, dx, fi.x);
@@ -227,10 +252,11 @@ __device__ __forceinline__ void nb_pair(const NbConsts& c, const float2* __restr
 
 constexpr int ATOMS_SC = CL * NCL; /* 64 atoms per super-cluster */
 
-/* MINB: CTAs per SM the register allocation aims at -- 4 (128 registers: every per-lane constant stays in a register) or
- * 5 (96: a fifth CTA per SM, at the price of recomputing some of them in every i-cluster block) */
-template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM, int MINB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fep_nb_kernel(const NbArgs a)
+/* Four CTAs per SM: with 128 registers every per-lane constant stays in a register; a build for five (96 registers)
+ * recomputes some of them in every i-cluster block and was 19 % slower (profiles/r02_nb_kernel_variants.txt).
+ * VDWMOD: 0 plain / potential shift (what nbnxn_kernel_gpu_ref computes), 1 force switch, 2 potential switch. */
+template<bool EWALD, bool ENERGY, bool SAMECUT, bool TABSMEM, int VDWMOD>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fep_nb_kernel(const NbArgs a)
 {
     /* per warp: the 64 i atoms of its item (shifted x, y, z and epsfac q; type row offset); then the LJ table */
     extern __shared__ float4 s_dyn[];
@@ -378,9 +404,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fep_nb_kernel(const 
                     {
                         const float4 vi = s_xi[im * CL + ii];
                         const int    ti = s_ti[im * CL + ii];
-                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, vi.x, vi.y, vi.z, vi.w, ti, xa, ta,
+                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM, VDWMOD>(c, nbtab, vi.x, vi.y, vi.z, vi.w, ti, xa, ta,
                                                                  (ea >> im) & 1u, (ska >> im) & 1u, fi[im], fa, e_el, e_lj);
-                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM>(c, nbtab, vi.x, vi.y, vi.z, vi.w, ti, xb, tb,
+                        nb_pair<EWALD, ENERGY, SAMECUT, TABSMEM, VDWMOD>(c, nbtab, vi.x, vi.y, vi.z, vi.w, ti, xb, tb,
                                                                  (eb >> im) & 1u, (skb >> im) & 1u, fi[im], fb, e_el, e_lj);
                     }
                 }
@@ -544,6 +570,7 @@ struct fepb200_nb
     cudaEvent_t    ev0 = nullptr, ev1 = nullptr;
     std::string    error;
     NbConsts       c{};
+    int            vdwmod = 0; /* 0 none / potential shift, 1 force switch, 2 potential switch */
     bool           ewald = false, have_params = false, have_nbfp = false, have_atoms = false, have_list = false;
     int            natoms = 0, ntype = 0, nsci = 0, ncj = 0, nexcl = 0, nitems = 0;
     long long      cluster_pairs = 0, launches = 0;
@@ -648,10 +675,7 @@ int nb_launch(fepb200_nb* h, const float4* d_xq, const float* d_shift, int flags
     NB_CUDA(cudaEventRecord(h->ev0, h->stream));
     if (h->nitems > 0)
     {
-        /* four CTAs of four warps per SM with 122 registers per thread; FEPB200_NB_CTAS_PER_SM=5 selects the 96-register
-         * build (A/B on C3: 0.175 ms against 0.209 ms, profiles/r02_nb_kernel_variants.txt) */
-        const char* env    = std::getenv("FEPB200_NB_CTAS_PER_SM");
-        const int   per_sm = (env && std::atoi(env) == 5) ? 5 : 4;
+        const int per_sm = 4;
         int       grid   = (h->nitems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         if (grid > h->sm_count * per_sm)
         {
@@ -663,12 +687,14 @@ int nb_launch(fepb200_nb* h, const float4* d_xq, const float* d_shift, int flags
         const bool   smem   = tab <= 16384;
         const int    which  = (h->ewald ? 8 : 0) | (energy ? 4 : 0) | (same ? 2 : 0) | (smem ? 1 : 0);
         const size_t shared = WARPS_PER_CTA * ATOMS_SC * (sizeof(float4) + sizeof(int)) + (smem ? tab : 0);
-#define NB_CASE(E, V, S, T)                                                                  \
-    case ((E) ? 8 : 0) | ((V) ? 4 : 0) | ((S) ? 2 : 0) | ((T) ? 1 : 0):                      \
-        if (per_sm == 4)                                                                     \
-            fep_nb_kernel<E, V, S, T, 4><<<grid, block, shared, h->stream>>>(a);             \
-        else                                                                                 \
-            fep_nb_kernel<E, V, S, T, 5><<<grid, block, shared, h->stream>>>(a);             \
+#define NB_CASE(E, V, S, T)                                                                          \
+    case ((E) ? 8 : 0) | ((V) ? 4 : 0) | ((S) ? 2 : 0) | ((T) ? 1 : 0):                              \
+        if (h->vdwmod == 1)                                                                          \
+            fep_nb_kernel<E, V, S, T, 1><<<grid, block, shared, h->stream>>>(a);                     \
+        else if (h->vdwmod == 2)                                                                     \
+            fep_nb_kernel<E, V, S, T, 2><<<grid, block, shared, h->stream>>>(a);                     \
+        else                                                                                         \
+            fep_nb_kernel<E, V, S, T, 0><<<grid, block, shared, h->stream>>>(a);                     \
         break;
         switch (which)
         {
@@ -843,6 +869,28 @@ int fepb200_nb_set_params(fepb200_nb* h, const fepb200_params* ic)
     c.beta3     = c.beta2 * c.beta;
     c.disp_cpot = ic->dispersion_shift_cpot;
     c.rep_cpot  = ic->repulsion_shift_cpot;
+    /* vdw_modifier: force switch / potential switch select the Lennard-Jones modifiers of the reference's CUDA kernels; every
+     * other value gives what nbnxn_kernel_gpu_ref computes (plain LJ, the two cpot constants shift the energy) */
+    h->vdwmod     = ic->vdw_modifier == FEPB200_MOD_FORCESWITCH ? 1 : (ic->vdw_modifier == FEPB200_MOD_POTSWITCH ? 2 : 0);
+    c.rvdw_switch = ic->rvdw_switch;
+    c.dsp_c2 = c.dsp_c3 = c.rep_c2 = c.rep_c3 = c.sw_c3 = c.sw_c4 = c.sw_c5 = 0.0f;
+    if (h->vdwmod != 0)
+    {
+        const double rsw = ic->rvdw_switch, rc = ic->rvdw, d = rc - rsw;
+        if (!(rsw >= 0.0) || !(d > 0.0))
+        {
+            return nb_fail(h, FEPB200_ERR_INVALID_ARGUMENT, "a switched Lennard-Jones needs 0 <= rvdw_switch < rvdw");
+        }
+        auto fsw = [&](double p, float* c2, float* c3) { /* interaction_const.cpp:216-230 */
+            *c2 = (float)(((p + 1) * rsw - (p + 4) * rc) / (std::pow(rc, p + 2) * d * d));
+            *c3 = (float)(-((p + 1) * rsw - (p + 3) * rc) / (std::pow(rc, p + 2) * d * d * d));
+        };
+        fsw(6.0, &c.dsp_c2, &c.dsp_c3);
+        fsw(12.0, &c.rep_c2, &c.rep_c3);
+        c.sw_c3 = (float)(-10.0 / (d * d * d)); /* interaction_const.cpp:232-245 */
+        c.sw_c4 = (float)(15.0 / (d * d * d * d));
+        c.sw_c5 = (float)(-6.0 / (d * d * d * d * d));
+    }
     if (h->ewald)
     {
         if (c.beta2 * c.rc2 > 16.0f)

@@ -69,7 +69,11 @@ int fepb200_nb_set_stream(fepb200_nb* h, void* stream);
 
 /* Constants: eeltype (cut-off / RF -> reaction field, PME / Ewald family -> Ewald real space, as usingFullElectrostatics),
  * epsfac, rcoulomb, rvdw, reactionFieldCoefficient, reactionFieldShift, sh_ewald, ewaldcoeff_q, dispersion/repulsion
- * shift (kernel_gpu_ref.cpp:88-101,226-287).  The soft-core fields are ignored. */
+ * shift (kernel_gpu_ref.cpp:88-101,226-287).  The soft-core fields are ignored.
+ * vdw_modifier = FEPB200_MOD_FORCESWITCH or FEPB200_MOD_POTSWITCH (with rvdw_switch) selects the Lennard-Jones force / potential
+ * switch the way the reference's CUDA kernels apply it (nbnxm/cuda/nbnxm_cuda_kernel_utils.cuh:104-211, constants of
+ * mdtypes/interaction_const.cpp:216-245); nbnxn_kernel_gpu_ref itself knows no switch, and every other value of vdw_modifier
+ * -- 0 included -- gives its arithmetic: plain LJ, the two cpot constants shifting the energy. */
 int fepb200_nb_set_params(fepb200_nb* h, const fepb200_params* ic);
 /* nbat->params().nbfp: {6*C6, 12*C12} for ntype x ntype types; type ntype-1 is the non-interacting type that filler atoms
  * and masked perturbed atoms carry and must have zero parameters (atomdata.cpp:930-964). */

@@ -53,7 +53,21 @@ typedef struct
     double tab_scale; /* Ewald force table, linear interpolation (kernel_gpu_ref.cpp:239-246); */
     int    tab_size;  /* tab_size == 0: the analytical function the table samples                */
     const double* tableF;
+    /* Lennard-Jones modifiers of the reference's CUDA kernels, which nbnxn_kernel_gpu_ref does not have
+     * (nbnxm/cuda/nbnxm_cuda_kernel_utils.cuh:104-211, applied at nbnxm_cuda_kernel.cuh:560-590):
+     * 0 none / potential shift only, 1 force switch, 2 potential switch */
+    int    vdw_switch_kind;
+    double rvdw_switch;
 } nbo_params;
+
+/* force-switch constants for r^-p (mdtypes/interaction_const.cpp:216-230) */
+void nbo_force_switch_constants(double p, double rsw, double rc, double* c2, double* c3, double* cpot)
+{
+    const double d = rc - rsw;
+    *c2            = ((p + 1) * rsw - (p + 4) * rc) / (pow(rc, p + 2) * d * d);
+    *c3            = -((p + 1) * rsw - (p + 3) * rc) / (pow(rc, p + 2) * d * d * d);
+    *cpot          = -pow(rc, -p) + p * *c2 / 3 * d * d * d + p * *c3 / 4 * d * d * d * d;
+}
 
 static int full_electrostatics(int eeltype)
 {
@@ -194,11 +208,38 @@ int nbo_run(int natoms, const double* xq, const int* type, int ntype, const doub
                             const double  r6  = bit * rinv2 * rinv2 * rinv2;
                             const double  v6  = c[0] * r6;
                             const double  v12 = c[1] * r6 * r6;
-                            fs += (v12 - v6) * rinv2;
+                            double        f_lj = (v12 - v6) * rinv2; /* force / r */
+                            double        v_lj = (v12 + bit * c[1] * p->rep_cpot) / 12.0 - (v6 + bit * c[0] * p->disp_cpot) / 6.0;
+                            if (p->vdw_switch_kind != 0)
+                            {
+                                /* c[0] = 6 C6, c[1] = 12 C12 are what the CUDA kernel calls c6, c12; like there, the
+                                 * switch terms are not multiplied by the interaction bit */
+                                const double r = r2 * rinv;
+                                double       sd = r - p->rvdw_switch;
+                                sd              = sd > 0.0 ? sd : 0.0;
+                                if (p->vdw_switch_kind == 1)
+                                {
+                                    double d2, d3, q2, q3, cp;
+                                    nbo_force_switch_constants(6.0, p->rvdw_switch, p->rvdw, &d2, &d3, &cp);
+                                    nbo_force_switch_constants(12.0, p->rvdw_switch, p->rvdw, &q2, &q3, &cp);
+                                    f_lj += (-c[0] * (d2 + d3 * sd) + c[1] * (q2 + q3 * sd)) * sd * sd * rinv;
+                                    v_lj += (c[0] * (d2 / 3 + d3 / 4 * sd) - c[1] * (q2 / 3 + q3 / 4 * sd)) * sd * sd * sd;
+                                }
+                                else
+                                {
+                                    const double d   = p->rvdw - p->rvdw_switch;
+                                    const double c3  = -10.0 / (d * d * d), c4 = 15.0 / (d * d * d * d), c5 = -6.0 / (d * d * d * d * d);
+                                    const double sw  = 1.0 + (c3 + (c4 + c5 * sd) * sd) * sd * sd * sd;
+                                    const double dsw = (3 * c3 + (4 * c4 + 5 * c5 * sd) * sd) * sd * sd;
+                                    f_lj             = f_lj * sw - rinv * v_lj * dsw;
+                                    v_lj *= sw;
+                                }
+                            }
+                            fs += f_lj;
                             /* the reference books the Coulomb energy only for pairs inside the LJ cut-off
                              * (kernel_gpu_ref.cpp:264-287: `vctot += vcoul` sits in the `rsq < rvdw2` branch) */
                             e_el += v_el;
-                            e_lj += (v12 + bit * c[1] * p->rep_cpot) / 12.0 - (v6 + bit * c[0] * p->disp_cpot) / 6.0;
+                            e_lj += v_lj;
                         }
                         fi[0] += fs * dx;
                         fi[1] += fs * dy;

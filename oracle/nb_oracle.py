@@ -32,7 +32,8 @@ _DP = ctypes.POINTER(ctypes.c_double)
 class PortParams(ctypes.Structure):
     _fields_ = [("eeltype", ctypes.c_int)] + [(n, ctypes.c_double) for n in (
         "epsfac", "rcoulomb", "rvdw", "rlist", "k_rf", "c_rf", "sh_ewald", "beta", "disp_cpot", "rep_cpot",
-        "min_rsq", "tab_scale")] + [("tab_size", ctypes.c_int), ("tableF", _DP)]  # fmt: skip
+        "min_rsq", "tab_scale")] + [("tab_size", ctypes.c_int), ("tableF", _DP), ("vdw_switch_kind", ctypes.c_int),
+                                     ("rvdw_switch", ctypes.c_double)]  # fmt: skip
 
 
 class RefParams(ctypes.Structure):
@@ -108,14 +109,21 @@ def _outputs(natoms):
     return np.zeros((natoms, 3)), np.zeros((45, 3)), ctypes.c_double(0), ctypes.c_double(0)
 
 
-def run_port(cs, params, *, energy=True, table=None, min_rsq=MIN_RSQ_FLOAT, repeats=1):
+def switch_kind(params) -> int:
+    """0: none / potential shift, 1: force switch, 2: potential switch (InteractionModifiers 5 / 3) -- the modifiers of the
+    reference's CUDA kernels; nbnxn_kernel_gpu_ref itself ignores them."""
+    return {5: 1, 3: 2}.get(int(params.vdw_modifier), 0)
+
+
+def run_port(cs, params, *, energy=True, table=None, min_rsq=MIN_RSQ_FLOAT, repeats=1, cuda_modifiers=False):
+    """cuda_modifiers: apply the Lennard-Jones force / potential switch the way the reference's CUDA kernels do."""
     lib = _load_port()
     xq, typ, nbfp, sv, sci, cj, excl = _common(cs)
     scale, n, tab = _table_for(params, table)
     p = PortParams(int(params.eeltype), params.epsfac, params.rcoulomb, params.rvdw, cs.rlist,
                    params.reactionFieldCoefficient, params.reactionFieldShift, params.sh_ewald, params.ewaldcoeff_q,
                    params.dispersion_shift_cpot, params.repulsion_shift_cpot, min_rsq, scale, n,
-                   _pd(tab) if tab is not None else None)
+                   _pd(tab) if tab is not None else None, switch_kind(params) if cuda_modifiers else 0, params.rvdw_switch)
     f, fsh, vc, vv = _outputs(cs.natoms)
     best = np.inf
     for _ in range(repeats):
@@ -174,7 +182,8 @@ _FP = ctypes.POINTER(ctypes.c_float)
 
 class ForkParams(ctypes.Structure):
     _fields_ = [("eeltype", ctypes.c_int)] + [(n, ctypes.c_double) for n in (
-        "epsfac", "rcoulomb", "rvdw", "krf", "crf", "sh_ewald", "ewaldcoeff_q", "dispersion_cpot", "repulsion_cpot")]  # fmt: skip
+        "epsfac", "rcoulomb", "rvdw", "krf", "crf", "sh_ewald", "ewaldcoeff_q", "dispersion_cpot", "repulsion_cpot")] + [
+        ("vdw_switch_kind", ctypes.c_int), ("rvdw_switch", ctypes.c_double)]  # fmt: skip
 
 
 def have_fork_cuda() -> bool:
@@ -187,7 +196,7 @@ def run_fork_cuda(cs, params, *, energy=False, repeats=5):
     lib = ctypes.CDLL(FORK_CUDA_LIB)
     p = ForkParams(int(params.eeltype), params.epsfac, params.rcoulomb, params.rvdw, params.reactionFieldCoefficient,
                    params.reactionFieldShift, params.sh_ewald, params.ewaldcoeff_q, params.dispersion_shift_cpot,
-                   params.repulsion_shift_cpot)
+                   params.repulsion_shift_cpot, switch_kind(params), params.rvdw_switch)
     xq = np.ascontiguousarray(cs.xq, np.float32)
     typ = np.ascontiguousarray(cs.type, np.int32)
     nbfp = _d(cs.nbfp)

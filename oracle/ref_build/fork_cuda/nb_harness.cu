@@ -24,6 +24,23 @@
 #include "nbnxm_cuda_kernel.cuh" /* VF */
 #undef CALC_ENERGIES
 #undef NB_KERNEL_FUNC_NAME
+/* ... with the Lennard-Jones force switch and potential switch (flavours _VdwLJFsw, _VdwLJPsw) */
+#define LJ_FORCE_SWITCH
+#define NB_KERNEL_FUNC_NAME(x, ...) x##_ElecEw_VdwLJFsw##__VA_ARGS__
+#include "nbnxm_cuda_kernel.cuh"
+#define CALC_ENERGIES
+#include "nbnxm_cuda_kernel.cuh"
+#undef CALC_ENERGIES
+#undef NB_KERNEL_FUNC_NAME
+#undef LJ_FORCE_SWITCH
+#define LJ_POT_SWITCH
+#define NB_KERNEL_FUNC_NAME(x, ...) x##_ElecEw_VdwLJPsw##__VA_ARGS__
+#include "nbnxm_cuda_kernel.cuh"
+#define CALC_ENERGIES
+#include "nbnxm_cuda_kernel.cuh"
+#undef CALC_ENERGIES
+#undef NB_KERNEL_FUNC_NAME
+#undef LJ_POT_SWITCH
 #undef EL_EWALD_ANA
 
 #define EL_RF
@@ -43,6 +60,8 @@ extern "C" struct nbfork_params
 {
     int    eeltype;
     double epsfac, rcoulomb, rvdw, krf, crf, sh_ewald, ewaldcoeff_q, dispersion_cpot, repulsion_cpot;
+    int    vdw_switch_kind; /* 0 plain, 1 force switch, 2 potential switch (Ewald flavours only) */
+    double rvdw_switch;
 };
 
 #define CK(call)                                                                                   \
@@ -158,6 +177,23 @@ extern "C" int nbfork_run(const nbfork_params* p, int ntype, const double* nbfp,
     nbp.useDynamicPruning     = false;
     nbp.dispersion_shift.cpot = (float)p->dispersion_cpot;
     nbp.repulsion_shift.cpot  = (float)p->repulsion_cpot;
+    if (p->vdw_switch_kind != 0)
+    {
+        /* force_switch_constants / potential_switch_constants, mdtypes/interaction_const.cpp:216-245, as
+         * set_cutoff_parameters copies them into NBParamGpu (nbnxm_gpu_data_mgmt.cpp:201-223) */
+        const double rsw = p->rvdw_switch, rc = p->rvdw, d = rc - rsw;
+        auto fsw = [&](double pw, shift_consts_t* sc) {
+            sc->c2 = (float)(((pw + 1) * rsw - (pw + 4) * rc) / (pow(rc, pw + 2) * d * d));
+            sc->c3 = (float)(-((pw + 1) * rsw - (pw + 3) * rc) / (pow(rc, pw + 2) * d * d * d));
+        };
+        fsw(6.0, &nbp.dispersion_shift);
+        fsw(12.0, &nbp.repulsion_shift);
+        nbp.vdw_switch.c3 = (float)(-10.0 / (d * d * d));
+        nbp.vdw_switch.c4 = (float)(15.0 / (d * d * d * d));
+        nbp.vdw_switch.c5 = (float)(-6.0 / (d * d * d * d * d));
+        nbp.rvdw_switch   = (float)rsw;
+        nbp.vdwType       = p->vdw_switch_kind == 1 ? Nbnxm::VdwType::FSwitch : Nbnxm::VdwType::PSwitch;
+    }
     nbp.nbfp                  = reinterpret_cast<Float2*>(d_nbfp.p);
     nbp.nbfp_texobj           = nbfp_tex;
 
@@ -188,7 +224,21 @@ extern "C" int nbfork_run(const nbfork_params* p, int ntype, const double* nbfp,
         CK(cudaEventRecord(e0, nullptr));
         if (nsci > 0)
         {
-            if (ewald)
+            if (ewald && p->vdw_switch_kind == 1)
+            {
+                if (energy)
+                    nbnxn_kernel_ElecEw_VdwLJFsw_VF_cuda<<<grid, block, shmem>>>(adat, nbp, pl, true);
+                else
+                    nbnxn_kernel_ElecEw_VdwLJFsw_F_cuda<<<grid, block, shmem>>>(adat, nbp, pl, false);
+            }
+            else if (ewald && p->vdw_switch_kind == 2)
+            {
+                if (energy)
+                    nbnxn_kernel_ElecEw_VdwLJPsw_VF_cuda<<<grid, block, shmem>>>(adat, nbp, pl, true);
+                else
+                    nbnxn_kernel_ElecEw_VdwLJPsw_F_cuda<<<grid, block, shmem>>>(adat, nbp, pl, false);
+            }
+            else if (ewald)
             {
                 if (energy)
                     nbnxn_kernel_ElecEw_VdwLJ_VF_cuda<<<grid, block, shmem>>>(adat, nbp, pl, true);

@@ -18,6 +18,8 @@ typedef struct
     double epsfac, rcoulomb, rvdw, rlist, k_rf, c_rf, sh_ewald, beta, disp_cpot, rep_cpot, min_rsq, tab_scale;
     int    tab_size;
     const double* tableF;
+    int    vdw_switch_kind;
+    double rvdw_switch;
 } nbo_params;
 int nbo_run(int natoms, const double* xq, const int* type, int ntype, const double* nbfp, const nbo_params* p, int nsci,
             const void* sci, int ncj, const void* cj, int nexcl, const void* excl, const double* shiftvec, int want_energy,

@@ -343,3 +343,35 @@ def test_list_read_from_the_caller_s_device_copy_with_pruned_masks(nb):
     nb.launch_device(d_xq.data_ptr(), cs.shiftvec, P.DO_FORCE | NB_Q_FROM_XQ, d_f.data_ptr())
     nb.wait()
     _check(dict(f=d_f.cpu().numpy()), full, "own list")
+
+
+@pytest.mark.parametrize("modifier", ["forceswitch", "potswitch"])
+def test_lennard_jones_switch_flavours_of_the_reference_s_cuda_kernels(nb, modifier):
+    """vdw_modifier = force switch / potential switch: flavours of the reference's CUDA kernels (nbnxm_cuda_kernel_utils.cuh:104-211)
+    that nbnxn_kernel_gpu_ref does not have.  The checker applies them the way those kernels do (oracle/nb_oracle.c,
+    cuda_modifiers); it is pinned HERE, on the GPU, against the reference's own kernels nbnxn_kernel_ElecEw_VdwLJ{Fsw,Psw}_{F,VF}_cuda
+    compiled in place, and then compared with ours."""
+    import copy
+
+    pr, cs = _system(**CASES["ewald"])
+    base = P.make_params(coulombtype="pme", vdw_modifier=modifier, rvdw_switch=0.8)
+    params = copy.copy(pr.params)
+    for k in ("vdw_modifier", "rvdw_switch", "dispersion_shift_cpot", "repulsion_shift_cpot"):
+        setattr(params, k, getattr(base, k))
+    params = params.rounded()
+    plain = nb_oracle.run_port(cs, params, table=None)  # what nbnxn_kernel_gpu_ref would give: the switch ignored
+    want = nb_oracle.run_port(cs, params, table=None, cuda_modifiers=True)
+    assert np.max(np.abs(want["f"] - plain["f"])) > 1e-4 * np.max(np.abs(plain["f"]))
+    assert abs(want["vvdw"] - plain["vvdw"]) > 1e-6 * abs(plain["vvdw"])
+    if nb_oracle.have_fork_cuda():
+        fork = nb_oracle.run_fork_cuda(cs, params, energy=True, repeats=1)
+        rms = np.sqrt(np.mean((fork["f"] - want["f"]) ** 2) / np.mean(want["f"] ** 2))
+        assert rms <= 5e-6, rms
+        assert abs(fork["vvdw"] - want["vvdw"]) <= 5e-5 * abs(want["vvdw"]) and abs(fork["vc"] - want["vc"]) <= 5e-5 * abs(want["vc"])
+    nb.setup(cs, params)
+    got = nb.compute(cs.xq[:, :3], cs.shiftvec, ALL)
+    _check(got, want, modifier)
+    assert abs(got["vvdw"] - want["vvdw"]) <= 1e-5 * abs(want["vvdw"]) and abs(got["vc"] - want["vc"]) <= 1e-5 * abs(want["vc"])
+    fo = nb.compute(cs.xq[:, :3], cs.shiftvec, P.DO_FORCE)
+    assert np.max(np.abs(fo["f"] - got["f"])) <= 4e-6 * np.max(np.abs(got["f"]))
+    nb.setup(cs, pr.params)  # back to the plain flavour for the tests that follow

@@ -29,7 +29,8 @@ def _gpu_rows(workdir):
     return rows
 
 
-@pytest.mark.parametrize("system", ["c1_methane", "c2_hexadecane"])
+# c1 / c2: potential shift (made here); coulandvdwtogether, transformAtoB: the reference's own test systems, force switch
+@pytest.mark.parametrize("system", ["c1_methane", "c2_hexadecane", "coulandvdwtogether", "transformAtoB"])
 def test_cluster_pairs_through_the_library_inside_the_forks_gpu_route(system, tmp_path):
     tpr = os.path.join(T.TPR, system + ".tpr")
     a, b, c = str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "c")
@@ -58,17 +59,17 @@ def test_cluster_pairs_through_the_library_inside_the_forks_gpu_route(system, tm
 
 
 def test_uncovered_flavour_stays_with_the_forks_kernel(tmp_path):
-    """The reference's own test systems use vdw-modifier = force-switch, a flavour of the fork's CUDA kernels that the library's
-    cluster kernel does not have: the hook says so once and the fork's kernel runs."""
-    tpr = os.path.join(T.TPR, "coulandvdwtogether.tpr")
+    """LJ-PME is a flavour of the fork's CUDA kernels that the library's cluster kernel does not have: the hook says so once
+    and the fork's kernel runs."""
+    tpr = os.path.join(T.TPR, "c1_methane_ljpme.tpr")
     a, b = str(tmp_path / "a"), str(tmp_path / "b")
     try:
-        fork = T._run(tpr, a, False, gmx=GMX_CUDA, nb="gpu", fep="gpu")
+        fork = T._run(tpr, a, False, gmx=GMX_CUDA, nb="gpu", fep="cpu")
     except AssertionError as exc:
         pytest.skip("the fork's CUDA build does not run here: " + str(exc)[-400:])
-    ours = T._run(tpr, b, False, gmx=GMX_CUDA, nb="gpu", fep="gpu", extra_env={"GMX_FEPB200_NB": "1"})
+    ours = T._run(tpr, b, False, gmx=GMX_CUDA, nb="gpu", fep="cpu", extra_env={"GMX_FEPB200_NB": "1"})
     assert "the cluster pairs stay on the fork's kernel" in ours[0]
-    compare_nb_runs("coulandvdwtogether", fork, ours, (a, b))
+    compare_nb_runs("c1_methane_ljpme", fork, ours, (a, b))
 
 
 @pytest.mark.parametrize("system", ["c2_hexadecane", "c3_hexadecane"])
@@ -98,3 +99,19 @@ def test_steady_state_timing_beside_the_forks_kernel(system, tmp_path):
     except OSError:
         pass
     assert _gpu_rows(b)
+
+
+def test_two_domain_decomposition_ranks(tmp_path):
+    """Two thread-MPI ranks: every rank has a local and a non-local pair list, each with its own stream, and all four kernels of
+    a rank (cluster pairs and perturbed pairs of both localities) add into ONE adat->f with atomic operations.  All pairs
+    through libfepb200 against the fork's own kernels, same decomposition."""
+    system = "c2_hexadecane"
+    tpr = os.path.join(T.TPR, system + ".tpr")
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    try:
+        fork = T._run(tpr, a, False, gmx=GMX_CUDA, nb="gpu", fep="gpu", ntmpi=2)
+    except AssertionError as exc:
+        pytest.skip("the fork's CUDA build does not run two ranks here: " + str(exc)[-400:])
+    both = T._run(tpr, b, True, gmx=GMX_CUDA, nb="gpu", fep="gpu", ntmpi=2, extra_env={"GMX_FEPB200_NB": "1"})
+    assert both[0].count("fepb200 nb GPU route: locality 1") >= 1, "the non-local lists did not go through the library"
+    compare_nb_runs(system, fork, both, (a, b))
