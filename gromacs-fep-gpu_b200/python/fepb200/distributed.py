@@ -158,6 +158,19 @@ class ShardedFep:
             return
         self.ctx.launch(flags)
 
+    def align(self) -> bool:
+        """Device-side barrier over the ranks on self.stream (the symmetric-memory handle's own barrier kernel, the one
+        the set-up uses): every rank's stream continues only when all ranks' streams have arrived.  For measurements:
+        bench.py puts it between the L2 flush and the start event of a timed step, so that the ranks' flush times do
+        not show up as waiting time inside the step's cross-GPU barrier.  Not part of a step.  Returns False when
+        there is nothing to align with (one rank, or no symmetric memory: the "nccl" reduction)."""
+        hdl = getattr(self, "_hdl", None)
+        if self.world == 1 or hdl is None:
+            return False
+        with torch.cuda.stream(self.stream):
+            hdl.barrier(channel=1)
+        return True
+
     def step(self, x, shiftvec, flags: int, out: dict | None = None) -> dict:
         """Host buffers in, reduced host buffers out ("fused" / "p2p": the forces of the atoms this rank owns and
         all scalars; "p2p-allreduce" / "nccl": every rank receives the full result)."""
