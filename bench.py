@@ -11,9 +11,9 @@ pair-interaction = one (i,j) list entry evaluated at one lambda point, so a step
 P * (1 + (L+1)) pair-interactions -- the reference's own count of kernel work.
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, device time (CUDA events, max over
-ranks), L2 flushed between steps; at N > 1 the ranks' streams are aligned on the device after the flush and before
-the start event of every timed step (`run.rank_alignment`; `run.ms_per_step_unaligned` is the same measurement
-without, --no-align makes it the headline).  `e2e`: the same step through the public call with HOST buffers
+ranks), L2 flushed between steps; at N > 1 the line also carries the same measurement with the ranks' streams aligned
+on the device after the flush and before the start event of every timed step (`run.ms_per_step_aligned`; --align makes
+it the headline).  `e2e`: the same step through the public call with HOST buffers
 (fepb200_compute: pinned staging, H2D of the touched coordinates, kernels, the result block written
 into pinned host memory by the last kernel, scatter-add into the caller's force array; at N > 1
 upload / kernels + reduction / download of the result block), wall clock.  `roofline`: the kernel that took
@@ -433,10 +433,11 @@ def run_ours(args, name):
         flush.zero_()
         sh.launch(flags)
     torch.cuda.synchronize()
-    # N > 1: the ranks' streams are aligned ON THE DEVICE between the L2 flush and the start event of every timed step
-    # (ShardedFep.align: the symmetric-memory barrier kernel, outside the timed region).  Without it the ranks leave
-    # their 512 MiB flushes at different times, and that difference is waited for inside the step's own cross-GPU
-    # barrier, i.e. counted as step time.  --no-align measures without; the line carries both.
+    # N > 1, align = True: the ranks' streams are aligned ON THE DEVICE between the L2 flush and the start event of every
+    # timed step (ShardedFep.align: the symmetric-memory barrier kernel, outside the timed region), so that the ranks'
+    # different flush times are not waited for inside the step's own cross-GPU barrier.  The headline is measured
+    # WITHOUT (ranks run free, as in round 1 and 2's records) unless --align is given; the line carries both
+    # (run.ms_per_step_aligned / _unaligned).  On 2 B200 the two agree to 1 us (profiles/r02_multi_gpu_bench_lines.json).
     def timed_steps(fl, steps, align):
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -455,12 +456,13 @@ def run_ours(args, name):
         t_w = time.perf_counter() - t_w0
         return max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))) / steps, t_w
 
-    aligned = world > 1 and not args.no_align and sh.align()
+    can_align = world > 1 and sh.align()
+    aligned = can_align and args.align
     torch.cuda.synchronize()
     n0 = ctx.launch_count()
     ms_per_step, t_wall = timed_steps(flags, args.steps, aligned)
     launches = ctx.launch_count() - n0
-    ms_unaligned = timed_steps(flags, args.steps, False)[0] if aligned else None
+    ms_other = timed_steps(flags, args.steps, not aligned)[0] if can_align else None
     value = wl["units_per_step"] / (ms_per_step * 1e-3)
 
     # ---- per-kernel times of the same launches: CUDA events of the library around every kernel ------
@@ -645,7 +647,8 @@ def run_ours(args, name):
                              reduction=sh.reduction if world > 1 else "none",
                              rank_alignment=("device-side barrier over the ranks between the L2 flush and the start event of "
                                              "every timed step (outside the timed region)") if aligned else "none",
-                             ms_per_step_unaligned=ms_unaligned,
+                             ms_per_step_aligned=ms_per_step if aligned else ms_other,
+                             ms_per_step_unaligned=ms_other if aligned else (ms_per_step if world > 1 else None),
                              outputs="forces reduce-scattered by atom range, scalars on every rank"
                              if sh.reduction in ("fused", "p2p") else "full result on every rank"),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -676,8 +679,8 @@ def main():
     ap.add_argument("--no-fork-gpu", action="store_true", help="skip the fork's CUDA kernels beside ours (fork_gpu_baseline)")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the C1-C4 sub-lines (configs)")
     ap.add_argument("--n-foreign", type=int, default=None, help="override the number of foreign lambda points")
-    ap.add_argument("--no-align", action="store_true",
-                    help="N > 1: do not align the ranks on the device before each timed step (see run.rank_alignment)")
+    ap.add_argument("--align", action="store_true",
+                    help="N > 1: headline measured with the ranks aligned on the device before each timed step (see run.rank_alignment)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference-gpu":
