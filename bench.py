@@ -491,7 +491,7 @@ def run_ours(args, name):
         p0, p1, a0, a1 = ctx.peer_ranges()
         my_entries = int(round(my_entries / world))
         my_pairs, my_atoms = int(round(my_pairs / world)), a1 - a0
-    elif sh.reduction == "p2p":
+    elif sh.reduction in ("p2p", "p2p-push"):
         p0, p1, a0, a1 = ctx.peer_ranges()  # the atoms this rank owns after the reduce-scatter
         my_atoms = a1 - a0
     points = problem.n_foreign + 1
@@ -650,7 +650,7 @@ def run_ours(args, name):
                              ms_per_step_aligned=ms_per_step if aligned else ms_other,
                              ms_per_step_unaligned=ms_other if aligned else (ms_per_step if world > 1 else None),
                              outputs="forces reduce-scattered by atom range, scalars on every rank"
-                             if sh.reduction in ("fused", "p2p") else "full result on every rank"),
+                             if sh.reduction in ("fused", "p2p", "p2p-push") else "full result on every rank"),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_s / args.steps * 1e3,
                              note="wall clock of the public call with host buffers; the device time of the L2 flush between "

@@ -344,15 +344,24 @@ __device__ __forceinline__ double block_sum_d(double v, double* s_buf)
  * `seq` or a later step.  All ranks must launch their steps in lockstep with the same `seq`; a peer that
  * never arrives within 4 s makes the kernel record the reason and trap (FEP_FAULT_PEER_TIMEOUT) instead
  * of hanging every GPU of the node.  Ends with a block-wide barrier. */
+/* light: the same barrier with ONE system-scope fence on either side instead of one per instruction -- the announcement
+ * is the release store alone (the data it publishes was written by the preceding kernel: it is ordered before the store
+ * by the kernel boundary, and a release is cumulative), the poll is a relaxed load, and one acquire fence follows the
+ * load that saw the announcement.  A system-scope fence costs microseconds on an NVSwitch box (profiles/: the barrier
+ * was 10 of the 13 us the reduction kernel takes with its data already local); the original form pays one before the
+ * store, one inside it, and one per poll. */
 template<typename FlagsOf>
 __device__ __forceinline__ void fep_flag_barrier(FlagsOf flags_of, int rank, int nranks, unsigned int seq, bool announce,
-                                                 unsigned int* fault)
+                                                 unsigned int* fault, bool light = false)
 {
     if (threadIdx.x < nranks)
     {
         if (announce)
         {
-            __threadfence_system();
+            if (!light)
+            {
+                __threadfence_system();
+            }
             unsigned int* dst = flags_of(threadIdx.x) + rank;
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
         }
@@ -361,9 +370,20 @@ __device__ __forceinline__ void fep_flag_barrier(FlagsOf flags_of, int rank, int
         unsigned long long  t0 = 0;
         for (unsigned int spins = 0;; spins++)
         {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if (light)
+            {
+                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            }
+            else
+            {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            }
             if ((int)(v - seq) >= 0)
             {
+                if (light)
+                {
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                }
                 break;
             }
             if ((spins & 1023u) == 1023u)
@@ -404,6 +424,25 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
     __shared__ bool   s_last;
     const int         tid = threadIdx.x;
     int               b   = blockIdx.x;
+/* where results go: the rank's own block, or -- push reduction (PushTargets) -- the receive block of the rank that owns
+ * the atom (forces) / of every rank (shift forces and scalars) */
+#define FEP_EPI_FORCE_DST(atom) \
+    ((!PEER && ka.push.nranks > 1) ? ka.push.f32[min((atom) / ka.push.per_rank, ka.push.nranks - 1)] : ka.res_f32)
+#define FEP_EPI_STORE_ALL(part, idx, val)                 \
+    do                                                    \
+    {                                                     \
+        if (!PEER && ka.push.nranks > 1)                  \
+        {                                                 \
+            for (int r_ = 0; r_ < ka.push.nranks; r_++)   \
+            {                                             \
+                ka.push.part[r_][idx] = (val);            \
+            }                                             \
+        }                                                 \
+        else                                              \
+        {                                                 \
+            ka.res_##part[idx] = (val);                   \
+        }                                                 \
+    } while (0)
     /* optional trace (fepb200_epilogue_trace): per block the global timer at entry, after the wait
      * for this rank's pair kernels, after the cross-GPU barrier, and when the block's sums are done */
     unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
@@ -559,13 +598,13 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         {
             if (b < 2)
             {
-                ka.res_f64[off_dvdl + b] = a;
+                FEP_EPI_STORE_ALL(f64, off_dvdl + b, a);
             }
             else if (b < 4)
             {
                 if (sf.energy && ka.n_gid == 1)
                 {
-                    ka.res_f64[b == 2 ? 0 : off_vv] = a;
+                    FEP_EPI_STORE_ALL(f64, b == 2 ? 0 : off_vv, a);
                 }
             }
             else
@@ -573,11 +612,11 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
                 const int p = (b - 4) / 3, k = (b - 4) - 3 * p;
                 if (k == 0)
                 {
-                    ka.res_f64[off_fe + p] = a;
+                    FEP_EPI_STORE_ALL(f64, off_fe + p, a);
                 }
                 else
                 {
-                    ka.res_f64[off_fd + 2 * p + (k - 1)] = a;
+                    FEP_EPI_STORE_ALL(f64, off_fd + 2 * p + (k - 1), a);
                 }
             }
         }
@@ -646,7 +685,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         }
         if (hi < hend && lane < 3)
         {
-            ka.res_f32[3 * (size_t)atom + lane] = lane == 0 ? fx : (lane == 1 ? fy : fz);
+            FEP_EPI_FORCE_DST(atom)[3 * (size_t)atom + lane] = lane == 0 ? fx : (lane == 1 ? fy : fz);
         }
     }
     else
@@ -718,7 +757,7 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
         }
         if (mine && sub < 3)
         {
-            ka.res_f32[3 * (size_t)atom + sub] = sub == 0 ? fx : (sub == 1 ? fy : fz);
+            FEP_EPI_FORCE_DST(atom)[3 * (size_t)atom + sub] = sub == 0 ? fx : (sub == 1 ? fy : fz);
         }
     }
 
@@ -800,11 +839,11 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
             }
             if (o < n_sh)
             {
-                ka.res_f32[3 * (size_t)ka.n_touched + o] = (float)a;
+                FEP_EPI_STORE_ALL(f32, 3 * (size_t)ka.n_touched + o, (float)a);
             }
             else
             {
-                ka.res_f64[(comp ? off_vv : 0) + (key - FEP_NUM_SHIFT)] = a;
+                FEP_EPI_STORE_ALL(f64, (comp ? off_vv : 0) + (key - FEP_NUM_SHIFT), a);
             }
         }
     }
@@ -814,6 +853,8 @@ __global__ void __launch_bounds__(FEP_EPI_CTA) fep_epilogue_kernel(const __grid_
     }
 #undef FEP_EPI_LOAD
 #undef FEP_EPI_SYNC_POINT
+#undef FEP_EPI_FORCE_DST
+#undef FEP_EPI_STORE_ALL
 }
 
 /* coordinates of the touched atoms from a device-resident array of `stride` floats per atom:
@@ -1145,6 +1186,17 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
 /* ------------------------------------------------------------------------------------------- */
 /* multi-GPU: one-shot reduction over peer memory                                              */
 /* ------------------------------------------------------------------------------------------- */
+/* FEPB200_BARRIER=sc: the reduction kernels' cross-GPU barrier in its original form (a fence per instruction); default:
+ * the light form (fep_flag_barrier) */
+static int fep_light_barrier()
+{
+    static const int light = [] {
+        const char* e = std::getenv("FEPB200_BARRIER");
+        return (e && std::strcmp(e, "sc") == 0) ? 0 : 1;
+    }();
+    return light;
+}
+
 /* Every rank has published its result block [f64 | f32] in a buffer all ranks have mapped
  * (NVLink peer access).  Each rank reads every block once and keeps the full sum: a one-shot
  * all-reduce, latency-optimal for the ~1 MB blocks of this path; the order of the additions is the
@@ -1154,7 +1206,7 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
                                                              const __grid_constant__ PeerPtrs flags, int rank,
                                                              unsigned int seq, int nranks, double* __restrict__ out_f64,
                                                              int n64, size_t f64_bytes, float* __restrict__ out_f32,
-                                                             long long n32, unsigned int* fault)
+                                                             long long n32, unsigned int* fault, int light_barrier)
 {
     fep_pdl_wait(); /* chained behind the epilogue that completes this rank's block */
     if (flags.p[0] != nullptr)
@@ -1164,7 +1216,7 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_kernel(const __grid_const
          * `rank`), then wait until every peer's announcement has arrived in ours.  One kernel per
          * GPU takes part, so the spin cannot starve a producer on the same device. */
         fep_flag_barrier([&](int r) { return static_cast<unsigned int*>(const_cast<void*>(flags.p[r])); }, rank, nranks, seq,
-                         blockIdx.x == 0, fault);
+                         blockIdx.x == 0, fault, light_barrier != 0);
     }
     /* NR > 0: compile-time rank count, all NR remote loads are in flight before the first add
      * (a peer load is ~1.5 us; serialising them would cost NR times that) */
@@ -1237,10 +1289,10 @@ extern "C" int fep_launch_peer_reduce(const PeerPtrs* peers, const PeerPtrs* fla
     const unsigned  blocks = (unsigned)((std::max<long long>(items, n64) + 255) / 256);
     switch (nranks)
     {
-        case 2: fep_launch_kernel(fep_peer_reduce_kernel<2>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
-        case 4: fep_launch_kernel(fep_peer_reduce_kernel<4>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
-        case 8: fep_launch_kernel(fep_peer_reduce_kernel<8>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
-        default: fep_launch_kernel(fep_peer_reduce_kernel<0>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault); break;
+        case 2: fep_launch_kernel(fep_peer_reduce_kernel<2>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault, fep_light_barrier()); break;
+        case 4: fep_launch_kernel(fep_peer_reduce_kernel<4>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault, fep_light_barrier()); break;
+        case 8: fep_launch_kernel(fep_peer_reduce_kernel<8>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault, fep_light_barrier()); break;
+        default: fep_launch_kernel(fep_peer_reduce_kernel<0>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, seq, nranks, out_f64, n64, f64_bytes, out_f32, n32, fault, fep_light_barrier()); break;
     }
     (*counter)++;
     return (int)cudaGetLastError();
@@ -1259,13 +1311,13 @@ __global__ void __launch_bounds__(256) fep_peer_reduce_scatter_kernel(const __gr
                                                                      unsigned int seq, int nranks, double* __restrict__ out_f64,
                                                                      int n64, size_t f64_bytes, float* __restrict__ out_f32,
                                                                      long long w0, long long w1, long long off_fshift,
-                                                                     unsigned int* fault)
+                                                                     unsigned int* fault, int light_barrier)
 {
     fep_pdl_wait(); /* chained behind the epilogue that completes this rank's block */
     if (flags.p[0] != nullptr)
     {
         fep_flag_barrier([&](int r) { return static_cast<unsigned int*>(const_cast<void*>(flags.p[r])); }, rank, nranks, seq,
-                         blockIdx.x == 0, fault);
+                         blockIdx.x == 0, fault, light_barrier != 0);
     }
     const int       nr     = NR > 0 ? NR : nranks;
     const long long n4     = (w1 - w0) >> 2;
@@ -1327,7 +1379,7 @@ extern "C" int fep_launch_peer_reduce_scatter(const PeerPtrs* peers, const PeerP
     const unsigned  blocks = (unsigned)((items + 255) / 256);
 #define FEP_RS_LAUNCH(N)                                                                                                  \
     fep_launch_kernel(fep_peer_reduce_scatter_kernel<N>, dim3(blocks), dim3(256), stream, chained != 0, *peers, *flags, rank, \
-                      seq, nranks, out_f64, n64, f64_bytes, out_f32, w0, w1, off_fshift, fault)
+                      seq, nranks, out_f64, n64, f64_bytes, out_f32, w0, w1, off_fshift, fault, fep_light_barrier())
     switch (nranks)
     {
         case 2: FEP_RS_LAUNCH(2); break;

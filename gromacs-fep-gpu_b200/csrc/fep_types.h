@@ -162,6 +162,19 @@ struct PeerExchange
     unsigned int* flags[FEP_XMAX]; /* per rank FEP_XMAX sequence numbers, slot r written by rank r */
 };
 
+/* Multi-GPU "push" reduction (fepb200_set_push_targets): the epilogue stores what it has summed straight into the memory
+ * of the ranks that need it, over NVLink -- the force of compact atom a into the receive block of the rank that owns a
+ * (equal ranges of `per_rank` atoms), the shift forces and scalars into the receive blocks of all ranks -- so that the
+ * reduction kernel behind the cross-GPU barrier (fep_peer_reduce_scatter_kernel on the rank's own receive blocks) reads
+ * local memory only: one one-way NVLink trip per step instead of an announcement plus a pull (a round trip and a half).
+ * nranks <= 1: the epilogue writes res_f32 / res_f64 as usual. */
+struct PushTargets
+{
+    int     nranks, per_rank;
+    float*  f32[FEP_XMAX]; /* this rank's receive block on rank r: f32 part ... */
+    double* f64[FEP_XMAX]; /* ... and f64 part */
+};
+
 /* Static constants + device pointers, passed by value as the kernel parameter. */
 struct KernelArgs
 {
@@ -218,6 +231,7 @@ struct KernelArgs
     float*  res_f32;
     double* res_f64;
     PeerExchange px;
+    PushTargets  push;
     unsigned long long* trace; /* NULL, or FEP_TRACE_BLOCKS x 4 global-timer stamps of the epilogue's blocks */
     unsigned int*       fault; /* host-mapped FEP_FAULT_WORDS words: why a kernel of this context trapped (fep_fault) */
 };

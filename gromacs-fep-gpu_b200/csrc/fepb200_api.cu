@@ -256,6 +256,9 @@ struct fepb200_ctx
     PinnedArray<unsigned char> h_step_in, h_result;
     size_t res_f64_bytes = 0, res_f32_bytes = 0;
     unsigned char* res_target = nullptr; /* where the epilogue writes; nullptr = own result block */
+    /* fepb200_set_push_targets(): the epilogue stores into the ranks' receive blocks (PushTargets) */
+    int            push_n = 0;
+    unsigned char* push_block[FEP_XMAX] = {};
 
     /* peer exchange (fepb200_set_peer_exchange): the list is evaluated by x_nranks GPUs, this one
      * takes a range of pairs and owns a range of atoms */
@@ -1014,6 +1017,7 @@ static int build_segments(fepb200_ctx* c, int run_trips)
     KernelArgs& k   = c->ka;
     c->result_needs_zero = true;
     c->own_on            = false;
+    c->push_n            = 0; /* the receive blocks were sized (and are only ever partly written) for the previous list */
     c->zeroed_targets.clear();
     c->n_segs       = NS;
     k.n_segs        = NS;
@@ -2002,6 +2006,20 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
         c->result_on_host = true;
     }
     c->zc_next = false;
+    if (c->push_n > 1)
+    {
+        /* push reduction: forces to the rank that owns the atom (the ranges of fepb200_reduce_scatter_peers), shift
+         * forces and scalars to every rank; nothing of this step is written to a block of our own */
+        const long long nT      = c->layout.ntouched;
+        ka_step.push.nranks     = c->push_n;
+        ka_step.push.per_rank   = (int)std::max(4LL, ((nT + c->push_n - 1) / c->push_n + 3) / 4 * 4);
+        for (int r = 0; r < c->push_n; r++)
+        {
+            ka_step.push.f64[r] = reinterpret_cast<double*>(c->push_block[r]);
+            ka_step.push.f32[r] = reinterpret_cast<float*>(c->push_block[r] + c->res_f64_bytes);
+        }
+        c->result_on_host = false;
+    }
     if (c->px_on)
     {
         /* the exchange slot of this step on every rank; all ranks launch in lockstep, so they agree
@@ -2049,7 +2067,7 @@ int fepb200_launch(fepb200_ctx* c, int flags, void* stream_v)
     }
     /* multi-GPU with a published partial block: the reduction kernel follows on the same stream and
      * is chained behind the epilogue (nothing may be queued between them); it records ev_stop */
-    c->chain_open = c->res_target != nullptr && stream == c->stream && !c->profiling;
+    c->chain_open = (c->res_target != nullptr || c->push_n > 1) && stream == c->stream && !c->profiling;
     if (!c->chain_open)
     {
         CU_CHECK(c, cudaEventRecord(c->ev_stop, stream));
@@ -2190,6 +2208,40 @@ int fepb200_set_partial_result_block(fepb200_ctx* c, void* d_block)
         return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "result block must be 16-byte aligned");
     }
     c->res_target = static_cast<unsigned char*>(d_block);
+    return FEPB200_OK;
+}
+
+int fepb200_set_push_targets(fepb200_ctx* c, int nranks, void* const* d_peer_blocks)
+{
+    if (!c || !c->have_list)
+    {
+        return fail(c, FEPB200_ERR_STATE, "no list has been set");
+    }
+    if (nranks <= 1 || !d_peer_blocks)
+    {
+        c->push_n = 0;
+        return FEPB200_OK;
+    }
+    if (nranks > FEP_XMAX)
+    {
+        return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_push_targets: at most %d ranks", FEP_XMAX);
+    }
+    if (c->px_on)
+    {
+        return fail(c, FEPB200_ERR_STATE, "fepb200_set_push_targets: the fused peer exchange is on (it is the reduction)");
+    }
+    for (int r = 0; r < nranks; r++)
+    {
+        if (!d_peer_blocks[r] || (reinterpret_cast<size_t>(d_peer_blocks[r]) & 15) != 0)
+        {
+            return fail(c, FEPB200_ERR_INVALID_ARGUMENT, "fepb200_set_push_targets: block %d is NULL or not 16-byte aligned", r);
+        }
+    }
+    for (int r = 0; r < nranks; r++)
+    {
+        c->push_block[r] = static_cast<unsigned char*>(d_peer_blocks[r]);
+    }
+    c->push_n = nranks;
     return FEPB200_OK;
 }
 

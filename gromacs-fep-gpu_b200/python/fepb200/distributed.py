@@ -56,7 +56,9 @@ class ShardedFep:
     node has mapped over NVLink), passes a device-side barrier, and libfepb200's own kernel sums, through
     the peer pointers and in rank order, the forces of the atoms this rank owns and all scalars
     (fepb200_reduce_scatter_peers); step() returns what "fused" returns.  "p2p-allreduce": every rank sums
-    everything (fepb200_reduce_peers).
+    everything (fepb200_reduce_peers).  "p2p-push": the same result as "p2p", but the epilogue stores its sums
+    straight into receive blocks on the ranks that need them (fepb200_set_push_targets) and the reduction kernel
+    reads local memory only: one one-way NVLink trip per step.
     reduction = "nccl": two ncclAllReduce calls on zero-copy views of the result block.
     """
 
@@ -85,9 +87,9 @@ class ShardedFep:
         self.f32, self.f64 = result_tensors(self.ctx)
         if world > 1 and self.reduction != "fused":
             self.reduction = "nccl"
-            if want in ("p2p", "p2p-allreduce"):
+            if want in ("p2p", "p2p-allreduce", "p2p-push"):
                 try:
-                    self._setup_p2p(device)
+                    self._setup_p2p(device, blocks_per_slot=world if want == "p2p-push" else 1)
                     self.reduction = want
                 except Exception as exc:  # no symmetric memory on this system: NCCL does the same job
                     self._p2p_error = repr(exc)
@@ -108,23 +110,29 @@ class ShardedFep:
         self.ctx.set_peer_exchange(self.world, self.rank, [int(p) for p in self._hdl.buffer_ptrs], nbytes)
         self.exchange_bytes = nbytes
 
-    def _setup_p2p(self, device: int) -> None:
+    def _setup_p2p(self, device: int, blocks_per_slot: int = 1) -> None:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
         group = self.group if self.group is not None else dist.group.WORLD
         self.block_bytes = (self.ctx.result_block_bytes() + 255) // 256 * 256
+        slot_bytes = blocks_per_slot * self.block_bytes
         with torch.cuda.stream(self.stream):
-            # [slot 0 | slot 1 | flag array (16 x uint32 sequence numbers)]
-            self._sym = symm_mem.empty(2 * self.block_bytes + 256, dtype=torch.uint8, device=torch.device("cuda", device))
+            # [slot 0 | slot 1 | flag array (16 x uint32 sequence numbers)]; a slot is one block ("p2p": the rank's own
+            # partial result, pulled by the others) or one receive block per rank ("p2p-push": written by that rank)
+            self._sym = symm_mem.empty(2 * slot_bytes + 256, dtype=torch.uint8, device=torch.device("cuda", device))
             self._sym.zero_()
             self._hdl = symm_mem.rendezvous(self._sym, group)
-            self._hdl.barrier(channel=0)  # everybody's flags are zero before anybody announces a step
+            self._hdl.barrier(channel=0)  # everybody's flags and blocks are zero before anybody announces or pushes
         base = [int(p) for p in self._hdl.buffer_ptrs]
         # two alternating slots: a rank that runs ahead writes the other slot, and cannot come back
         # to this one before everybody has announced the next step
-        self._slots = [[b + k * self.block_bytes for b in base] for k in (0, 1)]
-        self._flags = [b + 2 * self.block_bytes for b in base]
+        self._slots = [[b + k * slot_bytes for b in base] for k in (0, 1)]
+        self._flags = [b + 2 * slot_bytes for b in base]
+        if blocks_per_slot > 1:
+            # my receive block on rank r, and the blocks the ranks write on me
+            self._push = [[b + k * slot_bytes + self.rank * self.block_bytes for b in base] for k in (0, 1)]
+            self._recv = [[base[self.rank] + k * slot_bytes + s * self.block_bytes for s in range(self.world)] for k in (0, 1)]
         self.stream.synchronize()
 
     def launch(self, flags: int) -> None:
@@ -144,6 +152,15 @@ class ShardedFep:
                 self.ctx.reduce_scatter_peers(self._slots[k], self._flags, self.rank, self._step)
             else:
                 self.ctx.reduce_peers(self._slots[k], self._flags, self.rank, self._step)
+            return
+        if self.reduction == "p2p-push":
+            k = self._step & 1
+            self._step += 1
+            # the epilogue stores this rank's sums straight into the ranks that need them; the reduction kernel behind
+            # the barrier adds up the blocks the ranks have written HERE
+            self.ctx.set_push_targets(self._push[k])
+            self.ctx.launch(flags)
+            self.ctx.reduce_scatter_peers(self._recv[k], self._flags, self.rank, self._step)
             return
         if self.reduction == "nccl":
             import torch.distributed as dist

@@ -84,6 +84,7 @@ SYMBOLS = {
     "fepb200_result_block_bytes": (ctypes.c_size_t, [_VP]),
     "fepb200_publish_result": (ctypes.c_int, [_VP, _VP]),
     "fepb200_set_partial_result_block": (ctypes.c_int, [_VP, _VP]),
+    "fepb200_set_push_targets": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP)]),
     "fepb200_reduce_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int,
                                             ctypes.c_uint]),
     "fepb200_reduce_scatter_peers": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(_VP), ctypes.POINTER(_VP), ctypes.c_int,
@@ -392,6 +393,14 @@ class FepContext:
         arr = (_VP * len(peer_blocks))(*[_VP(p) for p in peer_blocks])
         flg = (_VP * len(peer_flags))(*[_VP(p) for p in peer_flags]) if peer_flags else None
         self._check(self._lib.fepb200_reduce_peers(self._h, len(peer_blocks), arr, flg, int(rank), int(seq) & 0xFFFFFFFF))
+
+    def set_push_targets(self, peer_blocks: list[int] | None) -> None:
+        """This rank's receive block on every rank (peer-mapped addresses, rank order), or None: off."""
+        if not peer_blocks:
+            self._check(self._lib.fepb200_set_push_targets(self._h, 0, None))
+            return
+        arr = (_VP * len(peer_blocks))(*[_VP(p) for p in peer_blocks])
+        self._check(self._lib.fepb200_set_push_targets(self._h, len(peer_blocks), arr))
 
     def reduce_scatter_peers(self, peer_blocks: list[int], peer_flags: list[int] | None = None, rank: int = 0,
                              seq: int = 0) -> None:

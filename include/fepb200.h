@@ -300,6 +300,17 @@ int    fepb200_reduce_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_bl
  * replaces ThreadedForceBuffer::reduce (mdtypes/threaded_force_buffer.cpp:320-402) across GPUs. */
 int    fepb200_reduce_scatter_peers(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks, void* const* d_peer_flags,
                                     int rank, unsigned int seq);
+/* The same reduction with ONE one-way NVLink trip per step instead of an announcement plus a pull: the kernel that forms
+ * this rank's sums stores them straight into the ranks that need them.  Every rank r owns, per step slot, `nranks`
+ * zero-initialised receive blocks of fepb200_result_block_bytes() bytes, block s written by rank s only.
+ * d_peer_blocks[r] = THIS rank's receive block on rank r (peer-mapped address).  The following fepb200_launch() calls
+ * store the force of a compact atom into the block on the rank that owns the atom (the ranges of
+ * fepb200_reduce_scatter_peers()) and the shift forces and scalars into the blocks on all ranks; nothing is written to a
+ * block of this context's own.  Follow each launch with fepb200_reduce_scatter_peers(ctx, nranks, LOCAL receive blocks
+ * in rank order, flags, rank, seq): its barrier orders the pushes before the sums, and the sums read local memory only.
+ * The set of words a rank writes is fixed by its list: the blocks must be zeroed again (on all ranks, behind a barrier)
+ * after a new fepb200_set_list(), which also switches the push off.  nranks <= 1 or d_peer_blocks == NULL: off. */
+int    fepb200_set_push_targets(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks);
 
 /* ---- multi-GPU, fused: no separate collective, every rank sums its own atoms ------------------
  * The force reduce-scatter and the scalar all-reduce of SURVEY 8e inside the epilogue kernel

@@ -493,6 +493,59 @@ def test_peer_reduce_entry_points_with_one_rank(ctx):
         assert np.array_equal(got[k], want[k]), k
 
 
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_push_reduction_with_shards_on_one_device(nranks):
+    """fepb200_set_push_targets: the epilogue of each shard stores its sums straight into receive blocks of the 'ranks'
+    that need them (forces: the rank that owns the atom; shift forces and scalars: every rank), and
+    fepb200_reduce_scatter_peers on a rank's OWN receive blocks adds them up.  Several contexts on one device play the
+    ranks (the barrier between pushes and sums is a device synchronisation here; across real GPUs it is the flag
+    barrier inside the reduction kernel, tests/test_multi_gpu.py)."""
+    import contextlib
+
+    import torch
+
+    from fepb200.lib import FepContext
+
+    prob = make_system(SMALL["C4"])
+    with contextlib.ExitStack() as stack:
+        whole = stack.enter_context(FepContext(0))
+        ranks = [stack.enter_context(FepContext(0)) for _ in range(nranks)]
+        whole.set_problem(prob)
+        want = whole.compute(prob.x, prob.shiftvec, ALL)
+        for r, c in enumerate(ranks):
+            c.set_problem(prob, rank=r, nranks=nranks)
+        nbytes = (ranks[0].result_block_bytes() + 255) // 256 * 256
+        assert all(c.result_block_bytes() == ranks[0].result_block_bytes() for c in ranks)
+        recv = [torch.zeros(nranks * nbytes, dtype=torch.uint8, device="cuda") for _ in ranks]  # recv[r]: blocks on rank r
+
+        def block(r, s):  # the block on rank r that rank s writes
+            return recv[r].data_ptr() + s * nbytes
+
+        for step in range(3):  # the write pattern is static: later steps overwrite the same words
+            for r, c in enumerate(ranks):
+                c.upload_x(prob.x, prob.shiftvec)
+                c.set_push_targets([block(t, r) for t in range(nranks)])
+                c.launch(ALL)
+            torch.cuda.synchronize()
+            outs = []
+            for r, c in enumerate(ranks):
+                c.reduce_scatter_peers([block(r, s) for s in range(nranks)], None, r, step + 1)
+                outs.append(c.download(ALL))
+            f = sum(o["f"] for o in outs)
+            assert np.max(sum((o["f"] != 0).astype(np.int32) for o in outs)) == 1  # every atom has one owner
+            assert sum(1 for o in outs if np.any(o["f"])) >= 2
+            assert np.allclose(f, want["f"], rtol=0.0, atol=2e-5 * np.max(np.abs(want["f"])))
+            for k in ("fshift", "Vc", "Vv", "dvdl", "foreign_energy", "foreign_dvdl"):
+                for o in outs[1:]:
+                    assert np.array_equal(outs[0][k], o[k]), k  # summed in rank order on every rank
+                assert np.allclose(outs[0][k], want[k], rtol=1e-5, atol=1e-5 * np.max(np.abs(want[k]))), k
+        # ... and switching the push off brings the context's own block back
+        ranks[0].set_push_targets(None)
+        ranks[0].upload_x(prob.x, prob.shiftvec)
+        ranks[0].launch(ALL)
+        ranks[0].wait()
+
+
 def test_lambda_update_without_new_list(ctx):
     prm = P.make_params(coulombtype="pme", softcore="beutler")
     prob = random_problem(21, prm, natoms=200, nri=50, n_foreign=3, frac_overlap=0.0)

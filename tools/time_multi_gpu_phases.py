@@ -59,6 +59,20 @@ for i in range(steps):
         ctx.set_partial_result_block(sh._slots[k][rank])
         ctx.launch(flags)
         e[i][1].record()
+        ctx.reduce_scatter_peers(sh._slots[k], sh._flags, rank, sh._step)
+    elif sh.reduction == "p2p-push":
+        k = sh._step & 1
+        sh._step += 1
+        ctx.set_push_targets(sh._push[k])
+        ctx.launch(flags)
+        e[i][1].record()
+        ctx.reduce_scatter_peers(sh._recv[k], sh._flags, rank, sh._step)
+    elif sh.reduction == "p2p-allreduce":
+        k = sh._step & 1
+        sh._step += 1
+        ctx.set_partial_result_block(sh._slots[k][rank])
+        ctx.launch(flags)
+        e[i][1].record()
         ctx.reduce_peers(sh._slots[k], sh._flags, rank, sh._step)
     else:
         sh.launch(flags)
@@ -68,6 +82,42 @@ torch.cuda.synchronize()
 whole = np.array([a.elapsed_time(c) for a, b, c in e]) * 1e3
 local_part = np.array([a.elapsed_time(b) for a, b, c in e]) * 1e3
 red_part = np.array([b.elapsed_time(c) for a, b, c in e]) * 1e3
+
+# the reduction kernel on its own, the ranks aligned on the device right before it (ShardedFep.align): the cost of the
+# exchange itself (barrier inside the kernel + the pull over NVLink), without any waiting for a slower rank
+red_alone = None
+if sh.reduction in ("p2p", "p2p-allreduce", "p2p-push"):
+    for cold in (True, False):
+        ea = [[ev(), ev()] for _ in range(steps)]
+        dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(steps):
+            if cold:
+                flush.zero_()
+            sh.align()
+            ea[i][0].record()
+            k = sh._step & 1
+            sh._step += 1
+            if sh.reduction == "p2p":
+                ctx.reduce_scatter_peers(sh._slots[k], sh._flags, rank, sh._step)
+            elif sh.reduction == "p2p-push":
+                ctx.reduce_scatter_peers(sh._recv[k], sh._flags, rank, sh._step)
+            else:
+                ctx.reduce_peers(sh._slots[k], sh._flags, rank, sh._step)
+            ea[i][1].record()
+        torch.cuda.synchronize()
+        t = np.array([a.elapsed_time(b) for a, b in ea]) * 1e3
+        red_alone = (red_alone or "") + f" {'L2 flushed' if cold else 'warm'} {t.mean():.1f} (min {t.min():.1f})"
+    # ... and an empty-ish reference: the alignment barrier kernel alone between two events
+    ea = [[ev(), ev()] for _ in range(steps)]
+    for i in range(steps):
+        sh.align()
+        ea[i][0].record()
+        sh.align()
+        ea[i][1].record()
+    torch.cuda.synchronize()
+    t = np.array([a.elapsed_time(b) for a, b in ea]) * 1e3
+    red_alone += f" | torch symm-mem barrier kernel alone {t.mean():.1f} (min {t.min():.1f})"
 
 # kernels one by one
 ctx.set_profiling(True)
@@ -82,7 +132,7 @@ kms = np.array(kms) * 1e3
 
 msg = (f"rank {rank}/{world} {name} red={sh.reduction} pairs {int(lay.nrj)} entries {int(lay.nri)} touched {int(lay.ntouched)} | "
        f"step mean {whole.mean():.1f} min {whole.min():.1f} us | shard kernels {local_part.mean():.1f} (min {local_part.min():.1f}) | "
-       f"reduction {red_part.mean():.1f} (min {red_part.min():.1f}) | alone: pass {kms[:,0].mean():.1f} foreign {kms[:,1].mean():.1f} "
+       f"reduction {red_part.mean():.1f} (min {red_part.min():.1f}) | reduction kernel alone, ranks aligned:{red_alone} | alone: pass {kms[:,0].mean():.1f} foreign {kms[:,1].mean():.1f} "
        f"epilogue {kms[:,2].mean():.1f} us")
 if world > 1:
     allmsg = [None] * world
