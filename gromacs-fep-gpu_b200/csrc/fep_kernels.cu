@@ -344,12 +344,12 @@ __device__ __forceinline__ double block_sum_d(double v, double* s_buf)
  * `seq` or a later step.  All ranks must launch their steps in lockstep with the same `seq`; a peer that
  * never arrives within 4 s makes the kernel record the reason and trap (FEP_FAULT_PEER_TIMEOUT) instead
  * of hanging every GPU of the node.  Ends with a block-wide barrier. */
-/* light: the same barrier with ONE system-scope fence on either side instead of one per instruction -- the announcement
- * is the release store alone (the data it publishes was written by the preceding kernel: it is ordered before the store
- * by the kernel boundary, and a release is cumulative), the poll is a relaxed load, and one acquire fence follows the
- * load that saw the announcement.  A system-scope fence costs microseconds on an NVSwitch box (profiles/: the barrier
- * was 10 of the 13 us the reduction kernel takes with its data already local); the original form pays one before the
- * store, one inside it, and one per poll. */
+/* light (experiment, FEPB200_BARRIER=light; not the default): the same barrier with ONE system-scope fence on either
+ * side instead of one per instruction -- the announcement is the release store alone (the data it publishes was written
+ * by the preceding kernel: it is ordered before the store by the kernel boundary, and a release is cumulative), the poll
+ * is a relaxed load, and one acquire fence follows the load that saw the announcement.  The idea: the barrier is 10 of
+ * the 13 us the reduction kernel takes with its data already local, and system-scope fences are what it consists of.
+ * Measured on 2 B200 it is SLOWER than the form with a fence before the store and acquire loads (4 us per step). */
 template<typename FlagsOf>
 __device__ __forceinline__ void fep_flag_barrier(FlagsOf flags_of, int rank, int nranks, unsigned int seq, bool announce,
                                                  unsigned int* fault, bool light = false)
@@ -1186,13 +1186,13 @@ extern "C" int fep_launch_step(const KernelArgs* kap, int softcore, int elec_ewa
 /* ------------------------------------------------------------------------------------------- */
 /* multi-GPU: one-shot reduction over peer memory                                              */
 /* ------------------------------------------------------------------------------------------- */
-/* FEPB200_BARRIER=sc: the reduction kernels' cross-GPU barrier in its original form (a fence per instruction); default:
- * the light form (fep_flag_barrier) */
+/* FEPB200_BARRIER=light: the reduction kernels' cross-GPU barrier in its light form (fep_flag_barrier; experiment,
+ * measured SLOWER on 2 B200: 57.8 against 53.3 us per C5 step, profiles/r02_multi_gpu_push_and_barrier.txt) */
 static int fep_light_barrier()
 {
     static const int light = [] {
         const char* e = std::getenv("FEPB200_BARRIER");
-        return (e && std::strcmp(e, "sc") == 0) ? 0 : 1;
+        return (e && std::strcmp(e, "light") == 0) ? 1 : 0;
     }();
     return light;
 }
