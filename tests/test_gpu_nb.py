@@ -22,6 +22,8 @@ ALL = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL
 
 CASES = {
     "ewald": dict(name="C2", box=4.2, n_blobs=1),
+    "ewald_no_overlaps": dict(name="C2", box=4.2, n_blobs=1, n_adversarial=0),  # every sum and energy at its ordinary size
+    "rf_no_overlaps": dict(name="C4", box=4.2, n_blobs=1, n_energy_groups=1, n_adversarial=0),
     "rf": dict(name="C4", box=4.2, n_blobs=1, n_energy_groups=1),
     "ewald_split_entries": dict(name="C1", box=3.6, n_blobs=1, split=3),
     "ewald_larger": dict(name="C3", box=6.0, n_blobs=2),
@@ -42,11 +44,19 @@ def nb():
     c.close()
 
 
-def _check(got, want, what=""):
+def _check(got, want, what="", core_tol=3e-6):
     f, fw = np.asarray(got["f"], np.float64), want["f"]
     rms = np.sqrt(np.mean((f - fw) ** 2) / np.mean(fw**2))
     assert rms <= 2e-6, f"{what}: force rel-RMS {rms:.2e}"
     assert np.max(np.abs(f - fw)) <= 2e-5 * np.max(np.abs(fw)), what
+    # The synthetic systems carry adversarial placements (fepb200.synth: a water molecule moved next to a soft-cored atom),
+    # which can put two waters on top of each other; one such pair (1e12 kJ/mol/nm) dominates the sums above.  The atoms
+    # with ordinary forces are therefore checked on their own (measured 1.0e-6 ... 1.5e-6, with and without the
+    # placements: profiles/r02_nb_parity_report.txt)
+    mag = np.linalg.norm(fw, axis=1)
+    core = mag <= 50 * np.median(mag[mag > 0])
+    rms_core = np.sqrt(np.mean((f[core] - fw[core]) ** 2) / np.mean(fw[core] ** 2))
+    assert rms_core <= core_tol, f"{what}: force rel-RMS over the atoms with ordinary forces {rms_core:.2e}"
     return rms
 
 
@@ -238,7 +248,7 @@ def test_reference_cuda_kernel_on_the_same_list(nb):
     oracle and with us (its analytical Ewald is the reference's own rational fit, ours is another: 5e-6 rel-RMS)."""
     if not nb_oracle.have_fork_cuda():
         pytest.skip("oracle/_ref/libnbfork_cuda.so not built")
-    for case in ("ewald", "rf"):
+    for case in ("ewald", "rf", "ewald_no_overlaps", "rf_no_overlaps"):
         pr, cs = _system(**CASES[case])
         nb.setup(cs, pr.params)
         want = nb_oracle.run_port(cs, pr.params, table=None)
@@ -335,7 +345,9 @@ def test_list_read_from_the_caller_s_device_copy_with_pruned_masks(nb):
     nb.use_device_list(d_sci.data_ptr(), d_cj.data_ptr(), d_excl.data_ptr())
     nb.launch_device(d_xq.data_ptr(), cs.shiftvec, P.DO_FORCE | NB_Q_FROM_XQ, d_f.data_ptr())
     nb.wait()
-    _check(dict(f=d_f.cpu().numpy()), want, "pruned device list")
+    # a random half of the atom pairs of a system with close contacts: the forces no longer cancel and the steep close
+    # pairs (r of 0.05 nm from fp32 coordinates of 4 nm) set the deviation: 4.5e-6 measured, the budget of the path is 1e-5
+    _check(dict(f=d_f.cpu().numpy()), want, "pruned device list", core_tol=1e-5)
     # back to the library's own copy of the host list
     nb.use_device_list(0, 0, 0)
     d_f.zero_()
@@ -353,7 +365,8 @@ def test_lennard_jones_switch_flavours_of_the_reference_s_cuda_kernels(nb, modif
     compiled in place, and then compared with ours."""
     import copy
 
-    pr, cs = _system(**CASES["ewald"])
+    # without overlapping waters: with them one pair's 1e10 kJ/mol would hide what the switch does to the sums
+    pr, cs = _system(**CASES["ewald_no_overlaps"])
     base = P.make_params(coulombtype="pme", vdw_modifier=modifier, rvdw_switch=0.8)
     params = copy.copy(pr.params)
     for k in ("vdw_modifier", "rvdw_switch", "dispersion_shift_cpot", "repulsion_shift_cpot"):
@@ -361,8 +374,9 @@ def test_lennard_jones_switch_flavours_of_the_reference_s_cuda_kernels(nb, modif
     params = params.rounded()
     plain = nb_oracle.run_port(cs, params, table=None)  # what nbnxn_kernel_gpu_ref would give: the switch ignored
     want = nb_oracle.run_port(cs, params, table=None, cuda_modifiers=True)
-    assert np.max(np.abs(want["f"] - plain["f"])) > 1e-4 * np.max(np.abs(plain["f"]))
-    assert abs(want["vvdw"] - plain["vvdw"]) > 1e-6 * abs(plain["vvdw"])
+    mag = np.linalg.norm(plain["f"], axis=1)
+    assert np.max(np.abs(want["f"] - plain["f"])) > 1e-4 * np.median(mag[mag > 0])  # the switch is felt
+    assert abs(want["vvdw"] - plain["vvdw"]) > 1e-2 * abs(plain["vvdw"])
     if nb_oracle.have_fork_cuda():
         fork = nb_oracle.run_fork_cuda(cs, params, energy=True, repeats=1)
         rms = np.sqrt(np.mean((fork["f"] - want["f"]) ** 2) / np.mean(want["f"] ** 2))
