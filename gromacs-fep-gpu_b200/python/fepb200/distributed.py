@@ -1,5 +1,5 @@
 """Multi-GPU driver of the perturbed-pair path: one process per GPU, the FEP pair list split over
-the ranks, coordinates and parameters replicated.  Three ways to combine the ranks' results
+the ranks, coordinates and parameters replicated.  Ways to combine the ranks' results
 (SURVEY.md section 8e), selected by ShardedFep.reduction:
 
   "fused": no separate collective.  Every rank holds the layout of the full list and
@@ -8,10 +8,15 @@ the ranks, coordinates and parameters replicated.  Three ways to combine the ran
       rank reads over NVLink, from whichever rank produced them, the contributions of the atoms it
       owns (forces: reduce-scatter) and all scalar inputs (all-reduce).
       fepb200_set_peer_exchange().
-  "p2p" (default): the list is split by i-entry (shard.py), every rank computes the result block of its
+  "p2p": the list is split by i-entry (shard.py), every rank computes the result block of its
       shard (its epilogue visits only the atoms its shard touches) and ONE kernel of libfepb200 does the
       force REDUCE-SCATTER over NVLink peer memory -- each rank sums the atoms it owns over all ranks'
       blocks -- together with the all-reduce of shift forces and scalars (fepb200_reduce_scatter_peers).
+  "p2p-push" (default): the same split and the same result, the data travelling the other way: the epilogue stores
+      the force of an atom straight into a receive block on the rank that owns it, shift forces and scalars into
+      receive blocks on all ranks (fepb200_set_push_targets), and the same reduction kernel sums a rank's OWN
+      receive blocks behind its barrier -- local loads only.  46.9 against 48.5 us per C5 step on 2 B200, 39.3
+      against 44.0 us on 4.
   "p2p-allreduce": the same split, every rank sums everything (fepb200_reduce_peers; round-1 default).
   "nccl": same split, two ncclAllReduce calls on zero-copy views of the result block.
 See DESIGN.md section 5 for the measurements.
@@ -51,12 +56,12 @@ class ShardedFep:
     reduction = "fused": see the module docstring; step() returns the
     forces of the atoms this rank owns (zeros elsewhere: the sum over ranks is the full force array)
     and the full scalars on every rank.
-    reduction = "p2p" (default when available): every rank writes its result block into
+    reduction = "p2p": every rank writes its result block into
     symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations every rank of the
     node has mapped over NVLink), passes a device-side barrier, and libfepb200's own kernel sums, through
     the peer pointers and in rank order, the forces of the atoms this rank owns and all scalars
     (fepb200_reduce_scatter_peers); step() returns what "fused" returns.  "p2p-allreduce": every rank sums
-    everything (fepb200_reduce_peers).  "p2p-push": the same result as "p2p", but the epilogue stores its sums
+    everything (fepb200_reduce_peers).  "p2p-push" (default when available): the same result as "p2p", but the epilogue stores its sums
     straight into receive blocks on the ranks that need them (fepb200_set_push_targets) and the reduction kernel
     reads local memory only: one one-way NVLink trip per step.
     reduction = "nccl": two ncclAllReduce calls on zero-copy views of the result block.
@@ -73,7 +78,8 @@ class ShardedFep:
         self.reduction = "none"
         self._p2p_error = None  # why symmetric memory was not used, if it was asked for
         self._step = 0
-        want = (reduction or os.environ.get("FEPB200_REDUCTION", "p2p")) if world > 1 else "none"
+        # default: push (measured faster than the pull on 2 and 4 B200); the push targets are kernel arguments for at most 8 ranks
+        want = (reduction or os.environ.get("FEPB200_REDUCTION", "p2p-push" if world <= 8 else "p2p")) if world > 1 else "none"
         if want == "fused":
             try:
                 self.ctx.set_problem(problem)  # the full list on every rank
