@@ -225,6 +225,12 @@ def test_full_size_configs_match_oracle(ctx, name):
     out = _run(ctx, prob)
     ref = _oracle().run_best(prob, ALL, nthreads=max(1, min(16, os.cpu_count() or 1)))
     _check(out, ref, ALL, label=name)
+    # The adversarial placements can put a water next to a hard-cored perturbed atom (C2: one pair at 3e8 kJ/mol/nm), which
+    # then is the whole of an RMS over all atoms: the same budget over the atoms whose force is at most 100 x the 99th
+    # percentile (measured 2.3e-7 ... 1.0e-6, profiles/r02_parity_report_full_size.txt)
+    mag = np.linalg.norm(ref["f"], axis=1)
+    keep = (mag > 0) & (mag <= 100.0 * np.percentile(mag[mag > 0], 99))
+    assert _force_rms(out["f"][keep], ref["f"][keep]) <= FORCE_RTOL, name
     # the pair count the library reports is the list's, bit for bit
     lay = ctx.layout()
     assert (lay.nri, lay.nrj) == (prob.nblist.nri, prob.nblist.nrj)
