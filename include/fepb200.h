@@ -309,7 +309,9 @@ int    fepb200_reduce_scatter_peers(fepb200_ctx* ctx, int nranks, void* const* d
  * block of this context's own.  Follow each launch with fepb200_reduce_scatter_peers(ctx, nranks, LOCAL receive blocks
  * in rank order, flags, rank, seq): its barrier orders the pushes before the sums, and the sums read local memory only.
  * The set of words a rank writes is fixed by its list: the blocks must be zeroed again (on all ranks, behind a barrier)
- * after a new fepb200_set_list(), which also switches the push off.  nranks <= 1 or d_peer_blocks == NULL: off. */
+ * after a new fepb200_set_list(), which also switches the push off.  nranks <= 1 or d_peer_blocks == NULL: off.  At most 8
+ * ranks (the targets travel as kernel arguments).  Measured on C5: 46.9 against 48.5 us per step on 2 B200, 39.3 against
+ * 44.0 us on 4. */
 int    fepb200_set_push_targets(fepb200_ctx* ctx, int nranks, void* const* d_peer_blocks);
 
 /* ---- multi-GPU, fused: no separate collective, every rank sums its own atoms ------------------
