@@ -137,8 +137,10 @@ class ShardedFep:
         self._flags = [b + 2 * slot_bytes for b in base]
         if blocks_per_slot > 1:
             # my receive block on rank r, and the blocks the ranks write on me
-            self._push = [[b + k * slot_bytes + self.rank * self.block_bytes for b in base] for k in (0, 1)]
-            self._recv = [[base[self.rank] + k * slot_bytes + s * self.block_bytes for s in range(self.world)] for k in (0, 1)]
+            from .shard import push_block_addresses
+
+            self._push, self._recv, flags = push_block_addresses(base, self.rank, self.block_bytes)
+            assert flags == self._flags
         self.stream.synchronize()
 
     def launch(self, flags: int) -> None:

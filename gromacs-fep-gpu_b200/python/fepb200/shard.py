@@ -142,6 +142,27 @@ def peer_atom_ranges(atom_ptr, nranks: int) -> list[tuple[int, int]]:
     return [(bounds[r], bounds[r + 1]) for r in range(nranks)]
 
 
+def owned_atom_ranges(ntouched: int, nranks: int) -> list[tuple[int, int]]:
+    """The compact atoms every rank owns after the force reduce-scatter: equal ranges starting on multiples of four atoms
+    (so that a range of 3-word forces starts on a 16-byte boundary) -- the rule of fepb200_reduce_scatter_peers() and of
+    the push targets (fepb200_set_push_targets: the epilogue sends the force of atom a to rank a // per)."""
+    per = max(4, ((ntouched + nranks - 1) // nranks + 3) // 4 * 4)
+    return [(min(ntouched, per * r), min(ntouched, per * (r + 1))) for r in range(nranks)]
+
+
+def push_block_addresses(base: list[int], rank: int, block_bytes: int) -> tuple[list[list[int]], list[list[int]], list[int]]:
+    """Push reduction over symmetric memory: every rank's buffer (base[r] = its address as mapped HERE) holds two slots of
+    len(base) receive blocks -- block s of a slot is written by rank s only -- followed by the flag array.  Returns
+    (push, recv, flags): push[k][r] = MY block of slot k on rank r, recv[k][s] = the block rank s writes in my slot k,
+    flags[r] = rank r's flag array."""
+    world = len(base)
+    slot_bytes = world * block_bytes
+    push = [[b + k * slot_bytes + rank * block_bytes for b in base] for k in (0, 1)]
+    recv = [[base[rank] + k * slot_bytes + s * block_bytes for s in range(world)] for k in (0, 1)]
+    flags = [b + 2 * slot_bytes for b in base]
+    return push, recv, flags
+
+
 class ResultLayout:
     """Host-side mirror of `struct fepb200_layout`: where forces, shift forces, energy-group
     energies, dV/dlambda and foreign-lambda terms sit in the fp32 / fp64 result blocks."""

@@ -511,6 +511,7 @@ def test_push_reduction_with_shards_on_one_device(nranks):
     import torch
 
     from fepb200.lib import FepContext
+    from fepb200.shard import owned_atom_ranges
 
     prob = make_system(SMALL["C4"])
     with contextlib.ExitStack() as stack:
@@ -537,6 +538,8 @@ def test_push_reduction_with_shards_on_one_device(nranks):
             for r, c in enumerate(ranks):
                 c.reduce_scatter_peers([block(r, s) for s in range(nranks)], None, r, step + 1)
                 outs.append(c.download(ALL))
+                # the host mirror of the ownership rule (fepb200.shard, what tests/test_sharding_cpu.py plays on CPU)
+                assert tuple(c.peer_ranges()[2:]) == owned_atom_ranges(int(c.layout().ntouched), nranks)[r]
             f = sum(o["f"] for o in outs)
             assert np.max(sum((o["f"] != 0).astype(np.int32) for o in outs)) == 1  # every atom has one owner
             assert sum(1 for o in outs if np.any(o["f"])) >= 2

@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from fepb200 import params as P
-from fepb200.shard import ResultLayout, balanced_ranges, touched_atoms
+from fepb200.shard import ResultLayout, balanced_ranges, owned_atom_ranges, push_block_addresses, touched_atoms
 from fepb200.synth import make_system, random_problem, scaled_spec
 
 ALL = P.DO_FORCE | P.DO_SHIFTFORCE | P.DO_POTENTIAL | P.DO_FOREIGNLAMBDA
@@ -224,4 +224,104 @@ def test_fused_exchange_data_flow_gloo(world, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     result = str(tmp_path / "result.txt")
     mp.spawn(_fused_worker, args=(world, _free_port(), root, result), nprocs=world, join=True)
+    assert open(result).read() == "ok"
+
+
+def test_owned_atom_ranges_and_push_addresses():
+    """Host mirrors of the push reduction's rules: the owned ranges are a partition on 4-atom boundaries, the owner of an
+    atom is a // per, and the block rank s pushes into on rank r is the block rank r reads as 'written by s'."""
+    for nT, n in ((75818, 8), (75818, 2), (10, 4), (3, 8), (0, 2), (4097, 3)):
+        rg = owned_atom_ranges(nT, n)
+        assert rg[0][0] == 0 and rg[-1][1] == nT and all(a1 == b0 for (_, a1), (b0, _) in zip(rg, rg[1:]))
+        assert all(a0 % 4 == 0 or a0 == nT for a0, _ in rg)
+        per = max(4, ((nT + n - 1) // n + 3) // 4 * 4)
+        for a in range(0, nT, max(1, nT // 97)):
+            r = min(a // per, n - 1)
+            assert rg[r][0] <= a < rg[r][1]
+    world, bb = 4, 4096
+    # base[r] as mapped on rank q: every rank sees the same buffers at its own virtual addresses
+    mapped = [[(q + 1) * 10**9 + r * 10**6 for r in range(world)] for q in range(world)]
+    plans = [push_block_addresses(mapped[q], q, bb) for q in range(world)]
+    for s_ in range(world):          # the writer
+        for r in range(world):       # the owner of the memory
+            for k in (0, 1):
+                off_w = plans[s_][0][k][r] - mapped[s_][r]   # where s writes inside r's buffer
+                off_r = plans[r][1][k][s_] - mapped[r][r]    # where r reads 'the block of s' inside its own buffer
+                assert off_w == off_r
+                assert 0 <= off_w and off_w + bb <= 2 * world * bb
+    # no two writers share a block, the two slots do not overlap, the flags follow the slots
+    offs = sorted(plans[s_][0][k][0] - mapped[s_][0] for s_ in range(world) for k in (0, 1))
+    assert offs == [i * bb for i in range(2 * world)]
+    assert plans[0][2][1] - mapped[0][1] == 2 * world * bb
+
+
+def _push_worker(rank, world, port, root, result_file):
+    for p in (os.path.join(root, "gromacs-fep-gpu_b200", "python"), root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import copy
+
+    from oracle import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob = make_system(scaled_spec("C4", 4.2, 2, 25, n_foreign=3))
+    touched = touched_atoms(prob.nblist)
+    nT = len(touched)
+    lay = ResultLayout(nT, prob.nenergrp_pairs, prob.n_foreign)
+    e0, e1 = balanced_ranges(prob.nblist.jindex, world)[rank]
+    shard = copy.copy(prob)
+    shard.nblist = prob.nblist.slice_entries(e0, e1)
+    f32, f64 = lay.pack(oracle.run_port(shard, ALL), touched)
+    ranges = owned_atom_ranges(nT, world)
+    # what the epilogue does: to rank r the forces of r's atoms (nothing else of the force part), shift forces and
+    # scalars to everybody; the receive blocks start zeroed
+    send = []
+    for r in range(world):
+        b32 = np.zeros_like(f32)
+        a0, a1 = ranges[r]
+        b32[3 * a0 : 3 * a1] = f32[3 * a0 : 3 * a1]
+        b32[3 * nT :] = f32[3 * nT :]
+        send.append((torch.from_numpy(b32), torch.from_numpy(f64.copy())))
+    recv32 = [torch.zeros(f32.size, dtype=torch.float32) for _ in range(world)]
+    recv64 = [torch.zeros(f64.size, dtype=torch.float64) for _ in range(world)]
+    for s_ in range(world):  # rank s_ "pushes": every rank receives its block from s_
+        dist.scatter(recv32[s_], [t[0] for t in send] if rank == s_ else None, src=s_)
+        dist.scatter(recv64[s_], [t[1] for t in send] if rank == s_ else None, src=s_)
+    # the reduction kernel on the rank's own receive blocks: sums in rank order
+    sum32, sum64 = np.zeros_like(f32), np.zeros_like(f64)
+    for s_ in range(world):
+        sum32 += recv32[s_].numpy()
+        sum64 += recv64[s_].numpy()
+    got = lay.unpack(sum32, sum64, touched, prob.natoms)
+    want = oracle.run_port(prob, ALL)
+    a0, a1 = ranges[rank]
+    owned = np.zeros(prob.natoms, bool)
+    owned[touched[a0:a1]] = True
+    ok = not np.any(got["f"][~owned])
+    scale = max(np.max(np.abs(want["f"])), 1e-12)
+    ok = ok and np.max(np.abs(got["f"][owned] - want["f"][owned])) <= 2e-6 * scale
+    for k in ("fshift", "Vc", "Vv", "dvdl", "foreign_energy", "foreign_dvdl"):
+        sc = max(np.max(np.abs(want[k])), 1e-12)
+        ok = ok and np.max(np.abs(got[k] - want[k])) <= (2e-6 if k == "fshift" else 1e-12) * sc
+    # the ranks' owned forces add up to the whole array
+    t = torch.from_numpy(got["f"].astype(np.float64))
+    dist.all_reduce(t)
+    ok = ok and np.max(np.abs(t.numpy() - want["f"])) <= 2e-6 * scale
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        with open(result_file, "w") as fh:
+            fh.write("ok" if int(flag.item()) == 1 else "mismatch")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_push_reduction_data_flow_gloo(world, tmp_path):
+    """The data flow of the push reduction (fepb200_set_push_targets + fepb200_reduce_scatter_peers on the receive blocks)
+    played on CPU: shards evaluated by the oracle, blocks moved with gloo, owner rule and block layout from fepb200.shard."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    result = str(tmp_path / "result.txt")
+    mp.spawn(_push_worker, args=(world, _free_port(), root, result), nprocs=world, join=True)
     assert open(result).read() == "ok"
